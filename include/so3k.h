@@ -1,0 +1,181 @@
+/* so3k.h -- C ABI of the B200-native SO3krates energy+force engine (libso3k.so).
+ *
+ * The reference (thorben-frank/mlff 0.3.0) is pure Python on JAX/flax: it has NO native
+ * operator / plugin / FFI interface.  The boundary below is therefore placed at the two Python
+ * seams through which the hot path is reached today; every entry point
+ * cites the reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   so3k_energy_forces          <- obs_fn = jax.vmap(get_obs_and_force_fn(net), (None, 0))
+ *                                  mlff/nn/stacknet/observable_function.py:127-149 (+ :41-63 jacrev),
+ *                                  StackNet.__call__ mlff/nn/stacknet/stacknet.py:40-87
+ *   so3k_potential_displacements<- MLFFPotential.potential_fn  mlff/mdx/potential/mlff_potential.py:95-109
+ *                                  + the caller's jax.value_and_grad  mlff/mdx/calculator.py:42-49,
+ *                                  mlff/md/calculator.py:101-109
+ *   so3k_featurise              <- GeometryEmbed.__call__  mlff/nn/embed/embed.py:66-169
+ *                                  (PhysNetBasis radial.py:154-166, cosine_cutoff_fn cutoff radial.py:39-51,
+ *                                   fn_Y1..fn_Y4 spherical.py:6-38, add_cell_offsets pbc.py:8-18)
+ *   so3k_neighbor_list          <- pbc_neighbor_list / get_pbc_neighbors  mlff/indexing/indices.py:194-275, 111-191
+ *                                  (ase.neighborlist.primitive_neighbor_list 'ijS'), and get_indices :15-84
+ *   so3k_load_params            <- flax variable dict {'params': ...} (valid_params, mlff/io/checkpoint.py:12-16)
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures: device buffers are raw pointers, the CUDA
+ *     stream is passed as `void*` (a cudaStream_t; NULL = legacy default stream).
+ *   - every function only ENQUEUES work on the caller's stream and never synchronises; the
+ *     caller owns all buffers including the workspace; the handle owns only its repacked
+ *     copy of the weights.  One handle may be used from several host threads / streams as long
+ *     as each concurrent call uses its own workspace.
+ *   - return value: SO3K_OK or an error code; nothing throws across the ABI.  Conditions that
+ *     are only known on the device (neighbour-list capacity overflow, an edge list that is not
+ *     symmetric) are reported through an `int32_t* dev_status` word in device memory, exactly
+ *     like PrimitiveNeighbors.overflow (indices.py:264-272): bit flags SO3K_STATUS_*.
+ *   - index arrays are int32; padding sentinels follow the reference: idx == -1 (training,
+ *     stacknet.py:131) and idx >= n (glp, mdx/calculator.py:133) both mean "no edge";
+ *     z == 0 means "padding atom" (stacknet.py:130).
+ *   - all model arithmetic is float32 (the reference default); energies of a structure are
+ *     accumulated in float64 before the final cast.
+ */
+#ifndef SO3K_H_
+#define SO3K_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO3K_MAX_DEGREES 8
+#define SO3K_MAX_M 32
+
+typedef struct so3k_handle so3k_handle;
+
+/* Hyper-parameters: So3krates(F, n_layer, degrees, n_heads) + GeometryEmbed(n_rbf, r_cut)
+ * (mlff/nn/representation/so3krates.py:13-67).  Fixed (default) choices of the reference that
+ * this engine implements: PhysNet radial basis, cosine cutoff, sphc=True with
+ * sphc_normalization=None (chi0 = 0), radial_spherical filters, filter widths [F,F] / [F/4,F]. */
+typedef struct so3k_config {
+  int32_t F;               /* feature dimension (132)                        */
+  int32_t n_rbf;           /* K, radial basis functions (32)                 */
+  int32_t n_layers;        /* So3kratesLayer count (CLI default 3)           */
+  int32_t n_heads;         /* feature-block heads H (4); F % H == 0          */
+  int32_t n_degrees;       /* len(degrees) = nl; F % nl == 0                 */
+  int32_t degrees[SO3K_MAX_DEGREES]; /* e.g. {1,2,3}; repeats allowed, l<=4  */
+  float r_cut;             /* 5.0                                            */
+  int32_t num_embeddings;  /* 100                                            */
+  int32_t flags;           /* SO3K_FLAG_*                                    */
+} so3k_config;
+
+enum {
+  SO3K_FLAG_NONE = 0,
+  /* filter-GEMM arithmetic: default = fp32 FMA on the CUDA cores (bit-faithful to fp32);
+   * SO3K_FLAG_TENSOR = tcgen05 tensor cores with split-operand (3-pass) error compensation. */
+  SO3K_FLAG_TENSOR = 1
+};
+
+enum {
+  SO3K_OK = 0,
+  SO3K_ERR_CONFIG = 1,     /* unsupported hyper-parameters                     */
+  SO3K_ERR_ARG = 2,        /* NULL / negative / inconsistent argument          */
+  SO3K_ERR_WORKSPACE = 3,  /* workspace too small                              */
+  SO3K_ERR_CUDA = 4,       /* a CUDA runtime call failed                       */
+  SO3K_ERR_NOPARAMS = 5    /* so3k_load_params has not been called             */
+};
+
+/* bits of the device status word */
+enum {
+  SO3K_STATUS_OVERFLOW = 1,    /* neighbour list did not fit `capacity`          */
+  SO3K_STATUS_ASYMMETRIC = 2,  /* edge (i,j) without its reverse (j,i)           */
+  SO3K_STATUS_BAD_Z = 4        /* atomic number outside [0, num_embeddings)      */
+};
+
+int so3k_create(const so3k_config* cfg, so3k_handle** out);
+int so3k_destroy(so3k_handle* h);
+const char* so3k_version(void);
+
+/* ---- parameters --------------------------------------------------------------------------
+ * One flat float32 blob in this fixed order (flax `Dense` convention y = x @ kernel + bias,
+ * kernel stored (in, out) row-major; leading vmap axes kept):
+ *   embed/embedding                         (num_embeddings, F)
+ *   for t in 0..n_layers-1:
+ *     for blk in (fb, gb):
+ *       layers_t/blk/rad/layers_0/{kernel (K,F), bias (F)}
+ *       layers_t/blk/rad/layers_1/{kernel (F,F), bias (F)}
+ *       layers_t/blk/sph/layers_0/{kernel (nl,F/4), bias (F/4)}
+ *       layers_t/blk/sph/layers_1/{kernel (F/4,F), bias (F)}
+ *       layers_t/blk/q/kernel (heads, d, d) ; layers_t/blk/k/kernel (heads, d, d)
+ *       [fb only] layers_t/fb/v/kernel (H, F/H, F/H)        (fb: heads=H ; gb: heads=nl)
+ *     layers_t/int/layers_0/{kernel (F+nl,F+nl), bias (F+nl)}
+ *   energy/layers_0/{kernel (F,F), bias (F)} ; energy/layers_1/{kernel (F,1), bias (1)}
+ *   energy/per_atom_scale (num_embeddings) ; energy/per_atom_shift (num_embeddings)
+ * so3k_param_lookup maps such a name to (offset, count) in the blob. */
+size_t so3k_param_count(const so3k_handle* h);
+int so3k_param_lookup(const so3k_handle* h, const char* name, size_t* offset, size_t* count);
+int so3k_load_params(so3k_handle* h, const float* blob_dev, size_t n_floats, void* stream);
+
+/* ---- workspace -------------------------------------------------------------------------- */
+/* bytes needed by so3k_energy_forces / so3k_potential_displacements for a flattened problem of
+ * n_atoms_total atoms (B*n) and n_edge_slots_total edge slots (B*P, padding included). */
+size_t so3k_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total);
+
+/* ---- energy + forces, training / evaluation seam ------------------------------------------
+ * Batched, padded inputs exactly as `vmap(obs_fn)` receives them:
+ *   R (B,n,3) f32, z (B,n) i32, idx_i / idx_j (B,P) i32 (indices local to the structure),
+ *   cell (B,3,3) f32 row-wise lattice vectors or NULL, cell_offset (B,P,3) i32 or NULL.
+ * Outputs: E (B) f32 [per_structure energy, observable.py:91], F (B,n,3) f32 = -dE/dR,
+ *   e_atom (B,n) f32 or NULL [per_atom convention, observable.py:88-89].
+ * dev_status (device int32, may be NULL) receives SO3K_STATUS_* bits (it is OR-ed, clear it first). */
+int so3k_energy_forces(so3k_handle* h, int32_t B, int32_t n, int32_t P,
+                       const float* R, const int32_t* z, const int32_t* idx_i, const int32_t* idx_j,
+                       const float* cell, const int32_t* cell_offset,
+                       float* E, float* F, float* e_atom,
+                       void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
+
+/* ---- MD seam ------------------------------------------------------------------------------
+ * Graph(edges, nodes, centers, others, mask) of mlff/utils/structures.py:5 in the
+ * 'displacements' convention: edges (P,3) f32 = R_j - R_i after MIC, nodes z (N) i32,
+ * centers / others (P) i32 with sentinel N (or -1), mask (P) u8 or NULL.
+ * Outputs: e_atom (N) f32 = per-atom energy * energy_scale (mlff_potential.py:80-109);
+ *   dE_dedges (P,3) f32 or NULL = d(sum e_atom)/d edges (what the caller's value_and_grad chains
+ *   through R_j - R_i); forces (N,3) f32 or NULL = -dE/dR obtained by that chain
+ *   (mdx/calculator.py:46-49). */
+int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
+                                 const float* edges, const int32_t* z,
+                                 const int32_t* centers, const int32_t* others, const uint8_t* mask,
+                                 float energy_scale,
+                                 float* e_atom, float* dE_dedges, float* forces,
+                                 void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
+
+/* ---- edge featurisation (standalone; the fused model path recomputes these on chip) ---------
+ * Inputs as GeometryEmbed: either positions R (n,3) [+ cell (3,3) row-wise + cell_offset (P,3)]
+ * or displacements (P,3).  Any output pointer may be NULL.  rbf (P,K), phi (P), d (P),
+ * unit (P,3), sph (P,M); padded edges (idx_i == -1 or >= n) give exact zeros. */
+int so3k_featurise(const so3k_handle* h, int32_t n, int32_t P,
+                   const float* R, const int32_t* idx_i, const int32_t* idx_j,
+                   const float* cell, const int32_t* cell_offset, const float* displacements,
+                   float* rbf, float* phi, float* d, float* unit, float* sph, void* stream);
+
+/* ---- neighbour list ------------------------------------------------------------------------
+ * Cell-list build on the device.  positions (N,3) f64 and z (N) i32 (may be NULL) are DEVICE
+ * buffers; cell (3,3) f64 row-wise (ASE convention; may be NULL / zero along non-periodic axes)
+ * and pbc[3] are small HOST arrays (they size the bin grid, like scalar arguments); cutoff f64.
+ * mode SO3K_NL_ASE  : all images, |R_j - R_i + S@cell| <  cutoff, (i != j or S != 0)   [indices.py:216-224]
+ * mode SO3K_NL_DENSE: non-periodic, 0 < d <= cutoff, z_i * z_j != 0 (z may be NULL)      [indices.py:56-60]
+ * Output (device): idx_i, idx_j (capacity) i32 padded with -1, shifts (capacity,3) i32 padded
+ * with 0, sorted by i then (j, S); *count (device int64) = number of edges found (may exceed capacity, in
+ * which case SO3K_STATUS_OVERFLOW is set and only the first `capacity` edges are stored). */
+enum { SO3K_NL_ASE = 0, SO3K_NL_DENSE = 1 };
+size_t so3k_neighbor_list_workspace_bytes(int64_t N, int64_t capacity);
+int so3k_neighbor_list(int32_t mode, int64_t N, const double* positions, const int32_t* z,
+                       const double* cell, const uint8_t* pbc, double cutoff, int64_t capacity,
+                       int32_t* idx_i, int32_t* idx_j, int32_t* shifts, int64_t* count,
+                       void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
+
+/* ---- instrumentation ------------------------------------------------------------------------
+ * Number of kernels this library has launched since process start (bench.py's gpu_launches). */
+uint64_t so3k_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SO3K_H_ */

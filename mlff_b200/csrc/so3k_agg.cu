@@ -1,0 +1,262 @@
+// Receiver-indexed aggregations over the receiver-sorted CSR -- no atomics.
+// A warp owns one receiver row.  It walks the row in chunks of 32 edges: the chunk's senders and attention
+// coefficients are staged in shared memory (coalesced lane-per-edge loads), then the warp loops over the staged
+// edges with lane == feature, gathering the F-wide sender rows with full 128-byte requests.  Quantities that are
+// narrow per edge (the M spherical-harmonic coordinates, 3-vectors) are accumulated lane-per-edge and combined
+// with warp-shuffle reductions at the end of the row.
+//   AttentionAggregation   mlff/nn/layer/so3krates_layer.py:607-608   x_local = segment_sum(alpha * v[idx_j], idx_i)
+//   SphConvAttention       mlff/nn/layer/so3krates_layer.py:563-564   chi_local = segment_sum(repeat(alpha') * Y, idx_i)
+//   skip connections       mlff/nn/layer/so3krates_layer.py:146-147
+// and the transposes needed by the analytic force backward.  Sender-indexed reductions are
+// turned into receiver-indexed ones through the reverse-edge permutation (the edge list is symmetric).
+// Algorithmic bytes (compulsory traffic, fp32): feature aggregation (4H+4)*P + (8F+4)*N, SPHC aggregation
+// (4nl+16+4)*P + 8M*N with Y recomputed from the 16-byte (u,d) record instead of read (SURVEY 8(d) counts 4M/edge).
+#include "so3k_internal.h"
+
+namespace {
+
+constexpr int WPB = 8;          // warps (rows) per block
+constexpr int TMAX = 8;         // F <= 32*TMAX
+constexpr int AMAX = 16;        // H + nl <= AMAX (stride in the alpha arrays is a multiple of 4)
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x1 = x + sum_e alpha_fb[e][h(f)] v[col e][f] ;  chi1 = chi + sum_e alpha_gb[e][l(m)] Y_m(u_e)
+__global__ void __launch_bounds__(WPB * 32)
+k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
+            const float4* __restrict__ geom, const float* __restrict__ x, const float* __restrict__ chi,
+            const float* __restrict__ proj, const float* __restrict__ alpha, float* __restrict__ x1,
+            float* __restrict__ chi1) {
+  __shared__ float s_a[WPB][32 * AMAX];
+  __shared__ int s_j[WPB][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const int F = D.F, M = D.M, H = D.H;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  float accx[TMAX];
+  int hsel[TMAX];
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    accx[t] = 0.f;
+    int f = lane + 32 * t;
+    hsel[t] = (f < F) ? f / D.dh : 0;
+  }
+  float cacc[SO3K_MAXM];
+  for (int m = 0; m < M; ++m) cacc[m] = 0.f;
+  const size_t F5 = 5 * (size_t)F;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const int cnt = (end - e0) < 32 ? (end - e0) : 32;
+    int j = 0;
+    if (e < end) {
+      j = col[e];
+      for (int a = 0; a < Ast; ++a) s_a[w][lane * Ast + a] = alpha[(size_t)e * Ast + a];
+      // SPHC part, lane-per-edge
+      float4 g = geom[e];
+      float y[SO3K_MAXM];
+      so3k_sph_all(D, g.x, g.y, g.z, y);
+      for (int m = 0; m < M; ++m) cacc[m] = fmaf(s_a[w][lane * Ast + H + D.m_seg[m]], y[m], cacc[m]);
+    }
+    s_j[w][lane] = j;
+    __syncwarp();
+    for (int q = 0; q < cnt; ++q) {
+      const float* vj = proj + (size_t)s_j[w][q] * F5 + 4 * (size_t)F;
+      const float* aq = &s_a[w][q * Ast];
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) {
+        int f = lane + 32 * t;
+        if (f < F) accx[t] = fmaf(aq[hsel[t]], vj[f], accx[t]);
+      }
+    }
+    __syncwarp();
+  }
+  // full-warp reductions of the lane-per-edge accumulators (every lane of the warp takes part)
+  for (int m = 0; m < M; ++m) {
+    float s = warp_sum(cacc[m]);
+    if (rowok && lane == 0) chi1[(size_t)i * M + m] = chi[(size_t)i * M + m] + s;
+  }
+  if (rowok) {
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      int f = lane + 32 * t;
+      if (f < F) x1[(size_t)i * F + f] = x[(size_t)i * F + f] + accx[t];
+    }
+  }
+}
+
+// alphabar_fb[e][h] = sum_{f in h} xbar1[i][f] v[j][f] ; alphabar_gb[e][l] = sum_{m in l} chibar1[i][m] Y_m(u_e)
+// gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
+__global__ void __launch_bounds__(WPB * 32)
+k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
+            const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
+            const float* __restrict__ alpha, const float* __restrict__ xbar1, const float* __restrict__ chibar1,
+            float* __restrict__ alphabar, float* __restrict__ gproj) {
+  __shared__ float s_a[WPB][32 * AMAX];     // alpha_fb of the reverse edges
+  __shared__ float s_o[WPB][32 * AMAX];     // alphabar staging (coalesced store)
+  __shared__ int s_j[WPB][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const int F = D.F, M = D.M, H = D.H, nl = D.nl;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  const size_t F5 = 5 * (size_t)F;
+  float xb[TMAX], accv[TMAX];
+  int hsel[TMAX];
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    int f = lane + 32 * t;
+    xb[t] = (rowok && f < F) ? xbar1[(size_t)i * F + f] : 0.f;
+    accv[t] = 0.f;
+    hsel[t] = (f < F) ? f / D.dh : -1;
+  }
+  float cb[SO3K_MAXM];
+  for (int m = 0; m < M; ++m) cb[m] = rowok ? chibar1[(size_t)i * M + m] : 0.f;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const int cnt = (end - e0) < 32 ? (end - e0) : 32;
+    int j = 0;
+    if (e < end) {
+      j = col[e];
+      int re = rev[e];
+      for (int h = 0; h < H; ++h) s_a[w][lane * Ast + h] = alpha[(size_t)re * Ast + h];
+      float4 g = geom[e];
+      float y[SO3K_MAXM];
+      so3k_sph_all(D, g.x, g.y, g.z, y);
+      for (int l = 0; l < nl; ++l) {
+        float s = 0.f;
+        for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s = fmaf(cb[m], y[m], s);
+        s_o[w][lane * Ast + H + l] = s;
+      }
+      for (int a = H + nl; a < Ast; ++a) s_o[w][lane * Ast + a] = 0.f;
+    }
+    s_j[w][lane] = j;
+    __syncwarp();
+    for (int q = 0; q < cnt; ++q) {
+      const int jq = s_j[w][q];
+      const float* vj = proj + (size_t)jq * F5 + 4 * (size_t)F;
+      const float* xj = xbar1 + (size_t)jq * F;
+      const float* aq = &s_a[w][q * Ast];
+      float ph[8];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) ph[h] = 0.f;
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t) {
+        int f = lane + 32 * t;
+        if (f < F) {
+          float p = xb[t] * vj[f];
+#pragma unroll
+          for (int h = 0; h < 8; ++h) ph[h] += (hsel[t] == h) ? p : 0.f;
+          accv[t] = fmaf(aq[hsel[t]], xj[f], accv[t]);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h < H) {                      // H is block-uniform: every lane executes the same shuffles
+          float s = warp_sum(ph[h]);
+          if (lane == 0) s_o[w][q * Ast + h] = s;
+        }
+      }
+    }
+    __syncwarp();
+    for (int t = lane; t < cnt * Ast; t += 32) alphabar[(size_t)e0 * Ast + t] = s_o[w][t];
+    __syncwarp();
+  }
+  if (rowok) {
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      int f = lane + 32 * t;
+      if (f < F) gproj[(size_t)i * F5 + 4 * (size_t)F + f] = accv[t];
+    }
+  }
+}
+
+// chibar[i][m] = chibar1[i][m] - 2 cg[m] sum_{e in row i} c_em (gbar[e][l(m)] + gbar[rev e][l(m)]),  c_e = chi[j]-chi[i]
+__global__ void __launch_bounds__(WPB * 32)
+k_chi_bwd(So3kDims D, int N, int Gst, const int* __restrict__ rowptr, const int* __restrict__ col,
+          const int* __restrict__ rev, const float* __restrict__ chi, const float* __restrict__ gbar,
+          const float* __restrict__ chibar1, float* __restrict__ chibar) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const int M = D.M;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  float acc[SO3K_MAXM], ci[SO3K_MAXM];
+  for (int m = 0; m < M; ++m) {
+    acc[m] = 0.f;
+    ci[m] = rowok ? chi[(size_t)i * M + m] : 0.f;
+  }
+  for (int e = beg + lane; e < end; e += 32) {
+    int j = col[e], re = rev[e];
+    float gs[SO3K_MAXDEG];
+    for (int l = 0; l < D.nl; ++l) gs[l] = gbar[(size_t)e * Gst + l] + gbar[(size_t)re * Gst + l];
+    for (int m = 0; m < M; ++m) {
+      float c = chi[(size_t)j * M + m] - ci[m];
+      acc[m] = fmaf(c, gs[D.m_seg[m]], acc[m]);
+    }
+  }
+  for (int m = 0; m < M; ++m) {
+    float s = warp_sum(acc[m]);
+    if (rowok && lane == 0) chibar[(size_t)i * M + m] = chibar1[(size_t)i * M + m] - 2.0f * D.m_cg[m] * s;
+  }
+}
+
+// F_i = sum_{e in row i} (rbar[e] - rbar[rev e]) ; dE_dedges[src e] = rbar[e]
+__global__ void __launch_bounds__(WPB * 32)
+k_forces(int N, const int* __restrict__ rowptr, const int* __restrict__ rev, const int* __restrict__ src,
+         const float* __restrict__ rbar, float* __restrict__ forces, float* __restrict__ dE_dedges) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  for (int e = beg + lane; e < end; e += 32) {
+    int re = rev[e];
+    float ax = rbar[3 * (size_t)e + 0], ay = rbar[3 * (size_t)e + 1], az = rbar[3 * (size_t)e + 2];
+    fx += ax - rbar[3 * (size_t)re + 0];
+    fy += ay - rbar[3 * (size_t)re + 1];
+    fz += az - rbar[3 * (size_t)re + 2];
+    if (dE_dedges) {
+      size_t s = (size_t)src[e];
+      dE_dedges[3 * s + 0] = ax; dE_dedges[3 * s + 1] = ay; dE_dedges[3 * s + 2] = az;
+    }
+  }
+  fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+  if (rowok && lane == 0 && forces) {
+    forces[3 * (size_t)i + 0] = fx; forces[3 * (size_t)i + 1] = fy; forces[3 * (size_t)i + 2] = fz;
+  }
+}
+
+}  // namespace
+
+void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
+                           const float* alpha, float* x1, float* chi1, cudaStream_t st) {
+  int Ast = (D.H + D.nl + 3) & ~3;
+  SO3K_LAUNCH(k_aggregate, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col, g.geom, x, chi,
+              proj, alpha, x1, chi1);
+}
+
+void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
+                           const float* xbar1, const float* chibar1, float* alphabar, float* gproj, cudaStream_t st) {
+  int Ast = (D.H + D.nl + 3) & ~3;
+  SO3K_LAUNCH(k_alpha_bwd, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col, g.rev, g.geom,
+              proj, alpha, xbar1, chibar1, alphabar, gproj);
+}
+
+void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,
+                         const float* chibar1, float* chibar, cudaStream_t st) {
+  int Gst = (D.nl + 3) & ~3;
+  SO3K_LAUNCH(k_chi_bwd, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Gst, g.rowptr, g.col, g.rev, chi, gbar,
+              chibar1, chibar);
+}
+
+void so3k_launch_forces(const So3kDims& D, const Graph& g, int P_slots, const float* rbar, float* forces,
+                        float* dE_dedges, cudaStream_t st) {
+  (void)D;
+  if (dE_dedges) cudaMemsetAsync(dE_dedges, 0, sizeof(float) * 3 * (size_t)P_slots, st);
+  SO3K_LAUNCH(k_forces, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, g.N, g.rowptr, g.rev, g.src, rbar, forces,
+              dE_dedges);
+}

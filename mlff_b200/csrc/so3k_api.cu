@@ -1,0 +1,347 @@
+// C ABI of libso3k (include/so3k.h): handle, parameter blob, workspace carving and the orchestration of one
+// energy+force evaluation:  CSR build -> embed -> L x [q/k/v projections, edge filter+attention, aggregation,
+// interaction] -> read-out -> reverse sweep (analytic data-gradient) -> forces.
+//   StackNet.__call__            mlff/nn/stacknet/stacknet.py:40-87
+//   So3kratesLayer.__call__      mlff/nn/layer/so3krates_layer.py:57-178
+//   get_obs_and_force_fn         mlff/nn/stacknet/observable_function.py:127-149
+//   MLFFPotential.potential_fn   mlff/mdx/potential/mlff_potential.py:95-109
+#include "so3k_internal.h"
+#include "so3k_edge.h"
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+static std::atomic<uint64_t> g_launches{0};
+void so3k_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+
+struct HandleImpl : so3k_handle {
+  float* repack = nullptr;
+  std::vector<EdgeBlockW> wf, wg;    // per layer
+};
+
+bool make_dims(const so3k_config& c, So3kDims* D) {
+  if (c.F <= 0 || c.n_rbf <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_degrees <= 0) return false;
+  if (c.n_degrees > SO3K_MAXDEG || c.n_heads > 8) return false;
+  if (c.F % c.n_heads != 0 || c.F % c.n_degrees != 0) return false;
+  if (c.F > 256 || c.F / 4 < 1) return false;
+  if (!(c.r_cut > 0.f)) return false;
+  memset(D, 0, sizeof(*D));
+  D->F = c.F; D->K = c.n_rbf; D->L = c.n_layers; D->H = c.n_heads; D->nl = c.n_degrees;
+  D->Fs = c.F / 4;                       // int(F/4), mlff/nn/representation/so3krates.py:64-66
+  D->dh = c.F / c.n_heads;
+  D->dg = c.F / c.n_degrees;
+  D->nemb = c.num_embeddings > 0 ? c.num_embeddings : 100;
+  D->r_cut = c.r_cut;
+  int M = 0;
+  for (int s = 0; s < c.n_degrees; ++s) {
+    int l = c.degrees[s];
+    if (l < 0 || l > 4) return false;
+    D->deg[s] = l;
+    D->seg_off[s] = M;
+    for (int m = 0; m < 2 * l + 1; ++m) {
+      if (M >= SO3K_MAXM) return false;
+      D->m_seg[M++] = s;
+    }
+  }
+  D->seg_off[c.n_degrees] = M;
+  D->M = M;
+  // l0-contraction coefficients in the reference's cg_rep order (sorted unique degrees, tiled by multiplicity):
+  // mlff/sph_ops/contract.py:168-172
+  int idx = 0;
+  for (int l = 0; l <= 4; ++l) {
+    int count = 0;
+    for (int s = 0; s < c.n_degrees; ++s) count += (c.degrees[s] == l);
+    for (int r = 0; r < count; ++r)
+      for (int m = 0; m < 2 * l + 1; ++m) D->m_cg[idx++] = (float)(1.0 / std::sqrt(2.0 * l + 1.0));
+  }
+  // PhysNet basis constants in float32, mlff/basis_function/radial.py:163-165
+  float rc = c.r_cut;
+  float e_rc = expf(-rc);
+  D->mu0 = e_rc;
+  D->dmu = c.n_rbf > 1 ? (1.0f - e_rc) / (float)(c.n_rbf - 1) : 0.f;
+  float t = (2.0f / (float)c.n_rbf) * (1.0f - e_rc);
+  D->gamma = 1.0f / (t * t);
+  if (D->H + D->nl > 16) return false;
+  return true;
+}
+
+void make_layout(const So3kDims& D, ModelLayout* ml) {
+  size_t off = 0;
+  auto add = [&](const std::string& name, size_t count) {
+    size_t o = off;
+    ml->names.push_back({name, {o, count}});
+    off += count;
+    return o;
+  };
+  const size_t F = D.F, K = D.K, nl = D.nl, Fs = D.Fs, H = D.H, dh = D.dh, dg = D.dg;
+  ml->embed = add("embed/embedding", (size_t)D.nemb * F);
+  ml->layers.resize(D.L);
+  for (int t = 0; t < D.L; ++t) {
+    std::string lt = "layers_" + std::to_string(t) + "/";
+    for (int b = 0; b < 2; ++b) {
+      BlockParams& bp = b ? ml->layers[t].gb : ml->layers[t].fb;
+      std::string pre = lt + (b ? "gb/" : "fb/");
+      bp.rad_W1 = add(pre + "rad/layers_0/kernel", K * F);
+      bp.rad_b1 = add(pre + "rad/layers_0/bias", F);
+      bp.rad_W2 = add(pre + "rad/layers_1/kernel", F * F);
+      bp.rad_b2 = add(pre + "rad/layers_1/bias", F);
+      bp.sph_W1 = add(pre + "sph/layers_0/kernel", nl * Fs);
+      bp.sph_b1 = add(pre + "sph/layers_0/bias", Fs);
+      bp.sph_W2 = add(pre + "sph/layers_1/kernel", Fs * F);
+      bp.sph_b2 = add(pre + "sph/layers_1/bias", F);
+      size_t heads = b ? nl : H, d = b ? dg : dh;
+      bp.Wq = add(pre + "q/kernel", heads * d * d);
+      bp.Wk = add(pre + "k/kernel", heads * d * d);
+      bp.Wv = b ? 0 : add(pre + "v/kernel", heads * d * d);
+    }
+    ml->layers[t].int_W = add(lt + "int/layers_0/kernel", (F + nl) * (F + nl));
+    ml->layers[t].int_b = add(lt + "int/layers_0/bias", F + nl);
+  }
+  ml->out_W1 = add("energy/layers_0/kernel", F * F);
+  ml->out_b1 = add("energy/layers_0/bias", F);
+  ml->out_W2 = add("energy/layers_1/kernel", F);
+  ml->out_b2 = add("energy/layers_1/bias", 1);
+  ml->scale = add("energy/per_atom_scale", D.nemb);
+  ml->shift = add("energy/per_atom_shift", D.nemb);
+  ml->total = off;
+}
+
+inline size_t a256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// ---- workspace carving ------------------------------------------------------------------------------
+struct Workspace {
+  Graph g;
+  int* scratch;
+  float *x, *chi;          // (L+1) states each
+  float *x1, *chi1, *bcoef;  // x1: 1 buffer ; chi1, bcoef: per layer
+  float *proj, *gproj;
+  float *alpha;            // per layer
+  float *alphabar, *gbar, *rbar;
+  float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
+  float *e_atom;
+  size_t bytes;
+};
+
+Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base) {
+  Workspace w;
+  char* p = (char*)base;
+  auto take = [&](size_t bytes) {
+    char* r = p;
+    p += a256(bytes);
+    return (void*)r;
+  };
+  const size_t F = D.F, M = D.M, nl = D.nl, L = D.L;
+  const size_t Ast = (D.H + D.nl + 3) & ~3, Gst = (D.nl + 3) & ~3;
+  const size_t Pe = Pt > 0 ? Pt : 1;
+  w.g.N = N; w.g.Pt = Pt;
+  w.g.rowptr = (int*)take(sizeof(int) * (N + 1));
+  w.g.col = (int*)take(sizeof(int) * Pe);
+  w.g.row = (int*)take(sizeof(int) * Pe);
+  w.g.src = (int*)take(sizeof(int) * Pe);
+  w.g.rev = (int*)take(sizeof(int) * Pe);
+  w.g.geom = (float4*)take(sizeof(float4) * Pe);
+  w.g.n_valid = w.g.rowptr + N;
+  w.scratch = (int*)take(sizeof(int) * so3k_graph_ws_ints(N, Pt));
+  w.x = (float*)take(sizeof(float) * (L + 1) * N * F);
+  w.chi = (float*)take(sizeof(float) * (L + 1) * N * M);
+  w.x1 = (float*)take(sizeof(float) * N * F);
+  w.chi1 = (float*)take(sizeof(float) * L * N * M);
+  w.bcoef = (float*)take(sizeof(float) * L * N * nl);
+  w.proj = (float*)take(sizeof(float) * N * 5 * F);
+  w.gproj = (float*)take(sizeof(float) * N * 5 * F);
+  w.alpha = (float*)take(sizeof(float) * L * Pe * Ast);
+  w.alphabar = (float*)take(sizeof(float) * Pe * Ast);
+  w.gbar = (float*)take(sizeof(float) * Pe * Gst);
+  w.rbar = (float*)take(sizeof(float) * Pe * 3);
+  w.xbar_a = (float*)take(sizeof(float) * N * F);
+  w.xbar_b = (float*)take(sizeof(float) * N * F);
+  w.chibar_a = (float*)take(sizeof(float) * N * M);
+  w.chibar_b = (float*)take(sizeof(float) * N * M);
+  w.e_atom = (float*)take(sizeof(float) * N);
+  w.bytes = (size_t)(p - (char*)base);
+  return w;
+}
+
+// One evaluation on an already-flattened problem description.
+int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, const int* idx_i, const int* idx_j,
+              const float* cell, const int* cell_offset, const float* disp, const unsigned char* mask,
+              float out_scale, float* E, float* forces, float* e_atom_out, float* dE_dedges, void* workspace,
+              size_t workspace_bytes, int* dev_status, cudaStream_t st) {
+  const So3kDims& D = h->dims;
+  const int N = B * n, Pt = B * P;
+  if (workspace_bytes < so3k_workspace_bytes(h, N, Pt)) return SO3K_ERR_WORKSPACE;
+  Workspace w = carve_ws(D, N, Pt, workspace);
+  const float* prm = h->params;
+  const size_t F = D.F, M = D.M, nl = D.nl;
+  const size_t Ast = (D.H + D.nl + 3) & ~3;
+  const size_t Pe = Pt > 0 ? Pt : 1;
+
+  so3k_build_graph(D, B, n, P, R, idx_i, idx_j, cell, cell_offset, disp, mask, w.g, w.scratch, dev_status, st);
+  so3k_launch_embed(D, N, z, prm + h->layout.embed, w.x, w.chi, dev_status, st);
+
+  // ---- forward ----------------------------------------------------------------------------------------
+  for (int t = 0; t < D.L; ++t) {
+    const LayerParams& lp = h->layout.layers[t];
+    float* xt = w.x + (size_t)t * N * F;
+    float* ct = w.chi + (size_t)t * N * M;
+    float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
+    so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st);
+    so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
+    so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+    so3k_launch_interaction(D, N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + (size_t)N * F, ct + (size_t)N * M,
+                            w.bcoef + (size_t)t * N * nl, st);
+  }
+  float* e_atom = e_atom_out ? e_atom_out : w.e_atom;
+  float* xbar = w.xbar_a;
+  float* xbar_nx = w.xbar_b;
+  float* chibar = w.chibar_a;
+  float* chibar_nx = w.chibar_b;
+  so3k_launch_readout(D, N, w.x + (size_t)D.L * N * F, z, prm, h->layout, out_scale, e_atom, xbar, st);
+  if (E) so3k_launch_energy_sum(B, n, e_atom, E, st);
+  if (!forces && !dE_dedges) return SO3K_OK;
+
+  // ---- reverse sweep ------------------------------------------------------------------------------------
+  cudaMemsetAsync(chibar, 0, sizeof(float) * N * M, st);
+  cudaMemsetAsync(w.rbar, 0, sizeof(float) * Pe * 3, st);
+  for (int t = D.L - 1; t >= 0; --t) {
+    const LayerParams& lp = h->layout.layers[t];
+    const float* xt = w.x + (size_t)t * N * F;
+    const float* ct = w.chi + (size_t)t * N * M;
+    const float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
+    // interaction block: (xbar, chibar) -> (xbar1, chibar1) written to the "next" buffers
+    so3k_launch_interaction_bwd(D, N, w.chi1 + (size_t)t * N * M, w.bcoef + (size_t)t * N * nl, prm, lp, xbar, chibar,
+                                xbar_nx, chibar_nx, st);
+    so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st);
+    cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
+    so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, xbar_nx, chibar_nx, w.alphabar, w.gproj, st);
+    so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, w.alphabar, chibar_nx, w.gproj, w.gbar,
+                         w.rbar, st);
+    if (t > 0) {
+      // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
+      so3k_launch_chi_bwd(D, w.g, ct, w.gbar, chibar_nx, chibar, st);      // chibar <- d/d chi_t
+      so3k_launch_node_proj_bwd(D, N, w.gproj, prm, lp, xbar_nx, st);      // xbar_nx += projections^T
+      float* tmp = xbar; xbar = xbar_nx; xbar_nx = tmp;                     // xbar <- d/d x_t
+    }
+  }
+  so3k_launch_forces(D, w.g, Pt, w.rbar, forces, dE_dedges, st);
+  return SO3K_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* so3k_version(void) { return "so3k-b200 0.1.0"; }
+uint64_t so3k_launch_count(void) { return g_launches.load(); }
+
+int so3k_create(const so3k_config* cfg, so3k_handle** out) {
+  if (!cfg || !out) return SO3K_ERR_ARG;
+  So3kDims D;
+  if (!make_dims(*cfg, &D)) return SO3K_ERR_CONFIG;
+  if (!so3k_edge_supported(D)) return SO3K_ERR_CONFIG;
+  HandleImpl* h = new (std::nothrow) HandleImpl();
+  if (!h) return SO3K_ERR_ARG;
+  h->cfg = *cfg;
+  h->dims = D;
+  make_layout(D, &h->layout);
+  *out = h;
+  return SO3K_OK;
+}
+
+int so3k_destroy(so3k_handle* hh) {
+  if (!hh) return SO3K_ERR_ARG;
+  HandleImpl* h = static_cast<HandleImpl*>(hh);
+  if (h->params) cudaFree(h->params);
+  if (h->repack) cudaFree(h->repack);
+  delete h;
+  return SO3K_OK;
+}
+
+size_t so3k_param_count(const so3k_handle* h) { return h ? h->layout.total : 0; }
+
+int so3k_param_lookup(const so3k_handle* h, const char* name, size_t* offset, size_t* count) {
+  if (!h || !name) return SO3K_ERR_ARG;
+  for (const auto& kv : h->layout.names) {
+    if (kv.first == name) {
+      if (offset) *offset = kv.second.first;
+      if (count) *count = kv.second.second;
+      return SO3K_OK;
+    }
+  }
+  return SO3K_ERR_ARG;
+}
+
+int so3k_load_params(so3k_handle* hh, const float* blob_dev, size_t n_floats, void* stream) {
+  if (!hh || !blob_dev) return SO3K_ERR_ARG;
+  HandleImpl* h = static_cast<HandleImpl*>(hh);
+  if (n_floats != h->layout.total) return SO3K_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const So3kDims& D = h->dims;
+  if (!h->params) {
+    if (cudaMalloc((void**)&h->params, sizeof(float) * ((h->layout.total + 3) & ~(size_t)3)) != cudaSuccess) return SO3K_ERR_CUDA;
+  }
+  size_t per = so3k_edge_repack_floats(D);
+  if (!h->repack) {
+    if (cudaMalloc((void**)&h->repack, sizeof(float) * per * 2 * D.L) != cudaSuccess) return SO3K_ERR_CUDA;
+  }
+  cudaMemcpyAsync(h->params, blob_dev, sizeof(float) * n_floats, cudaMemcpyDeviceToDevice, st);
+  h->wf.resize(D.L);
+  h->wg.resize(D.L);
+  for (int t = 0; t < D.L; ++t) {
+    so3k_edge_repack(D, h->params, h->layout.layers[t].fb, h->repack + per * (2 * t), &h->wf[t], st);
+    so3k_edge_repack(D, h->params, h->layout.layers[t].gb, h->repack + per * (2 * t + 1), &h->wg[t], st);
+  }
+  h->have_params = true;
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+size_t so3k_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total) {
+  if (!h || n_atoms_total <= 0 || n_edge_slots_total < 0) return 0;
+  Workspace w = carve_ws(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, nullptr);
+  return w.bytes + 256;
+}
+
+int so3k_energy_forces(so3k_handle* hh, int32_t B, int32_t n, int32_t P, const float* R, const int32_t* z,
+                       const int32_t* idx_i, const int32_t* idx_j, const float* cell, const int32_t* cell_offset,
+                       float* E, float* F, float* e_atom, void* workspace, size_t workspace_bytes, int32_t* dev_status,
+                       void* stream) {
+  if (!hh || B <= 0 || n <= 0 || P < 0 || !R || !z || !workspace) return SO3K_ERR_ARG;
+  if (P > 0 && (!idx_i || !idx_j)) return SO3K_ERR_ARG;
+  if ((cell == nullptr) != (cell_offset == nullptr)) return SO3K_ERR_ARG;
+  if ((int64_t)B * n > 0x7fffffff || (int64_t)B * P > 0x7fffffff) return SO3K_ERR_ARG;
+  HandleImpl* h = static_cast<HandleImpl*>(hh);
+  if (!h->have_params) return SO3K_ERR_NOPARAMS;
+  int rc = run_model(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, nullptr, nullptr, 1.0f, E, F, e_atom, nullptr,
+                     workspace, workspace_bytes, dev_status, (cudaStream_t)stream);
+  if (rc != SO3K_OK) return rc;
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+int so3k_potential_displacements(so3k_handle* hh, int32_t N, int32_t P, const float* edges, const int32_t* z,
+                                 const int32_t* centers, const int32_t* others, const uint8_t* mask,
+                                 float energy_scale, float* e_atom, float* dE_dedges, float* forces, void* workspace,
+                                 size_t workspace_bytes, int32_t* dev_status, void* stream) {
+  if (!hh || N <= 0 || P < 0 || !z || !workspace || !e_atom) return SO3K_ERR_ARG;
+  if (P > 0 && (!edges || !centers || !others)) return SO3K_ERR_ARG;
+  HandleImpl* h = static_cast<HandleImpl*>(hh);
+  if (!h->have_params) return SO3K_ERR_NOPARAMS;
+  int rc = run_model(h, 1, N, P, nullptr, z, centers, others, nullptr, nullptr, edges, mask, energy_scale, nullptr,
+                     forces, e_atom, dE_dedges, workspace, workspace_bytes, dev_status, (cudaStream_t)stream);
+  if (rc != SO3K_OK) return rc;
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+int so3k_featurise(const so3k_handle* h, int32_t n, int32_t P, const float* R, const int32_t* idx_i,
+                   const int32_t* idx_j, const float* cell, const int32_t* cell_offset, const float* displacements,
+                   float* rbf, float* phi, float* d, float* unit, float* sph, void* stream) {
+  if (!h || n <= 0 || P < 0 || !idx_i || !idx_j) return SO3K_ERR_ARG;
+  if (!R && !displacements) return SO3K_ERR_ARG;
+  so3k_launch_featurise(h->dims, n, P, R, idx_i, idx_j, cell, cell_offset, displacements, rbf, phi, d, unit, sph,
+                        (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,23 @@
+// Repacked filter weights of one block (fb or gb) of one layer, as consumed by the edge kernels.
+#pragma once
+#include "so3k_internal.h"
+
+struct EdgeBlockW {
+  const float* W1;    // (K, F)        rad layers_0 kernel
+  const float* b1;    // (F)
+  const float* W2c;   // (KC, F)       rows [0,F) = rad layers_1 kernel, rows [F,F+Fs) = sph layers_1 kernel, rest 0
+  const float* W2cT;  // (F, KC)       transpose of W2c
+  const float* b2c;   // (F)           rad layers_1 bias + sph layers_1 bias
+  const float* Ws1;   // (nl, Fs)      sph layers_0 kernel
+  const float* bs1;   // (Fs)
+};
+
+bool so3k_edge_supported(const So3kDims& D);
+size_t so3k_edge_repack_floats(const So3kDims& D);   // per block
+void so3k_edge_repack(const So3kDims& D, const float* params, const BlockParams& bp, float* dst, EdgeBlockW* out,
+                      cudaStream_t st);
+void so3k_launch_edge_fwd(const So3kDims& D, const Graph& g, const EdgeBlockW& Wf, const EdgeBlockW& Wg,
+                          const float* chi, const float* proj, float* alpha, cudaStream_t st);
+void so3k_launch_edge_bwd(const So3kDims& D, const Graph& g, const EdgeBlockW& Wf, const EdgeBlockW& Wg,
+                          const float* chi, const float* proj, const float* alpha, const float* alphabar,
+                          const float* chibar1, float* gproj, float* gbar, float* rbar, cudaStream_t st);

@@ -1,0 +1,82 @@
+// Internal structures shared by the translation units of libso3k.
+#pragma once
+#include "so3k_math.h"
+#include "../../include/so3k.h"
+#include <string>
+#include <vector>
+
+// ---- parameter blob layout (offsets in floats into the caller's blob order, so3k.h) ----------
+struct BlockParams {            // one filter block (fb or gb) of one layer
+  size_t rad_W1, rad_b1, rad_W2, rad_b2;   // (K,F) (F) (F,F) (F)
+  size_t sph_W1, sph_b1, sph_W2, sph_b2;   // (nl,Fs) (Fs) (Fs,F) (F)
+  size_t Wq, Wk, Wv;                        // (heads,d,d) each; Wv only for fb
+};
+struct LayerParams {
+  BlockParams fb, gb;
+  size_t int_W, int_b;                      // (F+nl,F+nl) (F+nl)
+};
+struct ModelLayout {
+  size_t embed;
+  std::vector<LayerParams> layers;
+  size_t out_W1, out_b1, out_W2, out_b2;    // (F,F) (F) (F,1) (1)
+  size_t scale, shift;                      // (nemb) each
+  size_t total;
+  std::vector<std::pair<std::string, std::pair<size_t, size_t>>> names;   // name -> (offset, count)
+};
+
+struct so3k_handle {
+  so3k_config cfg;
+  So3kDims dims;
+  ModelLayout layout;
+  float* params = nullptr;      // device copy of the blob (owned)
+  bool have_params = false;
+};
+
+// ---- graph (CSR) view living in the workspace --------------------------------------------------
+struct Graph {
+  int N = 0;          // atoms (flattened over the batch)
+  int Pt = 0;         // edge slots (flattened, padding included) ; valid edges = rowptr[N] (device)
+  int* rowptr;        // (N+1)
+  int* col;           // (Pt)  sender j of sorted edge e
+  int* row;           // (Pt)  receiver i of sorted edge e
+  int* src;           // (Pt)  original slot of sorted edge e
+  int* rev;           // (Pt)  sorted index of the reverse edge
+  float4* geom;       // (Pt)  (ux, uy, uz, d)
+  int* n_valid;       // device scalar = rowptr[N]
+};
+
+// ---- kernels' host launchers -------------------------------------------------------------------
+// graph.cu
+size_t so3k_graph_ws_ints(int N, int Pt);
+void so3k_build_graph(const So3kDims& D, int B, int n, int P, const float* R, const int* idx_i, const int* idx_j,
+                      const float* cell, const int* cell_offset, const float* disp, const unsigned char* mask,
+                      Graph& g, int* scratch /* >= so3k_graph_ws_ints */, int* dev_status, cudaStream_t st);
+// feat.cu
+void so3k_launch_featurise(const So3kDims& D, int n, int P, const float* R, const int* idx_i, const int* idx_j,
+                           const float* cell, const int* cell_offset, const float* disp, float* rbf, float* phi,
+                           float* d, float* unit, float* sph, cudaStream_t st);
+// node.cu
+void so3k_launch_embed(const So3kDims& D, int N, const int* z, const float* emb, float* x, float* chi,
+                       int* dev_status, cudaStream_t st);
+void so3k_launch_node_proj(const So3kDims& D, int N, const float* x, const float* params, const LayerParams& lp,
+                           float* proj, cudaStream_t st);
+void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* params,
+                               const LayerParams& lp, float* xbar /* += */, cudaStream_t st);
+void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const float* chi1, const float* params,
+                             const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st);
+void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, const float* bcoef,
+                                 const float* params, const LayerParams& lp, const float* xbar_out,
+                                 const float* chibar_out, float* xbar1, float* chibar1, cudaStream_t st);
+void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* params,
+                         const ModelLayout& ml, float out_scale, float* e_atom, float* xbar, cudaStream_t st);
+void so3k_launch_energy_sum(int B, int n, const float* e_atom, float* E, cudaStream_t st);
+// agg.cu
+void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
+                           const float* alpha, float* x1, float* chi1, cudaStream_t st);
+void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
+                           const float* xbar1, const float* chibar1, float* alphabar, float* gproj /* v grad */,
+                           cudaStream_t st);
+void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,
+                         const float* chibar1, float* chibar /* out */, cudaStream_t st);
+void so3k_launch_forces(const So3kDims& D, const Graph& g, int P_slots, const float* rbar, float* forces /* (N,3) or null */,
+                        float* dE_dedges /* (P_slots,3) or null, original order */, cudaStream_t st);

@@ -1,0 +1,361 @@
+// Node-level (per-atom) kernels: embedding, q/k/v projections, interaction block, energy read-out and
+// their data-gradients.  These are < 2 % of the FLOPs of a step;
+// they are written as small shared-memory tiled FMA kernels: a block owns TA atoms, the atom rows sit in
+// shared memory, each thread owns one output column and keeps TA accumulators so every weight element is
+// read once per block (coalesced across the threads of a warp).
+//   AtomTypeEmbed            mlff/nn/embed/embed.py:227-229
+//   q / k / v Dense          mlff/nn/layer/so3krates_layer.py:583-584, 607  (per head, no bias)
+//   InteractionBlock         mlff/nn/layer/so3krates_layer.py:355-379 (+ skip :163-164)
+//   Energy                   mlff/nn/observable/observable.py:77-91
+#include "so3k_internal.h"
+
+namespace {
+
+constexpr int TA = 16;        // atoms per block
+constexpr int NT = 256;       // threads per block
+
+// acc[a] += sum_c xs[a][c0 + c] * W[c * ldw + o]
+__device__ __forceinline__ void col_dot(const float* xs, int ldx, int c0, int nC, const float* __restrict__ W, int ldw,
+                                        int o, float* acc) {
+  for (int c = 0; c < nC; ++c) {
+    float w = W[(size_t)c * ldw + o];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = fmaf(xs[a * ldx + c0 + c], w, acc[a]);
+  }
+}
+// acc[a] += sum_o gs[a][o0 + o] * Wrow[o]       (Wrow contiguous)
+__device__ __forceinline__ void row_dot(const float* gs, int ldg, int o0, int nO, const float* __restrict__ Wrow,
+                                        float* acc) {
+  for (int o = 0; o < nO; ++o) {
+    float w = Wrow[o];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = fmaf(gs[a * ldg + o0 + o], w, acc[a]);
+  }
+}
+
+__global__ void k_embed(So3kDims D, int N, const int* __restrict__ z, const float* __restrict__ emb,
+                        float* __restrict__ x, float* __restrict__ chi, int* __restrict__ status) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)N * D.F;
+  if (t < tot) {
+    int a = (int)(t / D.F), f = (int)(t % D.F);
+    int za = z[a];
+    float v = 0.f;
+    if (za > 0 && za < D.nemb) v = emb[(size_t)za * D.F + f];
+    else if (za != 0 && f == 0 && status) atomicOr(status, SO3K_STATUS_BAD_Z);
+    x[t] = v;                                   // z == 0: point_mask = 0 -> exact zero (embed.py:228)
+  }
+  if (t < (long long)N * D.M) chi[t] = 0.f;     // chi0 = 0 (embed.py:196-197)
+}
+
+// proj[a][5F] = [q_fb | q_gb | k_fb | k_gb | v_fb]
+__global__ void __launch_bounds__(NT)
+k_node_proj(So3kDims D, int N, const float* __restrict__ x, const float* __restrict__ Wq_f,
+            const float* __restrict__ Wq_g, const float* __restrict__ Wk_f, const float* __restrict__ Wk_g,
+            const float* __restrict__ Wv_f, float* __restrict__ proj) {
+  SO3K_DYN_SMEM(float, xs);                     // [TA][F]
+  const int F = D.F;
+  const int a0 = blockIdx.x * TA;
+  for (int t = threadIdx.x; t < TA * F; t += NT) {
+    int a = t / F, f = t % F;
+    xs[t] = (a0 + a < N) ? x[(size_t)(a0 + a) * F + f] : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 5 * F; o += NT) {
+    int seg = o / F, f = o % F;
+    const float* W;
+    int dsz;
+    switch (seg) {
+      case 0: W = Wq_f; dsz = D.dh; break;
+      case 1: W = Wq_g; dsz = D.dg; break;
+      case 2: W = Wk_f; dsz = D.dh; break;
+      case 3: W = Wk_g; dsz = D.dg; break;
+      default: W = Wv_f; dsz = D.dh; break;
+    }
+    int hd = f / dsz, oo = f % dsz;
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(xs, F, hd * dsz, dsz, W + (size_t)hd * dsz * dsz, dsz, oo, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a)
+      if (a0 + a < N) proj[(size_t)(a0 + a) * 5 * F + o] = acc[a];
+  }
+}
+
+// xbar[a][f] += sum over the five projections of  gproj[a][seg][head(f) block] @ W[seg][head]^T
+__global__ void __launch_bounds__(NT)
+k_node_proj_bwd(So3kDims D, int N, const float* __restrict__ gproj, const float* __restrict__ Wq_f,
+                const float* __restrict__ Wq_g, const float* __restrict__ Wk_f, const float* __restrict__ Wk_g,
+                const float* __restrict__ Wv_f, float* __restrict__ xbar) {
+  SO3K_DYN_SMEM(float, gs);                     // [TA][5F]
+  const int F = D.F, F5 = 5 * D.F;
+  const int a0 = blockIdx.x * TA;
+  for (int t = threadIdx.x; t < TA * F5; t += NT) {
+    int a = t / F5, o = t % F5;
+    gs[t] = (a0 + a < N) ? gproj[(size_t)(a0 + a) * F5 + o] : 0.f;
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    for (int seg = 0; seg < 5; ++seg) {
+      const float* W;
+      int dsz;
+      switch (seg) {
+        case 0: W = Wq_f; dsz = D.dh; break;
+        case 1: W = Wq_g; dsz = D.dg; break;
+        case 2: W = Wk_f; dsz = D.dh; break;
+        case 3: W = Wk_g; dsz = D.dg; break;
+        default: W = Wv_f; dsz = D.dh; break;
+      }
+      int hd = f / dsz, c = f % dsz;
+      row_dot(gs, F5, seg * F + hd * dsz, dsz, W + ((size_t)hd * dsz + c) * dsz, acc);
+    }
+#pragma unroll
+    for (int a = 0; a < TA; ++a)
+      if (a0 + a < N) xbar[(size_t)(a0 + a) * F + f] += acc[a];
+  }
+}
+
+// x2 = x1 + a ; chi2 = chi1 * (1 + repeat(b)) ; [a|b] = [x1 | l0(chi1)] W + bias
+__global__ void __launch_bounds__(NT)
+k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __restrict__ chi1,
+              const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ x2,
+              float* __restrict__ chi2, float* __restrict__ bcoef) {
+  SO3K_DYN_SMEM(float, sm);
+  const int F = D.F, nl = D.nl, M = D.M, FI = D.F + D.nl;
+  float* ys = sm;                 // [TA][FI]
+  float* cs = ys + TA * FI;       // [TA][M]
+  float* bs = cs + TA * M;        // [TA][nl]
+  const int a0 = blockIdx.x * TA;
+  for (int t = threadIdx.x; t < TA * F; t += NT) {
+    int a = t / F, f = t % F;
+    ys[a * FI + f] = (a0 + a < N) ? x1[(size_t)(a0 + a) * F + f] : 0.f;
+  }
+  for (int t = threadIdx.x; t < TA * M; t += NT) {
+    int a = t / M, m = t % M;
+    cs[t] = (a0 + a < N) ? chi1[(size_t)(a0 + a) * M + m] : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < TA * nl; t += NT) {
+    int a = t / nl, l = t % nl;
+    float s = 0.f;
+    for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s += cs[a * M + m] * cs[a * M + m] * D.m_cg[m];
+    ys[a * FI + F + l] = s;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < FI; o += NT) {
+    float acc[TA];
+    float bo = bias[o];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = bo;
+    col_dot(ys, FI, 0, FI, W, FI, o, acc);
+    if (o < F) {
+#pragma unroll
+      for (int a = 0; a < TA; ++a)
+        if (a0 + a < N) x2[(size_t)(a0 + a) * F + o] = ys[a * FI + o] + acc[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < TA; ++a) {
+        bs[a * nl + (o - F)] = acc[a];
+        if (a0 + a < N) bcoef[(size_t)(a0 + a) * nl + (o - F)] = acc[a];
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < TA * M; t += NT) {
+    int a = t / M, m = t % M;
+    if (a0 + a < N) chi2[(size_t)(a0 + a) * M + m] = cs[t] + bs[a * nl + D.m_seg[m]] * cs[t];
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float* __restrict__ bcoef,
+                  const float* __restrict__ W, const float* __restrict__ xbar_out,
+                  const float* __restrict__ chibar_out, float* __restrict__ xbar1, float* __restrict__ chibar1) {
+  SO3K_DYN_SMEM(float, sm);
+  const int F = D.F, nl = D.nl, M = D.M, FI = D.F + D.nl;
+  float* gs = sm;                 // [TA][FI]  = [xbar_out | bbar]
+  float* cs = gs + TA * FI;       // [TA][M]   chi1
+  float* cb = cs + TA * M;        // [TA][M]   chibar_out
+  float* Gb = cb + TA * M;        // [TA][nl]  gradient wrt l0(chi1)
+  const int a0 = blockIdx.x * TA;
+  for (int t = threadIdx.x; t < TA * F; t += NT) {
+    int a = t / F, f = t % F;
+    gs[a * FI + f] = (a0 + a < N) ? xbar_out[(size_t)(a0 + a) * F + f] : 0.f;
+  }
+  for (int t = threadIdx.x; t < TA * M; t += NT) {
+    int a = t / M, m = t % M;
+    bool ok = a0 + a < N;
+    cs[t] = ok ? chi1[(size_t)(a0 + a) * M + m] : 0.f;
+    cb[t] = ok ? chibar_out[(size_t)(a0 + a) * M + m] : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < TA * nl; t += NT) {
+    int a = t / nl, l = t % nl;
+    float s = 0.f;
+    for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s += cb[a * M + m] * cs[a * M + m];
+    gs[a * FI + F + l] = s;       // bbar
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < FI; c += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    row_dot(gs, FI, 0, FI, W + (size_t)c * FI, acc);
+    if (c < F) {
+#pragma unroll
+      for (int a = 0; a < TA; ++a)
+        if (a0 + a < N) xbar1[(size_t)(a0 + a) * F + c] = gs[a * FI + c] + acc[a];
+    } else {
+#pragma unroll
+      for (int a = 0; a < TA; ++a) Gb[a * nl + (c - F)] = acc[a];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < TA * M; t += NT) {
+    int a = t / M, m = t % M;
+    if (a0 + a < N) {
+      int l = D.m_seg[m];
+      float b = bcoef[(size_t)(a0 + a) * nl + l];
+      chibar1[(size_t)(a0 + a) * M + m] = cb[t] * (1.0f + b) + 2.0f * D.m_cg[m] * cs[t] * Gb[a * nl + l];
+    }
+  }
+}
+
+// e = (Dense(F->1)(silu(Dense(F->F)(x)))) * scale[z] + shift[z], masked ; xbar = d(sum e)/dx
+__global__ void __launch_bounds__(NT)
+k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict__ z, const float* __restrict__ W1,
+          const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
+          const float* __restrict__ scale, const float* __restrict__ shift, float out_scale,
+          float* __restrict__ e_atom, float* __restrict__ xbar) {
+  SO3K_DYN_SMEM(float, sm);
+  const int F = D.F;
+  float* xs = sm;               // [TA][F]
+  float* ab = xs + TA * F;      // [TA][F]  abar
+  float* es = ab + TA * F;      // [TA][F]  silu(a) * W2
+  float* coef = es + TA * F;    // [TA]
+  const int a0 = blockIdx.x * TA;
+  for (int t = threadIdx.x; t < TA * F; t += NT) {
+    int a = t / F, f = t % F;
+    xs[t] = (a0 + a < N) ? x[(size_t)(a0 + a) * F + f] : 0.f;
+  }
+  if (threadIdx.x < TA) {
+    int a = a0 + threadIdx.x;
+    float c = 0.f;
+    if (a < N) {
+      int za = z[a];
+      if (za > 0 && za < D.nemb) c = scale[za] * out_scale;
+    }
+    coef[threadIdx.x] = c;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F; o += NT) {
+    float acc[TA];
+    float bo = b1[o];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = bo;
+    col_dot(xs, F, 0, F, W1, F, o, acc);
+    float w2 = W2[o];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) {
+      float s, ds;
+      so3k_silu_d(acc[a], &s, &ds);
+      es[a * F + o] = s * w2;
+      ab[a * F + o] = ds * w2 * coef[a];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TA) {
+    int a = a0 + threadIdx.x;
+    if (a < N) {
+      float s = 0.f;
+      for (int o = 0; o < F; ++o) s += es[threadIdx.x * F + o];
+      s += b2[0];
+      int za = z[a];
+      float e = 0.f;
+      if (za > 0 && za < D.nemb) e = (scale[za] * s + shift[za]) * out_scale;
+      e_atom[a] = e;
+    }
+  }
+  for (int c = threadIdx.x; c < F; c += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    row_dot(ab, F, 0, F, W1 + (size_t)c * F, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a)
+      if (a0 + a < N) xbar[(size_t)(a0 + a) * F + c] = acc[a];
+  }
+}
+
+// E[b] = sum_a e_atom[b][a]   (float64 accumulation, one warp per structure chunk)
+__global__ void k_energy_sum(int B, int n, const float* __restrict__ e_atom, float* __restrict__ E) {
+  __shared__ double s_part[NT / 32];
+  int b = blockIdx.x;
+  double s = 0.0;
+  for (int a = threadIdx.x; a < n; a += NT) s += (double)e_atom[(size_t)b * n + a];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < NT / 32; ++w) t += s_part[w];
+    E[b] = (float)t;
+  }
+}
+
+}  // namespace
+
+void so3k_launch_embed(const So3kDims& D, int N, const int* z, const float* emb, float* x, float* chi,
+                       int* dev_status, cudaStream_t st) {
+  long long tot = (long long)N * (D.F > D.M ? D.F : D.M);
+  SO3K_LAUNCH(k_embed, dim3(so3k_cdiv(tot, 256)), dim3(256), 0, st, D, N, z, emb, x, chi, dev_status);
+}
+
+void so3k_launch_node_proj(const So3kDims& D, int N, const float* x, const float* p, const LayerParams& lp,
+                           float* proj, cudaStream_t st) {
+  size_t smem = sizeof(float) * TA * D.F;
+  SO3K_SET_MAX_SMEM(k_node_proj, smem);
+  SO3K_LAUNCH(k_node_proj, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, p + lp.fb.Wq, p + lp.gb.Wq,
+              p + lp.fb.Wk, p + lp.gb.Wk, p + lp.fb.Wv, proj);
+}
+
+void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* p, const LayerParams& lp,
+                               float* xbar, cudaStream_t st) {
+  size_t smem = sizeof(float) * TA * 5 * D.F;
+  SO3K_SET_MAX_SMEM(k_node_proj_bwd, smem);
+  SO3K_LAUNCH(k_node_proj_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, gproj, p + lp.fb.Wq, p + lp.gb.Wq,
+              p + lp.fb.Wk, p + lp.gb.Wk, p + lp.fb.Wv, xbar);
+}
+
+void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const float* chi1, const float* p,
+                             const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st) {
+  size_t smem = sizeof(float) * TA * (D.F + D.nl + D.M + D.nl);
+  SO3K_SET_MAX_SMEM(k_interaction, smem);
+  SO3K_LAUNCH(k_interaction, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x1, chi1, p + lp.int_W, p + lp.int_b,
+              x2, chi2, bcoef);
+}
+
+void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, const float* bcoef, const float* p,
+                                 const LayerParams& lp, const float* xbar_out, const float* chibar_out, float* xbar1,
+                                 float* chibar1, cudaStream_t st) {
+  size_t smem = sizeof(float) * TA * (D.F + D.nl + 2 * D.M + D.nl);
+  SO3K_SET_MAX_SMEM(k_interaction_bwd, smem);
+  SO3K_LAUNCH(k_interaction_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, chi1, bcoef, p + lp.int_W,
+              xbar_out, chibar_out, xbar1, chibar1);
+}
+
+void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* p,
+                         const ModelLayout& ml, float out_scale, float* e_atom, float* xbar, cudaStream_t st) {
+  size_t smem = sizeof(float) * (3 * TA * D.F + TA);
+  SO3K_SET_MAX_SMEM(k_readout, smem);
+  SO3K_LAUNCH(k_readout, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, z, p + ml.out_W1, p + ml.out_b1,
+              p + ml.out_W2, p + ml.out_b2, p + ml.scale, p + ml.shift, out_scale, e_atom, xbar);
+}
+
+void so3k_launch_energy_sum(int B, int n, const float* e_atom, float* E, cudaStream_t st) {
+  SO3K_LAUNCH(k_energy_sum, dim3(B), dim3(NT), 0, st, B, n, e_atom, E);
+}

@@ -1,0 +1,497 @@
+"""CPU oracle for the SO3krates energy+force hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mlff_b200/`` may import this file; it is the
+checker used by ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py``.
+
+It is a restatement (torch-CPU, float64 or float32) of the reference's algorithm, written
+against the reference source line by line.  Citations are ``path:line`` relative to
+``/root/reference``:
+
+  masks                 mlff/nn/stacknet/stacknet.py:129-132
+  geometry embedding    mlff/nn/embed/embed.py:66-169, 189-197
+  PhysNet radial basis  mlff/basis_function/radial.py:154-166
+  cosine cutoff         mlff/cutoff_function/radial.py:39-51
+  cell offsets          mlff/cutoff_function/pbc.py:8-18
+  real sph. harmonics   mlff/basis_function/spherical.py:6-38
+  safe_mask/safe_scale  mlff/masking/mask.py:5-54
+  l=0 contraction       mlff/sph_ops/contract.py:162-190 (+ sph_ops/cgmatrix.npz)
+  So3krates layer       mlff/nn/layer/so3krates_layer.py:57-178, 207-379, 417-615
+  MLP                   mlff/nn/mlp/mlp.py:8-27
+  energy readout        mlff/nn/observable/observable.py:34-93
+  forces                mlff/nn/stacknet/observable_function.py:41-63, 127-149
+  MD potential          mlff/mdx/potential/mlff_potential.py:80-109
+  neighbour lists       mlff/indexing/indices.py:15-84 (dense, 0 < d <= r_cut)
+                        mlff/indexing/indices.py:194-275 (ASE primitive_neighbor_list('ijS'))
+
+PARITY PINNING.  The reference is pure Python on JAX/flax; neither jax, flax nor ase is
+installed in this image (and there is no network), so the reference cannot be executed here
+and its tests hold no golden energies / forces for this path.  What IS
+pinned against reference artefacts:
+  * the l=0 contraction coefficients are checked against the reference's own
+    ``sph_ops/cgmatrix.npz`` (tests/golden/make_golden.py writes them to
+    tests/golden/l0_cg_diag.npy; tests/test_oracle.py compares);
+  * the dense neighbour list reproduces the reference fixture property "every ethanol frame
+    has 72 directed edges at 5 A" and the distance-multiset test of
+    tests/test_neighbor_list.py:20-49;
+  * the model obeys the reference's behavioural spec tests/test_model_invariance.py:80-222
+    (rotation invariance / equivariance at atol 1e-5, padding invariance);
+  * forces = -dE/dR from float64 autograd are cross-checked with central finite differences.
+Numeric values of E and F are otherwise "parity unpinned" by the reference: this restatement is
+the arbiter, as SURVEY.md section 8(c) states.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+# --------------------------------------------------------------------------------------
+# configuration + parameters (names mirror the flax tree)
+# --------------------------------------------------------------------------------------
+@dataclass
+class OracleConfig:
+    F: int = 132
+    n_rbf: int = 32
+    degrees: Sequence[int] = (1, 2, 3)
+    n_heads: int = 4
+    n_layers: int = 3
+    r_cut: float = 5.0
+    num_embeddings: int = 100
+
+    @property
+    def nl(self) -> int:
+        return len(self.degrees)
+
+    @property
+    def M(self) -> int:
+        return int(sum(2 * l + 1 for l in self.degrees))
+
+    @property
+    def Fs(self) -> int:
+        # mlff/nn/representation/so3krates.py:64,66  -> int(F/4)
+        return int(self.F / 4)
+
+
+def init_params(cfg: OracleConfig, seed: int = 0, bias_scale: float = 0.01,
+                scale_shift: bool = False, embed_scale: float = 1.0) -> Dict[str, np.ndarray]:
+    """Random parameters with flax-like scales (lecun_normal kernels).  Biases are drawn
+    N(0, bias_scale) instead of flax' zeros so that bias paths are exercised.
+    ``embed_scale`` > 1 amplifies the embedding (flax default = 1) so that the message-passing
+    terms are O(1) and parity tests are discriminating.
+    Returned as a flat dict of float64 numpy arrays keyed by a flax-like path."""
+    rng = np.random.default_rng(seed)
+    F, K, nl, H, Fs = cfg.F, cfg.n_rbf, cfg.nl, cfg.n_heads, cfg.Fs
+    dh, dg = F // H, F // nl
+    p: Dict[str, np.ndarray] = {}
+
+    def dense(name, fin, fout, bias=True, lead=()):
+        p[name + '/kernel'] = rng.normal(0.0, 1.0 / math.sqrt(fin), size=(*lead, fin, fout))
+        if bias:
+            p[name + '/bias'] = rng.normal(0.0, bias_scale, size=(*lead, fout))
+
+    # flax nn.Embed default: variance_scaling(1.0, 'fan_in', 'normal', out_axis=0) -> std 1/sqrt(F)
+    p['embed/embedding'] = rng.normal(0.0, embed_scale / math.sqrt(F), size=(cfg.num_embeddings, F))
+    for t in range(cfg.n_layers):
+        for blk in ('fb', 'gb'):
+            pre = f'layers_{t}/{blk}'
+            dense(pre + '/rad/layers_0', K, F)
+            dense(pre + '/rad/layers_1', F, F)
+            dense(pre + '/sph/layers_0', nl, Fs)
+            dense(pre + '/sph/layers_1', Fs, F)
+            if blk == 'fb':
+                dense(pre + '/q', dh, dh, bias=False, lead=(H,))
+                dense(pre + '/k', dh, dh, bias=False, lead=(H,))
+                dense(pre + '/v', dh, dh, bias=False, lead=(H,))
+            else:
+                dense(pre + '/q', dg, dg, bias=False, lead=(nl,))
+                dense(pre + '/k', dg, dg, bias=False, lead=(nl,))
+        dense(f'layers_{t}/int/layers_0', F + nl, F + nl)
+    dense('energy/layers_0', F, F)
+    dense('energy/layers_1', F, 1)
+    if scale_shift:
+        p['energy/per_atom_scale'] = rng.uniform(0.5, 1.5, size=(cfg.num_embeddings,))
+        p['energy/per_atom_shift'] = rng.normal(0.0, 1.0, size=(cfg.num_embeddings,))
+    else:
+        p['energy/per_atom_scale'] = np.ones((cfg.num_embeddings,))
+        p['energy/per_atom_shift'] = np.zeros((cfg.num_embeddings,))
+    return p
+
+
+# --------------------------------------------------------------------------------------
+# math primitives
+# --------------------------------------------------------------------------------------
+def safe_mask(mask, fn, operand, placeholder=0.0):
+    """mlff/masking/mask.py:5-20 (double where)."""
+    masked = torch.where(mask, operand, torch.zeros_like(operand))
+    out = fn(masked)
+    return torch.where(mask, out, torch.full_like(out, placeholder))
+
+
+def safe_scale(x, scale, placeholder=0.0):
+    """mlff/masking/mask.py:41-54."""
+    scale = torch.as_tensor(scale, dtype=x.dtype)
+    return safe_mask(scale != 0, lambda y: scale * y, x, placeholder)
+
+
+def physnet_rbf(d, n_rbf: int, r_cut: float):
+    """mlff/basis_function/radial.py:163-166.  d: (...,1) -> (...,n_rbf)."""
+    dt = d.dtype
+    rc = torch.tensor(r_cut, dtype=dt)
+    offsets = torch.linspace(float(torch.exp(-rc)), 1.0, n_rbf, dtype=dt)
+    # jnp.linspace evaluates start + i*step in the array dtype; torch.linspace matches to 1 ulp.
+    coefficient = ((2.0 / n_rbf) * (1.0 - torch.exp(-rc))) ** (-2)
+    return torch.exp(-torch.abs(coefficient) * (torch.exp(-d) - offsets) ** 2)
+
+
+def cosine_cutoff(d, r_cut: float):
+    """mlff/cutoff_function/radial.py:39-51."""
+    return safe_mask(d < r_cut, lambda x: 0.5 * (torch.cos(x * math.pi / r_cut) + 1.0), d, 0.0)
+
+
+def sph_harm(l: int, u):
+    """mlff/basis_function/spherical.py:6-38; u (...,3) unit vectors -> (...,2l+1), m = -l..l."""
+    x, y, z = u[..., 0:1], u[..., 1:2], u[..., 2:3]
+    pi = math.pi
+    s = math.sqrt
+    if l == 0:
+        return torch.ones_like(x) * (0.5 * s(1 / pi))
+    if l == 1:
+        c = s(3 / (4 * pi))
+        return torch.cat([c * y, c * z, c * x], -1)
+    if l == 2:
+        return torch.cat([0.5 * s(15 / pi) * x * y,
+                          0.5 * s(15 / pi) * y * z,
+                          0.25 * s(5 / pi) * (3 * z ** 2 - 1),
+                          0.5 * s(15 / pi) * x * z,
+                          0.25 * s(15 / pi) * (x ** 2 - y ** 2)], -1)
+    if l == 3:
+        return torch.cat([0.25 * s(35 / (2 * pi)) * y * (3 * x ** 2 - y ** 2),
+                          0.5 * s(105 / pi) * x * y * z,
+                          0.25 * s(21 / (2 * pi)) * y * (5 * z ** 2 - 1),
+                          0.25 * s(7 / pi) * (5 * z ** 3 - 3 * z),
+                          0.25 * s(21 / (2 * pi)) * x * (5 * z ** 2 - 1),
+                          0.25 * s(105 / pi) * (x ** 2 - y ** 2) * z,
+                          0.25 * s(35 / (2 * pi)) * x * (x ** 2 - 3 * y ** 2)], -1)
+    if l == 4:
+        return torch.cat([0.75 * s(35 / pi) * x * y * (x ** 2 - y ** 2),
+                          0.75 * s(35 / (2 * pi)) * y * (3 * x ** 2 - y ** 2) * z,
+                          0.75 * s(5 / pi) * x * y * (7 * z ** 2 - 1),
+                          0.75 * s(5 / (2 * pi)) * y * (7 * z ** 3 - 3 * z),
+                          (3 / 16) * s(1 / pi) * (35 * z ** 4 - 30 * z ** 2 + 3),
+                          0.75 * s(5 / (2 * pi)) * x * (7 * z ** 3 - 3 * z),
+                          (3 / 8) * s(5 / pi) * (x ** 2 - y ** 2) * (7 * z ** 2 - 1),
+                          0.75 * s(35 / (2 * pi)) * x * (x ** 2 - 3 * y ** 2) * z,
+                          (3 / 16) * s(35 / pi) * (x ** 2 * (x ** 2 - 3 * y ** 2)
+                                                   - y ** 2 * (3 * x ** 2 - y ** 2))], -1)
+    raise NotImplementedError('Spherical harmonics are only defined up to order l = 4.')
+
+
+def l0_coefficients(degrees: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    """mlff/sph_ops/contract.py:162-177.  Returns (cg_rep (M,), segment_ids (M,)).
+
+    The reference concatenates the CG(l,l->0) diagonals in *sorted unique-degree* order
+    (``np.unique(degrees, return_counts=True)``) while the segment ids follow the *position*
+    in ``degrees``; both are reproduced here.  diag CG(l,l->0) = 1/sqrt(2l+1), verified
+    against the reference's cgmatrix.npz in tests/test_oracle.py."""
+    deg = np.asarray(degrees)
+    cg_rep: List[float] = []
+    for d, r in zip(*np.unique(deg, return_counts=True)):
+        cg_rep += [1.0 / math.sqrt(2 * int(d) + 1)] * (2 * int(d) + 1) * int(r)
+    seg = [n for n in range(len(degrees)) for _ in range(2 * int(degrees[n]) + 1)]
+    return np.asarray(cg_rep, dtype=np.float64), np.asarray(seg, dtype=np.int64)
+
+
+def l0_contraction(chi, degrees: Sequence[int]):
+    """contract.py:181-188: segment_sum(chi*chi*cg_rep) over the degree segments."""
+    cg, seg = l0_coefficients(degrees)
+    cg_t = torch.as_tensor(cg, dtype=chi.dtype)
+    seg_t = torch.as_tensor(seg)
+    prod = chi * chi * cg_t[None, :]
+    out = torch.zeros(chi.shape[0], len(degrees), dtype=chi.dtype)
+    return out.index_add(1, seg_t, prod)
+
+
+def repeat_degrees(a, degrees: Sequence[int]):
+    """jnp.repeat(a, repeats=[2l+1...], axis=-1) (so3krates_layer.py:349-350, 517-518)."""
+    reps = torch.as_tensor([2 * int(l) + 1 for l in degrees])
+    return torch.repeat_interleave(a, reps, dim=-1)
+
+
+def silu(x):
+    return x * torch.sigmoid(x)
+
+
+def mlp2(x, W0, b0, W1, b1):
+    """mlff/nn/mlp/mlp.py:21-27 with two layers, activation on the first only."""
+    return silu(x @ W0 + b0) @ W1 + b1
+
+
+def segment_sum(data, ids, n):
+    """jax.ops.segment_sum; callers guarantee rows with invalid ids carry exact zeros."""
+    ids = torch.where(ids < 0, torch.zeros_like(ids), ids)
+    out = torch.zeros((n,) + tuple(data.shape[1:]), dtype=data.dtype)
+    return out.index_add(0, ids, data)
+
+
+# --------------------------------------------------------------------------------------
+# model
+# --------------------------------------------------------------------------------------
+def _t(params, key, dtype):
+    return torch.as_tensor(params[key], dtype=dtype)
+
+
+def geometry_embed(cfg: OracleConfig, idx_i, idx_j, pair_mask, dtype, R=None, cell=None,
+                   cell_offset=None, displacements=None) -> Dict[str, torch.Tensor]:
+    """mlff/nn/embed/embed.py:66-169."""
+    pm = pair_mask
+    gi = torch.where(idx_i < 0, torch.zeros_like(idx_i), idx_i)
+    gj = torch.where(idx_j < 0, torch.zeros_like(idx_j), idx_j)
+    if displacements is None:
+        r_ij = safe_scale(R[gj] - R[gi], pm[:, None])                         # :88
+        if cell is not None:
+            offsets = torch.einsum('pi,ij->pj', cell_offset.to(dtype), cell)  # pbc.py:17
+            r_ij = r_ij + offsets                                             # pbc.py:18
+    else:
+        r_ij = displacements                                                  # :97-99
+    r_ij = safe_scale(r_ij, pm[:, None])                                      # :104
+    # jnp.linalg.norm: sqrt(sum(x*x)); the autograd NaN at 0 only occurs on masked rows and
+    # is removed by the select in safe_scale (mask.py:19-20) -- reproduced with a safe sqrt.
+    sq = (r_ij * r_ij).sum(-1)
+    d_raw = safe_mask(sq > 0, torch.sqrt, sq, 0.0)
+    d_ij = safe_scale(d_raw, pm)                                              # :107
+    rbf = safe_scale(physnet_rbf(d_ij[:, None], cfg.n_rbf, cfg.r_cut), pm[:, None])   # :110
+    phi = safe_scale(cosine_cutoff(d_ij, cfg.r_cut), pm)                      # :111
+    nz = (d_ij != 0)[:, None]
+    unit = torch.where(nz, torch.where(nz, r_ij, torch.zeros_like(r_ij))
+                       / torch.where(nz, d_ij[:, None], torch.ones_like(d_ij[:, None])),
+                       torch.zeros_like(r_ij))                                # :114-118
+    unit = safe_scale(unit, pm[:, None])                                      # :119
+    sph = torch.cat([safe_scale(sph_harm(int(l), unit), pm[:, None]) for l in cfg.degrees], -1)  # :122-127
+    return {'r_ij': r_ij, 'd_ij': d_ij, 'rbf_ij': rbf, 'phi_r_cut': phi, 'unit_r_ij': unit, 'sph_ij': sph}
+
+
+def _heads(x, n_heads):
+    return x.reshape(x.shape[0], n_heads, -1)                                 # so3krates_layer.py:611-615
+
+
+def _coefficients(xh, wh, Wq, Wk, gi, gj):
+    """ConvAttentionCoefficients vmapped over heads, so3krates_layer.py:568-586."""
+    q = torch.einsum('nhc,hcd->nhd', xh, Wq)[gi]
+    k = torch.einsum('nhc,hcd->nhd', xh, Wk)[gj]
+    return (q * wh * k).sum(-1) / math.sqrt(xh.shape[-1])
+
+
+def so3krates_layer(cfg: OracleConfig, params, t: int, x, chi, geo, idx_i, idx_j, pair_mask,
+                    record: Optional[dict] = None):
+    """So3kratesLayer.__call__, so3krates_layer.py:57-178 (default branches only)."""
+    dtype = x.dtype
+    n = x.shape[0]
+    pm = pair_mask
+    gi = torch.where(idx_i < 0, torch.zeros_like(idx_i), idx_i)
+    gj = torch.where(idx_j < 0, torch.zeros_like(idx_j), idx_j)
+    P = lambda k: _t(params, f'layers_{t}/{k}', dtype)
+
+    chi_ij = safe_scale(chi[gj] - chi[gi], pm[:, None])                       # :89-90
+    g = l0_contraction(chi_ij, cfg.degrees)                                   # :92-93
+
+    def filt(blk):                                                            # :462-464
+        w = mlp2(geo['rbf_ij'], P(f'{blk}/rad/layers_0/kernel'), P(f'{blk}/rad/layers_0/bias'),
+                 P(f'{blk}/rad/layers_1/kernel'), P(f'{blk}/rad/layers_1/bias'))
+        w = w + mlp2(g, P(f'{blk}/sph/layers_0/kernel'), P(f'{blk}/sph/layers_0/bias'),
+                     P(f'{blk}/sph/layers_1/kernel'), P(f'{blk}/sph/layers_1/bias'))
+        return w
+
+    # FeatureBlock (:258-265) -> ConvAttention (:498-509)
+    w_fb = filt('fb')
+    xh = _heads(x, cfg.n_heads)
+    alpha = _coefficients(xh, _heads(w_fb, cfg.n_heads), P('fb/q/kernel'), P('fb/k/kernel'), gi, gj)
+    alpha = safe_scale(alpha, pm[:, None] * geo['phi_r_cut'][:, None])        # :501
+    v = torch.einsum('nhc,hcd->nhd', xh, P('fb/v/kernel'))                    # :607
+    x_local = segment_sum(alpha[:, :, None] * v[gj], idx_i, n).reshape(n, -1)  # :608
+
+    # GeometricBlock (:326-337) -> SphConvAttention (:549-565)
+    w_gb = safe_scale(filt('gb'), pm[:, None])                                # :326
+    xg = _heads(x, cfg.nl)
+    a_gb = _coefficients(xg, _heads(w_gb, cfg.nl), P('gb/q/kernel'), P('gb/k/kernel'), gi, gj)
+    a_r = safe_scale(a_gb, pm[:, None] * geo['phi_r_cut'][:, None])           # :551
+    a_s = safe_scale(a_gb, pm[:, None] * torch.zeros_like(geo['phi_r_cut'])[:, None])  # :100, :552
+    a_gb = a_r + a_s                                                          # :553
+    chi_local = segment_sum(repeat_degrees(a_gb, cfg.degrees) * geo['sph_ij'], idx_i, n)  # :563-564
+
+    x1 = x + x_local                                                          # :146
+    chi1 = chi + chi_local                                                    # :147
+
+    # InteractionBlock (:355-379): single Dense, no activation (mlp.py:24-26)
+    d_chi = l0_contraction(chi1, cfg.degrees)
+    y = torch.cat([x1, d_chi], -1)
+    ab = y @ P('int/layers_0/kernel') + P('int/layers_0/bias')
+    a1, b1 = ab[:, :cfg.F], ab[:, cfg.F:]
+    x2 = x1 + a1                                                              # :163
+    chi2 = chi1 + repeat_degrees(b1, cfg.degrees) * chi1                      # :164, :379
+    if record is not None:
+        record[f'layer{t}'] = {'g': g, 'w_fb': w_fb, 'w_gb': w_gb, 'alpha_fb': alpha, 'alpha_gb': a_gb,
+                               'x_local': x_local, 'chi_local': chi_local, 'x': x2, 'chi': chi2}
+    return x2, chi2
+
+
+def forward(cfg: OracleConfig, params, z, idx_i, idx_j, dtype=torch.float64, R=None, cell=None,
+            cell_offset=None, displacements=None, record: Optional[dict] = None):
+    """StackNet.__call__ (stacknet.py:40-87) for ONE structure.  Returns per-atom energies (n,).
+    E (per_structure) = e.sum();  'per_atom' convention returns e[:, None] (observable.py:88-91)."""
+    z = torch.as_tensor(z).to(torch.int64)
+    idx_i = torch.as_tensor(idx_i).to(torch.int64)
+    idx_j = torch.as_tensor(idx_j).to(torch.int64)
+    point_mask = (z != 0).to(dtype)                                           # stacknet.py:130
+    pair_mask = (idx_i != -1).to(dtype)                                       # stacknet.py:131
+    geo = geometry_embed(cfg, idx_i, idx_j, pair_mask, dtype, R=R, cell=cell, cell_offset=cell_offset,
+                         displacements=displacements)
+    if record is not None:
+        record['geo'] = geo
+    chi = torch.zeros(z.shape[0], cfg.M, dtype=dtype)                         # embed.py:196-197
+    x = safe_scale(_t(params, 'embed/embedding', dtype)[z], point_mask[:, None])   # embed.py:227-229
+    x = x / math.sqrt(1.0)                                                    # stacknet.py:73 (one embed)
+    for t in range(cfg.n_layers):
+        x, chi = so3krates_layer(cfg, params, t, x, chi, geo, idx_i, idx_j, pair_mask, record)
+    e = mlp2(x, _t(params, 'energy/layers_0/kernel', dtype), _t(params, 'energy/layers_0/bias', dtype),
+             _t(params, 'energy/layers_1/kernel', dtype), _t(params, 'energy/layers_1/bias', dtype)).squeeze(-1)
+    e = _t(params, 'energy/per_atom_scale', dtype)[z] * e + _t(params, 'energy/per_atom_shift', dtype)[z]  # :78
+    e = safe_scale(e, point_mask)                                             # :79
+    return e
+
+
+def energy_forces(cfg: OracleConfig, params, R, z, idx_i, idx_j, dtype=torch.float64, cell=None,
+                  cell_offset=None, record: Optional[dict] = None):
+    """get_obs_and_force_fn (observable_function.py:127-149) for one structure:
+    returns E (scalar), F (n,3) = -dE/dR, e_atom (n,)."""
+    R_t = torch.as_tensor(np.asarray(R), dtype=dtype).clone().requires_grad_(True)
+    cell_t = None if cell is None else torch.as_tensor(np.asarray(cell), dtype=dtype)
+    off_t = None if cell_offset is None else torch.as_tensor(np.asarray(cell_offset))
+    e = forward(cfg, params, z, idx_i, idx_j, dtype, R=R_t, cell=cell_t, cell_offset=off_t, record=record)
+    E = e.sum()
+    (g,) = torch.autograd.grad(E, R_t)
+    return E.detach(), (-g).detach(), e.detach()
+
+
+def energy_forces_batch(cfg, params, R, z, idx_i, idx_j, dtype=torch.float64, cell=None, cell_offset=None):
+    """jax.vmap(obs_fn, in_axes=(None, 0)) over a padded batch: R (B,n,3), z (B,n), idx (B,P)."""
+    Es, Fs = [], []
+    for b in range(len(R)):
+        E, F, _ = energy_forces(cfg, params, R[b], z[b], idx_i[b], idx_j[b], dtype,
+                                None if cell is None else cell[b],
+                                None if cell_offset is None else cell_offset[b])
+        Es.append(E)
+        Fs.append(F)
+    return torch.stack(Es)[:, None], torch.stack(Fs)
+
+
+def potential_displacements(cfg, params, edges, z, centers, others, mask, dtype=torch.float64,
+                            energy_scale: float = 1.0):
+    """MLFFPotential.potential_fn (mlff_potential.py:95-109): per-atom energies from a Graph in the
+    'displacements' convention, plus dE/d(edges) (what the MD caller back-propagates)."""
+    edges_t = torch.as_tensor(np.asarray(edges), dtype=dtype).clone().requires_grad_(True)
+    mask = torch.as_tensor(np.asarray(mask)).bool()
+    ii = torch.where(mask, torch.as_tensor(np.asarray(centers)).long(), torch.tensor(-1))
+    jj = torch.where(mask, torch.as_tensor(np.asarray(others)).long(), torch.tensor(-1))
+    e = forward(cfg, params, z, ii, jj, dtype, displacements=edges_t) * energy_scale
+    (g,) = torch.autograd.grad(e.sum(), edges_t)
+    return e.detach(), g.detach()
+
+
+# --------------------------------------------------------------------------------------
+# neighbour lists
+# --------------------------------------------------------------------------------------
+def get_indices(R: np.ndarray, z: np.ndarray, r_cut: float) -> Dict[str, np.ndarray]:
+    """mlff/indexing/indices.py:15-84, non-periodic: all (i,j) with 0 < d_ij <= r_cut and
+    z_i*z_j != 0, row-major order, padded with -1 to the longest list in the batch.
+    R (B,n,3), z (B,n).  Distances are evaluated in the dtype of R (the reference evaluates
+    them under jax.jit, i.e. float32 unless x64 is enabled; pass float32 R to mirror that)."""
+    B, n = R.shape[0], R.shape[1]
+    lists = []
+    for b in range(B):
+        dv = R[b][:, None, :] - R[b][None, :, :]
+        D = (dv ** 2).sum(-1)
+        D = np.where(D > 0, np.sqrt(np.where(D > 0, D, 1.0)), 0.0).astype(R.dtype)     # metric.py:101-102
+        msk = (np.outer(z[b], z[b]) != 0)
+        Dm = D * msk
+        keep = (Dm <= r_cut) & (Dm > 0)
+        ii, jj = np.nonzero(keep)                                                     # row-major
+        lists.append((ii, jj))
+    pmax = max(len(a) for a, _ in lists)
+    idx_i = -np.ones((B, pmax), dtype=np.int64)
+    idx_j = -np.ones((B, pmax), dtype=np.int64)
+    for b, (ii, jj) in enumerate(lists):
+        idx_i[b, :len(ii)] = ii
+        idx_j[b, :len(jj)] = jj
+    return {'idx_i': idx_i, 'idx_j': idx_j}
+
+
+def primitive_neighbor_list(pos: np.ndarray, cell: np.ndarray, pbc: Sequence[bool], cutoff: float
+                            ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Brute-force restatement of what the reference obtains from
+    ``ase.neighborlist.primitive_neighbor_list('ijS', pbc, cell, positions, cutoff,
+    self_interaction=False)`` (third-party, ASE 3.22.x; call sites indices.py:216-224, 254-262):
+    the set {(i, j, S)}, S integer cell shifts (0 along non-periodic axes), with
+    |R_j - R_i + S @ cell| < cutoff (strict, float64, cell rows = lattice vectors) and
+    (i != j or S != 0).  Sorted by (i, j, S).  O(n^2 * images): small systems only."""
+    pos = np.asarray(pos, dtype=np.float64)
+    cell = np.asarray(cell, dtype=np.float64)
+    n = len(pos)
+    pbc = [bool(b) for b in pbc]
+    # number of images needed along each axis: face-to-face height of the cell
+    nmax = [0, 0, 0]
+    if any(pbc):
+        vol = abs(np.linalg.det(cell))
+        for a in range(3):
+            if pbc[a]:
+                cr = np.cross(cell[(a + 1) % 3], cell[(a + 2) % 3])
+                height = vol / np.linalg.norm(cr)
+                nmax[a] = int(math.ceil(cutoff / height)) + 1
+    out = []
+    # ASE wraps nothing: positions outside the cell are legal, shifts absorb it.  To stay exact
+    # for such inputs the image range is widened by the span of fractional coordinates.
+    if any(pbc):
+        frac = np.linalg.solve(cell.T, pos.T).T
+        span = np.ceil(frac.max(0) - frac.min(0)).astype(int)
+        for a in range(3):
+            if pbc[a]:
+                nmax[a] += int(span[a])
+    for s0 in range(-nmax[0], nmax[0] + 1):
+        for s1 in range(-nmax[1], nmax[1] + 1):
+            for s2 in range(-nmax[2], nmax[2] + 1):
+                S = np.array([s0, s1, s2])
+                off = S @ cell
+                dv = pos[None, :, :] - pos[:, None, :] + off[None, None, :]      # [i, j] = R_j - R_i + S@cell
+                d = np.sqrt((dv * dv).sum(-1))
+                keep = d < cutoff
+                if s0 == 0 and s1 == 0 and s2 == 0:
+                    keep &= ~np.eye(n, dtype=bool)
+                ii, jj = np.nonzero(keep)
+                for a, b in zip(ii, jj):
+                    out.append((a, b, s0, s1, s2))
+    out.sort()
+    arr = np.asarray(out, dtype=np.int64).reshape(-1, 5)
+    return arr[:, 0], arr[:, 1], arr[:, 2:5]
+
+
+def mic_neighbor_list(pos: np.ndarray, cell: Optional[np.ndarray], cutoff: float
+                      ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """glp ``quadratic_neighbor_list`` + ``make_displacement`` semantics as used by the MD path
+    (mdx/atoms.py:488-529, mdx/calculator.py:116-135; third-party glp, unpinned -- parity
+    unpinned): single minimum-image neighbour per ordered pair, d < cutoff, i != j.
+    ``cell`` rows = lattice vectors here.  Returns centers, others, edges = MIC(R_j - R_i)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    dv = pos[None, :, :] - pos[:, None, :]
+    if cell is not None:
+        cell = np.asarray(cell, dtype=np.float64)
+        frac = np.linalg.solve(cell.T, dv.reshape(-1, 3).T).T
+        frac -= np.floor(frac + 0.5)
+        dv = (frac @ cell).reshape(dv.shape)
+    d = np.sqrt((dv * dv).sum(-1))
+    keep = (d < cutoff) & ~np.eye(len(pos), dtype=bool)
+    ii, jj = np.nonzero(keep)
+    return ii, jj, dv[ii, jj]
