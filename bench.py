@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- SO3krates energy+force throughput (atom-steps/s) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c5|c1] [--impl ours|reference]
+
+Workloads (synthetic seeded positions, random-init weights):
+  c4  100 000-atom periodic box (100 A, water-like composition), default model F=132 L=3 r_cut=5   [default]
+  c3  3 000-atom periodic water box (31.072 A)
+  c5  1 000 atoms, F=256, degrees [1,2,3,4]
+  c1  32 x 9-atom ethanol-sized molecules (latency-bound; fits in L2)
+A step = one pass of the hot path: device neighbour list (cell list) -> CSR -> L layers -> read-out -> analytic
+forces.  `value` times steps with the positions already resident in HBM (CUDA events, max over ranks);
+`e2e` times the public calculator call with HOST numpy buffers (pinned H2D of positions, D2H of energy+forces).
+N > 1: the path has no collective in this round -- every rank runs an independent replica of the workload
+("replicas", weak scaling); domain decomposition of c4 with halo exchange is the next multi-GPU row.
+`--impl reference`: the reference is pure Python on JAX (not installable here), so the arm times the float32
+oracle restatement (torch-CPU, all host threads) on a bounded sub-box of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+from common import jittered_lattice, water_like_numbers  # noqa: E402
+
+WORKLOADS = {
+    'c4': dict(n_atoms=100_000, box=100.0, F=132, degrees=(1, 2, 3), L=3, seed=3, desc='100k-atom periodic box, E+F'),
+    'c3': dict(n_atoms=3_000, box=31.072, F=132, degrees=(1, 2, 3), L=3, seed=2, desc='3k-atom periodic water box, E+F'),
+    'c5': dict(n_atoms=1_000, box=21.544, F=256, degrees=(1, 2, 3, 4), L=3, seed=4, desc='1k atoms, F=256, L_max=4, E+F'),
+    'c1': dict(n_atoms=288, box=None, F=132, degrees=(1, 2, 3), L=3, seed=0, desc='32 x 9-atom molecules, E+F'),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+def build_inputs(w, rank=0):
+    if w['box'] is None:
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ethanol_32.npz'))
+        pos = (g['R'] + np.arange(32)[:, None, None] * 50.0).reshape(-1, 3)     # 32 molecules 50 A apart
+        z = np.tile(g['z'], 32)
+        return pos.astype(np.float64), z.astype(np.int64), None, (False, False, False)
+    pos = jittered_lattice(w['n_atoms'], w['box'], seed=w['seed'] + 1000 * rank)
+    if w['n_atoms'] == 3000:
+        z = np.where(np.arange(w['n_atoms']) % 3 == 0, 8, 1).astype(np.int64)
+    else:
+        z = water_like_numbers(w['n_atoms'], w['seed'])
+    return pos, z, np.eye(3) * w['box'], (True, True, True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        rows = [r.strip().split(',') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+                for k, nm in enumerate(names):
+                    if 'Active' in r[5 + k] and 'Not' not in r[5 + k]:
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            hi = sorted(sm)[len(sm) // 2:]        # under-load half
+            out = {'sm_mhz': float(np.median(hi)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                   'samples': len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def oracle_sample(w, n_sample, threads):
+    """float32 oracle (torch-CPU) on a bounded sub-box of the workload: returns a callable doing one E+F."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import so3k_oracle as o
+    torch.set_num_threads(threads)
+    cfg = o.OracleConfig(F=w['F'], degrees=w['degrees'], n_layers=w['L'])
+    p = o.init_params(cfg, 0)
+    if w['box'] is None:
+        pos, z, cell, pbc = build_inputs(w)
+        n_sample = len(pos)
+        ii, jj, S = o.primitive_neighbor_list(pos, np.eye(3), (False,) * 3, cfg.r_cut)
+        cell = None
+    else:
+        box = w['box'] * (n_sample / w['n_atoms']) ** (1.0 / 3.0)        # same density
+        pos = jittered_lattice(n_sample, box, seed=w['seed'])
+        z = water_like_numbers(n_sample, w['seed'])
+        cell = np.eye(3) * box
+        ii, jj, S = o.periodic_neighbor_list_kdtree(pos, box, cfg.r_cut)
+
+    def step():
+        E, F, _ = o.energy_forces(cfg, p, pos, z, ii, jj, dtype=torch.float32, cell=cell, cell_offset=S if cell is not None else None)
+        return float(E)
+    return step, n_sample, len(ii)
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = min(w['n_atoms'], 2000)
+    step, n_sample, n_edges = oracle_sample(w, n_sample, threads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_sample / dt
+    line = {'impl': 'reference', 'metric': 'SO3krates energy+force atom-steps/s', 'value': val, 'unit': 'atom-steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'description': w['desc'], 'F': w['F'], 'n_layers': w['L'],
+                       'degrees': list(w['degrees']), 'r_cut': 5.0},
+            'cpu_baseline': {'value': val, 'unit': 'atom-steps/s', 'cores': threads, 'kind': 'port',
+                             'sample': f'{n_sample}-atom sub-box at the workload density ({n_edges} edges), float32 oracle '
+                                       f'restatement on torch-CPU (the JAX reference is not installable here)'},
+            'e2e': {'value': val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.calculator import mlffCalculator
+    from mlff_b200 import params as P
+    from mlff_b200.capi import NL_ASE
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = f'cuda:{local}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    cfg = So3kratesConfig(F=w['F'], n_layer=w['L'], degrees=w['degrees'])
+    prm = P.init_params(cfg, 0)
+    rng = np.random.default_rng(7)
+    for k in prm:                                  # exercise the bias paths too
+        if k.endswith('/bias'):
+            prm[k] = rng.normal(0, 0.01, prm[k].shape).astype(np.float32)
+    flags = 1 if args.tensor else 0
+    calc = mlffCalculator(cfg, prm, device=dev, flags=flags)
+    eng = calc.engine
+    pos, z, cell, pbc = build_inputs(w, rank)
+    N = len(pos)
+    periodic = cell is not None
+
+    # ---- warm-up through the public call (sizes the neighbour-list capacity) ----------------------------
+    res = calc.calculate(pos, z, cell=cell, pbc=pbc)
+    n_edges = calc.n_edges
+    cap = calc.capacity
+    pos_d = torch.as_tensor(pos, device=dev)
+    z_d = torch.as_tensor(z, device=dev, dtype=torch.int32)
+    cell32 = None if not periodic else torch.as_tensor(cell, dtype=torch.float32, device=dev)[None]
+
+    def step_resident():
+        ii, jj, S, count = eng.neighbor_list(pos_d, calc.cutoff, cap, cell=cell, pbc=pbc, mode=NL_ASE)
+        R32 = pos_d.to(torch.float32)
+        return eng.energy_forces(R32[None], z_d[None], ii[None], jj[None], cell32, S[None] if periodic else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    # ---- timed region: K steps, CUDA events, per-kernel-category events inside libso3k --------------------
+    eng.lib.profile_collect(eng.h, reset=True)
+    eng.lib.profile_enable(eng.h, True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    nl_ev = []
+    l0 = eng.lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = eng.lib.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    prof = eng.lib.profile_collect(eng.h, reset=True)
+    eng.lib.profile_enable(eng.h, False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * N / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers through the public calculator call ---------------------------------------------
+    for _ in range(2):
+        calc.calculate(pos, z, cell=cell, pbc=pbc)
+    barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        res = calc.calculate(pos, z, cell=cell, pbc=pbc)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / k_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = world * N / float(t_e2e.item())
+    h2d = N * 3 * 8 + N * 4
+    d2h = (N * 3 + 2) * 8
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        nl_ = len(w['degrees'])
+        Fd, K = w['F'], 32
+        flop_block = 2.0 * n_edges * (K * Fd + Fd * Fd + nl_ * (Fd // 4) + (Fd // 4) * Fd)     # SURVEY 8(d), per block
+        # dominant kernel: the edge backward (recompute + transposed GEMMs).  Algorithmic FLOPs per launch:
+        # forward filter (both blocks) + W2^T GEMM + forward-mode radial GEMM + sph-branch transposes
+        #   = 2 blocks x [fwd + (F*KC) + (K*F)] ~ 2 x flop_block x (1 + (F^2+F*F/4+K*F)/(K*F+F^2+...)) -- we count
+        # conservatively: bwd launch = 2 x (2 x flop_block) ; fwd launch = 2 x flop_block.
+        ms_bwd, n_bwd = prof['edge_bwd']
+        ms_fwd, n_fwd = prof['edge_fwd']
+        dom = 'edge_bwd' if ms_bwd >= ms_fwd else 'edge_fwd'
+        flops_launch = (4.0 if dom == 'edge_bwd' else 2.0) * flop_block
+        ms_launch = (ms_bwd / max(n_bwd, 1)) if dom == 'edge_bwd' else (ms_fwd / max(n_fwd, 1))
+        tf = flops_launch / (ms_launch * 1e-3) / 1e12 if ms_launch > 0 else 0.0
+        peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+        roof = {'kernel': f'k_{dom}', 'bound': 'tensor', 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': tf / peak_tf, 'traffic': None, 'peak_kind': f'{pk_kind} sustained bf16 (kernel timed inside a long step)',
+                'ms_per_launch': ms_launch, 'flops_per_launch': flops_launch,
+                'share_of_step': (ms_bwd if dom == 'edge_bwd' else ms_fwd) / (ms_total if ms_total > 0 else 1.0)}
+        # HBM-bound side kernels (compulsory-traffic bytes): aggregation
+        ms_agg, n_agg = prof['aggregate']
+        agg_bytes = (4 * 8 + 4 + 16) * n_edges + (8 * Fd + 8 * sum(2 * l + 1 for l in w['degrees']) + 4) * N + 4 * Fd * N
+        agg = {'kernel': 'k_aggregate', 'bound': 'hbm', 'achieved': agg_bytes / (ms_agg / max(n_agg, 1) * 1e-3) / 1e9 if ms_agg > 0 else 0.0,
+               'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
+        agg['frac'] = agg['achieved'] / agg['peak']
+        # CPU baseline: bounded sample, all host threads
+        threads = os.cpu_count() or 1
+        cpu = None
+        if not args.no_cpu_baseline:
+            n_s = min(N, 2000)
+            step, n_s, n_e = oracle_sample(w, n_s, threads)
+            step()
+            reps, t0 = 0, time.perf_counter()
+            while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+                step()
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+            cpu = {'value': n_s / dt, 'unit': 'atom-steps/s', 'cores': threads, 'kind': 'port',
+                   'sample': f'{n_s}-atom sub-box at the workload density ({n_e} edges), {reps} E+F evaluations of the '
+                             f'float32 oracle restatement on torch-CPU (JAX reference not installable)'}
+        line = {'metric': 'SO3krates energy+force atom-steps/s', 'value': value, 'unit': 'atom-steps/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'description': w['desc'], 'n_atoms': N, 'n_edges': int(n_edges),
+                           'F': w['F'], 'n_layers': w['L'], 'degrees': list(w['degrees']), 'r_cut': 5.0,
+                           'parallelism': 'single' if world == 1 else f'replicas x{world} (no collective)',
+                           'filter_gemm': 'tcgen05 split-operand' if args.tensor else 'fp32 CUDA-core',
+                           'l2': 'working set (edge + node arrays) larger than the 126 MB L2' if N >= 50_000 else
+                                 'working set fits in L2 (latency/L2-bound configuration)'},
+                'e2e': {'value': e2e_val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_aggregate': agg,
+                'cpu_baseline': cpu,
+                'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
+                'energy_check': float(res['energy'])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--tensor', action='store_true', help='tcgen05 split-operand filter GEMMs')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -174,6 +174,13 @@ int so3k_neighbor_list(int32_t mode, int64_t N, const double* positions, const i
 /* ---- instrumentation ------------------------------------------------------------------------
  * Number of kernels this library has launched since process start (bench.py's gpu_launches). */
 uint64_t so3k_launch_count(void);
+/* Optional per-kernel-category timing with CUDA events recorded on the caller's stream around the launches of
+ * so3k_energy_forces / so3k_potential_displacements.  so3k_profile_categories() returns the comma-separated
+ * category names; so3k_profile_collect SYNCHRONISES on the recorded events and returns accumulated milliseconds
+ * and scope counts per category (n_categories >= number of names). */
+const char* so3k_profile_categories(void);
+int so3k_profile_enable(so3k_handle* h, int32_t enable);
+int so3k_profile_collect(so3k_handle* h, double* ms, int64_t* count, int32_t n_categories, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,8 @@ NL_DENSE = 1
 # every symbol include/so3k.h declares (checked by tests/test_capi.py)
 EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 'so3k_param_lookup',
            'so3k_load_params', 'so3k_workspace_bytes', 'so3k_energy_forces', 'so3k_potential_displacements',
-           'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count']
+           'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count',
+           'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect']
 
 
 class So3kConfigC(C.Structure):
@@ -76,6 +77,12 @@ class So3kLib:
         d.so3k_neighbor_list.restype = C.c_int
         d.so3k_launch_count.argtypes = []
         d.so3k_launch_count.restype = C.c_uint64
+        d.so3k_profile_categories.argtypes = []
+        d.so3k_profile_categories.restype = C.c_char_p
+        d.so3k_profile_enable.argtypes = [vp, i32]
+        d.so3k_profile_enable.restype = C.c_int
+        d.so3k_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32, i32]
+        d.so3k_profile_collect.restype = C.c_int
 
     # ---- handle -----------------------------------------------------------------------------
     def create(self, F: int, n_rbf: int, n_layers: int, n_heads: int, degrees: Sequence[int], r_cut: float,
@@ -142,3 +149,13 @@ class So3kLib:
 
     def launch_count(self) -> int:
         return int(self.dll.so3k_launch_count())
+
+    def profile_enable(self, h: int, on: bool):
+        _check(self.dll.so3k_profile_enable(h, 1 if on else 0), 'so3k_profile_enable')
+
+    def profile_collect(self, h: int, reset: bool = True):
+        names = self.dll.so3k_profile_categories().decode().split(',')
+        ms = (C.c_double * len(names))()
+        cnt = (C.c_int64 * len(names))()
+        _check(self.dll.so3k_profile_collect(h, ms, cnt, len(names), 1 if reset else 0), 'so3k_profile_collect')
+        return {n: (float(ms[k]), int(cnt[k])) for k, n in enumerate(names)}

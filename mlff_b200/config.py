@@ -1,0 +1,95 @@
+"""Hyper-parameters of the SO3krates model, mirroring the reference's constructor and JSON schema.
+
+  So3krates(...)                       mlff/nn/representation/so3krates.py:13-67
+  hyperparameters.json -> stack_net    mlff/nn/stacknet/stacknet.py:89-106, 135-145
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence
+
+md17_property_keys = {'energy': 'E', 'force': 'F', 'atomic_type': 'z', 'atomic_position': 'R', 'hirshfeld_volume': 'V_eff',
+                      'total_charge': 'Q', 'total_spin': 'S', 'partial_charge': 'q', 'idx_i': 'idx_i', 'idx_j': 'idx_j',
+                      'unit_cell': 'unit_cell', 'cell_offset': 'cell_offset', 'node_mask': 'node_mask',
+                      'stress': 'stress', 'pbc': 'pbc', 'displacement_vector': 'displacements',
+                      'atomic_energy': 'atomic_energy'}
+
+
+@dataclass
+class So3kratesConfig:
+    F: int = 132
+    n_layer: int = 6                      # python-API default (so3krates.py:16); the CLI default is 3
+    degrees: Sequence[int] = (1, 2, 3)
+    n_heads: int = 4
+    n_rbf: int = 32
+    r_cut: float = 5.0
+    num_embeddings: int = 100
+    mic: bool = False
+    prop_keys: Dict[str, str] = field(default_factory=lambda: dict(md17_property_keys))
+
+    def validate(self):
+        unsupported = []
+        if self.F % self.n_heads or self.F % len(self.degrees):
+            raise ValueError('F must be divisible by n_heads and by len(degrees) (equal_head_split, '
+                             'so3krates_layer.py:611-615)')
+        if any(l < 0 or l > 4 for l in self.degrees):
+            raise NotImplementedError('Spherical harmonics are only defined up to order l = 4.')
+        return unsupported
+
+    @property
+    def M(self) -> int:
+        return sum(2 * int(l) + 1 for l in self.degrees)
+
+    # ---- hyperparameters.json -----------------------------------------------------------------
+    @classmethod
+    def from_hyperparameters(cls, h: Dict) -> 'So3kratesConfig':
+        """Parse the dict the reference writes with StackNet.to_json (stacknet.py:89-111)."""
+        sn = h['stack_net'] if 'stack_net' in h else h
+        geo = next(iter(sn['geometry_embeddings'][0].values()))
+        feat = next(iter(sn['feature_embeddings'][0].values()))
+        layers = [next(iter(x.values())) for x in sn['layers']]
+        l0 = layers[0]
+        checks = {
+            'radial_basis_function': (geo.get('radial_basis_function', 'phys'), ('phys',)),
+            'radial_cutoff_fn': (geo.get('radial_cutoff_fn', 'cosine_cutoff_fn'), ('cosine_cutoff_fn',)),
+            'sphc_normalization': (geo.get('sphc_normalization', None), (None,)),
+            'solid_harmonic': (geo.get('solid_harmonic', False), (False,)),
+            'fb_filter': (l0.get('fb_filter', 'radial_spherical'), ('radial_spherical',)),
+            'gb_filter': (l0.get('gb_filter', 'radial_spherical'), ('radial_spherical',)),
+            'layer_normalization': (l0.get('layer_normalization', False), (False,)),
+            'residual_mlp_1': (l0.get('residual_mlp_1', False), (False,)),
+            'residual_mlp_2': (l0.get('residual_mlp_2', False), (False,)),
+        }
+        for k, (v, ok) in checks.items():
+            if v not in ok:
+                raise NotImplementedError(f'hyper-parameter {k}={v!r} is outside the hot path implemented by mlff_b200')
+        F = int(feat['features'])
+        if list(l0['fb_rad_filter_features']) != [F, F] or list(l0['fb_sph_filter_features']) != [int(F / 4), F]:
+            raise NotImplementedError('only the default filter widths [F,F] / [F/4,F] are implemented')
+        return cls(F=F, n_layer=len(layers), degrees=tuple(int(x) for x in geo['degrees']),
+                   n_heads=int(l0.get('n_heads', 4)), n_rbf=int(geo['n_rbf']), r_cut=float(geo['r_cut']),
+                   num_embeddings=int(feat.get('num_embeddings', 100)), mic=bool(geo.get('mic', False)),
+                   prop_keys=dict(sn.get('prop_keys', md17_property_keys)))
+
+    def to_hyperparameters(self) -> Dict:
+        """The same nested dict StackNet.__dict_repr__ produces (stacknet.py:89-106)."""
+        F = self.F
+        layer = {'so3krates_layer': {
+            'fb_filter': 'radial_spherical', 'fb_rad_filter_features': [F, F], 'fb_sph_filter_features': [int(F / 4), F],
+            'fb_attention': 'conv_att', 'gb_filter': 'radial_spherical', 'gb_rad_filter_features': [F, F],
+            'gb_sph_filter_features': [int(F / 4), F], 'gb_attention': 'conv_att', 'n_heads': self.n_heads,
+            'residual_mlp_1': False, 'residual_mlp_2': False, 'non_local_sphc': False, 'non_local_feature': False,
+            'fast_attention_kwargs': None, 'chi_cut': None, 'chi_cut_dynamic': False, 'degrees': list(self.degrees),
+            'parity': True, 'layer_normalization': False, 'sphc_normalization': False,
+            'neighborhood_normalization': False, 'final_layer': False}}
+        geo = {'geometry_embed': {'degrees': list(self.degrees), 'radial_basis_function': 'phys', 'n_rbf': self.n_rbf,
+                                  'radial_cutoff_fn': 'cosine_cutoff_fn', 'r_cut': self.r_cut, 'sphc': True,
+                                  'sphc_normalization': None, 'solid_harmonic': False, 'mic': self.mic,
+                                  'input_convention': 'positions', 'prop_keys': self.prop_keys}}
+        feat = {'atom_type_embed': {'num_embeddings': self.num_embeddings, 'features': F, 'prop_keys': self.prop_keys}}
+        obs = {'energy': {'per_atom_scale': None, 'per_atom_shift': None, 'num_embeddings': self.num_embeddings,
+                          'output_convention': 'per_structure', 'zbl_repulsion': False, 'zbl_repulsion_shift': 0.0,
+                          'prop_keys': self.prop_keys}}
+        return {'stack_net': {'geometry_embeddings': [geo], 'feature_embeddings': [feat],
+                              'layers': [layer for _ in range(self.n_layer)], 'observables': [obs],
+                              'prop_keys': self.prop_keys, 'n_layers': self.n_layer}}

@@ -17,10 +17,63 @@ void so3k_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 
+enum { CAT_GRAPH = 0, CAT_EMBED, CAT_NODE_PROJ, CAT_EDGE_FWD, CAT_AGGREGATE, CAT_INTERACTION, CAT_READOUT,
+       CAT_INTERACTION_BWD, CAT_ALPHA_BWD, CAT_EDGE_BWD, CAT_CHI_BWD, CAT_NODE_PROJ_BWD, CAT_FORCES, CAT_COUNT };
+const char* const kCatNames =
+    "graph,embed,node_proj,edge_fwd,aggregate,interaction,readout,interaction_bwd,alpha_bwd,edge_bwd,chi_bwd,"
+    "node_proj_bwd,forces";
+
+// Optional per-kernel-category timing with CUDA events on the caller's stream (bench.py's roofline numbers).
+struct Profiler {
+  bool on = false;
+#ifndef SO3K_EMU
+  std::vector<cudaEvent_t> ev;       // pairs (start, stop)
+  std::vector<int> cat;
+  size_t used = 0;
+#endif
+  double ms[CAT_COUNT] = {0};
+  long long cnt[CAT_COUNT] = {0};
+};
+
 struct HandleImpl : so3k_handle {
   float* repack = nullptr;
   std::vector<EdgeBlockW> wf, wg;    // per layer
+  Profiler prof;
 };
+
+struct Scope {
+  Profiler& p;
+  cudaStream_t st;
+  size_t slot = 0;
+  bool active = false;
+  Scope(Profiler& p_, int c, cudaStream_t st_) : p(p_), st(st_) {
+#ifndef SO3K_EMU
+    if (p.on) {
+      if (p.used + 2 > p.ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        p.ev.push_back(a);
+        p.ev.push_back(b);
+        p.cat.push_back(c);
+      }
+      slot = p.used;
+      p.cat[slot / 2] = c;
+      p.used += 2;
+      cudaEventRecord(p.ev[slot], st);
+      active = true;
+    }
+#else
+    (void)c;
+#endif
+  }
+  ~Scope() {
+#ifndef SO3K_EMU
+    if (active) cudaEventRecord(p.ev[slot + 1], st);
+#endif
+  }
+};
+#define PROF(cat) Scope _scope_##cat(h->prof, cat, st)
 
 bool make_dims(const so3k_config& c, So3kDims* D) {
   if (c.F <= 0 || c.n_rbf <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_degrees <= 0) return false;
@@ -179,8 +232,8 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
   const size_t Ast = (D.H + D.nl + 3) & ~3;
   const size_t Pe = Pt > 0 ? Pt : 1;
 
-  so3k_build_graph(D, B, n, P, R, idx_i, idx_j, cell, cell_offset, disp, mask, w.g, w.scratch, dev_status, st);
-  so3k_launch_embed(D, N, z, prm + h->layout.embed, w.x, w.chi, dev_status, st);
+  { PROF(CAT_GRAPH); so3k_build_graph(D, B, n, P, R, idx_i, idx_j, cell, cell_offset, disp, mask, w.g, w.scratch, dev_status, st); }
+  { PROF(CAT_EMBED); so3k_launch_embed(D, N, z, prm + h->layout.embed, w.x, w.chi, dev_status, st); }
 
   // ---- forward ----------------------------------------------------------------------------------------
   for (int t = 0; t < D.L; ++t) {
@@ -188,9 +241,10 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
     float* xt = w.x + (size_t)t * N * F;
     float* ct = w.chi + (size_t)t * N * M;
     float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
-    so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st);
-    so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
-    so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+    { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
+    { PROF(CAT_EDGE_FWD); so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st); }
+    { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
+    PROF(CAT_INTERACTION);
     so3k_launch_interaction(D, N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + (size_t)N * F, ct + (size_t)N * M,
                             w.bcoef + (size_t)t * N * nl, st);
   }
@@ -199,8 +253,11 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
   float* xbar_nx = w.xbar_b;
   float* chibar = w.chibar_a;
   float* chibar_nx = w.chibar_b;
-  so3k_launch_readout(D, N, w.x + (size_t)D.L * N * F, z, prm, h->layout, out_scale, e_atom, xbar, st);
-  if (E) so3k_launch_energy_sum(B, n, e_atom, E, st);
+  {
+    PROF(CAT_READOUT);
+    so3k_launch_readout(D, N, w.x + (size_t)D.L * N * F, z, prm, h->layout, out_scale, e_atom, xbar, st);
+    if (E) so3k_launch_energy_sum(B, n, e_atom, E, st);
+  }
   if (!forces && !dE_dedges) return SO3K_OK;
 
   // ---- reverse sweep ------------------------------------------------------------------------------------
@@ -212,21 +269,21 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
     const float* ct = w.chi + (size_t)t * N * M;
     const float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
     // interaction block: (xbar, chibar) -> (xbar1, chibar1) written to the "next" buffers
-    so3k_launch_interaction_bwd(D, N, w.chi1 + (size_t)t * N * M, w.bcoef + (size_t)t * N * nl, prm, lp, xbar, chibar,
-                                xbar_nx, chibar_nx, st);
-    so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st);
+    { PROF(CAT_INTERACTION_BWD); so3k_launch_interaction_bwd(D, N, w.chi1 + (size_t)t * N * M, w.bcoef + (size_t)t * N * nl, prm, lp, xbar, chibar,
+                                xbar_nx, chibar_nx, st); }
+    { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
     cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
-    so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, xbar_nx, chibar_nx, w.alphabar, w.gproj, st);
-    so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, w.alphabar, chibar_nx, w.gproj, w.gbar,
-                         w.rbar, st);
+    { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, xbar_nx, chibar_nx, w.alphabar, w.gproj, st); }
+    { PROF(CAT_EDGE_BWD); so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, w.alphabar, chibar_nx, w.gproj, w.gbar,
+                         w.rbar, st); }
     if (t > 0) {
       // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
-      so3k_launch_chi_bwd(D, w.g, ct, w.gbar, chibar_nx, chibar, st);      // chibar <- d/d chi_t
-      so3k_launch_node_proj_bwd(D, N, w.gproj, prm, lp, xbar_nx, st);      // xbar_nx += projections^T
+      { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, chibar_nx, chibar, st); }      // chibar <- d/d chi_t
+      { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, N, w.gproj, prm, lp, xbar_nx, st); }      // xbar_nx += projections^T
       float* tmp = xbar; xbar = xbar_nx; xbar_nx = tmp;                     // xbar <- d/d x_t
     }
   }
-  so3k_launch_forces(D, w.g, Pt, w.rbar, forces, dE_dedges, st);
+  { PROF(CAT_FORCES); so3k_launch_forces(D, w.g, Pt, w.rbar, forces, dE_dedges, st); }
   return SO3K_OK;
 }
 
@@ -342,6 +399,38 @@ int so3k_featurise(const so3k_handle* h, int32_t n, int32_t P, const float* R, c
   so3k_launch_featurise(h->dims, n, P, R, idx_i, idx_j, cell, cell_offset, displacements, rbf, phi, d, unit, sph,
                         (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+// ---- instrumentation ----------------------------------------------------------------------------------
+const char* so3k_profile_categories(void) { return kCatNames; }
+
+int so3k_profile_enable(so3k_handle* hh, int32_t enable) {
+  if (!hh) return SO3K_ERR_ARG;
+  static_cast<HandleImpl*>(hh)->prof.on = enable != 0;
+  return SO3K_OK;
+}
+
+// Waits for the recorded events (this call synchronises), adds their durations to the per-category totals and
+// copies the totals out: ms[c] (milliseconds) and count[c] (scopes) for the categories of so3k_profile_categories().
+int so3k_profile_collect(so3k_handle* hh, double* ms, int64_t* count, int32_t n_categories, int32_t reset) {
+  if (!hh || n_categories < CAT_COUNT) return SO3K_ERR_ARG;
+  Profiler& p = static_cast<HandleImpl*>(hh)->prof;
+#ifndef SO3K_EMU
+  for (size_t k = 0; k + 1 < p.used; k += 2) {
+    if (cudaEventSynchronize(p.ev[k + 1]) != cudaSuccess) return SO3K_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.ev[k], p.ev[k + 1]) != cudaSuccess) return SO3K_ERR_CUDA;
+    p.ms[p.cat[k / 2]] += t;
+    p.cnt[p.cat[k / 2]] += 1;
+  }
+  p.used = 0;
+#endif
+  for (int c = 0; c < CAT_COUNT; ++c) {
+    if (ms) ms[c] = p.ms[c];
+    if (count) count[c] = p.cnt[c];
+    if (reset) { p.ms[c] = 0; p.cnt[c] = 0; }
+  }
+  return SO3K_OK;
 }
 
 }  // extern "C"

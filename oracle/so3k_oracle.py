@@ -442,24 +442,18 @@ def primitive_neighbor_list(pos: np.ndarray, cell: np.ndarray, pbc: Sequence[boo
     cell = np.asarray(cell, dtype=np.float64)
     n = len(pos)
     pbc = [bool(b) for b in pbc]
-    # number of images needed along each axis: face-to-face height of the cell
+    # images needed along each axis: |S_a| <= cutoff / height_a + (extent of the fractional coordinates);
+    # ASE wraps nothing -- positions outside the cell are legal, the shifts absorb it.
     nmax = [0, 0, 0]
     if any(pbc):
         vol = abs(np.linalg.det(cell))
+        frac = np.linalg.solve(cell.T, pos.T).T
         for a in range(3):
             if pbc[a]:
                 cr = np.cross(cell[(a + 1) % 3], cell[(a + 2) % 3])
                 height = vol / np.linalg.norm(cr)
-                nmax[a] = int(math.ceil(cutoff / height)) + 1
+                nmax[a] = int(math.floor(cutoff / height + (frac[:, a].max() - frac[:, a].min()) + 1e-9))
     out = []
-    # ASE wraps nothing: positions outside the cell are legal, shifts absorb it.  To stay exact
-    # for such inputs the image range is widened by the span of fractional coordinates.
-    if any(pbc):
-        frac = np.linalg.solve(cell.T, pos.T).T
-        span = np.ceil(frac.max(0) - frac.min(0)).astype(int)
-        for a in range(3):
-            if pbc[a]:
-                nmax[a] += int(span[a])
     for s0 in range(-nmax[0], nmax[0] + 1):
         for s1 in range(-nmax[1], nmax[1] + 1):
             for s2 in range(-nmax[2], nmax[2] + 1):
@@ -476,6 +470,29 @@ def primitive_neighbor_list(pos: np.ndarray, cell: np.ndarray, pbc: Sequence[boo
     out.sort()
     arr = np.asarray(out, dtype=np.int64).reshape(-1, 5)
     return arr[:, 0], arr[:, 1], arr[:, 2:5]
+
+
+def periodic_neighbor_list_kdtree(pos: np.ndarray, box: float, cutoff: float
+                                  ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Same set as ``primitive_neighbor_list`` for a CUBIC box with box > 2*cutoff and pbc=TTT, found with a periodic
+    KD-tree (scipy) so that 10^5-atom systems are tractable on the CPU; candidates are re-tested with exactly the
+    formula of the brute-force version (|R_j - R_i + S@cell| < cutoff in float64), so the sets are identical."""
+    from scipy.spatial import cKDTree
+    pos = np.asarray(pos, dtype=np.float64)
+    assert box > 2 * cutoff
+    w = np.floor(pos / box)
+    tree = cKDTree(pos - w * box, boxsize=box)
+    pairs = tree.query_pairs(cutoff * (1 + 1e-9) + 1e-9, output_type='ndarray')
+    a = np.concatenate([pairs[:, 0], pairs[:, 1]])
+    b = np.concatenate([pairs[:, 1], pairs[:, 0]])
+    S = -np.round((pos[b] - pos[a]) / box).astype(np.int64)
+    cell = np.eye(3) * box
+    dv = pos[b] - pos[a] + S @ cell
+    d = np.sqrt((dv * dv).sum(-1))
+    keep = d < cutoff
+    a, b, S = a[keep], b[keep], S[keep]
+    order = np.lexsort((S[:, 2], S[:, 1], S[:, 0], b, a))
+    return a[order], b[order], S[order]
 
 
 def mic_neighbor_list(pos: np.ndarray, cell: Optional[np.ndarray], cutoff: float

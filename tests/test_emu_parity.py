@@ -1,0 +1,201 @@
+"""The SIMT kernels, executed on the CPU through the emulation layer (tests/emu), against the oracle.
+This exercises the same kernel SOURCE that nvcc compiles for sm_100a and the same C ABI, so indexing / masking /
+graph-construction logic is checked without a GPU.  The `-m gpu` suite repeats the comparison on the real device."""
+import numpy as np
+import pytest
+import torch
+
+import so3k_oracle as o
+from conftest import golden
+from emu_engine import EmuEngine, ptr, build_emu
+from mlff_b200.capi import So3kLib, NL_ASE, NL_DENSE, STATUS_ASYMMETRIC, STATUS_OVERFLOW
+from common import as_sets
+
+E_RTOL = 1e-5      # north_star: energies within 1e-5 relative
+F_ATOL = 1e-4      # north_star: forces within 1e-4 eV/A max-abs (fp32)
+
+
+def make(cfg, p):
+    eng = EmuEngine(cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads, cfg.degrees, cfg.r_cut)
+    eng.load(p)
+    return eng
+
+
+@pytest.mark.parametrize('F,degrees,H', [(36, (1, 2, 3), 4), (32, (1, 2, 2, 3), 4), (32, (1, 2, 3, 4), 2)])
+def test_featurise_matches_oracle(ethanol, F, degrees, H):
+    cfg = o.OracleConfig(F=F, degrees=degrees, n_heads=H, n_layers=1)
+    eng = make(cfg, o.init_params(cfg, 0))
+    R = ethanol['R'][0]
+    nl = o.get_indices(ethanol['R'][:1], ethanol['z'][None], 5.0)
+    ii = np.concatenate([nl['idx_i'][0], [-1, -1, -1]])
+    jj = np.concatenate([nl['idx_j'][0], [-1, -1, -1]])
+    out = eng.featurise(9, ii, jj, R=R)
+    geo = o.geometry_embed(cfg, torch.as_tensor(ii), torch.as_tensor(jj), torch.as_tensor((ii != -1).astype(np.float64)),
+                           torch.float64, R=torch.as_tensor(R))
+    np.testing.assert_allclose(out['d'], geo['d_ij'].numpy(), rtol=1e-6)
+    np.testing.assert_allclose(out['unit'], geo['unit_r_ij'].numpy(), atol=1e-6)
+    np.testing.assert_allclose(out['phi'], geo['phi_r_cut'].numpy(), atol=1e-6)
+    np.testing.assert_allclose(out['rbf'], geo['rbf_ij'].numpy(), atol=2e-6)
+    np.testing.assert_allclose(out['sph'], geo['sph_ij'].numpy(), atol=2e-6)
+    assert (out['rbf'][-3:] == 0).all() and (out['sph'][-3:] == 0).all() and (out['phi'][-3:] == 0).all()
+
+
+@pytest.mark.parametrize('F,L,degrees,H', [(132, 3, (1, 2, 3), 4), (36, 2, (1, 2, 3), 4), (32, 2, (1, 2, 2, 3), 4),
+                                           (64, 2, (1, 2, 3, 4), 4)])
+def test_energy_forces_match_oracle_ethanol(ethanol, F, L, degrees, H):
+    cfg = o.OracleConfig(F=F, n_layers=L, degrees=degrees, n_heads=H)
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    eng = make(cfg, p)
+    B = 2
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(R, z, 5.0)
+    E, Fo, ea, st = eng.energy_forces(R, z, nl['idx_i'], nl['idx_j'])
+    assert st == 0
+    Eo, Fr = o.energy_forces_batch(cfg, p, R, z, nl['idx_i'], nl['idx_j'])
+    np.testing.assert_allclose(E, Eo.numpy().reshape(-1), rtol=E_RTOL)
+    assert np.abs(Fo - Fr.numpy()).max() < F_ATOL
+    assert np.abs(Fo - Fr.numpy()).max() < 2e-5 * np.abs(Fr.numpy()).max()
+
+
+def test_golden_default_model(ethanol):
+    g = golden('oracle_ethanol_amplified.npz')
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+    eng = make(cfg, p)
+    z = np.tile(ethanol['z'][None], (4, 1))
+    E, F, ea, st = eng.energy_forces(ethanol['R'][:4], z, g['idx_i'], g['idx_j'])
+    np.testing.assert_allclose(E, g['E'].reshape(-1), rtol=E_RTOL)
+    assert np.abs(F - g['F']).max() < F_ATOL
+
+
+def test_padding_invariance_and_shuffled_edges(ethanol):
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p)
+    R = ethanol['R'][:1]
+    z = ethanol['z'][None]
+    nl = o.get_indices(R, z, 5.0)
+    E, F, _, _ = eng.energy_forces(R, z, nl['idx_i'], nl['idx_j'])
+    # extra zero-Z atoms, extra -1 edges, and a shuffled edge order (the engine sorts by receiver itself)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(72)
+    ii = np.concatenate([nl['idx_i'][0][perm][:30], [-1, -1], nl['idx_i'][0][perm][30:], [-1] * 3])[None]
+    jj = np.concatenate([nl['idx_j'][0][perm][:30], [-1, -1], nl['idx_j'][0][perm][30:], [-1] * 3])[None]
+    Rp = np.concatenate([R[0], np.zeros((3, 3))])[None]
+    zp = np.concatenate([z[0], [0, 0, 0]])[None]
+    Ep, Fp, _, st = eng.energy_forces(Rp, zp, ii, jj)
+    assert st == 0
+    np.testing.assert_allclose(Ep, E, rtol=2e-6)
+    np.testing.assert_allclose(Fp[0, :9], F[0], atol=2e-6)
+    assert (Fp[0, 9:] == 0).all()
+
+
+def test_periodic_solid_with_cell_offsets(solid):
+    g = golden('oracle_solid_pbc.npz')
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+    eng = make(cfg, p)
+    E, F, ea, st = eng.energy_forces(solid['R'][None], solid['z'][None], g['idx_i'][None], g['idx_j'][None],
+                                     cell=solid['unit_cell'][None], cell_offset=g['shifts'][None])
+    assert st == 0
+    assert abs(E[0] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
+    assert np.abs(F[0] - g['F']).max() < F_ATOL
+    np.testing.assert_allclose(ea[0], g['e_atom'], atol=2e-5)
+
+
+def test_md_seam_displacements(ethanol):
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p)
+    R = ethanol['R'][0]
+    z = ethanol['z']
+    nl = o.get_indices(R[None], z[None], 5.0)
+    ii, jj = nl['idx_i'][0], nl['idx_j'][0]
+    N = len(z)
+    # glp conventions: sentinel index N and a boolean mask
+    centers = np.concatenate([ii, [N, N]])
+    others = np.concatenate([jj, [N, N]])
+    edges = np.concatenate([R[jj] - R[ii], np.zeros((2, 3))])
+    mask = np.concatenate([np.ones(72, bool), [False, False]])
+    ea, dE, Fo, st = eng.potential(edges, z, centers, others, mask, energy_scale=1.7)
+    assert st == 0
+    ea_o, g_o = o.potential_displacements(cfg, p, edges, z, np.where(mask, centers, -1), np.where(mask, others, -1),
+                                          mask, energy_scale=1.7)
+    np.testing.assert_allclose(ea, ea_o.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dE, g_o.numpy(), rtol=2e-5, atol=5e-6)
+    _, F_o, _ = o.energy_forces(cfg, p, R, z, ii, jj)
+    np.testing.assert_allclose(Fo, 1.7 * F_o.numpy(), rtol=2e-5, atol=1e-5)
+
+
+def test_asymmetric_edge_list_is_flagged(ethanol):
+    cfg = o.OracleConfig(F=36, n_layers=1)
+    eng = make(cfg, o.init_params(cfg, 0))
+    R = ethanol['R'][:1]
+    z = ethanol['z'][None]
+    nl = o.get_indices(R, z, 5.0)
+    ii, jj = nl['idx_i'].copy(), nl['idx_j'].copy()
+    ii[0, 5] = -1
+    jj[0, 5] = -1          # drop one direction of a pair
+    _, _, _, st = eng.energy_forces(R, z, ii, jj)
+    assert st & STATUS_ASYMMETRIC
+
+
+# ---- neighbour list ---------------------------------------------------------------------------------
+def run_nl(lib, mode, pos, z, cell, pbc, cutoff, capacity):
+    N = len(pos)
+    pos = np.ascontiguousarray(pos, np.float64)
+    zz = None if z is None else np.ascontiguousarray(z, np.int32)
+    cell = None if cell is None else np.ascontiguousarray(cell, np.float64)
+    pbc = np.ascontiguousarray(pbc, np.uint8)
+    ii = np.zeros(capacity, np.int32)
+    jj = np.zeros(capacity, np.int32)
+    S = np.zeros((capacity, 3), np.int32)
+    cnt = np.zeros(1, np.int64)
+    st = np.zeros(1, np.int32)
+    nb = lib.neighbor_list_workspace_bytes(N, capacity)
+    ws = np.zeros(nb // 8 + 8, np.float64)
+    lib.neighbor_list(mode, N, ptr(pos), ptr(zz), ptr(cell), ptr(pbc), cutoff, capacity, ptr(ii), ptr(jj), ptr(S),
+                      ptr(cnt), ptr(ws), ws.nbytes, ptr(st))
+    return ii, jj, S, int(cnt[0]), int(st[0])
+
+
+@pytest.mark.parametrize('pbc', [(1, 1, 1), (1, 1, 0), (0, 0, 0), (1, 0, 1)])
+def test_neighbor_list_bit_exact_small_cell(solid, pbc):
+    # 9.05 A cell < 2 * 5 A cutoff: several periodic images of the same pair
+    lib = So3kLib(build_emu())
+    oi, oj, oS = o.primitive_neighbor_list(solid['R'], solid['unit_cell'], pbc, 5.0)
+    ii, jj, S, cnt, st = run_nl(lib, NL_ASE, solid['R'], None, solid['unit_cell'], pbc, 5.0, len(oi) + 5)
+    assert st == 0 and cnt == len(oi)
+    assert (ii[:cnt] == oi).all() and (jj[:cnt] == oj).all() and (S[:cnt] == oS).all()
+    assert (ii[cnt:] == -1).all() and (jj[cnt:] == -1).all() and (S[cnt:] == 0).all()      # indices.py:226-231
+
+
+def test_neighbor_list_overflow_triclinic_unwrapped_dense(solid, ethanol):
+    lib = So3kLib(build_emu())
+    oi, oj, oS = o.primitive_neighbor_list(solid['R'], solid['unit_cell'], (1, 1, 1), 5.0)
+    ii, jj, S, cnt, st = run_nl(lib, NL_ASE, solid['R'], None, solid['unit_cell'], (1, 1, 1), 5.0, 100)
+    assert (st & STATUS_OVERFLOW) and cnt == len(oi)                                        # indices.py:264-272
+    # atoms far outside the cell (ASE does not wrap; shifts absorb it)
+    pos2 = solid['R'] + np.array([13.0, -22.0, 40.0])
+    oi, oj, oS = o.primitive_neighbor_list(pos2, solid['unit_cell'], (1, 1, 1), 5.0)
+    ii, jj, S, cnt, st = run_nl(lib, NL_ASE, pos2, None, solid['unit_cell'], (1, 1, 1), 5.0, len(oi))
+    assert cnt == len(oi) and (ii == oi).all() and (jj == oj).all() and (S == oS).all()
+    # triclinic
+    rng = np.random.default_rng(0)
+    cell3 = np.array([[7.0, 0, 0], [2.0, 6.5, 0], [1.0, -1.5, 8.0]])
+    p3 = rng.uniform(0, 1, (60, 3)) @ cell3
+    oi, oj, oS = o.primitive_neighbor_list(p3, cell3, (1, 1, 1), 4.0)
+    ii, jj, S, cnt, st = run_nl(lib, NL_ASE, p3, None, cell3, (1, 1, 1), 4.0, len(oi) + 3)
+    assert cnt == len(oi) and (ii[:cnt] == oi).all() and (jj[:cnt] == oj).all() and (S[:cnt] == oS).all()
+    # dense (training) list: 0 < d <= r_cut, row-major, zero-Z atoms excluded
+    R = ethanol['R'][0]
+    z = ethanol['z'].copy()
+    nl = o.get_indices(R[None], z[None], 5.0)
+    ii, jj, S, cnt, st = run_nl(lib, NL_DENSE, R, z, None, (0, 0, 0), 5.0, 80)
+    assert cnt == 72 and (ii[:72] == nl['idx_i'][0]).all() and (jj[:72] == nl['idx_j'][0]).all()
+    z[4] = 0
+    nl = o.get_indices(R[None], z[None], 5.0)
+    ii, jj, S, cnt, st = run_nl(lib, NL_DENSE, R, z, None, (0, 0, 0), 5.0, 80)
+    k = (nl['idx_i'][0] >= 0).sum()
+    assert cnt == k and as_sets(ii, jj) == as_sets(nl['idx_i'][0], nl['idx_j'][0])

@@ -1,0 +1,288 @@
+"""Parity of the CUDA path (through the C ABI, libso3k.so) against the CPU oracle and the committed golden vectors.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+Tolerances are north_star's: neighbour lists bit-exact as sorted (i,j,S) sets, energies <= 1e-5 relative,
+forces <= 1e-4 eV/A max-abs (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+import so3k_oracle as o
+from conftest import golden
+from common import as_sets, jittered_lattice, water_like_numbers
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-5
+F_ATOL = 1e-4
+
+
+def _cfgs(ocfg):
+    from mlff_b200.config import So3kratesConfig
+    return So3kratesConfig(F=ocfg.F, n_layer=ocfg.n_layers, degrees=tuple(ocfg.degrees), n_heads=ocfg.n_heads,
+                           n_rbf=ocfg.n_rbf, r_cut=ocfg.r_cut)
+
+
+def make(ocfg, p, flags=0):
+    from mlff_b200.engine import So3kEngine
+    eng = So3kEngine(_cfgs(ocfg), 'cuda:0', flags)
+    eng.load_params({k: np.asarray(v, np.float32) for k, v in p.items()})
+    return eng
+
+
+def dev(a, dt):
+    return torch.as_tensor(np.asarray(a)).to('cuda:0', dt)
+
+
+def run_ef(eng, R, z, ii, jj, cell=None, off=None):
+    E, F, ea = eng.energy_forces(dev(R, torch.float32), dev(z, torch.int32), dev(ii, torch.int32), dev(jj, torch.int32),
+                                 None if cell is None else dev(cell, torch.float32),
+                                 None if off is None else dev(off, torch.int32), want_e_atom=True)
+    st = eng.check_status()
+    return E.cpu().numpy().reshape(-1), F.cpu().numpy(), ea.cpu().numpy(), st
+
+
+def test_native_library_is_loaded():
+    from mlff_b200 import _lib
+    lib = _lib.load()
+    assert lib.path.endswith('mlff_b200/lib/libso3k.so')
+    with open('/proc/self/maps') as f:
+        assert 'libso3k.so' in f.read()
+
+
+@pytest.mark.parametrize('F,degrees,H', [(132, (1, 2, 3), 4), (32, (1, 2, 2, 3), 4), (256, (1, 2, 3, 4), 4)])
+def test_featurise_matches_oracle(ethanol, F, degrees, H):
+    cfg = o.OracleConfig(F=F, degrees=degrees, n_heads=H, n_layers=1)
+    eng = make(cfg, o.init_params(cfg, 0))
+    R = ethanol['R'][0]
+    nl = o.get_indices(ethanol['R'][:1], ethanol['z'][None], 5.0)
+    ii = np.concatenate([nl['idx_i'][0], [-1, -1, -1]])
+    jj = np.concatenate([nl['idx_j'][0], [-1, -1, -1]])
+    out = {k: v.cpu().numpy() for k, v in eng.featurise(dev(ii, torch.int32), dev(jj, torch.int32), 9,
+                                                        R=dev(R, torch.float32)).items()}
+    geo = o.geometry_embed(cfg, torch.as_tensor(ii), torch.as_tensor(jj), torch.as_tensor((ii != -1).astype(np.float64)),
+                           torch.float64, R=torch.as_tensor(R))
+    for k, tol in (('d_ij', 2e-6), ('unit_r_ij', 1e-6), ('phi_r_cut', 1e-6), ('rbf_ij', 2e-6), ('sph_ij', 2e-6)):
+        np.testing.assert_allclose(out[k], geo[k].numpy(), atol=tol, err_msg=k)
+    assert (out['rbf_ij'][-3:] == 0).all() and (out['sph_ij'][-3:] == 0).all()
+
+
+@pytest.mark.parametrize('F,L,degrees,H', [(132, 3, (1, 2, 3), 4), (36, 2, (1, 2, 3), 4), (32, 2, (1, 2, 2, 3), 4),
+                                           (256, 3, (1, 2, 3, 4), 4)])
+def test_energy_forces_match_oracle_ethanol_batch(ethanol, F, L, degrees, H):
+    # config 1 of BASELINE.json: 32 x 9-atom ethanol frames, default model
+    cfg = o.OracleConfig(F=F, n_layers=L, degrees=degrees, n_heads=H)
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    eng = make(cfg, p)
+    B = 32 if F == 132 else 4
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(R, z, 5.0)
+    E, Fo, ea, st = run_ef(eng, R, z, nl['idx_i'], nl['idx_j'])
+    assert st == 0
+    Eo, Fr = o.energy_forces_batch(cfg, p, R, z, nl['idx_i'], nl['idx_j'])
+    np.testing.assert_allclose(E, Eo.numpy().reshape(-1), rtol=E_RTOL)
+    assert np.abs(Fo - Fr.numpy()).max() < F_ATOL
+    assert np.abs(Fo - Fr.numpy()).max() < 3e-5 * np.abs(Fr.numpy()).max()
+
+
+def test_golden_vectors(ethanol, solid):
+    cfg = o.OracleConfig()
+    for tag in ('default', 'amplified'):
+        g = golden(f'oracle_ethanol_{tag}.npz')
+        eng = make(cfg, o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale'])))
+        z = np.tile(ethanol['z'][None], (4, 1))
+        E, F, ea, st = run_ef(eng, ethanol['R'][:4], z, g['idx_i'], g['idx_j'])
+        np.testing.assert_allclose(E, g['E'].reshape(-1), rtol=E_RTOL)
+        assert np.abs(F - g['F']).max() < F_ATOL
+    g = golden('oracle_solid_pbc.npz')
+    eng = make(cfg, o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale'])))
+    E, F, ea, st = run_ef(eng, solid['R'][None], solid['z'][None], g['idx_i'][None], g['idx_j'][None],
+                          cell=solid['unit_cell'][None], off=g['shifts'][None])
+    assert st == 0
+    assert abs(E[0] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
+    assert np.abs(F[0] - g['F']).max() < F_ATOL
+    np.testing.assert_allclose(ea[0], g['e_atom'], atol=2e-5)
+
+
+def test_rotation_and_padding_invariance(ethanol):
+    # reference tests/test_model_invariance.py:80-222 re-expressed on the CUDA path
+    from scipy.spatial.transform import Rotation
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p)
+    R = ethanol['R'][:2]
+    z = np.tile(ethanol['z'][None], (2, 1))
+    nl = o.get_indices(R, z, 5.0)
+    E, F, _, _ = run_ef(eng, R, z, nl['idx_i'], nl['idx_j'])
+    for k in range(3):
+        Q = Rotation.random(random_state=k).as_matrix()
+        Er, Fr, _, _ = run_ef(eng, R @ Q.T, z, nl['idx_i'], nl['idx_j'])
+        assert np.isclose(Er, E).all()
+        assert np.isclose((F @ Q.T).reshape(-1), Fr.reshape(-1), atol=1e-5).all()
+    Rp = np.concatenate([R, np.zeros((2, 3, 3))], 1)
+    zp = np.concatenate([z, np.zeros((2, 3), z.dtype)], 1)
+    iip = np.concatenate([nl['idx_i'], -np.ones((2, 5), np.int64)], 1)
+    jjp = np.concatenate([nl['idx_j'], -np.ones((2, 5), np.int64)], 1)
+    Ep, Fp, _, _ = run_ef(eng, Rp, zp, iip, jjp)
+    np.testing.assert_allclose(Ep, E, rtol=2e-6)
+    np.testing.assert_allclose(Fp[:, :9], F, atol=2e-6)
+    assert (Fp[:, 9:] == 0).all()
+
+
+def test_md_seam_and_asymmetric_flag(ethanol):
+    from mlff_b200.capi import So3kError
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p)
+    R, z = ethanol['R'][0], ethanol['z']
+    nl = o.get_indices(R[None], z[None], 5.0)
+    ii, jj = nl['idx_i'][0], nl['idx_j'][0]
+    N = len(z)
+    centers = np.concatenate([ii, [N, N]])
+    others = np.concatenate([jj, [N, N]])
+    edges = np.concatenate([R[jj] - R[ii], np.zeros((2, 3))])
+    mask = np.concatenate([np.ones(72, bool), [False, False]])
+    ea, dE, Fo = eng.potential(dev(edges, torch.float32), dev(z, torch.int32), dev(centers, torch.int32),
+                               dev(others, torch.int32), dev(mask, torch.uint8), energy_scale=1.7)
+    assert eng.check_status() == 0
+    ea_o, g_o = o.potential_displacements(cfg, p, edges, z, np.where(mask, centers, -1), np.where(mask, others, -1),
+                                          mask, energy_scale=1.7)
+    np.testing.assert_allclose(ea.cpu().numpy(), ea_o.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dE.cpu().numpy(), g_o.numpy(), rtol=2e-5, atol=5e-6)
+    _, F_o, _ = o.energy_forces(cfg, p, R, z, ii, jj)
+    np.testing.assert_allclose(Fo.cpu().numpy(), 1.7 * F_o.numpy(), rtol=2e-5, atol=1e-5)
+    ii2, jj2 = ii.copy(), jj.copy()
+    ii2[5] = jj2[5] = -1
+    eng.energy_forces(dev(R[None], torch.float32), dev(z[None], torch.int32), dev(ii2[None], torch.int32),
+                      dev(jj2[None], torch.int32))
+    with pytest.raises(So3kError):
+        eng.check_status()
+
+
+def test_reference_api_mirror(ethanol):
+    # the drop-in surface: So3krates(...), net.init, get_obs_and_force_fn (reference tests/test_model_invariance.py:62-95)
+    from mlff_b200.nn import So3krates, get_obs_and_force_fn
+    from mlff_b200 import params as P
+    net = So3krates(F=36, n_layer=2)
+    variables = net.init(0)
+    obs_fn = get_obs_and_force_fn(net)
+    B = 3
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(R, z, 5.0)
+    out = obs_fn(variables, {'R': R, 'z': z, 'idx_i': nl['idx_i'], 'idx_j': nl['idx_j']})
+    assert out['E'].shape == (B, 1) and out['F'].shape == (B, 9, 3)
+    flat = P.from_flax_tree(net.cfg, variables)
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    Eo, Fr = o.energy_forces_batch(cfg, {k: v.astype(np.float64) for k, v in flat.items()}, R, z, nl['idx_i'], nl['idx_j'])
+    np.testing.assert_allclose(out['E'], Eo.numpy(), rtol=E_RTOL)
+    assert np.abs(out['F'] - Fr.numpy()).max() < F_ATOL
+    single = obs_fn(variables, {'R': R[0], 'z': z[0], 'idx_i': nl['idx_i'][0], 'idx_j': nl['idx_j'][0]})
+    assert single['E'].shape == (1,) and single['F'].shape == (9, 3)
+    np.testing.assert_allclose(single['F'], out['F'][0], atol=1e-7)
+
+
+# ---- neighbour list ---------------------------------------------------------------------------------------
+def gpu_nl(eng, pos, cell, pbc, cutoff, capacity, z=None, mode=0):
+    ii, jj, S, cnt = eng.neighbor_list(dev(pos, torch.float64), cutoff, capacity, cell=cell, pbc=pbc,
+                                       z=None if z is None else dev(z, torch.int32), mode=mode)
+    return ii.cpu().numpy(), jj.cpu().numpy(), S.cpu().numpy(), int(cnt.item())
+
+
+@pytest.mark.parametrize('pbc', [(1, 1, 1), (1, 1, 0), (0, 0, 0), (1, 0, 1)])
+def test_neighbor_list_bit_exact(solid, pbc):
+    cfg = o.OracleConfig(F=36, n_layers=1)
+    eng = make(cfg, o.init_params(cfg, 0))
+    oi, oj, oS = o.primitive_neighbor_list(solid['R'], solid['unit_cell'], pbc, 5.0)
+    ii, jj, S, cnt = gpu_nl(eng, solid['R'], solid['unit_cell'], pbc, 5.0, len(oi) + 5)
+    assert cnt == len(oi)
+    assert (ii[:cnt] == oi).all() and (jj[:cnt] == oj).all() and (S[:cnt] == oS).all()
+    assert (ii[cnt:] == -1).all() and (S[cnt:] == 0).all()
+    assert eng.check_status() == 0
+
+
+def test_neighbor_list_variants(solid, ethanol):
+    from mlff_b200.capi import NL_DENSE, STATUS_OVERFLOW
+    cfg = o.OracleConfig(F=36, n_layers=1)
+    eng = make(cfg, o.init_params(cfg, 0))
+    ii, jj, S, cnt = gpu_nl(eng, solid['R'], solid['unit_cell'], (1, 1, 1), 5.0, 100)
+    assert cnt == 5248 and (eng.check_status() & STATUS_OVERFLOW)
+    rng = np.random.default_rng(0)
+    cell3 = np.array([[7.0, 0, 0], [2.0, 6.5, 0], [1.0, -1.5, 8.0]])
+    p3 = rng.uniform(-1, 2, (200, 3)) @ cell3
+    oi, oj, oS = o.primitive_neighbor_list(p3, cell3, (1, 1, 1), 4.0)
+    ii, jj, S, cnt = gpu_nl(eng, p3, cell3, (1, 1, 1), 4.0, len(oi) + 3)
+    assert cnt == len(oi) and (ii[:cnt] == oi).all() and (jj[:cnt] == oj).all() and (S[:cnt] == oS).all()
+    R, z = ethanol['R'][0], ethanol['z']
+    nl = o.get_indices(R[None], z[None], 5.0)
+    ii, jj, S, cnt = gpu_nl(eng, R, None, (0, 0, 0), 5.0, 80, z=z, mode=NL_DENSE)
+    assert cnt == 72 and (ii[:72] == nl['idx_i'][0]).all() and (jj[:72] == nl['idx_j'][0]).all()
+
+
+def test_water_box_3000_atoms_vs_oracle():
+    # config 3 of BASELINE.json: 3 000 atoms, cubic 31.072 A cell, MIC neighbour list at 5 A, E+F on one GPU.
+    # The oracle (float64, brute-force list) still finishes in seconds at this size.
+    N, box = 3000, 31.072
+    pos = jittered_lattice(N, box, seed=2)
+    z = np.where(np.arange(N) % 3 == 0, 8, 1)
+    cell = np.eye(3) * box
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p)
+    oi, oj, oS = o.periodic_neighbor_list_kdtree(pos, box, 5.0)
+    ii, jj, S, cnt = gpu_nl(eng, pos, cell, (1, 1, 1), 5.0, int(1.1 * len(oi)))
+    assert cnt == len(oi) and (ii[:cnt] == oi).all() and (jj[:cnt] == oj).all() and (S[:cnt] == oS).all()
+    E, F, ea, st = run_ef(eng, pos[None], z[None], ii[None], jj[None], cell=cell[None], off=S[None])
+    assert st == 0
+    Eo, Fo, eao = o.energy_forces(cfg, p, pos, z, oi, oj, cell=cell, cell_offset=oS)
+    assert abs(E[0] - Eo.item()) <= E_RTOL * abs(Eo.item())
+    assert np.abs(F[0] - Fo.numpy()).max() < F_ATOL
+    # size-independent properties: translation invariance, net force ~ 0 (Newton's third law)
+    assert np.abs(F[0].sum(0)).max() < 1e-3
+
+
+def test_full_size_properties_100k_atoms():
+    # config 4 of BASELINE.json at full size (100 000 atoms, 100 A box): too big for the oracle, so check
+    # properties: list symmetric + sorted + strict cutoff, E invariant and F unchanged under a rigid translation
+    # through the periodic boundary, net force ~ 0, finite outputs; a 3 000-atom sub-problem is pinned above.
+    N, box = 100_000, 100.0
+    pos = jittered_lattice(N, box, seed=3)
+    z = water_like_numbers(N, 3)
+    cell = np.eye(3) * box
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p)
+    cap = 64 * N
+    ii, jj, S, cnt = gpu_nl(eng, pos, cell, (1, 1, 1), 5.0, cap)
+    assert 0 < cnt <= cap and eng.check_status() == 0
+    ii, jj, S = ii[:cnt], jj[:cnt], S[:cnt]
+    oi, oj, oS = o.periodic_neighbor_list_kdtree(pos, box, 5.0)          # bit-exact (i,j,S) set at full size
+    assert cnt == len(oi) and (ii == oi).all() and (jj == oj).all() and (S == oS).all()
+    assert (np.diff(ii) >= 0).all()
+    d = np.linalg.norm(pos[jj] - pos[ii] + S @ cell, axis=-1)
+    assert (d < 5.0).all() and (d > 0).all()
+    key = lambda a, b, s: (a.astype(np.int64) * N + b) * 27 + (s[:, 0] + 1) * 9 + (s[:, 1] + 1) * 3 + (s[:, 2] + 1)
+    assert np.array_equal(np.sort(key(ii, jj, S)), np.sort(key(jj, ii, -S)))
+    E, F, ea, st = run_ef(eng, pos[None], z[None], ii[None], jj[None], cell=cell[None], off=S[None])
+    assert st == 0 and np.isfinite(E).all() and np.isfinite(F).all()
+    assert np.abs(F[0].sum(0)).max() < 2e-2
+    pos2 = pos + np.array([3.7, -41.3, 12.9])
+    ii2, jj2, S2, cnt2 = gpu_nl(eng, pos2, cell, (1, 1, 1), 5.0, cap)
+    assert cnt2 == cnt
+    E2, F2, _, _ = run_ef(eng, pos2[None], z[None], ii2[None, :cnt2], jj2[None, :cnt2], cell=cell[None], off=S2[None, :cnt2])
+    assert abs(E2[0] - E[0]) <= 2e-5 * abs(E[0])
+    assert np.abs(F2[0] - F[0]).max() < 2e-4
+
+
+def test_calculator_end_to_end(solid):
+    from mlff_b200.calculator import mlffCalculator
+    from mlff_b200.config import So3kratesConfig
+    g = golden('oracle_solid_pbc.npz')
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+    calc = mlffCalculator(_cfgs(cfg), {k: np.asarray(v, np.float32) for k, v in p.items()})
+    calc.capacity = 1000                                     # force the overflow / re-allocation branch
+    res = calc.calculate(solid['R'], solid['z'], cell=solid['unit_cell'], pbc=(True, True, True))
+    assert calc.n_edges == 5248 and calc.capacity >= 5248
+    assert abs(res['energy'] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
+    assert np.abs(res['forces'] - g['F']).max() < F_ATOL

@@ -1,0 +1,138 @@
+"""The oracle against everything the reference pins for this path and against its
+own committed golden outputs."""
+import math
+
+import numpy as np
+import torch
+from scipy.spatial.transform import Rotation
+
+import so3k_oracle as o
+from conftest import golden
+
+
+def test_l0_coefficients_match_reference_cgmatrix():
+    # mlff/sph_ops/contract.py:162-177 reads diag CG(l,l->0) from cgmatrix.npz; golden/l0_cg_diag.npy holds it
+    diag = golden('l0_cg_diag.npy')
+    for degrees in ([1, 2, 3], [1, 2, 3, 4], [1, 2, 2, 3], [2, 1]):
+        cg, seg = o.l0_coefficients(degrees)
+        ref = []
+        for d, r in zip(*np.unique(np.array(degrees), return_counts=True)):
+            ref += [np.tile(diag[d * d:(d + 1) * (d + 1)], r)]
+        np.testing.assert_allclose(cg, np.concatenate(ref), rtol=0, atol=1e-15)
+        assert list(seg) == [n for n in range(len(degrees)) for _ in range(2 * degrees[n] + 1)]
+
+
+def test_ethanol_has_72_edges_per_frame(ethanol):
+    # fixture property recorded in SURVEY.md section 4 (r_cut = 5 A)
+    z = np.tile(ethanol['z'][None], (32, 1))
+    nl = o.get_indices(ethanol['R'], z, 5.0)
+    assert nl['idx_i'].shape == (32, 72)
+    assert (nl['idx_i'] >= 0).all()
+
+
+def test_dense_neighbor_list_distance_multiset(solid):
+    # reference tests/test_neighbor_list.py:20-49: distances of the list == all pair distances within the cutoff
+    R, z = solid['R'][None], solid['z'][None]
+    nl = o.get_indices(R, z, 4.0)
+    ii, jj = nl['idx_i'][0], nl['idx_j'][0]
+    d_list = np.sort(np.linalg.norm(R[0][jj] - R[0][ii], axis=-1))
+    D = np.linalg.norm(R[0][:, None] - R[0][None], axis=-1)
+    d_all = np.sort(D[(D <= 4.0) & (D > 0)])
+    np.testing.assert_allclose(d_list, d_all, rtol=1e-7)
+
+
+def test_primitive_neighbor_list_properties(solid):
+    pos, cell = solid['R'], solid['unit_cell']
+    ii, jj, S = o.primitive_neighbor_list(pos, cell, [True, True, True], 5.0)
+    d = np.linalg.norm(pos[jj] - pos[ii] + S @ cell, axis=-1)
+    assert (d < 5.0).all() and (d > 0).all()
+    # symmetric: (i,j,S) <-> (j,i,-S)
+    fwd = set(zip(ii.tolist(), jj.tolist(), map(tuple, S.tolist())))
+    assert all((j, i, (-s[0], -s[1], -s[2])) in fwd for i, j, s in fwd)
+    # non-periodic == dense list with strict cutoff
+    ii0, jj0, S0 = o.primitive_neighbor_list(pos, cell, [False] * 3, 5.0)
+    assert (S0 == 0).all()
+    D = np.linalg.norm(pos[:, None] - pos[None], axis=-1)
+    assert len(ii0) == int(((D < 5.0) & (D > 0)).sum())
+
+
+def test_kdtree_list_equals_brute_force():
+    from common import jittered_lattice
+    pos = jittered_lattice(600, 18.2, seed=5) + np.array([40.0, -3.0, 7.5])      # also outside the box
+    a = o.primitive_neighbor_list(pos, np.eye(3) * 18.2, (1, 1, 1), 5.0)
+    b = o.periodic_neighbor_list_kdtree(pos, 18.2, 5.0)
+    assert all((x == y).all() for x, y in zip(a, b))
+
+
+def _setup(ethanol, F=36, L=2, degrees=(1, 2, 3), H=4, es=4.0, seed=0):
+    cfg = o.OracleConfig(F=F, n_layers=L, degrees=degrees, n_heads=H)
+    p = o.init_params(cfg, seed, embed_scale=es)
+    R = ethanol['R'][:1]
+    z = ethanol['z'][None]
+    nl = o.get_indices(R, z, 5.0)
+    return cfg, p, R[0], z[0], nl['idx_i'][0], nl['idx_j'][0]
+
+
+def test_rotation_invariance_equivariance(ethanol):
+    # reference tests/test_model_invariance.py:80-130 (F=36, 2 layers ; and repeated degrees [1,2,2,3], F=32)
+    for kw in (dict(F=36), dict(F=32, degrees=(1, 2, 2, 3))):
+        cfg, p, R, z, ii, jj = _setup(ethanol, **kw)
+        E, F, _ = o.energy_forces(cfg, p, R, z, ii, jj, dtype=torch.float32)
+        for k in range(3):
+            Q = Rotation.random(random_state=k).as_matrix()
+            Er, Fr, _ = o.energy_forces(cfg, p, R @ Q.T, z, ii, jj, dtype=torch.float32)
+            assert np.isclose(Er.item(), E.item())
+            assert not np.isclose(Fr.numpy().reshape(-1), F.numpy().reshape(-1)).all()
+            assert np.isclose((F.double() @ torch.tensor(Q.T)).numpy().reshape(-1), Fr.numpy().reshape(-1), atol=1e-5).all()
+
+
+def test_padding_invariance(ethanol):
+    # reference tests/test_model_invariance.py:133-222
+    cfg, p, R, z, ii, jj = _setup(ethanol)
+    E, F, _ = o.energy_forces(cfg, p, R, z, ii, jj)
+    zp = np.concatenate([z, [0, 0, 0]])
+    Rp = np.concatenate([R, np.zeros((3, 3))])
+    iip = np.concatenate([ii, [-1] * 5])
+    jjp = np.concatenate([jj, [-1] * 5])
+    Ep, Fp, _ = o.energy_forces(cfg, p, Rp, zp, iip, jjp)
+    assert Ep.item() == E.item()
+    assert torch.equal(Fp[:9], F)
+    assert (Fp[9:] == 0).all()
+
+
+def test_forces_match_finite_differences(ethanol):
+    cfg, p, R, z, ii, jj = _setup(ethanol)
+    E, F, _ = o.energy_forces(cfg, p, R, z, ii, jj)
+    h = 1e-5
+    for (a, c) in ((0, 0), (3, 1), (8, 2)):
+        Rp, Rm = R.copy(), R.copy()
+        Rp[a, c] += h
+        Rm[a, c] -= h
+        fd = -(o.energy_forces(cfg, p, Rp, z, ii, jj)[0] - o.energy_forces(cfg, p, Rm, z, ii, jj)[0]).item() / (2 * h)
+        assert abs(fd - F[a, c].item()) < 1e-7 * max(1.0, abs(fd))
+
+
+def test_displacement_convention_equals_positions(ethanol):
+    # MD seam (mlff_potential.py:95-109): edges = R_j - R_i gives the same per-atom energies; chaining dE/dedges
+    # through R_j - R_i reproduces the forces.
+    cfg, p, R, z, ii, jj = _setup(ethanol)
+    E, F, ea = o.energy_forces(cfg, p, R, z, ii, jj)
+    edges = R[jj] - R[ii]
+    mask = np.ones(len(ii), bool)
+    ea2, g = o.potential_displacements(cfg, p, edges, z, ii, jj, mask)
+    np.testing.assert_allclose(ea2.numpy(), ea.numpy(), rtol=1e-12, atol=1e-14)
+    Fch = np.zeros((len(z), 3))
+    np.add.at(Fch, ii, g.numpy())
+    np.add.at(Fch, jj, -g.numpy())
+    np.testing.assert_allclose(Fch, F.numpy(), rtol=1e-10, atol=1e-13)
+
+
+def test_oracle_reproduces_committed_golden_outputs(ethanol, solid):
+    cfg = o.OracleConfig()
+    for tag in ('default', 'amplified'):
+        g = golden(f'oracle_ethanol_{tag}.npz')
+        p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+        z = np.tile(ethanol['z'][None], (4, 1))
+        E, F = o.energy_forces_batch(cfg, p, ethanol['R'][:4], z, g['idx_i'], g['idx_j'])
+        np.testing.assert_allclose(E.numpy(), g['E'], rtol=1e-12)
+        np.testing.assert_allclose(F.numpy(), g['F'], rtol=1e-9, atol=1e-13)
