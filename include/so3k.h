@@ -182,6 +182,13 @@ const char* so3k_profile_categories(void);
 int so3k_profile_enable(so3k_handle* h, int32_t enable);
 int so3k_profile_collect(so3k_handle* h, double* ms, int64_t* count, int32_t n_categories, int32_t reset);
 
+/* Diagnostic: one 128 x N x K split-bf16 GEMM tile on the tcgen05 tensor cores with the shared-memory operand
+ * layouts of the edge kernels (tests pin the descriptor conventions with it).  A (128,K) f32;
+ * variant 0: B (N,K) f32, D = A @ B^T ; variant 2: B (K,N) f32 consumed as an MN-major operand, D = A @ B.
+ * passes: 1 (bf16 x bf16) or 3 (split operands).  D (128,N) f32. */
+int so3k_tc_selftest(int32_t N, int32_t K, int32_t variant, int32_t passes, const float* A, const float* B,
+                     float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

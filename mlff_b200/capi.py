@@ -25,7 +25,7 @@ NL_DENSE = 1
 EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 'so3k_param_lookup',
            'so3k_load_params', 'so3k_workspace_bytes', 'so3k_energy_forces', 'so3k_potential_displacements',
            'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count',
-           'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect']
+           'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect', 'so3k_tc_selftest']
 
 
 class So3kConfigC(C.Structure):
@@ -77,6 +77,8 @@ class So3kLib:
         d.so3k_neighbor_list.restype = C.c_int
         d.so3k_launch_count.argtypes = []
         d.so3k_launch_count.restype = C.c_uint64
+        d.so3k_tc_selftest.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
+        d.so3k_tc_selftest.restype = C.c_int
         d.so3k_profile_categories.argtypes = []
         d.so3k_profile_categories.restype = C.c_char_p
         d.so3k_profile_enable.argtypes = [vp, i32]
@@ -146,6 +148,9 @@ class So3kLib:
                       ws_bytes, status, stream=0):
         _check(self.dll.so3k_neighbor_list(mode, N, positions, z, cell, pbc, float(cutoff), capacity, idx_i, idx_j,
                                            shifts, count, ws, ws_bytes, status, stream), 'so3k_neighbor_list')
+
+    def tc_selftest(self, N, K, variant, passes, A, B, D, stream=0):
+        _check(self.dll.so3k_tc_selftest(N, K, variant, passes, A, B, D, stream), 'so3k_tc_selftest')
 
     def launch_count(self) -> int:
         return int(self.dll.so3k_launch_count())

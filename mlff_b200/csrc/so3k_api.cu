@@ -38,6 +38,9 @@ struct Profiler {
 struct HandleImpl : so3k_handle {
   float* repack = nullptr;
   std::vector<EdgeBlockW> wf, wg;    // per layer
+  unsigned char* tc_images = nullptr;
+  std::vector<TcBlockW> tf, tg;      // per layer (tensor-core mode)
+  bool use_tc = false;
   Profiler prof;
 };
 
@@ -172,7 +175,7 @@ struct Workspace {
   float *x1, *chi1, *bcoef;  // x1: 1 buffer ; chi1, bcoef: per layer
   float *proj, *gproj;
   float *alpha;            // per layer
-  float *alphabar, *gbar, *rbar;
+  float *alphabar, *gbar, *rbar, *ebar;
   float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
   float *e_atom;
   size_t bytes;
@@ -209,6 +212,7 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base) {
   w.alphabar = (float*)take(sizeof(float) * Pe * Ast);
   w.gbar = (float*)take(sizeof(float) * Pe * Gst);
   w.rbar = (float*)take(sizeof(float) * Pe * 3);
+  w.ebar = (float*)take(sizeof(float) * Pe * 2);
   w.xbar_a = (float*)take(sizeof(float) * N * F);
   w.xbar_b = (float*)take(sizeof(float) * N * F);
   w.chibar_a = (float*)take(sizeof(float) * N * M);
@@ -242,7 +246,11 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
     float* ct = w.chi + (size_t)t * N * M;
     float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
     { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
-    { PROF(CAT_EDGE_FWD); so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st); }
+    {
+      PROF(CAT_EDGE_FWD);
+      if (h->use_tc) so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, dev_status, st);
+      else so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
+    }
     { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
     PROF(CAT_INTERACTION);
     so3k_launch_interaction(D, N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + (size_t)N * F, ct + (size_t)N * M,
@@ -274,8 +282,11 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
     { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
     cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
     { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, xbar_nx, chibar_nx, w.alphabar, w.gproj, st); }
-    { PROF(CAT_EDGE_BWD); so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, w.alphabar, chibar_nx, w.gproj, w.gbar,
-                         w.rbar, st); }
+    {
+      PROF(CAT_EDGE_BWD);
+      so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
+      so3k_launch_edge_finish(D, w.g, alpha_t, chibar_nx, w.ebar, w.rbar, st);
+    }
     if (t > 0) {
       // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
       { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, chibar_nx, chibar, st); }      // chibar <- d/d chi_t
@@ -299,10 +310,12 @@ int so3k_create(const so3k_config* cfg, so3k_handle** out) {
   So3kDims D;
   if (!make_dims(*cfg, &D)) return SO3K_ERR_CONFIG;
   if (!so3k_edge_supported(D)) return SO3K_ERR_CONFIG;
+  if ((cfg->flags & SO3K_FLAG_TENSOR) && !so3k_edge_tc_supported(D)) return SO3K_ERR_CONFIG;
   HandleImpl* h = new (std::nothrow) HandleImpl();
   if (!h) return SO3K_ERR_ARG;
   h->cfg = *cfg;
   h->dims = D;
+  h->use_tc = (cfg->flags & SO3K_FLAG_TENSOR) != 0;
   make_layout(D, &h->layout);
   *out = h;
   return SO3K_OK;
@@ -313,6 +326,7 @@ int so3k_destroy(so3k_handle* hh) {
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (h->params) cudaFree(h->params);
   if (h->repack) cudaFree(h->repack);
+  if (h->tc_images) cudaFree(h->tc_images);
   delete h;
   return SO3K_OK;
 }
@@ -350,6 +364,18 @@ int so3k_load_params(so3k_handle* hh, const float* blob_dev, size_t n_floats, vo
   for (int t = 0; t < D.L; ++t) {
     so3k_edge_repack(D, h->params, h->layout.layers[t].fb, h->repack + per * (2 * t), &h->wf[t], st);
     so3k_edge_repack(D, h->params, h->layout.layers[t].gb, h->repack + per * (2 * t + 1), &h->wg[t], st);
+  }
+  if (h->use_tc) {
+    size_t ib = so3k_edge_tc_image_bytes(D);
+    if (!h->tc_images) {
+      if (cudaMalloc((void**)&h->tc_images, ib * 2 * D.L) != cudaSuccess) return SO3K_ERR_CUDA;
+    }
+    h->tf.resize(D.L);
+    h->tg.resize(D.L);
+    for (int t = 0; t < D.L; ++t) {
+      so3k_edge_tc_build(D, h->params, h->layout.layers[t].fb, h->tc_images + ib * (2 * t), &h->tf[t], h->wf[t], st);
+      so3k_edge_tc_build(D, h->params, h->layout.layers[t].gb, h->tc_images + ib * (2 * t + 1), &h->tg[t], h->wg[t], st);
+    }
   }
   h->have_params = true;
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;

@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(NT)
 k_edge_bwd(So3kDims D, Tile T, int Ast, int Gst, const int* __restrict__ n_valid, const int* __restrict__ row,
            const int* __restrict__ col, const int* __restrict__ rev, const float4* __restrict__ geom,
            const float* __restrict__ chi, const float* __restrict__ proj, EdgeBlockW Wf, EdgeBlockW Wg,
-           const float* __restrict__ alpha, const float* __restrict__ alphabar, const float* __restrict__ chibar1,
-           float* __restrict__ gproj, float* __restrict__ gbar, float* __restrict__ rbar) {
+           const float* __restrict__ alphabar, int parts, float* __restrict__ gproj, float* __restrict__ gbar,
+           float* __restrict__ ebar) {
   SO3K_DYN_SMEM(float, smem);
   const int nv = *n_valid;
   const int e0 = blockIdx.x * T.TE;
@@ -348,7 +348,7 @@ k_edge_bwd(So3kDims D, Tile T, int Ast, int Gst, const int* __restrict__ n_valid
       }
       __syncthreads();
       const int goff = pass == 0 ? qoff : koff;
-      for (int f = threadIdx.x; f < F; f += NT) {
+      for (int f = threadIdx.x; f < ((parts & 1) ? F : 0); f += NT) {
         int cur = S.s_i[0];
         float acc = 0.f;
         for (int t = 0; t < ne; ++t) {
@@ -409,13 +409,29 @@ k_edge_bwd(So3kDims D, Tile T, int Ast, int Gst, const int* __restrict__ n_valid
     __syncthreads();
   }
 
-  // ---- per-edge epilogue: chain to the displacement vector --------------------------------------------
+  // ---- per-edge outputs: radial cotangent, cutoff cotangent, l0-contraction cotangent ------------------------
   for (int t = threadIdx.x; t < ne; t += NT) {
     const int e = e0 + t;
+    if (parts & 1) ebar[2 * (size_t)e + 1] = S.s_phibar[t];
+    if (parts & 2) {
+      ebar[2 * (size_t)e + 0] = S.s_dbar[t];
+      for (int l = 0; l < D.nl; ++l) gbar[(size_t)e * Gst + l] = S.s_gbar[t * D.nl + l];
+    }
+  }
+}
+
+// Chain the per-edge cotangents to the displacement vector (thread per edge):
+//   dbar = dbar_rad + phibar * phi'(d) ; Ybar = alpha' chibar1_i -> ubar ; rbar += dbar u + (ubar - (ubar.u) u) / d
+__global__ void k_edge_finish(So3kDims D, int Ast, const int* __restrict__ n_valid, const int* __restrict__ row,
+                              const float4* __restrict__ geom, const float* __restrict__ alpha,
+                              const float* __restrict__ chibar1, const float* __restrict__ ebar,
+                              float* __restrict__ rbar) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < *n_valid) {
     const float4 g = geom[e];
     const float d = g.w;
-    const int i = S.s_i[t];
-    float dbar = S.s_dbar[t] + S.s_phibar[t] * so3k_cutoff_d(d, D.r_cut);
+    const int i = row[e];
+    float dbar = ebar[2 * (size_t)e + 0] + ebar[2 * (size_t)e + 1] * so3k_cutoff_d(d, D.r_cut);
     float ybar[SO3K_MAXM];
     for (int m = 0; m < D.M; ++m)
       ybar[m] = alpha[(size_t)e * Ast + D.H + D.m_seg[m]] * chibar1[(size_t)i * D.M + m];
@@ -432,7 +448,6 @@ k_edge_bwd(So3kDims D, Tile T, int Ast, int Gst, const int* __restrict__ n_valid
     rbar[3 * (size_t)e + 0] += rx;
     rbar[3 * (size_t)e + 1] += ry;
     rbar[3 * (size_t)e + 2] += rz;
-    for (int l = 0; l < D.nl; ++l) gbar[(size_t)e * Gst + l] = S.s_gbar[t * D.nl + l];
   }
 }
 
@@ -522,8 +537,8 @@ void so3k_launch_edge_fwd(const So3kDims& D, const Graph& g, const EdgeBlockW& W
 }
 
 void so3k_launch_edge_bwd(const So3kDims& D, const Graph& g, const EdgeBlockW& Wf, const EdgeBlockW& Wg,
-                          const float* chi, const float* proj, const float* alpha, const float* alphabar,
-                          const float* chibar1, float* gproj, float* gbar, float* rbar, cudaStream_t st) {
+                          const float* chi, const float* proj, const float* alphabar, int parts, float* gproj,
+                          float* gbar, float* ebar, cudaStream_t st) {
   if (g.Pt <= 0) return;
   Tile T = make_tile(D);
   int Ast = (D.H + D.nl + 3) & ~3;
@@ -531,5 +546,13 @@ void so3k_launch_edge_bwd(const So3kDims& D, const Graph& g, const EdgeBlockW& W
   size_t smem = sizeof(float) * smem_floats(T, D, Ast, true);
   SO3K_SET_MAX_SMEM(k_edge_bwd, smem);
   SO3K_LAUNCH(k_edge_bwd, dim3(so3k_cdiv(g.Pt, T.TE)), dim3(NT), smem, st, D, T, Ast, Gst, g.n_valid, g.row, g.col, g.rev,
-              g.geom, chi, proj, Wf, Wg, alpha, alphabar, chibar1, gproj, gbar, rbar);
+              g.geom, chi, proj, Wf, Wg, alphabar, parts, gproj, gbar, ebar);
+}
+
+void so3k_launch_edge_finish(const So3kDims& D, const Graph& g, const float* alpha, const float* chibar1,
+                             const float* ebar, float* rbar, cudaStream_t st) {
+  if (g.Pt <= 0) return;
+  int Ast = (D.H + D.nl + 3) & ~3;
+  SO3K_LAUNCH(k_edge_finish, dim3(so3k_cdiv(g.Pt, 256)), dim3(256), 0, st, D, Ast, g.n_valid, g.row, g.geom, alpha, chibar1,
+              ebar, rbar);
 }

@@ -18,6 +18,24 @@ void so3k_edge_repack(const So3kDims& D, const float* params, const BlockParams&
                       cudaStream_t st);
 void so3k_launch_edge_fwd(const So3kDims& D, const Graph& g, const EdgeBlockW& Wf, const EdgeBlockW& Wg,
                           const float* chi, const float* proj, float* alpha, cudaStream_t st);
+// parts: bit 0 = q/k projection gradients (gproj, atomics) and the cutoff cotangent ebar[e][1];
+//        bit 1 = radial cotangent ebar[e][0] and the l0-contraction cotangent gbar.
 void so3k_launch_edge_bwd(const So3kDims& D, const Graph& g, const EdgeBlockW& Wf, const EdgeBlockW& Wg,
-                          const float* chi, const float* proj, const float* alpha, const float* alphabar,
-                          const float* chibar1, float* gproj, float* gbar, float* rbar, cudaStream_t st);
+                          const float* chi, const float* proj, const float* alphabar, int parts, float* gproj,
+                          float* gbar, float* ebar, cudaStream_t st);
+void so3k_launch_edge_finish(const So3kDims& D, const Graph& g, const float* alpha, const float* chibar1,
+                             const float* ebar, float* rbar, cudaStream_t st);
+
+// ---- tcgen05 path (so3k_edge_tc.cu) -----------------------------------------------------------------------------
+struct TcBlockW {
+  const unsigned char* img;   // [W1 hi | W1 lo | W2c hi | W2c lo] bf16 operand images (shared-memory layout)
+  const float* bias;          // [b1 padded to Fp | b2c padded to Fp]
+  const float* Ws1;           // (nl, Fs)
+  const float* bs1;           // (Fs)
+};
+bool so3k_edge_tc_supported(const So3kDims& D);
+size_t so3k_edge_tc_image_bytes(const So3kDims& D);   // per block
+void so3k_edge_tc_build(const So3kDims& D, const float* params, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
+                        const EdgeBlockW& simt, cudaStream_t st);
+void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
+                             const float* proj, float* alpha, int* status, cudaStream_t st);

@@ -1,0 +1,108 @@
+// Diagnostic entry point: one 128 x N x K split-bf16 GEMM tile on tcgen05 with the operand layouts the edge
+// kernels use.  Exercised by tests/test_gpu_parity.py to pin descriptor / layout conventions on the device.
+#include "so3k_internal.h"
+#ifndef SO3K_EMU
+#include "so3k_tc.cuh"
+
+namespace {
+
+// variant 0: B given as (N, K) row-major  -> K-major operand            D = A @ B^T
+// variant 2: B given as (K, N) row-major  -> image stored K-major with rows = reduction index, consumed as an
+//            MN-major operand                                            D = A @ B
+// passes: 1 = hi*hi only, 3 = hi*hi + lo*hi + hi*lo
+__global__ void __launch_bounds__(128)
+k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A, const float* __restrict__ B,
+              float* __restrict__ D) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t sboA = (uint32_t)(K / 8) * 128u;
+  const int imgRows = variant == 2 ? K : N;       // rows of the B image
+  const int imgCols = variant == 2 ? N : K;
+  const uint32_t sboB = (uint32_t)(imgCols / 8) * 128u;
+  const uint32_t szA = 16u * sboA, szB = (uint32_t)(imgRows / 8) * sboB;
+  unsigned char* Ahi = smem;
+  unsigned char* Alo = Ahi + szA;
+  unsigned char* Bhi = Alo + szA;
+  unsigned char* Blo = Bhi + szB;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+  }
+  // A image: thread = row
+  for (int c = 0; c < K / 8; ++c) {
+    float v[8];
+    for (int q = 0; q < 8; ++q) v[q] = A[(size_t)tid * K + c * 8 + q];
+    tc::store_chunk8(Ahi, Alo, tc::canon_off(tid, c, sboA), v);
+  }
+  for (int r = tid; r < imgRows; r += 128)
+    for (int c = 0; c < imgCols / 8; ++c) {
+      float v[8];
+      for (int q = 0; q < 8; ++q) v[q] = B[(size_t)r * imgCols + c * 8 + q];
+      tc::store_chunk8(Bhi, Blo, tc::canon_off(r, c, sboB), v);
+    }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, variant == 2 ? 1 : 0);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t aoff = (uint32_t)ks * 256u;
+      uint64_t a_hi = tc::make_desc(tc::smem_u32(Ahi) + aoff, 128u, sboA);
+      uint64_t a_lo = tc::make_desc(tc::smem_u32(Alo) + aoff, 128u, sboA);
+      uint64_t b_hi, b_lo;
+      if (variant == 2) {      // MN-major: LBO = distance between 8-row k groups (= image SBO), SBO = 128
+        const uint32_t boff = (uint32_t)ks * 2u * sboB;
+        b_hi = tc::make_desc(tc::smem_u32(Bhi) + boff, sboB, 128u);
+        b_lo = tc::make_desc(tc::smem_u32(Blo) + boff, sboB, 128u);
+      } else {
+        b_hi = tc::make_desc(tc::smem_u32(Bhi) + aoff, 128u, sboB);
+        b_lo = tc::make_desc(tc::smem_u32(Blo) + aoff, 128u, sboB);
+      }
+      tc::mma_bf16(tmem, a_hi, b_hi, idesc, acc);
+      acc = 1;
+      if (passes == 3) {
+        tc::mma_bf16(tmem, a_lo, b_hi, idesc, 1);
+        tc::mma_bf16(tmem, a_hi, b_lo, idesc, 1);
+      }
+    }
+    tc::commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  for (int c = 0; c < N; c += 8) {
+    float v[8];
+    tc::tmem_ld8(tmem + lane_base + (uint32_t)c, v);
+    tc::tmem_ld_wait();
+    for (int q = 0; q < 8; ++q) D[(size_t)tid * N + c + q] = v[q];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+#endif
+
+extern "C" int so3k_tc_selftest(int32_t N, int32_t K, int32_t variant, int32_t passes, const float* A, const float* B,
+                                float* D, void* stream) {
+#ifdef SO3K_EMU
+  (void)N; (void)K; (void)variant; (void)passes; (void)A; (void)B; (void)D; (void)stream;
+  return SO3K_ERR_CONFIG;
+#else
+  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || !A || !B || !D) return SO3K_ERR_ARG;
+  size_t smem = 2 * (size_t)16 * (K / 8) * 128 + 2 * (size_t)N * K * 2 + 1024;
+  if (smem > 227 * 1024) return SO3K_ERR_ARG;
+  cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  so3k_count_launch();
+  k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(N, K, variant, passes, A, B, D);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+#endif
+}

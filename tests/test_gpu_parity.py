@@ -289,3 +289,54 @@ def test_calculator_end_to_end(solid):
     assert calc.n_edges == 5248 and calc.capacity >= 5248
     assert abs(res['energy'] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
     assert np.abs(res['forces'] - g['F']).max() < F_ATOL
+
+
+# ---- tcgen05 operand-layout conventions ------------------------------------------------------------------------
+@pytest.mark.parametrize('N,K,variant', [(144, 32, 0), (144, 176, 0), (176, 144, 2), (256, 64, 0), (48, 144, 2)])
+def test_tcgen05_tile_gemm_layouts(N, K, variant):
+    """One 128 x N x K tile on the tensor cores with the canonical no-swizzle operand images the edge kernels
+    build (K-major, and the same image consumed MN-major), single pass and 3-pass split-bf16."""
+    from mlff_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(N * 1000 + K)
+    A = rng.normal(size=(128, K)).astype(np.float32)
+    Bm = rng.normal(size=(N, K) if variant == 0 else (K, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ (Bm.astype(np.float64).T if variant == 0 else Bm.astype(np.float64))
+    bf = lambda a: torch.as_tensor(a).to(torch.bfloat16).double().numpy()
+    ref1 = bf(A) @ (bf(Bm).T if variant == 0 else bf(Bm))
+    Ad, Bd = dev(A, torch.float32), dev(Bm, torch.float32)
+    for passes, target, tol in ((1, ref1, 2e-5), (3, ref, 3e-5)):
+        D = torch.zeros(128, N, dtype=torch.float32, device='cuda:0')
+        lib.tc_selftest(N, K, variant, passes, Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        scale = np.abs(A).astype(np.float64) @ (np.abs(Bm).astype(np.float64).T if variant == 0 else np.abs(Bm))
+        err = np.abs(D.cpu().numpy() - target) / scale
+        assert err.max() < tol, (passes, float(err.max()))
+
+
+# ---- tensor-core (tcgen05, split-bf16) filter GEMMs ------------------------------------------------------------
+@pytest.mark.parametrize('F,L,degrees,H', [(132, 3, (1, 2, 3), 4), (36, 2, (1, 2, 3), 4), (32, 2, (1, 2, 2, 3), 4)])
+def test_tensor_mode_matches_oracle(ethanol, solid, F, L, degrees, H):
+    from mlff_b200.capi import FLAG_TENSOR
+    cfg = o.OracleConfig(F=F, n_layers=L, degrees=degrees, n_heads=H)
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    eng = make(cfg, p, flags=FLAG_TENSOR)
+    B = 32
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(R, z, 5.0)
+    E, Fo, ea, st = run_ef(eng, R, z, nl['idx_i'], nl['idx_j'])
+    assert st == 0
+    Eo, Fr = o.energy_forces_batch(cfg, p, R, z, nl['idx_i'], nl['idx_j'])
+    scale = np.maximum(np.abs(Eo.numpy().reshape(-1)), np.abs(ea).sum(-1))
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= E_RTOL * scale).all()
+    assert np.abs(Fo - Fr.numpy()).max() < F_ATOL
+    assert np.abs(Fo - Fr.numpy()).max() < 1e-4 * np.abs(Fr.numpy()).max()
+    if F == 132:      # periodic solid: many tiles, partial last tile, several images per pair
+        g = golden('oracle_solid_pbc.npz')
+        eng2 = make(cfg, o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale'])), flags=FLAG_TENSOR)
+        E, F_, ea, st = run_ef(eng2, solid['R'][None], solid['z'][None], g['idx_i'][None], g['idx_j'][None],
+                               cell=solid['unit_cell'][None], off=g['shifts'][None])
+        assert st == 0
+        assert abs(E[0] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
+        assert np.abs(F_[0] - g['F']).max() < F_ATOL
