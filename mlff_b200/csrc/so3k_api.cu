@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 static std::atomic<uint64_t> g_launches{0};
@@ -41,6 +42,8 @@ struct HandleImpl : so3k_handle {
   unsigned char* tc_images = nullptr;
   std::vector<TcBlockW> tf, tg;      // per layer (tensor-core mode)
   bool use_tc = false;
+  int tc_parts = 3;                  // SO3K_TC_PARTS env: debugging aid to mix tensor-core / CUDA-core backward pieces
+  bool tc_fwd = true;
   Profiler prof;
 };
 
@@ -248,7 +251,7 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
     { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
     {
       PROF(CAT_EDGE_FWD);
-      if (h->use_tc) so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, dev_status, st);
+      if (h->use_tc && h->tc_fwd) so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, dev_status, st);
       else so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
     }
     { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
@@ -284,7 +287,13 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
     { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, xbar_nx, chibar_nx, w.alphabar, w.gproj, st); }
     {
       PROF(CAT_EDGE_BWD);
-      so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
+      // tc_parts: which backward pieces run on the tensor cores (bit 0: q/k gradients + cutoff cotangent,
+      // bit 1: radial + l0-contraction cotangents); the rest runs the fp32 CUDA-core kernel
+      const int tcp = h->use_tc ? h->tc_parts : 0;
+      if (tcp) so3k_launch_edge_bwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, w.alphabar, tcp, w.gproj, w.gbar, w.ebar,
+                                       dev_status, st);
+      if (tcp != 3) so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3 & ~tcp, w.gproj, w.gbar,
+                                         w.ebar, st);
       so3k_launch_edge_finish(D, w.g, alpha_t, chibar_nx, w.ebar, w.rbar, st);
     }
     if (t > 0) {
@@ -316,6 +325,11 @@ int so3k_create(const so3k_config* cfg, so3k_handle** out) {
   h->cfg = *cfg;
   h->dims = D;
   h->use_tc = (cfg->flags & SO3K_FLAG_TENSOR) != 0;
+  if (const char* e = getenv("SO3K_TC_PARTS")) {       // bit 0/1: backward pieces, bit 2: forward
+    int v = atoi(e);
+    h->tc_parts = v & 3;
+    h->tc_fwd = (v & 4) != 0;
+  }
   make_layout(D, &h->layout);
   *out = h;
   return SO3K_OK;

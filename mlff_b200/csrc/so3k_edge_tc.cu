@@ -1,23 +1,29 @@
-// Per-edge filter MLPs + attention coefficients on the 5th-generation tensor cores (tcgen05 + TMEM).
-//
-// Same math and same interface as k_edge_fwd (so3k_edge.cu):
+// Per-edge filter MLPs, attention coefficients and their data-gradients on the 5th-generation tensor cores
+// (tcgen05.mma + TMEM).  Same math and outputs as the fp32 CUDA-core kernels of so3k_edge.cu:
 //   chi_ij, l0 contraction     mlff/nn/layer/so3krates_layer.py:89-93 ; mlff/sph_ops/contract.py:181-188
 //   RadialSphericalFilter      mlff/nn/layer/so3krates_layer.py:449-465 ; MLP mlff/nn/mlp/mlp.py:21-27
 //   ConvAttentionCoefficients  mlff/nn/layer/so3krates_layer.py:568-586 ; masking/cutoff :500-501, :551-554
-// Design (one filter block -- fb or gb -- per launch, persistent CTAs, 1 CTA / SM, 256 threads):
-//   * the block's weights live in shared memory for the whole kernel as bf16 hi/lo operand images in the
-//     canonical no-swizzle K-major layout (so3k_tc.cuh): W1 (N=Fp, K=n_rbf) and W2c (N=Fp, K=KC) where the
-//     radial and the spherical second layers are stacked along K, so  w = [silu(a1) | silu(a_s)] @ W2c  is ONE GEMM;
-//   * a tile = 128 consecutive receiver-sorted edges = the M dimension of one UMMA (M=128, cta_group::1);
-//     thread t and thread t+128 own row t (TMEM lane t) and split its columns;
-//   * GEMM1  D1[128 x Fp] = rbf @ W1         (3 MMAs per 16-wide K step: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM)
-//     epilogue 1: tcgen05.ld -> +bias -> silu -> bf16 hi/lo split -> written straight into the A-operand image of
-//     GEMM2, together with the tiny spherical hidden layer (K = nl, CUDA cores);
-//   * GEMM2  D2[128 x Fp] = A1 @ W2c ;  epilogue 2: tcgen05.ld -> +bias -> * (q_i k_j) -> per-head sums -> alpha.
-//     q_i * k_j is gathered with full-line coalesced loads into the (by then dead) A1 region.
-//   The F-wide filter never exists outside TMEM/registers.
-// Algorithmic FLOPs per launch: 2 * P * (K*F + F*F + nl*F/4 + F*F/4); tensor work issued is 3x that
-// on padded shapes (Fp x KC).
+//   backward                   SURVEY.md appendix B (reverse of the above)
+//
+// Design (one filter block -- fb or gb -- per launch, persistent CTAs, 1 CTA / SM, 512 threads):
+//   * the block's weights live in shared memory for the whole kernel as bf16 hi/lo operand images in the canonical
+//     no-swizzle K-major layout (so3k_tc.cuh; measured at the tcgen05 issue floor, profiles/tc_mma_layout_bench.py):
+//     W1 (N=Fp, K=n_rbf) and W2c (N=Fp, K=KC) -- the radial and spherical second layers stacked along K, so
+//     w = [silu(a1) | silu(a_s)] @ W2c is ONE GEMM.  The backward reads the same W2c image as an MN-major operand
+//     (W2c^T) -- no transposed copy;
+//   * a tile = 128 consecutive receiver-sorted edges = M of one UMMA (M=128, cta_group::1).  Row r of the tile is
+//     TMEM lane r; warp w works on lane quadrant (w & 3) and on column quarter (w >> 2): 4 threads per row;
+//   * every product is 3 MMAs (hi*hi + lo*hi + hi*lo) accumulating in fp32 in TMEM;
+//   * epilogues read TMEM (tcgen05.ld 32x32b), do bias / silu / split in registers and write the NEXT GEMM's A-operand
+//     image directly; the F-wide filter w and its cotangent never leave the SM.
+// Kernels:
+//   k_edge_tc<0>      forward: rbf -> GEMM1 -> silu -> GEMM2 -> (w+b) q_i k_j -> per-head sums -> alpha
+//   k_edge_tc<1>      backward part 1: recompute w, qbar_i += sbar w k_j, kbar_i += sbar_rev w q_j (segmented
+//                     warp-shuffle reduction over receiver runs, one atomic per run), cutoff cotangent
+//   k_edge_bwd2_tc    backward part 2: wbar image -> GEMM3 (hbar = wbar W2c^T) -> radial cotangent (forward-mode
+//                     rbf' @ W1 from a second GEMM1) and l0-contraction cotangent
+// Algorithmic FLOPs per forward launch pair: 2 blocks x 2 P (K F + F^2 + nl F/4 + F^2/4); the tensor
+// pipe issues 3x that on padded shapes (Fp x KC).
 #include "so3k_internal.h"
 #include "so3k_edge.h"
 #ifndef SO3K_EMU
@@ -25,8 +31,11 @@
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 512;        // threads per CTA
+constexpr int NW = NT / 32;    // warps
 constexpr int TM = 128;        // edges per tile
+constexpr int WIN = 32;        // column window of the backward staging tiles
+constexpr int WS = 36;         // row stride (floats) of a staging tile: 36 mod 32 = 4 -> conflict-free LDS.128
 
 struct TcDims {
   int Fp, KC, K0, QS;          // padded N, padded K of GEMM2, K of GEMM1, row stride (floats) of the qk tile
@@ -52,12 +61,18 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   t.off_W1 = 0;
   t.off_W2 = t.off_W1 + 2 * t.szW1;
   t.off_A1 = t.off_W2 + 2 * t.szW2;
-  uint32_t a1_region = 2 * t.szA1;
-  uint32_t qk_bytes = (uint32_t)TM * t.QS * 4u;
-  if (qk_bytes > a1_region) a1_region = qk_bytes;
-  t.off_small = t.off_A1 + ((a1_region + 127u) & ~127u);
-  // small arrays: b1p, b2p (Fp each), Ws1 (nl*Fs), bs1 (Fs), s_phi (TM), s_g (TM*nl), s_part (TM*8*2), s_i, s_j (TM)
-  uint32_t small = 4u * (2u * t.Fp + (uint32_t)D.nl * D.Fs + D.Fs + TM + TM * D.nl + TM * 16 + 2 * TM);
+  uint32_t region = 2 * t.szA1;                                         // A1 hi | lo
+  const uint32_t qk_bytes = (uint32_t)TM * t.QS * 4u;                    // forward: q_i * k_j tile
+  if (qk_bytes > region) region = qk_bytes;
+  const uint32_t stage_bytes = 3u * TM * WS * 4u;                        // backward 1: QI | KJ | QJ windows
+  if (stage_bytes > region) region = stage_bytes;
+  const uint32_t wb_bytes = 2u * (uint32_t)(TM / 8) * (uint32_t)(t.Fp / 8) * 128u;   // backward 2: wbar image
+  if (wb_bytes > region) region = wb_bytes;
+  if (4u * t.szA0 > region) region = 4u * t.szA0;                        // backward 2: rbf and rbf' images
+  t.off_small = t.off_A1 + ((region + 127u) & ~127u);
+  // small arrays (floats): b1p, b2p (Fp each), Ws1 (nl*Fs), bs1 (Fs), s_phi (TM), s_g (TM*nl), s_part (TM*16),
+  //                        s_i, s_j (TM each), s_head (Fp bytes, rounded to Fp/4 words + 4)
+  uint32_t small = 4u * (2u * t.Fp + (uint32_t)D.nl * D.Fs + D.Fs + TM + TM * D.nl + TM * 16 + 2 * TM + t.Fp / 4 + 4);
   t.total = t.off_small + ((small + 127u) & ~127u);
   return t;
 }
@@ -104,21 +119,233 @@ __device__ __forceinline__ float silu_fast(float a) {
   // silu(a) = a / (1 + exp(-a)); ex2.approx + fast division (rel. error ~1e-7, far below the bf16x3 GEMM error)
   return __fdividef(a, 1.0f + __expf(-a));
 }
+__device__ __forceinline__ void silu_fast_d(float a, float* y, float* dy) {
+  float s = __fdividef(1.0f, 1.0f + __expf(-a));
+  *y = a * s;
+  *dy = s * (1.0f + a * (1.0f - s));
+}
+__device__ __forceinline__ float cutoff_fast(float d, float r_cut) {
+  // argument in [0, pi): __cosf absolute error ~2^-21
+  return d < r_cut ? 0.5f * (__cosf(d * (3.14159265358979323846f / r_cut)) + 1.0f) : 0.0f;
+}
 
+// shared-memory carve-up common to the tensor-core edge kernels
+struct TcSmem {
+  unsigned char *W1hi, *W1lo, *W2hi, *W2lo, *A1hi, *A1lo, *A0hi, *A0lo;
+  float *region;                 // start of the A1 region viewed as floats (staging tiles alias it)
+  float *b1p, *b2p, *Ws1, *bs1, *s_phi, *s_g, *s_part;
+  int *s_i, *s_j;
+  unsigned char* s_head;         // head index of every feature column
+};
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* smem, const TcDims& T, const So3kDims& D) {
+  TcSmem S;
+  S.W1hi = smem + T.off_W1;
+  S.W1lo = S.W1hi + T.szW1;
+  S.W2hi = smem + T.off_W2;
+  S.W2lo = S.W2hi + T.szW2;
+  S.A1hi = smem + T.off_A1;
+  S.A1lo = S.A1hi + T.szA1;
+  S.A0hi = S.A1hi;               // aliased: dead once GEMM1 has completed
+  S.A0lo = S.A1lo;
+  S.region = reinterpret_cast<float*>(smem + T.off_A1);
+  S.b1p = reinterpret_cast<float*>(smem + T.off_small);
+  S.b2p = S.b1p + T.Fp;
+  S.Ws1 = S.b2p + T.Fp;
+  S.bs1 = S.Ws1 + D.nl * D.Fs;
+  S.s_phi = S.bs1 + D.Fs;
+  S.s_g = S.s_phi + TM;
+  S.s_part = S.s_g + TM * D.nl;  // TM * 16 floats of scratch
+  S.s_i = reinterpret_cast<int*>(S.s_part + TM * 16);
+  S.s_j = S.s_i + TM;
+  S.s_head = reinterpret_cast<unsigned char*>(S.s_j + TM);
+  return S;
+}
+
+__device__ __forceinline__ void tc_setup(unsigned char* smem, const TcDims& T, const So3kDims& D, const TcSmem& S, int dhd,
+                                         const unsigned char* __restrict__ img, const float* __restrict__ bias_g,
+                                         const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g) {
+  const uint4* src = reinterpret_cast<const uint4*>(img);
+  uint4* dst = reinterpret_cast<uint4*>(smem);
+  const int n16 = (int)((2 * T.szW1 + 2 * T.szW2) / 16);
+  for (int k = threadIdx.x; k < n16; k += NT) dst[k] = src[k];
+  for (int k = threadIdx.x; k < 2 * T.Fp; k += NT) S.b1p[k] = bias_g[k];
+  for (int k = threadIdx.x; k < D.nl * D.Fs; k += NT) S.Ws1[k] = Ws1_g[k];
+  for (int k = threadIdx.x; k < D.Fs; k += NT) S.bs1[k] = bs1_g[k];
+  for (int k = threadIdx.x; k < T.Fp; k += NT) S.s_head[k] = (unsigned char)(k < D.F ? k / dhd : 0);
+}
+
+// one GEMM: D[128 x N] = A[128 x 16*ksteps] @ B^T, 3 MMAs per K step (hi*hi + lo*hi + hi*lo); single thread
+__device__ __forceinline__ void tc_issue_gemm(uint32_t tD, const unsigned char* Ahi, const unsigned char* Alo, uint32_t sboA,
+                                              const unsigned char* Bhi, const unsigned char* Blo, uint32_t sboB, int ksteps,
+                                              uint32_t idesc) {
+  uint32_t acc = 0;
+  const uint32_t ah = tc::smem_u32(Ahi), al = tc::smem_u32(Alo), bh = tc::smem_u32(Bhi), bl = tc::smem_u32(Blo);
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint32_t ko = (uint32_t)ks * 256u;
+    const uint64_t a_hi = tc::make_desc(ah + ko, 128u, sboA), a_lo = tc::make_desc(al + ko, 128u, sboA);
+    const uint64_t b_hi = tc::make_desc(bh + ko, 128u, sboB), b_lo = tc::make_desc(bl + ko, 128u, sboB);
+    tc::mma_bf16(tD, a_hi, b_hi, idesc, acc);
+    tc::mma_bf16(tD, a_lo, b_hi, idesc, 1);
+    tc::mma_bf16(tD, a_hi, b_lo, idesc, 1);
+    acc = 1;
+  }
+}
+
+#define TC_WAIT_OR_BAIL(bar, par)                              \
+  {                                                            \
+    bool ok_ = tc::mbar_wait(bar, par);                        \
+    if (__syncthreads_or(!ok_)) {                              \
+      if (threadIdx.x == 0 && status) atomicOr(status, 8);     \
+      break;                                                   \
+    }                                                          \
+    tc::fence_after_sync();                                    \
+  }
+
+// S0: per-edge metadata (receiver, sender, cutoff, l0 contraction of the chi difference) and the radial-basis
+// operand image(s).  WITH_D additionally writes the image of d rbf / d d.
+template <bool WITH_D>
+__device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, const TcSmem& S, int r, int qq, int e0, int ne,
+                                           const int* __restrict__ row, const int* __restrict__ col,
+                                           const float4* __restrict__ geom, const float* __restrict__ chi,
+                                           unsigned char* A0dhi, unsigned char* A0dlo) {
+  const bool valid = r < ne;
+  float d = 0.f;
+  if (valid) d = geom[e0 + r].w;
+  if (qq == 0) {
+    int i = 0, j = 0;
+    float gl[SO3K_MAXDEG];
+#pragma unroll
+    for (int l = 0; l < SO3K_MAXDEG; ++l) gl[l] = 0.f;
+    if (valid) {
+      i = row[e0 + r];
+      j = col[e0 + r];
+      for (int m = 0; m < D.M; ++m) {
+        const float c = chi[(size_t)j * D.M + m] - chi[(size_t)i * D.M + m];
+        const float cc = c * c * D.m_cg[m];
+        const int sg = D.m_seg[m];
+#pragma unroll
+        for (int l = 0; l < SO3K_MAXDEG; ++l) gl[l] += (l == sg) ? cc : 0.f;
+      }
+    }
+    S.s_i[r] = i; S.s_j[r] = j;
+    S.s_phi[r] = valid ? cutoff_fast(d, D.r_cut) : 0.f;
+#pragma unroll
+    for (int l = 0; l < SO3K_MAXDEG; ++l)
+      if (l < D.nl) S.s_g[r * D.nl + l] = gl[l];
+  }
+  const float ed = __expf(-d);
+  for (int c = qq; c < T.K0 / 8; c += 4) {     // this thread writes K chunks qq, qq+4, ... of its row
+    float v[8], dv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float t = ed - (D.mu0 + (float)(c * 8 + q) * D.dmu);
+      const float rb = valid ? __expf(-D.gamma * t * t) : 0.f;
+      v[q] = rb;
+      if (WITH_D) dv[q] = rb * 2.0f * D.gamma * t * ed;
+    }
+    tc::store_chunk8(S.A0hi, S.A0lo, tc::canon_off(r, c, T.sboA0), v);
+    if (WITH_D) tc::store_chunk8(A0dhi, A0dlo, tc::canon_off(r, c, T.sboA0), dv);
+  }
+}
+
+// spherical hidden unit c (< Fs), pre-activation: bs1[c] + sum_l g_l Ws1[l][c]
+__device__ __forceinline__ float hidden_pre(const So3kDims& D, const TcSmem& S, const float* gl, int c) {
+  float a = S.bs1[c];
+#pragma unroll
+  for (int l = 0; l < SO3K_MAXDEG; ++l)
+    if (l < D.nl) a = fmaf(gl[l], S.Ws1[l * D.Fs + c], a);
+  return a;
+}
+
+// epilogue 1: hidden activations of both MLP branches -> A1 operand image (K index: [h1 | h_s | 0])
+__device__ __forceinline__ void tc_epilogue1(const So3kDims& D, const TcDims& T, const TcSmem& S, uint32_t tD1,
+                                             uint32_t lane_sel, int r, int qq) {
+  const int F = D.F, Fs = D.Fs;
+  float gl[SO3K_MAXDEG];
+#pragma unroll
+  for (int l = 0; l < SO3K_MAXDEG; ++l) gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
+  const int nchunk_d = T.Fp / 8;
+  const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;
+  for (int cb = cbeg; cb < cend; cb += 2) {           // 2 TMEM loads in flight
+    float v[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (cb + u < cend) tc::tmem_ld8(tD1 + lane_sel + (uint32_t)((cb + u) * 8), v[u]);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (cb + u < cend) {
+        const int c0 = (cb + u) * 8;
+        if (c0 + 8 <= F) {                             // fast path: all radial hidden units
+          const float4 ba = *reinterpret_cast<const float4*>(S.b1p + c0);
+          const float4 bb = *reinterpret_cast<const float4*>(S.b1p + c0 + 4);
+          v[u][0] = silu_fast(v[u][0] + ba.x); v[u][1] = silu_fast(v[u][1] + ba.y);
+          v[u][2] = silu_fast(v[u][2] + ba.z); v[u][3] = silu_fast(v[u][3] + ba.w);
+          v[u][4] = silu_fast(v[u][4] + bb.x); v[u][5] = silu_fast(v[u][5] + bb.y);
+          v[u][6] = silu_fast(v[u][6] + bb.z); v[u][7] = silu_fast(v[u][7] + bb.w);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int k = c0 + q;
+            float y;
+            if (k < F) y = silu_fast(v[u][q] + S.b1p[k]);
+            else if (k - F < Fs) y = silu_fast(hidden_pre(D, S, gl, k - F));
+            else y = 0.f;
+            v[u][q] = y;
+          }
+        }
+        tc::store_chunk8(S.A1hi, S.A1lo, tc::canon_off(r, c0 >> 3, T.sboA1), v[u]);
+      }
+    }
+  }
+  // K chunks beyond the D1 columns: remaining spherical hidden units and zero padding
+  for (int ch = nchunk_d + qq; ch < T.KC / 8; ch += 4) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = ch * 8 + q;
+      v[q] = (k - F < Fs) ? silu_fast(hidden_pre(D, S, gl, k - F)) : 0.f;
+    }
+    tc::store_chunk8(S.A1hi, S.A1lo, tc::canon_off(r, ch, T.sboA1), v);
+  }
+}
+
+// segmented (by receiver run) reduction over the 32 rows of a warp; run heads end up with the run total
+struct SegMask { bool m1, m2, m4, m8, m16; };
+__device__ __forceinline__ float seg_reduce(float v, const SegMask& M) {
+  float t;
+  t = __shfl_down_sync(0xffffffffu, v, 1);  if (M.m1) v += t;
+  t = __shfl_down_sync(0xffffffffu, v, 2);  if (M.m2) v += t;
+  t = __shfl_down_sync(0xffffffffu, v, 4);  if (M.m4) v += t;
+  t = __shfl_down_sync(0xffffffffu, v, 8);  if (M.m8) v += t;
+  t = __shfl_down_sync(0xffffffffu, v, 16); if (M.m16) v += t;
+  return v;
+}
+__device__ __forceinline__ float sel8(const float* a, int h) {
+  float v = a[0];
+#pragma unroll
+  for (int x = 1; x < 8; ++x) v = (h == x) ? a[x] : v;
+  return v;
+}
+
+// MODE 0: forward  -> alpha[e][aoff + h]
+// MODE 1: backward part 1 (recomputes the tile's filter w) -> gproj q/k parts (atomics), ebar[e][1] (cutoff cotangent)
+template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
-k_edge_fwd_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __restrict__ n_valid,
-              const int* __restrict__ row, const int* __restrict__ col, const float4* __restrict__ geom,
-              const float* __restrict__ chi, const float* __restrict__ proj, const unsigned char* __restrict__ img,
-              const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
-              float* __restrict__ alpha, int* __restrict__ status) {
+k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __restrict__ n_valid,
+          const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ rev,
+          const float4* __restrict__ geom, const float* __restrict__ chi, const float* __restrict__ proj,
+          const unsigned char* __restrict__ img, const float* __restrict__ bias_g, const float* __restrict__ Ws1_g,
+          const float* __restrict__ bs1_g, float* __restrict__ alpha, const float* __restrict__ alphabar,
+          float* __restrict__ gproj, float* __restrict__ ebar, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r = 32 * (warp & 3) + lane;      // row of the tile / TMEM lane
-  const int hh = warp >> 2;                  // column half handled by this thread
-  const int F = D.F, nl = D.nl, Fs = D.Fs;
+  const int r = 32 * (warp & 3) + lane;      // row of the tile == TMEM lane
+  const int qq = warp >> 2;                  // column quarter handled by this thread
+  const int F = D.F;
   const int heads = blk ? D.nl : D.H;
   const int dhd = F / heads;
   const int aoff = blk ? D.H : 0;
@@ -126,42 +353,15 @@ k_edge_fwd_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __
   const int koff = 2 * F + (blk ? F : 0);
   const size_t F5 = 5 * (size_t)F;
   const float inv = 1.0f / sqrtf((float)dhd);
+  const TcSmem S = tc_carve(smem, T, D);
 
-  unsigned char* W1hi = smem + T.off_W1;
-  unsigned char* W1lo = W1hi + T.szW1;
-  unsigned char* W2hi = smem + T.off_W2;
-  unsigned char* W2lo = W2hi + T.szW2;
-  unsigned char* A1hi = smem + T.off_A1;
-  unsigned char* A1lo = A1hi + T.szA1;
-  unsigned char* A0hi = A1hi;                // aliased: dead once GEMM1 has completed
-  unsigned char* A0lo = A1lo;
-  float* qk = reinterpret_cast<float*>(smem + T.off_A1);   // aliased: A1 is dead once GEMM2 has completed
-  float* b1p = reinterpret_cast<float*>(smem + T.off_small);
-  float* b2p = b1p + T.Fp;
-  float* Ws1 = b2p + T.Fp;
-  float* bs1 = Ws1 + nl * Fs;
-  float* s_phi = bs1 + Fs;
-  float* s_g = s_phi + TM;
-  float* s_part = s_g + TM * nl;             // [TM][8][2]
-  int* s_i = reinterpret_cast<int*>(s_part + TM * 16);
-  int* s_j = s_i + TM;
-
-  // ---- one-time setup: TMEM, barriers, weights -----------------------------------------------------------
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
     tc::mbar_fence_init();
   }
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(img);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    const int n16 = (int)((2 * T.szW1 + 2 * T.szW2) / 16);
-    for (int k = tid; k < n16; k += NT) dst[k] = src[k];
-    for (int k = tid; k < 2 * T.Fp; k += NT) b1p[k] = bias_g[k];
-    for (int k = tid; k < nl * Fs; k += NT) Ws1[k] = Ws1_g[k];
-    for (int k = tid; k < Fs; k += NT) bs1[k] = bs1_g[k];
-  }
+  tc_setup(smem, T, D, S, dhd, img, bias_g, Ws1_g, bs1_g);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -171,9 +371,9 @@ k_edge_fwd_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __
   const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
   const uint32_t idesc = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
   const int nv = *n_valid;
-  const int half_cols = T.Fp / 2;            // D columns per thread (multiple of 8)
-  const int nchunk_d = T.Fp / 8;             // K chunks of A1 that come from D1 columns
-  const int nchunk_all = T.KC / 8;
+  const int nf4 = F / 4;
+  const int nchunk_d = T.Fp / 8;
+  const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;    // this thread's D2 chunks
 
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -182,189 +382,433 @@ k_edge_fwd_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
 
-    // ---- S0: per-edge metadata, radial basis -> A0 image ---------------------------------------------------
-    float ed = 1.0f;
-    {
-      int i = 0, j = 0;
-      float d = 0.f, ph = 0.f;
-      float gl[SO3K_MAXDEG];
-      for (int l = 0; l < nl; ++l) gl[l] = 0.f;
-      if (r < ne) {
-        const int e = e0 + r;
-        i = row[e];
-        j = col[e];
-        d = geom[e].w;
-        ph = so3k_cutoff(d, D.r_cut);
-        if (hh == 0) {
-          for (int m = 0; m < D.M; ++m) {
-            float c = chi[(size_t)j * D.M + m] - chi[(size_t)i * D.M + m];
-            gl[D.m_seg[m]] += c * c * D.m_cg[m];
-          }
-        }
-      }
-      ed = expf(-d);
-      if (hh == 0) {
-        s_i[r] = i; s_j[r] = j; s_phi[r] = ph;
-        for (int l = 0; l < nl; ++l) s_g[r * nl + l] = gl[l];
-      }
-      // rbf columns: this thread writes K chunks hh, hh+2, ... of its row
-      for (int c = hh; c < T.K0 / 8; c += 2) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (r < ne) ? so3k_rbf(ed, c * 8 + q, D) : 0.f;
-        tc::store_chunk8(A0hi, A0lo, tc::canon_off(r, c, T.sboA0), v);
-      }
-    }
+    tc_tile_s0<false>(D, T, S, r, qq, e0, ne, row, col, geom, chi, nullptr, nullptr);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    // ---- GEMM1 ------------------------------------------------------------------------------------------------
     if (tid == 0) {
       tc::fence_after_sync();
-      uint32_t acc = 0;
-      for (int ks = 0; ks < T.K0 / 16; ++ks) {
-        const uint32_t ko = (uint32_t)ks * 256u;
-        uint64_t a_hi = tc::make_desc(tc::smem_u32(A0hi) + ko, 128u, T.sboA0);
-        uint64_t a_lo = tc::make_desc(tc::smem_u32(A0lo) + ko, 128u, T.sboA0);
-        uint64_t b_hi = tc::make_desc(tc::smem_u32(W1hi) + ko, 128u, T.sboW1);
-        uint64_t b_lo = tc::make_desc(tc::smem_u32(W1lo) + ko, 128u, T.sboW1);
-        tc::mma_bf16(tD1, a_hi, b_hi, idesc, acc);
-        tc::mma_bf16(tD1, a_lo, b_hi, idesc, 1);
-        tc::mma_bf16(tD1, a_hi, b_lo, idesc, 1);
-        acc = 1;
-      }
+      tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc);
       tc::commit(&bars[0]);
     }
-    {
-      bool ok = tc::mbar_wait(&bars[0], par);
-      if (__syncthreads_or(!ok)) {
-        if (tid == 0 && status) atomicOr(status, 8);
-        break;
-      }
+    TC_WAIT_OR_BAIL(&bars[0], par);
+    tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
+      tc::commit(&bars[1]);
     }
-    tc::fence_after_sync();
-    // ---- epilogue 1: hidden activations -> A1 image ---------------------------------------------------------------
-    {
-      float gl[SO3K_MAXDEG];
-      for (int l = 0; l < nl; ++l) gl[l] = s_g[r * nl + l];
-      auto hidden_s = [&](int c) -> float {          // spherical hidden unit c (< Fs)
-        float a = bs1[c];
-        for (int l = 0; l < nl; ++l) a = fmaf(gl[l], Ws1[l * Fs + c], a);
-        return silu_fast(a);
-      };
-      for (int cc = 0; cc < half_cols / 8; ++cc) {
-        const int c0 = hh * half_cols + cc * 8;       // first column of this chunk (== K index in A1)
-        float v[8];
-        tc::tmem_ld8(tD1 + lane_sel + (uint32_t)c0, v);
-        tc::tmem_ld_wait();
+
+    if (MODE == 0) {
+      // ---- while GEMM2 runs: gather q_i * k_j for this warp's 8 rows into registers (full-line loads) ------------
+      float4 pq[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int k = c0 + q;
-          float y;
-          if (k < F) y = silu_fast(v[q] + b1p[k]);
-          else if (k - F < Fs) y = hidden_s(k - F);
-          else y = 0.f;
-          v[q] = y;
+      for (int u = 0; u < 8; ++u) {
+        const int rr = warp * 8 + u;
+        pq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < nf4) {
+          const float4 q = *reinterpret_cast<const float4*>(proj + (size_t)S.s_i[rr] * F5 + qoff + 4 * lane);
+          const float4 k = *reinterpret_cast<const float4*>(proj + (size_t)S.s_j[rr] * F5 + koff + 4 * lane);
+          pq[u] = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
         }
-        tc::store_chunk8(A1hi, A1lo, tc::canon_off(r, c0 >> 3, T.sboA1), v);
       }
-      // K chunks beyond the D1 columns: remaining spherical hidden units and zero padding
-      for (int ch = nchunk_d + hh; ch < nchunk_all; ch += 2) {
-        float v[8];
+      float4 px = make_float4(0.f, 0.f, 0.f, 0.f);   // float4 column 32 + qq of row r (F <= 144 -> at most 4 of them)
+      if (32 + qq < nf4) {
+        const float4 q = *reinterpret_cast<const float4*>(proj + (size_t)S.s_i[r] * F5 + qoff + 4 * (32 + qq));
+        const float4 k = *reinterpret_cast<const float4*>(proj + (size_t)S.s_j[r] * F5 + koff + 4 * (32 + qq));
+        px = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
+      }
+      TC_WAIT_OR_BAIL(&bars[1], par);
+      float* qk = S.region;                    // aliased: the A1 image is dead once GEMM2 has completed
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int k = ch * 8 + q;
-          v[q] = (k - F < Fs) ? hidden_s(k - F) : 0.f;
+      for (int u = 0; u < 8; ++u)
+        if (lane < nf4) *reinterpret_cast<float4*>(qk + (size_t)(warp * 8 + u) * T.QS + 4 * lane) = pq[u];
+      if (32 + qq < nf4) *reinterpret_cast<float4*>(qk + (size_t)r * T.QS + 4 * (32 + qq)) = px;
+#pragma unroll
+      for (int h = 0; h < 4; ++h) S.s_part[(r * 4 + qq) * 4 + h] = 0.f;     // [row][quarter][head slot]
+      __syncthreads();
+      // ---- epilogue 2: alpha_h = sum_{f in head h} (w_f + b_f) q_f k_f / sqrt(d_h) * phi ---------------------------
+      // a quarter (<= 40 columns) touches at most 4 heads; partial sums go to slot (head - first head of the quarter)
+      {
+        const float* qrow = qk + (size_t)r * T.QS;
+        const int f0 = cbeg * 8;
+        const int h0 = (f0 < F) ? S.s_head[f0] : 0;
+        float acc = 0.f;
+        int hcur = h0;
+        for (int cb = cbeg; cb < cend; cb += 2) {
+          float v[2][8];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (cb + u < cend) tc::tmem_ld8(tD2 + lane_sel + (uint32_t)((cb + u) * 8), v[u]);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c0 = (cb + u) * 8;
+            if (cb + u < cend && c0 < F) {
+              if (c0 + 8 <= F && S.s_head[c0 + 7] == hcur) {       // fast path: one head, no padding columns
+                const float4 qa = *reinterpret_cast<const float4*>(qrow + c0);
+                const float4 qb = *reinterpret_cast<const float4*>(qrow + c0 + 4);
+                const float4 ba = *reinterpret_cast<const float4*>(S.b2p + c0);
+                const float4 bb = *reinterpret_cast<const float4*>(S.b2p + c0 + 4);
+                acc = fmaf(v[u][0] + ba.x, qa.x, acc); acc = fmaf(v[u][1] + ba.y, qa.y, acc);
+                acc = fmaf(v[u][2] + ba.z, qa.z, acc); acc = fmaf(v[u][3] + ba.w, qa.w, acc);
+                acc = fmaf(v[u][4] + bb.x, qb.x, acc); acc = fmaf(v[u][5] + bb.y, qb.y, acc);
+                acc = fmaf(v[u][6] + bb.z, qb.z, acc); acc = fmaf(v[u][7] + bb.w, qb.w, acc);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int f = c0 + q;
+                  if (f < F) {
+                    const int hf = S.s_head[f];
+                    if (hf != hcur) {
+                      S.s_part[(r * 4 + qq) * 4 + (hcur - h0)] = acc;
+                      acc = 0.f;
+                      hcur = hf;
+                    }
+                    acc = fmaf(v[u][q] + S.b2p[f], qrow[f], acc);
+                  }
+                }
+              }
+            }
+          }
         }
-        tc::store_chunk8(A1hi, A1lo, tc::canon_off(r, ch, T.sboA1), v);
+        if (f0 < F) S.s_part[(r * 4 + qq) * 4 + (hcur - h0)] = acc;
+      }
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid < ne) {
+        const float ph = S.s_phi[tid];
+        float tot[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) tot[h] = 0.f;
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int f0 = ((nchunk_d * q4) / 4) * 8;
+          if (f0 >= F) break;
+          const int h0 = S.s_head[f0];
+          for (int s = 0; s < 4; ++s) {
+            const float p = S.s_part[(tid * 4 + q4) * 4 + s];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) tot[h] += (h == h0 + s) ? p : 0.f;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          if (h < heads) alpha[(size_t)(e0 + tid) * Ast + aoff + h] = tot[h] * inv * ph;
+        if (blk == 1)
+          for (int a = D.H + D.nl; a < Ast; ++a) alpha[(size_t)(e0 + tid) * Ast + a] = 0.f;
+      }
+      __syncthreads();      // qk tile / s_part fully consumed before the next tile overwrites the region
+    } else {
+      // ================= backward part 1 ========================================================================
+      // per row: ab[h] = alphabar[e][h] / sqrt(dh) ; abr[h] = alphabar[rev e][h] / sqrt(dh)
+      float ab[8], abr[8];
+      const float phi_r = S.s_phi[r];
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        ab[h] = 0.f;
+        abr[h] = 0.f;
+        if (h < heads && r < ne) {
+          ab[h] = alphabar[(size_t)(e0 + r) * Ast + aoff + h] * inv;
+          abr[h] = alphabar[(size_t)rev[e0 + r] * Ast + aoff + h] * inv;
+        }
+      }
+      // receiver runs inside this warp's 32 rows (rows are receiver-sorted)
+      SegMask SM;
+      bool run_head;
+      const int my_i = (r < ne) ? S.s_i[r] : -1 - r;           // invalid rows form runs of their own
+      {
+        const int i1 = __shfl_down_sync(0xffffffffu, my_i, 1), i2 = __shfl_down_sync(0xffffffffu, my_i, 2);
+        const int i4 = __shfl_down_sync(0xffffffffu, my_i, 4), i8 = __shfl_down_sync(0xffffffffu, my_i, 8);
+        const int i16 = __shfl_down_sync(0xffffffffu, my_i, 16);
+        const int ip = __shfl_up_sync(0xffffffffu, my_i, 1);
+        SM.m1 = lane + 1 < 32 && i1 == my_i;
+        SM.m2 = lane + 2 < 32 && i2 == my_i;
+        SM.m4 = lane + 4 < 32 && i4 == my_i;
+        SM.m8 = lane + 8 < 32 && i8 == my_i;
+        SM.m16 = lane + 16 < 32 && i16 == my_i;
+        run_head = (r < ne) && (lane == 0 || ip != my_i);
+      }
+      TC_WAIT_OR_BAIL(&bars[1], par);
+      // staging tiles (alias the dead A1 image): QI, KJ, QJ, each [TM][WS] floats, column window of WIN
+      float* QI = S.region;
+      float* KJ = QI + TM * WS;
+      float* QJ = KJ + TM * WS;
+      float phibar = 0.f;
+      for (int w0 = 0; w0 < T.Fp; w0 += WIN) {
+        // ---- gather the window [w0, w0+32) of q_i, k_j, q_j: lane -> (row of 4, float4 of 8); 8 rows per warp -------
+        {
+          const int sub = lane >> 3, f4 = lane & 7;
+          const int f = w0 + 4 * f4;
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int rr = warp * 8 + 4 * u + sub;
+            float4 qi = make_float4(0.f, 0.f, 0.f, 0.f), kj = qi, qj = qi;
+            if (f < F) {
+              const float* pi = proj + (size_t)S.s_i[rr] * F5;
+              const float* pj = proj + (size_t)S.s_j[rr] * F5;
+              qi = *reinterpret_cast<const float4*>(pi + qoff + f);
+              kj = *reinterpret_cast<const float4*>(pj + koff + f);
+              qj = *reinterpret_cast<const float4*>(pj + qoff + f);
+            }
+            *reinterpret_cast<float4*>(QI + rr * WS + 4 * f4) = qi;
+            *reinterpret_cast<float4*>(KJ + rr * WS + 4 * f4) = kj;
+            *reinterpret_cast<float4*>(QJ + rr * WS + 4 * f4) = qj;
+          }
+        }
+        __syncthreads();
+        // ---- this thread's 8 columns of the window -------------------------------------------------------------------
+        const int c0 = w0 + qq * 8;                      // warp-uniform
+        if (c0 < F) {
+          float v[8];
+          tc::tmem_ld8(tD2 + lane_sel + (uint32_t)c0, v);
+          float qi[8], kj[8], qj[8];
+          *reinterpret_cast<float4*>(qi) = *reinterpret_cast<const float4*>(QI + r * WS + qq * 8);
+          *reinterpret_cast<float4*>(qi + 4) = *reinterpret_cast<const float4*>(QI + r * WS + qq * 8 + 4);
+          *reinterpret_cast<float4*>(kj) = *reinterpret_cast<const float4*>(KJ + r * WS + qq * 8);
+          *reinterpret_cast<float4*>(kj + 4) = *reinterpret_cast<const float4*>(KJ + r * WS + qq * 8 + 4);
+          *reinterpret_cast<float4*>(qj) = *reinterpret_cast<const float4*>(QJ + r * WS + qq * 8);
+          *reinterpret_cast<float4*>(qj + 4) = *reinterpret_cast<const float4*>(QJ + r * WS + qq * 8 + 4);
+          tc::tmem_ld_wait();
+          int h = S.s_head[c0];
+          float abh = sel8(ab, h), abrh = sel8(abr, h);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int f = c0 + q;                        // warp-uniform
+            if (f < F) {
+              const int hf = S.s_head[f];
+              if (hf != h) {
+                h = hf;
+                abh = sel8(ab, h);
+                abrh = sel8(abr, h);
+              }
+              const float wv = v[q] + S.b2p[f];
+              phibar = fmaf(abh * wv, qi[q] * kj[q], phibar);      // alphabar_h * s_h accumulated over h
+              const float cq = seg_reduce(abh * phi_r * wv * kj[q], SM);
+              const float ck = seg_reduce(abrh * phi_r * wv * qj[q], SM);
+              if (run_head) {
+                atomicAdd(&gproj[(size_t)my_i * F5 + qoff + f], cq);
+                atomicAdd(&gproj[(size_t)my_i * F5 + koff + f], ck);
+              }
+            }
+          }
+        }
+        __syncthreads();       // window consumed before the next gather overwrites it
+      }
+      // combine the four column quarters of a row through shared memory
+      S.s_part[r * 4 + qq] = phibar;
+      __syncthreads();
+      if (tid < ne) {
+        const float pb = S.s_part[tid * 4] + S.s_part[tid * 4 + 1] + S.s_part[tid * 4 + 2] + S.s_part[tid * 4 + 3];
+        float* dst = ebar + 2 * (size_t)(e0 + tid) + 1;
+        if (blk == 0) *dst = pb; else *dst += pb;
+      }
+      __syncthreads();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// Backward part 2: radial cotangent and l0-contraction cotangent of one filter block.
+//   wbar[e][f] = alphabar[e][h(f)] phi q_i[f] k_j[f] / sqrt(d_h)      (built straight into an A-operand image)
+//   hbar = wbar @ W2c^T                                                 (GEMM3: the W2c image consumed MN-major)
+//   dbar_rad[e] += sum_c hbar[c] silu'(a1[c]) (rbf'(d) @ W1)[c]         (a1 and the forward-mode term from 2 GEMM1s)
+//   gbar[e][l]  += sum_c hbar_s[c] silu'(a_s[c]) Ws1[l][c]
+__global__ void __launch_bounds__(NT, 1)
+k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, const int* __restrict__ n_valid,
+               const int* __restrict__ row, const int* __restrict__ col, const float4* __restrict__ geom,
+               const float* __restrict__ chi, const float* __restrict__ proj, const unsigned char* __restrict__ img,
+               const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
+               const float* __restrict__ alphabar, float* __restrict__ gbar, float* __restrict__ ebar,
+               int* __restrict__ status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bars[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = 32 * (warp & 3) + lane;
+  const int qq = warp >> 2;
+  const int F = D.F, Fs = D.Fs;
+  const int heads = blk ? D.nl : D.H;
+  const int dhd = F / heads;
+  const int aoff = blk ? D.H : 0;
+  const int qoff = blk ? F : 0;
+  const int koff = 2 * F + (blk ? F : 0);
+  const size_t F5 = 5 * (size_t)F;
+  const float inv = 1.0f / sqrtf((float)dhd);
+  TcSmem S = tc_carve(smem, T, D);
+  // four radial-basis images packed at the start of the region: rbf hi | rbf lo | rbf' hi | rbf' lo
+  S.A0hi = reinterpret_cast<unsigned char*>(S.region);
+  S.A0lo = S.A0hi + T.szA0;
+  unsigned char* A0dhi = S.A0hi + 2 * T.szA0;
+  unsigned char* A0dlo = S.A0hi + 3 * T.szA0;
+  const uint32_t sboWb = (uint32_t)(T.Fp / 8) * 128u;
+  const uint32_t szWb = (uint32_t)(TM / 8) * sboWb;
+  unsigned char* Wbhi = reinterpret_cast<unsigned char*>(S.region);   // aliases the rbf images: dead once the GEMM1s are done
+  unsigned char* Wblo = Wbhi + szWb;
+  float* s_ab = S.s_part;                       // [TM][8]  alphabar * phi / sqrt(dh) per head
+  float* s_red = S.s_part + TM * 8;             // [TM][8]  cross-quarter reduction (dbar, gbar_l)
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::mbar_fence_init();
+  }
+  tc_setup(smem, T, D, S, dhd, img, bias_g, Ws1_g, bs1_g);
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tD1 = tmem, tD1p = tmem + (uint32_t)T.Fp, tD3 = tmem + 2u * (uint32_t)T.Fp;
+  const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
+  const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
+  const uint32_t idesc3 = tc::make_idesc_bf16(TM, T.KC, 0, 1);     // B = W2c image read MN-major
+  const int nv = *n_valid;
+  const int nchunkF = T.Fp / 8;
+  const int nchunkK = T.KC / 8;
+  const int kcb = (nchunkK * qq) / 4, kce = (nchunkK * (qq + 1)) / 4;   // this thread's hidden-column chunks
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int e0 = tile * TM;
+    if (e0 >= nv) break;
+    const int ne = (nv - e0) < TM ? (nv - e0) : TM;
+    const uint32_t par = it & 1u;
+
+    tc_tile_s0<true>(D, T, S, r, qq, e0, ne, row, col, geom, chi, A0dhi, A0dlo);
+    if (qq == 1) {
+      const float ph = (r < ne) ? cutoff_fast(geom[e0 + r].w, D.r_cut) * inv : 0.f;
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        s_ab[r * 8 + h] = (h < heads && r < ne) ? alphabar[(size_t)(e0 + r) * Ast + aoff + h] * ph : 0.f;
+    }
+    if (qq == 2) {
+#pragma unroll
+      for (int h = 0; h < 8; ++h) s_red[r * 8 + h] = 0.f;
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
+      tc_issue_gemm(tD1p, A0dhi, A0dlo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
+      tc::commit(&bars[0]);
+    }
+    // ---- wbar image: work item = (row group of 8 rows, column group of 4 chunks): lane -> (row = lane / 4, chunk = lane % 4)
+    const int ncg = (nchunkF + 3) / 4;
+    const int nitems = 16 * ncg;
+    TC_WAIT_OR_BAIL(&bars[0], par);
+    for (int item = warp; item < nitems; item += NW) {
+      const int rg = item / ncg, cg = item - rg * ncg;
+      const int rr = rg * 8 + (lane >> 2);
+      const int c = cg * 4 + (lane & 3);
+      if (c < nchunkF) {
+        const int f0 = c * 8;
+        float wv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) wv[q] = 0.f;
+        if (f0 < F) {
+          const float* qi = proj + (size_t)S.s_i[rr] * F5 + qoff + f0;
+          const float* kj = proj + (size_t)S.s_j[rr] * F5 + koff + f0;
+          const float4 qa = *reinterpret_cast<const float4*>(qi);
+          const float4 ka = *reinterpret_cast<const float4*>(kj);
+          float4 qb = make_float4(0.f, 0.f, 0.f, 0.f), kb = qb;
+          if (f0 + 4 < F) {
+            qb = *reinterpret_cast<const float4*>(qi + 4);
+            kb = *reinterpret_cast<const float4*>(kj + 4);
+          }
+          const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          const float kv[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+          const float* sab = s_ab + rr * 8;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) wv[q] = (f0 + q < F) ? sab[S.s_head[f0 + q]] * qv[q] * kv[q] : 0.f;
+        }
+        tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rr, c, sboWb), wv);
       }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    // ---- GEMM2 ------------------------------------------------------------------------------------------------
+    // ---- GEMM3: hbar[128 x KC] = wbar[128 x Fp] @ W2c^T --------------------------------------------------------------
     if (tid == 0) {
       tc::fence_after_sync();
       uint32_t acc = 0;
-      for (int ks = 0; ks < T.KC / 16; ++ks) {
-        const uint32_t ko = (uint32_t)ks * 256u;
-        uint64_t a_hi = tc::make_desc(tc::smem_u32(A1hi) + ko, 128u, T.sboA1);
-        uint64_t a_lo = tc::make_desc(tc::smem_u32(A1lo) + ko, 128u, T.sboA1);
-        uint64_t b_hi = tc::make_desc(tc::smem_u32(W2hi) + ko, 128u, T.sboW2);
-        uint64_t b_lo = tc::make_desc(tc::smem_u32(W2lo) + ko, 128u, T.sboW2);
-        tc::mma_bf16(tD2, a_hi, b_hi, idesc, acc);
-        tc::mma_bf16(tD2, a_lo, b_hi, idesc, 1);
-        tc::mma_bf16(tD2, a_hi, b_lo, idesc, 1);
+      const uint32_t ah = tc::smem_u32(Wbhi), al = tc::smem_u32(Wblo), bh = tc::smem_u32(S.W2hi), bl = tc::smem_u32(S.W2lo);
+      for (int ks = 0; ks < T.Fp / 16; ++ks) {
+        const uint32_t ao = (uint32_t)ks * 256u;
+        const uint32_t bo = (uint32_t)ks * 2u * T.sboW2;
+        const uint64_t a_hi = tc::make_desc(ah + ao, 128u, sboWb), a_lo = tc::make_desc(al + ao, 128u, sboWb);
+        const uint64_t b_hi = tc::make_desc(bh + bo, T.sboW2, 128u), b_lo = tc::make_desc(bl + bo, T.sboW2, 128u);
+        tc::mma_bf16(tD3, a_hi, b_hi, idesc3, acc);
+        tc::mma_bf16(tD3, a_lo, b_hi, idesc3, 1);
+        tc::mma_bf16(tD3, a_hi, b_lo, idesc3, 1);
         acc = 1;
       }
       tc::commit(&bars[1]);
     }
-    {
-      bool ok = tc::mbar_wait(&bars[1], par);
-      if (__syncthreads_or(!ok)) {
-        if (tid == 0 && status) atomicOr(status, 8);
-        break;
-      }
-    }
-    tc::fence_after_sync();
-    // ---- gather q_i * k_j into the (dead) A1 region: one warp per row, full-line loads ---------------------------
-    for (int rr = warp; rr < TM; rr += NT / 32) {
-      const float* qi = proj + (size_t)s_i[rr] * F5 + qoff;
-      const float* kj = proj + (size_t)s_j[rr] * F5 + koff;
-      for (int c4 = lane; c4 < F / 4; c4 += 32) {
-        float4 q = *reinterpret_cast<const float4*>(qi + 4 * c4);
-        float4 k = *reinterpret_cast<const float4*>(kj + 4 * c4);
-        *reinterpret_cast<float4*>(qk + (size_t)rr * T.QS + 4 * c4) = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
-      }
-    }
+    float gl[SO3K_MAXDEG], gb[SO3K_MAXDEG];
 #pragma unroll
-    for (int h = 0; h < 8; ++h) s_part[(r * 8 + h) * 2 + hh] = 0.f;
-    __syncthreads();
-    // ---- epilogue 2: alpha_h = sum_{f in head h} (w_f + b_f) q_f k_f / sqrt(d_h) * phi -------------------------------
+    for (int l = 0; l < SO3K_MAXDEG; ++l) {
+      gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
+      gb[l] = 0.f;
+    }
+    TC_WAIT_OR_BAIL(&bars[1], par);
+    // ---- epilogue: this thread's quarter of the KC hidden columns of its row ------------------------------------------------
     {
-      const int f_begin = hh * half_cols;
-      int h = f_begin / dhd;
-      int nb = (h + 1) * dhd;
-      float acc = 0.f;
-      const float* qrow = qk + (size_t)r * T.QS;
-      for (int cc = 0; cc < half_cols / 8; ++cc) {
-        const int c0 = f_begin + cc * 8;
-        float v[8];
-        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)c0, v);
-        tc::tmem_ld_wait();
+      float dbar = 0.f;
+      for (int cc = kcb; cc < kce; ++cc) {
+        const int c0 = cc * 8;
+        if (c0 >= F + Fs) break;                  // warp-uniform: only zero padding left
+        float hb[8], a1[8], tp[8];
+        tc::tmem_ld8(tD3 + lane_sel + (uint32_t)c0, hb);
         if (c0 < F) {
-          float4 qa = *reinterpret_cast<const float4*>(qrow + c0);
-          float4 qb = (c0 + 4 < F) ? *reinterpret_cast<const float4*>(qrow + c0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          tc::tmem_ld8(tD1 + lane_sel + (uint32_t)c0, a1);
+          tc::tmem_ld8(tD1p + lane_sel + (uint32_t)c0, tp);
+        }
+        tc::tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int f = c0 + q;
-            if (f < F) {
-              if (f == nb) {
-                s_part[(r * 8 + h) * 2 + hh] = acc;
-                acc = 0.f;
-                ++h;
-                nb += dhd;
-              }
-              acc = fmaf(v[q] + b2p[f], qq[q], acc);
-            }
+        for (int q = 0; q < 8; ++q) {
+          const int k = c0 + q;
+          if (k < F) {
+            float y, dy;
+            silu_fast_d(a1[q] + S.b1p[k], &y, &dy);
+            dbar = fmaf(hb[q] * dy, tp[q], dbar);
+          } else if (k - F < Fs) {
+            const int c = k - F;
+            float y, dy;
+            silu_fast_d(hidden_pre(D, S, gl, c), &y, &dy);
+            const float as = hb[q] * dy;
+#pragma unroll
+            for (int l = 0; l < SO3K_MAXDEG; ++l)
+              if (l < D.nl) gb[l] = fmaf(as, S.Ws1[l * Fs + c], gb[l]);
           }
         }
       }
-      if (f_begin < F) s_part[(r * 8 + h) * 2 + hh] = acc;
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (tid < ne) {
-      const float ph = s_phi[tid];
-      for (int h = 0; h < heads; ++h) {
-        float s = s_part[(tid * 8 + h) * 2 + 0] + s_part[(tid * 8 + h) * 2 + 1];
-        alpha[(size_t)(e0 + tid) * Ast + aoff + h] = s * inv * ph;
+      // cross-quarter combination: 4 contributions per slot through shared-memory atomics
+      atomicAdd(&s_red[r * 8 + 0], dbar);
+#pragma unroll
+      for (int l = 0; l < SO3K_MAXDEG; ++l)
+        if (l < D.nl && l < 7) atomicAdd(&s_red[r * 8 + 1 + l], gb[l]);
+      tc::fence_before_sync();
+      __syncthreads();
+      if (qq == 0 && r < ne) {
+        const size_t e = (size_t)(e0 + r);
+        const float db = s_red[r * 8 + 0];
+        if (blk == 0) ebar[2 * e] = db; else ebar[2 * e] += db;
+        for (int l = 0; l < D.nl; ++l) {
+          const float gsum = s_red[r * 8 + 1 + l];
+          if (blk == 0) gbar[e * Gst + l] = gsum; else gbar[e * Gst + l] += gsum;
+        }
       }
-      if (blk == 1)
-        for (int a = D.H + D.nl; a < Ast; ++a) alpha[(size_t)(e0 + tid) * Ast + a] = 0.f;
     }
-    __syncthreads();      // qk tile / s_part fully consumed before the next tile overwrites the region
+    __syncthreads();
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -377,7 +821,9 @@ bool so3k_edge_tc_supported(const So3kDims& D) {
   if (D.F % 4 != 0 || D.K % 16 != 0) return false;
   TcDims T = make_tc_dims(D);
   if (T.Fp > 256 || T.Fp % 16 != 0) return false;
-  if (D.H > 8 || D.nl > 8) return false;
+  if (D.H > 8 || D.nl > 7) return false;
+  if (2 * T.Fp + T.KC > 512 || T.Fp > 144) return false;      // TMEM columns ; tail float4 handling of the qk gather
+  if (D.F / D.H < 8 || D.F / D.nl < 8) return false;            // a column quarter must not span more than 4 heads
   return T.total + 1024 <= 227u * 1024u;
 }
 
@@ -401,25 +847,56 @@ void so3k_edge_tc_build(const So3kDims& D, const float* p, const BlockParams& bp
   out->bs1 = simt.bs1;
 }
 
+static int tc_grid(int n_tiles, const TcDims& T) {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_edge_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
+    cudaFuncSetAttribute(k_edge_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
+    cudaFuncSetAttribute(k_edge_bwd2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
+  }
+  return n_tiles < n_sm ? n_tiles : n_sm;
+}
+
 void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
                              const float* proj, float* alpha, int* status, cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
   int Ast = (D.H + D.nl + 3) & ~3;
   int n_tiles = so3k_cdiv(g.Pt, TM);
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_edge_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
-  }
-  int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  int grid = tc_grid(n_tiles, T);
   for (int blk = 0; blk < 2; ++blk) {
     const TcBlockW& W = blk ? Wg : Wf;
     so3k_count_launch();
-    k_edge_fwd_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.geom, chi, proj,
-                                                     W.img, W.bias, W.Ws1, W.bs1, alpha, status);
+    k_edge_tc<0><<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.rev, g.geom, chi, proj,
+                                                    W.img, W.bias, W.Ws1, W.bs1, alpha, nullptr, nullptr, nullptr, status);
+  }
+}
+
+// parts: bit 0 -> q/k projection gradients + cutoff cotangent (ebar[e][1]) ; bit 1 -> radial cotangent (ebar[e][0]) + gbar
+void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
+                             const float* proj, const float* alphabar, int parts, float* gproj, float* gbar, float* ebar,
+                             int* status, cudaStream_t st) {
+  if (g.Pt <= 0) return;
+  TcDims T = make_tc_dims(D);
+  int Ast = (D.H + D.nl + 3) & ~3;
+  int Gst = (D.nl + 3) & ~3;
+  int n_tiles = so3k_cdiv(g.Pt, TM);
+  int grid = tc_grid(n_tiles, T);
+  for (int blk = 0; blk < 2; ++blk) {
+    const TcBlockW& W = blk ? Wg : Wf;
+    if (parts & 1) {
+      so3k_count_launch();
+      k_edge_tc<1><<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.rev, g.geom, chi,
+                                                      proj, W.img, W.bias, W.Ws1, W.bs1, nullptr, alphabar, gproj, ebar, status);
+    }
+    if (parts & 2) {
+      so3k_count_launch();
+      k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, Gst, n_tiles, g.n_valid, g.row, g.col, g.geom, chi, proj,
+                                                        W.img, W.bias, W.Ws1, W.bs1, alphabar, gbar, ebar, status);
+    }
   }
 }
 #else
@@ -429,4 +906,6 @@ void so3k_edge_tc_build(const So3kDims&, const float*, const BlockParams&, unsig
                         cudaStream_t) {}
 void so3k_launch_edge_fwd_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
                              float*, int*, cudaStream_t) {}
+void so3k_launch_edge_bwd_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
+                             const float*, int, float*, float*, float*, int*, cudaStream_t) {}
 #endif

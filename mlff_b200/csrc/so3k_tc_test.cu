@@ -88,6 +88,50 @@ k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+
+// Micro-benchmark: cycles per tcgen05.mma (M=128, N, K=16, bf16) for the two operand layouts.
+// layout 0: canonical no-swizzle (LBO=128, SBO=(K/8)*128) ; layout 2: SWIZZLE_128B K-major (64-wide K blocks, SBO=1024)
+__global__ void __launch_bounds__(128)
+k_tc_bench(int N, int layout, int reps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+  for (int k = tid; k < 48 * 1024 / 4; k += 128) reinterpret_cast<uint32_t*>(smem)[k] = 0x3f803f80u;
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+    const uint32_t a0 = tc::smem_u32(smem), b0 = a0 + 20 * 1024;      // A: 128 x 64 (16 KB) ; B: N x 64 (<= 32 KB... N<=224)
+    long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+      for (int ks = 0; ks < 4; ++ks) {
+        uint64_t ad, bd;
+        if (layout == 0) {
+          ad = tc::make_desc(a0 + ks * 256, 128u, 8 * 128u);
+          bd = tc::make_desc(b0 + ks * 256, 128u, 8 * 128u);
+        } else {
+          ad = tc::make_desc(a0 + ks * 32, 16u, 1024u) | ((uint64_t)2 << 61);
+          bd = tc::make_desc(b0 + ks * 32, 16u, 1024u) | ((uint64_t)2 << 61);
+        }
+        tc::mma_bf16(tmem, ad, bd, idesc, 1);
+      }
+    }
+    tc::commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+    out[1] = (long long)reps * 4;
+  }
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
 }  // namespace
 #endif
 
@@ -103,6 +147,18 @@ extern "C" int so3k_tc_selftest(int32_t N, int32_t K, int32_t variant, int32_t p
   cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   so3k_count_launch();
   k_tc_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(N, K, variant, passes, A, B, D);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+#endif
+}
+
+extern "C" int so3k_tc_bench(int32_t N, int32_t layout, int32_t reps, long long* out_dev, void* stream) {
+#ifdef SO3K_EMU
+  (void)N; (void)layout; (void)reps; (void)out_dev; (void)stream;
+  return SO3K_ERR_CONFIG;
+#else
+  cudaFuncSetAttribute(k_tc_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  so3k_count_launch();
+  k_tc_bench<<<1, 128, 64 * 1024, (cudaStream_t)stream>>>(N, layout, reps, out_dev);
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
 #endif
 }
