@@ -28,11 +28,15 @@
 #include "so3k_edge.h"
 #ifndef SO3K_EMU
 #include "so3k_tc.cuh"
+#include <cstdio>
+#include <cstring>
 
 namespace {
 
-constexpr int NT = 512;        // threads per CTA
-constexpr int NW = NT / 32;    // warps
+constexpr int NC = 512;        // compute threads per CTA (16 warps: 4 TMEM lane quadrants x 4 column quarters)
+constexpr int NW = NC / 32;    // compute warps
+constexpr int NT = NC;         // (a 17th, issue-only warp was tried: the warp-allocation granularity of 4 then caps registers at 96/thread)
+constexpr int ISSUER = 0;      // thread that issues the MMAs
 constexpr int TM = 128;        // edges per tile
 constexpr int WIN = 32;        // column window of the backward staging tiles
 constexpr int WS = 36;         // row stride (floats) of a staging tile: 36 mod 32 = 4 -> conflict-free LDS.128
@@ -115,12 +119,22 @@ __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ r
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float silu_fast(float a) {
-  // silu(a) = a / (1 + exp(-a)); ex2.approx + fast division (rel. error ~1e-7, far below the bf16x3 GEMM error)
-  return __fdividef(a, 1.0f + __expf(-a));
+  // silu(a) = a / (1 + exp(-a)) with two MUFU ops (rel. error ~2e-7, far below the bf16x3 GEMM error)
+  return a * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * a));
 }
 __device__ __forceinline__ void silu_fast_d(float a, float* y, float* dy) {
-  float s = __fdividef(1.0f, 1.0f + __expf(-a));
+  float s = rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * a));
   *y = a * s;
   *dy = s * (1.0f + a * (1.0f - s));
 }
@@ -191,6 +205,18 @@ __device__ __forceinline__ void tc_issue_gemm(uint32_t tD, const unsigned char* 
   }
 }
 
+// optional phase timing (debug): cycles between phase boundaries accumulated by thread 0 of block 0
+__device__ unsigned long long g_tc_phase[3][16];
+#define TC_PHASE(kern, idx)                                                        \
+  if (TC_TIMING && blockIdx.x == 0 && threadIdx.x == 0) {                          \
+    const long long now_ = clock64();                                              \
+    atomicAdd(&g_tc_phase[kern][idx], (unsigned long long)(now_ - t_prev_));       \
+    t_prev_ = now_;                                                                \
+  }
+#ifndef TC_TIMING
+#define TC_TIMING 0
+#endif
+
 #define TC_WAIT_OR_BAIL(bar, par)                              \
   {                                                            \
     bool ok_ = tc::mbar_wait(bar, par);                        \
@@ -201,37 +227,62 @@ __device__ __forceinline__ void tc_issue_gemm(uint32_t tD, const unsigned char* 
     tc::fence_after_sync();                                    \
   }
 
-// S0: per-edge metadata (receiver, sender, cutoff, l0 contraction of the chi difference) and the radial-basis
-// operand image(s).  WITH_D additionally writes the image of d rbf / d d.
-template <bool WITH_D>
-__device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, const TcSmem& S, int r, int qq, int e0, int ne,
-                                           const int* __restrict__ row, const int* __restrict__ col,
-                                           const float4* __restrict__ geom, const float* __restrict__ chi,
-                                           unsigned char* A0dhi, unsigned char* A0dlo) {
-  const bool valid = r < ne;
-  float d = 0.f;
-  if (valid) d = geom[e0 + r].w;
-  if (qq == 0) {
-    int i = 0, j = 0;
-    float gl[SO3K_MAXDEG];
+// Per-edge metadata of one tile row, prefetched one tile ahead (global loads with a dependent chain: row/col -> chi rows)
+struct TileMeta {
+  int i, j;
+  float d;
+  float gl[SO3K_MAXDEG];        // l0 contraction of the chi difference (only meaningful for column quarter 0)
+};
+// level 1: receiver / sender / distance (issued early) ; level 2: chi rows -> l0 contraction (issued one GEMM later)
+__device__ __forceinline__ TileMeta tc_prefetch_meta1(int r, int qq, int e0, int nv, bool comp, const int* __restrict__ row,
+                                                      const int* __restrict__ col, const float4* __restrict__ geom) {
+  TileMeta m;
+  m.i = 0; m.j = 0; m.d = 0.f;
 #pragma unroll
-    for (int l = 0; l < SO3K_MAXDEG; ++l) gl[l] = 0.f;
-    if (valid) {
-      i = row[e0 + r];
-      j = col[e0 + r];
-      for (int m = 0; m < D.M; ++m) {
-        const float c = chi[(size_t)j * D.M + m] - chi[(size_t)i * D.M + m];
-        const float cc = c * c * D.m_cg[m];
-        const int sg = D.m_seg[m];
-#pragma unroll
-        for (int l = 0; l < SO3K_MAXDEG; ++l) gl[l] += (l == sg) ? cc : 0.f;
-      }
+  for (int l = 0; l < SO3K_MAXDEG; ++l) m.gl[l] = 0.f;
+  const int e = e0 + r;
+  if (comp && e < nv) {
+    m.d = geom[e].w;
+    if (qq == 0) {
+      m.i = row[e];
+      m.j = col[e];
     }
-    S.s_i[r] = i; S.s_j[r] = j;
+  }
+  return m;
+}
+__device__ __forceinline__ void tc_prefetch_meta2(const So3kDims& D, TileMeta& m, int r, int qq, int e0, int nv, bool comp,
+                                                  const float* __restrict__ chi) {
+  if (comp && qq == 0 && e0 + r < nv) {
+    for (int k = 0; k < D.M; ++k) {
+      const float c = chi[(size_t)m.j * D.M + k] - chi[(size_t)m.i * D.M + k];
+      const float cc = c * c * D.m_cg[k];
+      const int sg = D.m_seg[k];
+#pragma unroll
+      for (int l = 0; l < SO3K_MAXDEG; ++l) m.gl[l] += (l == sg) ? cc : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ TileMeta tc_prefetch_meta(const So3kDims& D, int r, int qq, int e0, int nv, bool comp,
+                                                     const int* __restrict__ row, const int* __restrict__ col,
+                                                     const float4* __restrict__ geom, const float* __restrict__ chi) {
+  TileMeta m = tc_prefetch_meta1(r, qq, e0, nv, comp, row, col, geom);
+  tc_prefetch_meta2(D, m, r, qq, e0, nv, comp, chi);
+  return m;
+}
+
+// S0: publish the tile's metadata to shared memory and write the radial-basis operand image(s).
+// WITH_D additionally writes the image of d rbf / d d.
+template <bool WITH_D>
+__device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, const TcSmem& S, int r, int qq, int ne,
+                                           const TileMeta& m, unsigned char* A0dhi, unsigned char* A0dlo) {
+  const bool valid = r < ne;
+  const float d = m.d;
+  if (qq == 0) {
+    S.s_i[r] = m.i; S.s_j[r] = m.j;
     S.s_phi[r] = valid ? cutoff_fast(d, D.r_cut) : 0.f;
 #pragma unroll
     for (int l = 0; l < SO3K_MAXDEG; ++l)
-      if (l < D.nl) S.s_g[r * D.nl + l] = gl[l];
+      if (l < D.nl) S.s_g[r * D.nl + l] = m.gl[l];
   }
   const float ed = __expf(-d);
   for (int c = qq; c < T.K0 / 8; c += 4) {     // this thread writes K chunks qq, qq+4, ... of its row
@@ -343,8 +394,9 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool comp = warp < NW;               // compute warp (the extra warp only issues MMAs)
   const int r = 32 * (warp & 3) + lane;      // row of the tile == TMEM lane
-  const int qq = warp >> 2;                  // column quarter handled by this thread
+  const int qq = comp ? (warp >> 2) : 0;     // column quarter handled by this thread
   const int F = D.F;
   const int heads = blk ? D.nl : D.H;
   const int dhd = F / heads;
@@ -376,63 +428,85 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
   const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;    // this thread's D2 chunks
 
   uint32_t it = 0;
+  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;                     // block-uniform
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
+    long long t_prev_ = TC_TIMING ? clock64() : 0;
 
-    tc_tile_s0<false>(D, T, S, r, qq, e0, ne, row, col, geom, chi, nullptr, nullptr);
+    if (comp) tc_tile_s0<false>(D, T, S, r, qq, ne, meta, nullptr, nullptr);
+    TC_PHASE(MODE, 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    TC_PHASE(MODE, 1);
+    if (tid == ISSUER) {
       tc::fence_after_sync();
       tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc);
       tc::commit(&bars[0]);
     }
-    TC_WAIT_OR_BAIL(&bars[0], par);
-    tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
-    tc::fence_async_smem();
-    tc::fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      tc::fence_after_sync();
-      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
-      tc::commit(&bars[1]);
-    }
-
+    // long-latency global loads issued as early as possible: level-1 metadata of this CTA's next tile and (forward)
+    // the q_i * k_j rows of this tile; both are consumed only after GEMM2
+    const int e0_next = (tile + (int)gridDim.x) * TM;
+    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom);
+    float4 pq[8];
+    float4 px = make_float4(0.f, 0.f, 0.f, 0.f);   // float4 column 32 + qq of row r (F <= 144 -> at most 4 of them)
     if (MODE == 0) {
-      // ---- while GEMM2 runs: gather q_i * k_j for this warp's 8 rows into registers (full-line loads) ------------
-      float4 pq[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int rr = warp * 8 + u;
+        const int rr = (warp & 15) * 8 + u;
         pq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < nf4) {
+        if (comp && lane < nf4) {
           const float4 q = *reinterpret_cast<const float4*>(proj + (size_t)S.s_i[rr] * F5 + qoff + 4 * lane);
           const float4 k = *reinterpret_cast<const float4*>(proj + (size_t)S.s_j[rr] * F5 + koff + 4 * lane);
           pq[u] = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
         }
       }
-      float4 px = make_float4(0.f, 0.f, 0.f, 0.f);   // float4 column 32 + qq of row r (F <= 144 -> at most 4 of them)
-      if (32 + qq < nf4) {
+      if (comp && 32 + qq < nf4) {
         const float4 q = *reinterpret_cast<const float4*>(proj + (size_t)S.s_i[r] * F5 + qoff + 4 * (32 + qq));
         const float4 k = *reinterpret_cast<const float4*>(proj + (size_t)S.s_j[r] * F5 + koff + 4 * (32 + qq));
         px = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
       }
+    }
+    TC_PHASE(MODE, 2);
+    TC_WAIT_OR_BAIL(&bars[0], par);
+    TC_PHASE(MODE, 3);
+    if (comp) tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
+    TC_PHASE(MODE, 4);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    TC_PHASE(MODE, 5);
+    if (tid == ISSUER) {
+      tc::fence_after_sync();
+      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
+      tc::commit(&bars[1]);
+    }
+    // while GEMM2 runs: level-2 metadata (chi rows) of this CTA's next tile
+    tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
+    meta = meta_nx;
+    TC_PHASE(MODE, 6);
+
+    if (MODE == 0) {
+      TC_PHASE(MODE, 7);
       TC_WAIT_OR_BAIL(&bars[1], par);
+      TC_PHASE(MODE, 8);
       float* qk = S.region;                    // aliased: the A1 image is dead once GEMM2 has completed
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (lane < nf4) *reinterpret_cast<float4*>(qk + (size_t)(warp * 8 + u) * T.QS + 4 * lane) = pq[u];
-      if (32 + qq < nf4) *reinterpret_cast<float4*>(qk + (size_t)r * T.QS + 4 * (32 + qq)) = px;
+        if (comp && lane < nf4) *reinterpret_cast<float4*>(qk + (size_t)(warp * 8 + u) * T.QS + 4 * lane) = pq[u];
+      if (comp && 32 + qq < nf4) *reinterpret_cast<float4*>(qk + (size_t)r * T.QS + 4 * (32 + qq)) = px;
+      if (comp) {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) S.s_part[(r * 4 + qq) * 4 + h] = 0.f;     // [row][quarter][head slot]
+        for (int h = 0; h < 4; ++h) S.s_part[(r * 4 + qq) * 4 + h] = 0.f;     // [row][quarter][head slot]
+      }
       __syncthreads();
+      TC_PHASE(MODE, 9);
       // ---- epilogue 2: alpha_h = sum_{f in head h} (w_f + b_f) q_f k_f / sqrt(d_h) * phi ---------------------------
       // a quarter (<= 40 columns) touches at most 4 heads; partial sums go to slot (head - first head of the quarter)
-      {
+      if (comp) {
         const float* qrow = qk + (size_t)r * T.QS;
         const int f0 = cbeg * 8;
         const int h0 = (f0 < F) ? S.s_head[f0] : 0;
@@ -477,30 +551,30 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
         }
         if (f0 < F) S.s_part[(r * 4 + qq) * 4 + (hcur - h0)] = acc;
       }
+      TC_PHASE(MODE, 10);
       tc::fence_before_sync();
       __syncthreads();
-      if (tid < ne) {
-        const float ph = S.s_phi[tid];
-        float tot[8];
+      TC_PHASE(MODE, 11);
+      if (comp && r < ne) {                    // thread (r, qq) finishes heads qq and qq + 4 of its row
+        const float ph = S.s_phi[r];
+        for (int h = qq; h < heads; h += 4) {
+          float tot = 0.f;
 #pragma unroll
-        for (int h = 0; h < 8; ++h) tot[h] = 0.f;
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int f0 = ((nchunk_d * q4) / 4) * 8;
-          if (f0 >= F) break;
-          const int h0 = S.s_head[f0];
-          for (int s = 0; s < 4; ++s) {
-            const float p = S.s_part[(tid * 4 + q4) * 4 + s];
-#pragma unroll
-            for (int h = 0; h < 8; ++h) tot[h] += (h == h0 + s) ? p : 0.f;
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int f0 = ((nchunk_d * q4) / 4) * 8;
+            if (f0 < F) {
+              const int s = h - (int)S.s_head[f0];
+              if (s >= 0 && s < 4) tot += S.s_part[(r * 4 + q4) * 4 + s];
+            }
           }
+          alpha[(size_t)(e0 + r) * Ast + aoff + h] = tot * inv * ph;
         }
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-          if (h < heads) alpha[(size_t)(e0 + tid) * Ast + aoff + h] = tot[h] * inv * ph;
-        if (blk == 1)
-          for (int a = D.H + D.nl; a < Ast; ++a) alpha[(size_t)(e0 + tid) * Ast + a] = 0.f;
+        if (blk == 1 && qq == 0)
+          for (int a = D.H + D.nl; a < Ast; ++a) alpha[(size_t)(e0 + r) * Ast + a] = 0.f;
       }
       __syncthreads();      // qk tile / s_part fully consumed before the next tile overwrites the region
+      TC_PHASE(MODE, 12);
+      if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[MODE][15], 1ull);
     } else {
       // ================= backward part 1 ========================================================================
       // per row: ab[h] = alphabar[e][h] / sqrt(dh) ; abr[h] = alphabar[rev e][h] / sqrt(dh)
@@ -510,16 +584,16 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
       for (int h = 0; h < 8; ++h) {
         ab[h] = 0.f;
         abr[h] = 0.f;
-        if (h < heads && r < ne) {
+        if (comp && h < heads && r < ne) {
           ab[h] = alphabar[(size_t)(e0 + r) * Ast + aoff + h] * inv;
           abr[h] = alphabar[(size_t)rev[e0 + r] * Ast + aoff + h] * inv;
         }
       }
       // receiver runs inside this warp's 32 rows (rows are receiver-sorted)
-      SegMask SM;
-      bool run_head;
+      SegMask SM = {false, false, false, false, false};
+      bool run_head = false;
       const int my_i = (r < ne) ? S.s_i[r] : -1 - r;           // invalid rows form runs of their own
-      {
+      if (comp) {
         const int i1 = __shfl_down_sync(0xffffffffu, my_i, 1), i2 = __shfl_down_sync(0xffffffffu, my_i, 2);
         const int i4 = __shfl_down_sync(0xffffffffu, my_i, 4), i8 = __shfl_down_sync(0xffffffffu, my_i, 8);
         const int i16 = __shfl_down_sync(0xffffffffu, my_i, 16);
@@ -539,7 +613,7 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
       float phibar = 0.f;
       for (int w0 = 0; w0 < T.Fp; w0 += WIN) {
         // ---- gather the window [w0, w0+32) of q_i, k_j, q_j: lane -> (row of 4, float4 of 8); 8 rows per warp -------
-        {
+        if (comp) {
           const int sub = lane >> 3, f4 = lane & 7;
           const int f = w0 + 4 * f4;
 #pragma unroll
@@ -561,7 +635,7 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
         __syncthreads();
         // ---- this thread's 8 columns of the window -------------------------------------------------------------------
         const int c0 = w0 + qq * 8;                      // warp-uniform
-        if (c0 < F) {
+        if (comp && c0 < F) {
           float v[8];
           tc::tmem_ld8(tD2 + lane_sel + (uint32_t)c0, v);
           float qi[8], kj[8], qj[8];
@@ -598,7 +672,7 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
         __syncthreads();       // window consumed before the next gather overwrites it
       }
       // combine the four column quarters of a row through shared memory
-      S.s_part[r * 4 + qq] = phibar;
+      if (comp) S.s_part[r * 4 + qq] = phibar;
       __syncthreads();
       if (tid < ne) {
         const float pb = S.s_part[tid * 4] + S.s_part[tid * 4 + 1] + S.s_part[tid * 4 + 2] + S.s_part[tid * 4 + 3];
@@ -630,8 +704,9 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool comp = warp < NW;
   const int r = 32 * (warp & 3) + lane;
-  const int qq = warp >> 2;
+  const int qq = comp ? (warp >> 2) : 0;
   const int F = D.F, Fs = D.Fs;
   const int heads = blk ? D.nl : D.H;
   const int dhd = F / heads;
@@ -675,27 +750,28 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const int kcb = (nchunkK * qq) / 4, kce = (nchunkK * (qq + 1)) / 4;   // this thread's hidden-column chunks
 
   uint32_t it = 0;
+  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
 
-    tc_tile_s0<true>(D, T, S, r, qq, e0, ne, row, col, geom, chi, A0dhi, A0dlo);
-    if (qq == 1) {
-      const float ph = (r < ne) ? cutoff_fast(geom[e0 + r].w, D.r_cut) * inv : 0.f;
+    if (comp) tc_tile_s0<true>(D, T, S, r, qq, ne, meta, A0dhi, A0dlo);
+    if (comp && qq == 1) {
+      const float ph = (r < ne) ? cutoff_fast(meta.d, D.r_cut) * inv : 0.f;
 #pragma unroll
       for (int h = 0; h < 8; ++h)
         s_ab[r * 8 + h] = (h < heads && r < ne) ? alphabar[(size_t)(e0 + r) * Ast + aoff + h] * ph : 0.f;
     }
-    if (qq == 2) {
+    if (comp && qq == 2) {
 #pragma unroll
       for (int h = 0; h < 8; ++h) s_red[r * 8 + h] = 0.f;
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == ISSUER) {
       tc::fence_after_sync();
       tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
       tc_issue_gemm(tD1p, A0dhi, A0dlo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
@@ -705,7 +781,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
     const int ncg = (nchunkF + 3) / 4;
     const int nitems = 16 * ncg;
     TC_WAIT_OR_BAIL(&bars[0], par);
-    for (int item = warp; item < nitems; item += NW) {
+    for (int item = comp ? warp : nitems; item < nitems; item += NW) {
       const int rg = item / ncg, cg = item - rg * ncg;
       const int rr = rg * 8 + (lane >> 2);
       const int c = cg * 4 + (lane & 3);
@@ -737,7 +813,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
     tc::fence_before_sync();
     __syncthreads();
     // ---- GEMM3: hbar[128 x KC] = wbar[128 x Fp] @ W2c^T --------------------------------------------------------------
-    if (tid == 0) {
+    if (tid == ISSUER) {
       tc::fence_after_sync();
       uint32_t acc = 0;
       const uint32_t ah = tc::smem_u32(Wbhi), al = tc::smem_u32(Wblo), bh = tc::smem_u32(S.W2hi), bl = tc::smem_u32(S.W2lo);
@@ -754,16 +830,18 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       tc::commit(&bars[1]);
     }
     float gl[SO3K_MAXDEG], gb[SO3K_MAXDEG];
+    // (gl is read from shared memory before `meta` is overwritten with the next tile's values)
 #pragma unroll
     for (int l = 0; l < SO3K_MAXDEG; ++l) {
       gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
       gb[l] = 0.f;
     }
+    meta = tc_prefetch_meta(D, r, qq, (tile + (int)gridDim.x) * TM, nv, comp, row, col, geom, chi);   // overlaps GEMM3
     TC_WAIT_OR_BAIL(&bars[1], par);
     // ---- epilogue: this thread's quarter of the KC hidden columns of its row ------------------------------------------------
     {
       float dbar = 0.f;
-      for (int cc = kcb; cc < kce; ++cc) {
+      for (int cc = comp ? kcb : kce; cc < kce; ++cc) {
         const int c0 = cc * 8;
         if (c0 >= F + Fs) break;                  // warp-uniform: only zero padding left
         float hb[8], a1[8], tp[8];
@@ -792,13 +870,15 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
         }
       }
       // cross-quarter combination: 4 contributions per slot through shared-memory atomics
-      atomicAdd(&s_red[r * 8 + 0], dbar);
+      if (comp) {
+        atomicAdd(&s_red[r * 8 + 0], dbar);
 #pragma unroll
-      for (int l = 0; l < SO3K_MAXDEG; ++l)
-        if (l < D.nl && l < 7) atomicAdd(&s_red[r * 8 + 1 + l], gb[l]);
+        for (int l = 0; l < SO3K_MAXDEG; ++l)
+          if (l < D.nl && l < 7) atomicAdd(&s_red[r * 8 + 1 + l], gb[l]);
+      }
       tc::fence_before_sync();
       __syncthreads();
-      if (qq == 0 && r < ne) {
+      if (comp && qq == 0 && r < ne) {
         const size_t e = (size_t)(e0 + r);
         const float db = s_red[r * 8 + 0];
         if (blk == 0) ebar[2 * e] = db; else ebar[2 * e] += db;
@@ -899,7 +979,24 @@ void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& 
     }
   }
 }
+extern "C" void so3k_tc_phase_dump(void) {
+  unsigned long long h[3][16];
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_tc_phase, sizeof(h));
+  const char* names[13] = {"S0", "sync", "issue1", "wait1", "epi1", "sync", "issue2", "gather", "wait2", "qkstore+sync",
+                           "epi2", "sync", "alpha+sync"};
+  for (int k = 0; k < 3; ++k) {
+    if (!h[k][15]) continue;
+    double tot = 0;
+    printf("tc phase timing kernel %d (%llu tiles of block 0):", k, h[k][15]);
+    for (int p = 0; p < 13; ++p) { printf(" %s=%.0f", names[p], (double)h[k][p] / h[k][15]); tot += (double)h[k][p] / h[k][15]; }
+    printf(" | total=%.0f cycles/tile\n", tot);
+  }
+  memset(h, 0, sizeof(h));
+  cudaMemcpyToSymbol(g_tc_phase, h, sizeof(h));
+}
 #else
+extern "C" void so3k_tc_phase_dump(void) {}
 bool so3k_edge_tc_supported(const So3kDims&) { return false; }
 size_t so3k_edge_tc_image_bytes(const So3kDims&) { return 0; }
 void so3k_edge_tc_build(const So3kDims&, const float*, const BlockParams&, unsigned char*, TcBlockW*, const EdgeBlockW&,

@@ -108,12 +108,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- split fp32 -> bf16 hi / lo ----------------------------------------------------------------------------
+// Integer-pipe split (no F2FP conversions, which share the XU pipe with the MUFU ops of the silu epilogues):
+//   hi = round-half-up(x) to bf16 ; lo = round-half-up(x - hi) to bf16.  x - hi is exact in fp32 and |lo| <= 2^-9 |x|
+//   with either sign (a truncating hi would make lo*lo a biased, coherently accumulating error).
 __device__ __forceinline__ void split2(float x, float y, uint32_t* hi, uint32_t* lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-  float2 hf = __bfloat1622float2(h);
-  __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
-  *hi = *reinterpret_cast<uint32_t*>(&h);
-  *lo = *reinterpret_cast<uint32_t*>(&l);
+  const uint32_t xh = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
+  const uint32_t yh = (__float_as_uint(y) + 0x8000u) & 0xFFFF0000u;
+  *hi = __byte_perm(xh, yh, 0x7632);                       // {y[31:16], x[31:16]}
+  const float lx = x - __uint_as_float(xh);
+  const float ly = y - __uint_as_float(yh);
+  *lo = __byte_perm(__float_as_uint(lx) + 0x8000u, __float_as_uint(ly) + 0x8000u, 0x7632);
 }
 // 8 consecutive columns (one 16-byte core-matrix row) of a canonical K-major operand
 __device__ __forceinline__ void store_chunk8(unsigned char* hi_base, unsigned char* lo_base, uint32_t off,
