@@ -270,6 +270,14 @@ __device__ __forceinline__ TileMeta tc_prefetch_meta(const So3kDims& D, int r, i
   return m;
 }
 
+// L2 prefetch of the F-wide segment [off, off + F) of atom `a`'s projection row (one 128-byte line per instruction)
+__device__ __forceinline__ void tc_l2_prefetch_seg(const float* __restrict__ proj, size_t F5, int a, int off, int F) {
+  const char* p = reinterpret_cast<const char*>(proj + (size_t)a * F5 + off);
+  const char* end = p + 4 * F;
+  p = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127);
+  for (; p < end; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // S0: publish the tile's metadata to shared memory and write the radial-basis operand image(s).
 // WITH_D additionally writes the image of d rbf / d d.
 template <bool WITH_D>
@@ -451,6 +459,30 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
     // the q_i * k_j rows of this tile; both are consumed only after GEMM2
     const int e0_next = (tile + (int)gridDim.x) * TM;
     TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom);
+    TC_PHASE(MODE, 2);
+    TC_WAIT_OR_BAIL(&bars[0], par);
+    TC_PHASE(MODE, 3);
+    if (comp) tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
+    TC_PHASE(MODE, 4);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    TC_PHASE(MODE, 5);
+    if (tid == ISSUER) {
+      tc::fence_after_sync();
+      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
+      tc::commit(&bars[1]);
+    }
+    // while GEMM2 runs: pull the next tile's gather rows into L2 (their senders are random atoms: DRAM tail latency
+    // would otherwise sit on the critical path), gather this tile's q_i * k_j rows, level-2 metadata of the next tile
+    {
+      const int prev_i = __shfl_up_sync(0xffffffffu, meta_nx.i, 1);
+      if (comp && qq == 0 && e0_next + r < nv) {
+        tc_l2_prefetch_seg(proj, F5, meta_nx.j, koff, F);
+        if (MODE == 1) tc_l2_prefetch_seg(proj, F5, meta_nx.j, qoff, F);
+        if (lane == 0 || prev_i != meta_nx.i) tc_l2_prefetch_seg(proj, F5, meta_nx.i, qoff, F);
+      }
+    }
     float4 pq[8];
     float4 px = make_float4(0.f, 0.f, 0.f, 0.f);   // float4 column 32 + qq of row r (F <= 144 -> at most 4 of them)
     if (MODE == 0) {
@@ -470,21 +502,6 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
         px = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
       }
     }
-    TC_PHASE(MODE, 2);
-    TC_WAIT_OR_BAIL(&bars[0], par);
-    TC_PHASE(MODE, 3);
-    if (comp) tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
-    TC_PHASE(MODE, 4);
-    tc::fence_async_smem();
-    tc::fence_before_sync();
-    __syncthreads();
-    TC_PHASE(MODE, 5);
-    if (tid == ISSUER) {
-      tc::fence_after_sync();
-      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
-      tc::commit(&bars[1]);
-    }
-    // while GEMM2 runs: level-2 metadata (chi rows) of this CTA's next tile
     tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
     meta = meta_nx;
     TC_PHASE(MODE, 6);

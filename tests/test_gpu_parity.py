@@ -302,7 +302,9 @@ def test_tcgen05_tile_gemm_layouts(N, K, variant):
     A = rng.normal(size=(128, K)).astype(np.float32)
     Bm = rng.normal(size=(N, K) if variant == 0 else (K, N)).astype(np.float32)
     ref = A.astype(np.float64) @ (Bm.astype(np.float64).T if variant == 0 else Bm.astype(np.float64))
-    bf = lambda a: torch.as_tensor(a).to(torch.bfloat16).double().numpy()
+    def bf(a):      # the kernels' hi part: round-half-up to bf16 (so3k_tc.cuh split2), done on the integer pipe
+        b = np.ascontiguousarray(a, np.float32).view(np.uint32)
+        return ((b + np.uint32(0x8000)) & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
     ref1 = bf(A) @ (bf(Bm).T if variant == 0 else bf(Bm))
     Ad, Bd = dev(A, torch.float32), dev(Bm, torch.float32)
     for passes, target, tol in ((1, ref1, 2e-5), (3, ref, 3e-5)):
