@@ -146,6 +146,27 @@ int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
                                  float* e_atom, float* dE_dedges, float* forces,
                                  void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
 
+/* ---- stepwise evaluation (spatial domain decomposition) ----------------------------------------------------
+ * No counterpart in the reference (it has no multi-device path).  A rank's local problem is
+ * its OWNED atoms followed by GHOST atoms, with all edges received by owned atoms plus their reverses ("mirror
+ * edges": receiver ghost, sender owned), which keeps the local list symmetric so every reduction needed on an owned
+ * atom is local.  The caller runs the stages in order and, between them, overwrites the ghost rows of the named
+ * workspace buffers with their owners' rows (NCCL / peer copies):
+ *   so3k_dd_begin                          graph + embedding           (x_0 needs no exchange)
+ *   for t: so3k_dd_stage(0, t)             layer forward               -> exchange x_{t+1}, chi_{t+1}
+ *   so3k_dd_stage(1)                       read-out: out = e_atom (N)  (sum the OWNED entries, all-reduce)
+ *   for t desc: so3k_dd_stage(2, t)        interaction backward        -> exchange xbar1, chibar1
+ *               so3k_dd_stage(3, t)        edge + node backward
+ *   so3k_dd_stage(4)                       out = forces (N,3); only OWNED rows are complete
+ * so3k_dd_buffer returns the byte offset (inside the workspace) and row width of x_t / chi_t / xbar1 / chibar1. */
+int so3k_dd_begin(so3k_handle* h, int32_t N, int32_t P, const float* R, const int32_t* z, const int32_t* idx_i,
+                  const int32_t* idx_j, const float* cell, const int32_t* cell_offset, void* workspace,
+                  size_t workspace_bytes, int32_t* dev_status, void* stream);
+int so3k_dd_stage(so3k_handle* h, int32_t stage, int32_t t, int32_t N, int32_t P, const int32_t* z, float* out,
+                  void* workspace, int32_t* dev_status, void* stream);
+int so3k_dd_buffer(const so3k_handle* h, int32_t which, int32_t t, int32_t N, int32_t P, size_t* offset,
+                   size_t* row_floats);
+
 /* ---- edge featurisation (standalone; the fused model path recomputes these on chip) ---------
  * Inputs as GeometryEmbed: either positions R (n,3) [+ cell (3,3) row-wise + cell_offset (P,3)]
  * or displacements (P,3).  Any output pointer may be NULL.  rbf (P,K), phi (P), d (P),

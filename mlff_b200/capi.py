@@ -25,7 +25,8 @@ NL_DENSE = 1
 EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 'so3k_param_lookup',
            'so3k_load_params', 'so3k_workspace_bytes', 'so3k_energy_forces', 'so3k_potential_displacements',
            'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count',
-           'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect', 'so3k_tc_selftest']
+           'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect', 'so3k_tc_selftest',
+           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_buffer']
 
 
 class So3kConfigC(C.Structure):
@@ -77,6 +78,12 @@ class So3kLib:
         d.so3k_neighbor_list.restype = C.c_int
         d.so3k_launch_count.argtypes = []
         d.so3k_launch_count.restype = C.c_uint64
+        d.so3k_dd_begin.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]
+        d.so3k_dd_begin.restype = C.c_int
+        d.so3k_dd_stage.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+        d.so3k_dd_stage.restype = C.c_int
+        d.so3k_dd_buffer.argtypes = [vp, i32, i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]
+        d.so3k_dd_buffer.restype = C.c_int
         d.so3k_tc_selftest.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
         d.so3k_tc_selftest.restype = C.c_int
         d.so3k_profile_categories.argtypes = []
@@ -148,6 +155,19 @@ class So3kLib:
                       ws_bytes, status, stream=0):
         _check(self.dll.so3k_neighbor_list(mode, N, positions, z, cell, pbc, float(cutoff), capacity, idx_i, idx_j,
                                            shifts, count, ws, ws_bytes, status, stream), 'so3k_neighbor_list')
+
+    # ---- stepwise / domain decomposition --------------------------------------------------------
+    def dd_begin(self, h, N, P, R, z, idx_i, idx_j, cell, cell_offset, ws, ws_bytes, status, stream=0):
+        _check(self.dll.so3k_dd_begin(h, N, P, R, z, idx_i, idx_j, cell, cell_offset, ws, ws_bytes, status, stream),
+               'so3k_dd_begin')
+
+    def dd_stage(self, h, stage, t, N, P, z, out, ws, status, stream=0):
+        _check(self.dll.so3k_dd_stage(h, stage, t, N, P, z, out, ws, status, stream), 'so3k_dd_stage')
+
+    def dd_buffer(self, h, which, t, N, P):
+        off, rf = C.c_size_t(), C.c_size_t()
+        _check(self.dll.so3k_dd_buffer(h, which, t, N, P, C.byref(off), C.byref(rf)), 'so3k_dd_buffer')
+        return int(off.value), int(rf.value)
 
     def tc_selftest(self, N, K, variant, passes, A, B, D, stream=0):
         _check(self.dll.so3k_tc_selftest(N, K, variant, passes, A, B, D, stream), 'so3k_tc_selftest')

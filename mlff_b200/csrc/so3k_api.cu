@@ -225,6 +225,90 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base) {
   return w;
 }
 
+// ---- stages of one evaluation (also exposed one by one through the so3k_dd_* entry points, so that a
+// domain-decomposed caller can exchange ghost rows between them) ------------------------------------------------
+void stage_begin(HandleImpl* h, Workspace& w, int B, int n, int P, const float* R, const int* z, const int* idx_i,
+                 const int* idx_j, const float* cell, const int* cell_offset, const float* disp,
+                 const unsigned char* mask, int* dev_status, cudaStream_t st) {
+  const So3kDims& D = h->dims;
+  { PROF(CAT_GRAPH); so3k_build_graph(D, B, n, P, R, idx_i, idx_j, cell, cell_offset, disp, mask, w.g, w.scratch, dev_status, st); }
+  { PROF(CAT_EMBED); so3k_launch_embed(D, B * n, z, h->params + h->layout.embed, w.x, w.chi, dev_status, st); }
+}
+
+// x_{t+1}, chi_{t+1} from x_t, chi_t
+void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaStream_t st) {
+  const So3kDims& D = h->dims;
+  const size_t N = w.g.N, F = D.F, M = D.M, nl = D.nl, Ast = (D.H + D.nl + 3) & ~3, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
+  const float* prm = h->params;
+  const LayerParams& lp = h->layout.layers[t];
+  float* xt = w.x + (size_t)t * N * F;
+  float* ct = w.chi + (size_t)t * N * M;
+  float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
+  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
+  {
+    PROF(CAT_EDGE_FWD);
+    if (h->use_tc && h->tc_fwd) so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, dev_status, st);
+    else so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
+  }
+  { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
+  PROF(CAT_INTERACTION);
+  so3k_launch_interaction(D, (int)N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + N * F, ct + N * M,
+                          w.bcoef + (size_t)t * N * nl, st);
+}
+
+// e_atom and d(sum e)/dx_L -> xbar_a ; chibar_a = 0 ; rbar = 0
+void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, float* e_atom, cudaStream_t st) {
+  const So3kDims& D = h->dims;
+  const size_t N = w.g.N, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
+  {
+    PROF(CAT_READOUT);
+    so3k_launch_readout(D, (int)N, w.x + (size_t)D.L * N * D.F, z, h->params, h->layout, out_scale, e_atom, w.xbar_a, st);
+  }
+  cudaMemsetAsync(w.chibar_a, 0, sizeof(float) * N * D.M, st);
+  cudaMemsetAsync(w.rbar, 0, sizeof(float) * Pe * 3, st);
+}
+
+// interaction block of layer t: (xbar_a, chibar_a) = cotangent of (x_{t+1}, chi_{t+1})  ->  (xbar_b, chibar_b) = (xbar1, chibar1)
+void stage_layer_bwd_a(HandleImpl* h, Workspace& w, int t, cudaStream_t st) {
+  const So3kDims& D = h->dims;
+  const size_t N = w.g.N;
+  PROF(CAT_INTERACTION_BWD);
+  so3k_launch_interaction_bwd(D, (int)N, w.chi1 + (size_t)t * N * D.M, w.bcoef + (size_t)t * N * D.nl, h->params,
+                              h->layout.layers[t], w.xbar_a, w.chibar_a, w.xbar_b, w.chibar_b, st);
+}
+
+// everything below the interaction block of layer t: edge cotangents, rbar += ..., and (t > 0) the cotangent of
+// (x_t, chi_t) back into (xbar_a, chibar_a)
+void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaStream_t st) {
+  const So3kDims& D = h->dims;
+  const size_t N = w.g.N, F = D.F, M = D.M, Ast = (D.H + D.nl + 3) & ~3, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
+  const float* prm = h->params;
+  const LayerParams& lp = h->layout.layers[t];
+  const float* xt = w.x + (size_t)t * N * F;
+  const float* ct = w.chi + (size_t)t * N * M;
+  const float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
+  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
+  cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
+  { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, w.xbar_b, w.chibar_b, w.alphabar, w.gproj, st); }
+  {
+    PROF(CAT_EDGE_BWD);
+    // tc_parts: which backward pieces run on the tensor cores (bit 0: q/k gradients + cutoff cotangent,
+    // bit 1: radial + l0-contraction cotangents); the rest runs the fp32 CUDA-core kernel
+    const int tcp = h->use_tc ? h->tc_parts : 0;
+    if (tcp) so3k_launch_edge_bwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, w.alphabar, tcp, w.gproj, w.gbar, w.ebar,
+                                     dev_status, st);
+    if (tcp != 3) so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3 & ~tcp, w.gproj, w.gbar,
+                                       w.ebar, st);
+    so3k_launch_edge_finish(D, w.g, alpha_t, w.chibar_b, w.ebar, w.rbar, st);
+  }
+  if (t > 0) {
+    // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
+    { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, w.chibar_b, w.chibar_a, st); }     // chibar_a <- d/d chi_t
+    { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, (int)N, w.gproj, prm, lp, w.xbar_b, st); }   // xbar_b += proj^T
+    cudaMemcpyAsync(w.xbar_a, w.xbar_b, sizeof(float) * N * F, cudaMemcpyDeviceToDevice, st);      // xbar_a <- d/d x_t
+  }
+}
+
 // One evaluation on an already-flattened problem description.
 int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, const int* idx_i, const int* idx_j,
               const float* cell, const int* cell_offset, const float* disp, const unsigned char* mask,
@@ -234,74 +318,15 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
   const int N = B * n, Pt = B * P;
   if (workspace_bytes < so3k_workspace_bytes(h, N, Pt)) return SO3K_ERR_WORKSPACE;
   Workspace w = carve_ws(D, N, Pt, workspace);
-  const float* prm = h->params;
-  const size_t F = D.F, M = D.M, nl = D.nl;
-  const size_t Ast = (D.H + D.nl + 3) & ~3;
-  const size_t Pe = Pt > 0 ? Pt : 1;
-
-  { PROF(CAT_GRAPH); so3k_build_graph(D, B, n, P, R, idx_i, idx_j, cell, cell_offset, disp, mask, w.g, w.scratch, dev_status, st); }
-  { PROF(CAT_EMBED); so3k_launch_embed(D, N, z, prm + h->layout.embed, w.x, w.chi, dev_status, st); }
-
-  // ---- forward ----------------------------------------------------------------------------------------
-  for (int t = 0; t < D.L; ++t) {
-    const LayerParams& lp = h->layout.layers[t];
-    float* xt = w.x + (size_t)t * N * F;
-    float* ct = w.chi + (size_t)t * N * M;
-    float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
-    { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
-    {
-      PROF(CAT_EDGE_FWD);
-      if (h->use_tc && h->tc_fwd) so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, dev_status, st);
-      else so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
-    }
-    { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
-    PROF(CAT_INTERACTION);
-    so3k_launch_interaction(D, N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + (size_t)N * F, ct + (size_t)N * M,
-                            w.bcoef + (size_t)t * N * nl, st);
-  }
+  stage_begin(h, w, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, disp, mask, dev_status, st);
+  for (int t = 0; t < D.L; ++t) stage_layer_fwd(h, w, t, dev_status, st);
   float* e_atom = e_atom_out ? e_atom_out : w.e_atom;
-  float* xbar = w.xbar_a;
-  float* xbar_nx = w.xbar_b;
-  float* chibar = w.chibar_a;
-  float* chibar_nx = w.chibar_b;
-  {
-    PROF(CAT_READOUT);
-    so3k_launch_readout(D, N, w.x + (size_t)D.L * N * F, z, prm, h->layout, out_scale, e_atom, xbar, st);
-    if (E) so3k_launch_energy_sum(B, n, e_atom, E, st);
-  }
+  stage_readout(h, w, z, out_scale, e_atom, st);
+  if (E) { PROF(CAT_READOUT); so3k_launch_energy_sum(B, n, e_atom, E, st); }
   if (!forces && !dE_dedges) return SO3K_OK;
-
-  // ---- reverse sweep ------------------------------------------------------------------------------------
-  cudaMemsetAsync(chibar, 0, sizeof(float) * N * M, st);
-  cudaMemsetAsync(w.rbar, 0, sizeof(float) * Pe * 3, st);
   for (int t = D.L - 1; t >= 0; --t) {
-    const LayerParams& lp = h->layout.layers[t];
-    const float* xt = w.x + (size_t)t * N * F;
-    const float* ct = w.chi + (size_t)t * N * M;
-    const float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
-    // interaction block: (xbar, chibar) -> (xbar1, chibar1) written to the "next" buffers
-    { PROF(CAT_INTERACTION_BWD); so3k_launch_interaction_bwd(D, N, w.chi1 + (size_t)t * N * M, w.bcoef + (size_t)t * N * nl, prm, lp, xbar, chibar,
-                                xbar_nx, chibar_nx, st); }
-    { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, N, xt, prm, lp, w.proj, st); }
-    cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
-    { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, xbar_nx, chibar_nx, w.alphabar, w.gproj, st); }
-    {
-      PROF(CAT_EDGE_BWD);
-      // tc_parts: which backward pieces run on the tensor cores (bit 0: q/k gradients + cutoff cotangent,
-      // bit 1: radial + l0-contraction cotangents); the rest runs the fp32 CUDA-core kernel
-      const int tcp = h->use_tc ? h->tc_parts : 0;
-      if (tcp) so3k_launch_edge_bwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, w.alphabar, tcp, w.gproj, w.gbar, w.ebar,
-                                       dev_status, st);
-      if (tcp != 3) so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3 & ~tcp, w.gproj, w.gbar,
-                                         w.ebar, st);
-      so3k_launch_edge_finish(D, w.g, alpha_t, chibar_nx, w.ebar, w.rbar, st);
-    }
-    if (t > 0) {
-      // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
-      { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, chibar_nx, chibar, st); }      // chibar <- d/d chi_t
-      { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, N, w.gproj, prm, lp, xbar_nx, st); }      // xbar_nx += projections^T
-      float* tmp = xbar; xbar = xbar_nx; xbar_nx = tmp;                     // xbar <- d/d x_t
-    }
+    stage_layer_bwd_a(h, w, t, st);
+    stage_layer_bwd_b(h, w, t, dev_status, st);
   }
   { PROF(CAT_FORCES); so3k_launch_forces(D, w.g, Pt, w.rbar, forces, dE_dedges, st); }
   return SO3K_OK;
@@ -439,6 +464,62 @@ int so3k_featurise(const so3k_handle* h, int32_t n, int32_t P, const float* R, c
   so3k_launch_featurise(h->dims, n, P, R, idx_i, idx_j, cell, cell_offset, displacements, rbf, phi, d, unit, sph,
                         (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+// ---- stepwise evaluation for domain decomposition ----------------------------------------------------------
+// The local problem of a rank = its owned atoms followed by ghost atoms; edges = all edges received by owned atoms
+// plus their reverses ("mirror edges": receiver ghost, sender owned), so the local list is symmetric and every
+// reduction the backward needs on an OWNED atom is local.  Between the stages the caller refreshes the GHOST rows of
+// the named buffers from their owners (forward: x, chi of layer t+1 ; backward: xbar1, chibar1).
+int so3k_dd_begin(so3k_handle* hh, int32_t N, int32_t P, const float* R, const int32_t* z, const int32_t* idx_i,
+                  const int32_t* idx_j, const float* cell, const int32_t* cell_offset, void* workspace,
+                  size_t workspace_bytes, int32_t* dev_status, void* stream) {
+  if (!hh || N <= 0 || P < 0 || !R || !z || !workspace) return SO3K_ERR_ARG;
+  HandleImpl* h = static_cast<HandleImpl*>(hh);
+  if (!h->have_params) return SO3K_ERR_NOPARAMS;
+  if (workspace_bytes < so3k_workspace_bytes(h, N, P)) return SO3K_ERR_WORKSPACE;
+  Workspace w = carve_ws(h->dims, N, P, workspace);
+  stage_begin(h, w, 1, N, P, R, z, idx_i, idx_j, cell, cell_offset, nullptr, nullptr, dev_status, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+// stage: 0 = layer forward t ; 1 = read-out (e_atom (N) out, needs z) ; 2 = layer backward A (interaction block) ;
+//        3 = layer backward B ; 4 = forces (N,3) out
+int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t P, const int32_t* z, float* out,
+                  void* workspace, int32_t* dev_status, void* stream) {
+  if (!hh || !workspace || N <= 0) return SO3K_ERR_ARG;
+  HandleImpl* h = static_cast<HandleImpl*>(hh);
+  if (t < 0 || t >= h->dims.L) return SO3K_ERR_ARG;
+  Workspace w = carve_ws(h->dims, N, P, workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (stage) {
+    case 0: stage_layer_fwd(h, w, t, dev_status, st); break;
+    case 1: if (!z || !out) return SO3K_ERR_ARG; stage_readout(h, w, z, 1.0f, out, st); break;
+    case 2: stage_layer_bwd_a(h, w, t, st); break;
+    case 3: stage_layer_bwd_b(h, w, t, dev_status, st); break;
+    case 4: if (!out) return SO3K_ERR_ARG; so3k_launch_forces(h->dims, w.g, P, w.rbar, out, nullptr, st); break;
+    default: return SO3K_ERR_ARG;
+  }
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
+// byte offset inside the workspace of a node buffer: which = 0: x_t (N,F) ; 1: chi_t (N,M) ; 2: xbar1 (N,F) ; 3: chibar1 (N,M)
+int so3k_dd_buffer(const so3k_handle* hh, int32_t which, int32_t t, int32_t N, int32_t P, size_t* offset, size_t* row_floats) {
+  if (!hh || !offset || !row_floats || N <= 0) return SO3K_ERR_ARG;
+  const So3kDims& D = hh->dims;
+  if (t < 0 || t > D.L) return SO3K_ERR_ARG;
+  Workspace w = carve_ws(D, N, P, nullptr);
+  const char* base = nullptr;
+  const char* p = nullptr;
+  switch (which) {
+    case 0: p = (const char*)(w.x + (size_t)t * N * D.F); *row_floats = D.F; break;
+    case 1: p = (const char*)(w.chi + (size_t)t * N * D.M); *row_floats = D.M; break;
+    case 2: p = (const char*)w.xbar_b; *row_floats = D.F; break;
+    case 3: p = (const char*)w.chibar_b; *row_floats = D.M; break;
+    default: return SO3K_ERR_ARG;
+  }
+  *offset = (size_t)(p - base);
+  return SO3K_OK;
 }
 
 // ---- instrumentation ----------------------------------------------------------------------------------

@@ -342,3 +342,35 @@ def test_tensor_mode_matches_oracle(ethanol, solid, F, L, degrees, H):
         assert st == 0
         assert abs(E[0] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
         assert np.abs(F_[0] - g['F']).max() < F_ATOL
+
+
+# ---- domain decomposition (virtual ranks on one GPU; the multi-process NCCL exchange is exercised by bench.py --gpus N
+# and, on the CPU, by tests/test_dd.py over gloo) ----------------------------------------------------------------------
+@pytest.mark.parametrize('flags', [0, 1])
+def test_domain_decomposition_virtual_ranks(solid, flags):
+    from mlff_b200 import dist as dd
+    from mlff_b200 import _lib
+    g = golden('oracle_solid_pbc.npz')
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+    device = torch.device('cuda:0')
+    pos, z = dev(solid['R'], torch.float64), dev(solid['z'], torch.int64)
+    ii, jj, S = (dev(g[k], torch.int64) for k in ('idx_i', 'idx_j', 'shifts'))
+    world = 3
+    owner = dd.assign_owners_slab(pos, solid['unit_cell'], world, axis=2)
+    engines, ranks = [], []
+    for r in range(world):
+        eng = make(cfg, p, flags=flags)
+        engines.append(eng)
+        rk = dd.DDRank(eng.lib, eng.h, cfg.n_layers, device)
+        rk.begin(dd.build_plan(ii, jj, S, owner, r, world), pos, z, solid['unit_cell'])
+        ranks.append(rk)
+    dd.run_energy_forces(ranks, dd.exchange_inprocess)
+    torch.cuda.synchronize()
+    E = sum(float(rk.e_atom[:rk.plan.n_own].double().sum()) for rk in ranks)
+    F = np.zeros((110, 3), np.float32)
+    for rk in ranks:
+        assert int(rk.status.item()) == 0
+        F[rk.plan.local_atoms[:rk.plan.n_own].cpu().numpy()] = rk.forces[:rk.plan.n_own].cpu().numpy()
+    assert abs(E - float(g['E'])) <= E_RTOL * abs(float(g['E']))
+    assert np.abs(F - g['F']).max() < F_ATOL
