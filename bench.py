@@ -235,15 +235,28 @@ def run_ours(args, w):
         z_d = torch.as_tensor(z, device=dev, dtype=torch.int32)
         N = len(pos)
         ddrank = dd.DDRank(eng.lib, eng.h, cfg.n_layer, torch.device(dev))
-        axis = int(np.argmax(np.linalg.norm(cell, axis=1)))
+        grid = dd.brick_grid(cell, world)
         e_tot = torch.zeros(1, dtype=torch.float64, device=dev)
 
+        cap_dd = [int(cap * 1.6 / world) + 4096]
+
         def step_resident():
-            ii, jj, S, count = eng.neighbor_list(pos_d, calc.cutoff, cap, cell=cell, pbc=pbc, mode=NL_ASE)
-            nv = int(count.item())                            # plan sizes are host values (one sync per step)
-            owner = dd.assign_owners_slab(pos_d, cell, world, axis)
+            # this rank only needs the atoms of its brick + r_cut: neighbour list, plan and kernels are O(local)
+            keep = dd.brick_halo_mask(pos_d, cell, world, rank, calc.cutoff)
+            sub = torch.nonzero(keep).reshape(-1)                 # ascending: subset order == global order
+            pos_s, z_s = pos_d[sub], z_d[sub]
+            while True:
+                ii, jj, S, count = eng.neighbor_list(pos_s, calc.cutoff, cap_dd[0], cell=cell, pbc=pbc, mode=NL_ASE)
+                nv = int(count.item())                            # plan sizes are host values (one sync per step)
+                if nv <= cap_dd[0]:
+                    break
+                cap_dd[0] = int(1.25 * nv)
+                eng._status.zero_()
+            owner = dd.assign_owners_bricks(pos_s, cell, world)
             plan = dd.build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, rank, world)
-            ddrank.begin(plan, pos_d, z_d, cell)
+            ddrank.begin(plan, pos_s, z_s, cell)
+            step_resident.p_local = ddrank.P
+            step_resident.n_local = ddrank.N
             dd.run_energy_forces([ddrank], dd.exchange_distributed)
             e_tot[0] = ddrank.e_atom[:plan.n_own].double().sum()
             dist.all_reduce(e_tot)
@@ -310,7 +323,8 @@ def run_ours(args, w):
         pk, pk_kind = peaks()
         nl_ = len(w['degrees'])
         Fd, K = w['F'], 32
-        flop_block = 2.0 * n_edges * (K * Fd + Fd * Fd + nl_ * (Fd // 4) + (Fd // 4) * Fd)     # SURVEY 8(d), per block
+        p_rank = getattr(step_resident, 'p_local', n_edges)        # edges this rank's kernels processed (owned + mirror)
+        flop_block = 2.0 * p_rank * (K * Fd + Fd * Fd + nl_ * (Fd // 4) + (Fd // 4) * Fd)     # SURVEY 8(d), per block
         # dominant kernel: the edge backward (recompute + transposed GEMMs).  Algorithmic FLOPs per launch:
         # forward filter (both blocks) + W2^T GEMM + forward-mode radial GEMM + sph-branch transposes
         #   = 2 blocks x [fwd + (F*KC) + (K*F)] ~ 2 x flop_block x (1 + (F^2+F*F/4+K*F)/(K*F+F^2+...)) -- we count
@@ -336,7 +350,8 @@ def run_ours(args, w):
                 'share_of_step': (ms_bwd if dom == 'edge_bwd' else ms_fwd) / (ms_total if ms_total > 0 else 1.0)}
         # HBM-bound side kernels (compulsory-traffic bytes): aggregation
         ms_agg, n_agg = prof['aggregate']
-        agg_bytes = (4 * 8 + 4 + 16) * n_edges + (8 * Fd + 8 * sum(2 * l + 1 for l in w['degrees']) + 4) * N + 4 * Fd * N
+        n_rank = getattr(step_resident, 'n_local', N)
+        agg_bytes = (4 * 8 + 4 + 16) * p_rank + (8 * Fd + 8 * sum(2 * l + 1 for l in w['degrees']) + 4) * n_rank + 4 * Fd * n_rank
         agg = {'kernel': 'k_aggregate', 'bound': 'hbm', 'achieved': agg_bytes / (ms_agg / max(n_agg, 1) * 1e-3) / 1e9 if ms_agg > 0 else 0.0,
                'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
         agg['frac'] = agg['achieved'] / agg['peak']
@@ -361,7 +376,7 @@ def run_ours(args, w):
                 'config': {'workload': args.workload, 'description': w['desc'], 'n_atoms': N, 'n_edges': int(n_edges),
                            'F': w['F'], 'n_layers': w['L'], 'degrees': list(w['degrees']), 'r_cut': 5.0,
                            'parallelism': 'single' if world == 1 else (
-                               f'domain decomposition: {world} slabs, mirror edges, per-layer halo exchange (NCCL all_to_all)'
+                               f'domain decomposition: {grid[0]}x{grid[1]}x{grid[2]} bricks, mirror edges, per-layer halo exchange (NCCL all_to_all)'
                                if use_dd else f'replicas x{world} (no collective)'),
                            'filter_gemm': 'tcgen05 split-operand' if args.tensor else 'fp32 CUDA-core',
                            'l2': 'working set (edge + node arrays) larger than the 126 MB L2' if N >= 50_000 else
@@ -370,7 +385,8 @@ def run_ours(args, w):
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_aggregate': agg,
                 'cpu_baseline': cpu,
                 'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
-                'energy_check': float(res['energy'])}
+                'energy_check': float(res['energy']),
+                'rank0_local': {'atoms': int(getattr(step_resident, 'n_local', N)), 'edges': int(p_rank)}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -25,6 +25,63 @@ import torch
 from .capi import So3kLib
 
 
+def brick_grid(cell: np.ndarray, world: int) -> tuple:
+    """(px, py, pz) with px*py*pz == world minimising the brick surface for this cell (e.g. 8 -> 2x2x2 in a cube)."""
+    L = np.linalg.norm(np.asarray(cell, dtype=np.float64).reshape(3, 3), axis=1)
+    best, best_cost = (world, 1, 1), None
+    for px in range(1, world + 1):
+        if world % px:
+            continue
+        for py in range(1, world // px + 1):
+            if (world // px) % py:
+                continue
+            pz = world // (px * py)
+            a, b, c = L[0] / px, L[1] / py, L[2] / pz
+            cost = (px > 1) * b * c + (py > 1) * a * c + (pz > 1) * a * b      # exposed face area per brick
+            if best_cost is None or cost < best_cost - 1e-12:
+                best, best_cost = (px, py, pz), cost
+    return best
+
+
+def assign_owners_bricks(pos: torch.Tensor, cell: np.ndarray, world: int) -> torch.Tensor:
+    """owner[a] = index of the brick (fractional-coordinate grid of brick_grid(cell, world)) that contains atom a."""
+    px, py, pz = brick_grid(cell, world)
+    inv = torch.as_tensor(np.linalg.inv(np.asarray(cell, dtype=np.float64)), dtype=pos.dtype, device=pos.device)
+    frac = pos @ inv
+    frac = frac - torch.floor(frac)
+    cx = torch.clamp((frac[:, 0] * px).to(torch.int64), 0, px - 1)
+    cy = torch.clamp((frac[:, 1] * py).to(torch.int64), 0, py - 1)
+    cz = torch.clamp((frac[:, 2] * pz).to(torch.int64), 0, pz - 1)
+    return (cx * py + cy) * pz + cz
+
+
+def brick_halo_mask(pos: torch.Tensor, cell: np.ndarray, world: int, rank: int, margin: float) -> torch.Tensor:
+    """Atoms inside brick `rank` expanded by `margin` (a length, e.g. r_cut) on every side, with periodic wrap.
+    These are the only atoms the rank needs to build its rows and its mirror edges (senders of owned rows and
+    receivers of mirror edges are within r_cut of an owned atom)."""
+    px, py, pz = brick_grid(cell, world)
+    c = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    inv_np = np.linalg.inv(c)
+    inv = torch.as_tensor(inv_np, dtype=pos.dtype, device=pos.device)
+    frac = pos @ inv
+    frac = frac - torch.floor(frac)
+    heights = 1.0 / np.linalg.norm(inv_np, axis=0)                 # face-to-face distances
+    idx = (rank // (py * pz), (rank // pz) % py, rank % pz)
+    keep = torch.ones(pos.shape[0], dtype=torch.bool, device=pos.device)
+    for a, (n, k) in enumerate(zip((px, py, pz), idx)):
+        if n == 1:
+            continue
+        lo, hi = k / n, (k + 1) / n
+        m = margin / heights[a] * (1.0 + 1e-9) + 1e-12
+        centre, half = 0.5 * (lo + hi), 0.5 * (hi - lo) + m
+        if half >= 0.5:
+            continue
+        dist = torch.abs(frac[:, a] - centre)
+        dist = torch.minimum(dist, 1.0 - dist)                      # periodic distance to the brick centre
+        keep &= dist <= half
+    return keep
+
+
 def assign_owners_slab(pos: torch.Tensor, cell: np.ndarray, world: int, axis: int = 0) -> torch.Tensor:
     """owner[a] = slab index of atom a along `axis` (fractional coordinate wrapped into [0,1))."""
     inv = torch.as_tensor(np.linalg.inv(np.asarray(cell, dtype=np.float64)), dtype=pos.dtype, device=pos.device)

@@ -127,3 +127,27 @@ def test_domain_decomposition_over_gloo_world_size_2():
         assert pr.exitcode == 0
     assert abs(E - Eref) <= 1e-5 * abs(Eref)
     assert np.abs(F - Fref).max() < 1e-4
+
+
+def test_halo_subset_gives_the_same_plan_edges(solid):
+    """Building a rank's neighbour list only on the atoms of its brick + r_cut yields the same owned rows and mirror
+    edges (as global (i, j, S) sets) as building it on the whole system."""
+    pos_np, cell = solid['R'], solid['unit_cell']
+    pos = torch.as_tensor(pos_np)
+    world = 3
+    oi, oj, oS = o.primitive_neighbor_list(pos_np, cell, (1, 1, 1), 5.0)
+    owner = dd.assign_owners_bricks(pos, cell, world)
+    assert dd.brick_grid(cell, world) == (1, 1, 3)
+    for rank in range(world):
+        full = dd.build_plan(torch.as_tensor(oi), torch.as_tensor(oj), torch.as_tensor(oS), owner, rank, world)
+        keep = dd.brick_halo_mask(pos, cell, world, rank, 5.0)
+        sub = torch.nonzero(keep).reshape(-1)
+        si, sj, sS = o.primitive_neighbor_list(pos_np[sub.numpy()], cell, (1, 1, 1), 5.0)
+        part = dd.build_plan(torch.as_tensor(si), torch.as_tensor(sj), torch.as_tensor(sS), owner[sub], rank, world)
+
+        def edge_set(pl, ids):
+            gi, gj = ids[pl.local_atoms[pl.idx_i]], ids[pl.local_atoms[pl.idx_j]]
+            return sorted(zip(gi.tolist(), gj.tolist(), map(tuple, pl.shifts.tolist())))
+        assert edge_set(full, torch.arange(110)) == edge_set(part, sub)
+        assert torch.equal(sub[part.local_atoms], full.local_atoms)
+        assert part.send_counts == full.send_counts and part.recv_counts == full.recv_counts
