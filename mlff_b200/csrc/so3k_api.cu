@@ -201,6 +201,8 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base) {
   w.g.row = (int*)take(sizeof(int) * Pe);
   w.g.src = (int*)take(sizeof(int) * Pe);
   w.g.rev = (int*)take(sizeof(int) * Pe);
+  w.g.canon = (int*)take(sizeof(int) * (Pe + 4));
+  w.g.n_canon = w.g.canon + Pe;
   w.g.geom = (float4*)take(sizeof(float4) * Pe);
   w.g.n_valid = w.g.rowptr + N;
   w.scratch = (int*)take(sizeof(int) * so3k_graph_ws_ints(N, Pt));

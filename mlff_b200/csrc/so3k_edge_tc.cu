@@ -75,8 +75,8 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   if (4u * t.szA0 > region) region = 4u * t.szA0;                        // backward 2: rbf and rbf' images
   t.off_small = t.off_A1 + ((region + 127u) & ~127u);
   // small arrays (floats): b1p, b2p (Fp each), Ws1 (nl*Fs), bs1 (Fs), s_phi (TM), s_g (TM*nl), s_part (TM*16),
-  //                        s_i, s_j (TM each), s_head (Fp bytes, rounded to Fp/4 words + 4)
-  uint32_t small = 4u * (2u * t.Fp + (uint32_t)D.nl * D.Fs + D.Fs + TM + TM * D.nl + TM * 16 + 2 * TM + t.Fp / 4 + 4);
+  //                        (s_part is TM*24) s_i, s_j (TM each), s_head (Fp bytes, rounded to Fp/4 words + 4)
+  uint32_t small = 4u * (2u * t.Fp + (uint32_t)D.nl * D.Fs + D.Fs + TM + TM * D.nl + TM * 24 + 2 * TM + t.Fp / 4 + 4);
   t.total = t.off_small + ((small + 127u) & ~127u);
   return t;
 }
@@ -168,8 +168,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* smem, const TcDims& T,
   S.bs1 = S.Ws1 + D.nl * D.Fs;
   S.s_phi = S.bs1 + D.Fs;
   S.s_g = S.s_phi + TM;
-  S.s_part = S.s_g + TM * D.nl;  // TM * 16 floats of scratch
-  S.s_i = reinterpret_cast<int*>(S.s_part + TM * 16);
+  S.s_part = S.s_g + TM * D.nl;  // TM * 24 floats of scratch
+  S.s_i = reinterpret_cast<int*>(S.s_part + TM * 24);
   S.s_j = S.s_i + TM;
   S.s_head = reinterpret_cast<unsigned char*>(S.s_j + TM);
   return S;
@@ -230,18 +230,26 @@ __device__ unsigned long long g_tc_phase[3][16];
 // Per-edge metadata of one tile row, prefetched one tile ahead (global loads with a dependent chain: row/col -> chi rows)
 struct TileMeta {
   int i, j;
+  int e, re;                    // sorted edge index of this row and of its reverse (canonical-pair tiles)
   float d;
   float gl[SO3K_MAXDEG];        // l0 contraction of the chi difference (only meaningful for column quarter 0)
 };
 // level 1: receiver / sender / distance (issued early) ; level 2: chi rows -> l0 contraction (issued one GEMM later)
 __device__ __forceinline__ TileMeta tc_prefetch_meta1(int r, int qq, int e0, int nv, bool comp, const int* __restrict__ row,
-                                                      const int* __restrict__ col, const float4* __restrict__ geom) {
+                                                      const int* __restrict__ col, const float4* __restrict__ geom,
+                                                      const int* __restrict__ canon = nullptr,
+                                                      const int* __restrict__ rev = nullptr) {
   TileMeta m;
-  m.i = 0; m.j = 0; m.d = 0.f;
+  m.i = 0; m.j = 0; m.d = 0.f; m.e = 0; m.re = 0;
 #pragma unroll
   for (int l = 0; l < SO3K_MAXDEG; ++l) m.gl[l] = 0.f;
-  const int e = e0 + r;
+  int e = e0 + r;
   if (comp && e < nv) {
+    if (canon) {                 // rows are canonical edges: one per undirected pair
+      e = canon[e];
+      m.re = rev[e];
+    }
+    m.e = e;
     m.d = geom[e].w;
     if (qq == 0) {
       m.i = row[e];
@@ -264,8 +272,10 @@ __device__ __forceinline__ void tc_prefetch_meta2(const So3kDims& D, TileMeta& m
 }
 __device__ __forceinline__ TileMeta tc_prefetch_meta(const So3kDims& D, int r, int qq, int e0, int nv, bool comp,
                                                      const int* __restrict__ row, const int* __restrict__ col,
-                                                     const float4* __restrict__ geom, const float* __restrict__ chi) {
-  TileMeta m = tc_prefetch_meta1(r, qq, e0, nv, comp, row, col, geom);
+                                                     const float4* __restrict__ geom, const float* __restrict__ chi,
+                                                     const int* __restrict__ canon = nullptr,
+                                                     const int* __restrict__ rev = nullptr) {
+  TileMeta m = tc_prefetch_meta1(r, qq, e0, nv, comp, row, col, geom, canon, rev);
   tc_prefetch_meta2(D, m, r, qq, e0, nv, comp, chi);
   return m;
 }
@@ -710,8 +720,9 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
 //   dbar_rad[e] += sum_c hbar[c] silu'(a1[c]) (rbf'(d) @ W1)[c]         (a1 and the forward-mode term from 2 GEMM1s)
 //   gbar[e][l]  += sum_c hbar_s[c] silu'(a_s[c]) Ws1[l][c]
 __global__ void __launch_bounds__(NT, 1)
-k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, const int* __restrict__ n_valid,
-               const int* __restrict__ row, const int* __restrict__ col, const float4* __restrict__ geom,
+k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, const int* __restrict__ n_canon,
+               const int* __restrict__ canon, const int* __restrict__ rev, const int* __restrict__ row,
+               const int* __restrict__ col, const float4* __restrict__ geom,
                const float* __restrict__ chi, const float* __restrict__ proj, const unsigned char* __restrict__ img,
                const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
                const float* __restrict__ alphabar, float* __restrict__ gbar, float* __restrict__ ebar,
@@ -742,8 +753,9 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const uint32_t szWb = (uint32_t)(TM / 8) * sboWb;
   unsigned char* Wbhi = reinterpret_cast<unsigned char*>(S.region);   // aliases the rbf images: dead once the GEMM1s are done
   unsigned char* Wblo = Wbhi + szWb;
-  float* s_ab = S.s_part;                       // [TM][8]  alphabar * phi / sqrt(dh) per head
+  float* s_ab = S.s_part;                       // [TM][8]  alphabar[e] * phi / sqrt(dh) per head
   float* s_red = S.s_part + TM * 8;             // [TM][8]  cross-quarter reduction (dbar, gbar_l)
+  float* s_abr = S.s_part + TM * 16;            // [TM][8]  alphabar[rev e] * phi / sqrt(dh)
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -761,25 +773,28 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
   const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
   const uint32_t idesc3 = tc::make_idesc_bf16(TM, T.KC, 0, 1);     // B = W2c image read MN-major
-  const int nv = *n_valid;
-  const int nchunkF = T.Fp / 8;
-  const int nchunkK = T.KC / 8;
+  const int nv = *n_canon;                      // rows of this kernel = canonical edges (undirected pairs): the filter
+  const int nchunkF = T.Fp / 8;                 // and everything downstream of it are identical for e and rev e, and
+  const int nchunkK = T.KC / 8;                 // only dbar_e + dbar_rev / gbar_e + gbar_rev enter the forces
   const int kcb = (nchunkK * qq) / 4, kce = (nchunkK * (qq + 1)) / 4;   // this thread's hidden-column chunks
 
   uint32_t it = 0;
-  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi);
+  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, canon, rev);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
+    const int my_e = meta.e, my_re = meta.re;     // valid for r < ne
 
     if (comp) tc_tile_s0<true>(D, T, S, r, qq, ne, meta, A0dhi, A0dlo);
-    if (comp && qq == 1) {
+    if (comp && (qq == 1 || qq == 3)) {
       const float ph = (r < ne) ? cutoff_fast(meta.d, D.r_cut) * inv : 0.f;
+      float* dstab = (qq == 1) ? s_ab : s_abr;
+      const int esrc = (qq == 1) ? my_e : my_re;
 #pragma unroll
       for (int h = 0; h < 8; ++h)
-        s_ab[r * 8 + h] = (h < heads && r < ne) ? alphabar[(size_t)(e0 + r) * Ast + aoff + h] * ph : 0.f;
+        dstab[r * 8 + h] = (h < heads && r < ne) ? alphabar[(size_t)esrc * Ast + aoff + h] * ph : 0.f;
     }
     if (comp && qq == 2) {
 #pragma unroll
@@ -808,20 +823,27 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
 #pragma unroll
         for (int q = 0; q < 8; ++q) wv[q] = 0.f;
         if (f0 < F) {
-          const float* qi = proj + (size_t)S.s_i[rr] * F5 + qoff + f0;
-          const float* kj = proj + (size_t)S.s_j[rr] * F5 + koff + f0;
-          const float4 qa = *reinterpret_cast<const float4*>(qi);
-          const float4 ka = *reinterpret_cast<const float4*>(kj);
-          float4 qb = make_float4(0.f, 0.f, 0.f, 0.f), kb = qb;
+          // both directions of the pair: e = (i <- j) uses q_i k_j, rev e = (j <- i) uses q_j k_i
+          const float* pi = proj + (size_t)S.s_i[rr] * F5 + f0;
+          const float* pj = proj + (size_t)S.s_j[rr] * F5 + f0;
+          const float4 qia = *reinterpret_cast<const float4*>(pi + qoff), kja = *reinterpret_cast<const float4*>(pj + koff);
+          const float4 qja = *reinterpret_cast<const float4*>(pj + qoff), kia = *reinterpret_cast<const float4*>(pi + koff);
+          float4 qib = make_float4(0.f, 0.f, 0.f, 0.f), kjb = qib, qjb = qib, kib = qib;
           if (f0 + 4 < F) {
-            qb = *reinterpret_cast<const float4*>(qi + 4);
-            kb = *reinterpret_cast<const float4*>(kj + 4);
+            qib = *reinterpret_cast<const float4*>(pi + qoff + 4); kjb = *reinterpret_cast<const float4*>(pj + koff + 4);
+            qjb = *reinterpret_cast<const float4*>(pj + qoff + 4); kib = *reinterpret_cast<const float4*>(pi + koff + 4);
           }
-          const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-          const float kv[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+          const float fw[8] = {qia.x * kja.x, qia.y * kja.y, qia.z * kja.z, qia.w * kja.w,
+                               qib.x * kjb.x, qib.y * kjb.y, qib.z * kjb.z, qib.w * kjb.w};
+          const float bw[8] = {qja.x * kia.x, qja.y * kia.y, qja.z * kia.z, qja.w * kia.w,
+                               qjb.x * kib.x, qjb.y * kib.y, qjb.z * kib.z, qjb.w * kib.w};
           const float* sab = s_ab + rr * 8;
+          const float* sabr = s_abr + rr * 8;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) wv[q] = (f0 + q < F) ? sab[S.s_head[f0 + q]] * qv[q] * kv[q] : 0.f;
+          for (int q = 0; q < 8; ++q) {
+            const int hq = S.s_head[f0 + q];
+            wv[q] = (f0 + q < F) ? fmaf(sab[hq], fw[q], sabr[hq] * bw[q]) : 0.f;
+          }
         }
         tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rr, c, sboWb), wv);
       }
@@ -853,7 +875,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
       gb[l] = 0.f;
     }
-    meta = tc_prefetch_meta(D, r, qq, (tile + (int)gridDim.x) * TM, nv, comp, row, col, geom, chi);   // overlaps GEMM3
+    meta = tc_prefetch_meta(D, r, qq, (tile + (int)gridDim.x) * TM, nv, comp, row, col, geom, chi, canon, rev);   // overlaps GEMM3
     TC_WAIT_OR_BAIL(&bars[1], par);
     // ---- epilogue: this thread's quarter of the KC hidden columns of its row ------------------------------------------------
     {
@@ -896,12 +918,13 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       tc::fence_before_sync();
       __syncthreads();
       if (comp && qq == 0 && r < ne) {
-        const size_t e = (size_t)(e0 + r);
+        // the pair's totals go to the canonical edge; its reverse gets zeros (only the sums enter chi-bar and F)
+        const size_t e = (size_t)my_e, re = (size_t)my_re;
         const float db = s_red[r * 8 + 0];
-        if (blk == 0) ebar[2 * e] = db; else ebar[2 * e] += db;
+        if (blk == 0) { ebar[2 * e] = db; ebar[2 * re] = 0.f; } else ebar[2 * e] += db;
         for (int l = 0; l < D.nl; ++l) {
           const float gsum = s_red[r * 8 + 1 + l];
-          if (blk == 0) gbar[e * Gst + l] = gsum; else gbar[e * Gst + l] += gsum;
+          if (blk == 0) { gbar[e * Gst + l] = gsum; gbar[re * Gst + l] = 0.f; } else gbar[e * Gst + l] += gsum;
         }
       }
     }
@@ -991,7 +1014,7 @@ void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& 
     }
     if (parts & 2) {
       so3k_count_launch();
-      k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, Gst, n_tiles, g.n_valid, g.row, g.col, g.geom, chi, proj,
+      k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, Gst, n_tiles, g.n_canon, g.canon, g.rev, g.row, g.col, g.geom, chi, proj,
                                                         W.img, W.bias, W.Ws1, W.bs1, alphabar, gbar, ebar, status);
     }
   }

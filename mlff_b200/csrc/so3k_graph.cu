@@ -202,11 +202,24 @@ __global__ void k_rev(int N, const int* __restrict__ rowptr, const int* __restri
   }
 }
 
+// canonical edges: one representative per undirected pair {e, rev e} (the one with the smaller sorted index)
+__global__ void k_canon_flag(int N, const int* __restrict__ rowptr, const int* __restrict__ rev, int* __restrict__ flag, int Pt) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < Pt) flag[e] = (e < rowptr[N] && e < rev[e]) ? 1 : 0;
+}
+__global__ void k_canon_fill(int Pt, const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ canon,
+                             int* __restrict__ n_canon) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < Pt && flag[e]) canon[pos[e]] = e;
+  if (e == 0) *n_canon = pos[Pt];
+}
+
 }  // namespace
 
 size_t so3k_graph_ws_ints(int N, int Pt) {
   // deg (N+1) + cursor (N) + tmp_src (Pt) + slot_row (Pt) + bsum (cdiv(N+1,SCAN_BLK)+1) + total (1)
-  return (size_t)(N + 1) + N + 2 * (size_t)Pt + so3k_cdiv(N + 1, SCAN_BLK) + 8;
+  return (size_t)(N + 1) + N + 2 * (size_t)Pt + so3k_cdiv(N + 1, SCAN_BLK) + 8 +
+         (size_t)(Pt + 1) + so3k_cdiv(Pt + 1, SCAN_BLK) + 16;          // + canonical-edge scan
 }
 
 void so3k_build_graph(const So3kDims& D, int B, int n, int P, const float* R, const int* idx_i, const int* idx_j,
@@ -236,5 +249,15 @@ void so3k_build_graph(const So3kDims& D, int B, int n, int P, const float* R, co
     SO3K_LAUNCH(k_rowsort_geom, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, N, n, P, g.rowptr, deg, tmp_src, idx_j, R, cell,
                 cell_offset, disp, g.row, g.col, g.src, g.geom, slot_row);
     SO3K_LAUNCH(k_rev, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, N, g.rowptr, g.row, g.col, g.geom, g.rev, dev_status);
+    // canonical edge list (tmp_src is free again: reuse it for the flags)
+    int* flag = tmp_src;
+    int* cpos = total + 8;                         // (Pt + 1)
+    int nbp = so3k_cdiv(Pt, SCAN_BLK);
+    int* cbsum = cpos + Pt + 1;                    // (nbp + 2)
+    SO3K_LAUNCH(k_canon_flag, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, N, g.rowptr, g.rev, flag, Pt);
+    SO3K_LAUNCH(k_scan_local, dim3(nbp), dim3(SCAN_T), 0, st, Pt, flag, cpos, cbsum);
+    SO3K_LAUNCH(k_scan_bsum, dim3(1), dim3(SCAN_T), 0, st, nbp, cbsum, cbsum + nbp);
+    SO3K_LAUNCH(k_scan_add, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, cpos, cbsum, cbsum + nbp);
+    SO3K_LAUNCH(k_canon_fill, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, flag, cpos, g.canon, g.n_canon);
   }
 }

@@ -43,6 +43,8 @@ struct Graph {
   int* rev;           // (Pt)  sorted index of the reverse edge
   float4* geom;       // (Pt)  (ux, uy, uz, d)
   int* n_valid;       // device scalar = rowptr[N]
+  int* canon;         // (Pt)  sorted indices e with e < rev[e]: one representative per undirected pair
+  int* n_canon;       // device scalar
 };
 
 // ---- kernels' host launchers -------------------------------------------------------------------
