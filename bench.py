@@ -193,7 +193,7 @@ def run_ours(args, w):
     for k in prm:                                  # exercise the bias paths too
         if k.endswith('/bias'):
             prm[k] = rng.normal(0, 0.01, prm[k].shape).astype(np.float32)
-    flags = 0 if args.fp32_simt else 1
+    flags = 0 if args.fp32_simt else (1 if args.no_keep_filters else 3)
     try:
         calc = mlffCalculator(cfg, prm, device=dev, flags=flags)
     except Exception:
@@ -379,6 +379,7 @@ def run_ours(args, w):
                                f'domain decomposition: {grid[0]}x{grid[1]}x{grid[2]} bricks, mirror edges, per-layer halo exchange (NCCL all_to_all)'
                                if use_dd else f'replicas x{world} (no collective)'),
                            'filter_gemm': 'tcgen05 split-operand' if args.tensor else 'fp32 CUDA-core',
+                           'filters': 'kept for the backward' if (args.tensor and not args.no_keep_filters) else 'recomputed',
                            'l2': 'working set (edge + node arrays) larger than the 126 MB L2' if N >= 50_000 else
                                  'working set fits in L2 (latency/L2-bound configuration)'},
                 'e2e': {'value': e2e_val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
@@ -399,6 +400,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-keep-filters', action='store_true', help='recompute the filters in the backward instead of keeping '
+                    'them in HBM (2F floats per edge and layer)')
     ap.add_argument('--fp32-simt', action='store_true', help='run the filter GEMMs as fp32 FMA on the CUDA cores instead of '
                     'tcgen05 split-bf16 (the default where the shapes are supported)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

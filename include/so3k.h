@@ -70,7 +70,11 @@ enum {
   SO3K_FLAG_NONE = 0,
   /* filter-GEMM arithmetic: default = fp32 FMA on the CUDA cores (bit-faithful to fp32);
    * SO3K_FLAG_TENSOR = tcgen05 tensor cores with split-operand (3-pass) error compensation. */
-  SO3K_FLAG_TENSOR = 1
+  SO3K_FLAG_TENSOR = 1,
+  /* with SO3K_FLAG_TENSOR: the forward keeps every edge's filter vectors (2 * F floats per edge and layer in the
+   * workspace -- so3k_workspace_bytes accounts for it) and the backward streams them instead of recomputing the
+   * filter MLP for the q/k projection gradients.  Memory for time; results are identical. */
+  SO3K_FLAG_KEEP_FILTERS = 2
 };
 
 enum {

@@ -18,6 +18,7 @@ STATUS_OVERFLOW = 1
 STATUS_ASYMMETRIC = 2
 STATUS_BAD_Z = 4
 FLAG_TENSOR = 1
+FLAG_KEEP_FILTERS = 2    # with FLAG_TENSOR: keep the forward's filters for the backward (memory for time)
 NL_ASE = 0
 NL_DENSE = 1
 

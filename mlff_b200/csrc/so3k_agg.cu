@@ -174,6 +174,113 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
 }
 
+// q/k projection gradients from KEPT filters (SO3K_FLAG_KEEP_FILTERS: the forward stored w[e][f] of both blocks):
+//   qbar_i[f] = sum_{e in row i} alphabar[e][h(f)]     phi_e / sqrt(d_h) w_e[f] k_j[f]
+//   kbar_i[f] = sum_{e in row i} alphabar[rev e][h(f)] phi_e / sqrt(d_h) w_e[f] q_j[f]     (w, phi are symmetric in e <-> rev e)
+// and the cutoff cotangent  ebar[e][1] = sum_a alphabar[e][a] alpha[e][a] / phi_e.
+// Pure streaming: 2F floats of filters per edge from HBM, 4F floats of sender q/k rows (L2), no atomics.
+template <int TN>                               // TN = ceil(F / 32): feature slots per lane
+__global__ void __launch_bounds__(WPB * 32)
+k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
+                const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
+                const float* __restrict__ alpha, const float* __restrict__ alphabar, const float* __restrict__ wst_f,
+                const float* __restrict__ wst_g, float* __restrict__ gproj, float* __restrict__ ebar) {
+  __shared__ float s_ab[WPB][32 * AMAX];    // alphabar[e]     * phi / sqrt(d_h)
+  __shared__ float s_abr[WPB][32 * AMAX];   // alphabar[rev e] * phi / sqrt(d_h)
+  __shared__ int s_j[WPB][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const int F = D.F, H = D.H, nl = D.nl;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  const size_t F5 = 5 * (size_t)F;
+  const float inv_f = 1.0f / sqrtf((float)(F / H)), inv_g = 1.0f / sqrtf((float)(F / nl));
+  float aqf[TN], akf[TN], aqg[TN], akg[TN];
+  int hf[TN], hg[TN];
+#pragma unroll
+  for (int t = 0; t < TN; ++t) {
+    aqf[t] = akf[t] = aqg[t] = akg[t] = 0.f;
+    const int f = lane + 32 * t;
+    hf[t] = (f < F) ? f / (F / H) : 0;
+    hg[t] = (f < F) ? H + f / (F / nl) : 0;
+  }
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const int cnt = (end - e0) < 32 ? (end - e0) : 32;
+    int j = 0;
+    if (e < end) {
+      j = col[e];
+      const int re = rev[e];
+      const float ph = so3k_cutoff(geom[e].w, D.r_cut);
+      float pb = 0.f;
+      for (int a = 0; a < H + nl; ++a) {
+        const float ab = alphabar[(size_t)e * Ast + a];
+        const float sc = ph * (a < H ? inv_f : inv_g);
+        pb = fmaf(ab, alpha[(size_t)e * Ast + a], pb);
+        s_ab[w][lane * Ast + a] = ab * sc;
+        s_abr[w][lane * Ast + a] = alphabar[(size_t)re * Ast + a] * sc;
+      }
+      ebar[2 * (size_t)e + 1] = ph > 1e-30f ? pb / ph : 0.f;
+    }
+    s_j[w][lane] = j;
+    __syncwarp();
+    // two edges per iteration: 12 * TN independent loads in flight per lane (the kernel is latency-bound otherwise)
+    for (int q = 0; q < cnt; q += 2) {
+      const bool two = q + 1 < cnt;
+      const int q1 = two ? q + 1 : q;
+      const float* pj0 = proj + (size_t)s_j[w][q] * F5;
+      const float* pj1 = proj + (size_t)s_j[w][q1] * F5;
+      const float* wf0 = wst_f + (size_t)(e0 + q) * F;
+      const float* wg0 = wst_g + (size_t)(e0 + q) * F;
+      const float* wf1 = wst_f + (size_t)(e0 + q1) * F;
+      const float* wg1 = wst_g + (size_t)(e0 + q1) * F;
+      float vf0[TN], vg0[TN], kf0[TN], kg0[TN], qf0[TN], qg0[TN];
+      float vf1[TN], vg1[TN], kf1[TN], kg1[TN], qf1[TN], qg1[TN];
+#pragma unroll
+      for (int t = 0; t < TN; ++t) {
+        const int f = lane + 32 * t;
+        const bool ok = (t + 1 < TN) || f < F;
+        vf0[t] = ok ? __ldcs(wf0 + f) : 0.f;  vg0[t] = ok ? __ldcs(wg0 + f) : 0.f;
+        kf0[t] = ok ? pj0[2 * F + f] : 0.f;   kg0[t] = ok ? pj0[3 * F + f] : 0.f;
+        qf0[t] = ok ? pj0[f] : 0.f;           qg0[t] = ok ? pj0[F + f] : 0.f;
+        vf1[t] = ok ? __ldcs(wf1 + f) : 0.f;  vg1[t] = ok ? __ldcs(wg1 + f) : 0.f;
+        kf1[t] = ok ? pj1[2 * F + f] : 0.f;   kg1[t] = ok ? pj1[3 * F + f] : 0.f;
+        qf1[t] = ok ? pj1[f] : 0.f;           qg1[t] = ok ? pj1[F + f] : 0.f;
+      }
+      const float* ab0 = &s_ab[w][q * Ast];
+      const float* abr0 = &s_abr[w][q * Ast];
+      const float* ab1 = &s_ab[w][q1 * Ast];
+      const float* abr1 = &s_abr[w][q1 * Ast];
+      const float m1 = two ? 1.f : 0.f;
+#pragma unroll
+      for (int t = 0; t < TN; ++t) {
+        aqf[t] = fmaf(ab0[hf[t]] * vf0[t], kf0[t], aqf[t]);
+        akf[t] = fmaf(abr0[hf[t]] * vf0[t], qf0[t], akf[t]);
+        aqg[t] = fmaf(ab0[hg[t]] * vg0[t], kg0[t], aqg[t]);
+        akg[t] = fmaf(abr0[hg[t]] * vg0[t], qg0[t], akg[t]);
+        aqf[t] = fmaf(m1 * ab1[hf[t]] * vf1[t], kf1[t], aqf[t]);
+        akf[t] = fmaf(m1 * abr1[hf[t]] * vf1[t], qf1[t], akf[t]);
+        aqg[t] = fmaf(m1 * ab1[hg[t]] * vg1[t], kg1[t], aqg[t]);
+        akg[t] = fmaf(m1 * abr1[hg[t]] * vg1[t], qg1[t], akg[t]);
+      }
+    }
+    __syncwarp();
+  }
+  if (rowok) {
+    float* gi = gproj + (size_t)i * F5;
+#pragma unroll
+    for (int t = 0; t < TN; ++t) {
+      const int f = lane + 32 * t;
+      if (f < F) {
+        gi[f] = aqf[t];
+        gi[F + f] = aqg[t];
+        gi[2 * F + f] = akf[t];
+        gi[3 * F + f] = akg[t];
+      }
+    }
+  }
+}
+
 // chibar[i][m] = chibar1[i][m] - 2 cg[m] sum_{e in row i} c_em (gbar[e][l(m)] + gbar[rev e][l(m)]),  c_e = chi[j]-chi[i]
 __global__ void __launch_bounds__(WPB * 32)
 k_chi_bwd(So3kDims D, int N, int Gst, const int* __restrict__ rowptr, const int* __restrict__ col,
@@ -244,6 +351,23 @@ void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj,
   int Ast = (D.H + D.nl + 3) & ~3;
   SO3K_LAUNCH(k_alpha_bwd, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col, g.rev, g.geom,
               proj, alpha, xbar1, chibar1, alphabar, gproj);
+}
+
+void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
+                               const float* alphabar, const float* wst_f, const float* wst_g, float* gproj, float* ebar,
+                               cudaStream_t st) {
+  int Ast = (D.H + D.nl + 3) & ~3;
+#define SO3K_QK_CASE(TN_)                                                                                              \
+  case TN_:                                                                                                            \
+    SO3K_LAUNCH(k_qk_bwd_stream<TN_>, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,  \
+                g.rev, g.geom, proj, alpha, alphabar, wst_f, wst_g, gproj, ebar);                                      \
+    break;
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_QK_CASE(1) SO3K_QK_CASE(2) SO3K_QK_CASE(3) SO3K_QK_CASE(4) SO3K_QK_CASE(5) SO3K_QK_CASE(6) SO3K_QK_CASE(7)
+    SO3K_QK_CASE(8)
+    default: break;
+  }
+#undef SO3K_QK_CASE
 }
 
 void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,

@@ -44,6 +44,7 @@ struct HandleImpl : so3k_handle {
   bool use_tc = false;
   int tc_parts = 3;                  // SO3K_TC_PARTS env: debugging aid to mix tensor-core / CUDA-core backward pieces
   bool tc_fwd = true;
+  bool keep_w = false;               // SO3K_FLAG_KEEP_FILTERS (only with the tensor-core forward)
   Profiler prof;
 };
 
@@ -179,12 +180,13 @@ struct Workspace {
   float *proj, *gproj;
   float *alpha;            // per layer
   float *alphabar, *gbar, *rbar, *ebar;
+  float *wst;              // kept filters: [layer][block][edge][F] (SO3K_FLAG_KEEP_FILTERS), else nullptr
   float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
   float *e_atom;
   size_t bytes;
 };
 
-Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base) {
+Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, bool keep_w) {
   Workspace w;
   char* p = (char*)base;
   auto take = [&](size_t bytes) {
@@ -218,6 +220,7 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base) {
   w.gbar = (float*)take(sizeof(float) * Pe * Gst);
   w.rbar = (float*)take(sizeof(float) * Pe * 3);
   w.ebar = (float*)take(sizeof(float) * Pe * 2);
+  w.wst = keep_w ? (float*)take(sizeof(float) * L * 2 * Pe * F) : nullptr;
   w.xbar_a = (float*)take(sizeof(float) * N * F);
   w.xbar_b = (float*)take(sizeof(float) * N * F);
   w.chibar_a = (float*)take(sizeof(float) * N * M);
@@ -249,7 +252,10 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
   { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
   {
     PROF(CAT_EDGE_FWD);
-    if (h->use_tc && h->tc_fwd) so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, dev_status, st);
+    float* wst_t = w.wst ? w.wst + (size_t)t * 2 * Pe * F : nullptr;
+    if (h->use_tc && h->tc_fwd)
+      so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, wst_t, wst_t ? wst_t + Pe * F : nullptr,
+                              dev_status, st);
     else so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
   }
   { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
@@ -296,11 +302,16 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
     PROF(CAT_EDGE_BWD);
     // tc_parts: which backward pieces run on the tensor cores (bit 0: q/k gradients + cutoff cotangent,
     // bit 1: radial + l0-contraction cotangents); the rest runs the fp32 CUDA-core kernel
-    const int tcp = h->use_tc ? h->tc_parts : 0;
-    if (tcp) so3k_launch_edge_bwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, w.alphabar, tcp, w.gproj, w.gbar, w.ebar,
+    int tcp = h->use_tc ? h->tc_parts : 0;
+    const int simt = 3 & ~tcp;         // pieces left to the fp32 CUDA-core kernel
+    if (w.wst && (tcp & 1)) {          // kept filters: the q/k gradients are a streaming pass, no filter recomputation
+      const float* wst_t = w.wst + (size_t)t * 2 * Pe * F;
+      so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, wst_t + Pe * F, w.gproj, w.ebar, st);
+      tcp &= ~1;
+    }
+    if (tcp) so3k_launch_edge_bwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, w.alphabar, tcp, w.gproj, w.gbar, w.ebar,
                                      dev_status, st);
-    if (tcp != 3) so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3 & ~tcp, w.gproj, w.gbar,
-                                       w.ebar, st);
+    if (simt) so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, simt, w.gproj, w.gbar, w.ebar, st);
     so3k_launch_edge_finish(D, w.g, alpha_t, w.chibar_b, w.ebar, w.rbar, st);
   }
   if (t > 0) {
@@ -319,7 +330,7 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
   const So3kDims& D = h->dims;
   const int N = B * n, Pt = B * P;
   if (workspace_bytes < so3k_workspace_bytes(h, N, Pt)) return SO3K_ERR_WORKSPACE;
-  Workspace w = carve_ws(D, N, Pt, workspace);
+  Workspace w = carve_ws(D, N, Pt, workspace, h->keep_w && h->tc_fwd);
   stage_begin(h, w, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, disp, mask, dev_status, st);
   for (int t = 0; t < D.L; ++t) stage_layer_fwd(h, w, t, dev_status, st);
   float* e_atom = e_atom_out ? e_atom_out : w.e_atom;
@@ -352,6 +363,7 @@ int so3k_create(const so3k_config* cfg, so3k_handle** out) {
   h->cfg = *cfg;
   h->dims = D;
   h->use_tc = (cfg->flags & SO3K_FLAG_TENSOR) != 0;
+  h->keep_w = h->use_tc && (cfg->flags & SO3K_FLAG_KEEP_FILTERS) != 0;
   if (const char* e = getenv("SO3K_TC_PARTS")) {       // bit 0/1: backward pieces, bit 2: forward
     int v = atoi(e);
     h->tc_parts = v & 3;
@@ -424,7 +436,8 @@ int so3k_load_params(so3k_handle* hh, const float* blob_dev, size_t n_floats, vo
 
 size_t so3k_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total) {
   if (!h || n_atoms_total <= 0 || n_edge_slots_total < 0) return 0;
-  Workspace w = carve_ws(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, nullptr);
+  const HandleImpl* hi = static_cast<const HandleImpl*>(h);
+  Workspace w = carve_ws(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, nullptr, hi->keep_w && hi->tc_fwd);
   return w.bytes + 256;
 }
 
@@ -480,7 +493,7 @@ int so3k_dd_begin(so3k_handle* hh, int32_t N, int32_t P, const float* R, const i
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (!h->have_params) return SO3K_ERR_NOPARAMS;
   if (workspace_bytes < so3k_workspace_bytes(h, N, P)) return SO3K_ERR_WORKSPACE;
-  Workspace w = carve_ws(h->dims, N, P, workspace);
+  Workspace w = carve_ws(h->dims, N, P, workspace, h->keep_w && h->tc_fwd);
   stage_begin(h, w, 1, N, P, R, z, idx_i, idx_j, cell, cell_offset, nullptr, nullptr, dev_status, (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
 }
@@ -492,7 +505,7 @@ int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t 
   if (!hh || !workspace || N <= 0) return SO3K_ERR_ARG;
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (t < 0 || t >= h->dims.L) return SO3K_ERR_ARG;
-  Workspace w = carve_ws(h->dims, N, P, workspace);
+  Workspace w = carve_ws(h->dims, N, P, workspace, h->keep_w && h->tc_fwd);
   cudaStream_t st = (cudaStream_t)stream;
   switch (stage) {
     case 0: stage_layer_fwd(h, w, t, dev_status, st); break;
@@ -510,7 +523,8 @@ int so3k_dd_buffer(const so3k_handle* hh, int32_t which, int32_t t, int32_t N, i
   if (!hh || !offset || !row_floats || N <= 0) return SO3K_ERR_ARG;
   const So3kDims& D = hh->dims;
   if (t < 0 || t > D.L) return SO3K_ERR_ARG;
-  Workspace w = carve_ws(D, N, P, nullptr);
+  const HandleImpl* h = static_cast<const HandleImpl*>(hh);
+  Workspace w = carve_ws(D, N, P, nullptr, h->keep_w && h->tc_fwd);
   const char* base = nullptr;
   const char* p = nullptr;
   switch (which) {

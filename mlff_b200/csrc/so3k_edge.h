@@ -38,7 +38,7 @@ size_t so3k_edge_tc_image_bytes(const So3kDims& D);   // per block
 void so3k_edge_tc_build(const So3kDims& D, const float* params, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
                         const EdgeBlockW& simt, cudaStream_t st);
 void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, float* alpha, int* status, cudaStream_t st);
+                             const float* proj, float* alpha, float* wst_f, float* wst_g, int* status, cudaStream_t st);
 void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, const float* alphabar, int parts, float* gproj, float* gbar, float* ebar,
-                             int* status, cudaStream_t st);
+                             const float* proj, const float* alpha, const float* alphabar, int parts, float* gproj,
+                             float* gbar, float* ebar, int* status, cudaStream_t st);

@@ -248,6 +248,8 @@ __device__ __forceinline__ TileMeta tc_prefetch_meta1(int r, int qq, int e0, int
     if (canon) {                 // rows are canonical edges: one per undirected pair
       e = canon[e];
       m.re = rev[e];
+    } else if (rev && qq == 3) {
+      m.re = rev[e];             // backward part 1: quarter 3 stages alphabar of the reverse edge
     }
     m.e = e;
     m.d = geom[e].w;
@@ -397,6 +399,45 @@ __device__ __forceinline__ float sel8(const float* a, int h) {
   return v;
 }
 
+// backward part 1 helpers: rows [rb, rb+8) of the transposed epilogue for the feature this thread owns
+__device__ __forceinline__ void b1_gather8(float* kj, float* qj, const float* __restrict__ pk, const float* __restrict__ pq,
+                                           const int* s_j, size_t F5, int rb, int rend) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    kj[u] = 0.f;
+    qj[u] = 0.f;
+    if (rb + u < rend) {
+      const size_t jo = (size_t)s_j[rb + u] * F5;
+      kj[u] = __ldg(pk + jo);
+      qj[u] = __ldg(pq + jo);
+    }
+  }
+}
+__device__ __forceinline__ void b1_accum8(const float* v, const float* kj, const float* qj, const float* s_ab,
+                                          const float* s_abr, const int* s_i, int rb, int rend, int hf, float b2, bool fok,
+                                          float* __restrict__ gq, float* __restrict__ gk, size_t F5, int& icur, float& cq,
+                                          float& ck) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int rr = rb + u;
+    if (rr < rend) {                               // warp-uniform
+      const int ir = s_i[rr];
+      if (ir != icur) {                            // receiver run ends: one atomic per (run, feature)
+        if (fok) {
+          atomicAdd(gq + (size_t)icur * F5, cq);
+          atomicAdd(gk + (size_t)icur * F5, ck);
+        }
+        cq = 0.f;
+        ck = 0.f;
+        icur = ir;
+      }
+      const float wv = v[u] + b2;
+      cq = fmaf(s_ab[rr * 8 + hf] * wv, kj[u], cq);
+      ck = fmaf(s_abr[rr * 8 + hf] * wv, qj[u], ck);
+    }
+  }
+}
+
 // MODE 0: forward  -> alpha[e][aoff + h]
 // MODE 1: backward part 1 (recomputes the tile's filter w) -> gproj q/k parts (atomics), ebar[e][1] (cutoff cotangent)
 template <int MODE>
@@ -406,7 +447,7 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
           const float4* __restrict__ geom, const float* __restrict__ chi, const float* __restrict__ proj,
           const unsigned char* __restrict__ img, const float* __restrict__ bias_g, const float* __restrict__ Ws1_g,
           const float* __restrict__ bs1_g, float* __restrict__ alpha, const float* __restrict__ alphabar,
-          float* __restrict__ gproj, float* __restrict__ ebar, int* __restrict__ status) {
+          float* __restrict__ gproj, float* __restrict__ ebar, float* __restrict__ wst, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
@@ -446,13 +487,32 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
   const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;    // this thread's D2 chunks
 
   uint32_t it = 0;
-  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi);
+  const int* rev_m = (MODE == 1) ? rev : nullptr;
+  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, nullptr, rev_m);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;                     // block-uniform
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
     long long t_prev_ = TC_TIMING ? clock64() : 0;
+
+    // backward part 1: alphabar of this row (quarter 1) / of its reverse edge (quarter 3), loaded now, staged to shared
+    // memory after GEMM1 is issued; cutoff cotangent from the stored forward coefficients:
+    //   phibar = sum_h alphabar_h alpha_h / phi
+    float abv[8];
+    float pbv = 0.f;
+    if (MODE == 1) {
+      const bool okb = comp && (qq == 1 || qq == 3) && r < ne;
+      const size_t es = okb ? (size_t)(qq == 1 ? e0 + r : meta.re) : 0;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        abv[h] = 0.f;
+        if (okb && h < heads) {
+          abv[h] = alphabar[es * Ast + aoff + h];
+          if (qq == 1) pbv = fmaf(abv[h], alpha[es * Ast + aoff + h], pbv);
+        }
+      }
+    }
 
     if (comp) tc_tile_s0<false>(D, T, S, r, qq, ne, meta, nullptr, nullptr);
     TC_PHASE(MODE, 0);
@@ -468,7 +528,20 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
     // long-latency global loads issued as early as possible: level-1 metadata of this CTA's next tile and (forward)
     // the q_i * k_j rows of this tile; both are consumed only after GEMM2
     const int e0_next = (tile + (int)gridDim.x) * TM;
-    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom);
+    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom, nullptr, rev_m);
+    if (MODE == 1 && comp && (qq == 1 || qq == 3)) {
+      // per row and head: ab = alphabar[e] phi / sqrt(dh) (quarter 1), abr = alphabar[rev e] phi / sqrt(dh) (quarter 3)
+      const float ph = S.s_phi[r];
+      float* dstab = S.s_part + (qq == 1 ? 0 : TM * 8) + r * 8;
+      const float sc = inv * ph;
+      *reinterpret_cast<float4*>(dstab) = make_float4(abv[0] * sc, abv[1] * sc, abv[2] * sc, abv[3] * sc);
+      *reinterpret_cast<float4*>(dstab + 4) = make_float4(abv[4] * sc, abv[5] * sc, abv[6] * sc, abv[7] * sc);
+      if (r < ne && qq == 1) {
+        const float pb = ph > 1e-30f ? pbv / ph : 0.f;
+        float* dst = ebar + 2 * (size_t)(e0 + r) + 1;
+        if (blk == 0) *dst = pb; else *dst += pb;
+      }
+    }
     TC_PHASE(MODE, 2);
     TC_WAIT_OR_BAIL(&bars[0], par);
     TC_PHASE(MODE, 3);
@@ -480,7 +553,18 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
     TC_PHASE(MODE, 5);
     if (tid == ISSUER) {
       tc::fence_after_sync();
-      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
+      if (MODE == 0) {
+        tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
+      } else {
+        // backward: the filter TRANSPOSED, D2T[f][r] (TMEM lane = feature, column = tile row), so that the sums over
+        // the rows of a receiver become serial register sums of the thread that owns feature f.  Features >= 128
+        // (at most 16 of them) come from a small untransposed GEMM, D2x[r][f - 128].
+        tc_issue_gemm(tD2, S.W2hi, S.W2lo, T.sboW2, S.A1hi, S.A1lo, T.sboA1, T.KC / 16,
+                      tc::make_idesc_bf16(128, TM, 0, 0));
+        if (T.Fp > 128)
+          tc_issue_gemm(tD2 + 128, S.A1hi, S.A1lo, T.sboA1, S.W2hi + 16 * T.sboW2, S.W2lo + 16 * T.sboW2, T.sboW2,
+                        T.KC / 16, tc::make_idesc_bf16(TM, T.Fp - 128, 0, 0));
+      }
       tc::commit(&bars[1]);
     }
     // while GEMM2 runs: pull the next tile's gather rows into L2 (their senders are random atoms: DRAM tail latency
@@ -490,8 +574,10 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
       if (comp && qq == 0 && e0_next + r < nv) {
         tc_l2_prefetch_seg(proj, F5, meta_nx.j, koff, F);
         if (MODE == 1) tc_l2_prefetch_seg(proj, F5, meta_nx.j, qoff, F);
-        if (lane == 0 || prev_i != meta_nx.i) tc_l2_prefetch_seg(proj, F5, meta_nx.i, qoff, F);
+        if (MODE == 0 && (lane == 0 || prev_i != meta_nx.i)) tc_l2_prefetch_seg(proj, F5, meta_nx.i, qoff, F);
       }
+      if (MODE == 1 && comp && qq == 3 && e0_next + r < nv)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(alphabar + (size_t)meta_nx.re * Ast + aoff));
     }
     float4 pq[8];
     float4 px = make_float4(0.f, 0.f, 0.f, 0.f);   // float4 column 32 + qq of row r (F <= 144 -> at most 4 of them)
@@ -535,6 +621,7 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
       // a quarter (<= 40 columns) touches at most 4 heads; partial sums go to slot (head - first head of the quarter)
       if (comp) {
         const float* qrow = qk + (size_t)r * T.QS;
+        float* wrow = (wst && r < ne) ? wst + (size_t)(e0 + r) * F : nullptr;    // keep the filter for the backward
         const int f0 = cbeg * 8;
         const int h0 = (f0 < F) ? S.s_head[f0] : 0;
         float acc = 0.f;
@@ -554,10 +641,16 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
                 const float4 qb = *reinterpret_cast<const float4*>(qrow + c0 + 4);
                 const float4 ba = *reinterpret_cast<const float4*>(S.b2p + c0);
                 const float4 bb = *reinterpret_cast<const float4*>(S.b2p + c0 + 4);
-                acc = fmaf(v[u][0] + ba.x, qa.x, acc); acc = fmaf(v[u][1] + ba.y, qa.y, acc);
-                acc = fmaf(v[u][2] + ba.z, qa.z, acc); acc = fmaf(v[u][3] + ba.w, qa.w, acc);
-                acc = fmaf(v[u][4] + bb.x, qb.x, acc); acc = fmaf(v[u][5] + bb.y, qb.y, acc);
-                acc = fmaf(v[u][6] + bb.z, qb.z, acc); acc = fmaf(v[u][7] + bb.w, qb.w, acc);
+                const float4 wa = make_float4(v[u][0] + ba.x, v[u][1] + ba.y, v[u][2] + ba.z, v[u][3] + ba.w);
+                const float4 wb = make_float4(v[u][4] + bb.x, v[u][5] + bb.y, v[u][6] + bb.z, v[u][7] + bb.w);
+                if (wrow) {
+                  __stcs(reinterpret_cast<float4*>(wrow + c0), wa);
+                  __stcs(reinterpret_cast<float4*>(wrow + c0 + 4), wb);
+                }
+                acc = fmaf(wa.x, qa.x, acc); acc = fmaf(wa.y, qa.y, acc);
+                acc = fmaf(wa.z, qa.z, acc); acc = fmaf(wa.w, qa.w, acc);
+                acc = fmaf(wb.x, qb.x, acc); acc = fmaf(wb.y, qb.y, acc);
+                acc = fmaf(wb.z, qb.z, acc); acc = fmaf(wb.w, qb.w, acc);
               } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -569,7 +662,9 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
                       acc = 0.f;
                       hcur = hf;
                     }
-                    acc = fmaf(v[u][q] + S.b2p[f], qrow[f], acc);
+                    const float wv = v[u][q] + S.b2p[f];
+                    if (wrow) wrow[f] = wv;
+                    acc = fmaf(wv, qrow[f], acc);
                   }
                 }
               }
@@ -604,109 +699,108 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
       if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[MODE][15], 1ull);
     } else {
       // ================= backward part 1 ========================================================================
-      // per row: ab[h] = alphabar[e][h] / sqrt(dh) ; abr[h] = alphabar[rev e][h] / sqrt(dh)
-      float ab[8], abr[8];
-      const float phi_r = S.s_phi[r];
+      //   qbar_i[f] += sum_{e -> i} ab_e[h(f)]  w_e[f] k_j[f]      kbar_i[f] += sum_{e -> i} abr_e[h(f)] w_e[f] q_j[f]
+      // (the second through the reverse edge: kbar_i collects alphabar of the edges that i SENDS)
+      const float* s_ab = S.s_part;
+      const float* s_abr = S.s_part + TM * 8;
+      // ---- features < 128: thread = (feature f = TMEM lane, 32-row range qq); rows are receiver-sorted, so a
+      //      receiver's rows are consecutive: serial sums in registers, one atomic per (run, feature).
+      //      The k_j / q_j gathers run two 8-row chunks ahead (the first two are in flight while GEMM2 executes).
+      const int f = 32 * (warp & 3) + lane;
+      const bool fok = comp && f < F;
+      const float b2 = fok ? S.b2p[f] : 0.f;
+      const int hf = fok ? (int)S.s_head[f] : 0;
+      const float* pkj = proj + koff + (fok ? f : 0);
+      const float* pqj = proj + qoff + (fok ? f : 0);
+      float* gq = gproj + qoff + (fok ? f : 0);
+      float* gk = gproj + koff + (fok ? f : 0);
+      const int rbeg = 32 * qq;
+      const int rend = (rbeg + 32 < ne) ? rbeg + 32 : ne;
+      float kA[8], qA[8], kB[8], qB[8];
+      b1_gather8(kA, qA, pkj, pqj, S.s_j, F5, rbeg, rend);
+      b1_gather8(kB, qB, pkj, pqj, S.s_j, F5, rbeg + 8, rend);
+      const int ntail = F - 128;                             // features >= 128: column 128 + qq + 4k of row r
+      float tkj[4], tqj[4];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        ab[h] = 0.f;
-        abr[h] = 0.f;
-        if (comp && h < heads && r < ne) {
-          ab[h] = alphabar[(size_t)(e0 + r) * Ast + aoff + h] * inv;
-          abr[h] = alphabar[(size_t)rev[e0 + r] * Ast + aoff + h] * inv;
+      for (int k = 0; k < 4; ++k) {
+        tkj[k] = 0.f;
+        tqj[k] = 0.f;
+        if (comp && qq + 4 * k < ntail && r < ne) {
+          const size_t jo = (size_t)S.s_j[r] * F5 + 128 + qq + 4 * k;
+          tkj[k] = __ldg(proj + jo + koff);
+          tqj[k] = __ldg(proj + jo + qoff);
         }
       }
-      // receiver runs inside this warp's 32 rows (rows are receiver-sorted)
-      SegMask SM = {false, false, false, false, false};
-      bool run_head = false;
-      const int my_i = (r < ne) ? S.s_i[r] : -1 - r;           // invalid rows form runs of their own
-      if (comp) {
-        const int i1 = __shfl_down_sync(0xffffffffu, my_i, 1), i2 = __shfl_down_sync(0xffffffffu, my_i, 2);
-        const int i4 = __shfl_down_sync(0xffffffffu, my_i, 4), i8 = __shfl_down_sync(0xffffffffu, my_i, 8);
-        const int i16 = __shfl_down_sync(0xffffffffu, my_i, 16);
-        const int ip = __shfl_up_sync(0xffffffffu, my_i, 1);
-        SM.m1 = lane + 1 < 32 && i1 == my_i;
-        SM.m2 = lane + 2 < 32 && i2 == my_i;
-        SM.m4 = lane + 4 < 32 && i4 == my_i;
-        SM.m8 = lane + 8 < 32 && i8 == my_i;
-        SM.m16 = lane + 16 < 32 && i16 == my_i;
-        run_head = (r < ne) && (lane == 0 || ip != my_i);
-      }
+      TC_PHASE(MODE, 7);
       TC_WAIT_OR_BAIL(&bars[1], par);
-      // staging tiles (alias the dead A1 image): QI, KJ, QJ, each [TM][WS] floats, column window of WIN
-      float* QI = S.region;
-      float* KJ = QI + TM * WS;
-      float* QJ = KJ + TM * WS;
-      float phibar = 0.f;
-      for (int w0 = 0; w0 < T.Fp; w0 += WIN) {
-        // ---- gather the window [w0, w0+32) of q_i, k_j, q_j: lane -> (row of 4, float4 of 8); 8 rows per warp -------
-        if (comp) {
-          const int sub = lane >> 3, f4 = lane & 7;
-          const int f = w0 + 4 * f4;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int rr = warp * 8 + 4 * u + sub;
-            float4 qi = make_float4(0.f, 0.f, 0.f, 0.f), kj = qi, qj = qi;
-            if (f < F) {
-              const float* pi = proj + (size_t)S.s_i[rr] * F5;
-              const float* pj = proj + (size_t)S.s_j[rr] * F5;
-              qi = *reinterpret_cast<const float4*>(pi + qoff + f);
-              kj = *reinterpret_cast<const float4*>(pj + koff + f);
-              qj = *reinterpret_cast<const float4*>(pj + qoff + f);
-            }
-            *reinterpret_cast<float4*>(QI + rr * WS + 4 * f4) = qi;
-            *reinterpret_cast<float4*>(KJ + rr * WS + 4 * f4) = kj;
-            *reinterpret_cast<float4*>(QJ + rr * WS + 4 * f4) = qj;
-          }
+      TC_PHASE(MODE, 8);
+      if (comp) {
+        float cq = 0.f, ck = 0.f;
+        int icur = (rbeg < rend) ? S.s_i[rbeg] : -1;
+        float vA[8], vB[8];
+        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)rbeg, vA);
+        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)(rbeg + 8), vB);
+        tc::tmem_ld_wait();
+        b1_accum8(vA, kA, qA, s_ab, s_abr, S.s_i, rbeg, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
+        b1_gather8(kA, qA, pkj, pqj, S.s_j, F5, rbeg + 16, rend);
+        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)(rbeg + 16), vA);
+        b1_accum8(vB, kB, qB, s_ab, s_abr, S.s_i, rbeg + 8, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
+        b1_gather8(kB, qB, pkj, pqj, S.s_j, F5, rbeg + 24, rend);
+        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)(rbeg + 24), vB);
+        tc::tmem_ld_wait();
+        b1_accum8(vA, kA, qA, s_ab, s_abr, S.s_i, rbeg + 16, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
+        b1_accum8(vB, kB, qB, s_ab, s_abr, S.s_i, rbeg + 24, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
+        if (icur >= 0 && fok) {
+          atomicAdd(gq + (size_t)icur * F5, cq);
+          atomicAdd(gk + (size_t)icur * F5, ck);
         }
-        __syncthreads();
-        // ---- this thread's 8 columns of the window -------------------------------------------------------------------
-        const int c0 = w0 + qq * 8;                      // warp-uniform
-        if (comp && c0 < F) {
-          float v[8];
-          tc::tmem_ld8(tD2 + lane_sel + (uint32_t)c0, v);
-          float qi[8], kj[8], qj[8];
-          *reinterpret_cast<float4*>(qi) = *reinterpret_cast<const float4*>(QI + r * WS + qq * 8);
-          *reinterpret_cast<float4*>(qi + 4) = *reinterpret_cast<const float4*>(QI + r * WS + qq * 8 + 4);
-          *reinterpret_cast<float4*>(kj) = *reinterpret_cast<const float4*>(KJ + r * WS + qq * 8);
-          *reinterpret_cast<float4*>(kj + 4) = *reinterpret_cast<const float4*>(KJ + r * WS + qq * 8 + 4);
-          *reinterpret_cast<float4*>(qj) = *reinterpret_cast<const float4*>(QJ + r * WS + qq * 8);
-          *reinterpret_cast<float4*>(qj + 4) = *reinterpret_cast<const float4*>(QJ + r * WS + qq * 8 + 4);
+        TC_PHASE(MODE, 9);
+        // ---- features >= 128 (untransposed, TMEM lane = row): column 128 + qq + 4k of row r; segmented warp sums -------
+        if (ntail > 0) {
+          float vt[16];
+          tc::tmem_ld8(tD2 + 128 + lane_sel, vt);
+          tc::tmem_ld8(tD2 + 128 + lane_sel + 8, vt + 8);
           tc::tmem_ld_wait();
-          int h = S.s_head[c0];
-          float abh = sel8(ab, h), abrh = sel8(abr, h);
+          SegMask SM = {false, false, false, false, false};
+          const int my_i = (r < ne) ? S.s_i[r] : -1 - r;         // invalid rows form runs of their own
+          const int i1 = __shfl_down_sync(0xffffffffu, my_i, 1), i2 = __shfl_down_sync(0xffffffffu, my_i, 2);
+          const int i4 = __shfl_down_sync(0xffffffffu, my_i, 4), i8 = __shfl_down_sync(0xffffffffu, my_i, 8);
+          const int i16 = __shfl_down_sync(0xffffffffu, my_i, 16);
+          const int ip = __shfl_up_sync(0xffffffffu, my_i, 1);
+          SM.m1 = lane + 1 < 32 && i1 == my_i;
+          SM.m2 = lane + 2 < 32 && i2 == my_i;
+          SM.m4 = lane + 4 < 32 && i4 == my_i;
+          SM.m8 = lane + 8 < 32 && i8 == my_i;
+          SM.m16 = lane + 16 < 32 && i16 == my_i;
+          const bool run_head = (r < ne) && (lane == 0 || ip != my_i);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int f = c0 + q;                        // warp-uniform
-            if (f < F) {
-              const int hf = S.s_head[f];
-              if (hf != h) {
-                h = hf;
-                abh = sel8(ab, h);
-                abrh = sel8(abr, h);
+          for (int k = 0; k < 4; ++k) {
+            const int c = qq + 4 * k;                          // warp-uniform
+            if (c < ntail) {
+              const int ft = 128 + c;
+              const float val = (qq == 0) ? vt[4 * k] : (qq == 1) ? vt[4 * k + 1] : (qq == 2) ? vt[4 * k + 2] : vt[4 * k + 3];
+              float xq = 0.f, xk = 0.f;
+              if (r < ne) {
+                const int ht = S.s_head[ft];
+                const float wv = val + S.b2p[ft];
+                xq = s_ab[r * 8 + ht] * wv * tkj[k];
+                xk = s_abr[r * 8 + ht] * wv * tqj[k];
               }
-              const float wv = v[q] + S.b2p[f];
-              phibar = fmaf(abh * wv, qi[q] * kj[q], phibar);      // alphabar_h * s_h accumulated over h
-              const float cq = seg_reduce(abh * phi_r * wv * kj[q], SM);
-              const float ck = seg_reduce(abrh * phi_r * wv * qj[q], SM);
+              const float tq = seg_reduce(xq, SM);
+              const float tk = seg_reduce(xk, SM);
               if (run_head) {
-                atomicAdd(&gproj[(size_t)my_i * F5 + qoff + f], cq);
-                atomicAdd(&gproj[(size_t)my_i * F5 + koff + f], ck);
+                atomicAdd(&gproj[(size_t)my_i * F5 + qoff + ft], tq);
+                atomicAdd(&gproj[(size_t)my_i * F5 + koff + ft], tk);
               }
             }
           }
         }
-        __syncthreads();       // window consumed before the next gather overwrites it
       }
-      // combine the four column quarters of a row through shared memory
-      if (comp) S.s_part[r * 4 + qq] = phibar;
-      __syncthreads();
-      if (tid < ne) {
-        const float pb = S.s_part[tid * 4] + S.s_part[tid * 4 + 1] + S.s_part[tid * 4 + 2] + S.s_part[tid * 4 + 3];
-        float* dst = ebar + 2 * (size_t)(e0 + tid) + 1;
-        if (blk == 0) *dst = pb; else *dst += pb;
-      }
-      __syncthreads();
+      TC_PHASE(MODE, 10);
+      tc::fence_before_sync();
+      __syncthreads();         // s_i / s_j / s_part and the accumulators are free for the next tile
+      TC_PHASE(MODE, 11);
+      if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[MODE][15], 1ull);
     }
   }
   tc::fence_before_sync();
@@ -981,7 +1075,7 @@ static int tc_grid(int n_tiles, const TcDims& T) {
 }
 
 void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, float* alpha, int* status, cudaStream_t st) {
+                             const float* proj, float* alpha, float* wst_f, float* wst_g, int* status, cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
   int Ast = (D.H + D.nl + 3) & ~3;
@@ -991,14 +1085,15 @@ void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& 
     const TcBlockW& W = blk ? Wg : Wf;
     so3k_count_launch();
     k_edge_tc<0><<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.rev, g.geom, chi, proj,
-                                                    W.img, W.bias, W.Ws1, W.bs1, alpha, nullptr, nullptr, nullptr, status);
+                                                    W.img, W.bias, W.Ws1, W.bs1, alpha, nullptr, nullptr, nullptr,
+                                                    blk ? wst_g : wst_f, status);
   }
 }
 
 // parts: bit 0 -> q/k projection gradients + cutoff cotangent (ebar[e][1]) ; bit 1 -> radial cotangent (ebar[e][0]) + gbar
 void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, const float* alphabar, int parts, float* gproj, float* gbar, float* ebar,
-                             int* status, cudaStream_t st) {
+                             const float* proj, const float* alpha, const float* alphabar, int parts, float* gproj,
+                             float* gbar, float* ebar, int* status, cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
   int Ast = (D.H + D.nl + 3) & ~3;
@@ -1010,7 +1105,8 @@ void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& 
     if (parts & 1) {
       so3k_count_launch();
       k_edge_tc<1><<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.rev, g.geom, chi,
-                                                      proj, W.img, W.bias, W.Ws1, W.bs1, nullptr, alphabar, gproj, ebar, status);
+                                                      proj, W.img, W.bias, W.Ws1, W.bs1, const_cast<float*>(alpha), alphabar, gproj, ebar,
+                                                      nullptr, status);
     }
     if (parts & 2) {
       so3k_count_launch();
@@ -1023,6 +1119,7 @@ extern "C" void so3k_tc_phase_dump(void) {
   unsigned long long h[3][16];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_tc_phase, sizeof(h));
+  // forward names; backward part 1 reuses 0-6, then 7 = (none), 8 = wait2, 9 = transposed epilogue, 10 = tail, 11 = sync
   const char* names[13] = {"S0", "sync", "issue1", "wait1", "epi1", "sync", "issue2", "gather", "wait2", "qkstore+sync",
                            "epi2", "sync", "alpha+sync"};
   for (int k = 0; k < 3; ++k) {
@@ -1042,7 +1139,7 @@ size_t so3k_edge_tc_image_bytes(const So3kDims&) { return 0; }
 void so3k_edge_tc_build(const So3kDims&, const float*, const BlockParams&, unsigned char*, TcBlockW*, const EdgeBlockW&,
                         cudaStream_t) {}
 void so3k_launch_edge_fwd_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
-                             float*, int*, cudaStream_t) {}
+                             float*, float*, float*, int*, cudaStream_t) {}
 void so3k_launch_edge_bwd_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
-                             const float*, int, float*, float*, float*, int*, cudaStream_t) {}
+                             const float*, const float*, int, float*, float*, float*, int*, cudaStream_t) {}
 #endif

@@ -78,6 +78,9 @@ void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, co
 void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                            const float* xbar1, const float* chibar1, float* alphabar, float* gproj /* v grad */,
                            cudaStream_t st);
+void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
+                               const float* alphabar, const float* wst_f, const float* wst_g, float* gproj, float* ebar,
+                               cudaStream_t st);
 void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,
                          const float* chibar1, float* chibar /* out */, cudaStream_t st);
 void so3k_launch_forces(const So3kDims& D, const Graph& g, int P_slots, const float* rbar, float* forces /* (N,3) or null */,

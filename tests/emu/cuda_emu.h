@@ -161,6 +161,8 @@ static inline int atomicOr(int* p, int v) { return std::atomic_ref<int>(*p).fetc
 static inline int atomicExch(int* p, int v) { return std::atomic_ref<int>(*p).exchange(v); }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 // glibc already declares __expf/__cosf/__sinf (same semantics as the accurate versions): nothing to add.
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }

@@ -317,9 +317,11 @@ def test_tcgen05_tile_gemm_layouts(N, K, variant):
 
 
 # ---- tensor-core (tcgen05, split-bf16) filter GEMMs ------------------------------------------------------------
+@pytest.mark.parametrize('keep', [0, 2])
 @pytest.mark.parametrize('F,L,degrees,H', [(132, 3, (1, 2, 3), 4), (36, 2, (1, 2, 3), 4), (32, 2, (1, 2, 2, 3), 4)])
-def test_tensor_mode_matches_oracle(ethanol, solid, F, L, degrees, H):
-    from mlff_b200.capi import FLAG_TENSOR
+def test_tensor_mode_matches_oracle(ethanol, solid, F, L, degrees, H, keep):
+    from mlff_b200.capi import FLAG_TENSOR as _FT
+    FLAG_TENSOR = _FT | keep          # keep = FLAG_KEEP_FILTERS: the backward streams the forward's filters
     cfg = o.OracleConfig(F=F, n_layers=L, degrees=degrees, n_heads=H)
     p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
     eng = make(cfg, p, flags=FLAG_TENSOR)
@@ -346,7 +348,7 @@ def test_tensor_mode_matches_oracle(ethanol, solid, F, L, degrees, H):
 
 # ---- domain decomposition (virtual ranks on one GPU; the multi-process NCCL exchange is exercised by bench.py --gpus N
 # and, on the CPU, by tests/test_dd.py over gloo) ----------------------------------------------------------------------
-@pytest.mark.parametrize('flags', [0, 1])
+@pytest.mark.parametrize('flags', [0, 1, 3])
 def test_domain_decomposition_virtual_ranks(solid, flags):
     from mlff_b200 import dist as dd
     from mlff_b200 import _lib
