@@ -25,6 +25,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // x1 = x + sum_e alpha_fb[e][h(f)] v[col e][f] ;  chi1 = chi + sum_e alpha_gb[e][l(m)] Y_m(u_e)
+template <int TN>                               // TN = ceil(F / 32): feature slots per lane
 __global__ void __launch_bounds__(WPB * 32)
 k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
             const float4* __restrict__ geom, const float* __restrict__ x, const float* __restrict__ chi,
@@ -37,10 +38,10 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   const int F = D.F, M = D.M, H = D.H;
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
-  float accx[TMAX];
-  int hsel[TMAX];
+  float accx[TN];
+  int hsel[TN];
 #pragma unroll
-  for (int t = 0; t < TMAX; ++t) {
+  for (int t = 0; t < TN; ++t) {
     accx[t] = 0.f;
     int f = lane + 32 * t;
     hsel[t] = (f < F) ? f / D.dh : 0;
@@ -63,13 +64,27 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
     }
     s_j[w][lane] = j;
     __syncwarp();
-    for (int q = 0; q < cnt; ++q) {
-      const float* vj = proj + (size_t)s_j[w][q] * F5 + 4 * (size_t)F;
-      const float* aq = &s_a[w][q * Ast];
+    // four sender rows in flight per iteration (the gathers are latency-bound otherwise)
+    for (int q = 0; q < cnt; q += 4) {
+      float vv[4][TN];
+      float am[4];
+      int qk[4];
 #pragma unroll
-      for (int t = 0; t < TMAX; ++t) {
-        int f = lane + 32 * t;
-        if (f < F) accx[t] = fmaf(aq[hsel[t]], vj[f], accx[t]);
+      for (int k = 0; k < 4; ++k) {
+        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+        am[k] = (q + k < cnt) ? 1.f : 0.f;
+        const float* vj = proj + (size_t)s_j[w][qk[k]] * F5 + 4 * (size_t)F;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          vv[k][t] = ((t + 1 < TN) || f < F) ? vj[f] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* aq = &s_a[w][qk[k] * Ast];
+#pragma unroll
+        for (int t = 0; t < TN; ++t) accx[t] = fmaf(am[k] * aq[hsel[t]], vv[k][t], accx[t]);
       }
     }
     __syncwarp();
@@ -81,7 +96,7 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
   if (rowok) {
 #pragma unroll
-    for (int t = 0; t < TMAX; ++t) {
+    for (int t = 0; t < TN; ++t) {
       int f = lane + 32 * t;
       if (f < F) x1[(size_t)i * F + f] = x[(size_t)i * F + f] + accx[t];
     }
@@ -90,11 +105,15 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 
 // alphabar_fb[e][h] = sum_{f in h} xbar1[i][f] v[j][f] ; alphabar_gb[e][l] = sum_{m in l} chibar1[i][m] Y_m(u_e)
 // gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
+// EP = 16 / HP edges per iteration: their EP * HP per-lane head partials are reduced over the warp with ONE halving
+// butterfly (16 shuffles for all of them instead of 5 per value).
+template <int TN, int HP>                       // TN = ceil(F / 32) ; HP = heads padded to 4 or 8
 __global__ void __launch_bounds__(WPB * 32)
 k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
             const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
             const float* __restrict__ alpha, const float* __restrict__ xbar1, const float* __restrict__ chibar1,
             float* __restrict__ alphabar, float* __restrict__ gproj) {
+  constexpr int EP = 16 / HP;
   __shared__ float s_a[WPB][32 * AMAX];     // alpha_fb of the reverse edges
   __shared__ float s_o[WPB][32 * AMAX];     // alphabar staging (coalesced store)
   __shared__ int s_j[WPB][32];
@@ -104,14 +123,14 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
   const size_t F5 = 5 * (size_t)F;
-  float xb[TMAX], accv[TMAX];
-  int hsel[TMAX];
+  float xb[TN], accv[TN];
+  int hsel[TN];
 #pragma unroll
-  for (int t = 0; t < TMAX; ++t) {
+  for (int t = 0; t < TN; ++t) {
     int f = lane + 32 * t;
     xb[t] = (rowok && f < F) ? xbar1[(size_t)i * F + f] : 0.f;
     accv[t] = 0.f;
-    hsel[t] = (f < F) ? f / D.dh : -1;
+    hsel[t] = (f < F) ? f / D.dh : 0;       // xb = 0 beyond F: those slots add nothing
   }
   float cb[SO3K_MAXM];
   for (int m = 0; m < M; ++m) cb[m] = rowok ? chibar1[(size_t)i * M + m] : 0.f;
@@ -135,30 +154,56 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
     }
     s_j[w][lane] = j;
     __syncwarp();
-    for (int q = 0; q < cnt; ++q) {
-      const int jq = s_j[w][q];
-      const float* vj = proj + (size_t)jq * F5 + 4 * (size_t)F;
-      const float* xj = xbar1 + (size_t)jq * F;
-      const float* aq = &s_a[w][q * Ast];
-      float ph[8];
+    for (int q = 0; q < cnt; q += EP) {
+      float vv[EP][TN], xx[EP][TN];
+      int qk[EP];
+      float am[EP];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) ph[h] = 0.f;
+      for (int k = 0; k < EP; ++k) {
+        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+        am[k] = (q + k < cnt) ? 1.f : 0.f;
+        const int jq = s_j[w][qk[k]];
+        const float* vj = proj + (size_t)jq * F5 + 4 * (size_t)F;
+        const float* xj = xbar1 + (size_t)jq * F;
 #pragma unroll
-      for (int t = 0; t < TMAX; ++t) {
-        int f = lane + 32 * t;
-        if (f < F) {
-          float p = xb[t] * vj[f];
-#pragma unroll
-          for (int h = 0; h < 8; ++h) ph[h] += (hsel[t] == h) ? p : 0.f;
-          accv[t] = fmaf(aq[hsel[t]], xj[f], accv[t]);
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          const bool ok = (t + 1 < TN) || f < F;
+          vv[k][t] = ok ? vj[f] : 0.f;
+          xx[k][t] = ok ? xj[f] : 0.f;
         }
       }
+      float val[16];                           // [edge k][head h]: this lane's partial of alphabar_fb
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        if (h < H) {                      // H is block-uniform: every lane executes the same shuffles
-          float s = warp_sum(ph[h]);
-          if (lane == 0) s_o[w][q * Ast + h] = s;
+      for (int u = 0; u < 16; ++u) val[u] = 0.f;
+#pragma unroll
+      for (int k = 0; k < EP; ++k) {
+        const float* aq = &s_a[w][qk[k] * Ast];
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const float p = xb[t] * vv[k][t];
+#pragma unroll
+          for (int h = 0; h < HP; ++h) val[k * HP + h] += (hsel[t] == h) ? p : 0.f;
+          accv[t] = fmaf(am[k] * aq[hsel[t]], xx[k][t], accv[t]);
         }
+      }
+      // halving butterfly: after the stages with offsets 16, 8, 4, 2 a lane holds value index (lane >> 1); the last
+      // stage completes the sum over the remaining lane bit
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        const int off = 16 >> st, half = 8 >> st;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int u = 0; u < half; ++u) {
+          const float send = up ? val[u] : val[u + half];
+          const float keep = up ? val[u + half] : val[u];
+          val[u] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+      {
+        const int idx = lane >> 1, k = idx / HP, h = idx % HP;
+        if ((lane & 1) == 0 && h < H && q + k < cnt) s_o[w][(q + k) * Ast + h] = val[0];
       }
     }
     __syncwarp();
@@ -167,7 +212,7 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
   if (rowok) {
 #pragma unroll
-    for (int t = 0; t < TMAX; ++t) {
+    for (int t = 0; t < TN; ++t) {
       int f = lane + 32 * t;
       if (f < F) gproj[(size_t)i * F5 + 4 * (size_t)F + f] = accv[t];
     }
@@ -342,15 +387,37 @@ k_forces(int N, const int* __restrict__ rowptr, const int* __restrict__ rev, con
 void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
                            const float* alpha, float* x1, float* chi1, cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
-  SO3K_LAUNCH(k_aggregate, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col, g.geom, x, chi,
-              proj, alpha, x1, chi1);
+#define SO3K_AGG_CASE(TN_)                                                                                             \
+  case TN_:                                                                                                            \
+    SO3K_LAUNCH(k_aggregate<TN_>, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,      \
+                g.geom, x, chi, proj, alpha, x1, chi1);                                                                \
+    break;
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_AGG_CASE(1) SO3K_AGG_CASE(2) SO3K_AGG_CASE(3) SO3K_AGG_CASE(4) SO3K_AGG_CASE(5) SO3K_AGG_CASE(6)
+    SO3K_AGG_CASE(7) SO3K_AGG_CASE(8)
+    default: break;
+  }
+#undef SO3K_AGG_CASE
 }
 
 void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                            const float* xbar1, const float* chibar1, float* alphabar, float* gproj, cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
-  SO3K_LAUNCH(k_alpha_bwd, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col, g.rev, g.geom,
-              proj, alpha, xbar1, chibar1, alphabar, gproj);
+#define SO3K_AB_CASE(TN_)                                                                                              \
+  case TN_:                                                                                                            \
+    if (D.H <= 4)                                                                                                      \
+      SO3K_LAUNCH((k_alpha_bwd<TN_, 4>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
+                  g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
+    else                                                                                                               \
+      SO3K_LAUNCH((k_alpha_bwd<TN_, 8>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
+                  g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
+    break;
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_AB_CASE(1) SO3K_AB_CASE(2) SO3K_AB_CASE(3) SO3K_AB_CASE(4) SO3K_AB_CASE(5) SO3K_AB_CASE(6) SO3K_AB_CASE(7)
+    SO3K_AB_CASE(8)
+    default: break;
+  }
+#undef SO3K_AB_CASE
 }
 
 void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
