@@ -103,6 +103,147 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
 }
 
+// Tensor-core path: attention coefficients from the pair-indexed filters, fused with both aggregations.
+//   alpha_fb[e][h] = phi_e / sqrt(F/H)  sum_{f in h} w_fb[pid e][f] q_fb[i][f] k_fb[j][f]       (so3krates_layer.py:590-606)
+//   alpha_gb[e][l] = phi_e / sqrt(F/nl) sum_{f in l} w_gb[pid e][f] q_gb[i][f] k_gb[j][f]       (so3krates_layer.py:545-562)
+//   x1 = x + sum_e alpha_fb[e][h(f)] v[j][f] ;  chi1 = chi + sum_e alpha_gb[e][l(m)] Y_m(u_e)
+// EP edges per iteration; their EP * 2 * HS per-lane head partials (HS slots per block) are reduced over the warp by one
+// halving butterfly (16 shuffles), as in k_alpha_bwd.
+template <int TN, int HS>                       // TN = ceil(F / 32) ; HS = 4 (H, nl <= 4: two edges per pass) or 8
+__global__ void __launch_bounds__(WPB * 32)
+k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ x,
+                  const float* __restrict__ chi, const float* __restrict__ proj, const float* __restrict__ wst_f,
+                  const float* __restrict__ wst_g, float* __restrict__ alpha, float* __restrict__ x1,
+                  float* __restrict__ chi1) {
+  constexpr int EP = 8 / HS;
+  __shared__ float s_a[WPB][32 * AMAX];
+  __shared__ float s_ph[WPB][32];
+  __shared__ int s_j[WPB][32];
+  __shared__ int s_p[WPB][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const int F = D.F, M = D.M, H = D.H, nl = D.nl;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  const size_t F5 = 5 * (size_t)F;
+  const float inv_f = 1.0f / sqrtf((float)(F / H)), inv_g = 1.0f / sqrtf((float)(F / nl));
+  float accx[TN], qf[TN], qg[TN];
+  int hf[TN], hg[TN];
+#pragma unroll
+  for (int t = 0; t < TN; ++t) {
+    accx[t] = 0.f;
+    const int f = lane + 32 * t;
+    const bool ok = rowok && f < F;
+    qf[t] = ok ? proj[(size_t)i * F5 + f] : 0.f;           // zero beyond F: those slots add nothing
+    qg[t] = ok ? proj[(size_t)i * F5 + F + f] : 0.f;
+    hf[t] = (f < F) ? f / (F / H) : 0;
+    hg[t] = (f < F) ? f / (F / nl) : 0;
+  }
+  float cacc[SO3K_MAXM];
+  for (int m = 0; m < M; ++m) cacc[m] = 0.f;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const int cnt = (end - e0) < 32 ? (end - e0) : 32;
+    float4 g = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (e < end) {
+      g = geom[e];
+      s_j[w][lane] = col[e];
+      s_p[w][lane] = pid[e];
+      s_ph[w][lane] = so3k_cutoff(g.w, D.r_cut);
+      for (int a = H + nl; a < Ast; ++a) s_a[w][lane * Ast + a] = 0.f;
+    }
+    __syncwarp();
+    for (int q = 0; q < cnt; q += EP) {
+      float wf[EP][TN], wg[EP][TN], kf[EP][TN], kg[EP][TN], vv[EP][TN];
+      int qk[EP];
+#pragma unroll
+      for (int k = 0; k < EP; ++k) {
+        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+        const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
+        const float* pwf = wst_f + (size_t)s_p[w][qk[k]] * F;
+        const float* pwg = wst_g + (size_t)s_p[w][qk[k]] * F;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          const bool ok = (t + 1 < TN) || f < F;
+          wf[k][t] = ok ? pwf[f] : 0.f;
+          wg[k][t] = ok ? pwg[f] : 0.f;
+          kf[k][t] = ok ? pj[2 * F + f] : 0.f;
+          kg[k][t] = ok ? pj[3 * F + f] : 0.f;
+          vv[k][t] = ok ? pj[4 * F + f] : 0.f;
+        }
+      }
+      float val[16];                           // [edge k][block][head slot]
+#pragma unroll
+      for (int u = 0; u < 16; ++u) val[u] = 0.f;
+#pragma unroll
+      for (int k = 0; k < EP; ++k) {
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const float pf = wf[k][t] * qf[t] * kf[k][t];
+          const float pg = wg[k][t] * qg[t] * kg[k][t];
+#pragma unroll
+          for (int h = 0; h < HS; ++h) {
+            val[k * 2 * HS + h] += (hf[t] == h) ? pf : 0.f;
+            val[k * 2 * HS + HS + h] += (hg[t] == h) ? pg : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {         // halving butterfly: afterwards a lane holds value index (lane >> 1)
+        const int off = 16 >> st, half = 8 >> st;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int u = 0; u < half; ++u) {
+          const float send = up ? val[u] : val[u + half];
+          const float keep = up ? val[u + half] : val[u];
+          val[u] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+      {
+        const int idx = lane >> 1, k = idx / (2 * HS), a = idx % (2 * HS);
+        if ((lane & 1) == 0 && q + k < cnt) {
+          const float ph = s_ph[w][q + k];
+          if (a < HS) {
+            if (a < H) s_a[w][(q + k) * Ast + a] = val[0] * inv_f * ph;
+          } else if (a - HS < nl) {
+            s_a[w][(q + k) * Ast + H + a - HS] = val[0] * inv_g * ph;
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < EP; ++k) {
+        const float m = (q + k < cnt) ? 1.f : 0.f;
+        const float* aq = &s_a[w][qk[k] * Ast];
+#pragma unroll
+        for (int t = 0; t < TN; ++t) accx[t] = fmaf(m * aq[hf[t]], vv[k][t], accx[t]);
+      }
+    }
+    __syncwarp();
+    if (e < end) {                             // SPHC part, lane-per-edge
+      float y[SO3K_MAXM];
+      so3k_sph_all(D, g.x, g.y, g.z, y);
+      for (int m = 0; m < M; ++m) cacc[m] = fmaf(s_a[w][lane * Ast + H + D.m_seg[m]], y[m], cacc[m]);
+    }
+    for (int t = lane; t < cnt * Ast; t += 32) alpha[(size_t)e0 * Ast + t] = s_a[w][t];
+    __syncwarp();
+  }
+  for (int m = 0; m < M; ++m) {
+    float s = warp_sum(cacc[m]);
+    if (rowok && lane == 0) chi1[(size_t)i * M + m] = chi[(size_t)i * M + m] + s;
+  }
+  if (rowok) {
+#pragma unroll
+    for (int t = 0; t < TN; ++t) {
+      int f = lane + 32 * t;
+      if (f < F) x1[(size_t)i * F + f] = x[(size_t)i * F + f] + accx[t];
+    }
+  }
+}
+
 // alphabar_fb[e][h] = sum_{f in h} xbar1[i][f] v[j][f] ; alphabar_gb[e][l] = sum_{m in l} chibar1[i][m] Y_m(u_e)
 // gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
 // EP = 16 / HP edges per iteration: their EP * HP per-lane head partials are reduced over the warp with ONE halving
@@ -219,7 +360,8 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
 }
 
-// q/k projection gradients from KEPT filters (SO3K_FLAG_KEEP_FILTERS: the forward stored w[e][f] of both blocks):
+// q/k projection gradients from the pair-indexed filters w[pid e][f] of both blocks (kept from the forward with
+// SO3K_FLAG_KEEP_FILTERS, else recomputed by k_filter_tc just before):
 //   qbar_i[f] = sum_{e in row i} alphabar[e][h(f)]     phi_e / sqrt(d_h) w_e[f] k_j[f]
 //   kbar_i[f] = sum_{e in row i} alphabar[rev e][h(f)] phi_e / sqrt(d_h) w_e[f] q_j[f]     (w, phi are symmetric in e <-> rev e)
 // and the cutoff cotangent  ebar[e][1] = sum_a alphabar[e][a] alpha[e][a] / phi_e.
@@ -227,12 +369,13 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 template <int TN>                               // TN = ceil(F / 32): feature slots per lane
 __global__ void __launch_bounds__(WPB * 32)
 k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
-                const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
+                const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ proj,
                 const float* __restrict__ alpha, const float* __restrict__ alphabar, const float* __restrict__ wst_f,
                 const float* __restrict__ wst_g, float* __restrict__ gproj, float* __restrict__ ebar) {
   __shared__ float s_ab[WPB][32 * AMAX];    // alphabar[e]     * phi / sqrt(d_h)
   __shared__ float s_abr[WPB][32 * AMAX];   // alphabar[rev e] * phi / sqrt(d_h)
   __shared__ int s_j[WPB][32];
+  __shared__ int s_p[WPB][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * WPB + w;
   const int F = D.F, H = D.H, nl = D.nl;
@@ -252,9 +395,10 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     const int cnt = (end - e0) < 32 ? (end - e0) : 32;
-    int j = 0;
+    int j = 0, pe = 0;
     if (e < end) {
       j = col[e];
+      pe = pid[e];
       const int re = rev[e];
       const float ph = so3k_cutoff(geom[e].w, D.r_cut);
       float pb = 0.f;
@@ -268,6 +412,7 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       ebar[2 * (size_t)e + 1] = ph > 1e-30f ? pb / ph : 0.f;
     }
     s_j[w][lane] = j;
+    s_p[w][lane] = pe;
     __syncwarp();
     // two edges per iteration: 12 * TN independent loads in flight per lane (the kernel is latency-bound otherwise)
     for (int q = 0; q < cnt; q += 2) {
@@ -275,20 +420,20 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       const int q1 = two ? q + 1 : q;
       const float* pj0 = proj + (size_t)s_j[w][q] * F5;
       const float* pj1 = proj + (size_t)s_j[w][q1] * F5;
-      const float* wf0 = wst_f + (size_t)(e0 + q) * F;
-      const float* wg0 = wst_g + (size_t)(e0 + q) * F;
-      const float* wf1 = wst_f + (size_t)(e0 + q1) * F;
-      const float* wg1 = wst_g + (size_t)(e0 + q1) * F;
+      const float* wf0 = wst_f + (size_t)s_p[w][q] * F;
+      const float* wg0 = wst_g + (size_t)s_p[w][q] * F;
+      const float* wf1 = wst_f + (size_t)s_p[w][q1] * F;
+      const float* wg1 = wst_g + (size_t)s_p[w][q1] * F;
       float vf0[TN], vg0[TN], kf0[TN], kg0[TN], qf0[TN], qg0[TN];
       float vf1[TN], vg1[TN], kf1[TN], kg1[TN], qf1[TN], qg1[TN];
 #pragma unroll
       for (int t = 0; t < TN; ++t) {
         const int f = lane + 32 * t;
         const bool ok = (t + 1 < TN) || f < F;
-        vf0[t] = ok ? __ldcs(wf0 + f) : 0.f;  vg0[t] = ok ? __ldcs(wg0 + f) : 0.f;
+        vf0[t] = ok ? wf0[f] : 0.f;           vg0[t] = ok ? wg0[f] : 0.f;
         kf0[t] = ok ? pj0[2 * F + f] : 0.f;   kg0[t] = ok ? pj0[3 * F + f] : 0.f;
         qf0[t] = ok ? pj0[f] : 0.f;           qg0[t] = ok ? pj0[F + f] : 0.f;
-        vf1[t] = ok ? __ldcs(wf1 + f) : 0.f;  vg1[t] = ok ? __ldcs(wg1 + f) : 0.f;
+        vf1[t] = ok ? wf1[f] : 0.f;           vg1[t] = ok ? wg1[f] : 0.f;
         kf1[t] = ok ? pj1[2 * F + f] : 0.f;   kg1[t] = ok ? pj1[3 * F + f] : 0.f;
         qf1[t] = ok ? pj1[f] : 0.f;           qg1[t] = ok ? pj1[F + f] : 0.f;
       }
@@ -400,6 +545,27 @@ void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, co
 #undef SO3K_AGG_CASE
 }
 
+void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
+                                 const float* wst_f, const float* wst_g, float* alpha, float* x1, float* chi1,
+                                 cudaStream_t st) {
+  int Ast = (D.H + D.nl + 3) & ~3;
+#define SO3K_AA_CASE(TN_)                                                                                              \
+  case TN_:                                                                                                            \
+    if (D.H <= 4 && D.nl <= 4)                                                                                         \
+      SO3K_LAUNCH((k_alpha_aggregate<TN_, 4>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, \
+                  g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                                  \
+    else                                                                                                               \
+      SO3K_LAUNCH((k_alpha_aggregate<TN_, 8>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, \
+                  g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                                  \
+    break;
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_AA_CASE(1) SO3K_AA_CASE(2) SO3K_AA_CASE(3) SO3K_AA_CASE(4) SO3K_AA_CASE(5) SO3K_AA_CASE(6) SO3K_AA_CASE(7)
+    SO3K_AA_CASE(8)
+    default: break;
+  }
+#undef SO3K_AA_CASE
+}
+
 void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                            const float* xbar1, const float* chibar1, float* alphabar, float* gproj, cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
@@ -427,7 +593,7 @@ void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* p
 #define SO3K_QK_CASE(TN_)                                                                                              \
   case TN_:                                                                                                            \
     SO3K_LAUNCH(k_qk_bwd_stream<TN_>, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,  \
-                g.rev, g.geom, proj, alpha, alphabar, wst_f, wst_g, gproj, ebar);                                      \
+                g.rev, g.pid, g.geom, proj, alpha, alphabar, wst_f, wst_g, gproj, ebar);                                      \
     break;
   switch (so3k_cdiv(D.F, 32)) {
     SO3K_QK_CASE(1) SO3K_QK_CASE(2) SO3K_QK_CASE(3) SO3K_QK_CASE(4) SO3K_QK_CASE(5) SO3K_QK_CASE(6) SO3K_QK_CASE(7)

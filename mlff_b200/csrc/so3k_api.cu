@@ -42,9 +42,8 @@ struct HandleImpl : so3k_handle {
   unsigned char* tc_images = nullptr;
   std::vector<TcBlockW> tf, tg;      // per layer (tensor-core mode)
   bool use_tc = false;
-  int tc_parts = 3;                  // SO3K_TC_PARTS env: debugging aid to mix tensor-core / CUDA-core backward pieces
-  bool tc_fwd = true;
-  bool keep_w = false;               // SO3K_FLAG_KEEP_FILTERS (only with the tensor-core forward)
+  bool tc_b2 = true;                 // SO3K_TC_B2=0 (env): debugging aid, radial / l0 cotangents on the fp32 CUDA-core kernel
+  bool keep_w = false;               // SO3K_FLAG_KEEP_FILTERS
   Profiler prof;
 };
 
@@ -180,13 +179,17 @@ struct Workspace {
   float *proj, *gproj;
   float *alpha;            // per layer
   float *alphabar, *gbar, *rbar, *ebar;
-  float *wst;              // kept filters: [layer][block][edge][F] (SO3K_FLAG_KEEP_FILTERS), else nullptr
+  float *wst;              // tensor mode: filters [layer or 1][block][pair][F] (all layers with SO3K_FLAG_KEEP_FILTERS)
+  int wst_layers;
   float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
   float *e_atom;
   size_t bytes;
 };
 
-Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, bool keep_w) {
+static inline int wst_layers_of(const HandleImpl* h) { return h->use_tc ? (h->keep_w ? h->dims.L : 1) : 0; }
+
+// wst_layers: 0 (fp32 CUDA-core mode), 1 (tensor mode, filters recomputed in the backward) or L (kept)
+Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int wst_layers) {
   Workspace w;
   char* p = (char*)base;
   auto take = [&](size_t bytes) {
@@ -220,7 +223,9 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, bool keep_w) {
   w.gbar = (float*)take(sizeof(float) * Pe * Gst);
   w.rbar = (float*)take(sizeof(float) * Pe * 3);
   w.ebar = (float*)take(sizeof(float) * Pe * 2);
-  w.wst = keep_w ? (float*)take(sizeof(float) * L * 2 * Pe * F) : nullptr;
+  w.g.pid = (int*)take(sizeof(int) * Pe);
+  w.wst_layers = wst_layers;
+  w.wst = wst_layers ? (float*)take(sizeof(float) * wst_layers * 2 * (size_t)so3k_pair_capacity(Pt) * F) : nullptr;
   w.xbar_a = (float*)take(sizeof(float) * N * F);
   w.xbar_b = (float*)take(sizeof(float) * N * F);
   w.chibar_a = (float*)take(sizeof(float) * N * M);
@@ -250,15 +255,23 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
   float* ct = w.chi + (size_t)t * N * M;
   float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
   { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
-  {
-    PROF(CAT_EDGE_FWD);
-    float* wst_t = w.wst ? w.wst + (size_t)t * 2 * Pe * F : nullptr;
-    if (h->use_tc && h->tc_fwd)
-      so3k_launch_edge_fwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, wst_t, wst_t ? wst_t + Pe * F : nullptr,
-                              dev_status, st);
-    else so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st);
+  if (h->use_tc) {
+    // filters of both blocks per undirected pair on the tensor cores, then one streaming pass: attention coefficients
+    // + both aggregations
+    const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
+    float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
+    {
+      PROF(CAT_EDGE_FWD);
+      so3k_launch_filter_tc(D, w.g, h->tf[t], ct, wst_t, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tg[t], ct, wst_t + Pc * F, dev_status, st);
+    }
+    PROF(CAT_AGGREGATE);
+    so3k_launch_alpha_aggregate(D, w.g, xt, ct, w.proj, wst_t, wst_t + Pc * F, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+  } else {
+    { PROF(CAT_EDGE_FWD); so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st); }
+    PROF(CAT_AGGREGATE);
+    so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
   }
-  { PROF(CAT_AGGREGATE); so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st); }
   PROF(CAT_INTERACTION);
   so3k_launch_interaction(D, (int)N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + N * F, ct + N * M,
                           w.bcoef + (size_t)t * N * nl, st);
@@ -300,18 +313,21 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
   { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, w.xbar_b, w.chibar_b, w.alphabar, w.gproj, st); }
   {
     PROF(CAT_EDGE_BWD);
-    // tc_parts: which backward pieces run on the tensor cores (bit 0: q/k gradients + cutoff cotangent,
-    // bit 1: radial + l0-contraction cotangents); the rest runs the fp32 CUDA-core kernel
-    int tcp = h->use_tc ? h->tc_parts : 0;
-    const int simt = 3 & ~tcp;         // pieces left to the fp32 CUDA-core kernel
-    if (w.wst && (tcp & 1)) {          // kept filters: the q/k gradients are a streaming pass, no filter recomputation
-      const float* wst_t = w.wst + (size_t)t * 2 * Pe * F;
-      so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, wst_t + Pe * F, w.gproj, w.ebar, st);
-      tcp &= ~1;
+    if (h->use_tc) {
+      const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
+      float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
+      if (w.wst_layers == 1) {         // filters not kept: recompute this layer's
+        so3k_launch_filter_tc(D, w.g, h->tf[t], ct, wst_t, dev_status, st);
+        so3k_launch_filter_tc(D, w.g, h->tg[t], ct, wst_t + Pc * F, dev_status, st);
+      }
+      // q/k projection gradients + cutoff cotangent: one streaming pass over the filters
+      so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, wst_t + Pc * F, w.gproj, w.ebar, st);
+      // radial + l0-contraction cotangents
+      if (h->tc_b2) so3k_launch_edge_bwd2_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, w.alphabar, w.gbar, w.ebar, dev_status, st);
+      else so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 2, w.gproj, w.gbar, w.ebar, st);
+    } else {
+      so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
     }
-    if (tcp) so3k_launch_edge_bwd_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, alpha_t, w.alphabar, tcp, w.gproj, w.gbar, w.ebar,
-                                     dev_status, st);
-    if (simt) so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, simt, w.gproj, w.gbar, w.ebar, st);
     so3k_launch_edge_finish(D, w.g, alpha_t, w.chibar_b, w.ebar, w.rbar, st);
   }
   if (t > 0) {
@@ -330,7 +346,7 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
   const So3kDims& D = h->dims;
   const int N = B * n, Pt = B * P;
   if (workspace_bytes < so3k_workspace_bytes(h, N, Pt)) return SO3K_ERR_WORKSPACE;
-  Workspace w = carve_ws(D, N, Pt, workspace, h->keep_w && h->tc_fwd);
+  Workspace w = carve_ws(D, N, Pt, workspace, wst_layers_of(h));
   stage_begin(h, w, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, disp, mask, dev_status, st);
   for (int t = 0; t < D.L; ++t) stage_layer_fwd(h, w, t, dev_status, st);
   float* e_atom = e_atom_out ? e_atom_out : w.e_atom;
@@ -364,11 +380,7 @@ int so3k_create(const so3k_config* cfg, so3k_handle** out) {
   h->dims = D;
   h->use_tc = (cfg->flags & SO3K_FLAG_TENSOR) != 0;
   h->keep_w = h->use_tc && (cfg->flags & SO3K_FLAG_KEEP_FILTERS) != 0;
-  if (const char* e = getenv("SO3K_TC_PARTS")) {       // bit 0/1: backward pieces, bit 2: forward
-    int v = atoi(e);
-    h->tc_parts = v & 3;
-    h->tc_fwd = (v & 4) != 0;
-  }
+  if (const char* e = getenv("SO3K_TC_B2")) h->tc_b2 = atoi(e) != 0;
   make_layout(D, &h->layout);
   *out = h;
   return SO3K_OK;
@@ -437,7 +449,7 @@ int so3k_load_params(so3k_handle* hh, const float* blob_dev, size_t n_floats, vo
 size_t so3k_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total) {
   if (!h || n_atoms_total <= 0 || n_edge_slots_total < 0) return 0;
   const HandleImpl* hi = static_cast<const HandleImpl*>(h);
-  Workspace w = carve_ws(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, nullptr, hi->keep_w && hi->tc_fwd);
+  Workspace w = carve_ws(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, nullptr, wst_layers_of(hi));
   return w.bytes + 256;
 }
 
@@ -493,7 +505,7 @@ int so3k_dd_begin(so3k_handle* hh, int32_t N, int32_t P, const float* R, const i
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (!h->have_params) return SO3K_ERR_NOPARAMS;
   if (workspace_bytes < so3k_workspace_bytes(h, N, P)) return SO3K_ERR_WORKSPACE;
-  Workspace w = carve_ws(h->dims, N, P, workspace, h->keep_w && h->tc_fwd);
+  Workspace w = carve_ws(h->dims, N, P, workspace, wst_layers_of(h));
   stage_begin(h, w, 1, N, P, R, z, idx_i, idx_j, cell, cell_offset, nullptr, nullptr, dev_status, (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
 }
@@ -505,7 +517,7 @@ int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t 
   if (!hh || !workspace || N <= 0) return SO3K_ERR_ARG;
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (t < 0 || t >= h->dims.L) return SO3K_ERR_ARG;
-  Workspace w = carve_ws(h->dims, N, P, workspace, h->keep_w && h->tc_fwd);
+  Workspace w = carve_ws(h->dims, N, P, workspace, wst_layers_of(h));
   cudaStream_t st = (cudaStream_t)stream;
   switch (stage) {
     case 0: stage_layer_fwd(h, w, t, dev_status, st); break;
@@ -524,7 +536,7 @@ int so3k_dd_buffer(const so3k_handle* hh, int32_t which, int32_t t, int32_t N, i
   const So3kDims& D = hh->dims;
   if (t < 0 || t > D.L) return SO3K_ERR_ARG;
   const HandleImpl* h = static_cast<const HandleImpl*>(hh);
-  Workspace w = carve_ws(D, N, P, nullptr, h->keep_w && h->tc_fwd);
+  Workspace w = carve_ws(D, N, P, nullptr, wst_layers_of(h));
   const char* base = nullptr;
   const char* p = nullptr;
   switch (which) {

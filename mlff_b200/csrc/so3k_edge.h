@@ -37,8 +37,10 @@ bool so3k_edge_tc_supported(const So3kDims& D);
 size_t so3k_edge_tc_image_bytes(const So3kDims& D);   // per block
 void so3k_edge_tc_build(const So3kDims& D, const float* params, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
                         const EdgeBlockW& simt, cudaStream_t st);
-void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, float* alpha, float* wst_f, float* wst_g, int* status, cudaStream_t st);
-void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, const float* alpha, const float* alphabar, int parts, float* gproj,
-                             float* gbar, float* ebar, int* status, cudaStream_t st);
+// filter w[pair][F] of one block for every canonical (undirected) pair of the list
+void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* chi, float* wst, int* status,
+                           cudaStream_t st);
+// radial cotangent ebar[e][0] and l0-contraction cotangent gbar of both blocks (written on the canonical edge of a pair)
+void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
+                              const float* proj, const float* alphabar, float* gbar, float* ebar, int* status,
+                              cudaStream_t st);

@@ -247,7 +247,7 @@ __device__ __forceinline__ TileMeta tc_prefetch_meta1(int r, int qq, int e0, int
   if (comp && e < nv) {
     if (canon) {                 // rows are canonical edges: one per undirected pair
       e = canon[e];
-      m.re = rev[e];
+      if (rev) m.re = rev[e];
     } else if (rev && qq == 3) {
       m.re = rev[e];             // backward part 1: quarter 3 stages alphabar of the reverse edge
     }
@@ -381,89 +381,26 @@ __device__ __forceinline__ void tc_epilogue1(const So3kDims& D, const TcDims& T,
   }
 }
 
-// segmented (by receiver run) reduction over the 32 rows of a warp; run heads end up with the run total
-struct SegMask { bool m1, m2, m4, m8, m16; };
-__device__ __forceinline__ float seg_reduce(float v, const SegMask& M) {
-  float t;
-  t = __shfl_down_sync(0xffffffffu, v, 1);  if (M.m1) v += t;
-  t = __shfl_down_sync(0xffffffffu, v, 2);  if (M.m2) v += t;
-  t = __shfl_down_sync(0xffffffffu, v, 4);  if (M.m4) v += t;
-  t = __shfl_down_sync(0xffffffffu, v, 8);  if (M.m8) v += t;
-  t = __shfl_down_sync(0xffffffffu, v, 16); if (M.m16) v += t;
-  return v;
-}
-__device__ __forceinline__ float sel8(const float* a, int h) {
-  float v = a[0];
-#pragma unroll
-  for (int x = 1; x < 8; ++x) v = (h == x) ? a[x] : v;
-  return v;
-}
-
-// backward part 1 helpers: rows [rb, rb+8) of the transposed epilogue for the feature this thread owns
-__device__ __forceinline__ void b1_gather8(float* kj, float* qj, const float* __restrict__ pk, const float* __restrict__ pq,
-                                           const int* s_j, size_t F5, int rb, int rend) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    kj[u] = 0.f;
-    qj[u] = 0.f;
-    if (rb + u < rend) {
-      const size_t jo = (size_t)s_j[rb + u] * F5;
-      kj[u] = __ldg(pk + jo);
-      qj[u] = __ldg(pq + jo);
-    }
-  }
-}
-__device__ __forceinline__ void b1_accum8(const float* v, const float* kj, const float* qj, const float* s_ab,
-                                          const float* s_abr, const int* s_i, int rb, int rend, int hf, float b2, bool fok,
-                                          float* __restrict__ gq, float* __restrict__ gk, size_t F5, int& icur, float& cq,
-                                          float& ck) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int rr = rb + u;
-    if (rr < rend) {                               // warp-uniform
-      const int ir = s_i[rr];
-      if (ir != icur) {                            // receiver run ends: one atomic per (run, feature)
-        if (fok) {
-          atomicAdd(gq + (size_t)icur * F5, cq);
-          atomicAdd(gk + (size_t)icur * F5, ck);
-        }
-        cq = 0.f;
-        ck = 0.f;
-        icur = ir;
-      }
-      const float wv = v[u] + b2;
-      cq = fmaf(s_ab[rr * 8 + hf] * wv, kj[u], cq);
-      ck = fmaf(s_abr[rr * 8 + hf] * wv, qj[u], ck);
-    }
-  }
-}
-
-// MODE 0: forward  -> alpha[e][aoff + h]
-// MODE 1: backward part 1 (recomputes the tile's filter w) -> gproj q/k parts (atomics), ebar[e][1] (cutoff cotangent)
-template <int MODE>
+// Filter kernel: w[c][f] of one filter block for every canonical pair c (the filter is symmetric in e <-> rev e,
+// so it is computed once per undirected pair).  Pure dense work on contiguous tiles of pairs:
+//   S0 (radial basis image) -> GEMM1 -> epilogue 1 (both hidden layers -> image) -> GEMM2 -> + bias -> HBM.
+// Everything that gathers or reduces over neighbours (attention coefficients, aggregation, the q/k gradients)
+// lives in the streaming kernels of so3k_agg.cu, which read w back through the pair index of an edge.
 __global__ void __launch_bounds__(NT, 1)
-k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __restrict__ n_valid,
-          const int* __restrict__ row, const int* __restrict__ col, const int* __restrict__ rev,
-          const float4* __restrict__ geom, const float* __restrict__ chi, const float* __restrict__ proj,
-          const unsigned char* __restrict__ img, const float* __restrict__ bias_g, const float* __restrict__ Ws1_g,
-          const float* __restrict__ bs1_g, float* __restrict__ alpha, const float* __restrict__ alphabar,
-          float* __restrict__ gproj, float* __restrict__ ebar, float* __restrict__ wst, int* __restrict__ status) {
+k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restrict__ n_canon,
+            const int* __restrict__ canon, const int* __restrict__ row, const int* __restrict__ col,
+            const float4* __restrict__ geom, const float* __restrict__ chi, const unsigned char* __restrict__ img,
+            const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
+            float* __restrict__ wst, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool comp = warp < NW;               // compute warp (the extra warp only issues MMAs)
+  const bool comp = warp < NW;
   const int r = 32 * (warp & 3) + lane;      // row of the tile == TMEM lane
   const int qq = comp ? (warp >> 2) : 0;     // column quarter handled by this thread
   const int F = D.F;
-  const int heads = blk ? D.nl : D.H;
-  const int dhd = F / heads;
-  const int aoff = blk ? D.H : 0;
-  const int qoff = blk ? F : 0;
-  const int koff = 2 * F + (blk ? F : 0);
-  const size_t F5 = 5 * (size_t)F;
-  const float inv = 1.0f / sqrtf((float)dhd);
   const TcSmem S = tc_carve(smem, T, D);
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
@@ -472,7 +409,7 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
     tc::mbar_init(&bars[1], 1);
     tc::mbar_fence_init();
   }
-  tc_setup(smem, T, D, S, dhd, img, bias_g, Ws1_g, bs1_g);
+  tc_setup(smem, T, D, S, F, img, bias_g, Ws1_g, bs1_g);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -481,14 +418,12 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
   const uint32_t tD1 = tmem, tD2 = tmem + 256;
   const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
   const uint32_t idesc = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
-  const int nv = *n_valid;
-  const int nf4 = F / 4;
+  const int nv = (*n_canon < pair_cap) ? *n_canon : pair_cap;
   const int nchunk_d = T.Fp / 8;
   const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;    // this thread's D2 chunks
 
   uint32_t it = 0;
-  const int* rev_m = (MODE == 1) ? rev : nullptr;
-  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, nullptr, rev_m);
+  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, canon);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;                     // block-uniform
@@ -496,312 +431,75 @@ k_edge_tc(So3kDims D, TcDims T, int blk, int Ast, int n_tiles, const int* __rest
     const uint32_t par = it & 1u;
     long long t_prev_ = TC_TIMING ? clock64() : 0;
 
-    // backward part 1: alphabar of this row (quarter 1) / of its reverse edge (quarter 3), loaded now, staged to shared
-    // memory after GEMM1 is issued; cutoff cotangent from the stored forward coefficients:
-    //   phibar = sum_h alphabar_h alpha_h / phi
-    float abv[8];
-    float pbv = 0.f;
-    if (MODE == 1) {
-      const bool okb = comp && (qq == 1 || qq == 3) && r < ne;
-      const size_t es = okb ? (size_t)(qq == 1 ? e0 + r : meta.re) : 0;
-#pragma unroll
-      for (int h = 0; h < 8; ++h) {
-        abv[h] = 0.f;
-        if (okb && h < heads) {
-          abv[h] = alphabar[es * Ast + aoff + h];
-          if (qq == 1) pbv = fmaf(abv[h], alpha[es * Ast + aoff + h], pbv);
-        }
-      }
-    }
-
     if (comp) tc_tile_s0<false>(D, T, S, r, qq, ne, meta, nullptr, nullptr);
-    TC_PHASE(MODE, 0);
+    TC_PHASE(0, 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    TC_PHASE(MODE, 1);
+    TC_PHASE(0, 1);
     if (tid == ISSUER) {
       tc::fence_after_sync();
       tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc);
       tc::commit(&bars[0]);
     }
-    // long-latency global loads issued as early as possible: level-1 metadata of this CTA's next tile and (forward)
-    // the q_i * k_j rows of this tile; both are consumed only after GEMM2
+    // level-1 metadata of this CTA's next tile: a dependent load chain (canon -> row/col/geom -> chi rows) that is
+    // started here and finished (level 2) by the column quarter that has the lightest epilogue-1 share
     const int e0_next = (tile + (int)gridDim.x) * TM;
-    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom, nullptr, rev_m);
-    if (MODE == 1 && comp && (qq == 1 || qq == 3)) {
-      // per row and head: ab = alphabar[e] phi / sqrt(dh) (quarter 1), abr = alphabar[rev e] phi / sqrt(dh) (quarter 3)
-      const float ph = S.s_phi[r];
-      float* dstab = S.s_part + (qq == 1 ? 0 : TM * 8) + r * 8;
-      const float sc = inv * ph;
-      *reinterpret_cast<float4*>(dstab) = make_float4(abv[0] * sc, abv[1] * sc, abv[2] * sc, abv[3] * sc);
-      *reinterpret_cast<float4*>(dstab + 4) = make_float4(abv[4] * sc, abv[5] * sc, abv[6] * sc, abv[7] * sc);
-      if (r < ne && qq == 1) {
-        const float pb = ph > 1e-30f ? pbv / ph : 0.f;
-        float* dst = ebar + 2 * (size_t)(e0 + r) + 1;
-        if (blk == 0) *dst = pb; else *dst += pb;
-      }
-    }
-    TC_PHASE(MODE, 2);
+    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom, canon);
+    TC_PHASE(0, 2);
     TC_WAIT_OR_BAIL(&bars[0], par);
-    TC_PHASE(MODE, 3);
+    TC_PHASE(0, 3);
     if (comp) tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
-    TC_PHASE(MODE, 4);
+    tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
+    TC_PHASE(0, 4);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    TC_PHASE(MODE, 5);
+    TC_PHASE(0, 5);
     if (tid == ISSUER) {
       tc::fence_after_sync();
-      if (MODE == 0) {
-        tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
-      } else {
-        // backward: the filter TRANSPOSED, D2T[f][r] (TMEM lane = feature, column = tile row), so that the sums over
-        // the rows of a receiver become serial register sums of the thread that owns feature f.  Features >= 128
-        // (at most 16 of them) come from a small untransposed GEMM, D2x[r][f - 128].
-        tc_issue_gemm(tD2, S.W2hi, S.W2lo, T.sboW2, S.A1hi, S.A1lo, T.sboA1, T.KC / 16,
-                      tc::make_idesc_bf16(128, TM, 0, 0));
-        if (T.Fp > 128)
-          tc_issue_gemm(tD2 + 128, S.A1hi, S.A1lo, T.sboA1, S.W2hi + 16 * T.sboW2, S.W2lo + 16 * T.sboW2, T.sboW2,
-                        T.KC / 16, tc::make_idesc_bf16(TM, T.Fp - 128, 0, 0));
-      }
+      tc_issue_gemm(tD2, S.A1hi, S.A1lo, T.sboA1, S.W2hi, S.W2lo, T.sboW2, T.KC / 16, idesc);
       tc::commit(&bars[1]);
     }
-    // while GEMM2 runs: pull the next tile's gather rows into L2 (their senders are random atoms: DRAM tail latency
-    // would otherwise sit on the critical path), gather this tile's q_i * k_j rows, level-2 metadata of the next tile
-    {
-      const int prev_i = __shfl_up_sync(0xffffffffu, meta_nx.i, 1);
-      if (comp && qq == 0 && e0_next + r < nv) {
-        tc_l2_prefetch_seg(proj, F5, meta_nx.j, koff, F);
-        if (MODE == 1) tc_l2_prefetch_seg(proj, F5, meta_nx.j, qoff, F);
-        if (MODE == 0 && (lane == 0 || prev_i != meta_nx.i)) tc_l2_prefetch_seg(proj, F5, meta_nx.i, qoff, F);
-      }
-      if (MODE == 1 && comp && qq == 3 && e0_next + r < nv)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(alphabar + (size_t)meta_nx.re * Ast + aoff));
-    }
-    float4 pq[8];
-    float4 px = make_float4(0.f, 0.f, 0.f, 0.f);   // float4 column 32 + qq of row r (F <= 144 -> at most 4 of them)
-    if (MODE == 0) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int rr = (warp & 15) * 8 + u;
-        pq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (comp && lane < nf4) {
-          const float4 q = *reinterpret_cast<const float4*>(proj + (size_t)S.s_i[rr] * F5 + qoff + 4 * lane);
-          const float4 k = *reinterpret_cast<const float4*>(proj + (size_t)S.s_j[rr] * F5 + koff + 4 * lane);
-          pq[u] = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
-        }
-      }
-      if (comp && 32 + qq < nf4) {
-        const float4 q = *reinterpret_cast<const float4*>(proj + (size_t)S.s_i[r] * F5 + qoff + 4 * (32 + qq));
-        const float4 k = *reinterpret_cast<const float4*>(proj + (size_t)S.s_j[r] * F5 + koff + 4 * (32 + qq));
-        px = make_float4(q.x * k.x, q.y * k.y, q.z * k.z, q.w * k.w);
-      }
-    }
-    tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
     meta = meta_nx;
-    TC_PHASE(MODE, 6);
-
-    if (MODE == 0) {
-      TC_PHASE(MODE, 7);
-      TC_WAIT_OR_BAIL(&bars[1], par);
-      TC_PHASE(MODE, 8);
-      float* qk = S.region;                    // aliased: the A1 image is dead once GEMM2 has completed
+    TC_PHASE(0, 6);
+    TC_WAIT_OR_BAIL(&bars[1], par);
+    TC_PHASE(0, 7);
+    // ---- epilogue 2: w = D2 + b2 -> HBM (streaming stores; row c of the pair-indexed filter array) -------------------
+    if (comp) {
+      const bool rowok = r < ne;             // every lane takes part in the warp-collective TMEM loads
+      float* wrow = wst + (size_t)(e0 + (rowok ? r : 0)) * F;
+      for (int cb = cbeg; cb < cend; cb += 2) {
+        float v[2][8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (comp && lane < nf4) *reinterpret_cast<float4*>(qk + (size_t)(warp * 8 + u) * T.QS + 4 * lane) = pq[u];
-      if (comp && 32 + qq < nf4) *reinterpret_cast<float4*>(qk + (size_t)r * T.QS + 4 * (32 + qq)) = px;
-      if (comp) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) S.s_part[(r * 4 + qq) * 4 + h] = 0.f;     // [row][quarter][head slot]
-      }
-      __syncthreads();
-      TC_PHASE(MODE, 9);
-      // ---- epilogue 2: alpha_h = sum_{f in head h} (w_f + b_f) q_f k_f / sqrt(d_h) * phi ---------------------------
-      // a quarter (<= 40 columns) touches at most 4 heads; partial sums go to slot (head - first head of the quarter)
-      if (comp) {
-        const float* qrow = qk + (size_t)r * T.QS;
-        float* wrow = (wst && r < ne) ? wst + (size_t)(e0 + r) * F : nullptr;    // keep the filter for the backward
-        const int f0 = cbeg * 8;
-        const int h0 = (f0 < F) ? S.s_head[f0] : 0;
-        float acc = 0.f;
-        int hcur = h0;
-        for (int cb = cbeg; cb < cend; cb += 2) {
-          float v[2][8];
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-            if (cb + u < cend) tc::tmem_ld8(tD2 + lane_sel + (uint32_t)((cb + u) * 8), v[u]);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c0 = (cb + u) * 8;
-            if (cb + u < cend && c0 < F) {
-              if (c0 + 8 <= F && S.s_head[c0 + 7] == hcur) {       // fast path: one head, no padding columns
-                const float4 qa = *reinterpret_cast<const float4*>(qrow + c0);
-                const float4 qb = *reinterpret_cast<const float4*>(qrow + c0 + 4);
-                const float4 ba = *reinterpret_cast<const float4*>(S.b2p + c0);
-                const float4 bb = *reinterpret_cast<const float4*>(S.b2p + c0 + 4);
-                const float4 wa = make_float4(v[u][0] + ba.x, v[u][1] + ba.y, v[u][2] + ba.z, v[u][3] + ba.w);
-                const float4 wb = make_float4(v[u][4] + bb.x, v[u][5] + bb.y, v[u][6] + bb.z, v[u][7] + bb.w);
-                if (wrow) {
-                  __stcs(reinterpret_cast<float4*>(wrow + c0), wa);
-                  __stcs(reinterpret_cast<float4*>(wrow + c0 + 4), wb);
-                }
-                acc = fmaf(wa.x, qa.x, acc); acc = fmaf(wa.y, qa.y, acc);
-                acc = fmaf(wa.z, qa.z, acc); acc = fmaf(wa.w, qa.w, acc);
-                acc = fmaf(wb.x, qb.x, acc); acc = fmaf(wb.y, qb.y, acc);
-                acc = fmaf(wb.z, qb.z, acc); acc = fmaf(wb.w, qb.w, acc);
-              } else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const int f = c0 + q;
-                  if (f < F) {
-                    const int hf = S.s_head[f];
-                    if (hf != hcur) {
-                      S.s_part[(r * 4 + qq) * 4 + (hcur - h0)] = acc;
-                      acc = 0.f;
-                      hcur = hf;
-                    }
-                    const float wv = v[u][q] + S.b2p[f];
-                    if (wrow) wrow[f] = wv;
-                    acc = fmaf(wv, qrow[f], acc);
-                  }
-                }
-              }
-            }
-          }
-        }
-        if (f0 < F) S.s_part[(r * 4 + qq) * 4 + (hcur - h0)] = acc;
-      }
-      TC_PHASE(MODE, 10);
-      tc::fence_before_sync();
-      __syncthreads();
-      TC_PHASE(MODE, 11);
-      if (comp && r < ne) {                    // thread (r, qq) finishes heads qq and qq + 4 of its row
-        const float ph = S.s_phi[r];
-        for (int h = qq; h < heads; h += 4) {
-          float tot = 0.f;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int f0 = ((nchunk_d * q4) / 4) * 8;
-            if (f0 < F) {
-              const int s = h - (int)S.s_head[f0];
-              if (s >= 0 && s < 4) tot += S.s_part[(r * 4 + q4) * 4 + s];
-            }
-          }
-          alpha[(size_t)(e0 + r) * Ast + aoff + h] = tot * inv * ph;
-        }
-        if (blk == 1 && qq == 0)
-          for (int a = D.H + D.nl; a < Ast; ++a) alpha[(size_t)(e0 + r) * Ast + a] = 0.f;
-      }
-      __syncthreads();      // qk tile / s_part fully consumed before the next tile overwrites the region
-      TC_PHASE(MODE, 12);
-      if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[MODE][15], 1ull);
-    } else {
-      // ================= backward part 1 ========================================================================
-      //   qbar_i[f] += sum_{e -> i} ab_e[h(f)]  w_e[f] k_j[f]      kbar_i[f] += sum_{e -> i} abr_e[h(f)] w_e[f] q_j[f]
-      // (the second through the reverse edge: kbar_i collects alphabar of the edges that i SENDS)
-      const float* s_ab = S.s_part;
-      const float* s_abr = S.s_part + TM * 8;
-      // ---- features < 128: thread = (feature f = TMEM lane, 32-row range qq); rows are receiver-sorted, so a
-      //      receiver's rows are consecutive: serial sums in registers, one atomic per (run, feature).
-      //      The k_j / q_j gathers run two 8-row chunks ahead (the first two are in flight while GEMM2 executes).
-      const int f = 32 * (warp & 3) + lane;
-      const bool fok = comp && f < F;
-      const float b2 = fok ? S.b2p[f] : 0.f;
-      const int hf = fok ? (int)S.s_head[f] : 0;
-      const float* pkj = proj + koff + (fok ? f : 0);
-      const float* pqj = proj + qoff + (fok ? f : 0);
-      float* gq = gproj + qoff + (fok ? f : 0);
-      float* gk = gproj + koff + (fok ? f : 0);
-      const int rbeg = 32 * qq;
-      const int rend = (rbeg + 32 < ne) ? rbeg + 32 : ne;
-      float kA[8], qA[8], kB[8], qB[8];
-      b1_gather8(kA, qA, pkj, pqj, S.s_j, F5, rbeg, rend);
-      b1_gather8(kB, qB, pkj, pqj, S.s_j, F5, rbeg + 8, rend);
-      const int ntail = F - 128;                             // features >= 128: column 128 + qq + 4k of row r
-      float tkj[4], tqj[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        tkj[k] = 0.f;
-        tqj[k] = 0.f;
-        if (comp && qq + 4 * k < ntail && r < ne) {
-          const size_t jo = (size_t)S.s_j[r] * F5 + 128 + qq + 4 * k;
-          tkj[k] = __ldg(proj + jo + koff);
-          tqj[k] = __ldg(proj + jo + qoff);
-        }
-      }
-      TC_PHASE(MODE, 7);
-      TC_WAIT_OR_BAIL(&bars[1], par);
-      TC_PHASE(MODE, 8);
-      if (comp) {
-        float cq = 0.f, ck = 0.f;
-        int icur = (rbeg < rend) ? S.s_i[rbeg] : -1;
-        float vA[8], vB[8];
-        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)rbeg, vA);
-        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)(rbeg + 8), vB);
+        for (int u = 0; u < 2; ++u)
+          if (cb + u < cend) tc::tmem_ld8(tD2 + lane_sel + (uint32_t)((cb + u) * 8), v[u]);
         tc::tmem_ld_wait();
-        b1_accum8(vA, kA, qA, s_ab, s_abr, S.s_i, rbeg, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
-        b1_gather8(kA, qA, pkj, pqj, S.s_j, F5, rbeg + 16, rend);
-        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)(rbeg + 16), vA);
-        b1_accum8(vB, kB, qB, s_ab, s_abr, S.s_i, rbeg + 8, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
-        b1_gather8(kB, qB, pkj, pqj, S.s_j, F5, rbeg + 24, rend);
-        tc::tmem_ld8(tD2 + lane_sel + (uint32_t)(rbeg + 24), vB);
-        tc::tmem_ld_wait();
-        b1_accum8(vA, kA, qA, s_ab, s_abr, S.s_i, rbeg + 16, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
-        b1_accum8(vB, kB, qB, s_ab, s_abr, S.s_i, rbeg + 24, rend, hf, b2, fok, gq, gk, F5, icur, cq, ck);
-        if (icur >= 0 && fok) {
-          atomicAdd(gq + (size_t)icur * F5, cq);
-          atomicAdd(gk + (size_t)icur * F5, ck);
-        }
-        TC_PHASE(MODE, 9);
-        // ---- features >= 128 (untransposed, TMEM lane = row): column 128 + qq + 4k of row r; segmented warp sums -------
-        if (ntail > 0) {
-          float vt[16];
-          tc::tmem_ld8(tD2 + 128 + lane_sel, vt);
-          tc::tmem_ld8(tD2 + 128 + lane_sel + 8, vt + 8);
-          tc::tmem_ld_wait();
-          SegMask SM = {false, false, false, false, false};
-          const int my_i = (r < ne) ? S.s_i[r] : -1 - r;         // invalid rows form runs of their own
-          const int i1 = __shfl_down_sync(0xffffffffu, my_i, 1), i2 = __shfl_down_sync(0xffffffffu, my_i, 2);
-          const int i4 = __shfl_down_sync(0xffffffffu, my_i, 4), i8 = __shfl_down_sync(0xffffffffu, my_i, 8);
-          const int i16 = __shfl_down_sync(0xffffffffu, my_i, 16);
-          const int ip = __shfl_up_sync(0xffffffffu, my_i, 1);
-          SM.m1 = lane + 1 < 32 && i1 == my_i;
-          SM.m2 = lane + 2 < 32 && i2 == my_i;
-          SM.m4 = lane + 4 < 32 && i4 == my_i;
-          SM.m8 = lane + 8 < 32 && i8 == my_i;
-          SM.m16 = lane + 16 < 32 && i16 == my_i;
-          const bool run_head = (r < ne) && (lane == 0 || ip != my_i);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = qq + 4 * k;                          // warp-uniform
-            if (c < ntail) {
-              const int ft = 128 + c;
-              const float val = (qq == 0) ? vt[4 * k] : (qq == 1) ? vt[4 * k + 1] : (qq == 2) ? vt[4 * k + 2] : vt[4 * k + 3];
-              float xq = 0.f, xk = 0.f;
-              if (r < ne) {
-                const int ht = S.s_head[ft];
-                const float wv = val + S.b2p[ft];
-                xq = s_ab[r * 8 + ht] * wv * tkj[k];
-                xk = s_abr[r * 8 + ht] * wv * tqj[k];
-              }
-              const float tq = seg_reduce(xq, SM);
-              const float tk = seg_reduce(xk, SM);
-              if (run_head) {
-                atomicAdd(&gproj[(size_t)my_i * F5 + qoff + ft], tq);
-                atomicAdd(&gproj[(size_t)my_i * F5 + koff + ft], tk);
-              }
+        for (int u = 0; u < 2; ++u) {
+          const int c0 = (cb + u) * 8;
+          if (rowok && cb + u < cend && c0 < F) {
+            if (c0 + 8 <= F) {
+              const float4 ba = *reinterpret_cast<const float4*>(S.b2p + c0);
+              const float4 bb = *reinterpret_cast<const float4*>(S.b2p + c0 + 4);
+              __stcs(reinterpret_cast<float4*>(wrow + c0),
+                     make_float4(v[u][0] + ba.x, v[u][1] + ba.y, v[u][2] + ba.z, v[u][3] + ba.w));
+              __stcs(reinterpret_cast<float4*>(wrow + c0 + 4),
+                     make_float4(v[u][4] + bb.x, v[u][5] + bb.y, v[u][6] + bb.z, v[u][7] + bb.w));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (c0 + q < F) wrow[c0 + q] = v[u][q] + S.b2p[c0 + q];
             }
           }
         }
       }
-      TC_PHASE(MODE, 10);
-      tc::fence_before_sync();
-      __syncthreads();         // s_i / s_j / s_part and the accumulators are free for the next tile
-      TC_PHASE(MODE, 11);
-      if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[MODE][15], 1ull);
     }
+    TC_PHASE(0, 8);
+    if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[0][15], 1ull);
+    // no barrier here: the next tile's S0 only overwrites buffers whose last readers (GEMM2 via bars[1], epilogue 1 via
+    // the barrier before GEMM2) are already complete, and the next GEMM2 is issued behind the next tile's barriers
+    tc::fence_before_sync();
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -870,7 +568,10 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const int nv = *n_canon;                      // rows of this kernel = canonical edges (undirected pairs): the filter
   const int nchunkF = T.Fp / 8;                 // and everything downstream of it are identical for e and rev e, and
   const int nchunkK = T.KC / 8;                 // only dbar_e + dbar_rev / gbar_e + gbar_rev enter the forces
-  const int kcb = (nchunkK * qq) / 4, kce = (nchunkK * (qq + 1)) / 4;   // this thread's hidden-column chunks
+  // this thread's hidden-column chunks: a quarter of the radial range plus every 4th chunk beyond it (the spherical
+  // hidden units cost more per column, so they are dealt round-robin)
+  const int kcb = (nchunkF * qq) / 4, kce = (nchunkF * (qq + 1)) / 4;
+  const int nmine = comp ? (kce - kcb) + ((nchunkK - nchunkF - qq + 3) / 4) : 0;
 
   uint32_t it = 0;
   TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, canon, rev);
@@ -880,71 +581,100 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
     const int my_e = meta.e, my_re = meta.re;     // valid for r < ne
+    long long t_prev_ = TC_TIMING ? clock64() : 0;
 
+    float abv[8];                                 // alphabar of e (quarter 1) / rev e (quarter 3): loaded before S0,
+    {                                             // staged after it (the latency hides behind the S0 arithmetic)
+      const bool okb = comp && (qq == 1 || qq == 3) && r < ne;
+      const int esrc = (qq == 1) ? my_e : my_re;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) abv[h] = (okb && h < heads) ? alphabar[(size_t)esrc * Ast + aoff + h] : 0.f;
+    }
     if (comp) tc_tile_s0<true>(D, T, S, r, qq, ne, meta, A0dhi, A0dlo);
     if (comp && (qq == 1 || qq == 3)) {
       const float ph = (r < ne) ? cutoff_fast(meta.d, D.r_cut) * inv : 0.f;
-      float* dstab = (qq == 1) ? s_ab : s_abr;
-      const int esrc = (qq == 1) ? my_e : my_re;
-#pragma unroll
-      for (int h = 0; h < 8; ++h)
-        dstab[r * 8 + h] = (h < heads && r < ne) ? alphabar[(size_t)esrc * Ast + aoff + h] * ph : 0.f;
+      float* dstab = ((qq == 1) ? s_ab : s_abr) + r * 8;
+      *reinterpret_cast<float4*>(dstab) = make_float4(abv[0] * ph, abv[1] * ph, abv[2] * ph, abv[3] * ph);
+      *reinterpret_cast<float4*>(dstab + 4) = make_float4(abv[4] * ph, abv[5] * ph, abv[6] * ph, abv[7] * ph);
     }
     if (comp && qq == 2) {
 #pragma unroll
       for (int h = 0; h < 8; ++h) s_red[r * 8 + h] = 0.f;
     }
+    TC_PHASE(2, 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
+    TC_PHASE(2, 1);
     if (tid == ISSUER) {
       tc::fence_after_sync();
       tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
       tc_issue_gemm(tD1p, A0dhi, A0dlo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
       tc::commit(&bars[0]);
     }
+    // level-1 metadata of this CTA's next tile (consumed after GEMM3 is issued)
+    const int e0_next = (tile + (int)gridDim.x) * TM;
+    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom, canon, rev);
     // ---- wbar image: work item = (row group of 8 rows, column group of 4 chunks): lane -> (row = lane / 4, chunk = lane % 4)
+    //      two items per iteration: 16 independent 16-byte gathers in flight per lane
     const int ncg = (nchunkF + 3) / 4;
     const int nitems = 16 * ncg;
+    TC_PHASE(2, 2);
     TC_WAIT_OR_BAIL(&bars[0], par);
-    for (int item = comp ? warp : nitems; item < nitems; item += NW) {
-      const int rg = item / ncg, cg = item - rg * ncg;
-      const int rr = rg * 8 + (lane >> 2);
-      const int c = cg * 4 + (lane & 3);
-      if (c < nchunkF) {
-        const int f0 = c * 8;
-        float wv[8];
+    TC_PHASE(2, 3);
+    for (int item0 = comp ? warp : nitems; item0 < nitems; item0 += 2 * NW) {
+      float4 g[2][8];
+      int rrs[2], cs[2];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) wv[q] = 0.f;
-        if (f0 < F) {
+      for (int v = 0; v < 2; ++v) {
+        const int item = item0 + v * NW;
+        const int rg = item / ncg, cg = item - rg * ncg;
+        rrs[v] = (item < nitems) ? rg * 8 + (lane >> 2) : 0;
+        cs[v] = (item < nitems) ? cg * 4 + (lane & 3) : nchunkF;
+        const int f0 = cs[v] * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) g[v][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cs[v] < nchunkF && f0 < F) {
           // both directions of the pair: e = (i <- j) uses q_i k_j, rev e = (j <- i) uses q_j k_i
-          const float* pi = proj + (size_t)S.s_i[rr] * F5 + f0;
-          const float* pj = proj + (size_t)S.s_j[rr] * F5 + f0;
-          const float4 qia = *reinterpret_cast<const float4*>(pi + qoff), kja = *reinterpret_cast<const float4*>(pj + koff);
-          const float4 qja = *reinterpret_cast<const float4*>(pj + qoff), kia = *reinterpret_cast<const float4*>(pi + koff);
-          float4 qib = make_float4(0.f, 0.f, 0.f, 0.f), kjb = qib, qjb = qib, kib = qib;
+          const float* pi = proj + (size_t)S.s_i[rrs[v]] * F5 + f0;
+          const float* pj = proj + (size_t)S.s_j[rrs[v]] * F5 + f0;
+          g[v][0] = *reinterpret_cast<const float4*>(pi + qoff);
+          g[v][1] = *reinterpret_cast<const float4*>(pj + koff);
+          g[v][2] = *reinterpret_cast<const float4*>(pj + qoff);
+          g[v][3] = *reinterpret_cast<const float4*>(pi + koff);
           if (f0 + 4 < F) {
-            qib = *reinterpret_cast<const float4*>(pi + qoff + 4); kjb = *reinterpret_cast<const float4*>(pj + koff + 4);
-            qjb = *reinterpret_cast<const float4*>(pj + qoff + 4); kib = *reinterpret_cast<const float4*>(pi + koff + 4);
+            g[v][4] = *reinterpret_cast<const float4*>(pi + qoff + 4);
+            g[v][5] = *reinterpret_cast<const float4*>(pj + koff + 4);
+            g[v][6] = *reinterpret_cast<const float4*>(pj + qoff + 4);
+            g[v][7] = *reinterpret_cast<const float4*>(pi + koff + 4);
           }
-          const float fw[8] = {qia.x * kja.x, qia.y * kja.y, qia.z * kja.z, qia.w * kja.w,
-                               qib.x * kjb.x, qib.y * kjb.y, qib.z * kjb.z, qib.w * kjb.w};
-          const float bw[8] = {qja.x * kia.x, qja.y * kia.y, qja.z * kia.z, qja.w * kia.w,
-                               qjb.x * kib.x, qjb.y * kib.y, qjb.z * kib.z, qjb.w * kib.w};
-          const float* sab = s_ab + rr * 8;
-          const float* sabr = s_abr + rr * 8;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        if (cs[v] < nchunkF) {
+          const int f0 = cs[v] * 8;
+          const float fw[8] = {g[v][0].x * g[v][1].x, g[v][0].y * g[v][1].y, g[v][0].z * g[v][1].z, g[v][0].w * g[v][1].w,
+                               g[v][4].x * g[v][5].x, g[v][4].y * g[v][5].y, g[v][4].z * g[v][5].z, g[v][4].w * g[v][5].w};
+          const float bw[8] = {g[v][2].x * g[v][3].x, g[v][2].y * g[v][3].y, g[v][2].z * g[v][3].z, g[v][2].w * g[v][3].w,
+                               g[v][6].x * g[v][7].x, g[v][6].y * g[v][7].y, g[v][6].z * g[v][7].z, g[v][6].w * g[v][7].w};
+          const float* sab = s_ab + rrs[v] * 8;
+          const float* sabr = s_abr + rrs[v] * 8;
+          float wv[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int hq = S.s_head[f0 + q];
             wv[q] = (f0 + q < F) ? fmaf(sab[hq], fw[q], sabr[hq] * bw[q]) : 0.f;
           }
+          tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rrs[v], cs[v], sboWb), wv);
         }
-        tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rr, c, sboWb), wv);
       }
     }
+    TC_PHASE(2, 4);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
+    TC_PHASE(2, 5);
     // ---- GEMM3: hbar[128 x KC] = wbar[128 x Fp] @ W2c^T --------------------------------------------------------------
     if (tid == ISSUER) {
       tc::fence_after_sync();
@@ -969,12 +699,30 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
       gb[l] = 0.f;
     }
-    meta = tc_prefetch_meta(D, r, qq, (tile + (int)gridDim.x) * TM, nv, comp, row, col, geom, chi, canon, rev);   // overlaps GEMM3
+    // overlapping GEMM3: pull the next tile's gather rows into L2, finish its metadata
+    {
+      const int prev_i = __shfl_up_sync(0xffffffffu, meta_nx.i, 1);
+      if (comp && qq == 0 && e0_next + r < nv) {
+        tc_l2_prefetch_seg(proj, F5, meta_nx.j, koff, F);
+        tc_l2_prefetch_seg(proj, F5, meta_nx.j, qoff, F);
+        if (lane == 0 || prev_i != meta_nx.i) {
+          tc_l2_prefetch_seg(proj, F5, meta_nx.i, koff, F);
+          tc_l2_prefetch_seg(proj, F5, meta_nx.i, qoff, F);
+        }
+      }
+      if (comp && (qq == 1 || qq == 3) && e0_next + r < nv)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(alphabar + (size_t)(qq == 1 ? meta_nx.e : meta_nx.re) * Ast + aoff));
+    }
+    tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
+    meta = meta_nx;
+    TC_PHASE(2, 6);
     TC_WAIT_OR_BAIL(&bars[1], par);
+    TC_PHASE(2, 7);
     // ---- epilogue: this thread's quarter of the KC hidden columns of its row ------------------------------------------------
     {
       float dbar = 0.f;
-      for (int cc = comp ? kcb : kce; cc < kce; ++cc) {
+      for (int ci = 0; ci < nmine; ++ci) {
+        const int cc = (ci < kce - kcb) ? kcb + ci : nchunkF + qq + 4 * (ci - (kce - kcb));
         const int c0 = cc * 8;
         if (c0 >= F + Fs) break;                  // warp-uniform: only zero padding left
         float hb[8], a1[8], tp[8];
@@ -1002,6 +750,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
           }
         }
       }
+      TC_PHASE(2, 8);
       // cross-quarter combination: 4 contributions per slot through shared-memory atomics
       if (comp) {
         atomicAdd(&s_red[r * 8 + 0], dbar);
@@ -1011,18 +760,22 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       }
       tc::fence_before_sync();
       __syncthreads();
+      TC_PHASE(2, 9);
       if (comp && qq == 0 && r < ne) {
         // the pair's totals go to the canonical edge; its reverse gets zeros (only the sums enter chi-bar and F)
         const size_t e = (size_t)my_e, re = (size_t)my_re;
         const float db = s_red[r * 8 + 0];
-        if (blk == 0) { ebar[2 * e] = db; ebar[2 * re] = 0.f; } else ebar[2 * e] += db;
+        // (second block: fire-and-forget reductions instead of read-modify-write round trips)
+        if (blk == 0) { ebar[2 * e] = db; ebar[2 * re] = 0.f; } else atomicAdd(&ebar[2 * e], db);
         for (int l = 0; l < D.nl; ++l) {
           const float gsum = s_red[r * 8 + 1 + l];
-          if (blk == 0) { gbar[e * Gst + l] = gsum; gbar[re * Gst + l] = 0.f; } else gbar[e * Gst + l] += gsum;
+          if (blk == 0) { gbar[e * Gst + l] = gsum; gbar[re * Gst + l] = 0.f; } else atomicAdd(&gbar[e * Gst + l], gsum);
         }
       }
     }
     __syncthreads();
+    TC_PHASE(2, 10);
+    if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[2][15], 1ull);
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -1067,59 +820,51 @@ static int tc_grid(int n_tiles, const TcDims& T) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_edge_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
-    cudaFuncSetAttribute(k_edge_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
-    cudaFuncSetAttribute(k_edge_bwd2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T.total + 1024));
+    (void)T;
   }
   return n_tiles < n_sm ? n_tiles : n_sm;
 }
 
-void so3k_launch_edge_fwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, float* alpha, float* wst_f, float* wst_g, int* status, cudaStream_t st) {
+// filter of one block for every canonical pair -> wst[pair][F]
+void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* chi, float* wst, int* status,
+                           cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
-  int Ast = (D.H + D.nl + 3) & ~3;
-  int n_tiles = so3k_cdiv(g.Pt, TM);
+  const int pair_cap = so3k_pair_capacity(g.Pt);
+  int n_tiles = so3k_cdiv(pair_cap, TM);
   int grid = tc_grid(n_tiles, T);
-  for (int blk = 0; blk < 2; ++blk) {
-    const TcBlockW& W = blk ? Wg : Wf;
-    so3k_count_launch();
-    k_edge_tc<0><<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.rev, g.geom, chi, proj,
-                                                    W.img, W.bias, W.Ws1, W.bs1, alpha, nullptr, nullptr, nullptr,
-                                                    blk ? wst_g : wst_f, status);
-  }
+  cudaFuncSetAttribute(k_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total + 1024);
+  so3k_count_launch();
+  k_filter_tc<<<grid, NT, T.total + 1024, st>>>(D, T, n_tiles, pair_cap, g.n_canon, g.canon, g.row, g.col, g.geom, chi, W.img,
+                                                 W.bias, W.Ws1, W.bs1, wst, status);
 }
 
-// parts: bit 0 -> q/k projection gradients + cutoff cotangent (ebar[e][1]) ; bit 1 -> radial cotangent (ebar[e][0]) + gbar
-void so3k_launch_edge_bwd_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                             const float* proj, const float* alpha, const float* alphabar, int parts, float* gproj,
-                             float* gbar, float* ebar, int* status, cudaStream_t st) {
+// radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of both filter blocks
+void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
+                              const float* proj, const float* alphabar, float* gbar, float* ebar, int* status,
+                              cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
   int Ast = (D.H + D.nl + 3) & ~3;
   int Gst = (D.nl + 3) & ~3;
-  int n_tiles = so3k_cdiv(g.Pt, TM);
+  int n_tiles = so3k_cdiv(so3k_pair_capacity(g.Pt), TM);
   int grid = tc_grid(n_tiles, T);
+  cudaFuncSetAttribute(k_edge_bwd2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total + 1024);
   for (int blk = 0; blk < 2; ++blk) {
     const TcBlockW& W = blk ? Wg : Wf;
-    if (parts & 1) {
-      so3k_count_launch();
-      k_edge_tc<1><<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, n_tiles, g.n_valid, g.row, g.col, g.rev, g.geom, chi,
-                                                      proj, W.img, W.bias, W.Ws1, W.bs1, const_cast<float*>(alpha), alphabar, gproj, ebar,
-                                                      nullptr, status);
-    }
-    if (parts & 2) {
-      so3k_count_launch();
-      k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, Gst, n_tiles, g.n_canon, g.canon, g.rev, g.row, g.col, g.geom, chi, proj,
-                                                        W.img, W.bias, W.Ws1, W.bs1, alphabar, gbar, ebar, status);
-    }
+    so3k_count_launch();
+    k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, Gst, n_tiles, g.n_canon, g.canon, g.rev, g.row, g.col,
+                                                      g.geom, chi, proj, W.img, W.bias, W.Ws1, W.bs1, alphabar, gbar, ebar,
+                                                      status);
   }
 }
 extern "C" void so3k_tc_phase_dump(void) {
   unsigned long long h[3][16];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_tc_phase, sizeof(h));
-  // forward names; backward part 1 reuses 0-6, then 7 = (none), 8 = wait2, 9 = transposed epilogue, 10 = tail, 11 = sync
+  // forward names; backward part 1 reuses 0-6, then 7 = (none), 8 = wait2, 9 = transposed epilogue, 10 = tail, 11 = sync;
+  // backward part 2: 0 S0+alphabar, 1 sync, 2 issue GEMM1s, 3 wait, 4 wbar image (gathers), 5 sync, 6 issue GEMM3 + next
+  // tile's metadata, 7 wait, 8 epilogue, 9 reduce+sync, 10 stores+sync
   const char* names[13] = {"S0", "sync", "issue1", "wait1", "epi1", "sync", "issue2", "gather", "wait2", "qkstore+sync",
                            "epi2", "sync", "alpha+sync"};
   for (int k = 0; k < 3; ++k) {
@@ -1138,8 +883,7 @@ bool so3k_edge_tc_supported(const So3kDims&) { return false; }
 size_t so3k_edge_tc_image_bytes(const So3kDims&) { return 0; }
 void so3k_edge_tc_build(const So3kDims&, const float*, const BlockParams&, unsigned char*, TcBlockW*, const EdgeBlockW&,
                         cudaStream_t) {}
-void so3k_launch_edge_fwd_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
-                             float*, float*, float*, int*, cudaStream_t) {}
-void so3k_launch_edge_bwd_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
-                             const float*, const float*, int, float*, float*, float*, int*, cudaStream_t) {}
+void so3k_launch_filter_tc(const So3kDims&, const Graph&, const TcBlockW&, const float*, float*, int*, cudaStream_t) {}
+void so3k_launch_edge_bwd2_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
+                              const float*, float*, float*, int*, cudaStream_t) {}
 #endif

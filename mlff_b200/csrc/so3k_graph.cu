@@ -203,14 +203,24 @@ __global__ void k_rev(int N, const int* __restrict__ rowptr, const int* __restri
 }
 
 // canonical edges: one representative per undirected pair {e, rev e} (the one with the smaller sorted index)
-__global__ void k_canon_flag(int N, const int* __restrict__ rowptr, const int* __restrict__ rev, int* __restrict__ flag, int Pt) {
+__global__ void k_canon_flag(int N, const int* __restrict__ rowptr, const int* __restrict__ rev, int* __restrict__ flag,
+                             int* __restrict__ pid, int Pt) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < Pt) flag[e] = (e < rowptr[N] && e < rev[e]) ? 1 : 0;
+  if (e < Pt) {
+    flag[e] = (e < rowptr[N] && e < rev[e]) ? 1 : 0;
+    pid[e] = 0;         // edges without a partner (asymmetric list, flagged by k_rev) keep an in-range index
+  }
 }
-__global__ void k_canon_fill(int Pt, const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ canon,
-                             int* __restrict__ n_canon) {
+__global__ void k_canon_fill(int Pt, const int* __restrict__ flag, const int* __restrict__ pos, const int* __restrict__ rev,
+                             int* __restrict__ canon, int* __restrict__ n_canon, int* __restrict__ pid) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < Pt && flag[e]) canon[pos[e]] = e;
+  if (e < Pt && flag[e]) {
+    const int c = pos[e];
+    canon[c] = e;
+    const int cc = c < so3k_pair_capacity(Pt) ? c : 0;
+    pid[e] = cc;
+    pid[rev[e]] = cc;
+  }
   if (e == 0) *n_canon = pos[Pt];
 }
 
@@ -254,10 +264,10 @@ void so3k_build_graph(const So3kDims& D, int B, int n, int P, const float* R, co
     int* cpos = total + 8;                         // (Pt + 1)
     int nbp = so3k_cdiv(Pt, SCAN_BLK);
     int* cbsum = cpos + Pt + 1;                    // (nbp + 2)
-    SO3K_LAUNCH(k_canon_flag, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, N, g.rowptr, g.rev, flag, Pt);
+    SO3K_LAUNCH(k_canon_flag, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, N, g.rowptr, g.rev, flag, g.pid, Pt);
     SO3K_LAUNCH(k_scan_local, dim3(nbp), dim3(SCAN_T), 0, st, Pt, flag, cpos, cbsum);
     SO3K_LAUNCH(k_scan_bsum, dim3(1), dim3(SCAN_T), 0, st, nbp, cbsum, cbsum + nbp);
     SO3K_LAUNCH(k_scan_add, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, cpos, cbsum, cbsum + nbp);
-    SO3K_LAUNCH(k_canon_fill, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, flag, cpos, g.canon, g.n_canon);
+    SO3K_LAUNCH(k_canon_fill, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, flag, cpos, g.rev, g.canon, g.n_canon, g.pid);
   }
 }

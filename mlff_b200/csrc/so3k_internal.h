@@ -45,7 +45,10 @@ struct Graph {
   int* n_valid;       // device scalar = rowptr[N]
   int* canon;         // (Pt)  sorted indices e with e < rev[e]: one representative per undirected pair
   int* n_canon;       // device scalar
+  int* pid;           // (Pt)  pair index of sorted edge e: canon[pid[e]] is e or rev[e]
 };
+// rows of the pair-indexed arrays (a symmetric list has exactly Pt / 2 pairs; malformed lists are clamped to this)
+SO3K_HD static inline int so3k_pair_capacity(int Pt) { return Pt / 2 + 1; }
 
 // ---- kernels' host launchers -------------------------------------------------------------------
 // graph.cu
@@ -78,6 +81,9 @@ void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, co
 void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                            const float* xbar1, const float* chibar1, float* alphabar, float* gproj /* v grad */,
                            cudaStream_t st);
+void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
+                                 const float* wst_f, const float* wst_g, float* alpha, float* x1, float* chi1,
+                                 cudaStream_t st);
 void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                                const float* alphabar, const float* wst_f, const float* wst_g, float* gproj, float* ebar,
                                cudaStream_t st);
