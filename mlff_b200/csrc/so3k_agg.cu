@@ -360,98 +360,104 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
 }
 
-// q/k projection gradients from the pair-indexed filters w[pid e][f] of both blocks (kept from the forward with
-// SO3K_FLAG_KEEP_FILTERS, else recomputed by k_filter_tc just before):
-//   qbar_i[f] = sum_{e in row i} alphabar[e][h(f)]     phi_e / sqrt(d_h) w_e[f] k_j[f]
-//   kbar_i[f] = sum_{e in row i} alphabar[rev e][h(f)] phi_e / sqrt(d_h) w_e[f] q_j[f]     (w, phi are symmetric in e <-> rev e)
-// and the cutoff cotangent  ebar[e][1] = sum_a alphabar[e][a] alpha[e][a] / phi_e.
-// Pure streaming: 2F floats of filters per edge from HBM, 4F floats of sender q/k rows (L2), no atomics.
+// q/k projection gradients of one filter block (blockIdx.y) from its pair-indexed filters w[pid e][f] (kept from the
+// forward with SO3K_FLAG_KEEP_FILTERS, else recomputed by k_filter_tc just before):
+//   qbar_i[f] = sum_{e in row i} ab_e[h(f)]  w_e[f] k_j[f]        ab_e  = alphabar[e]     phi_e / sqrt(d_h)
+//   kbar_i[f] = sum_{e in row i} abr_e[h(f)] w_e[f] q_j[f]        abr_e = alphabar[rev e] phi_e / sqrt(d_h)
+// (w and phi are symmetric in e <-> rev e), the cutoff cotangent ebar[e][1] = sum_a alphabar[e][a] alpha[e][a] / phi_e,
+// and, for the canonical edge of every pair, the filter cotangent of the PAIR
+//   wbar[pid e][f] = ab_e[h(f)] q_i[f] k_j[f] + abr_e[h(f)] q_j[f] k_i[f]
+// which the tensor-core kernel of backward part 2 then reads as a contiguous tile.
+// Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics.
 template <int TN>                               // TN = ceil(F / 32): feature slots per lane
 __global__ void __launch_bounds__(WPB * 32)
 k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
-                const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ proj,
-                const float* __restrict__ alpha, const float* __restrict__ alphabar, const float* __restrict__ wst_f,
-                const float* __restrict__ wst_g, float* __restrict__ gproj, float* __restrict__ ebar) {
-  __shared__ float s_ab[WPB][32 * AMAX];    // alphabar[e]     * phi / sqrt(d_h)
-  __shared__ float s_abr[WPB][32 * AMAX];   // alphabar[rev e] * phi / sqrt(d_h)
+                const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom,
+                const float* __restrict__ proj, const float* __restrict__ alpha, const float* __restrict__ alphabar,
+                const float* __restrict__ wst, size_t blk_stride, float* __restrict__ gproj, float* __restrict__ ebar,
+                float* __restrict__ wbar) {
+  __shared__ float s_ab[WPB][32 * 8];
+  __shared__ float s_abr[WPB][32 * 8];
   __shared__ int s_j[WPB][32];
-  __shared__ int s_p[WPB][32];
+  __shared__ int s_p[WPB][32];              // pair index ; bit 31 set: e is the canonical edge of its pair
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * WPB + w;
+  const int blk = blockIdx.y;
   const int F = D.F, H = D.H, nl = D.nl;
+  const int heads = blk ? nl : H, aoff = blk ? H : 0;
+  const int qoff = blk ? F : 0, koff = 2 * F + (blk ? F : 0);
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
   const size_t F5 = 5 * (size_t)F;
-  const float inv_f = 1.0f / sqrtf((float)(F / H)), inv_g = 1.0f / sqrtf((float)(F / nl));
-  float aqf[TN], akf[TN], aqg[TN], akg[TN];
-  int hf[TN], hg[TN];
+  const float inv = 1.0f / sqrtf((float)(F / heads));
+  wst += blk * blk_stride;
+  wbar += blk * blk_stride;
+  float aq[TN], ak[TN], qi[TN], ki[TN];
+  int hf[TN];
 #pragma unroll
   for (int t = 0; t < TN; ++t) {
-    aqf[t] = akf[t] = aqg[t] = akg[t] = 0.f;
+    aq[t] = ak[t] = 0.f;
     const int f = lane + 32 * t;
-    hf[t] = (f < F) ? f / (F / H) : 0;
-    hg[t] = (f < F) ? H + f / (F / nl) : 0;
+    const bool ok = rowok && f < F;
+    qi[t] = ok ? proj[(size_t)i * F5 + qoff + f] : 0.f;
+    ki[t] = ok ? proj[(size_t)i * F5 + koff + f] : 0.f;
+    hf[t] = (f < F) ? f / (F / heads) : 0;
   }
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     const int cnt = (end - e0) < 32 ? (end - e0) : 32;
-    int j = 0, pe = 0;
     if (e < end) {
-      j = col[e];
-      pe = pid[e];
       const int re = rev[e];
+      s_j[w][lane] = col[e];
+      s_p[w][lane] = pid[e] | (e < re ? (int)0x80000000 : 0);
       const float ph = so3k_cutoff(geom[e].w, D.r_cut);
-      float pb = 0.f;
-      for (int a = 0; a < H + nl; ++a) {
-        const float ab = alphabar[(size_t)e * Ast + a];
-        const float sc = ph * (a < H ? inv_f : inv_g);
-        pb = fmaf(ab, alpha[(size_t)e * Ast + a], pb);
-        s_ab[w][lane * Ast + a] = ab * sc;
-        s_abr[w][lane * Ast + a] = alphabar[(size_t)re * Ast + a] * sc;
+      const float sc = ph * inv;
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        s_ab[w][lane * 8 + h] = (h < heads) ? alphabar[(size_t)e * Ast + aoff + h] * sc : 0.f;
+        s_abr[w][lane * 8 + h] = (h < heads) ? alphabar[(size_t)re * Ast + aoff + h] * sc : 0.f;
       }
-      ebar[2 * (size_t)e + 1] = ph > 1e-30f ? pb / ph : 0.f;
+      if (blk == 0) {
+        float pb = 0.f;
+        for (int a = 0; a < H + nl; ++a) pb = fmaf(alphabar[(size_t)e * Ast + a], alpha[(size_t)e * Ast + a], pb);
+        ebar[2 * (size_t)e + 1] = ph > 1e-30f ? pb / ph : 0.f;
+      }
     }
-    s_j[w][lane] = j;
-    s_p[w][lane] = pe;
     __syncwarp();
-    // two edges per iteration: 12 * TN independent loads in flight per lane (the kernel is latency-bound otherwise)
+    // two edges per iteration: 6 * TN independent loads in flight per lane (the kernel is latency-bound otherwise)
     for (int q = 0; q < cnt; q += 2) {
-      const bool two = q + 1 < cnt;
-      const int q1 = two ? q + 1 : q;
-      const float* pj0 = proj + (size_t)s_j[w][q] * F5;
-      const float* pj1 = proj + (size_t)s_j[w][q1] * F5;
-      const float* wf0 = wst_f + (size_t)s_p[w][q] * F;
-      const float* wg0 = wst_g + (size_t)s_p[w][q] * F;
-      const float* wf1 = wst_f + (size_t)s_p[w][q1] * F;
-      const float* wg1 = wst_g + (size_t)s_p[w][q1] * F;
-      float vf0[TN], vg0[TN], kf0[TN], kg0[TN], qf0[TN], qg0[TN];
-      float vf1[TN], vg1[TN], kf1[TN], kg1[TN], qf1[TN], qg1[TN];
+      float wv[2][TN], kj[2][TN], qj[2][TN];
+      int qk[2], pp[2];
 #pragma unroll
-      for (int t = 0; t < TN; ++t) {
-        const int f = lane + 32 * t;
-        const bool ok = (t + 1 < TN) || f < F;
-        vf0[t] = ok ? wf0[f] : 0.f;           vg0[t] = ok ? wg0[f] : 0.f;
-        kf0[t] = ok ? pj0[2 * F + f] : 0.f;   kg0[t] = ok ? pj0[3 * F + f] : 0.f;
-        qf0[t] = ok ? pj0[f] : 0.f;           qg0[t] = ok ? pj0[F + f] : 0.f;
-        vf1[t] = ok ? wf1[f] : 0.f;           vg1[t] = ok ? wg1[f] : 0.f;
-        kf1[t] = ok ? pj1[2 * F + f] : 0.f;   kg1[t] = ok ? pj1[3 * F + f] : 0.f;
-        qf1[t] = ok ? pj1[f] : 0.f;           qg1[t] = ok ? pj1[F + f] : 0.f;
+      for (int k = 0; k < 2; ++k) {
+        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+        pp[k] = s_p[w][qk[k]];
+        const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
+        const float* pw = wst + (size_t)(pp[k] & 0x7fffffff) * F;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          const bool ok = (t + 1 < TN) || f < F;
+          wv[k][t] = ok ? pw[f] : 0.f;
+          kj[k][t] = ok ? pj[koff + f] : 0.f;
+          qj[k][t] = ok ? pj[qoff + f] : 0.f;
+        }
       }
-      const float* ab0 = &s_ab[w][q * Ast];
-      const float* abr0 = &s_abr[w][q * Ast];
-      const float* ab1 = &s_ab[w][q1 * Ast];
-      const float* abr1 = &s_abr[w][q1 * Ast];
-      const float m1 = two ? 1.f : 0.f;
 #pragma unroll
-      for (int t = 0; t < TN; ++t) {
-        aqf[t] = fmaf(ab0[hf[t]] * vf0[t], kf0[t], aqf[t]);
-        akf[t] = fmaf(abr0[hf[t]] * vf0[t], qf0[t], akf[t]);
-        aqg[t] = fmaf(ab0[hg[t]] * vg0[t], kg0[t], aqg[t]);
-        akg[t] = fmaf(abr0[hg[t]] * vg0[t], qg0[t], akg[t]);
-        aqf[t] = fmaf(m1 * ab1[hf[t]] * vf1[t], kf1[t], aqf[t]);
-        akf[t] = fmaf(m1 * abr1[hf[t]] * vf1[t], qf1[t], akf[t]);
-        aqg[t] = fmaf(m1 * ab1[hg[t]] * vg1[t], kg1[t], aqg[t]);
-        akg[t] = fmaf(m1 * abr1[hg[t]] * vg1[t], qg1[t], akg[t]);
+      for (int k = 0; k < 2; ++k) {
+        const float m = (q + k < cnt) ? 1.f : 0.f;
+        const float* ab = &s_ab[w][qk[k] * 8];
+        const float* abr = &s_abr[w][qk[k] * 8];
+        const bool canon = (pp[k] < 0) && (q + k < cnt);          // warp-uniform
+        float* wb = wbar + (size_t)(pp[k] & 0x7fffffff) * F;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const float a0 = ab[hf[t]], a1 = abr[hf[t]];
+          aq[t] = fmaf(m * a0 * wv[k][t], kj[k][t], aq[t]);
+          ak[t] = fmaf(m * a1 * wv[k][t], qj[k][t], ak[t]);
+          const int f = lane + 32 * t;
+          if (canon && ((t + 1 < TN) || f < F)) __stcs(wb + f, fmaf(a0 * qi[t], kj[k][t], a1 * qj[k][t] * ki[t]));
+        }
       }
     }
     __syncwarp();
@@ -462,10 +468,8 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
     for (int t = 0; t < TN; ++t) {
       const int f = lane + 32 * t;
       if (f < F) {
-        gi[f] = aqf[t];
-        gi[F + f] = aqg[t];
-        gi[2 * F + f] = akf[t];
-        gi[3 * F + f] = akg[t];
+        gi[qoff + f] = aq[t];
+        gi[koff + f] = ak[t];
       }
     }
   }
@@ -586,14 +590,16 @@ void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj,
 #undef SO3K_AB_CASE
 }
 
+// wst / wbar: [block][pair capacity][F] (block stride = so3k_pair_capacity(Pt) * F floats)
 void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
-                               const float* alphabar, const float* wst_f, const float* wst_g, float* gproj, float* ebar,
+                               const float* alphabar, const float* wst, float* gproj, float* ebar, float* wbar,
                                cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
+  const size_t blk_stride = (size_t)so3k_pair_capacity(g.Pt) * D.F;
 #define SO3K_QK_CASE(TN_)                                                                                              \
   case TN_:                                                                                                            \
-    SO3K_LAUNCH(k_qk_bwd_stream<TN_>, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,  \
-                g.rev, g.pid, g.geom, proj, alpha, alphabar, wst_f, wst_g, gproj, ebar);                                      \
+    SO3K_LAUNCH(k_qk_bwd_stream<TN_>, dim3(so3k_cdiv(g.N, WPB), 2), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
+                g.col, g.rev, g.pid, g.geom, proj, alpha, alphabar, wst, blk_stride, gproj, ebar, wbar);               \
     break;
   switch (so3k_cdiv(D.F, 32)) {
     SO3K_QK_CASE(1) SO3K_QK_CASE(2) SO3K_QK_CASE(3) SO3K_QK_CASE(4) SO3K_QK_CASE(5) SO3K_QK_CASE(6) SO3K_QK_CASE(7)

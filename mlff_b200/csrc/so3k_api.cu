@@ -181,6 +181,8 @@ struct Workspace {
   float *alphabar, *gbar, *rbar, *ebar;
   float *wst;              // tensor mode: filters [layer or 1][block][pair][F] (all layers with SO3K_FLAG_KEEP_FILTERS)
   int wst_layers;
+  float *rec;              // tensor mode: per-pair records of the current layer [pair][8]
+  float *wbar;             // tensor mode: pair-indexed filter cotangents of the layer being differentiated [block][pair][F]
   float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
   float *e_atom;
   size_t bytes;
@@ -226,6 +228,8 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int wst_layers)
   w.g.pid = (int*)take(sizeof(int) * Pe);
   w.wst_layers = wst_layers;
   w.wst = wst_layers ? (float*)take(sizeof(float) * wst_layers * 2 * (size_t)so3k_pair_capacity(Pt) * F) : nullptr;
+  w.rec = wst_layers ? (float*)take(sizeof(float) * 8 * (size_t)so3k_pair_capacity(Pt)) : nullptr;
+  w.wbar = wst_layers ? (float*)take(sizeof(float) * 2 * (size_t)so3k_pair_capacity(Pt) * F) : nullptr;
   w.xbar_a = (float*)take(sizeof(float) * N * F);
   w.xbar_b = (float*)take(sizeof(float) * N * F);
   w.chibar_a = (float*)take(sizeof(float) * N * M);
@@ -262,8 +266,9 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
     float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
     {
       PROF(CAT_EDGE_FWD);
-      so3k_launch_filter_tc(D, w.g, h->tf[t], ct, wst_t, dev_status, st);
-      so3k_launch_filter_tc(D, w.g, h->tg[t], ct, wst_t + Pc * F, dev_status, st);
+      so3k_launch_pair_records(D, w.g, ct, w.rec, st);
+      so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
     }
     PROF(CAT_AGGREGATE);
     so3k_launch_alpha_aggregate(D, w.g, xt, ct, w.proj, wst_t, wst_t + Pc * F, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
@@ -316,14 +321,18 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
     if (h->use_tc) {
       const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
       float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
+      so3k_launch_pair_records(D, w.g, ct, w.rec, st);
       if (w.wst_layers == 1) {         // filters not kept: recompute this layer's
-        so3k_launch_filter_tc(D, w.g, h->tf[t], ct, wst_t, dev_status, st);
-        so3k_launch_filter_tc(D, w.g, h->tg[t], ct, wst_t + Pc * F, dev_status, st);
+        so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
+        so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
       }
-      // q/k projection gradients + cutoff cotangent: one streaming pass over the filters
-      so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, wst_t + Pc * F, w.gproj, w.ebar, st);
-      // radial + l0-contraction cotangents
-      if (h->tc_b2) so3k_launch_edge_bwd2_tc(D, w.g, h->tf[t], h->tg[t], ct, w.proj, w.alphabar, w.gbar, w.ebar, dev_status, st);
+      const size_t Gst = (D.nl + 3) & ~3;
+      cudaMemsetAsync(w.ebar, 0, sizeof(float) * Pe * 2, st);
+      cudaMemsetAsync(w.gbar, 0, sizeof(float) * Pe * Gst, st);
+      // q/k projection gradients, cutoff cotangent and the pairs' filter cotangents: one streaming pass per block
+      so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, w.gproj, w.ebar, w.wbar, st);
+      // radial + l0-contraction cotangents (added onto the canonical edge of each pair)
+      if (h->tc_b2) so3k_launch_edge_bwd2_tc(D, w.g, h->tf[t], h->tg[t], w.rec, w.wbar, w.gbar, w.ebar, dev_status, st);
       else so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 2, w.gproj, w.gbar, w.ebar, st);
     } else {
       so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);

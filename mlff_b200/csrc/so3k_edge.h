@@ -38,9 +38,11 @@ size_t so3k_edge_tc_image_bytes(const So3kDims& D);   // per block
 void so3k_edge_tc_build(const So3kDims& D, const float* params, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
                         const EdgeBlockW& simt, cudaStream_t st);
 // filter w[pair][F] of one block for every canonical (undirected) pair of the list
-void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* chi, float* wst, int* status,
+// rec[pair capacity][8]: per canonical pair (d, l0 contractions of chi_j - chi_i) of the current layer
+void so3k_launch_pair_records(const So3kDims& D, const Graph& g, const float* chi, float* rec, cudaStream_t st);
+void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, int* status,
                            cudaStream_t st);
-// radial cotangent ebar[e][0] and l0-contraction cotangent gbar of both blocks (written on the canonical edge of a pair)
-void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                              const float* proj, const float* alphabar, float* gbar, float* ebar, int* status,
-                              cudaStream_t st);
+// radial cotangent ebar[e][0] and l0-contraction cotangent gbar of both blocks, added onto the canonical edge of each
+// pair (the arrays must be zero on entry); wbar: pair-indexed filter cotangents from so3k_launch_qk_bwd_stream
+void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,
+                              const float* wbar, float* gbar, float* ebar, int* status, cudaStream_t st);

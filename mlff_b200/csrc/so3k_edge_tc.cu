@@ -227,67 +227,58 @@ __device__ unsigned long long g_tc_phase[3][16];
     tc::fence_after_sync();                                    \
   }
 
-// Per-edge metadata of one tile row, prefetched one tile ahead (global loads with a dependent chain: row/col -> chi rows)
+// Per-pair record (k_pair_records, once per layer): [d, g_0 .. g_{nl-1}, 0 ...] = distance and the l0 contractions of
+// (chi_j - chi_i) -- everything the filter MLP needs about a pair, so the tensor-core kernels read one contiguous
+// 32-byte record per row (prefetched one tile ahead) instead of chasing row/col -> chi rows.
+constexpr int REC = 8;                                   // floats per record (nl <= 7)
+__global__ void k_pair_records(So3kDims D, int pair_cap, const int* __restrict__ n_canon, const int* __restrict__ canon,
+                               const int* __restrict__ row, const int* __restrict__ col, const float4* __restrict__ geom,
+                               const float* __restrict__ chi, float* __restrict__ rec) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = (*n_canon < pair_cap) ? *n_canon : pair_cap;
+  if (c >= nv) return;
+  const int e = canon[c];
+  const int i = row[e], j = col[e];
+  float v[REC];
+#pragma unroll
+  for (int l = 0; l < REC; ++l) v[l] = 0.f;
+  v[0] = geom[e].w;
+  for (int k = 0; k < D.M; ++k) {
+    const float cd = chi[(size_t)j * D.M + k] - chi[(size_t)i * D.M + k];
+    const float cc = cd * cd * D.m_cg[k];
+    const int sg = D.m_seg[k];
+#pragma unroll
+    for (int l = 0; l < REC - 1; ++l) v[1 + l] += (l == sg) ? cc : 0.f;
+  }
+  float4* dst = reinterpret_cast<float4*>(rec + (size_t)c * REC);
+  dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+  dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 struct TileMeta {
-  int i, j;
-  int e, re;                    // sorted edge index of this row and of its reverse (canonical-pair tiles)
+  int e;                        // canonical sorted edge of this row's pair (loaded only when `canon` is given)
   float d;
   float gl[SO3K_MAXDEG];        // l0 contraction of the chi difference (only meaningful for column quarter 0)
 };
-// level 1: receiver / sender / distance (issued early) ; level 2: chi rows -> l0 contraction (issued one GEMM later)
-__device__ __forceinline__ TileMeta tc_prefetch_meta1(int r, int qq, int e0, int nv, bool comp, const int* __restrict__ row,
-                                                      const int* __restrict__ col, const float4* __restrict__ geom,
-                                                      const int* __restrict__ canon = nullptr,
-                                                      const int* __restrict__ rev = nullptr) {
+__device__ __forceinline__ TileMeta tc_prefetch_meta(int r, int qq, int e0, int nv, bool comp, const float* __restrict__ rec,
+                                                     const int* __restrict__ canon = nullptr) {
   TileMeta m;
-  m.i = 0; m.j = 0; m.d = 0.f; m.e = 0; m.re = 0;
+  m.e = 0; m.d = 0.f;
 #pragma unroll
   for (int l = 0; l < SO3K_MAXDEG; ++l) m.gl[l] = 0.f;
-  int e = e0 + r;
-  if (comp && e < nv) {
-    if (canon) {                 // rows are canonical edges: one per undirected pair
-      e = canon[e];
-      if (rev) m.re = rev[e];
-    } else if (rev && qq == 3) {
-      m.re = rev[e];             // backward part 1: quarter 3 stages alphabar of the reverse edge
-    }
-    m.e = e;
-    m.d = geom[e].w;
+  const int c = e0 + r;
+  if (comp && c < nv) {
     if (qq == 0) {
-      m.i = row[e];
-      m.j = col[e];
+      const float4 a = *reinterpret_cast<const float4*>(rec + (size_t)c * REC);
+      const float4 b = *reinterpret_cast<const float4*>(rec + (size_t)c * REC + 4);
+      m.d = a.x;
+      m.gl[0] = a.y; m.gl[1] = a.z; m.gl[2] = a.w; m.gl[3] = b.x; m.gl[4] = b.y; m.gl[5] = b.z; m.gl[6] = b.w;
+      if (canon) m.e = canon[c];
+    } else {
+      m.d = rec[(size_t)c * REC];
     }
   }
   return m;
-}
-__device__ __forceinline__ void tc_prefetch_meta2(const So3kDims& D, TileMeta& m, int r, int qq, int e0, int nv, bool comp,
-                                                  const float* __restrict__ chi) {
-  if (comp && qq == 0 && e0 + r < nv) {
-    for (int k = 0; k < D.M; ++k) {
-      const float c = chi[(size_t)m.j * D.M + k] - chi[(size_t)m.i * D.M + k];
-      const float cc = c * c * D.m_cg[k];
-      const int sg = D.m_seg[k];
-#pragma unroll
-      for (int l = 0; l < SO3K_MAXDEG; ++l) m.gl[l] += (l == sg) ? cc : 0.f;
-    }
-  }
-}
-__device__ __forceinline__ TileMeta tc_prefetch_meta(const So3kDims& D, int r, int qq, int e0, int nv, bool comp,
-                                                     const int* __restrict__ row, const int* __restrict__ col,
-                                                     const float4* __restrict__ geom, const float* __restrict__ chi,
-                                                     const int* __restrict__ canon = nullptr,
-                                                     const int* __restrict__ rev = nullptr) {
-  TileMeta m = tc_prefetch_meta1(r, qq, e0, nv, comp, row, col, geom, canon, rev);
-  tc_prefetch_meta2(D, m, r, qq, e0, nv, comp, chi);
-  return m;
-}
-
-// L2 prefetch of the F-wide segment [off, off + F) of atom `a`'s projection row (one 128-byte line per instruction)
-__device__ __forceinline__ void tc_l2_prefetch_seg(const float* __restrict__ proj, size_t F5, int a, int off, int F) {
-  const char* p = reinterpret_cast<const char*>(proj + (size_t)a * F5 + off);
-  const char* end = p + 4 * F;
-  p = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127);
-  for (; p < end; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // S0: publish the tile's metadata to shared memory and write the radial-basis operand image(s).
@@ -298,7 +289,6 @@ __device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, c
   const bool valid = r < ne;
   const float d = m.d;
   if (qq == 0) {
-    S.s_i[r] = m.i; S.s_j[r] = m.j;
     S.s_phi[r] = valid ? cutoff_fast(d, D.r_cut) : 0.f;
 #pragma unroll
     for (int l = 0; l < SO3K_MAXDEG; ++l)
@@ -388,8 +378,7 @@ __device__ __forceinline__ void tc_epilogue1(const So3kDims& D, const TcDims& T,
 // lives in the streaming kernels of so3k_agg.cu, which read w back through the pair index of an edge.
 __global__ void __launch_bounds__(NT, 1)
 k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restrict__ n_canon,
-            const int* __restrict__ canon, const int* __restrict__ row, const int* __restrict__ col,
-            const float4* __restrict__ geom, const float* __restrict__ chi, const unsigned char* __restrict__ img,
+            const float* __restrict__ rec, const unsigned char* __restrict__ img,
             const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
             float* __restrict__ wst, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -423,7 +412,12 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
   const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;    // this thread's D2 chunks
 
   uint32_t it = 0;
-  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, canon);
+  // epilogue-2 staging tile [TM][F] fp32 at the END of the operand region (the radial-basis images of the next tile
+  // live at its start), drained to HBM by one bulk copy per tile
+  const uint32_t stage_off = 2 * T.szA1 - (uint32_t)TM * F * 4u;         // (KC >= F: the tile always fits)
+  float* stage = reinterpret_cast<float*>(smem + T.off_A1 + stage_off);
+  const bool stage_hits_a0 = stage_off < 2 * T.szA0;                       // small F: S0 itself would overwrite the tile
+  TileMeta meta = tc_prefetch_meta(r, qq, blockIdx.x * TM, nv, comp, rec);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;                     // block-uniform
@@ -431,7 +425,14 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
     const uint32_t par = it & 1u;
     long long t_prev_ = TC_TIMING ? clock64() : 0;
 
+    // the previous tile's bulk store must have finished READING the staging tile before it is overwritten (by
+    // epilogue 1; by S0 already when the radial-basis images overlap it)
+    if (stage_hits_a0) {
+      if (tid == ISSUER) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+    }
     if (comp) tc_tile_s0<false>(D, T, S, r, qq, ne, meta, nullptr, nullptr);
+    if (!stage_hits_a0 && tid == ISSUER) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     TC_PHASE(0, 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -442,15 +443,13 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
       tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc);
       tc::commit(&bars[0]);
     }
-    // level-1 metadata of this CTA's next tile: a dependent load chain (canon -> row/col/geom -> chi rows) that is
-    // started here and finished (level 2) by the column quarter that has the lightest epilogue-1 share
+    // records of this CTA's next tile (consumed by its S0)
     const int e0_next = (tile + (int)gridDim.x) * TM;
-    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom, canon);
+    TileMeta meta_nx = tc_prefetch_meta(r, qq, e0_next, nv, comp, rec);
     TC_PHASE(0, 2);
     TC_WAIT_OR_BAIL(&bars[0], par);
     TC_PHASE(0, 3);
     if (comp) tc_epilogue1(D, T, S, tD1, lane_sel, r, qq);
-    tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
     TC_PHASE(0, 4);
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -465,10 +464,10 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
     TC_PHASE(0, 6);
     TC_WAIT_OR_BAIL(&bars[1], par);
     TC_PHASE(0, 7);
-    // ---- epilogue 2: w = D2 + b2 -> HBM (streaming stores; row c of the pair-indexed filter array) -------------------
+    // ---- epilogue 2: w = D2 + b2 -> staging tile (row stride F: F mod 32 == 4 keeps the 16-byte row-per-lane stores
+    //      conflict-free) -> one bulk copy to the tile's contiguous block of pair rows ----------------------------------
     if (comp) {
-      const bool rowok = r < ne;             // every lane takes part in the warp-collective TMEM loads
-      float* wrow = wst + (size_t)(e0 + (rowok ? r : 0)) * F;
+      float* srow = stage + (size_t)r * F;
       for (int cb = cbeg; cb < cend; cb += 2) {
         float v[2][8];
 #pragma unroll
@@ -478,46 +477,52 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int c0 = (cb + u) * 8;
-          if (rowok && cb + u < cend && c0 < F) {
+          if (cb + u < cend && c0 < F) {
             if (c0 + 8 <= F) {
               const float4 ba = *reinterpret_cast<const float4*>(S.b2p + c0);
               const float4 bb = *reinterpret_cast<const float4*>(S.b2p + c0 + 4);
-              __stcs(reinterpret_cast<float4*>(wrow + c0),
-                     make_float4(v[u][0] + ba.x, v[u][1] + ba.y, v[u][2] + ba.z, v[u][3] + ba.w));
-              __stcs(reinterpret_cast<float4*>(wrow + c0 + 4),
-                     make_float4(v[u][4] + bb.x, v[u][5] + bb.y, v[u][6] + bb.z, v[u][7] + bb.w));
+              *reinterpret_cast<float4*>(srow + c0) = make_float4(v[u][0] + ba.x, v[u][1] + ba.y, v[u][2] + ba.z, v[u][3] + ba.w);
+              *reinterpret_cast<float4*>(srow + c0 + 4) =
+                  make_float4(v[u][4] + bb.x, v[u][5] + bb.y, v[u][6] + bb.z, v[u][7] + bb.w);
             } else {
 #pragma unroll
               for (int q = 0; q < 8; ++q)
-                if (c0 + q < F) wrow[c0 + q] = v[u][q] + S.b2p[c0 + q];
+                if (c0 + q < F) srow[c0 + q] = v[u][q] + S.b2p[c0 + q];
             }
           }
         }
       }
     }
     TC_PHASE(0, 8);
-    if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[0][15], 1ull);
-    // no barrier here: the next tile's S0 only overwrites buffers whose last readers (GEMM2 via bars[1], epilogue 1 via
-    // the barrier before GEMM2) are already complete, and the next GEMM2 is issued behind the next tile's barriers
+    tc::fence_async_smem();                  // staging tile (generic proxy) -> visible to the bulk-copy engine
     tc::fence_before_sync();
+    __syncthreads();
+    if (tid == ISSUER) {
+      const uint32_t bytes = (uint32_t)ne * (uint32_t)F * 4u;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(wst + (size_t)e0 * F),
+                   "r"(tc::smem_u32(stage)), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    TC_PHASE(0, 9);
+    if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[0][15], 1ull);
   }
+  if (tid == ISSUER) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // Backward part 2: radial cotangent and l0-contraction cotangent of one filter block.
-//   wbar[e][f] = alphabar[e][h(f)] phi q_i[f] k_j[f] / sqrt(d_h)      (built straight into an A-operand image)
+// Rows are canonical pairs; the pair's filter cotangent wbar[c][f] comes from k_qk_bwd_stream as a contiguous tile.
 //   hbar = wbar @ W2c^T                                                 (GEMM3: the W2c image consumed MN-major)
 //   dbar_rad[e] += sum_c hbar[c] silu'(a1[c]) (rbf'(d) @ W1)[c]         (a1 and the forward-mode term from 2 GEMM1s)
 //   gbar[e][l]  += sum_c hbar_s[c] silu'(a_s[c]) Ws1[l][c]
 __global__ void __launch_bounds__(NT, 1)
-k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, const int* __restrict__ n_canon,
-               const int* __restrict__ canon, const int* __restrict__ rev, const int* __restrict__ row,
-               const int* __restrict__ col, const float4* __restrict__ geom,
-               const float* __restrict__ chi, const float* __restrict__ proj, const unsigned char* __restrict__ img,
+k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const int* __restrict__ n_canon,
+               const int* __restrict__ canon, const float* __restrict__ rec, const unsigned char* __restrict__ img,
                const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
-               const float* __restrict__ alphabar, float* __restrict__ gbar, float* __restrict__ ebar,
+               const float* __restrict__ wbar, float* __restrict__ gbar, float* __restrict__ ebar,
                int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[2];
@@ -528,13 +533,6 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const int r = 32 * (warp & 3) + lane;
   const int qq = comp ? (warp >> 2) : 0;
   const int F = D.F, Fs = D.Fs;
-  const int heads = blk ? D.nl : D.H;
-  const int dhd = F / heads;
-  const int aoff = blk ? D.H : 0;
-  const int qoff = blk ? F : 0;
-  const int koff = 2 * F + (blk ? F : 0);
-  const size_t F5 = 5 * (size_t)F;
-  const float inv = 1.0f / sqrtf((float)dhd);
   TcSmem S = tc_carve(smem, T, D);
   // four radial-basis images packed at the start of the region: rbf hi | rbf lo | rbf' hi | rbf' lo
   S.A0hi = reinterpret_cast<unsigned char*>(S.region);
@@ -545,9 +543,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const uint32_t szWb = (uint32_t)(TM / 8) * sboWb;
   unsigned char* Wbhi = reinterpret_cast<unsigned char*>(S.region);   // aliases the rbf images: dead once the GEMM1s are done
   unsigned char* Wblo = Wbhi + szWb;
-  float* s_ab = S.s_part;                       // [TM][8]  alphabar[e] * phi / sqrt(dh) per head
-  float* s_red = S.s_part + TM * 8;             // [TM][8]  cross-quarter reduction (dbar, gbar_l)
-  float* s_abr = S.s_part + TM * 16;            // [TM][8]  alphabar[rev e] * phi / sqrt(dh)
+  float* s_red = S.s_part;                      // [TM][8]  cross-quarter reduction (dbar, gbar_l)
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -555,7 +551,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
     tc::mbar_init(&bars[1], 1);
     tc::mbar_fence_init();
   }
-  tc_setup(smem, T, D, S, dhd, img, bias_g, Ws1_g, bs1_g);
+  tc_setup(smem, T, D, S, F, img, bias_g, Ws1_g, bs1_g);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -565,7 +561,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
   const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
   const uint32_t idesc3 = tc::make_idesc_bf16(TM, T.KC, 0, 1);     // B = W2c image read MN-major
-  const int nv = *n_canon;                      // rows of this kernel = canonical edges (undirected pairs): the filter
+  const int nv = (*n_canon < pair_cap) ? *n_canon : pair_cap;   // rows = canonical edges (undirected pairs): the filter
   const int nchunkF = T.Fp / 8;                 // and everything downstream of it are identical for e and rev e, and
   const int nchunkK = T.KC / 8;                 // only dbar_e + dbar_rev / gbar_e + gbar_rev enter the forces
   // this thread's hidden-column chunks: a quarter of the radial range plus every 4th chunk beyond it (the spherical
@@ -574,29 +570,16 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
   const int nmine = comp ? (kce - kcb) + ((nchunkK - nchunkF - qq + 3) / 4) : 0;
 
   uint32_t it = 0;
-  TileMeta meta = tc_prefetch_meta(D, r, qq, blockIdx.x * TM, nv, comp, row, col, geom, chi, canon, rev);
+  TileMeta meta = tc_prefetch_meta(r, qq, blockIdx.x * TM, nv, comp, rec, canon);
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int e0 = tile * TM;
     if (e0 >= nv) break;
     const int ne = (nv - e0) < TM ? (nv - e0) : TM;
     const uint32_t par = it & 1u;
-    const int my_e = meta.e, my_re = meta.re;     // valid for r < ne
+    const int my_e = meta.e;                      // valid for r < ne
     long long t_prev_ = TC_TIMING ? clock64() : 0;
 
-    float abv[8];                                 // alphabar of e (quarter 1) / rev e (quarter 3): loaded before S0,
-    {                                             // staged after it (the latency hides behind the S0 arithmetic)
-      const bool okb = comp && (qq == 1 || qq == 3) && r < ne;
-      const int esrc = (qq == 1) ? my_e : my_re;
-#pragma unroll
-      for (int h = 0; h < 8; ++h) abv[h] = (okb && h < heads) ? alphabar[(size_t)esrc * Ast + aoff + h] : 0.f;
-    }
     if (comp) tc_tile_s0<true>(D, T, S, r, qq, ne, meta, A0dhi, A0dlo);
-    if (comp && (qq == 1 || qq == 3)) {
-      const float ph = (r < ne) ? cutoff_fast(meta.d, D.r_cut) * inv : 0.f;
-      float* dstab = ((qq == 1) ? s_ab : s_abr) + r * 8;
-      *reinterpret_cast<float4*>(dstab) = make_float4(abv[0] * ph, abv[1] * ph, abv[2] * ph, abv[3] * ph);
-      *reinterpret_cast<float4*>(dstab + 4) = make_float4(abv[4] * ph, abv[5] * ph, abv[6] * ph, abv[7] * ph);
-    }
     if (comp && qq == 2) {
 #pragma unroll
       for (int h = 0; h < 8; ++h) s_red[r * 8 + h] = 0.f;
@@ -612,61 +595,43 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       tc_issue_gemm(tD1p, A0dhi, A0dlo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
       tc::commit(&bars[0]);
     }
-    // level-1 metadata of this CTA's next tile (consumed after GEMM3 is issued)
+    // records of this CTA's next tile (consumed by its S0)
     const int e0_next = (tile + (int)gridDim.x) * TM;
-    TileMeta meta_nx = tc_prefetch_meta1(r, qq, e0_next, nv, comp, row, col, geom, canon, rev);
-    // ---- wbar image: work item = (row group of 8 rows, column group of 4 chunks): lane -> (row = lane / 4, chunk = lane % 4)
-    //      two items per iteration: 16 independent 16-byte gathers in flight per lane
+    TileMeta meta_nx = tc_prefetch_meta(r, qq, e0_next, nv, comp, rec, canon);
+    // ---- wbar image from the tile's contiguous block of pair rows: work item = (8 rows, 4 chunks of 8 columns),
+    //      lane -> (row = lane / 4, chunk = lane % 4); the loads of all of a warp's items are issued before the GEMM1 wait
     const int ncg = (nchunkF + 3) / 4;
     const int nitems = 16 * ncg;
+    constexpr int MAXIT = 6;                      // items per warp: 16 * ceil(Fp / 32) / 16 <= 5 for Fp <= 144
+    float4 wa[MAXIT], wb2[MAXIT];
+#pragma unroll
+    for (int v = 0; v < MAXIT; ++v) {
+      const int item = warp + v * NW;
+      wa[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb2[v] = wa[v];
+      if (comp && item < nitems) {
+        const int rg = item / ncg, cg = item - rg * ncg;
+        const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
+        const int f0 = c * 8;
+        if (c < nchunkF && f0 < F && rr < ne) {
+          const float* src = wbar + (size_t)(e0 + rr) * F + f0;
+          wa[v] = __ldcs(reinterpret_cast<const float4*>(src));
+          if (f0 + 4 < F) wb2[v] = __ldcs(reinterpret_cast<const float4*>(src + 4));
+        }
+      }
+    }
     TC_PHASE(2, 2);
     TC_WAIT_OR_BAIL(&bars[0], par);
     TC_PHASE(2, 3);
-    for (int item0 = comp ? warp : nitems; item0 < nitems; item0 += 2 * NW) {
-      float4 g[2][8];
-      int rrs[2], cs[2];
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int item = item0 + v * NW;
+    for (int v = 0; v < MAXIT; ++v) {
+      const int item = warp + v * NW;
+      if (comp && item < nitems) {
         const int rg = item / ncg, cg = item - rg * ncg;
-        rrs[v] = (item < nitems) ? rg * 8 + (lane >> 2) : 0;
-        cs[v] = (item < nitems) ? cg * 4 + (lane & 3) : nchunkF;
-        const int f0 = cs[v] * 8;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) g[v][u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cs[v] < nchunkF && f0 < F) {
-          // both directions of the pair: e = (i <- j) uses q_i k_j, rev e = (j <- i) uses q_j k_i
-          const float* pi = proj + (size_t)S.s_i[rrs[v]] * F5 + f0;
-          const float* pj = proj + (size_t)S.s_j[rrs[v]] * F5 + f0;
-          g[v][0] = *reinterpret_cast<const float4*>(pi + qoff);
-          g[v][1] = *reinterpret_cast<const float4*>(pj + koff);
-          g[v][2] = *reinterpret_cast<const float4*>(pj + qoff);
-          g[v][3] = *reinterpret_cast<const float4*>(pi + koff);
-          if (f0 + 4 < F) {
-            g[v][4] = *reinterpret_cast<const float4*>(pi + qoff + 4);
-            g[v][5] = *reinterpret_cast<const float4*>(pj + koff + 4);
-            g[v][6] = *reinterpret_cast<const float4*>(pj + qoff + 4);
-            g[v][7] = *reinterpret_cast<const float4*>(pi + koff + 4);
-          }
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        if (cs[v] < nchunkF) {
-          const int f0 = cs[v] * 8;
-          const float fw[8] = {g[v][0].x * g[v][1].x, g[v][0].y * g[v][1].y, g[v][0].z * g[v][1].z, g[v][0].w * g[v][1].w,
-                               g[v][4].x * g[v][5].x, g[v][4].y * g[v][5].y, g[v][4].z * g[v][5].z, g[v][4].w * g[v][5].w};
-          const float bw[8] = {g[v][2].x * g[v][3].x, g[v][2].y * g[v][3].y, g[v][2].z * g[v][3].z, g[v][2].w * g[v][3].w,
-                               g[v][6].x * g[v][7].x, g[v][6].y * g[v][7].y, g[v][6].z * g[v][7].z, g[v][6].w * g[v][7].w};
-          const float* sab = s_ab + rrs[v] * 8;
-          const float* sabr = s_abr + rrs[v] * 8;
-          float wv[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int hq = S.s_head[f0 + q];
-            wv[q] = (f0 + q < F) ? fmaf(sab[hq], fw[q], sabr[hq] * bw[q]) : 0.f;
-          }
-          tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rrs[v], cs[v], sboWb), wv);
+        const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
+        if (c < nchunkF) {
+          const float wv[8] = {wa[v].x, wa[v].y, wa[v].z, wa[v].w, wb2[v].x, wb2[v].y, wb2[v].z, wb2[v].w};
+          tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rr, c, sboWb), wv);
         }
       }
     }
@@ -699,21 +664,13 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
       gb[l] = 0.f;
     }
-    // overlapping GEMM3: pull the next tile's gather rows into L2, finish its metadata
-    {
-      const int prev_i = __shfl_up_sync(0xffffffffu, meta_nx.i, 1);
-      if (comp && qq == 0 && e0_next + r < nv) {
-        tc_l2_prefetch_seg(proj, F5, meta_nx.j, koff, F);
-        tc_l2_prefetch_seg(proj, F5, meta_nx.j, qoff, F);
-        if (lane == 0 || prev_i != meta_nx.i) {
-          tc_l2_prefetch_seg(proj, F5, meta_nx.i, koff, F);
-          tc_l2_prefetch_seg(proj, F5, meta_nx.i, qoff, F);
-        }
-      }
-      if (comp && (qq == 1 || qq == 3) && e0_next + r < nv)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(alphabar + (size_t)(qq == 1 ? meta_nx.e : meta_nx.re) * Ast + aoff));
+    // overlapping GEMM3: pull the next tile's filter-cotangent block (contiguous, TM * F floats) into L2
+    if (e0_next < nv) {
+      const int nrow = (nv - e0_next) < TM ? (nv - e0_next) : TM;
+      const char* pb = reinterpret_cast<const char*>(wbar + (size_t)e0_next * F);
+      const int nline = (nrow * F * 4 + 127) / 128;
+      for (int k = tid; k < nline; k += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)k * 128));
     }
-    tc_prefetch_meta2(D, meta_nx, r, qq, e0_next, nv, comp, chi);
     meta = meta_nx;
     TC_PHASE(2, 6);
     TC_WAIT_OR_BAIL(&bars[1], par);
@@ -762,15 +719,12 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int blk, int Ast, int Gst, int n_tiles, con
       __syncthreads();
       TC_PHASE(2, 9);
       if (comp && qq == 0 && r < ne) {
-        // the pair's totals go to the canonical edge; its reverse gets zeros (only the sums enter chi-bar and F)
-        const size_t e = (size_t)my_e, re = (size_t)my_re;
-        const float db = s_red[r * 8 + 0];
-        // (second block: fire-and-forget reductions instead of read-modify-write round trips)
-        if (blk == 0) { ebar[2 * e] = db; ebar[2 * re] = 0.f; } else atomicAdd(&ebar[2 * e], db);
-        for (int l = 0; l < D.nl; ++l) {
-          const float gsum = s_red[r * 8 + 1 + l];
-          if (blk == 0) { gbar[e * Gst + l] = gsum; gbar[re * Gst + l] = 0.f; } else atomicAdd(&gbar[e * Gst + l], gsum);
-        }
+        // the pair's totals go to the canonical edge; its reverse keeps the zeros of the memset (only the sums
+        // ebar[e] + ebar[rev e], gbar[e] + gbar[rev e] enter chi-bar and the forces).  Fire-and-forget reductions: both
+        // blocks add into the same slots.
+        const size_t e = (size_t)my_e;
+        atomicAdd(&ebar[2 * e], s_red[r * 8 + 0]);
+        for (int l = 0; l < D.nl; ++l) atomicAdd(&gbar[e * Gst + l], s_red[r * 8 + 1 + l]);
       }
     }
     __syncthreads();
@@ -826,7 +780,15 @@ static int tc_grid(int n_tiles, const TcDims& T) {
 }
 
 // filter of one block for every canonical pair -> wst[pair][F]
-void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* chi, float* wst, int* status,
+// per-pair records of the current layer (distance + l0 contractions of the chi differences) -> rec[pair capacity][8]
+void so3k_launch_pair_records(const So3kDims& D, const Graph& g, const float* chi, float* rec, cudaStream_t st) {
+  if (g.Pt <= 0) return;
+  const int pair_cap = so3k_pair_capacity(g.Pt);
+  so3k_count_launch();
+  k_pair_records<<<so3k_cdiv(pair_cap, 256), 256, 0, st>>>(D, pair_cap, g.n_canon, g.canon, g.row, g.col, g.geom, chi, rec);
+}
+
+void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, int* status,
                            cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
@@ -835,27 +797,26 @@ void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W,
   int grid = tc_grid(n_tiles, T);
   cudaFuncSetAttribute(k_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total + 1024);
   so3k_count_launch();
-  k_filter_tc<<<grid, NT, T.total + 1024, st>>>(D, T, n_tiles, pair_cap, g.n_canon, g.canon, g.row, g.col, g.geom, chi, W.img,
-                                                 W.bias, W.Ws1, W.bs1, wst, status);
+  k_filter_tc<<<grid, NT, T.total + 1024, st>>>(D, T, n_tiles, pair_cap, g.n_canon, rec, W.img, W.bias, W.Ws1, W.bs1, wst,
+                                                 status);
 }
 
-// radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of both filter blocks
-void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* chi,
-                              const float* proj, const float* alphabar, float* gbar, float* ebar, int* status,
-                              cudaStream_t st) {
+// radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of both filter blocks, ADDED to zero-initialised
+// arrays; wbar = [block][pair capacity][F] filter cotangents from k_qk_bwd_stream
+void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,
+                              const float* wbar, float* gbar, float* ebar, int* status, cudaStream_t st) {
   if (g.Pt <= 0) return;
   TcDims T = make_tc_dims(D);
-  int Ast = (D.H + D.nl + 3) & ~3;
   int Gst = (D.nl + 3) & ~3;
-  int n_tiles = so3k_cdiv(so3k_pair_capacity(g.Pt), TM);
+  const int pair_cap = so3k_pair_capacity(g.Pt);
+  int n_tiles = so3k_cdiv(pair_cap, TM);
   int grid = tc_grid(n_tiles, T);
   cudaFuncSetAttribute(k_edge_bwd2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total + 1024);
   for (int blk = 0; blk < 2; ++blk) {
     const TcBlockW& W = blk ? Wg : Wf;
     so3k_count_launch();
-    k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, blk, Ast, Gst, n_tiles, g.n_canon, g.canon, g.rev, g.row, g.col,
-                                                      g.geom, chi, proj, W.img, W.bias, W.Ws1, W.bs1, alphabar, gbar, ebar,
-                                                      status);
+    k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, Gst, n_tiles, pair_cap, g.n_canon, g.canon, rec, W.img, W.bias, W.Ws1, W.bs1, wbar + (size_t)blk * pair_cap * D.F, gbar,
+                                                      ebar, status);
   }
 }
 extern "C" void so3k_tc_phase_dump(void) {
@@ -883,7 +844,8 @@ bool so3k_edge_tc_supported(const So3kDims&) { return false; }
 size_t so3k_edge_tc_image_bytes(const So3kDims&) { return 0; }
 void so3k_edge_tc_build(const So3kDims&, const float*, const BlockParams&, unsigned char*, TcBlockW*, const EdgeBlockW&,
                         cudaStream_t) {}
+void so3k_launch_pair_records(const So3kDims&, const Graph&, const float*, float*, cudaStream_t) {}
 void so3k_launch_filter_tc(const So3kDims&, const Graph&, const TcBlockW&, const float*, float*, int*, cudaStream_t) {}
 void so3k_launch_edge_bwd2_tc(const So3kDims&, const Graph&, const TcBlockW&, const TcBlockW&, const float*, const float*,
-                              const float*, float*, float*, int*, cudaStream_t) {}
+                              float*, float*, int*, cudaStream_t) {}
 #endif

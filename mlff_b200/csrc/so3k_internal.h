@@ -85,7 +85,7 @@ void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float*
                                  const float* wst_f, const float* wst_g, float* alpha, float* x1, float* chi1,
                                  cudaStream_t st);
 void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
-                               const float* alphabar, const float* wst_f, const float* wst_g, float* gproj, float* ebar,
+                               const float* alphabar, const float* wst, float* gproj, float* ebar, float* wbar,
                                cudaStream_t st);
 void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,
                          const float* chibar1, float* chibar /* out */, cudaStream_t st);
