@@ -324,37 +324,67 @@ def run_ours(args, w):
         nl_ = len(w['degrees'])
         Fd, K = w['F'], 32
         p_rank = getattr(step_resident, 'p_local', n_edges)        # edges this rank's kernels processed (owned + mirror)
-        flop_block = 2.0 * p_rank * (K * Fd + Fd * Fd + nl_ * (Fd // 4) + (Fd // 4) * Fd)     # SURVEY 8(d), per block
-        # dominant kernel: the edge backward (recompute + transposed GEMMs).  Algorithmic FLOPs per launch:
-        # forward filter (both blocks) + W2^T GEMM + forward-mode radial GEMM + sph-branch transposes
-        #   = 2 blocks x [fwd + (F*KC) + (K*F)] ~ 2 x flop_block x (1 + (F^2+F*F/4+K*F)/(K*F+F^2+...)) -- we count
-        # conservatively: bwd launch = 2 x (2 x flop_block) ; fwd launch = 2 x flop_block.
-        ms_bwd, n_bwd = prof['edge_bwd']
-        ms_fwd, n_fwd = prof['edge_fwd']
-        # a profiler scope = one layer's edge work: forward = 2 launches (fb, gb) in tensor mode / 1 launch in SIMT mode;
-        # backward = 4 launches (2 blocks x parts 1,2) / 1 launch (+ k_edge_finish).  Algorithmic FLOPs per scope:
-        # forward 2 x flop_block ; backward ~ 2 x forward (recompute + transposed GEMMs), as in DESIGN.md section 4.
-        dom = 'edge_bwd' if ms_bwd >= ms_fwd else 'edge_fwd'
-        flops_scope = (4.0 if dom == 'edge_bwd' else 2.0) * flop_block
-        ms_scope = (ms_bwd / max(n_bwd, 1)) if dom == 'edge_bwd' else (ms_fwd / max(n_fwd, 1))
-        tf = flops_scope / (ms_scope * 1e-3) / 1e12 if ms_scope > 0 else 0.0
-        peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
-        kname = {('edge_bwd', True): 'k_edge_tc<1> + k_edge_bwd2_tc (per layer: 2 blocks x 2 parts)',
-                 ('edge_fwd', True): 'k_edge_tc<0> (per layer: 2 blocks)',
-                 ('edge_bwd', False): 'k_edge_bwd', ('edge_fwd', False): 'k_edge_fwd'}[(dom, bool(args.tensor))]
-        roof = {'kernel': kname, 'bound': 'tensor', 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': tf / peak_tf, 'traffic': None,
-                'peak_kind': f'{pk_kind} sustained bf16 (kernel timed inside a long step)',
-                'ms_per_layer_scope': ms_scope, 'algorithmic_flops_per_scope': flops_scope,
-                'note': 'algorithmic fp32-equivalent FLOPs; the split-bf16 scheme issues 3 MMAs per product on padded shapes',
-                'share_of_step': (ms_bwd if dom == 'edge_bwd' else ms_fwd) / (ms_total if ms_total > 0 else 1.0)}
-        # HBM-bound side kernels (compulsory-traffic bytes): aggregation
-        ms_agg, n_agg = prof['aggregate']
+        Fs_ = Fd // 4
+        M_ = sum(2 * l + 1 for l in w['degrees'])
+        Ast_ = (4 + nl_ + 3) // 4 * 4
         n_rank = getattr(step_resident, 'n_local', N)
-        agg_bytes = (4 * 8 + 4 + 16) * p_rank + (8 * Fd + 8 * sum(2 * l + 1 for l in w['degrees']) + 4) * n_rank + 4 * Fd * n_rank
-        agg = {'kernel': 'k_aggregate', 'bound': 'hbm', 'achieved': agg_bytes / (ms_agg / max(n_agg, 1) * 1e-3) / 1e9 if ms_agg > 0 else 0.0,
-               'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
-        agg['frac'] = agg['achieved'] / agg['peak']
+        flop_unit = 2.0 * (K * Fd + Fd * Fd + nl_ * Fs_ + Fs_ * Fd)          # one filter block, one edge
+        peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+        peak_bw = pk['hbm_gbs']
+
+        def tensor_roof(kernel, cat, flops_scope, note):
+            ms, n = prof[cat]
+            ms_scope = ms / max(n, 1)
+            tf = flops_scope / (ms_scope * 1e-3) / 1e12 if ms_scope > 0 else 0.0
+            return {'kernel': kernel, 'bound': 'tensor', 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                    'frac': tf / peak_tf, 'traffic': None,
+                    'peak_kind': f'{pk_kind} sustained bf16 (kernel timed inside a long step)',
+                    'ms_per_layer_scope': ms_scope, 'algorithmic_flops_per_scope': flops_scope, 'note': note,
+                    'share_of_step': ms / (ms_total if ms_total > 0 else 1.0)}
+
+        def hbm_roof(kernel, cat, bytes_scope, note):
+            ms, n = prof[cat]
+            ms_scope = ms / max(n, 1)
+            gbs = bytes_scope / (ms_scope * 1e-3) / 1e9 if ms_scope > 0 else 0.0
+            return {'kernel': kernel, 'bound': 'hbm', 'achieved': gbs, 'peak': peak_bw, 'unit': 'GB/s',
+                    'frac': gbs / peak_bw, 'traffic': None, 'peak_kind': f'{pk_kind} HBM copy bandwidth',
+                    'ms_per_layer_scope': ms_scope, 'algorithmic_bytes_per_scope': bytes_scope, 'note': note,
+                    'share_of_step': ms / (ms_total if ms_total > 0 else 1.0)}
+
+        if args.tensor:
+            # tensor mode works on undirected pairs (the filter is symmetric): units = p_rank / 2 pairs, 2 blocks per layer
+            n_pairs = p_rank / 2.0
+            split = 'algorithmic fp32-equivalent FLOPs; the split-bf16 scheme issues 3 MMAs per product on padded shapes'
+            roofs = [
+                tensor_roof('k_filter_tc (per layer: 2 blocks)', 'edge_fwd', 2.0 * n_pairs * flop_unit, split),
+                tensor_roof('k_edge_bwd2_tc (per layer: 2 blocks)', 'edge_bwd',
+                            2.0 * n_pairs * 2.0 * (2 * K * Fd + Fd * (Fd + Fs_) + nl_ * Fs_),
+                            split + '; two radial-basis GEMMs + the W2^T GEMM + the l0 transposes per pair'),
+                hbm_roof('k_alpha_aggregate', 'aggregate',
+                         n_pairs * 8 * Fd + n_rank * (5 * 4 * Fd + 8 * Fd + 8 * M_) + p_rank * (4 * Ast_ + 8 + 16),
+                         'compulsory bytes: both filters once per pair, 5 projection rows + x/chi in and out per atom, '
+                         'alpha out + (col, pid, geom) per edge; the sender-row gathers are served by L2'),
+                hbm_roof('k_qk_bwd_stream (per layer: 2 blocks)', 'qk_stream',
+                         n_pairs * 16 * Fd + n_rank * 32 * Fd + p_rank * (8 * Ast_ + 4 + 12 + 16),
+                         'compulsory bytes: filters in + filter cotangents out once per pair, q/k rows in + their '
+                         'gradients out per atom, alphabar + alpha in, ebar out, (col, rev, pid, geom) per edge'),
+                hbm_roof('k_alpha_bwd', 'alpha_bwd',
+                         n_rank * (4 * Fd * 3 + 8 * M_) + p_rank * (4 * 4 + 4 * Ast_ + 8 + 16),
+                         'compulsory bytes: v and xbar1 rows in, v gradient out per atom; alpha (reverse edge) in, '
+                         'alphabar out, (col, rev, geom) per edge'),
+            ]
+        else:
+            roofs = [
+                tensor_roof('k_edge_bwd', 'edge_bwd', 4.0 * p_rank * flop_unit,
+                            'fp32 FMA on the CUDA cores, reported against the bf16 tensor peak; backward ~ 2 x forward'),
+                tensor_roof('k_edge_fwd', 'edge_fwd', 2.0 * p_rank * flop_unit,
+                            'fp32 FMA on the CUDA cores, reported against the bf16 tensor peak'),
+                hbm_roof('k_aggregate', 'aggregate',
+                         (4 * 8 + 4 + 16) * p_rank + (8 * Fd + 8 * M_ + 4) * n_rank + 4 * Fd * n_rank,
+                         'compulsory bytes (DESIGN.md)'),
+            ]
+        roofs.sort(key=lambda r: -r['share_of_step'])
+        roof, agg = roofs[0], roofs[1:]          # `roofline` = the kernel with the largest share of the step
         # CPU baseline: bounded sample, all host threads
         threads = os.cpu_count() or 1
         cpu = None
@@ -383,7 +413,7 @@ def run_ours(args, w):
                            'l2': 'working set (edge + node arrays) larger than the 126 MB L2' if N >= 50_000 else
                                  'working set fits in L2 (latency/L2-bound configuration)'},
                 'e2e': {'value': e2e_val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_aggregate': agg,
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'roofline_others': agg,
                 'cpu_baseline': cpu,
                 'kernel_ms_per_step': {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
                 'energy_check': float(res['energy']),

@@ -18,11 +18,14 @@ void so3k_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 
-enum { CAT_GRAPH = 0, CAT_EMBED, CAT_NODE_PROJ, CAT_EDGE_FWD, CAT_AGGREGATE, CAT_INTERACTION, CAT_READOUT,
-       CAT_INTERACTION_BWD, CAT_ALPHA_BWD, CAT_EDGE_BWD, CAT_CHI_BWD, CAT_NODE_PROJ_BWD, CAT_FORCES, CAT_COUNT };
+// edge_fwd: filter kernels (tensor mode) / k_edge_fwd ; aggregate: k_alpha_aggregate (tensor mode) / k_aggregate ;
+// edge_bwd: k_edge_bwd2_tc (tensor mode) / k_edge_bwd ; pair_records and qk_stream exist in tensor mode only
+enum { CAT_GRAPH = 0, CAT_EMBED, CAT_NODE_PROJ, CAT_PAIR_RECORDS, CAT_EDGE_FWD, CAT_AGGREGATE, CAT_INTERACTION, CAT_READOUT,
+       CAT_INTERACTION_BWD, CAT_ALPHA_BWD, CAT_FILTER_RECOMPUTE, CAT_QK_STREAM, CAT_EDGE_BWD, CAT_EDGE_FINISH, CAT_CHI_BWD,
+       CAT_NODE_PROJ_BWD, CAT_FORCES, CAT_COUNT };
 const char* const kCatNames =
-    "graph,embed,node_proj,edge_fwd,aggregate,interaction,readout,interaction_bwd,alpha_bwd,edge_bwd,chi_bwd,"
-    "node_proj_bwd,forces";
+    "graph,embed,node_proj,pair_records,edge_fwd,aggregate,interaction,readout,interaction_bwd,alpha_bwd,"
+    "filter_recompute,qk_stream,edge_bwd,edge_finish,chi_bwd,node_proj_bwd,forces";
 
 // Optional per-kernel-category timing with CUDA events on the caller's stream (bench.py's roofline numbers).
 struct Profiler {
@@ -264,9 +267,9 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
     // + both aggregations
     const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
     float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
+    { PROF(CAT_PAIR_RECORDS); so3k_launch_pair_records(D, w.g, ct, w.rec, st); }
     {
       PROF(CAT_EDGE_FWD);
-      so3k_launch_pair_records(D, w.g, ct, w.rec, st);
       so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
       so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
     }
@@ -316,29 +319,34 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
   { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
   cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
   { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, w.xbar_b, w.chibar_b, w.alphabar, w.gproj, st); }
-  {
-    PROF(CAT_EDGE_BWD);
-    if (h->use_tc) {
-      const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
-      float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
-      so3k_launch_pair_records(D, w.g, ct, w.rec, st);
-      if (w.wst_layers == 1) {         // filters not kept: recompute this layer's
-        so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
-        so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
-      }
-      const size_t Gst = (D.nl + 3) & ~3;
-      cudaMemsetAsync(w.ebar, 0, sizeof(float) * Pe * 2, st);
-      cudaMemsetAsync(w.gbar, 0, sizeof(float) * Pe * Gst, st);
+  if (h->use_tc) {
+    const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
+    float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
+    { PROF(CAT_PAIR_RECORDS); so3k_launch_pair_records(D, w.g, ct, w.rec, st); }
+    if (w.wst_layers == 1) {         // filters not kept: recompute this layer's
+      PROF(CAT_FILTER_RECOMPUTE);
+      so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
+    }
+    const size_t Gst = (D.nl + 3) & ~3;
+    cudaMemsetAsync(w.ebar, 0, sizeof(float) * Pe * 2, st);
+    cudaMemsetAsync(w.gbar, 0, sizeof(float) * Pe * Gst, st);
+    {
       // q/k projection gradients, cutoff cotangent and the pairs' filter cotangents: one streaming pass per block
+      PROF(CAT_QK_STREAM);
       so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, w.gproj, w.ebar, w.wbar, st);
+    }
+    {
       // radial + l0-contraction cotangents (added onto the canonical edge of each pair)
+      PROF(CAT_EDGE_BWD);
       if (h->tc_b2) so3k_launch_edge_bwd2_tc(D, w.g, h->tf[t], h->tg[t], w.rec, w.wbar, w.gbar, w.ebar, dev_status, st);
       else so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 2, w.gproj, w.gbar, w.ebar, st);
-    } else {
-      so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
     }
-    so3k_launch_edge_finish(D, w.g, alpha_t, w.chibar_b, w.ebar, w.rbar, st);
+  } else {
+    PROF(CAT_EDGE_BWD);
+    so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
   }
+  { PROF(CAT_EDGE_FINISH); so3k_launch_edge_finish(D, w.g, alpha_t, w.chibar_b, w.ebar, w.rbar, st); }
   if (t > 0) {
     // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
     { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, w.chibar_b, w.chibar_a, st); }     // chibar_a <- d/d chi_t
