@@ -253,7 +253,7 @@ def run_ours(args, w):
                 cap_dd[0] = int(1.25 * nv)
                 eng._status.zero_()
             owner = dd.assign_owners_bricks(pos_s, cell, world)
-            plan = dd.build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, rank, world)
+            plan = dd.build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, rank, world, check=False)
             ddrank.begin(plan, pos_s, z_s, cell)
             step_resident.p_local = ddrank.P
             step_resident.n_local = ddrank.N

@@ -221,7 +221,7 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int wst_layers)
   w.x1 = (float*)take(sizeof(float) * N * F);
   w.chi1 = (float*)take(sizeof(float) * L * N * M);
   w.bcoef = (float*)take(sizeof(float) * L * N * nl);
-  w.proj = (float*)take(sizeof(float) * N * 5 * F);
+  w.proj = (float*)take(sizeof(float) * L * N * 5 * F);     // per layer: kept for the backward (2 640 B per atom at F=132)
   w.gproj = (float*)take(sizeof(float) * N * 5 * F);
   w.alpha = (float*)take(sizeof(float) * L * Pe * Ast);
   w.alphabar = (float*)take(sizeof(float) * Pe * Ast);
@@ -261,7 +261,8 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
   float* xt = w.x + (size_t)t * N * F;
   float* ct = w.chi + (size_t)t * N * M;
   float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
-  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
+  float* proj_t = w.proj + (size_t)t * N * 5 * F;
+  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, proj_t, st); }
   if (h->use_tc) {
     // filters of both blocks per undirected pair on the tensor cores, then one streaming pass: attention coefficients
     // + both aggregations
@@ -274,11 +275,11 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
       so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
     }
     PROF(CAT_AGGREGATE);
-    so3k_launch_alpha_aggregate(D, w.g, xt, ct, w.proj, wst_t, wst_t + Pc * F, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+    so3k_launch_alpha_aggregate(D, w.g, xt, ct, proj_t, wst_t, wst_t + Pc * F, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
   } else {
-    { PROF(CAT_EDGE_FWD); so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, alpha_t, st); }
+    { PROF(CAT_EDGE_FWD); so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, proj_t, alpha_t, st); }
     PROF(CAT_AGGREGATE);
-    so3k_launch_aggregate(D, w.g, xt, ct, w.proj, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+    so3k_launch_aggregate(D, w.g, xt, ct, proj_t, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
   }
   PROF(CAT_INTERACTION);
   so3k_launch_interaction(D, (int)N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + N * F, ct + N * M,
@@ -316,9 +317,9 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
   const float* xt = w.x + (size_t)t * N * F;
   const float* ct = w.chi + (size_t)t * N * M;
   const float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
-  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, w.proj, st); }
+  const float* proj_t = w.proj + (size_t)t * N * 5 * F;     // kept from the forward
   cudaMemsetAsync(w.gproj, 0, sizeof(float) * N * 5 * F, st);
-  { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, w.proj, alpha_t, w.xbar_b, w.chibar_b, w.alphabar, w.gproj, st); }
+  { PROF(CAT_ALPHA_BWD); so3k_launch_alpha_bwd(D, w.g, proj_t, alpha_t, w.xbar_b, w.chibar_b, w.alphabar, w.gproj, st); }
   if (h->use_tc) {
     const size_t Pc = (size_t)so3k_pair_capacity(w.g.Pt);
     float* wst_t = w.wst + (size_t)(w.wst_layers > 1 ? t : 0) * 2 * Pc * F;
@@ -334,17 +335,17 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
     {
       // q/k projection gradients, cutoff cotangent and the pairs' filter cotangents: one streaming pass per block
       PROF(CAT_QK_STREAM);
-      so3k_launch_qk_bwd_stream(D, w.g, w.proj, alpha_t, w.alphabar, wst_t, w.gproj, w.ebar, w.wbar, st);
+      so3k_launch_qk_bwd_stream(D, w.g, proj_t, alpha_t, w.alphabar, wst_t, w.gproj, w.ebar, w.wbar, st);
     }
     {
       // radial + l0-contraction cotangents (added onto the canonical edge of each pair)
       PROF(CAT_EDGE_BWD);
       if (h->tc_b2) so3k_launch_edge_bwd2_tc(D, w.g, h->tf[t], h->tg[t], w.rec, w.wbar, w.gbar, w.ebar, dev_status, st);
-      else so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 2, w.gproj, w.gbar, w.ebar, st);
+      else so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, proj_t, w.alphabar, 2, w.gproj, w.gbar, w.ebar, st);
     }
   } else {
     PROF(CAT_EDGE_BWD);
-    so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, w.proj, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
+    so3k_launch_edge_bwd(D, w.g, h->wf[t], h->wg[t], ct, proj_t, w.alphabar, 3, w.gproj, w.gbar, w.ebar, st);
   }
   { PROF(CAT_EDGE_FINISH); so3k_launch_edge_finish(D, w.g, alpha_t, w.chibar_b, w.ebar, w.rbar, st); }
   if (t > 0) {

@@ -42,18 +42,20 @@ constexpr int WIN = 32;        // column window of the backward staging tiles
 constexpr int WS = 36;         // row stride (floats) of a staging tile: 36 mod 32 = 4 -> conflict-free LDS.128
 
 struct TcDims {
-  int Fp, KC, K0, QS;          // padded N, padded K of GEMM2, K of GEMM1, row stride (floats) of the qk tile
+  int Fp, KC, K0, NS;          // padded N, padded K of GEMM2, K of GEMM1, padded width of the spherical hidden layer
   uint32_t sboW1, sboW2, sboA0, sboA1;
   uint32_t szW1, szW2, szA0, szA1;   // bytes of ONE (hi or lo) image
-  uint32_t off_W1, off_W2, off_A1, off_small, total;
+  uint32_t szWs, szA0s;              // spherical first layer: weight image (NS x 16) and operand image (TM x 16)
+  uint32_t off_W1, off_W2, off_Ws, off_A0s, off_A1, off_small, total;
 };
+constexpr uint32_t SBO_S = 256u;     // 8-row group stride of the K = 16 images of the spherical first layer
 
 __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   TcDims t;
   t.Fp = (D.F + 15) & ~15;
   t.KC = (D.F + D.Fs + 15) & ~15;
   t.K0 = D.K;
-  t.QS = ((D.F - 4 + 31) / 32) * 32 + 4;
+  t.NS = (D.Fs + 15) & ~15;
   t.sboW1 = (uint32_t)(t.K0 / 8) * 128u;
   t.sboW2 = (uint32_t)(t.KC / 8) * 128u;
   t.sboA0 = t.sboW1;
@@ -62,29 +64,30 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   t.szW2 = (uint32_t)(t.Fp / 8) * t.sboW2;
   t.szA0 = (uint32_t)(TM / 8) * t.sboA0;
   t.szA1 = (uint32_t)(TM / 8) * t.sboA1;
+  t.szWs = (uint32_t)(t.NS / 8) * SBO_S;
+  t.szA0s = (uint32_t)(TM / 8) * SBO_S;
   t.off_W1 = 0;
   t.off_W2 = t.off_W1 + 2 * t.szW1;
-  t.off_A1 = t.off_W2 + 2 * t.szW2;
+  t.off_Ws = t.off_W2 + 2 * t.szW2;
+  t.off_A0s = t.off_Ws + 2 * t.szWs;                                     // own buffer: written by S0 of the next tile
+  t.off_A1 = t.off_A0s + 2 * t.szA0s;
   uint32_t region = 2 * t.szA1;                                         // A1 hi | lo
-  const uint32_t qk_bytes = (uint32_t)TM * t.QS * 4u;                    // forward: q_i * k_j tile
-  if (qk_bytes > region) region = qk_bytes;
-  const uint32_t stage_bytes = 3u * TM * WS * 4u;                        // backward 1: QI | KJ | QJ windows
-  if (stage_bytes > region) region = stage_bytes;
   const uint32_t wb_bytes = 2u * (uint32_t)(TM / 8) * (uint32_t)(t.Fp / 8) * 128u;   // backward 2: wbar image
   if (wb_bytes > region) region = wb_bytes;
   if (4u * t.szA0 > region) region = 4u * t.szA0;                        // backward 2: rbf and rbf' images
   t.off_small = t.off_A1 + ((region + 127u) & ~127u);
-  // small arrays (floats): b1p, b2p (Fp each), Ws1 (nl*Fs), bs1 (Fs), s_phi (TM), s_g (TM*nl), s_part (TM*16),
-  //                        (s_part is TM*24) s_i, s_j (TM each), s_head (Fp bytes, rounded to Fp/4 words + 4)
-  uint32_t small = 4u * (2u * t.Fp + (uint32_t)D.nl * D.Fs + D.Fs + TM + TM * D.nl + TM * 24 + 2 * TM + t.Fp / 4 + 4);
+  // small arrays (floats): b1x (KC), b2p (Fp), Ws1 (nl*Fs), s_phi (TM), s_part (TM*8)
+  uint32_t small = 4u * ((uint32_t)t.KC + t.Fp + (uint32_t)D.nl * D.Fs + TM + TM * 8);
   t.total = t.off_small + ((small + 127u) & ~127u);
   return t;
 }
 
 // ---- weight images (built once at so3k_load_params) -------------------------------------------------------
-// image layout in global memory == shared-memory layout: [W1 hi | W1 lo | W2 hi | W2 lo] then fp32 [b1p | b2p]
+// image layout in global memory == shared-memory layout: [W1 hi | W1 lo | W2c hi | W2c lo | Ws1 hi | Ws1 lo], then fp32
+// [b1x (KC) | b2p (Fp)], b1x = [rad_b1 (F) | sph_b1 (Fs) | 0] indexed like the hidden units (K index of GEMM2)
 __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ rW1, const float* __restrict__ rb1,
                                const float* __restrict__ rW2, const float* __restrict__ rb2,
+                               const float* __restrict__ sW1, const float* __restrict__ sb1,
                                const float* __restrict__ sW2, const float* __restrict__ sb2,
                                unsigned char* __restrict__ img, float* __restrict__ bias) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -113,10 +116,18 @@ __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ r
     *reinterpret_cast<__nv_bfloat16*>(img + T.off_W2 + off) = h;
     *reinterpret_cast<__nv_bfloat16*>(img + T.off_W2 + T.szW2 + off) = l;
   }
-  if (t < T.Fp) {
-    bias[t] = (t < F) ? rb1[t] : 0.f;
-    bias[T.Fp + t] = (t < F) ? rb2[t] + sb2[t] : 0.f;
+  // Ws1 image: rows n = c (NS), cols k = l (16): value sph_W1[l][c]
+  if (t < T.NS * 16) {
+    int n = t / 16, k = t % 16;
+    float v = (n < D.Fs && k < D.nl) ? sW1[(size_t)k * D.Fs + n] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    uint32_t off = (uint32_t)(n >> 3) * SBO_S + (uint32_t)(k >> 3) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(img + T.off_Ws + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(img + T.off_Ws + T.szWs + off) = l;
   }
+  if (t < T.KC) bias[t] = (t < F) ? rb1[t] : (t - F < D.Fs ? sb1[t - F] : 0.f);
+  if (t < T.Fp) bias[T.KC + t] = (t < F) ? rb2[t] + sb2[t] : 0.f;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -145,11 +156,9 @@ __device__ __forceinline__ float cutoff_fast(float d, float r_cut) {
 
 // shared-memory carve-up common to the tensor-core edge kernels
 struct TcSmem {
-  unsigned char *W1hi, *W1lo, *W2hi, *W2lo, *A1hi, *A1lo, *A0hi, *A0lo;
+  unsigned char *W1hi, *W1lo, *W2hi, *W2lo, *Wshi, *Wslo, *A1hi, *A1lo, *A0hi, *A0lo, *A0shi, *A0slo;
   float *region;                 // start of the A1 region viewed as floats (staging tiles alias it)
-  float *b1p, *b2p, *Ws1, *bs1, *s_phi, *s_g, *s_part;
-  int *s_i, *s_j;
-  unsigned char* s_head;         // head index of every feature column
+  float *b1p, *b2p, *Ws1, *s_phi, *s_part;
 };
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* smem, const TcDims& T, const So3kDims& D) {
   TcSmem S;
@@ -157,35 +166,33 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* smem, const TcDims& T,
   S.W1lo = S.W1hi + T.szW1;
   S.W2hi = smem + T.off_W2;
   S.W2lo = S.W2hi + T.szW2;
+  S.Wshi = smem + T.off_Ws;
+  S.Wslo = S.Wshi + T.szWs;
   S.A1hi = smem + T.off_A1;
   S.A1lo = S.A1hi + T.szA1;
-  S.A0hi = S.A1hi;               // aliased: dead once GEMM1 has completed
-  S.A0lo = S.A1lo;
+  // radial-basis operand images at the start of the region (dead once the GEMM1s have completed)
+  S.A0hi = S.A1hi;
+  S.A0lo = S.A0hi + T.szA0;
+  S.A0shi = smem + T.off_A0s;
+  S.A0slo = S.A0shi + T.szA0s;
   S.region = reinterpret_cast<float*>(smem + T.off_A1);
   S.b1p = reinterpret_cast<float*>(smem + T.off_small);
-  S.b2p = S.b1p + T.Fp;
+  S.b2p = S.b1p + T.KC;
   S.Ws1 = S.b2p + T.Fp;
-  S.bs1 = S.Ws1 + D.nl * D.Fs;
-  S.s_phi = S.bs1 + D.Fs;
-  S.s_g = S.s_phi + TM;
-  S.s_part = S.s_g + TM * D.nl;  // TM * 24 floats of scratch
-  S.s_i = reinterpret_cast<int*>(S.s_part + TM * 24);
-  S.s_j = S.s_i + TM;
-  S.s_head = reinterpret_cast<unsigned char*>(S.s_j + TM);
+  S.s_phi = S.Ws1 + D.nl * D.Fs;
+  S.s_part = S.s_phi + TM;       // TM * 8 floats of scratch
   return S;
 }
 
-__device__ __forceinline__ void tc_setup(unsigned char* smem, const TcDims& T, const So3kDims& D, const TcSmem& S, int dhd,
+__device__ __forceinline__ void tc_setup(unsigned char* smem, const TcDims& T, const So3kDims& D, const TcSmem& S,
                                          const unsigned char* __restrict__ img, const float* __restrict__ bias_g,
-                                         const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g) {
+                                         const float* __restrict__ Ws1_g) {
   const uint4* src = reinterpret_cast<const uint4*>(img);
   uint4* dst = reinterpret_cast<uint4*>(smem);
-  const int n16 = (int)((2 * T.szW1 + 2 * T.szW2) / 16);
+  const int n16 = (int)(T.off_A0s / 16);
   for (int k = threadIdx.x; k < n16; k += NT) dst[k] = src[k];
-  for (int k = threadIdx.x; k < 2 * T.Fp; k += NT) S.b1p[k] = bias_g[k];
+  for (int k = threadIdx.x; k < T.KC + T.Fp; k += NT) S.b1p[k] = bias_g[k];
   for (int k = threadIdx.x; k < D.nl * D.Fs; k += NT) S.Ws1[k] = Ws1_g[k];
-  for (int k = threadIdx.x; k < D.Fs; k += NT) S.bs1[k] = bs1_g[k];
-  for (int k = threadIdx.x; k < T.Fp; k += NT) S.s_head[k] = (unsigned char)(k < D.F ? k / dhd : 0);
 }
 
 // one GEMM: D[128 x N] = A[128 x 16*ksteps] @ B^T, 3 MMAs per K step (hi*hi + lo*hi + hi*lo); single thread
@@ -289,10 +296,17 @@ __device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, c
   const bool valid = r < ne;
   const float d = m.d;
   if (qq == 0) {
+    // operand row of the spherical first layer: [g_0 .. g_{nl-1}, 0 ...] (K = 16)
     S.s_phi[r] = valid ? cutoff_fast(d, D.r_cut) : 0.f;
+    float g0[8], g1[8];
 #pragma unroll
-    for (int l = 0; l < SO3K_MAXDEG; ++l)
-      if (l < D.nl) S.s_g[r * D.nl + l] = m.gl[l];
+    for (int l = 0; l < 8; ++l) {
+      g0[l] = (valid && l < D.nl) ? m.gl[l] : 0.f;
+      g1[l] = 0.f;
+    }
+    const uint32_t off = (uint32_t)(r >> 3) * SBO_S + (uint32_t)(r & 7) * 16u;
+    tc::store_chunk8(S.A0shi, S.A0slo, off, g0);
+    tc::store_chunk8(S.A0shi, S.A0slo, off + 128u, g1);
   }
   const float ed = __expf(-d);
   for (int c = qq; c < T.K0 / 8; c += 4) {     // this thread writes K chunks qq, qq+4, ... of its row
@@ -309,24 +323,21 @@ __device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, c
   }
 }
 
-// spherical hidden unit c (< Fs), pre-activation: bs1[c] + sum_l g_l Ws1[l][c]
-__device__ __forceinline__ float hidden_pre(const So3kDims& D, const TcSmem& S, const float* gl, int c) {
-  float a = S.bs1[c];
-#pragma unroll
-  for (int l = 0; l < SO3K_MAXDEG; ++l)
-    if (l < D.nl) a = fmaf(gl[l], S.Ws1[l * D.Fs + c], a);
-  return a;
+// first layer of both MLP branches on the tensor cores: D1[:, 0:Fp] = rbf @ W1 (radial), then D1[:, F:F+NS] = g @ Ws1
+// (spherical) written OVER the radial padding columns, so that TMEM column k == hidden unit k == K index of GEMM2
+__device__ __forceinline__ void tc_issue_gemm1(const TcDims& T, const So3kDims& D, const TcSmem& S, uint32_t tD1,
+                                               const unsigned char* A0hi, const unsigned char* A0lo, bool with_sph) {
+  tc_issue_gemm(tD1, A0hi, A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, tc::make_idesc_bf16(TM, T.Fp, 0, 0));
+  if (with_sph)
+    tc_issue_gemm(tD1 + (uint32_t)D.F, S.A0shi, S.A0slo, SBO_S, S.Wshi, S.Wslo, SBO_S, 1, tc::make_idesc_bf16(TM, T.NS, 0, 0));
 }
 
-// epilogue 1: hidden activations of both MLP branches -> A1 operand image (K index: [h1 | h_s | 0])
+// epilogue 1: hidden activations of both MLP branches -> A1 operand image (K index: [h1 (F) | h_s (Fs) | 0])
 __device__ __forceinline__ void tc_epilogue1(const So3kDims& D, const TcDims& T, const TcSmem& S, uint32_t tD1,
                                              uint32_t lane_sel, int r, int qq) {
-  const int F = D.F, Fs = D.Fs;
-  float gl[SO3K_MAXDEG];
-#pragma unroll
-  for (int l = 0; l < SO3K_MAXDEG; ++l) gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
-  const int nchunk_d = T.Fp / 8;
-  const int cbeg = (nchunk_d * qq) / 4, cend = (nchunk_d * (qq + 1)) / 4;
+  const int nh = D.F + D.Fs;                          // hidden units
+  const int nchunk = T.KC / 8;
+  const int cbeg = (nchunk * qq) / 4, cend = (nchunk * (qq + 1)) / 4;
   for (int cb = cbeg; cb < cend; cb += 2) {           // 2 TMEM loads in flight
     float v[2][8];
 #pragma unroll
@@ -337,37 +348,25 @@ __device__ __forceinline__ void tc_epilogue1(const So3kDims& D, const TcDims& T,
     for (int u = 0; u < 2; ++u) {
       if (cb + u < cend) {
         const int c0 = (cb + u) * 8;
-        if (c0 + 8 <= F) {                             // fast path: all radial hidden units
+        if (c0 >= nh) {                                // zero padding of K (warp-uniform)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[u][q] = 0.f;
+        } else {
           const float4 ba = *reinterpret_cast<const float4*>(S.b1p + c0);
           const float4 bb = *reinterpret_cast<const float4*>(S.b1p + c0 + 4);
           v[u][0] = silu_fast(v[u][0] + ba.x); v[u][1] = silu_fast(v[u][1] + ba.y);
           v[u][2] = silu_fast(v[u][2] + ba.z); v[u][3] = silu_fast(v[u][3] + ba.w);
           v[u][4] = silu_fast(v[u][4] + bb.x); v[u][5] = silu_fast(v[u][5] + bb.y);
           v[u][6] = silu_fast(v[u][6] + bb.z); v[u][7] = silu_fast(v[u][7] + bb.w);
-        } else {
+          if (c0 + 8 > nh) {                           // last partial chunk: units beyond F + Fs are padding
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int k = c0 + q;
-            float y;
-            if (k < F) y = silu_fast(v[u][q] + S.b1p[k]);
-            else if (k - F < Fs) y = silu_fast(hidden_pre(D, S, gl, k - F));
-            else y = 0.f;
-            v[u][q] = y;
+            for (int q = 0; q < 8; ++q)
+              if (c0 + q >= nh) v[u][q] = 0.f;
           }
         }
         tc::store_chunk8(S.A1hi, S.A1lo, tc::canon_off(r, c0 >> 3, T.sboA1), v[u]);
       }
     }
-  }
-  // K chunks beyond the D1 columns: remaining spherical hidden units and zero padding
-  for (int ch = nchunk_d + qq; ch < T.KC / 8; ch += 4) {
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int k = ch * 8 + q;
-      v[q] = (k - F < Fs) ? silu_fast(hidden_pre(D, S, gl, k - F)) : 0.f;
-    }
-    tc::store_chunk8(S.A1hi, S.A1lo, tc::canon_off(r, ch, T.sboA1), v);
   }
 }
 
@@ -379,8 +378,8 @@ __device__ __forceinline__ void tc_epilogue1(const So3kDims& D, const TcDims& T,
 __global__ void __launch_bounds__(NT, 1)
 k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restrict__ n_canon,
             const float* __restrict__ rec, const unsigned char* __restrict__ img,
-            const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
-            float* __restrict__ wst, int* __restrict__ status) {
+            const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, float* __restrict__ wst,
+            int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
@@ -398,7 +397,7 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
     tc::mbar_init(&bars[1], 1);
     tc::mbar_fence_init();
   }
-  tc_setup(smem, T, D, S, F, img, bias_g, Ws1_g, bs1_g);
+  tc_setup(smem, T, D, S, img, bias_g, Ws1_g);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
@@ -440,7 +439,7 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
     TC_PHASE(0, 1);
     if (tid == ISSUER) {
       tc::fence_after_sync();
-      tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc);
+      tc_issue_gemm1(T, D, S, tD1, S.A0hi, S.A0lo, true);
       tc::commit(&bars[0]);
     }
     // records of this CTA's next tile (consumed by its S0)
@@ -521,9 +520,8 @@ k_filter_tc(So3kDims D, TcDims T, int n_tiles, int pair_cap, const int* __restri
 __global__ void __launch_bounds__(NT, 1)
 k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const int* __restrict__ n_canon,
                const int* __restrict__ canon, const float* __restrict__ rec, const unsigned char* __restrict__ img,
-               const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ bs1_g,
-               const float* __restrict__ wbar, float* __restrict__ gbar, float* __restrict__ ebar,
-               int* __restrict__ status) {
+               const float* __restrict__ bias_g, const float* __restrict__ Ws1_g, const float* __restrict__ wbar,
+               float* __restrict__ gbar, float* __restrict__ ebar, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
@@ -551,13 +549,14 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
     tc::mbar_init(&bars[1], 1);
     tc::mbar_fence_init();
   }
-  tc_setup(smem, T, D, S, F, img, bias_g, Ws1_g, bs1_g);
+  tc_setup(smem, T, D, S, img, bias_g, Ws1_g);
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tD1 = tmem, tD1p = tmem + (uint32_t)T.Fp, tD3 = tmem + 2u * (uint32_t)T.Fp;
+  // TMEM columns: a (both branches' pre-activations, F + NS <= 192) | forward-mode radial derivative (Fp) | hbar (KC)
+  const uint32_t tD1 = tmem, tD1p = tmem + 192u, tD3 = tmem + 192u + (uint32_t)T.Fp;
   const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
   const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
   const uint32_t idesc3 = tc::make_idesc_bf16(TM, T.KC, 0, 1);     // B = W2c image read MN-major
@@ -591,8 +590,8 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
     TC_PHASE(2, 1);
     if (tid == ISSUER) {
       tc::fence_after_sync();
-      tc_issue_gemm(tD1, S.A0hi, S.A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
-      tc_issue_gemm(tD1p, A0dhi, A0dlo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
+      tc_issue_gemm1(T, D, S, tD1, S.A0hi, S.A0lo, true);
+      tc_issue_gemm1(T, D, S, tD1p, A0dhi, A0dlo, false);
       tc::commit(&bars[0]);
     }
     // records of this CTA's next tile (consumed by its S0)
@@ -657,13 +656,9 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
       }
       tc::commit(&bars[1]);
     }
-    float gl[SO3K_MAXDEG], gb[SO3K_MAXDEG];
-    // (gl is read from shared memory before `meta` is overwritten with the next tile's values)
+    float gb[SO3K_MAXDEG];
 #pragma unroll
-    for (int l = 0; l < SO3K_MAXDEG; ++l) {
-      gl[l] = (l < D.nl) ? S.s_g[r * D.nl + l] : 0.f;
-      gb[l] = 0.f;
-    }
+    for (int l = 0; l < SO3K_MAXDEG; ++l) gb[l] = 0.f;
     // overlapping GEMM3: pull the next tile's filter-cotangent block (contiguous, TM * F floats) into L2
     if (e0_next < nv) {
       const int nrow = (nv - e0_next) < TM ? (nv - e0_next) : TM;
@@ -684,26 +679,24 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
         if (c0 >= F + Fs) break;                  // warp-uniform: only zero padding left
         float hb[8], a1[8], tp[8];
         tc::tmem_ld8(tD3 + lane_sel + (uint32_t)c0, hb);
-        if (c0 < F) {
-          tc::tmem_ld8(tD1 + lane_sel + (uint32_t)c0, a1);
-          tc::tmem_ld8(tD1p + lane_sel + (uint32_t)c0, tp);
-        }
+        tc::tmem_ld8(tD1 + lane_sel + (uint32_t)c0, a1);                 // pre-activations of both branches
+        if (c0 < F) tc::tmem_ld8(tD1p + lane_sel + (uint32_t)c0, tp);    // forward-mode radial derivative
         tc::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int k = c0 + q;
-          if (k < F) {
+          if (k < F + Fs) {
             float y, dy;
             silu_fast_d(a1[q] + S.b1p[k], &y, &dy);
-            dbar = fmaf(hb[q] * dy, tp[q], dbar);
-          } else if (k - F < Fs) {
-            const int c = k - F;
-            float y, dy;
-            silu_fast_d(hidden_pre(D, S, gl, c), &y, &dy);
             const float as = hb[q] * dy;
+            if (k < F) {
+              dbar = fmaf(as, tp[q], dbar);
+            } else {
+              const int c = k - F;
 #pragma unroll
-            for (int l = 0; l < SO3K_MAXDEG; ++l)
-              if (l < D.nl) gb[l] = fmaf(as, S.Ws1[l * Fs + c], gb[l]);
+              for (int l = 0; l < SO3K_MAXDEG; ++l)
+                if (l < D.nl) gb[l] = fmaf(as, S.Ws1[l * Fs + c], gb[l]);
+            }
           }
         }
       }
@@ -741,27 +734,27 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
 bool so3k_edge_tc_supported(const So3kDims& D) {
   if (D.F % 4 != 0 || D.K % 16 != 0) return false;
   TcDims T = make_tc_dims(D);
-  if (T.Fp > 256 || T.Fp % 16 != 0) return false;
-  if (D.H > 8 || D.nl > 7) return false;
-  if (2 * T.Fp + T.KC > 512 || T.Fp > 144) return false;      // TMEM columns ; tail float4 handling of the qk gather
-  if (D.F / D.H < 8 || D.F / D.nl < 8) return false;            // a column quarter must not span more than 4 heads
+  if (T.Fp > 192 || T.Fp % 16 != 0) return false;               // <= 6 image items per warp in backward part 2
+  if (D.H > 8 || D.nl > 7) return false;                        // pair records hold 7 contractions
+  if (D.F + T.NS > 192 || 192 + T.Fp + T.KC > 512) return false;   // TMEM columns (backward part 2: a | t' | hbar)
   return T.total + 1024 <= 227u * 1024u;
 }
 
 size_t so3k_edge_tc_image_bytes(const So3kDims& D) {
   TcDims T = make_tc_dims(D);
-  return ((size_t)(2 * T.szW1 + 2 * T.szW2) + 255) / 256 * 256 + sizeof(float) * 2 * T.Fp + 256;
+  return ((size_t)T.off_A0s + 255) / 256 * 256 + sizeof(float) * (T.KC + T.Fp) + 256;
 }
 
 void so3k_edge_tc_build(const So3kDims& D, const float* p, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
                         const EdgeBlockW& simt, cudaStream_t st) {
   TcDims T = make_tc_dims(D);
-  size_t img_bytes = ((size_t)(2 * T.szW1 + 2 * T.szW2) + 255) / 256 * 256;
+  size_t img_bytes = ((size_t)T.off_A0s + 255) / 256 * 256;
   float* bias = reinterpret_cast<float*>(dst + img_bytes);
   int tot = T.Fp * T.KC;
   so3k_count_launch();
   k_build_images<<<so3k_cdiv(tot, 256), 256, 0, st>>>(D, T, p + bp.rad_W1, p + bp.rad_b1, p + bp.rad_W2, p + bp.rad_b2,
-                                                       p + bp.sph_W2, p + bp.sph_b2, dst, bias);
+                                                       p + bp.sph_W1, p + bp.sph_b1, p + bp.sph_W2, p + bp.sph_b2, dst,
+                                                       bias);
   out->img = dst;
   out->bias = bias;
   out->Ws1 = simt.Ws1;
@@ -797,8 +790,7 @@ void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W,
   int grid = tc_grid(n_tiles, T);
   cudaFuncSetAttribute(k_filter_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total + 1024);
   so3k_count_launch();
-  k_filter_tc<<<grid, NT, T.total + 1024, st>>>(D, T, n_tiles, pair_cap, g.n_canon, rec, W.img, W.bias, W.Ws1, W.bs1, wst,
-                                                 status);
+  k_filter_tc<<<grid, NT, T.total + 1024, st>>>(D, T, n_tiles, pair_cap, g.n_canon, rec, W.img, W.bias, W.Ws1, wst, status);
 }
 
 // radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of both filter blocks, ADDED to zero-initialised
@@ -815,8 +807,8 @@ void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW&
   for (int blk = 0; blk < 2; ++blk) {
     const TcBlockW& W = blk ? Wg : Wf;
     so3k_count_launch();
-    k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, Gst, n_tiles, pair_cap, g.n_canon, g.canon, rec, W.img, W.bias, W.Ws1, W.bs1, wbar + (size_t)blk * pair_cap * D.F, gbar,
-                                                      ebar, status);
+    k_edge_bwd2_tc<<<grid, NT, T.total + 1024, st>>>(D, T, Gst, n_tiles, pair_cap, g.n_canon, g.canon, rec, W.img, W.bias,
+                                                      W.Ws1, wbar + (size_t)blk * pair_cap * D.F, gbar, ebar, status);
   }
 }
 extern "C" void so3k_tc_phase_dump(void) {

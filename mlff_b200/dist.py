@@ -109,8 +109,11 @@ class DDPlan:
         return self.n_own + self.n_ghost
 
 
-def build_plan(ii: torch.Tensor, jj: torch.Tensor, S: torch.Tensor, owner: torch.Tensor, rank: int, world: int) -> DDPlan:
-    """ii, jj (P) int64 global ids of the valid edges (receiver, sender), S (P,3), owner (N)."""
+def build_plan(ii: torch.Tensor, jj: torch.Tensor, S: torch.Tensor, owner: torch.Tensor, rank: int, world: int,
+               check: bool = True) -> DDPlan:
+    """ii, jj (P) int64 global ids of the valid edges (receiver, sender), S (P,3), owner (N).
+    check=False skips the symmetry assertion (one host synchronisation less per step; an asymmetric list is still
+    reported by the kernels through SO3K_STATUS_ASYMMETRIC)."""
     dev = ii.device
     N = owner.shape[0]
     oi, oj = owner[ii], owner[jj]
@@ -125,12 +128,17 @@ def build_plan(ii: torch.Tensor, jj: torch.Tensor, S: torch.Tensor, owner: torch
     g2l[local_atoms] = torch.arange(local_atoms.shape[0], device=dev)
     sel = own_recv | mirror
     li, lj = g2l[ii[sel]], g2l[jj[sel]]
-    assert bool((li >= 0).all()) and bool((lj >= 0).all()), 'mirror edge whose receiver is not a ghost (asymmetric list?)'
-    recv_counts = [int(((owner[gh]) == p).sum()) for p in range(world)]
+    if check:
+        assert bool(((li >= 0) & (lj >= 0)).all()), 'mirror edge whose receiver is not a ghost (asymmetric list?)'
+    else:
+        li, lj = li.clamp_min(0), lj.clamp_min(0)
+    counts = torch.stack([torch.bincount(owner[gh], minlength=world)[:world],
+                          torch.zeros(world, dtype=torch.int64, device=dev)])
     # what the others need from me: unique (needing rank, my atom) over edges received elsewhere and sent by me
     need = torch.unique(oi[mirror] * N + jj[mirror])         # sorted by (needing rank, global id)
     need_rank, need_atom = need // N, need % N
-    send_counts = [int((need_rank == p).sum()) for p in range(world)]
+    counts[1] = torch.bincount(need_rank, minlength=world)[:world]
+    recv_counts, send_counts = counts.tolist()                # one host synchronisation for both
     send_idx = g2l[need_atom]
     return DDPlan(rank, world, int(owned.shape[0]), int(gh.shape[0]), local_atoms, li, lj, S[sel], send_idx,
                   send_counts, recv_counts)
@@ -237,7 +245,8 @@ def run_energy_forces(ranks: Sequence[DDRank], exchange: Exchange) -> None:
     for t in range(L):
         for r in ranks:
             r.stage(0, t)
-        exchange(ranks, (0, 1), t + 1)            # x_{t+1}, chi_{t+1} of the ghosts
+        if t + 1 < L:                             # (x_L, chi_L of a ghost are never read: its read-out and its
+            exchange(ranks, (0, 1), t + 1)        #  cotangents belong to the owner)  x_{t+1}, chi_{t+1} of the ghosts
     for r in ranks:
         r.stage(1)
     for t in range(L - 1, -1, -1):
