@@ -76,8 +76,8 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   if (wb_bytes > region) region = wb_bytes;
   if (4u * t.szA0 > region) region = 4u * t.szA0;                        // backward 2: rbf and rbf' images
   t.off_small = t.off_A1 + ((region + 127u) & ~127u);
-  // small arrays (floats): b1x (KC), b2p (Fp), Ws1 (nl*Fs), s_phi (TM), s_part (TM*8)
-  uint32_t small = 4u * ((uint32_t)t.KC + t.Fp + (uint32_t)D.nl * D.Fs + TM + TM * 8);
+  // small arrays (floats): b1x (KC), b2p (Fp), Ws1 (nl*Fs)
+  uint32_t small = 4u * ((uint32_t)t.KC + t.Fp + (uint32_t)D.nl * D.Fs);
   t.total = t.off_small + ((small + 127u) & ~127u);
   return t;
 }
@@ -158,7 +158,7 @@ __device__ __forceinline__ float cutoff_fast(float d, float r_cut) {
 struct TcSmem {
   unsigned char *W1hi, *W1lo, *W2hi, *W2lo, *Wshi, *Wslo, *A1hi, *A1lo, *A0hi, *A0lo, *A0shi, *A0slo;
   float *region;                 // start of the A1 region viewed as floats (staging tiles alias it)
-  float *b1p, *b2p, *Ws1, *s_phi, *s_part;
+  float *b1p, *b2p, *Ws1;
 };
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* smem, const TcDims& T, const So3kDims& D) {
   TcSmem S;
@@ -179,8 +179,6 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* smem, const TcDims& T,
   S.b1p = reinterpret_cast<float*>(smem + T.off_small);
   S.b2p = S.b1p + T.KC;
   S.Ws1 = S.b2p + T.Fp;
-  S.s_phi = S.Ws1 + D.nl * D.Fs;
-  S.s_part = S.s_phi + TM;       // TM * 8 floats of scratch
   return S;
 }
 
@@ -297,7 +295,6 @@ __device__ __forceinline__ void tc_tile_s0(const So3kDims& D, const TcDims& T, c
   const float d = m.d;
   if (qq == 0) {
     // operand row of the spherical first layer: [g_0 .. g_{nl-1}, 0 ...] (K = 16)
-    S.s_phi[r] = valid ? cutoff_fast(d, D.r_cut) : 0.f;
     float g0[8], g1[8];
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
@@ -541,7 +538,8 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
   const uint32_t szWb = (uint32_t)(TM / 8) * sboWb;
   unsigned char* Wbhi = reinterpret_cast<unsigned char*>(S.region);   // aliases the rbf images: dead once the GEMM1s are done
   unsigned char* Wblo = Wbhi + szWb;
-  float* s_red = S.s_part;                      // [TM][8]  cross-quarter reduction (dbar, gbar_l)
+  float* s_red = S.region;                      // [4 quarters][8][TM]: cross-quarter reduction of (dbar, gbar_l); aliases
+                                                // the wbar image, dead once GEMM3 has completed
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -579,10 +577,6 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
     long long t_prev_ = TC_TIMING ? clock64() : 0;
 
     if (comp) tc_tile_s0<true>(D, T, S, r, qq, ne, meta, A0dhi, A0dlo);
-    if (comp && qq == 2) {
-#pragma unroll
-      for (int h = 0; h < 8; ++h) s_red[r * 8 + h] = 0.f;
-    }
     TC_PHASE(2, 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -701,12 +695,13 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
         }
       }
       TC_PHASE(2, 8);
-      // cross-quarter combination: 4 contributions per slot through shared-memory atomics
+      // cross-quarter combination through shared memory (one 32-byte slot per thread)
       if (comp) {
-        atomicAdd(&s_red[r * 8 + 0], dbar);
+        float* slot = s_red + (size_t)qq * 8 * TM + r;         // lanes = consecutive rows: conflict-free
+        slot[0] = dbar;
 #pragma unroll
-        for (int l = 0; l < SO3K_MAXDEG; ++l)
-          if (l < D.nl && l < 7) atomicAdd(&s_red[r * 8 + 1 + l], gb[l]);
+        for (int l = 0; l < 7; ++l)
+          if (l < D.nl) slot[(1 + l) * TM] = gb[l];
       }
       tc::fence_before_sync();
       __syncthreads();
@@ -716,8 +711,15 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
         // ebar[e] + ebar[rev e], gbar[e] + gbar[rev e] enter chi-bar and the forces).  Fire-and-forget reductions: both
         // blocks add into the same slots.
         const size_t e = (size_t)my_e;
-        atomicAdd(&ebar[2 * e], s_red[r * 8 + 0]);
-        for (int l = 0; l < D.nl; ++l) atomicAdd(&gbar[e * Gst + l], s_red[r * 8 + 1 + l]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k <= D.nl) {
+            const float tot = s_red[(0 * 8 + k) * TM + r] + s_red[(1 * 8 + k) * TM + r] + s_red[(2 * 8 + k) * TM + r] +
+                              s_red[(3 * 8 + k) * TM + r];
+            if (k == 0) atomicAdd(&ebar[2 * e], tot);
+            else atomicAdd(&gbar[e * Gst + k - 1], tot);
+          }
+        }
       }
     }
     __syncthreads();
