@@ -676,20 +676,32 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
         tc::tmem_ld8(tD1 + lane_sel + (uint32_t)c0, a1);                 // pre-activations of both branches
         if (c0 < F) tc::tmem_ld8(tD1p + lane_sel + (uint32_t)c0, tp);    // forward-mode radial derivative
         tc::tmem_ld_wait();
+        if (c0 + 8 <= F) {                        // radial chunk: no per-element control flow
+          const float4 ba = *reinterpret_cast<const float4*>(S.b1p + c0);
+          const float4 bb = *reinterpret_cast<const float4*>(S.b1p + c0 + 4);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int k = c0 + q;
-          if (k < F + Fs) {
+          for (int q = 0; q < 8; ++q) {
             float y, dy;
-            silu_fast_d(a1[q] + S.b1p[k], &y, &dy);
-            const float as = hb[q] * dy;
-            if (k < F) {
-              dbar = fmaf(as, tp[q], dbar);
-            } else {
-              const int c = k - F;
+            silu_fast_d(a1[q] + bv[q], &y, &dy);
+            dbar = fmaf(hb[q] * dy, tp[q], dbar);
+          }
+        } else {
 #pragma unroll
-              for (int l = 0; l < SO3K_MAXDEG; ++l)
-                if (l < D.nl) gb[l] = fmaf(as, S.Ws1[l * Fs + c], gb[l]);
+          for (int q = 0; q < 8; ++q) {
+            const int k = c0 + q;
+            if (k < F + Fs) {
+              float y, dy;
+              silu_fast_d(a1[q] + S.b1p[k], &y, &dy);
+              const float as = hb[q] * dy;
+              if (k < F) {
+                dbar = fmaf(as, tp[q], dbar);
+              } else {
+                const int c = k - F;
+#pragma unroll
+                for (int l = 0; l < 7; ++l)
+                  if (l < D.nl) gb[l] = fmaf(as, S.Ws1[l * Fs + c], gb[l]);
+              }
             }
           }
         }
