@@ -240,8 +240,18 @@ def run_ours(args, w):
 
         cap_dd = [int(cap * 1.6 / world) + 4096]
 
+        dd_marks = []                                              # (label, event) of one step, --dd-timing
+
+        def mark(label):
+            if args.dd_timing:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                dd_marks.append((label, ev))
+
         def step_resident():
             # this rank only needs the atoms of its brick + r_cut: neighbour list, plan and kernels are O(local)
+            dd_marks.clear()
+            mark('start')
             keep = dd.brick_halo_mask(pos_d, cell, world, rank, calc.cutoff)
             sub = torch.nonzero(keep).reshape(-1)                 # ascending: subset order == global order
             pos_s, z_s = pos_d[sub], z_d[sub]
@@ -252,14 +262,19 @@ def run_ours(args, w):
                     break
                 cap_dd[0] = int(1.25 * nv)
                 eng._status.zero_()
+            mark('subset + neighbour list')
             owner = dd.assign_owners_bricks(pos_s, cell, world)
             plan = dd.build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, rank, world, check=False)
+            mark('plan')
             ddrank.begin(plan, pos_s, z_s, cell)
+            mark('begin (local arrays, CSR, embedding)')
             step_resident.p_local = ddrank.P
             step_resident.n_local = ddrank.N
             dd.run_energy_forces([ddrank], dd.exchange_distributed)
+            mark('layers + exchanges')
             e_tot[0] = ddrank.e_atom[:plan.n_own].double().sum()
             dist.all_reduce(e_tot)
+            mark('energy all-reduce')
             return e_tot, ddrank.forces[:plan.n_own], None
 
     for _ in range(args.warmup):
@@ -281,6 +296,10 @@ def run_ours(args, w):
     e1.record()
     barrier()
     launches = eng.lib.launch_count() - l0
+    if use_dd and args.dd_timing and rank == 0:
+        torch.cuda.synchronize()
+        print('dd step phases (ms): ' + ', '.join(f'{lab} {a.elapsed_time(b):.3f}' for (_, a), (lab, b) in
+                                                     zip(dd_marks[:-1], dd_marks[1:])), file=sys.stderr)
     ms_total = e0.elapsed_time(e1)
     prof = eng.lib.profile_collect(eng.h, reset=True)
     eng.lib.profile_enable(eng.h, False)
@@ -383,6 +402,16 @@ def run_ours(args, w):
                          (4 * 8 + 4 + 16) * p_rank + (8 * Fd + 8 * M_ + 4) * n_rank + 4 * Fd * n_rank,
                          'compulsory bytes (DESIGN.md)'),
             ]
+        # DRAM bytes per scope from the round's `ncu --set full` captures of THIS workload on one GPU
+        # (profiles/r01h_<kernel>_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch x launches per scope)
+        if args.tensor and args.workload == 'c4' and world == 1 and not args.no_keep_filters:
+            ncu_traffic = {'k_edge_bwd2_tc': 2 * (1.589e9 + 0.061e9), 'k_filter_tc': 2 * (0.085e9 + 1.334e9),
+                           'k_qk_bwd_stream': 4.865e9 + 3.031e9, 'k_alpha_aggregate': 4.853e9 + 0.577e9,
+                           'k_alpha_bwd': 0.436e9 + 0.207e9}
+            for r_ in roofs:
+                for k_, v_ in ncu_traffic.items():
+                    if r_['kernel'].startswith(k_ + ' ') or r_['kernel'] == k_:
+                        r_['traffic'] = v_
         roofs.sort(key=lambda r: -r['share_of_step'])
         roof, agg = roofs[0], roofs[1:]          # `roofline` = the kernel with the largest share of the step
         # CPU baseline: bounded sample, all host threads
@@ -430,6 +459,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--dd-timing', action='store_true', help='print the per-phase device time of one domain-decomposed step '
+                    '(rank 0, stderr)')
     ap.add_argument('--no-keep-filters', action='store_true', help='recompute the filters in the backward instead of keeping '
                     'them in HBM (2F floats per edge and layer)')
     ap.add_argument('--fp32-simt', action='store_true', help='run the filter GEMMs as fp32 FMA on the CUDA cores instead of '
