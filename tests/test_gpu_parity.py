@@ -156,10 +156,12 @@ def test_md_seam_and_asymmetric_flag(ethanol):
     np.testing.assert_allclose(Fo.cpu().numpy(), 1.7 * F_o.numpy(), rtol=2e-5, atol=1e-5)
     ii2, jj2 = ii.copy(), jj.copy()
     ii2[5] = jj2[5] = -1
-    eng.energy_forces(dev(R[None], torch.float32), dev(z[None], torch.int32), dev(ii2[None], torch.int32),
-                      dev(jj2[None], torch.int32))
-    with pytest.raises(So3kError):
-        eng.check_status()
+    for flags in (0, 3):                # an asymmetric list is flagged, never a crash, in every arithmetic mode
+        eng2 = make(cfg, p, flags=flags)
+        eng2.energy_forces(dev(R[None], torch.float32), dev(z[None], torch.int32), dev(ii2[None], torch.int32),
+                           dev(jj2[None], torch.int32))
+        with pytest.raises(So3kError):
+            eng2.check_status()
 
 
 def test_reference_api_mirror(ethanol):
@@ -222,7 +224,8 @@ def test_neighbor_list_variants(solid, ethanol):
     assert cnt == 72 and (ii[:72] == nl['idx_i'][0]).all() and (jj[:72] == nl['idx_j'][0]).all()
 
 
-def test_water_box_3000_atoms_vs_oracle():
+@pytest.mark.parametrize('flags', [0, 3])          # fp32 CUDA-core mode ; tensor mode + kept filters (the bench default)
+def test_water_box_3000_atoms_vs_oracle(flags):
     # config 3 of BASELINE.json: 3 000 atoms, cubic 31.072 A cell, MIC neighbour list at 5 A, E+F on one GPU.
     # The oracle (float64, brute-force list) still finishes in seconds at this size.
     N, box = 3000, 31.072
@@ -231,7 +234,7 @@ def test_water_box_3000_atoms_vs_oracle():
     cell = np.eye(3) * box
     cfg = o.OracleConfig()
     p = o.init_params(cfg, 0, embed_scale=4.0)
-    eng = make(cfg, p)
+    eng = make(cfg, p, flags=flags)
     oi, oj, oS = o.periodic_neighbor_list_kdtree(pos, box, 5.0)
     ii, jj, S, cnt = gpu_nl(eng, pos, cell, (1, 1, 1), 5.0, int(1.1 * len(oi)))
     assert cnt == len(oi) and (ii[:cnt] == oi).all() and (jj[:cnt] == oj).all() and (S[:cnt] == oS).all()
@@ -244,7 +247,8 @@ def test_water_box_3000_atoms_vs_oracle():
     assert np.abs(F[0].sum(0)).max() < 1e-3
 
 
-def test_full_size_properties_100k_atoms():
+@pytest.mark.parametrize('flags', [0, 1, 3])
+def test_full_size_properties_100k_atoms(flags):
     # config 4 of BASELINE.json at full size (100 000 atoms, 100 A box): too big for the oracle, so check
     # properties: list symmetric + sorted + strict cutoff, E invariant and F unchanged under a rigid translation
     # through the periodic boundary, net force ~ 0, finite outputs; a 3 000-atom sub-problem is pinned above.
@@ -254,7 +258,7 @@ def test_full_size_properties_100k_atoms():
     cell = np.eye(3) * box
     cfg = o.OracleConfig()
     p = o.init_params(cfg, 0, embed_scale=4.0)
-    eng = make(cfg, p)
+    eng = make(cfg, p, flags=flags)
     cap = 64 * N
     ii, jj, S, cnt = gpu_nl(eng, pos, cell, (1, 1, 1), 5.0, cap)
     assert 0 < cnt <= cap and eng.check_status() == 0
