@@ -33,6 +33,7 @@ struct float3 { float x, y, z; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct double2 { double x, y; };
 struct double3 { double x, y, z; };
 static inline float2 make_float2(float x, float y) { return {x, y}; }
@@ -161,6 +162,8 @@ static inline int atomicOr(int* p, int v) { return std::atomic_ref<int>(*p).fetc
 static inline int atomicExch(int* p, int v) { return std::atomic_ref<int>(*p).exchange(v); }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <class T> static inline T __ldcs(const T* p) { return *p; }
 template <class T> static inline void __stcs(T* p, T v) { *p = v; }
 // glibc already declares __expf/__cosf/__sinf (same semantics as the accurate versions): nothing to add.
