@@ -62,6 +62,18 @@ def build_inputs(w, rank=0):
         z = np.where(np.arange(w['n_atoms']) % 3 == 0, 8, 1).astype(np.int64)
     else:
         z = water_like_numbers(w['n_atoms'], w['seed'])
+    order = os.environ.get('SO3K_BENCH_ATOM_ORDER', 'lattice')      # experiment knob: sensitivity to the caller's atom order
+    if order != 'lattice':
+        if order == 'random':
+            perm = np.random.default_rng(5).permutation(len(pos))
+        else:                                                      # 'morton': Z-order of 4 A cells
+            c = np.floor(pos / 4.0).astype(np.int64) & 1023
+            key = np.zeros(len(pos), np.int64)
+            for b in range(10):
+                for ax in range(3):
+                    key |= ((c[:, ax] >> b) & 1) << (3 * b + ax)
+            perm = np.argsort(key, kind='stable')
+        pos, z = pos[perm], z[perm]
     return pos, z, np.eye(3) * w['box'], (True, True, True)
 
 
@@ -252,8 +264,7 @@ def run_ours(args, w):
             # this rank only needs the atoms of its brick + r_cut: neighbour list, plan and kernels are O(local)
             dd_marks.clear()
             mark('start')
-            keep = dd.brick_halo_mask(pos_d, cell, world, rank, calc.cutoff)
-            sub = torch.nonzero(keep).reshape(-1)                 # ascending: subset order == global order
+            sub, owner = dd.brick_select(pos_d, cell, world, rank, calc.cutoff)   # ascending: subset order == global order
             pos_s, z_s = pos_d[sub], z_d[sub]
             while True:
                 ii, jj, S, count = eng.neighbor_list(pos_s, calc.cutoff, cap_dd[0], cell=cell, pbc=pbc, mode=NL_ASE)
@@ -263,7 +274,6 @@ def run_ours(args, w):
                 cap_dd[0] = int(1.25 * nv)
                 eng._status.zero_()
             mark('subset + neighbour list')
-            owner = dd.assign_owners_bricks(pos_s, cell, world)
             plan = dd.build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, rank, world, check=False)
             mark('plan')
             ddrank.begin(plan, pos_s, z_s, cell)

@@ -43,12 +43,18 @@ def brick_grid(cell: np.ndarray, world: int) -> tuple:
     return best
 
 
+def _frac(pos: torch.Tensor, inv_np: np.ndarray) -> torch.Tensor:
+    """Fractional coordinates wrapped into [0, 1), evaluated element-wise (no GEMM): every rank must get bit-identical
+    values for an atom whatever the size of the array it sits in, or two ranks could disagree about its owner."""
+    inv = torch.as_tensor(inv_np, dtype=pos.dtype, device=pos.device)
+    frac = pos[:, 0:1] * inv[0] + pos[:, 1:2] * inv[1] + pos[:, 2:3] * inv[2]
+    return frac - torch.floor(frac)
+
+
 def assign_owners_bricks(pos: torch.Tensor, cell: np.ndarray, world: int) -> torch.Tensor:
     """owner[a] = index of the brick (fractional-coordinate grid of brick_grid(cell, world)) that contains atom a."""
     px, py, pz = brick_grid(cell, world)
-    inv = torch.as_tensor(np.linalg.inv(np.asarray(cell, dtype=np.float64)), dtype=pos.dtype, device=pos.device)
-    frac = pos @ inv
-    frac = frac - torch.floor(frac)
+    frac = _frac(pos, np.linalg.inv(np.asarray(cell, dtype=np.float64)))
     cx = torch.clamp((frac[:, 0] * px).to(torch.int64), 0, px - 1)
     cy = torch.clamp((frac[:, 1] * py).to(torch.int64), 0, py - 1)
     cz = torch.clamp((frac[:, 2] * pz).to(torch.int64), 0, pz - 1)
@@ -62,9 +68,7 @@ def brick_halo_mask(pos: torch.Tensor, cell: np.ndarray, world: int, rank: int, 
     px, py, pz = brick_grid(cell, world)
     c = np.asarray(cell, dtype=np.float64).reshape(3, 3)
     inv_np = np.linalg.inv(c)
-    inv = torch.as_tensor(inv_np, dtype=pos.dtype, device=pos.device)
-    frac = pos @ inv
-    frac = frac - torch.floor(frac)
+    frac = _frac(pos, inv_np)
     heights = 1.0 / np.linalg.norm(inv_np, axis=0)                 # face-to-face distances
     idx = (rank // (py * pz), (rank // pz) % py, rank % pz)
     keep = torch.ones(pos.shape[0], dtype=torch.bool, device=pos.device)
@@ -82,11 +86,35 @@ def brick_halo_mask(pos: torch.Tensor, cell: np.ndarray, world: int, rank: int, 
     return keep
 
 
+def brick_select(pos: torch.Tensor, cell: np.ndarray, world: int, rank: int, margin: float):
+    """(sub, owner_sub): ascending global ids of the atoms inside brick `rank` + margin (brick_halo_mask) and the owning
+    brick of each of them (assign_owners_bricks) from ONE evaluation of the fractional coordinates -- the per-step
+    preparation of a rank is launch-bound, so the number of small device ops matters."""
+    px, py, pz = brick_grid(cell, world)
+    c = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    inv_np = np.linalg.inv(c)
+    frac = _frac(pos, inv_np)
+    heights = 1.0 / np.linalg.norm(inv_np, axis=0)
+    grid = torch.tensor([px, py, pz], dtype=pos.dtype, device=pos.device)
+    cells = torch.minimum((frac * grid).to(torch.int64), (grid - 1).to(torch.int64)).clamp_min_(0)
+    owner = (cells[:, 0] * py + cells[:, 1]) * pz + cells[:, 2]
+    idx = (rank // (py * pz), (rank // pz) % py, rank % pz)
+    centre = np.zeros(3)
+    half = np.full(3, 2.0)                                          # > 0.5: no restriction along this axis
+    for a_, (n, k) in enumerate(zip((px, py, pz), idx)):
+        if n > 1:
+            m = margin / heights[a_] * (1.0 + 1e-9) + 1e-12
+            centre[a_], half[a_] = (k + 0.5) / n, 0.5 / n + m
+    d = torch.abs(frac - torch.as_tensor(centre, dtype=pos.dtype, device=pos.device))
+    d = torch.minimum(d, 1.0 - d)                                   # periodic distance to the brick centre
+    keep = (d <= torch.as_tensor(half, dtype=pos.dtype, device=pos.device)).all(dim=1)
+    sub = torch.nonzero(keep).reshape(-1)
+    return sub, owner[sub]
+
+
 def assign_owners_slab(pos: torch.Tensor, cell: np.ndarray, world: int, axis: int = 0) -> torch.Tensor:
     """owner[a] = slab index of atom a along `axis` (fractional coordinate wrapped into [0,1))."""
-    inv = torch.as_tensor(np.linalg.inv(np.asarray(cell, dtype=np.float64)), dtype=pos.dtype, device=pos.device)
-    frac = (pos @ inv)[:, axis]
-    frac = frac - torch.floor(frac)
+    frac = _frac(pos, np.linalg.inv(np.asarray(cell, dtype=np.float64)))[:, axis]
     return torch.clamp((frac * world).to(torch.int64), 0, world - 1)
 
 
@@ -120,8 +148,10 @@ def build_plan(ii: torch.Tensor, jj: torch.Tensor, S: torch.Tensor, owner: torch
     own_recv = oi == rank
     mirror = (oj == rank) & (oi != rank)                     # receiver is someone else's atom, sender is mine
     # ghosts: senders of my rows that I do not own, ordered by (owner, global id)
-    gh = torch.unique(jj[own_recv & (oj != rank)])
-    gh = gh[torch.argsort(owner[gh] * N + gh)]
+    gflag = torch.zeros(N, dtype=torch.bool, device=dev)     # (flag + nonzero: cheaper than a sort-based unique)
+    gflag[jj[own_recv & (oj != rank)]] = True
+    gh = torch.nonzero(gflag).reshape(-1)                    # ascending global id
+    gh = gh[torch.sort(owner[gh], stable=True).indices]      # -> ordered by (owner, global id)
     owned = torch.nonzero(owner == rank).reshape(-1)
     local_atoms = torch.cat([owned, gh])
     g2l = torch.full((N,), -1, dtype=torch.int64, device=dev)
@@ -135,7 +165,9 @@ def build_plan(ii: torch.Tensor, jj: torch.Tensor, S: torch.Tensor, owner: torch
     counts = torch.stack([torch.bincount(owner[gh], minlength=world)[:world],
                           torch.zeros(world, dtype=torch.int64, device=dev)])
     # what the others need from me: unique (needing rank, my atom) over edges received elsewhere and sent by me
-    need = torch.unique(oi[mirror] * N + jj[mirror])         # sorted by (needing rank, global id)
+    nflag = torch.zeros(world * N, dtype=torch.bool, device=dev)
+    nflag[oi[mirror] * N + jj[mirror]] = True
+    need = torch.nonzero(nflag).reshape(-1)                  # sorted by (needing rank, global id)
     need_rank, need_atom = need // N, need % N
     counts[1] = torch.bincount(need_rank, minlength=world)[:world]
     recv_counts, send_counts = counts.tolist()                # one host synchronisation for both

@@ -151,3 +151,15 @@ def test_halo_subset_gives_the_same_plan_edges(solid):
         assert edge_set(full, torch.arange(110)) == edge_set(part, sub)
         assert torch.equal(sub[part.local_atoms], full.local_atoms)
         assert part.send_counts == full.send_counts and part.recv_counts == full.recv_counts
+
+
+def test_brick_select_equals_mask_and_owners():
+    rng = np.random.default_rng(3)
+    cell = np.array([[31.0, 0.0, 0.0], [3.0, 29.0, 0.0], [-2.0, 4.0, 33.0]])
+    pos = torch.as_tensor(rng.uniform(-40, 80, size=(5000, 3)))
+    for world in (2, 3, 4, 8):
+        for rank in range(world):
+            sub, own = dd.brick_select(pos, cell, world, rank, 5.0)
+            keep = dd.brick_halo_mask(pos, cell, world, rank, 5.0)
+            assert torch.equal(sub, torch.nonzero(keep).reshape(-1))
+            assert torch.equal(own, dd.assign_owners_bricks(pos[sub], cell, world))
