@@ -1,8 +1,9 @@
 // Node-level (per-atom) kernels: embedding, q/k/v projections, interaction block, energy read-out and
 // their data-gradients.  These are < 2 % of the FLOPs of a step;
 // they are written as small shared-memory tiled FMA kernels: a block owns TA atoms, the atom rows sit in
-// shared memory, each thread owns one output column and keeps TA accumulators so every weight element is
-// read once per block (coalesced across the threads of a warp).
+// shared memory TRANSPOSED ([column][atom], column stride LDA) so that one broadcast 16-byte load feeds four FMAs,
+// each thread owns one output column and keeps TA accumulators so every weight element is read once per block
+// (coalesced across the threads of a warp).  NT is sized to the ~F output columns of a pass; several blocks share an SM.
 //   AtomTypeEmbed            mlff/nn/embed/embed.py:227-229
 //   q / k / v Dense          mlff/nn/layer/so3krates_layer.py:583-584, 607  (per head, no bias)
 //   InteractionBlock         mlff/nn/layer/so3krates_layer.py:355-379 (+ skip :163-164)
@@ -12,25 +13,28 @@
 namespace {
 
 constexpr int TA = 16;        // atoms per block
-constexpr int NT = 256;       // threads per block
+constexpr int LDA = TA + 4;   // column stride of a transposed tile: 16-byte aligned, 20 mod 32 spreads the banks
+constexpr int NT = 160;       // threads per block
 
-// acc[a] += sum_c xs[a][c0 + c] * W[c * ldw + o]
-__device__ __forceinline__ void col_dot(const float* xs, int ldx, int c0, int nC, const float* __restrict__ W, int ldw,
-                                        int o, float* acc) {
-  for (int c = 0; c < nC; ++c) {
-    float w = W[(size_t)c * ldw + o];
+// acc[a] += w * col[a], a < TA, col = one column of a transposed tile (all lanes read the same 16 bytes: broadcast)
+__device__ __forceinline__ void axpy_col(const float* col, float w, float* acc) {
 #pragma unroll
-    for (int a = 0; a < TA; ++a) acc[a] = fmaf(xs[a * ldx + c0 + c], w, acc[a]);
+  for (int k = 0; k < TA / 4; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(col + 4 * k);
+    acc[4 * k + 0] = fmaf(v.x, w, acc[4 * k + 0]);
+    acc[4 * k + 1] = fmaf(v.y, w, acc[4 * k + 1]);
+    acc[4 * k + 2] = fmaf(v.z, w, acc[4 * k + 2]);
+    acc[4 * k + 3] = fmaf(v.w, w, acc[4 * k + 3]);
   }
 }
-// acc[a] += sum_o gs[a][o0 + o] * Wrow[o]       (Wrow contiguous)
-__device__ __forceinline__ void row_dot(const float* gs, int ldg, int o0, int nO, const float* __restrict__ Wrow,
+// acc[a] += sum_c xs[c0 + c][a] * W[c * ldw + o]
+__device__ __forceinline__ void col_dot(const float* xs, int c0, int nC, const float* __restrict__ W, int ldw, int o,
                                         float* acc) {
-  for (int o = 0; o < nO; ++o) {
-    float w = Wrow[o];
-#pragma unroll
-    for (int a = 0; a < TA; ++a) acc[a] = fmaf(gs[a * ldg + o0 + o], w, acc[a]);
-  }
+  for (int c = 0; c < nC; ++c) axpy_col(xs + (size_t)(c0 + c) * LDA, W[(size_t)c * ldw + o], acc);
+}
+// acc[a] += sum_o gs[o0 + o][a] * Wrow[o]       (Wrow contiguous)
+__device__ __forceinline__ void row_dot(const float* gs, int o0, int nO, const float* __restrict__ Wrow, float* acc) {
+  for (int o = 0; o < nO; ++o) axpy_col(gs + (size_t)(o0 + o) * LDA, Wrow[o], acc);
 }
 
 __global__ void k_embed(So3kDims D, int N, const int* __restrict__ z, const float* __restrict__ emb,
@@ -53,12 +57,12 @@ __global__ void __launch_bounds__(NT)
 k_node_proj(So3kDims D, int N, const float* __restrict__ x, const float* __restrict__ Wq_f,
             const float* __restrict__ Wq_g, const float* __restrict__ Wk_f, const float* __restrict__ Wk_g,
             const float* __restrict__ Wv_f, float* __restrict__ proj) {
-  SO3K_DYN_SMEM(float, xs);                     // [TA][F]
+  SO3K_DYN_SMEM(float, xs);                     // [F][LDA]
   const int F = D.F;
   const int a0 = blockIdx.x * TA;
   for (int t = threadIdx.x; t < TA * F; t += NT) {
     int a = t / F, f = t % F;
-    xs[t] = (a0 + a < N) ? x[(size_t)(a0 + a) * F + f] : 0.f;
+    xs[f * LDA + a] = (a0 + a < N) ? x[(size_t)(a0 + a) * F + f] : 0.f;
   }
   __syncthreads();
   for (int o = threadIdx.x; o < 5 * F; o += NT) {
@@ -76,7 +80,7 @@ k_node_proj(So3kDims D, int N, const float* __restrict__ x, const float* __restr
     float acc[TA];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = 0.f;
-    col_dot(xs, F, hd * dsz, dsz, W + (size_t)hd * dsz * dsz, dsz, oo, acc);
+    col_dot(xs, hd * dsz, dsz, W + (size_t)hd * dsz * dsz, dsz, oo, acc);
 #pragma unroll
     for (int a = 0; a < TA; ++a)
       if (a0 + a < N) proj[(size_t)(a0 + a) * 5 * F + o] = acc[a];
@@ -88,12 +92,12 @@ __global__ void __launch_bounds__(NT)
 k_node_proj_bwd(So3kDims D, int N, const float* __restrict__ gproj, const float* __restrict__ Wq_f,
                 const float* __restrict__ Wq_g, const float* __restrict__ Wk_f, const float* __restrict__ Wk_g,
                 const float* __restrict__ Wv_f, float* __restrict__ xbar) {
-  SO3K_DYN_SMEM(float, gs);                     // [TA][5F]
+  SO3K_DYN_SMEM(float, gs);                     // [5F][LDA]
   const int F = D.F, F5 = 5 * D.F;
   const int a0 = blockIdx.x * TA;
   for (int t = threadIdx.x; t < TA * F5; t += NT) {
     int a = t / F5, o = t % F5;
-    gs[t] = (a0 + a < N) ? gproj[(size_t)(a0 + a) * F5 + o] : 0.f;
+    gs[o * LDA + a] = (a0 + a < N) ? gproj[(size_t)(a0 + a) * F5 + o] : 0.f;
   }
   __syncthreads();
   for (int f = threadIdx.x; f < F; f += NT) {
@@ -111,7 +115,7 @@ k_node_proj_bwd(So3kDims D, int N, const float* __restrict__ gproj, const float*
         default: W = Wv_f; dsz = D.dh; break;
       }
       int hd = f / dsz, c = f % dsz;
-      row_dot(gs, F5, seg * F + hd * dsz, dsz, W + ((size_t)hd * dsz + c) * dsz, acc);
+      row_dot(gs, seg * F + hd * dsz, dsz, W + ((size_t)hd * dsz + c) * dsz, acc);
     }
 #pragma unroll
     for (int a = 0; a < TA; ++a)
@@ -126,13 +130,13 @@ k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __re
               float* __restrict__ chi2, float* __restrict__ bcoef) {
   SO3K_DYN_SMEM(float, sm);
   const int F = D.F, nl = D.nl, M = D.M, FI = D.F + D.nl;
-  float* ys = sm;                 // [TA][FI]
-  float* cs = ys + TA * FI;       // [TA][M]
+  float* ys = sm;                 // [FI][LDA]
+  float* cs = ys + FI * LDA;      // [TA][M]
   float* bs = cs + TA * M;        // [TA][nl]
   const int a0 = blockIdx.x * TA;
   for (int t = threadIdx.x; t < TA * F; t += NT) {
     int a = t / F, f = t % F;
-    ys[a * FI + f] = (a0 + a < N) ? x1[(size_t)(a0 + a) * F + f] : 0.f;
+    ys[f * LDA + a] = (a0 + a < N) ? x1[(size_t)(a0 + a) * F + f] : 0.f;
   }
   for (int t = threadIdx.x; t < TA * M; t += NT) {
     int a = t / M, m = t % M;
@@ -143,7 +147,7 @@ k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __re
     int a = t / nl, l = t % nl;
     float s = 0.f;
     for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s += cs[a * M + m] * cs[a * M + m] * D.m_cg[m];
-    ys[a * FI + F + l] = s;
+    ys[(F + l) * LDA + a] = s;
   }
   __syncthreads();
   for (int o = threadIdx.x; o < FI; o += NT) {
@@ -151,11 +155,11 @@ k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __re
     float bo = bias[o];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = bo;
-    col_dot(ys, FI, 0, FI, W, FI, o, acc);
+    col_dot(ys, 0, FI, W, FI, o, acc);
     if (o < F) {
 #pragma unroll
       for (int a = 0; a < TA; ++a)
-        if (a0 + a < N) x2[(size_t)(a0 + a) * F + o] = ys[a * FI + o] + acc[a];
+        if (a0 + a < N) x2[(size_t)(a0 + a) * F + o] = ys[o * LDA + a] + acc[a];
     } else {
 #pragma unroll
       for (int a = 0; a < TA; ++a) {
@@ -177,14 +181,14 @@ k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float
                   const float* __restrict__ chibar_out, float* __restrict__ xbar1, float* __restrict__ chibar1) {
   SO3K_DYN_SMEM(float, sm);
   const int F = D.F, nl = D.nl, M = D.M, FI = D.F + D.nl;
-  float* gs = sm;                 // [TA][FI]  = [xbar_out | bbar]
-  float* cs = gs + TA * FI;       // [TA][M]   chi1
+  float* gs = sm;                 // [FI][LDA] = [xbar_out | bbar] transposed
+  float* cs = gs + FI * LDA;      // [TA][M]   chi1
   float* cb = cs + TA * M;        // [TA][M]   chibar_out
   float* Gb = cb + TA * M;        // [TA][nl]  gradient wrt l0(chi1)
   const int a0 = blockIdx.x * TA;
   for (int t = threadIdx.x; t < TA * F; t += NT) {
     int a = t / F, f = t % F;
-    gs[a * FI + f] = (a0 + a < N) ? xbar_out[(size_t)(a0 + a) * F + f] : 0.f;
+    gs[f * LDA + a] = (a0 + a < N) ? xbar_out[(size_t)(a0 + a) * F + f] : 0.f;
   }
   for (int t = threadIdx.x; t < TA * M; t += NT) {
     int a = t / M, m = t % M;
@@ -197,18 +201,18 @@ k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float
     int a = t / nl, l = t % nl;
     float s = 0.f;
     for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s += cb[a * M + m] * cs[a * M + m];
-    gs[a * FI + F + l] = s;       // bbar
+    gs[(F + l) * LDA + a] = s;    // bbar
   }
   __syncthreads();
   for (int c = threadIdx.x; c < FI; c += NT) {
     float acc[TA];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = 0.f;
-    row_dot(gs, FI, 0, FI, W + (size_t)c * FI, acc);
+    row_dot(gs, 0, FI, W + (size_t)c * FI, acc);
     if (c < F) {
 #pragma unroll
       for (int a = 0; a < TA; ++a)
-        if (a0 + a < N) xbar1[(size_t)(a0 + a) * F + c] = gs[a * FI + c] + acc[a];
+        if (a0 + a < N) xbar1[(size_t)(a0 + a) * F + c] = gs[c * LDA + a] + acc[a];
     } else {
 #pragma unroll
       for (int a = 0; a < TA; ++a) Gb[a * nl + (c - F)] = acc[a];
@@ -233,14 +237,14 @@ k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict_
           float* __restrict__ e_atom, float* __restrict__ xbar) {
   SO3K_DYN_SMEM(float, sm);
   const int F = D.F;
-  float* xs = sm;               // [TA][F]
-  float* ab = xs + TA * F;      // [TA][F]  abar
-  float* es = ab + TA * F;      // [TA][F]  silu(a) * W2
+  float* xs = sm;               // [F][LDA]
+  float* ab = xs + F * LDA;     // [F][LDA] abar
+  float* es = ab + F * LDA;     // [TA][F]  silu(a) * W2
   float* coef = es + TA * F;    // [TA]
   const int a0 = blockIdx.x * TA;
   for (int t = threadIdx.x; t < TA * F; t += NT) {
     int a = t / F, f = t % F;
-    xs[t] = (a0 + a < N) ? x[(size_t)(a0 + a) * F + f] : 0.f;
+    xs[f * LDA + a] = (a0 + a < N) ? x[(size_t)(a0 + a) * F + f] : 0.f;
   }
   if (threadIdx.x < TA) {
     int a = a0 + threadIdx.x;
@@ -257,14 +261,14 @@ k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict_
     float bo = b1[o];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = bo;
-    col_dot(xs, F, 0, F, W1, F, o, acc);
+    col_dot(xs, 0, F, W1, F, o, acc);
     float w2 = W2[o];
 #pragma unroll
     for (int a = 0; a < TA; ++a) {
       float s, ds;
       so3k_silu_d(acc[a], &s, &ds);
       es[a * F + o] = s * w2;
-      ab[a * F + o] = ds * w2 * coef[a];
+      ab[o * LDA + a] = ds * w2 * coef[a];
     }
   }
   __syncthreads();
@@ -284,7 +288,7 @@ k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict_
     float acc[TA];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = 0.f;
-    row_dot(ab, F, 0, F, W1 + (size_t)c * F, acc);
+    row_dot(ab, 0, F, W1 + (size_t)c * F, acc);
 #pragma unroll
     for (int a = 0; a < TA; ++a)
       if (a0 + a < N) xbar[(size_t)(a0 + a) * F + c] = acc[a];
@@ -317,7 +321,7 @@ void so3k_launch_embed(const So3kDims& D, int N, const int* z, const float* emb,
 
 void so3k_launch_node_proj(const So3kDims& D, int N, const float* x, const float* p, const LayerParams& lp,
                            float* proj, cudaStream_t st) {
-  size_t smem = sizeof(float) * TA * D.F;
+  size_t smem = sizeof(float) * LDA * D.F;
   SO3K_SET_MAX_SMEM(k_node_proj, smem);
   SO3K_LAUNCH(k_node_proj, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, p + lp.fb.Wq, p + lp.gb.Wq,
               p + lp.fb.Wk, p + lp.gb.Wk, p + lp.fb.Wv, proj);
@@ -325,7 +329,7 @@ void so3k_launch_node_proj(const So3kDims& D, int N, const float* x, const float
 
 void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* p, const LayerParams& lp,
                                float* xbar, cudaStream_t st) {
-  size_t smem = sizeof(float) * TA * 5 * D.F;
+  size_t smem = sizeof(float) * LDA * 5 * D.F;
   SO3K_SET_MAX_SMEM(k_node_proj_bwd, smem);
   SO3K_LAUNCH(k_node_proj_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, gproj, p + lp.fb.Wq, p + lp.gb.Wq,
               p + lp.fb.Wk, p + lp.gb.Wk, p + lp.fb.Wv, xbar);
@@ -333,7 +337,7 @@ void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, con
 
 void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const float* chi1, const float* p,
                              const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st) {
-  size_t smem = sizeof(float) * TA * (D.F + D.nl + D.M + D.nl);
+  size_t smem = sizeof(float) * (LDA * (D.F + D.nl) + TA * (D.M + D.nl));
   SO3K_SET_MAX_SMEM(k_interaction, smem);
   SO3K_LAUNCH(k_interaction, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x1, chi1, p + lp.int_W, p + lp.int_b,
               x2, chi2, bcoef);
@@ -342,7 +346,7 @@ void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const fl
 void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, const float* bcoef, const float* p,
                                  const LayerParams& lp, const float* xbar_out, const float* chibar_out, float* xbar1,
                                  float* chibar1, cudaStream_t st) {
-  size_t smem = sizeof(float) * TA * (D.F + D.nl + 2 * D.M + D.nl);
+  size_t smem = sizeof(float) * (LDA * (D.F + D.nl) + TA * (2 * D.M + D.nl));
   SO3K_SET_MAX_SMEM(k_interaction_bwd, smem);
   SO3K_LAUNCH(k_interaction_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, chi1, bcoef, p + lp.int_W,
               xbar_out, chibar_out, xbar1, chibar1);
@@ -350,7 +354,7 @@ void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, co
 
 void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* p,
                          const ModelLayout& ml, float out_scale, float* e_atom, float* xbar, cudaStream_t st) {
-  size_t smem = sizeof(float) * (3 * TA * D.F + TA);
+  size_t smem = sizeof(float) * (2 * LDA * D.F + TA * D.F + TA);
   SO3K_SET_MAX_SMEM(k_readout, smem);
   SO3K_LAUNCH(k_readout, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, z, p + ml.out_W1, p + ml.out_b1,
               p + ml.out_W2, p + ml.out_b2, p + ml.scale, p + ml.shift, out_scale, e_atom, xbar);
