@@ -292,7 +292,8 @@ void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, f
   const size_t N = w.g.N, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
   {
     PROF(CAT_READOUT);
-    so3k_launch_readout(D, (int)N, w.x + (size_t)D.L * N * D.F, z, h->params, h->layout, out_scale, e_atom, w.xbar_a, st);
+    so3k_launch_readout(D, (int)N, w.x + (size_t)D.L * N * D.F, z, h->params, h->params_T, h->layout, out_scale, e_atom,
+                        w.xbar_a, st);
   }
   cudaMemsetAsync(w.chibar_a, 0, sizeof(float) * N * D.M, st);
   cudaMemsetAsync(w.rbar, 0, sizeof(float) * Pe * 3, st);
@@ -303,7 +304,7 @@ void stage_layer_bwd_a(HandleImpl* h, Workspace& w, int t, cudaStream_t st) {
   const So3kDims& D = h->dims;
   const size_t N = w.g.N;
   PROF(CAT_INTERACTION_BWD);
-  so3k_launch_interaction_bwd(D, (int)N, w.chi1 + (size_t)t * N * D.M, w.bcoef + (size_t)t * N * D.nl, h->params,
+  so3k_launch_interaction_bwd(D, (int)N, w.chi1 + (size_t)t * N * D.M, w.bcoef + (size_t)t * N * D.nl, h->params_T,
                               h->layout.layers[t], w.xbar_a, w.chibar_a, w.xbar_b, w.chibar_b, st);
 }
 
@@ -351,7 +352,7 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
   if (t > 0) {
     // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
     { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, w.chibar_b, w.chibar_a, st); }     // chibar_a <- d/d chi_t
-    { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, (int)N, w.gproj, prm, lp, w.xbar_b, st); }   // xbar_b += proj^T
+    { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, (int)N, w.gproj, h->params_T, lp, w.xbar_b, st); }   // xbar_b += proj^T
     cudaMemcpyAsync(w.xbar_a, w.xbar_b, sizeof(float) * N * F, cudaMemcpyDeviceToDevice, st);      // xbar_a <- d/d x_t
   }
 }
@@ -408,6 +409,7 @@ int so3k_destroy(so3k_handle* hh) {
   if (!hh) return SO3K_ERR_ARG;
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (h->params) cudaFree(h->params);
+  if (h->params_T) cudaFree(h->params_T);
   if (h->repack) cudaFree(h->repack);
   if (h->tc_images) cudaFree(h->tc_images);
   delete h;
@@ -437,11 +439,16 @@ int so3k_load_params(so3k_handle* hh, const float* blob_dev, size_t n_floats, vo
   if (!h->params) {
     if (cudaMalloc((void**)&h->params, sizeof(float) * ((h->layout.total + 3) & ~(size_t)3)) != cudaSuccess) return SO3K_ERR_CUDA;
   }
+  if (!h->params_T) {
+    if (cudaMalloc((void**)&h->params_T, sizeof(float) * ((h->layout.total + 3) & ~(size_t)3)) != cudaSuccess) return SO3K_ERR_CUDA;
+  }
   size_t per = so3k_edge_repack_floats(D);
   if (!h->repack) {
     if (cudaMalloc((void**)&h->repack, sizeof(float) * per * 2 * D.L) != cudaSuccess) return SO3K_ERR_CUDA;
   }
   cudaMemcpyAsync(h->params, blob_dev, sizeof(float) * n_floats, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(h->params_T, blob_dev, sizeof(float) * n_floats, cudaMemcpyDeviceToDevice, st);
+  so3k_launch_transpose_params(D, h->layout, h->params, h->params_T, st);
   h->wf.resize(D.L);
   h->wg.resize(D.L);
   for (int t = 0; t < D.L; ++t) {

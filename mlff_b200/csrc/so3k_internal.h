@@ -29,6 +29,7 @@ struct so3k_handle {
   So3kDims dims;
   ModelLayout layout;
   float* params = nullptr;      // device copy of the blob (owned)
+  float* params_T = nullptr;    // same layout, with every matrix the backward reads TRANSPOSED (coalesced weight loads)
   bool have_params = false;
 };
 
@@ -65,15 +66,19 @@ void so3k_launch_embed(const So3kDims& D, int N, const int* z, const float* emb,
                        int* dev_status, cudaStream_t st);
 void so3k_launch_node_proj(const So3kDims& D, int N, const float* x, const float* params, const LayerParams& lp,
                            float* proj, cudaStream_t st);
-void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* params,
+// params_T = blob of so3k_launch_transpose_params (per-head q/k/v matrices, interaction and read-out matrices transposed)
+void so3k_launch_transpose_params(const So3kDims& D, const ModelLayout& ml, const float* params, float* params_T,
+                                  cudaStream_t st);
+void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* params_T,
                                const LayerParams& lp, float* xbar /* += */, cudaStream_t st);
 void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const float* chi1, const float* params,
                              const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st);
 void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, const float* bcoef,
-                                 const float* params, const LayerParams& lp, const float* xbar_out,
+                                 const float* params_T, const LayerParams& lp, const float* xbar_out,
                                  const float* chibar_out, float* xbar1, float* chibar1, cudaStream_t st);
 void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* params,
-                         const ModelLayout& ml, float out_scale, float* e_atom, float* xbar, cudaStream_t st);
+                         const float* params_T, const ModelLayout& ml, float out_scale, float* e_atom, float* xbar,
+                         cudaStream_t st);
 void so3k_launch_energy_sum(int B, int n, const float* e_atom, float* E, cudaStream_t st);
 // agg.cu
 void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,

@@ -32,11 +32,6 @@ __device__ __forceinline__ void col_dot(const float* xs, int c0, int nC, const f
                                         float* acc) {
   for (int c = 0; c < nC; ++c) axpy_col(xs + (size_t)(c0 + c) * LDA, W[(size_t)c * ldw + o], acc);
 }
-// acc[a] += sum_o gs[o0 + o][a] * Wrow[o]       (Wrow contiguous)
-__device__ __forceinline__ void row_dot(const float* gs, int o0, int nO, const float* __restrict__ Wrow, float* acc) {
-  for (int o = 0; o < nO; ++o) axpy_col(gs + (size_t)(o0 + o) * LDA, Wrow[o], acc);
-}
-
 __global__ void k_embed(So3kDims D, int N, const int* __restrict__ z, const float* __restrict__ emb,
                         float* __restrict__ x, float* __restrict__ chi, int* __restrict__ status) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,6 +83,7 @@ k_node_proj(So3kDims D, int N, const float* __restrict__ x, const float* __restr
 }
 
 // xbar[a][f] += sum over the five projections of  gproj[a][seg][head(f) block] @ W[seg][head]^T
+// (the W* pointers are the TRANSPOSED per-head matrices: thread = column c reads WT[o][c], coalesced)
 __global__ void __launch_bounds__(NT)
 k_node_proj_bwd(So3kDims D, int N, const float* __restrict__ gproj, const float* __restrict__ Wq_f,
                 const float* __restrict__ Wq_g, const float* __restrict__ Wk_f, const float* __restrict__ Wk_g,
@@ -115,7 +111,7 @@ k_node_proj_bwd(So3kDims D, int N, const float* __restrict__ gproj, const float*
         default: W = Wv_f; dsz = D.dh; break;
       }
       int hd = f / dsz, c = f % dsz;
-      row_dot(gs, seg * F + hd * dsz, dsz, W + ((size_t)hd * dsz + c) * dsz, acc);
+      col_dot(gs, seg * F + hd * dsz, dsz, W + (size_t)hd * dsz * dsz, dsz, c, acc);
     }
 #pragma unroll
     for (int a = 0; a < TA; ++a)
@@ -208,7 +204,7 @@ k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float
     float acc[TA];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = 0.f;
-    row_dot(gs, 0, FI, W + (size_t)c * FI, acc);
+    col_dot(gs, 0, FI, W, FI, c, acc);              // W = int_W^T
     if (c < F) {
 #pragma unroll
       for (int a = 0; a < TA; ++a)
@@ -232,8 +228,8 @@ k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float
 // e = (Dense(F->1)(silu(Dense(F->F)(x)))) * scale[z] + shift[z], masked ; xbar = d(sum e)/dx
 __global__ void __launch_bounds__(NT)
 k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict__ z, const float* __restrict__ W1,
-          const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ b2,
-          const float* __restrict__ scale, const float* __restrict__ shift, float out_scale,
+          const float* __restrict__ W1T, const float* __restrict__ b1, const float* __restrict__ W2,
+          const float* __restrict__ b2, const float* __restrict__ scale, const float* __restrict__ shift, float out_scale,
           float* __restrict__ e_atom, float* __restrict__ xbar) {
   SO3K_DYN_SMEM(float, sm);
   const int F = D.F;
@@ -288,7 +284,7 @@ k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict_
     float acc[TA];
 #pragma unroll
     for (int a = 0; a < TA; ++a) acc[a] = 0.f;
-    row_dot(ab, 0, F, W1 + (size_t)c * F, acc);
+    col_dot(ab, 0, F, W1T, F, c, acc);
 #pragma unroll
     for (int a = 0; a < TA; ++a)
       if (a0 + a < N) xbar[(size_t)(a0 + a) * F + c] = acc[a];
@@ -327,6 +323,31 @@ void so3k_launch_node_proj(const So3kDims& D, int N, const float* x, const float
               p + lp.fb.Wk, p + lp.gb.Wk, p + lp.fb.Wv, proj);
 }
 
+// dst[b][j][i] = src[b][i][j], n x n matrices
+__global__ void k_transpose_sq(int batch, int n, const float* __restrict__ src, float* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < batch * n * n) {
+    const int b = t / (n * n), r = t % (n * n), i = r / n, j = r % n;
+    dst[(size_t)b * n * n + (size_t)j * n + i] = src[t];
+  }
+}
+static void transpose_sq(int batch, int n, const float* src, float* dst, cudaStream_t st) {
+  SO3K_LAUNCH(k_transpose_sq, dim3(so3k_cdiv(batch * n * n, 256)), dim3(256), 0, st, batch, n, src, dst);
+}
+
+void so3k_launch_transpose_params(const So3kDims& D, const ModelLayout& ml, const float* p, float* pT, cudaStream_t st) {
+  for (size_t t = 0; t < ml.layers.size(); ++t) {
+    const LayerParams& lp = ml.layers[t];
+    transpose_sq(D.H, D.dh, p + lp.fb.Wq, pT + lp.fb.Wq, st);
+    transpose_sq(D.H, D.dh, p + lp.fb.Wk, pT + lp.fb.Wk, st);
+    transpose_sq(D.H, D.dh, p + lp.fb.Wv, pT + lp.fb.Wv, st);
+    transpose_sq(D.nl, D.dg, p + lp.gb.Wq, pT + lp.gb.Wq, st);
+    transpose_sq(D.nl, D.dg, p + lp.gb.Wk, pT + lp.gb.Wk, st);
+    transpose_sq(1, D.F + D.nl, p + lp.int_W, pT + lp.int_W, st);
+  }
+  transpose_sq(1, D.F, p + ml.out_W1, pT + ml.out_W1, st);
+}
+
 void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* p, const LayerParams& lp,
                                float* xbar, cudaStream_t st) {
   size_t smem = sizeof(float) * LDA * 5 * D.F;
@@ -352,12 +373,12 @@ void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, co
               xbar_out, chibar_out, xbar1, chibar1);
 }
 
-void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* p,
+void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* p, const float* pT,
                          const ModelLayout& ml, float out_scale, float* e_atom, float* xbar, cudaStream_t st) {
   size_t smem = sizeof(float) * (2 * LDA * D.F + TA * D.F + TA);
   SO3K_SET_MAX_SMEM(k_readout, smem);
-  SO3K_LAUNCH(k_readout, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, z, p + ml.out_W1, p + ml.out_b1,
-              p + ml.out_W2, p + ml.out_b2, p + ml.scale, p + ml.shift, out_scale, e_atom, xbar);
+  SO3K_LAUNCH(k_readout, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, z, p + ml.out_W1, pT + ml.out_W1,
+              p + ml.out_b1, p + ml.out_W2, p + ml.out_b2, p + ml.scale, p + ml.shift, out_scale, e_atom, xbar);
 }
 
 void so3k_launch_energy_sum(int B, int n, const float* e_atom, float* E, cudaStream_t st) {
