@@ -16,7 +16,6 @@
 namespace {
 
 constexpr int WPB = 8;          // warps (rows) per block
-constexpr int TMAX = 8;         // F <= 32*TMAX
 constexpr int AMAX = 16;        // H + nl <= AMAX (stride in the alpha arrays is a multiple of 4)
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -313,9 +313,7 @@ void stage_layer_bwd_a(HandleImpl* h, Workspace& w, int t, cudaStream_t st) {
 void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaStream_t st) {
   const So3kDims& D = h->dims;
   const size_t N = w.g.N, F = D.F, M = D.M, Ast = (D.H + D.nl + 3) & ~3, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
-  const float* prm = h->params;
   const LayerParams& lp = h->layout.layers[t];
-  const float* xt = w.x + (size_t)t * N * F;
   const float* ct = w.chi + (size_t)t * N * M;
   const float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
   const float* proj_t = w.proj + (size_t)t * N * 5 * F;     // kept from the forward

@@ -28,9 +28,9 @@ void so3k_launch_edge_finish(const So3kDims& D, const Graph& g, const float* alp
 
 // ---- tcgen05 path (so3k_edge_tc.cu) -----------------------------------------------------------------------------
 struct TcBlockW {
-  const unsigned char* img;   // [W1 hi | W1 lo | W2c hi | W2c lo] bf16 operand images (shared-memory layout)
-  const float* bias;          // [b1 padded to Fp | b2c padded to Fp]
-  const float* Ws1;           // (nl, Fs)
+  const unsigned char* img;   // [W1 hi | lo | W2c hi | lo | Ws1 hi | lo] bf16 operand images (shared-memory layout)
+  const float* bias;          // [b1x = (rad b1 | sph b1 | 0) over the KC hidden units | b2c padded to Fp]
+  const float* Ws1;           // (nl, Fs) fp32 (epilogue of backward part 2)
   const float* bs1;           // (Fs)
 };
 bool so3k_edge_tc_supported(const So3kDims& D);

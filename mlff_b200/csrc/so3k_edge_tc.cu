@@ -1,29 +1,35 @@
-// Per-edge filter MLPs, attention coefficients and their data-gradients on the 5th-generation tensor cores
-// (tcgen05.mma + TMEM).  Same math and outputs as the fp32 CUDA-core kernels of so3k_edge.cu:
+// The dense part of the edge path on the 5th-generation tensor cores (tcgen05.mma + TMEM): both filter MLPs and
+// their transposes, evaluated once per UNDIRECTED pair (the filter depends on d_ij and on |chi_j - chi_i|^2 only, so
+// w_ij = w_ji).  Same math as the fp32 CUDA-core kernels of so3k_edge.cu:
 //   chi_ij, l0 contraction     mlff/nn/layer/so3krates_layer.py:89-93 ; mlff/sph_ops/contract.py:181-188
 //   RadialSphericalFilter      mlff/nn/layer/so3krates_layer.py:449-465 ; MLP mlff/nn/mlp/mlp.py:21-27
-//   ConvAttentionCoefficients  mlff/nn/layer/so3krates_layer.py:568-586 ; masking/cutoff :500-501, :551-554
 //   backward                   SURVEY.md appendix B (reverse of the above)
+// Everything that gathers or reduces over neighbours (attention coefficients mlff/nn/layer/so3krates_layer.py:568-586,
+// aggregation, q/k gradients) lives in the streaming kernels of so3k_agg.cu, which exchange pair-indexed arrays with
+// the kernels below: filters w[pair][F] (out), filter cotangents wbar[pair][F] (in).
 //
 // Design (one filter block -- fb or gb -- per launch, persistent CTAs, 1 CTA / SM, 512 threads):
 //   * the block's weights live in shared memory for the whole kernel as bf16 hi/lo operand images in the canonical
 //     no-swizzle K-major layout (so3k_tc.cuh; measured at the tcgen05 issue floor, profiles/tc_mma_layout_bench.py):
-//     W1 (N=Fp, K=n_rbf) and W2c (N=Fp, K=KC) -- the radial and spherical second layers stacked along K, so
-//     w = [silu(a1) | silu(a_s)] @ W2c is ONE GEMM.  The backward reads the same W2c image as an MN-major operand
-//     (W2c^T) -- no transposed copy;
-//   * a tile = 128 consecutive receiver-sorted edges = M of one UMMA (M=128, cta_group::1).  Row r of the tile is
-//     TMEM lane r; warp w works on lane quadrant (w & 3) and on column quarter (w >> 2): 4 threads per row;
+//     W1 (N=Fp, K=n_rbf), Ws1 (N=NS, K=16: the first layer of the spherical branch) and W2c (N=Fp, K=KC) -- the radial
+//     and spherical second layers stacked along K, so w = [silu(a1) | silu(a_s)] @ W2c is ONE GEMM.  The backward reads
+//     the same W2c image as an MN-major operand (W2c^T) -- no transposed copy;
+//   * a tile = 128 consecutive pairs = M of one UMMA (M=128, cta_group::1).  Row r of the tile is TMEM lane r; warp w
+//     works on lane quadrant (w & 3) and on column quarter (w >> 2): 4 threads per row;
 //   * every product is 3 MMAs (hi*hi + lo*hi + hi*lo) accumulating in fp32 in TMEM;
-//   * epilogues read TMEM (tcgen05.ld 32x32b), do bias / silu / split in registers and write the NEXT GEMM's A-operand
-//     image directly; the F-wide filter w and its cotangent never leave the SM.
+//   * both first layers run as MMAs into one accumulator whose column k is hidden unit k (the spherical one is written
+//     over the radial padding columns), so epilogue 1 is one uniform loop: tcgen05.ld, + bias, silu, hi/lo split,
+//     store of the NEXT GEMM's A-operand image;
+//   * per-pair inputs come from 32-byte records (k_pair_records), prefetched one tile ahead: no dependent loads.
 // Kernels:
-//   k_edge_tc<0>      forward: rbf -> GEMM1 -> silu -> GEMM2 -> (w+b) q_i k_j -> per-head sums -> alpha
-//   k_edge_tc<1>      backward part 1: recompute w, qbar_i += sbar w k_j, kbar_i += sbar_rev w q_j (segmented
-//                     warp-shuffle reduction over receiver runs, one atomic per run), cutoff cotangent
-//   k_edge_bwd2_tc    backward part 2: wbar image -> GEMM3 (hbar = wbar W2c^T) -> radial cotangent (forward-mode
-//                     rbf' @ W1 from a second GEMM1) and l0-contraction cotangent
-// Algorithmic FLOPs per forward launch pair: 2 blocks x 2 P (K F + F^2 + nl F/4 + F^2/4); the tensor
-// pipe issues 3x that on padded shapes (Fp x KC).
+//   k_pair_records    per pair: d and the l0 contractions of (chi_j - chi_i)
+//   k_filter_tc       records -> operand images -> GEMM1 -> silu -> GEMM2 -> + bias -> staging tile -> one bulk copy
+//                     (cp.async.bulk) of the tile's contiguous 128 x F block of w
+//   k_edge_bwd2_tc    wbar tile -> operand image -> GEMM3 (hbar = wbar W2c^T); pre-activations and the forward-mode
+//                     radial derivative from two GEMM1s (rbf, rbf'); epilogue: radial cotangent dbar and l0-contraction
+//                     cotangents gbar, added onto the canonical edge of the pair
+// Algorithmic FLOPs per k_filter_tc launch: 2 C (K F + F^2 + nl F/4 + F^2/4), C pairs; the tensor pipe
+// issues 3x that on padded shapes (Fp x KC).
 #include "so3k_internal.h"
 #include "so3k_edge.h"
 #ifndef SO3K_EMU
@@ -37,9 +43,7 @@ constexpr int NC = 512;        // compute threads per CTA (16 warps: 4 TMEM lane
 constexpr int NW = NC / 32;    // compute warps
 constexpr int NT = NC;         // (a 17th, issue-only warp was tried: the warp-allocation granularity of 4 then caps registers at 96/thread)
 constexpr int ISSUER = 0;      // thread that issues the MMAs
-constexpr int TM = 128;        // edges per tile
-constexpr int WIN = 32;        // column window of the backward staging tiles
-constexpr int WS = 36;         // row stride (floats) of a staging tile: 36 mod 32 = 4 -> conflict-free LDS.128
+constexpr int TM = 128;        // pairs per tile
 
 struct TcDims {
   int Fp, KC, K0, NS;          // padded N, padded K of GEMM2, K of GEMM1, padded width of the spherical hidden layer
@@ -149,11 +153,6 @@ __device__ __forceinline__ void silu_fast_d(float a, float* y, float* dy) {
   *y = a * s;
   *dy = s * (1.0f + a * (1.0f - s));
 }
-__device__ __forceinline__ float cutoff_fast(float d, float r_cut) {
-  // argument in [0, pi): __cosf absolute error ~2^-21
-  return d < r_cut ? 0.5f * (__cosf(d * (3.14159265358979323846f / r_cut)) + 1.0f) : 0.0f;
-}
-
 // shared-memory carve-up common to the tensor-core edge kernels
 struct TcSmem {
   unsigned char *W1hi, *W1lo, *W2hi, *W2lo, *Wshi, *Wslo, *A1hi, *A1lo, *A0hi, *A0lo, *A0shi, *A0slo;
@@ -829,16 +828,22 @@ extern "C" void so3k_tc_phase_dump(void) {
   unsigned long long h[3][16];
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(h, g_tc_phase, sizeof(h));
-  // forward names; backward part 1 reuses 0-6, then 7 = (none), 8 = wait2, 9 = transposed epilogue, 10 = tail, 11 = sync;
-  // backward part 2: 0 S0+alphabar, 1 sync, 2 issue GEMM1s, 3 wait, 4 wbar image (gathers), 5 sync, 6 issue GEMM3 + next
-  // tile's metadata, 7 wait, 8 epilogue, 9 reduce+sync, 10 stores+sync
-  const char* names[13] = {"S0", "sync", "issue1", "wait1", "epi1", "sync", "issue2", "gather", "wait2", "qkstore+sync",
-                           "epi2", "sync", "alpha+sync"};
+  // phase names per kernel index (TC_PHASE(kernel, phase)): 0 = k_filter_tc, 2 = k_edge_bwd2_tc
+  static const char* const names[3][13] = {
+      {"records+images", "sync", "issue GEMM1", "wait", "epilogue1", "sync", "issue GEMM2", "wait", "epilogue2",
+       "sync+bulk store", "-", "-", "-"},
+      {"-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"},
+      {"rbf images", "sync", "issue GEMM1s + wbar loads", "wait", "wbar image", "sync", "issue GEMM3 + prefetch", "wait",
+       "epilogue", "reduce+sync", "stores+sync", "-", "-"}};
   for (int k = 0; k < 3; ++k) {
     if (!h[k][15]) continue;
     double tot = 0;
     printf("tc phase timing kernel %d (%llu tiles of block 0):", k, h[k][15]);
-    for (int p = 0; p < 13; ++p) { printf(" %s=%.0f", names[p], (double)h[k][p] / h[k][15]); tot += (double)h[k][p] / h[k][15]; }
+    for (int p = 0; p < 13; ++p) {
+      if (names[k][p][0] == '-' && !h[k][p]) continue;
+      printf(" %s=%.0f", names[k][p], (double)h[k][p] / h[k][15]);
+      tot += (double)h[k][p] / h[k][15];
+    }
     printf(" | total=%.0f cycles/tile\n", tot);
   }
   memset(h, 0, sizeof(h));

@@ -158,9 +158,7 @@ __global__ void k_rowsort_geom(int N, int n, int P, const int* __restrict__ rowp
       }
     }
     float d = sqrtf(rx * rx + ry * ry + rz * rz);
-    float inv = d > 0.f ? 1.0f / d : 0.f;
     geom[dst] = make_float4(d > 0.f ? rx / d : 0.f, d > 0.f ? ry / d : 0.f, d > 0.f ? rz / d : 0.f, d);
-    (void)inv;
   }
 }
 
