@@ -1,0 +1,184 @@
+"""MD inner loop around the force call, state resident on the device.
+
+Mirrors the pieces of the reference's `mdx` package that sit immediately around the hot path, with the same names and
+update rules, on torch tensors instead of jax arrays:
+
+* `AtomsX`            mlff/mdx/atoms.py (positions, momenta, masses, numbers, cell, neighbours; get_* accessors :202-246,
+                      `update_positions(..., update_neighbors=True)` :365-383)
+* `SkinNeighborList`  mlff/mdx/atoms.py:488-510 -> glp `quadratic_neighbor_list(cell, cutoff, skin, capacity_multiplier)`:
+                      the list is built with cutoff + skin at reference positions and re-used until an atom has moved
+                      more than skin / 2; edges between r_cut and r_cut + skin contribute exactly zero (cosine cutoff)
+* `CalculatorX`       mlff/mdx/calculator.py:46-49 (energy + forces of an AtomsX)
+* `VelocityVerletX`   mlff/mdx/integrator.py:313-342 (the reference evaluates the forces twice per step; the second
+                      evaluation of a step is the first of the next one, so it is cached here -- same trajectory)
+* `simulate`          mlff/mdx/simulate.py:60-82 (kinetic / potential energy per step, one host read-back at the end)
+
+Everything per step is O(N) tensor arithmetic on the device plus the engine calls; the only host synchronisation is the
+scalar "has any atom moved more than skin / 2" decision of the neighbour list (and the list size after a rebuild).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+KB_EV = 8.617333262e-5            # Boltzmann constant in eV / K (ase.units.kB)
+FS = 0.09822694788464063          # one femtosecond in ASE time units (ase.units.fs)
+
+
+class SkinNeighborList:
+    """Neighbour list with a skin, re-used while no atom has moved more than skin / 2 since it was built."""
+
+    def __init__(self, engine, cutoff: float, skin: float, cell: Optional[np.ndarray] = None,
+                 pbc: Sequence[bool] = (False, False, False), capacity_multiplier: float = 1.25, mode: Optional[int] = None):
+        self.engine, self.cutoff, self.skin = engine, float(cutoff), float(skin)
+        self.cell = None if cell is None else np.asarray(cell, dtype=np.float64).reshape(3, 3)
+        self.pbc = tuple(bool(b) for b in pbc)
+        self.capacity_multiplier = capacity_multiplier
+        self.mode = mode
+        self.capacity = 0
+        self.reference_positions: Optional[torch.Tensor] = None
+        self.idx_i = self.idx_j = self.shifts = None
+        self.count = 0
+        self.n_builds = 0
+
+    def allocate(self, positions: torch.Tensor) -> 'SkinNeighborList':
+        """Build the list at `positions` (glp `allocate`): sizes the capacity from the actual count."""
+        kw = {} if self.mode is None else {'mode': self.mode}
+        cap = self.capacity if self.capacity > 0 else 64 * int(positions.shape[0]) + 16
+        while True:
+            ii, jj, S, count = self.engine.neighbor_list(positions, self.cutoff + self.skin, cap, cell=self.cell,
+                                                         pbc=self.pbc, **kw)
+            n = int(count.item())
+            if n <= cap:
+                break
+            cap = int(self.capacity_multiplier * n) + 16          # overflow: re-allocate (indices.py:264-272 semantics)
+            if hasattr(self.engine, '_status'):
+                self.engine._status.zero_()
+        if self.capacity == 0 or cap > self.capacity:
+            self.capacity = max(int(self.capacity_multiplier * n) + 16, n)
+        self.idx_i, self.idx_j, self.shifts, self.count = ii[:n], jj[:n], S[:n], n
+        self.reference_positions = positions.clone()
+        self.n_builds += 1
+        return self
+
+    def update(self, positions: torch.Tensor) -> 'SkinNeighborList':
+        """glp `update`: rebuild only if some atom moved more than skin / 2 since the last build."""
+        if self.reference_positions is None:
+            return self.allocate(positions)
+        d2 = ((positions - self.reference_positions) ** 2).sum(-1).max()
+        if float(d2.item()) > (0.5 * self.skin) ** 2:
+            self.allocate(positions)
+        return self
+
+
+@dataclass
+class AtomsX:
+    positions: torch.Tensor                     # (N,3) float64
+    momenta: torch.Tensor                       # (N,3) float64
+    masses: torch.Tensor                        # (N)   float64
+    numbers: torch.Tensor                       # (N)   int32
+    cell: Optional[np.ndarray] = None           # (3,3) row-wise (host)
+    pbc: Sequence[bool] = (False, False, False)
+    neighbors: Optional[SkinNeighborList] = None
+    cache: Optional[Dict[str, torch.Tensor]] = None     # properties evaluated at `positions` (force re-use)
+
+    def get_positions(self): return self.positions
+    def get_momenta(self): return self.momenta
+    def get_masses(self): return self.masses
+    def get_number_of_atoms(self): return int(self.numbers.shape[0])
+    def get_velocities(self): return self.momenta / self.masses[:, None]
+
+    def get_kinetic_energy(self):
+        return 0.5 * (self.momenta * self.get_velocities()).sum()
+
+    def get_temperature(self, eckart_frame: bool = True):
+        """Temperature in eV (mlff/mdx/atoms.py:211-226): 2 E_kin / DOF, DOF = 3n - 6 in the Eckart frame."""
+        n = self.get_number_of_atoms()
+        dof = 3 * n - 6 if eckart_frame else 3 * n
+        return 2.0 * self.get_kinetic_energy() / dof
+
+    def update_positions(self, positions: torch.Tensor, update_neighbors: bool = True) -> 'AtomsX':
+        if update_neighbors:
+            if self.neighbors is None:
+                raise RuntimeError('AtomsX object has no spatial partitioning.')
+            self.neighbors.update(positions)
+        return replace(self, positions=positions, cache=None)
+
+    def update_momenta(self, momenta: torch.Tensor) -> 'AtomsX':
+        return replace(self, momenta=momenta)
+
+    def init_spatial_partitioning(self, engine, cutoff: float, skin: float, capacity_multiplier: float = 1.25,
+                                  mode: Optional[int] = None) -> 'AtomsX':
+        nl = SkinNeighborList(engine, cutoff, skin, self.cell, self.pbc, capacity_multiplier, mode).allocate(self.positions)
+        return replace(self, neighbors=nl, cache=None)
+
+
+class CalculatorX:
+    """energy + forces of an AtomsX through the engine (one structure; the skin list of the atoms object)."""
+
+    def __init__(self, engine, energy_scale: float = 1.0):
+        self.engine = engine
+        self.energy_scale = energy_scale
+        self.n_calls = 0
+
+    def __call__(self, atoms: AtomsX) -> Dict[str, torch.Tensor]:
+        if atoms.cache is not None:
+            return atoms.cache
+        nl = atoms.neighbors
+        periodic = atoms.cell is not None
+        R32 = atoms.positions.to(torch.float32)
+        cell32 = None
+        if periodic:
+            cell32 = torch.as_tensor(np.asarray(atoms.cell, dtype=np.float32), device=R32.device)[None]
+        E, F, _ = self.engine.energy_forces(R32[None], atoms.numbers[None], nl.idx_i[None], nl.idx_j[None], cell32,
+                                            nl.shifts[None] if periodic else None)
+        self.n_calls += 1
+        out = {'energy': self.energy_scale * E.reshape(()).to(torch.float64),
+               'forces': self.energy_scale * F[0].to(torch.float64)}
+        atoms.cache = out
+        return out
+
+
+class VelocityVerletX:
+    def __init__(self, timestep: float, calculator: CalculatorX):
+        self.timestep, self.calculator = float(timestep), calculator
+
+    @classmethod
+    def create(cls, timestep, calculator):
+        return cls(timestep, calculator)
+
+    def step(self, atoms: AtomsX):
+        masses = atoms.get_masses()[:, None]
+        forces = self.calculator(atoms)['forces']
+        p = atoms.get_momenta() + 0.5 * self.timestep * forces
+        pos = atoms.get_positions()
+        atoms_displaced = atoms.update_positions(pos + self.timestep * p / masses, update_neighbors=True)
+        atoms_displaced = atoms_displaced.update_momenta(p)
+        properties = self.calculator(atoms_displaced)
+        forces = properties['forces']
+        atoms_displaced = atoms_displaced.update_momenta(atoms_displaced.get_momenta() + 0.5 * self.timestep * forces)
+        return self, atoms_displaced, properties
+
+
+def simulate(integrator: VelocityVerletX, atoms: AtomsX, steps: int):
+    """Take `steps` steps; returns (atoms, {'kinetic_energy', 'potential_energy', 'temperature'} as (steps,) numpy arrays)."""
+    ek, ep = [], []
+    for _ in range(steps):
+        integrator, atoms, prop = integrator.step(atoms)
+        ek.append(atoms.get_kinetic_energy())
+        ep.append(prop['energy'])
+    ek_t, ep_t = torch.stack(ek).cpu().numpy(), torch.stack(ep).cpu().numpy()       # the only read-back of the run
+    n = atoms.get_number_of_atoms()
+    return atoms, {'kinetic_energy': ek_t, 'potential_energy': ep_t,
+                   'temperature': 2.0 * ek_t / max(3 * n - 6, 1) / KB_EV}
+
+
+def maxwell_boltzmann_momenta(masses: torch.Tensor, temperature_K: float, seed: int = 0) -> torch.Tensor:
+    """Momenta drawn from a Maxwell-Boltzmann distribution, centre-of-mass momentum removed (ASE convention)."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    xi = torch.randn(masses.shape[0], 3, generator=g, dtype=torch.float64).to(masses.device)
+    p = xi * torch.sqrt(masses * KB_EV * temperature_K)[:, None]
+    return p - p.mean(0, keepdim=True)

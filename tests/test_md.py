@@ -1,0 +1,155 @@
+"""MD inner loop (mlff_b200/md.py): the integrator / skin-list logic against a plain numpy velocity Verlet
+driven by the oracle.  CPU tests use an oracle-backed engine stand-in; GPU tests use the CUDA engine."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..', 'oracle'))
+import so3k_oracle as o
+from conftest import golden
+from mlff_b200 import md
+
+MASS = {1: 1.008, 6: 12.011, 8: 15.999}
+
+
+class OracleEngine:
+    """neighbor_list / energy_forces with the engine's signatures, computed by the oracle in float64 (test stand-in)."""
+
+    def __init__(self, cfg, params):
+        self.cfg, self.params = cfg, params
+
+    def neighbor_list(self, positions, cutoff, capacity, cell=None, pbc=(False, False, False), **kw):
+        pos = positions.detach().cpu().numpy()
+        c = np.eye(3) * 1e3 if cell is None else cell
+        i, j, S = o.primitive_neighbor_list(pos, c, pbc, cutoff)
+        n = len(i)
+        ii = torch.full((capacity,), -1, dtype=torch.int32)
+        jj = torch.full((capacity,), -1, dtype=torch.int32)
+        SS = torch.zeros((capacity, 3), dtype=torch.int32)
+        m = min(n, capacity)
+        ii[:m], jj[:m], SS[:m] = torch.as_tensor(i[:m]), torch.as_tensor(j[:m]), torch.as_tensor(S[:m])
+        return ii, jj, SS, torch.tensor([n])
+
+    def energy_forces(self, R, z, idx_i, idx_j, cell=None, cell_offset=None):
+        E, F, _ = o.energy_forces(self.cfg, self.params, R[0].double().numpy(), z[0].numpy(), idx_i[0].numpy(),
+                                  idx_j[0].numpy(), cell=None if cell is None else cell[0].double().numpy(),
+                                  cell_offset=None if cell_offset is None else cell_offset[0].numpy())
+        return E.reshape(1, 1), F[None], None
+
+
+def reference_trajectory(cfg, params, R0, z, p0, masses, dt, steps, r_cut=5.0):
+    """numpy velocity Verlet with the exact-cutoff list rebuilt at every step and oracle forces (float64)."""
+    def forces(R):
+        nl = o.get_indices(R[None], z[None], r_cut)
+        _, F, _ = o.energy_forces(cfg, params, R, z, nl['idx_i'][0], nl['idx_j'][0])
+        return F.numpy()
+    R, p = R0.copy(), p0.copy()
+    F = forces(R)
+    for _ in range(steps):
+        p = p + 0.5 * dt * F
+        R = R + dt * p / masses[:, None]
+        F = forces(R)
+        p = p + 0.5 * dt * F
+    return R, p
+
+
+def ethanol_state(device='cpu'):
+    g = golden('ethanol_32.npz')
+    R0, z = g['R'][0].astype(np.float64), g['z'].astype(np.int64)
+    masses = np.array([MASS[int(a)] for a in z])
+    p0 = md.maxwell_boltzmann_momenta(torch.as_tensor(masses), 300.0, seed=1).numpy()
+    atoms = md.AtomsX(positions=torch.as_tensor(R0, device=device), momenta=torch.as_tensor(p0, device=device),
+                      masses=torch.as_tensor(masses, device=device), numbers=torch.as_tensor(z, dtype=torch.int32, device=device))
+    return R0, z, masses, p0, atoms
+
+
+def test_velocity_verlet_with_skin_list_matches_plain_integrator():
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    params = o.init_params(cfg, 0, embed_scale=4.0)
+    R0, z, masses, p0, atoms = ethanol_state()
+    eng = OracleEngine(cfg, params)
+    atoms = atoms.init_spatial_partitioning(eng, cutoff=5.0, skin=1.0)
+    calc = md.CalculatorX(eng)
+    integ = md.VelocityVerletX.create(0.5 * md.FS, calc)
+    steps = 6
+    atoms, stats = md.simulate(integ, atoms, steps)
+    R_ref, p_ref = reference_trajectory(cfg, params, R0, z, p0, masses, 0.5 * md.FS, steps)
+    # skin edges (5 A <= d < 6 A) contribute exactly zero, so the trajectories agree up to the float32 rounding of the
+    # positions handed to the calculator (the engine's input type)
+    np.testing.assert_allclose(atoms.positions.numpy(), R_ref, atol=1e-7)
+    np.testing.assert_allclose(atoms.momenta.numpy(), p_ref, atol=1e-6)
+    assert calc.n_calls == steps + 1                      # force re-use: one evaluation per step (+ the initial one)
+    assert atoms.neighbors.n_builds == 1                  # nothing moved 0.5 A in 3 fs
+    assert stats['kinetic_energy'].shape == (steps,) and np.isfinite(stats['potential_energy']).all()
+
+
+def test_skin_list_rebuilds_after_half_skin_displacement():
+    cfg = o.OracleConfig(F=36, n_layers=1)
+    eng = OracleEngine(cfg, None)
+    _, _, _, _, atoms = ethanol_state()
+    atoms = atoms.init_spatial_partitioning(eng, cutoff=3.0, skin=0.4)
+    n0 = atoms.neighbors.count
+    small = atoms.positions.clone()
+    small[0, 0] += 0.19
+    a1 = atoms.update_positions(small)
+    assert a1.neighbors.n_builds == 1
+    big = atoms.positions.clone()
+    big[0, 0] += 0.21
+    a2 = atoms.update_positions(big)
+    assert a2.neighbors.n_builds == 2 and a2.neighbors.count > 0 and n0 > 0
+    i, j, _ = o.primitive_neighbor_list(big.numpy(), np.eye(3) * 1e3, (False,) * 3, 3.4)
+    assert a2.neighbors.count == len(i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('flags', [0, 3])
+def test_md_on_device_matches_oracle_trajectory(flags):
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.engine import So3kEngine
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    params = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = So3kEngine(So3kratesConfig(F=36, n_layer=2), 'cuda:0', flags)
+    eng.load_params({k: np.asarray(v, np.float32) for k, v in params.items()})
+    R0, z, masses, p0, atoms = ethanol_state('cuda:0')
+    atoms = atoms.init_spatial_partitioning(eng, cutoff=5.0, skin=1.0)
+    calc = md.CalculatorX(eng)
+    steps = 10
+    atoms, stats = md.simulate(md.VelocityVerletX.create(0.5 * md.FS, calc), atoms, steps)
+    assert eng.check_status() == 0
+    R_ref, p_ref = reference_trajectory(cfg, params, R0, z, p0, masses, 0.5 * md.FS, steps)
+    assert np.abs(atoms.positions.cpu().numpy() - R_ref).max() < 1e-5
+    assert np.abs(atoms.momenta.cpu().numpy() - p_ref).max() < 1e-4
+    assert calc.n_calls == steps + 1
+
+
+@pytest.mark.gpu
+def test_md_periodic_box_conserves_energy_and_reuses_the_list():
+    from common import jittered_lattice
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.engine import So3kEngine
+    N, box = 1000, 21.5
+    pos = jittered_lattice(N, box, seed=4)
+    z = np.where(np.arange(N) % 3 == 0, 8, 1)
+    masses = np.array([MASS[int(a)] for a in z])
+    cfg = o.OracleConfig()
+    params = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = So3kEngine(So3kratesConfig(n_layer=3), 'cuda:0', 3)
+    eng.load_params({k: np.asarray(v, np.float32) for k, v in params.items()})
+    dev = 'cuda:0'
+    m_t = torch.as_tensor(masses, device=dev)
+    atoms = md.AtomsX(positions=torch.as_tensor(pos, device=dev), momenta=md.maxwell_boltzmann_momenta(m_t, 300.0, seed=2),
+                      masses=m_t, numbers=torch.as_tensor(z, dtype=torch.int32, device=dev), cell=np.eye(3) * box,
+                      pbc=(True, True, True))
+    atoms = atoms.init_spatial_partitioning(eng, cutoff=5.0, skin=0.5)
+    calc = md.CalculatorX(eng)
+    steps = 40
+    atoms, stats = md.simulate(md.VelocityVerletX.create(0.25 * md.FS, calc), atoms, steps)
+    assert eng.check_status() == 0
+    etot = stats['kinetic_energy'] + stats['potential_energy']
+    # NVE: the total energy fluctuates by a small fraction of the kinetic energy and does not drift
+    assert np.abs(etot - etot[0]).max() < 0.02 * stats['kinetic_energy'].mean()
+    assert atoms.neighbors.n_builds < steps // 4          # the skin list is re-used
+    assert calc.n_calls == steps + 1
