@@ -396,3 +396,22 @@ def test_domain_decomposition_virtual_ranks(solid, flags):
         F[rk.plan.local_atoms[:rk.plan.n_own].cpu().numpy()] = rk.forces[:rk.plan.n_own].cpu().numpy()
     assert abs(E - float(g['E'])) <= E_RTOL * abs(float(g['E']))
     assert np.abs(F - g['F']).max() < F_ATOL
+
+
+# ---- batched neighbour lists of a training set in one launch (mlff_b200/indexing.py) ----------------------------------
+def test_batched_get_indices_matches_reference_semantics(ethanol):
+    from mlff_b200.indexing import get_indices
+    cfg = o.OracleConfig(F=36, n_layers=1)
+    eng = make(cfg, o.init_params(cfg, 0))
+    B = 32
+    R = ethanol['R'][:B].astype(np.float64)
+    z = np.tile(ethanol['z'][None], (B, 1))
+    Rp = np.concatenate([R, np.zeros((B, 2, 3))], 1)            # two padding atoms per frame (z = 0, at the origin)
+    zp = np.concatenate([z, np.zeros((B, 2), z.dtype)], 1)
+    for r_cut in (5.0, 2.0):                                     # 2 A: ragged lists, frames of different length
+        Rr = Rp.copy()
+        Rr[3] *= 1.3                                             # stretch one frame so that its list is shorter
+        ref = o.get_indices(Rr, zp, r_cut)
+        out = get_indices(eng, Rr, zp, r_cut)
+        assert out['idx_i'].shape == ref['idx_i'].shape
+        assert (out['idx_i'].cpu().numpy() == ref['idx_i']).all() and (out['idx_j'].cpu().numpy() == ref['idx_j']).all()
