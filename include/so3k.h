@@ -135,6 +135,15 @@ int so3k_energy_forces(so3k_handle* h, int32_t B, int32_t n, int32_t P,
                        float* E, float* F, float* e_atom,
                        void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
 
+/* ---- stress ---------------------------------------------------------------------------------
+ * dE/d(strain) of the evaluation that last used `workspace` (so3k_energy_forces with the same B, n, P):
+ *   stress[b] = sym( sum_e dE/dr_e (x) r_e ) over the edges of structure b, r_e = R_j - R_i + S@cell,
+ * i.e. what the reference obtains by differentiating the energy through strained positions and cell,
+ * get_energy_force_stress_fn  mlff/nn/stacknet/observable_function.py:152-186 (no volume factor there either).
+ * stress: (B,3,3) f32 device buffer. */
+int so3k_stress(const so3k_handle* h, int32_t B, int32_t n, int32_t P, const void* workspace, size_t workspace_bytes,
+                float* stress, void* stream);
+
 /* ---- MD seam ------------------------------------------------------------------------------
  * Graph(edges, nodes, centers, others, mask) of mlff/utils/structures.py:5 in the
  * 'displacements' convention: edges (P,3) f32 = R_j - R_i after MIC, nodes z (N) i32,

@@ -27,7 +27,7 @@ EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 's
            'so3k_load_params', 'so3k_workspace_bytes', 'so3k_energy_forces', 'so3k_potential_displacements',
            'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count',
            'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect', 'so3k_tc_selftest',
-           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_buffer']
+           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_buffer', 'so3k_stress']
 
 
 class So3kConfigC(C.Structure):
@@ -69,6 +69,8 @@ class So3kLib:
         d.so3k_workspace_bytes.restype = sz
         d.so3k_energy_forces.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]
         d.so3k_energy_forces.restype = C.c_int
+        d.so3k_stress.argtypes = [vp, i32, i32, i32, vp, sz, vp, vp]
+        d.so3k_stress.restype = C.c_int
         d.so3k_potential_displacements.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, sz, vp, vp]
         d.so3k_potential_displacements.restype = C.c_int
         d.so3k_featurise.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -138,6 +140,9 @@ class So3kLib:
                       status, stream=0):
         _check(self.dll.so3k_energy_forces(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E, F, e_atom, ws,
                                            ws_bytes, status, stream), 'so3k_energy_forces')
+
+    def stress(self, h, B, n, P, ws, ws_bytes, stress, stream=0):
+        _check(self.dll.so3k_stress(h, B, n, P, ws, ws_bytes, stress, stream), 'so3k_stress')
 
     def potential_displacements(self, h, N, P, edges, z, centers, others, mask, energy_scale, e_atom, dE_dedges,
                                 forces, ws, ws_bytes, status, stream=0):

@@ -530,7 +530,44 @@ k_forces(int N, const int* __restrict__ rowptr, const int* __restrict__ rev, con
   }
 }
 
+// stress[b] += sym( sum_{e in rows of structure b} rbar_e (x) r_e ),  r_e = d_e u_e : dE/d(strain), the quantity the
+// reference obtains by differentiating through strained positions and cell (observable_function.py:152-186)
+__global__ void __launch_bounds__(WPB * 32)
+k_stress(int N, int n_per, const int* __restrict__ rowptr, const float4* __restrict__ geom, const float* __restrict__ rbar,
+         float* __restrict__ stress) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};               // xx, yy, zz, xy, xz, yz
+  for (int e = beg + lane; e < end; e += 32) {
+    const float4 g = geom[e];
+    const float rx = g.x * g.w, ry = g.y * g.w, rz = g.z * g.w;
+    const float ax = rbar[3 * (size_t)e + 0], ay = rbar[3 * (size_t)e + 1], az = rbar[3 * (size_t)e + 2];
+    s[0] = fmaf(ax, rx, s[0]);
+    s[1] = fmaf(ay, ry, s[1]);
+    s[2] = fmaf(az, rz, s[2]);
+    s[3] += 0.5f * (ax * ry + ay * rx);
+    s[4] += 0.5f * (ax * rz + az * rx);
+    s[5] += 0.5f * (ay * rz + az * ry);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s[k] = warp_sum(s[k]);
+  if (rowok && lane == 0 && beg < end) {
+    float* o = stress + 9 * (size_t)(i / n_per);
+    atomicAdd(o + 0, s[0]); atomicAdd(o + 4, s[1]); atomicAdd(o + 8, s[2]);
+    atomicAdd(o + 1, s[3]); atomicAdd(o + 3, s[3]);
+    atomicAdd(o + 2, s[4]); atomicAdd(o + 6, s[4]);
+    atomicAdd(o + 5, s[5]); atomicAdd(o + 7, s[5]);
+  }
+}
+
 }  // namespace
+
+void so3k_launch_stress(const Graph& g, int B, int n_per, const float* rbar, float* stress, cudaStream_t st) {
+  cudaMemsetAsync(stress, 0, sizeof(float) * 9 * (size_t)B, st);
+  SO3K_LAUNCH(k_stress, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, g.N, n_per, g.rowptr, g.geom, rbar, stress);
+}
 
 void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
                            const float* alpha, float* x1, float* chi1, cudaStream_t st) {

@@ -492,6 +492,16 @@ int so3k_energy_forces(so3k_handle* hh, int32_t B, int32_t n, int32_t P, const f
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
 }
 
+int so3k_stress(const so3k_handle* hh, int32_t B, int32_t n, int32_t P, const void* workspace, size_t workspace_bytes,
+                float* stress, void* stream) {
+  if (!hh || B <= 0 || n <= 0 || P < 0 || !workspace || !stress) return SO3K_ERR_ARG;
+  const HandleImpl* h = static_cast<const HandleImpl*>(hh);
+  Workspace w = carve_ws(h->dims, B * n, B * P, const_cast<void*>(workspace), wst_layers_of(h));
+  if (w.bytes > workspace_bytes) return SO3K_ERR_WORKSPACE;
+  so3k_launch_stress(w.g, B, n, w.rbar, stress, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
 int so3k_potential_displacements(so3k_handle* hh, int32_t N, int32_t P, const float* edges, const int32_t* z,
                                  const int32_t* centers, const int32_t* others, const uint8_t* mask,
                                  float energy_scale, float* e_atom, float* dE_dedges, float* forces, void* workspace,

@@ -92,6 +92,7 @@ void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float*
 void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                                const float* alphabar, const float* wst, float* gproj, float* ebar, float* wbar,
                                cudaStream_t st);
+void so3k_launch_stress(const Graph& g, int B, int n_per, const float* rbar, float* stress /* (B,3,3) */, cudaStream_t st);
 void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,
                          const float* chibar1, float* chibar /* out */, cudaStream_t st);
 void so3k_launch_forces(const So3kDims& D, const Graph& g, int P_slots, const float* rbar, float* forces /* (N,3) or null */,

@@ -75,9 +75,10 @@ class So3kEngine:
     # ---- energy + forces (training / evaluation seam) ----------------------------------------------
     def energy_forces(self, R: torch.Tensor, z: torch.Tensor, idx_i: torch.Tensor, idx_j: torch.Tensor,
                       cell: Optional[torch.Tensor] = None, cell_offset: Optional[torch.Tensor] = None,
-                      want_e_atom: bool = False) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+                      want_e_atom: bool = False, want_stress: bool = False):
         """R (B,n,3) f32, z (B,n) i32, idx (B,P) i32 [, cell (B,3,3) f32, cell_offset (B,P,3) i32] on the device.
-        Returns E (B,1), F (B,n,3) [, e_atom (B,n)]."""
+        Returns E (B,1), F (B,n,3), e_atom (B,n) or None [, stress (B,3,3) = dE/d(strain) when want_stress:
+        get_energy_force_stress_fn, observable_function.py:152-186]."""
         dev = self.device
         R = R.to(dev, torch.float32).contiguous()
         z = z.to(dev, torch.int32).contiguous()
@@ -95,6 +96,10 @@ class So3kEngine:
         with torch.cuda.device(dev):
             self.lib.energy_forces(self.h, B, n, P, _p(R), _p(z), _p(idx_i), _p(idx_j), _p(cell), _p(cell_offset),
                                    _p(E), _p(F), _p(ea), _p(ws), ws.numel(), _p(self._status), self._stream())
+            if want_stress:
+                st = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+                self.lib.stress(self.h, B, n, P, _p(ws), ws.numel(), _p(st), self._stream())
+                return E[:, None], F, ea, st
         return E[:, None], F, ea
 
     # ---- MD seam ------------------------------------------------------------------------------------

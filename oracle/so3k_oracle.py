@@ -377,6 +377,26 @@ def energy_forces(cfg: OracleConfig, params, R, z, idx_i, idx_j, dtype=torch.flo
     return E.detach(), (-g).detach(), e.detach()
 
 
+def energy_forces_stress(cfg: OracleConfig, params, R, z, idx_i, idx_j, dtype=torch.float64, cell=None,
+                         cell_offset=None):
+    """get_energy_force_stress_fn (observable_function.py:152-186): positions and cell are strained by the symmetrised
+    eps, R -> R + R eps_s^T, cell -> cell + cell eps_s^T (:172-174), and stress = dE/d eps at eps = 0 (no volume
+    factor, as in the reference).  Returns E, F (n,3), stress (3,3)."""
+    R_t = torch.as_tensor(np.asarray(R), dtype=dtype).clone().requires_grad_(True)
+    eps = torch.zeros(3, 3, dtype=dtype, requires_grad=True)
+    eps_s = 0.5 * (eps + eps.T)
+    Rs = R_t + torch.einsum('ij,nj->ni', eps_s, R_t)
+    cell_t = None
+    if cell is not None:
+        c0 = torch.as_tensor(np.asarray(cell), dtype=dtype)
+        cell_t = c0 + torch.einsum('ab,Ab->Aa', eps_s, c0)
+    off_t = None if cell_offset is None else torch.as_tensor(np.asarray(cell_offset))
+    e = forward(cfg, params, z, idx_i, idx_j, dtype, R=Rs, cell=cell_t, cell_offset=off_t)
+    E = e.sum()
+    g, st = torch.autograd.grad(E, (R_t, eps))
+    return E.detach(), (-g).detach(), st.detach()
+
+
 def energy_forces_batch(cfg, params, R, z, idx_i, idx_j, dtype=torch.float64, cell=None, cell_offset=None):
     """jax.vmap(obs_fn, in_axes=(None, 0)) over a padded batch: R (B,n,3), z (B,n), idx (B,P)."""
     Es, Fs = [], []

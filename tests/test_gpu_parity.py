@@ -415,3 +415,35 @@ def test_batched_get_indices_matches_reference_semantics(ethanol):
         out = get_indices(eng, Rr, zp, r_cut)
         assert out['idx_i'].shape == ref['idx_i'].shape
         assert (out['idx_i'].cpu().numpy() == ref['idx_i']).all() and (out['idx_j'].cpu().numpy() == ref['idx_j']).all()
+
+
+# ---- stress = dE/d(strain) (observable_function.py:152-186) ---------------------------------------------------------------
+@pytest.mark.parametrize('flags', [0, 3])
+def test_stress_matches_oracle_strain_derivative(solid, ethanol, flags):
+    cfg = o.OracleConfig()
+    g = golden('oracle_solid_pbc.npz')
+    p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+    eng = make(cfg, p, flags=flags)
+    R, z, cell = solid['R'], solid['z'], solid['unit_cell']
+    ii, jj, S = g['idx_i'], g['idx_j'], g['shifts']
+    E, F, _, st = eng.energy_forces(dev(R[None], torch.float32), dev(z[None], torch.int32), dev(ii[None], torch.int32),
+                                    dev(jj[None], torch.int32), dev(cell[None], torch.float32), dev(S[None], torch.int32),
+                                    want_stress=True)
+    assert eng.check_status() == 0
+    Eo, Fo, So = o.energy_forces_stress(cfg, p, R, z, ii, jj, cell=cell, cell_offset=S)
+    st = st[0].cpu().numpy()
+    assert np.abs(st - st.T).max() < 1e-6 * np.abs(st).max()
+    assert np.abs(st - So.numpy()).max() < 2e-4 * max(np.abs(So.numpy()).max(), 1.0)
+    # non-periodic batch: every structure gets its own tensor
+    B = 3
+    Rb = ethanol['R'][:B]
+    zb = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(Rb, zb, 5.0)
+    cfg2 = o.OracleConfig(F=36, n_layers=2)
+    p2 = o.init_params(cfg2, 0, embed_scale=4.0)
+    eng2 = make(cfg2, p2, flags=flags)
+    _, _, _, stb = eng2.energy_forces(dev(Rb, torch.float32), dev(zb, torch.int32), dev(nl['idx_i'], torch.int32),
+                                      dev(nl['idx_j'], torch.int32), want_stress=True)
+    for b in range(B):
+        _, _, So = o.energy_forces_stress(cfg2, p2, Rb[b], zb[b], nl['idx_i'][b], nl['idx_j'][b])
+        assert np.abs(stb[b].cpu().numpy() - So.numpy()).max() < 2e-4 * max(np.abs(So.numpy()).max(), 1.0)

@@ -136,3 +136,32 @@ def test_oracle_reproduces_committed_golden_outputs(ethanol, solid):
         E, F = o.energy_forces_batch(cfg, p, ethanol['R'][:4], z, g['idx_i'], g['idx_j'])
         np.testing.assert_allclose(E.numpy(), g['E'], rtol=1e-12)
         np.testing.assert_allclose(F.numpy(), g['F'], rtol=1e-9, atol=1e-13)
+
+
+def test_stress_is_the_strain_derivative_of_the_energy():
+    # observable_function.py:152-186: stress = dE/d eps for R -> R + R eps_s^T, cell -> cell + cell eps_s^T;
+    # check the autograd result against central finite differences in float64 and against the virial form
+    # sym(sum_e dE/dr_e (x) r_e) that the CUDA kernel evaluates
+    g = golden('oracle_solid_pbc.npz')
+    sol = golden('solid_0.npz')
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 3, embed_scale=4.0)
+    R, z, cell = sol['R'], sol['z'], sol['unit_cell']
+    ii, jj, S = g['idx_i'], g['idx_j'], g['shifts']
+    E, F, st = o.energy_forces_stress(cfg, p, R, z, ii, jj, cell=cell, cell_offset=S)
+    st = st.numpy()
+    assert np.abs(st - st.T).max() < 1e-12 * max(np.abs(st).max(), 1.0)
+    h = 1e-6
+    for a, b in ((0, 0), (0, 1), (2, 1)):
+        eps = np.zeros((3, 3))
+        eps[a, b] = h
+        es = 0.5 * (eps + eps.T)
+        Ep, _, _ = o.energy_forces(cfg, p, R + R @ es.T, z, ii, jj, cell=cell + cell @ es.T, cell_offset=S)
+        Em, _, _ = o.energy_forces(cfg, p, R - R @ es.T, z, ii, jj, cell=cell - cell @ es.T, cell_offset=S)
+        fd = (Ep.item() - Em.item()) / (2 * h)
+        assert abs(fd - st[a, b]) < 1e-6 * max(np.abs(st).max(), 1.0)
+    # virial form over the directed edges
+    r = R[jj] - R[ii] + S @ cell
+    e_atom, dE = o.potential_displacements(cfg, p, r, z, ii, jj, np.ones(len(ii), bool))
+    vir = dE.numpy().T @ r
+    np.testing.assert_allclose(0.5 * (vir + vir.T), st, atol=1e-9 * max(np.abs(st).max(), 1.0))
