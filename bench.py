@@ -361,13 +361,14 @@ def run_ours(args, w):
     d2h = ((N // world if use_dd else N) * 3 + 2) * 8
 
     md_info = None
-    if args.md_steps > 0 and world == 1 and periodic:
+    if args.md_steps > 0 and world == 1:
         # MD inner loop on the device: velocity Verlet, skin list re-used until an atom moved skin / 2
         from mlff_b200 import md
-        masses = torch.as_tensor(np.where(z == 8, 15.999, 1.008), device=dev)
+        masses = torch.as_tensor(np.where(z == 8, 15.999, np.where(z == 6, 12.011, 1.008)), device=dev)
         atoms = md.AtomsX(positions=pos_d.clone(), momenta=md.maxwell_boltzmann_momenta(masses, 300.0, seed=1), masses=masses,
-                          numbers=z_d, cell=cell, pbc=pbc).init_spatial_partitioning(eng, calc.cutoff, args.md_skin)
-        integ = md.VelocityVerletX.create(0.5 * md.FS, md.CalculatorX(eng))
+                          numbers=z_d, cell=cell, pbc=pbc if periodic else (False, False, False)
+                          ).init_spatial_partitioning(eng, calc.cutoff, args.md_skin)
+        integ = md.VelocityVerletX.create(0.5 * md.FS, md.CalculatorX(eng, cuda_graph=args.md_graph))
         atoms, _ = md.simulate(integ, atoms, 3)
         torch.cuda.synchronize()
         b0, t0 = atoms.neighbors.n_builds, time.perf_counter()
@@ -376,7 +377,7 @@ def run_ours(args, w):
         dt_md = (time.perf_counter() - t0) / args.md_steps
         etot = st_md['kinetic_energy'] + st_md['potential_energy']
         md_info = {'steps': args.md_steps, 'ms_per_step': dt_md * 1e3, 'atom_steps_per_s': N / dt_md, 'timestep_fs': 0.5,
-                   'skin_A': args.md_skin, 'edges_with_skin': int(atoms.neighbors.count),
+                   'skin_A': args.md_skin, 'cuda_graph': bool(args.md_graph), 'edges_with_skin': int(atoms.neighbors.count),
                    'list_rebuilds': atoms.neighbors.n_builds - b0,
                    'total_energy_drift_over_kinetic': float(np.abs(etot - etot[0]).max() / st_md['kinetic_energy'].mean())}
 
@@ -503,6 +504,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c4', choices=sorted(WORKLOADS))
+    ap.add_argument('--md-graph', action='store_true', help='replay the force evaluation of the MD loop as one CUDA graph')
     ap.add_argument('--md-skin', type=float, default=0.5, help='skin (Angstrom) of the MD neighbour list')
     ap.add_argument('--md-steps', type=int, default=0, help='additionally run this many velocity-Verlet MD steps with a '
                     '0.5 A skin list (mlff_b200.md, one GPU) and report them under "md"')

@@ -102,6 +102,12 @@ class So3kEngine:
                 return E[:, None], F, ea, st
         return E[:, None], F, ea
 
+    def graphed_energy_forces(self, B: int, n: int, P: int, periodic: bool) -> 'GraphedEnergyForces':
+        """One evaluation captured into a CUDA graph for fixed shapes (B, n, P): small systems are launch-bound (a step is
+        ~75 kernel launches), a replay is one launch.  The library only enqueues on the given stream and never
+        synchronises or allocates, so the capture needs no special path."""
+        return GraphedEnergyForces(self, B, n, P, periodic)
+
     # ---- MD seam ------------------------------------------------------------------------------------
     def potential(self, edges: torch.Tensor, z: torch.Tensor, centers: torch.Tensor, others: torch.Tensor,
                   mask: Optional[torch.Tensor] = None, energy_scale: float = 1.0, want_dE_dedges: bool = True,
@@ -169,3 +175,47 @@ class So3kEngine:
                                    pbc_h.ctypes.data, cutoff, capacity, _p(ii), _p(jj), _p(S), _p(count),
                                    _p(self._nl_ws), self._nl_ws.numel(), _p(self._status), self._stream())
         return ii, jj, S, count
+
+
+class GraphedEnergyForces:
+    """Static buffers + a captured CUDA graph of So3kEngine.energy_forces for one shape.
+    __call__(R, z, idx_i, idx_j[, cell, cell_offset]) copies the inputs into the static buffers and replays the graph;
+    the returned E (B,1) and F (B,n,3) are the static output buffers (valid until the next call)."""
+
+    def __init__(self, eng: So3kEngine, B: int, n: int, P: int, periodic: bool):
+        dev = eng.device
+        self.eng, self.shape, self.periodic = eng, (B, n, P), periodic
+        f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+        self.R = torch.zeros(B, n, 3, **f32)
+        self.z = torch.zeros(B, n, **i32)
+        self.ii = torch.full((B, P), -1, **i32)
+        self.jj = torch.full((B, P), -1, **i32)
+        self.cell = torch.zeros(B, 3, 3, **f32) if periodic else None
+        self.off = torch.zeros(B, P, 3, **i32) if periodic else None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.E = self.F = None
+
+    def _run(self):
+        self.E, self.F, _ = self.eng.energy_forces(self.R, self.z, self.ii, self.jj, self.cell, self.off)
+
+    def __call__(self, R, z, idx_i, idx_j, cell=None, cell_offset=None):
+        self.R.copy_(R)
+        self.z.copy_(z)
+        self.ii.copy_(idx_i)
+        self.jj.copy_(idx_j)
+        if self.periodic:
+            self.cell.copy_(cell)
+            self.off.copy_(cell_offset)
+        if self.graph is None:
+            B, n, P = self.shape
+            self.eng._workspace(B * n, B * P)                    # allocate outside the capture
+            side = torch.cuda.Stream(device=self.eng.device)
+            side.wait_stream(torch.cuda.current_stream(self.eng.device))
+            with torch.cuda.stream(side):                         # warm-up: function attributes, lazy module loading
+                self._run()
+            torch.cuda.current_stream(self.eng.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._run()
+        self.graph.replay()
+        return self.E, self.F

@@ -59,7 +59,9 @@ class SkinNeighborList:
                 self.engine._status.zero_()
         if self.capacity == 0 or cap > self.capacity:
             self.capacity = max(int(self.capacity_multiplier * n) + 16, n)
-        self.idx_i, self.idx_j, self.shifts, self.count = ii[:n], jj[:n], S[:n], n
+        # full-capacity arrays (padded with -1 / 0 behind `count`): their shape only changes when the capacity grows, which
+        # lets the calculator replay one CUDA graph between re-allocations
+        self.idx_i, self.idx_j, self.shifts, self.count = ii, jj, S, n
         self.reference_positions = positions.clone()
         self.n_builds += 1
         return self
@@ -119,10 +121,14 @@ class AtomsX:
 class CalculatorX:
     """energy + forces of an AtomsX through the engine (one structure; the skin list of the atoms object)."""
 
-    def __init__(self, engine, energy_scale: float = 1.0):
+    def __init__(self, engine, energy_scale: float = 1.0, cuda_graph: bool = False):
+        """cuda_graph=True replays one captured graph per evaluation while the list capacity is unchanged (small,
+        launch-bound systems); the engine must provide `graphed_energy_forces`."""
         self.engine = engine
         self.energy_scale = energy_scale
         self.n_calls = 0
+        self.cuda_graph = cuda_graph
+        self._graphed = None
 
     def __call__(self, atoms: AtomsX) -> Dict[str, torch.Tensor]:
         if atoms.cache is not None:
@@ -133,8 +139,14 @@ class CalculatorX:
         cell32 = None
         if periodic:
             cell32 = torch.as_tensor(np.asarray(atoms.cell, dtype=np.float32), device=R32.device)[None]
-        E, F, _ = self.engine.energy_forces(R32[None], atoms.numbers[None], nl.idx_i[None], nl.idx_j[None], cell32,
-                                            nl.shifts[None] if periodic else None)
+        args = (R32[None], atoms.numbers[None], nl.idx_i[None], nl.idx_j[None], cell32, nl.shifts[None] if periodic else None)
+        if self.cuda_graph:
+            shape = (1, int(R32.shape[0]), int(nl.idx_i.shape[0]))
+            if self._graphed is None or self._graphed.shape != shape:
+                self._graphed = self.engine.graphed_energy_forces(*shape, periodic)
+            E, F = self._graphed(*args)
+        else:
+            E, F, _ = self.engine.energy_forces(*args)
         self.n_calls += 1
         out = {'energy': self.energy_scale * E.reshape(()).to(torch.float64),
                'forces': self.energy_scale * F[0].to(torch.float64)}

@@ -153,3 +153,24 @@ def test_md_periodic_box_conserves_energy_and_reuses_the_list():
     assert np.abs(etot - etot[0]).max() < 0.02 * stats['kinetic_energy'].mean()
     assert atoms.neighbors.n_builds < steps // 4          # the skin list is re-used
     assert calc.n_calls == steps + 1
+
+
+@pytest.mark.gpu
+def test_md_cuda_graph_replay_equals_eager():
+    # small systems are launch-bound: CalculatorX(cuda_graph=True) replays one captured graph per evaluation
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.engine import So3kEngine
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    params = o.init_params(cfg, 0, embed_scale=4.0)
+    out = []
+    for use_graph in (False, True):
+        eng = So3kEngine(So3kratesConfig(F=36, n_layer=2), 'cuda:0', 3)
+        eng.load_params({k: np.asarray(v, np.float32) for k, v in params.items()})
+        _, _, _, _, atoms = ethanol_state('cuda:0')
+        atoms = atoms.init_spatial_partitioning(eng, cutoff=5.0, skin=1.0)
+        calc = md.CalculatorX(eng, cuda_graph=use_graph)
+        atoms, stats = md.simulate(md.VelocityVerletX.create(0.5 * md.FS, calc), atoms, 12)
+        assert eng.check_status() == 0
+        out.append((atoms.positions.cpu().numpy(), stats['potential_energy']))
+    np.testing.assert_allclose(out[0][0], out[1][0], atol=1e-9)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6)
