@@ -64,6 +64,7 @@ typedef struct so3k_config {
   float r_cut;             /* 5.0                                            */
   int32_t num_embeddings;  /* 100                                            */
   int32_t flags;           /* SO3K_FLAG_*                                    */
+  float zbl_shift;         /* Energy(zbl_repulsion_shift), used with SO3K_FLAG_ZBL; 0 */
 } so3k_config;
 
 enum {
@@ -74,7 +75,13 @@ enum {
   /* with SO3K_FLAG_TENSOR: the forward keeps every edge's filter vectors (2 * F floats per edge and layer in the
    * workspace -- so3k_workspace_bytes accounts for it) and the backward streams them instead of recomputing the
    * filter MLP for the q/k projection gradients.  Memory for time; results are identical. */
-  SO3K_FLAG_KEEP_FILTERS = 2
+  SO3K_FLAG_KEEP_FILTERS = 2,
+  /* Energy(zbl_repulsion=True) (mlff/nn/observable/observable.py:81-84, 110-183; CLI --zbl_repulsion): adds the
+   * Ziegler-Biersack-Littmark pair repulsion to the energy and its derivative to the forces.  The parameter blob then
+   * ends with the ten RAW ZBLRepulsion scalars zbl/{a1,a2,a3,a4,c1,c2,c3,c4,p,d} (softplus is applied at use, as in the
+   * reference).  so3k_config.zbl_shift is subtracted once per structure (so3k_energy_forces, 'per_structure'
+   * convention) or from every atom (so3k_potential_displacements, 'per_atom' convention), as the reference does. */
+  SO3K_FLAG_ZBL = 4
 };
 
 enum {
@@ -151,7 +158,12 @@ int so3k_stress(const so3k_handle* h, int32_t B, int32_t n, int32_t P, const voi
  * Outputs: e_atom (N) f32 = per-atom energy * energy_scale (mlff_potential.py:80-109);
  *   dE_dedges (P,3) f32 or NULL = d(sum e_atom)/d edges (what the caller's value_and_grad chains
  *   through R_j - R_i); forces (N,3) f32 or NULL = -dE/dR obtained by that chain
- *   (mdx/calculator.py:46-49). */
+ *   (mdx/calculator.py:46-49).
+ * With SO3K_FLAG_TENSOR the radial and l0-contraction cotangents are evaluated once per undirected pair and booked on
+ * ONE of its two directed edges: dE_dedges then equals the reference's per-edge gradient up to that antisymmetric pair
+ * gauge (dE_dedges[e] - dE_dedges[rev e] is exact), so everything the MD caller derives from it -- forces by scatter
+ * over centers / others, stress sum_e dE_dedges[e] (x) edges[e] -- is unchanged; per-edge equality holds in fp32 mode.
+ */
 int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
                                  const float* edges, const int32_t* z,
                                  const int32_t* centers, const int32_t* others, const uint8_t* mask,

@@ -19,6 +19,7 @@ STATUS_ASYMMETRIC = 2
 STATUS_BAD_Z = 4
 FLAG_TENSOR = 1
 FLAG_KEEP_FILTERS = 2    # with FLAG_TENSOR: keep the forward's filters for the backward (memory for time)
+FLAG_ZBL = 4             # Energy(zbl_repulsion=True): ZBL pair repulsion, ten extra scalars at the end of the blob
 NL_ASE = 0
 NL_DENSE = 1
 
@@ -33,7 +34,7 @@ EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 's
 class So3kConfigC(C.Structure):
     _fields_ = [('F', C.c_int32), ('n_rbf', C.c_int32), ('n_layers', C.c_int32), ('n_heads', C.c_int32),
                 ('n_degrees', C.c_int32), ('degrees', C.c_int32 * SO3K_MAX_DEGREES), ('r_cut', C.c_float),
-                ('num_embeddings', C.c_int32), ('flags', C.c_int32)]
+                ('num_embeddings', C.c_int32), ('flags', C.c_int32), ('zbl_shift', C.c_float)]
 
 
 class So3kError(RuntimeError):
@@ -98,7 +99,7 @@ class So3kLib:
 
     # ---- handle -----------------------------------------------------------------------------
     def create(self, F: int, n_rbf: int, n_layers: int, n_heads: int, degrees: Sequence[int], r_cut: float,
-               num_embeddings: int = 100, flags: int = 0) -> int:
+               num_embeddings: int = 100, flags: int = 0, zbl_shift: float = 0.0) -> int:
         cfg = So3kConfigC()
         cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads = F, n_rbf, n_layers, n_heads
         cfg.n_degrees = len(degrees)
@@ -109,6 +110,7 @@ class So3kLib:
         cfg.r_cut = float(r_cut)
         cfg.num_embeddings = num_embeddings
         cfg.flags = flags
+        cfg.zbl_shift = float(zbl_shift)
         h = C.c_void_p()
         _check(self.dll.so3k_create(C.byref(cfg), C.byref(h)), 'so3k_create')
         return h.value

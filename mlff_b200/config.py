@@ -25,6 +25,8 @@ class So3kratesConfig:
     r_cut: float = 5.0
     num_embeddings: int = 100
     mic: bool = False
+    zbl_repulsion: bool = False           # Energy(zbl_repulsion=...), mlff/nn/observable/observable.py:39 (CLI --zbl_repulsion)
+    zbl_repulsion_shift: float = 0.0      # observable.py:40
     prop_keys: Dict[str, str] = field(default_factory=lambda: dict(md17_property_keys))
 
     def validate(self):
@@ -66,9 +68,12 @@ class So3kratesConfig:
         F = int(feat['features'])
         if list(l0['fb_rad_filter_features']) != [F, F] or list(l0['fb_sph_filter_features']) != [int(F / 4), F]:
             raise NotImplementedError('only the default filter widths [F,F] / [F/4,F] are implemented')
+        obs = next(iter(sn['observables'][0].values())) if sn.get('observables') else {}
         return cls(F=F, n_layer=len(layers), degrees=tuple(int(x) for x in geo['degrees']),
                    n_heads=int(l0.get('n_heads', 4)), n_rbf=int(geo['n_rbf']), r_cut=float(geo['r_cut']),
                    num_embeddings=int(feat.get('num_embeddings', 100)), mic=bool(geo.get('mic', False)),
+                   zbl_repulsion=bool(obs.get('zbl_repulsion', False)),
+                   zbl_repulsion_shift=float(obs.get('zbl_repulsion_shift', 0.0) or 0.0),
                    prop_keys=dict(sn.get('prop_keys', md17_property_keys)))
 
     def to_hyperparameters(self) -> Dict:
@@ -88,7 +93,8 @@ class So3kratesConfig:
                                   'input_convention': 'positions', 'prop_keys': self.prop_keys}}
         feat = {'atom_type_embed': {'num_embeddings': self.num_embeddings, 'features': F, 'prop_keys': self.prop_keys}}
         obs = {'energy': {'per_atom_scale': None, 'per_atom_shift': None, 'num_embeddings': self.num_embeddings,
-                          'output_convention': 'per_structure', 'zbl_repulsion': False, 'zbl_repulsion_shift': 0.0,
+                          'output_convention': 'per_structure', 'zbl_repulsion': self.zbl_repulsion,
+                          'zbl_repulsion_shift': self.zbl_repulsion_shift,
                           'prop_keys': self.prop_keys}}
         return {'stack_net': {'geometry_embeddings': [geo], 'feature_embeddings': [feat],
                               'layers': [layer for _ in range(self.n_layer)], 'observables': [obs],

@@ -562,7 +562,85 @@ k_stress(int N, int n_per, const int* __restrict__ rowptr, const float4* __restr
   }
 }
 
+// ZBLRepulsion (mlff/nn/observable/observable.py:131-183), receiver rows:
+//   e_edge = 1/2 w(d) ke phi(d) z_i z_j / d * sum_k c_k exp(-a_k d (z_i^p + z_j^p) dpar),  w = switching_fn(d, 0, 1.5)
+// and its derivative with respect to d, added to the edge cotangent rbar (E depends on d only: dE/dr = dE/dd u).
+struct ZblP { float a[4], c[4], p, dpar; };
+__device__ __forceinline__ float zbl_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float zbl_sigma(float x, float* ds) {          // exp(-1/x), x > 0 ; derivative exp(-1/x)/x^2
+  if (x > 0.f) {
+    const float s = expf(-1.0f / x);
+    *ds = s / (x * x);
+    return s;
+  }
+  *ds = 0.f;
+  return 0.f;
+}
+__global__ void __launch_bounds__(WPB * 32)
+k_zbl(So3kDims D, int N, const int* __restrict__ rowptr, const int* __restrict__ col, const float4* __restrict__ geom,
+      const int* __restrict__ z, const float* __restrict__ raw, float out_scale, float atom_shift,
+      float* __restrict__ e_atom, float* __restrict__ rbar) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  ZblP P;
+  float csum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    P.a[k] = zbl_softplus(raw[k]);
+    P.c[k] = zbl_softplus(raw[4 + k]);
+    csum += P.c[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) P.c[k] /= csum;
+  P.p = zbl_softplus(raw[8]);
+  P.dpar = zbl_softplus(raw[9]);
+  const float ke = 14.399645351950548f;
+  const float zi = rowok ? (float)z[i] : 0.f;
+  const float zip = zi > 0.f ? powf(zi, P.p) : 0.f;
+  float esum = 0.f;
+  for (int e = beg + lane; e < end; e += 32) {
+    const float4 g = geom[e];
+    const float d = g.w;
+    const float zj = (float)z[col[e]];
+    if (d > 0.f && zi > 0.f && zj > 0.f) {
+      const float cc = d * (1.0f / 1.5f);
+      float dA, dB;
+      const float A = zbl_sigma(1.0f - cc, &dA), Bv = zbl_sigma(cc, &dB);
+      const float den = A + Bv;
+      const float wsw = A / den;
+      const float dw = ((-dA) * Bv - A * dB) / (den * den) * (1.0f / 1.5f);
+      const float ph = so3k_cutoff(d, D.r_cut), dph = so3k_cutoff_d(d, D.r_cut);
+      const float s = (zip + powf(zj, P.p)) * P.dpar;
+      float y = 0.f, dy = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float t = P.c[k] * expf(-P.a[k] * s * d);
+        y += t;
+        dy -= t * P.a[k] * s;
+      }
+      const float pre = 0.5f * ke * zi * zj * out_scale;
+      const float f = wsw * ph * y / d;
+      const float df = (dw * ph * y + wsw * dph * y + wsw * ph * dy) / d - f / d;
+      esum = fmaf(pre, f, esum);
+      const float gd = pre * df;
+      rbar[3 * (size_t)e + 0] += gd * g.x;
+      rbar[3 * (size_t)e + 1] += gd * g.y;
+      rbar[3 * (size_t)e + 2] += gd * g.z;
+    }
+  }
+  esum = warp_sum(esum);
+  if (rowok && lane == 0) e_atom[i] += esum - atom_shift * out_scale;
+}
+
 }  // namespace
+
+void so3k_launch_zbl(const So3kDims& D, const Graph& g, const int* z, const float* zbl_raw, float out_scale,
+                     float atom_shift, float* e_atom, float* rbar, cudaStream_t st) {
+  SO3K_LAUNCH(k_zbl, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, g.rowptr, g.col, g.geom, z, zbl_raw,
+              out_scale, atom_shift, e_atom, rbar);
+}
 
 void so3k_launch_stress(const Graph& g, int B, int n_per, const float* rbar, float* stress, cudaStream_t st) {
   cudaMemsetAsync(stress, 0, sizeof(float) * 9 * (size_t)B, st);

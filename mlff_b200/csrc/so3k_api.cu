@@ -130,7 +130,7 @@ bool make_dims(const so3k_config& c, So3kDims* D) {
   return true;
 }
 
-void make_layout(const So3kDims& D, ModelLayout* ml) {
+void make_layout(const So3kDims& D, ModelLayout* ml, bool zbl) {
   size_t off = 0;
   auto add = [&](const std::string& name, size_t count) {
     size_t o = off;
@@ -168,6 +168,14 @@ void make_layout(const So3kDims& D, ModelLayout* ml) {
   ml->out_b2 = add("energy/layers_1/bias", 1);
   ml->scale = add("energy/per_atom_scale", D.nemb);
   ml->shift = add("energy/per_atom_shift", D.nemb);
+  ml->has_zbl = zbl;
+  if (zbl) {
+    static const char* const zn[10] = {"a1", "a2", "a3", "a4", "c1", "c2", "c3", "c4", "p", "d"};
+    for (int k = 0; k < 10; ++k) {
+      size_t o = add(std::string("zbl/") + zn[k], 1);
+      if (k == 0) ml->zbl = o;
+    }
+  }
   ml->total = off;
 }
 
@@ -287,7 +295,9 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
 }
 
 // e_atom and d(sum e)/dx_L -> xbar_a ; chibar_a = 0 ; rbar = 0
-void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, float* e_atom, cudaStream_t st) {
+// atom_shift: ZBL shift subtracted from every atom ('per_atom' convention of the MD seam), 0 otherwise
+void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, float atom_shift, float* e_atom,
+                   cudaStream_t st) {
   const So3kDims& D = h->dims;
   const size_t N = w.g.N, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
   {
@@ -297,6 +307,10 @@ void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, f
   }
   cudaMemsetAsync(w.chibar_a, 0, sizeof(float) * N * D.M, st);
   cudaMemsetAsync(w.rbar, 0, sizeof(float) * Pe * 3, st);
+  if (h->layout.has_zbl) {
+    PROF(CAT_READOUT);
+    so3k_launch_zbl(D, w.g, z, h->params + h->layout.zbl, out_scale, atom_shift, e_atom, w.rbar, st);
+  }
 }
 
 // interaction block of layer t: (xbar_a, chibar_a) = cotangent of (x_{t+1}, chi_{t+1})  ->  (xbar_b, chibar_b) = (xbar1, chibar1)
@@ -367,8 +381,10 @@ int run_model(HandleImpl* h, int B, int n, int P, const float* R, const int* z, 
   stage_begin(h, w, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, disp, mask, dev_status, st);
   for (int t = 0; t < D.L; ++t) stage_layer_fwd(h, w, t, dev_status, st);
   float* e_atom = e_atom_out ? e_atom_out : w.e_atom;
-  stage_readout(h, w, z, out_scale, e_atom, st);
-  if (E) { PROF(CAT_READOUT); so3k_launch_energy_sum(B, n, e_atom, E, st); }
+  const float zshift = h->layout.has_zbl ? h->cfg.zbl_shift : 0.f;
+  const bool md_seam = disp != nullptr;      // 'per_atom' convention: the ZBL shift is subtracted from every atom
+  stage_readout(h, w, z, out_scale, md_seam ? zshift : 0.f, e_atom, st);
+  if (E) { PROF(CAT_READOUT); so3k_launch_energy_sum(B, n, e_atom, md_seam ? 0.f : zshift * out_scale, E, st); }
   if (!forces && !dE_dedges) return SO3K_OK;
   for (int t = D.L - 1; t >= 0; --t) {
     stage_layer_bwd_a(h, w, t, st);
@@ -398,7 +414,7 @@ int so3k_create(const so3k_config* cfg, so3k_handle** out) {
   h->use_tc = (cfg->flags & SO3K_FLAG_TENSOR) != 0;
   h->keep_w = h->use_tc && (cfg->flags & SO3K_FLAG_KEEP_FILTERS) != 0;
   if (const char* e = getenv("SO3K_TC_B2")) h->tc_b2 = atoi(e) != 0;
-  make_layout(D, &h->layout);
+  make_layout(D, &h->layout, (cfg->flags & SO3K_FLAG_ZBL) != 0);
   *out = h;
   return SO3K_OK;
 }
@@ -554,7 +570,7 @@ int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   switch (stage) {
     case 0: stage_layer_fwd(h, w, t, dev_status, st); break;
-    case 1: if (!z || !out) return SO3K_ERR_ARG; stage_readout(h, w, z, 1.0f, out, st); break;
+    case 1: if (!z || !out) return SO3K_ERR_ARG; stage_readout(h, w, z, 1.0f, 0.f, out, st); break;
     case 2: stage_layer_bwd_a(h, w, t, st); break;
     case 3: stage_layer_bwd_b(h, w, t, dev_status, st); break;
     case 4: if (!out) return SO3K_ERR_ARG; so3k_launch_forces(h->dims, w.g, P, w.rbar, out, nullptr, st); break;

@@ -20,6 +20,8 @@ struct ModelLayout {
   std::vector<LayerParams> layers;
   size_t out_W1, out_b1, out_W2, out_b2;    // (F,F) (F) (F,1) (1)
   size_t scale, shift;                      // (nemb) each
+  size_t zbl = 0;                           // 10 raw ZBLRepulsion scalars (a1..a4, c1..c4, p, d) with SO3K_FLAG_ZBL
+  bool has_zbl = false;
   size_t total;
   std::vector<std::pair<std::string, std::pair<size_t, size_t>>> names;   // name -> (offset, count)
 };
@@ -79,7 +81,10 @@ void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, co
 void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* params,
                          const float* params_T, const ModelLayout& ml, float out_scale, float* e_atom, float* xbar,
                          cudaStream_t st);
-void so3k_launch_energy_sum(int B, int n, const float* e_atom, float* E, cudaStream_t st);
+void so3k_launch_energy_sum(int B, int n, const float* e_atom, float offset, float* E, cudaStream_t st);   // E[b] = sum - offset
+// Ziegler-Biersack-Littmark repulsion: e_atom[i] += out_scale * (sum_{e in row i} e_edge - atom_shift), rbar[e] += dE/dr_e
+void so3k_launch_zbl(const So3kDims& D, const Graph& g, const int* z, const float* zbl_raw, float out_scale,
+                     float atom_shift, float* e_atom, float* rbar, cudaStream_t st);
 // agg.cu
 void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
                            const float* alpha, float* x1, float* chi1, cudaStream_t st);

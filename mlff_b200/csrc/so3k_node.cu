@@ -292,7 +292,7 @@ k_readout(So3kDims D, int N, const float* __restrict__ x, const int* __restrict_
 }
 
 // E[b] = sum_a e_atom[b][a]   (float64 accumulation, one warp per structure chunk)
-__global__ void k_energy_sum(int B, int n, const float* __restrict__ e_atom, float* __restrict__ E) {
+__global__ void k_energy_sum(int B, int n, const float* __restrict__ e_atom, float offset, float* __restrict__ E) {
   __shared__ double s_part[NT / 32];
   int b = blockIdx.x;
   double s = 0.0;
@@ -303,7 +303,7 @@ __global__ void k_energy_sum(int B, int n, const float* __restrict__ e_atom, flo
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < NT / 32; ++w) t += s_part[w];
-    E[b] = (float)t;
+    E[b] = (float)(t - (double)offset);
   }
 }
 
@@ -381,6 +381,6 @@ void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z,
               p + ml.out_b1, p + ml.out_W2, p + ml.out_b2, p + ml.scale, p + ml.shift, out_scale, e_atom, xbar);
 }
 
-void so3k_launch_energy_sum(int B, int n, const float* e_atom, float* E, cudaStream_t st) {
-  SO3K_LAUNCH(k_energy_sum, dim3(B), dim3(NT), 0, st, B, n, e_atom, E);
+void so3k_launch_energy_sum(int B, int n, const float* e_atom, float offset, float* E, cudaStream_t st) {
+  SO3K_LAUNCH(k_energy_sum, dim3(B), dim3(NT), 0, st, B, n, e_atom, offset, E);
 }

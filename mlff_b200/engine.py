@@ -27,8 +27,11 @@ class So3kEngine:
         self.cfg = cfg
         self.device = torch.device(device)
         self.lib = _lib.load()
+        from .capi import FLAG_ZBL
+        if cfg.zbl_repulsion:
+            flags |= FLAG_ZBL
         self.h = self.lib.create(cfg.F, cfg.n_rbf, cfg.n_layer, cfg.n_heads, list(cfg.degrees), cfg.r_cut,
-                                 cfg.num_embeddings, flags)
+                                 cfg.num_embeddings, flags, cfg.zbl_repulsion_shift)
         self._ws: Optional[torch.Tensor] = None
         self._nl_ws: Optional[torch.Tensor] = None
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)

@@ -41,7 +41,14 @@ def param_shapes(cfg: So3kratesConfig) -> List[Tuple[str, Tuple[int, ...]]]:
     out += [('energy/layers_0/kernel', (F, F)), ('energy/layers_0/bias', (F,)),
             ('energy/layers_1/kernel', (F, 1)), ('energy/layers_1/bias', (1,)),
             ('energy/per_atom_scale', (cfg.num_embeddings,)), ('energy/per_atom_shift', (cfg.num_embeddings,))]
+    if cfg.zbl_repulsion:            # raw ZBLRepulsion scalars (softplus applied at use), observable.py:133-142
+        out += [('zbl/' + k, (1,)) for k in ZBL_NAMES]
     return out
+
+
+ZBL_NAMES = ('a1', 'a2', 'a3', 'a4', 'c1', 'c2', 'c3', 'c4', 'p', 'd')
+_ZBL_INIT = {'a1': 3.2, 'a2': 0.9423, 'a3': 0.4028, 'a4': 0.2016, 'c1': 0.1818, 'c2': 0.5099, 'c3': 0.2802, 'c4': 0.02817,
+             'p': 0.23, 'd': 1.0 / (0.8854 * 0.5291772105638411)}
 
 
 def init_params(cfg: So3kratesConfig, seed: int = 0) -> Dict[str, np.ndarray]:
@@ -57,6 +64,9 @@ def init_params(cfg: So3kratesConfig, seed: int = 0) -> Dict[str, np.ndarray]:
             p[name] = np.ones(shape, np.float32)
         elif name == 'energy/per_atom_shift':
             p[name] = np.zeros(shape, np.float32)
+        elif name.startswith('zbl/'):
+            v = _ZBL_INIT[name[4:]]
+            p[name] = np.array([v + math.log(-math.expm1(-v))], np.float32)     # softplus_inverse, as the reference
         elif name == 'embed/embedding':
             p[name] = rng.normal(0.0, 1.0 / math.sqrt(shape[1]), shape).astype(np.float32)
         else:
@@ -84,6 +94,8 @@ def _flax_path(name: str) -> Tuple[List[str], bool]:
     parts = name.split('/')
     if parts[0] == 'embed':
         return ['feature_embeddings_0', 'Embed_0', 'embedding'], False
+    if parts[0] == 'zbl':
+        return ['observables_0', 'ZBLRepulsion_0', parts[1]], False
     if parts[0] == 'energy':
         if parts[1] in ('per_atom_scale', 'per_atom_shift'):
             return [], False

@@ -62,6 +62,8 @@ class OracleConfig:
     n_layers: int = 3
     r_cut: float = 5.0
     num_embeddings: int = 100
+    zbl_repulsion: bool = False           # Energy(zbl_repulsion=...)   observable.py:39, CLI --zbl_repulsion
+    zbl_repulsion_shift: float = 0.0      # observable.py:40
 
     @property
     def nl(self) -> int:
@@ -119,7 +121,50 @@ def init_params(cfg: OracleConfig, seed: int = 0, bias_scale: float = 0.01,
     else:
         p['energy/per_atom_scale'] = np.ones((cfg.num_embeddings,))
         p['energy/per_atom_shift'] = np.zeros((cfg.num_embeddings,))
+    if cfg.zbl_repulsion:
+        # ZBLRepulsion parameters are stored RAW (softplus is applied at use), initialised to softplus_inverse of the
+        # ZBL constants (observable.py:133-142); a little noise makes the parity tests discriminate between them
+        for name, v in ZBL_DEFAULTS.items():
+            raw = v + math.log(-math.expm1(-v))                               # activation_function.py:19-20
+            p['zbl/' + name] = np.array([raw + (rng.normal(0.0, 0.05) if scale_shift else 0.0)])
     return p
+
+
+ZBL_A0 = 0.5291772105638411                                                   # observable.py:118
+ZBL_KE = 14.399645351950548                                                   # observable.py:119
+ZBL_DEFAULTS = {'a1': 3.2, 'a2': 0.9423, 'a3': 0.4028, 'a4': 0.2016, 'c1': 0.1818, 'c2': 0.5099, 'c3': 0.2802,
+                'c4': 0.02817, 'p': 0.23, 'd': 1.0 / (0.8854 * ZBL_A0)}
+
+
+def zbl_repulsion_per_atom(cfg: OracleConfig, params, z, idx_i, idx_j, geo, pair_mask, dtype):
+    """ZBLRepulsion.__call__ (observable.py:131-183), 'per_atom' form WITHOUT the shift: (n,) repulsion energies."""
+    sp = torch.nn.functional.softplus
+    g = lambda k: sp(_t(params, 'zbl/' + k, dtype))
+    a = [g('a1'), g('a2'), g('a3'), g('a4')]
+    c = [g('c1'), g('c2'), g('c3'), g('c4')]
+    csum = c[0] + c[1] + c[2] + c[3]
+    c = [ck / csum for ck in c]                                               # :144-148
+    pw, dd = g('p'), g('d')
+    d_ij = geo['d_ij']
+    zf = z.to(dtype)
+    ii = torch.where(idx_i >= 0, idx_i, torch.zeros_like(idx_i))
+    jj = torch.where(idx_j >= 0, idx_j, torch.zeros_like(idx_j))
+    z_i, z_j = zf[ii], zf[jj]
+    nz = d_ij != 0
+    z_d = torch.where(nz, z_i * z_j / torch.where(nz, d_ij, torch.ones_like(d_ij)), torch.zeros_like(d_ij))   # :164-168
+    x = ZBL_KE * geo['phi_r_cut'] * z_d                                       # :170
+    rzd = d_ij * (z_i ** pw + z_j ** pw) * dd                                 # :172
+    y = sum(ck * torch.exp(-ak * rzd) for ck, ak in zip(c, a))                # :173
+
+    def sigma(u):                                                             # observable.py:17-18
+        pos = u > 0
+        return torch.where(pos, torch.exp(-1.0 / torch.where(pos, u, torch.ones_like(u))), torch.zeros_like(u))
+    cc = d_ij / 1.5                                                           # switching_fn(d, 0, 1.5)  :21-23, :176
+    w = sigma(1 - cc) / (sigma(1 - cc) + sigma(cc))
+    w = torch.where(nz, w, torch.zeros_like(w))                               # (d = 0 only on padded pairs)
+    e_edge = safe_scale(w * x * y, pair_mask) / 2.0                           # :177
+    out = torch.zeros(z.shape[0], dtype=dtype)
+    return out.index_add(0, ii, e_edge)                                       # segment_sum over idx_i  :180
 
 
 # --------------------------------------------------------------------------------------
@@ -361,6 +406,8 @@ def forward(cfg: OracleConfig, params, z, idx_i, idx_j, dtype=torch.float64, R=N
              _t(params, 'energy/layers_1/kernel', dtype), _t(params, 'energy/layers_1/bias', dtype)).squeeze(-1)
     e = _t(params, 'energy/per_atom_scale', dtype)[z] * e + _t(params, 'energy/per_atom_shift', dtype)[z]  # :78
     e = safe_scale(e, point_mask)                                             # :79
+    if cfg.zbl_repulsion:                                                     # :81-84 (the shift is applied by the callers:
+        e = e + zbl_repulsion_per_atom(cfg, params, z, idx_i, idx_j, geo, pair_mask, dtype)   # once per structure or per atom)
     return e
 
 
@@ -372,7 +419,7 @@ def energy_forces(cfg: OracleConfig, params, R, z, idx_i, idx_j, dtype=torch.flo
     cell_t = None if cell is None else torch.as_tensor(np.asarray(cell), dtype=dtype)
     off_t = None if cell_offset is None else torch.as_tensor(np.asarray(cell_offset))
     e = forward(cfg, params, z, idx_i, idx_j, dtype, R=R_t, cell=cell_t, cell_offset=off_t, record=record)
-    E = e.sum()
+    E = e.sum() - (cfg.zbl_repulsion_shift if cfg.zbl_repulsion else 0.0)     # per_structure: observable.py:84, :91
     (g,) = torch.autograd.grad(E, R_t)
     return E.detach(), (-g).detach(), e.detach()
 
@@ -392,7 +439,7 @@ def energy_forces_stress(cfg: OracleConfig, params, R, z, idx_i, idx_j, dtype=to
         cell_t = c0 + torch.einsum('ab,Ab->Aa', eps_s, c0)
     off_t = None if cell_offset is None else torch.as_tensor(np.asarray(cell_offset))
     e = forward(cfg, params, z, idx_i, idx_j, dtype, R=Rs, cell=cell_t, cell_offset=off_t)
-    E = e.sum()
+    E = e.sum() - (cfg.zbl_repulsion_shift if cfg.zbl_repulsion else 0.0)
     g, st = torch.autograd.grad(E, (R_t, eps))
     return E.detach(), (-g).detach(), st.detach()
 
@@ -417,7 +464,10 @@ def potential_displacements(cfg, params, edges, z, centers, others, mask, dtype=
     mask = torch.as_tensor(np.asarray(mask)).bool()
     ii = torch.where(mask, torch.as_tensor(np.asarray(centers)).long(), torch.tensor(-1))
     jj = torch.where(mask, torch.as_tensor(np.asarray(others)).long(), torch.tensor(-1))
-    e = forward(cfg, params, z, ii, jj, dtype, displacements=edges_t) * energy_scale
+    e = forward(cfg, params, z, ii, jj, dtype, displacements=edges_t)
+    if cfg.zbl_repulsion:
+        e = e - cfg.zbl_repulsion_shift                                       # per_atom convention: observable.py:84, :89
+    e = e * energy_scale
     (g,) = torch.autograd.grad(e.sum(), edges_t)
     return e.detach(), g.detach()
 

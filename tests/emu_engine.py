@@ -30,9 +30,9 @@ def ptr(a: Optional[np.ndarray]) -> Optional[int]:
 
 
 class EmuEngine:
-    def __init__(self, F, n_rbf, n_layers, n_heads, degrees, r_cut, flags=0):
+    def __init__(self, F, n_rbf, n_layers, n_heads, degrees, r_cut, flags=0, zbl_shift=0.0):
         self.lib = So3kLib(build_emu())
-        self.h = self.lib.create(F, n_rbf, n_layers, n_heads, list(degrees), r_cut, 100, flags)
+        self.h = self.lib.create(F, n_rbf, n_layers, n_heads, list(degrees), r_cut, 100, flags, zbl_shift)
         self.F, self.M = F, sum(2 * l + 1 for l in degrees)
         self.K = n_rbf
 

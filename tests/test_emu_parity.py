@@ -16,7 +16,9 @@ F_ATOL = 1e-4      # north_star: forces within 1e-4 eV/A max-abs (fp32)
 
 
 def make(cfg, p):
-    eng = EmuEngine(cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads, cfg.degrees, cfg.r_cut)
+    from mlff_b200.capi import FLAG_ZBL
+    eng = EmuEngine(cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads, cfg.degrees, cfg.r_cut,
+                    flags=FLAG_ZBL if cfg.zbl_repulsion else 0, zbl_shift=cfg.zbl_repulsion_shift)
     eng.load(p)
     return eng
 
@@ -202,3 +204,28 @@ def test_neighbor_list_overflow_triclinic_unwrapped_dense(solid, ethanol):
     ii, jj, S, cnt, st = run_nl(lib, NL_DENSE, R, z, None, (0, 0, 0), 5.0, 80)
     k = (nl['idx_i'][0] >= 0).sum()
     assert cnt == k and as_sets(ii, jj) == as_sets(nl['idx_i'][0], nl['idx_j'][0])
+
+
+def test_zbl_repulsion(ethanol):
+    # Energy(zbl_repulsion=True), observable.py:81-84, 110-183: both seams, shift conventions included
+    cfg = o.OracleConfig(F=36, n_layers=2, zbl_repulsion=True, zbl_repulsion_shift=0.37)
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    eng = make(cfg, p)
+    R = ethanol['R'][:2]
+    z = np.tile(ethanol['z'][None], (2, 1))
+    nl = o.get_indices(R, z, 5.0)
+    E, F, ea, st = eng.energy_forces(R, z, nl['idx_i'], nl['idx_j'])
+    assert st == 0
+    Eo, Fo = o.energy_forces_batch(cfg, p, R, z, nl['idx_i'], nl['idx_j'])
+    E0, F0 = o.energy_forces_batch(o.OracleConfig(F=36, n_layers=2), p, R, z, nl['idx_i'], nl['idx_j'])
+    assert np.abs(Fo.numpy() - F0.numpy()).max() > 1.0          # the repulsion matters here (C-H, O-H bonds < 1.5 A)
+    scale = np.maximum(np.abs(Eo.numpy().reshape(-1)), np.abs(ea).sum(-1))
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= E_RTOL * scale).all()
+    assert np.abs(F - Fo.numpy()).max() < F_ATOL
+    ii, jj = nl['idx_i'][0], nl['idx_j'][0]
+    edges = R[0][jj] - R[0][ii]
+    mask = np.ones(len(ii), bool)
+    out = eng.potential(edges, z[0], ii, jj, mask, energy_scale=1.3)
+    ea_o, dE_o = o.potential_displacements(cfg, p, edges, z[0], ii, jj, mask, energy_scale=1.3)
+    np.testing.assert_allclose(out[0], ea_o.numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(out[1], dE_o.numpy(), rtol=2e-5, atol=2e-5)
