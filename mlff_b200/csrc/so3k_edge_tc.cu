@@ -666,7 +666,32 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int n_tiles, int pair_cap, const i
     // ---- epilogue: this thread's quarter of the KC hidden columns of its row ------------------------------------------------
     {
       float dbar = 0.f;
-      for (int ci = 0; ci < nmine; ++ci) {
+      int ci = 0;
+      // radial chunks two at a time: six TMEM loads in flight, sixteen independent silu' chains
+      for (; comp && ci + 1 < kce - kcb && (kcb + ci + 2) * 8 <= F; ci += 2) {
+        const int c0 = (kcb + ci) * 8;
+        float hb[2][8], a1[2][8], tp[2][8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          tc::tmem_ld8(tD3 + lane_sel + (uint32_t)(c0 + 8 * u), hb[u]);
+          tc::tmem_ld8(tD1 + lane_sel + (uint32_t)(c0 + 8 * u), a1[u]);
+          tc::tmem_ld8(tD1p + lane_sel + (uint32_t)(c0 + 8 * u), tp[u]);
+        }
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 ba = *reinterpret_cast<const float4*>(S.b1p + c0 + 8 * u);
+          const float4 bb = *reinterpret_cast<const float4*>(S.b1p + c0 + 8 * u + 4);
+          const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float y, dy;
+            silu_fast_d(a1[u][q] + bv[q], &y, &dy);
+            dbar = fmaf(hb[u][q] * dy, tp[u][q], dbar);
+          }
+        }
+      }
+      for (; ci < nmine; ++ci) {
         const int cc = (ci < kce - kcb) ? kcb + ci : nchunkF + qq + 4 * (ci - (kce - kcb));
         const int c0 = cc * 8;
         if (c0 >= F + Fs) break;                  // warp-uniform: only zero padding left
