@@ -80,11 +80,32 @@ k_featurise(So3kDims D, int n, int P, const float* __restrict__ R, const int* __
   }
   // ---- radial basis: one edge-row per iteration, lane == k ------------------------------------------
   if (rbf) {
-    for (int q = 0; q < 32; ++q) {
-      float edq = __shfl_sync(0xffffffffu, ed, q);
-      int vq = __shfl_sync(0xffffffffu, valid ? 1 : 0, q);
-      if (q < nrow) {
-        for (int k = lane; k < D.K; k += 32) rbf[(e0 + q) * D.K + k] = vq ? so3k_rbf(edq, k, D) : 0.f;
+    const int lpr = D.K >> 2;                                // lanes per edge row when every lane writes 16 bytes
+    if ((D.K & 3) == 0 && lpr <= 32 && (32 % lpr) == 0) {
+      // vectorised: a store instruction writes 32 / lpr complete rows (one row at K = 128, four at K = 32)
+      const int rpi = 32 / lpr, sub = lane / lpr, k0 = 4 * (lane % lpr);
+      const float edv = valid ? ed : -1.0f;                  // ed = exp(-d) > 0 for a valid edge
+      for (int q0 = 0; q0 < 32; q0 += rpi) {
+        const int q = q0 + sub;
+        const float edq = __shfl_sync(0xffffffffu, edv, q);
+        if (q < nrow) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (edq >= 0.f) {
+            const float t0 = edq - (D.mu0 + (float)k0 * D.dmu);
+            const float t1 = t0 - D.dmu, t2 = t1 - D.dmu, t3 = t2 - D.dmu;
+            v = make_float4(expf(-D.gamma * t0 * t0), expf(-D.gamma * t1 * t1), expf(-D.gamma * t2 * t2),
+                            expf(-D.gamma * t3 * t3));
+          }
+          *reinterpret_cast<float4*>(rbf + (e0 + q) * D.K + k0) = v;
+        }
+      }
+    } else {
+      for (int q = 0; q < 32; ++q) {
+        float edq = __shfl_sync(0xffffffffu, ed, q);
+        int vq = __shfl_sync(0xffffffffu, valid ? 1 : 0, q);
+        if (q < nrow) {
+          for (int k = lane; k < D.K; k += 32) rbf[(e0 + q) * D.K + k] = vq ? so3k_rbf(edq, k, D) : 0.f;
+        }
       }
     }
   }
