@@ -18,6 +18,22 @@ namespace {
 constexpr int WPB = 8;          // warps (rows) per block
 constexpr int AMAX = 16;        // H + nl <= AMAX (stride in the alpha arrays is a multiple of 4)
 
+// Head partial of feature slot t (features 32 t + lane) when the head width DHC is a compile-time constant >= 32: a
+// slot then touches at most two heads, split at a compile-time lane index -- 1 or 2 predicated adds instead of one
+// compare-select-add per head.
+template <int DHC, int HPAD>
+__device__ __forceinline__ void head_accum(float* val, int t, int lane, float p) {
+  const int f0 = 32 * t;
+  const int hlo = f0 / DHC;
+  const int b = (hlo + 1) * DHC - f0;          // lanes < b belong to head hlo, the rest to hlo + 1
+  if (b >= 32) {
+    if (hlo < HPAD) val[hlo] += p;
+  } else {
+    if (hlo < HPAD) val[hlo] += (lane < b) ? p : 0.f;
+    if (hlo + 1 < HPAD) val[hlo + 1] += (lane >= b) ? p : 0.f;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -108,8 +124,8 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 //   x1 = x + sum_e alpha_fb[e][h(f)] v[j][f] ;  chi1 = chi + sum_e alpha_gb[e][l(m)] Y_m(u_e)
 // EP edges per iteration; their EP * 2 * HS per-lane head partials (HS slots per block) are reduced over the warp by one
 // halving butterfly (16 shuffles), as in k_alpha_bwd.
-template <int TN, int HS>                       // TN = ceil(F / 32) ; HS = 4 (H, nl <= 4: two edges per pass) or 8
-__global__ void __launch_bounds__(WPB * 32)
+template <int TN, int HS, int DHF, int DHG>     // TN = ceil(F / 32) ; HS = 4 (H, nl <= 4: two edges per pass) or 8 ;
+__global__ void __launch_bounds__(WPB * 32)     // DHF / DHG = compile-time head widths F/H, F/nl (0: run-time)
 k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ x,
                   const float* __restrict__ chi, const float* __restrict__ proj, const float* __restrict__ wst_f,
@@ -182,10 +198,15 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
         for (int t = 0; t < TN; ++t) {
           const float pf = wf[k][t] * qf[t] * kf[k][t];
           const float pg = wg[k][t] * qg[t] * kg[k][t];
+          if (DHF >= 32 && DHG >= 32) {
+            head_accum<(DHF >= 32 ? DHF : 32), HS>(val + k * 2 * HS, t, lane, pf);
+            head_accum<(DHG >= 32 ? DHG : 32), HS>(val + k * 2 * HS + HS, t, lane, pg);
+          } else {
 #pragma unroll
-          for (int h = 0; h < HS; ++h) {
-            val[k * 2 * HS + h] += (hf[t] == h) ? pf : 0.f;
-            val[k * 2 * HS + HS + h] += (hg[t] == h) ? pg : 0.f;
+            for (int h = 0; h < HS; ++h) {
+              val[k * 2 * HS + h] += (hf[t] == h) ? pf : 0.f;
+              val[k * 2 * HS + HS + h] += (hg[t] == h) ? pg : 0.f;
+            }
           }
         }
       }
@@ -247,8 +268,8 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
 // gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
 // EP = 16 / HP edges per iteration: their EP * HP per-lane head partials are reduced over the warp with ONE halving
 // butterfly (16 shuffles for all of them instead of 5 per value).
-template <int TN, int HP>                       // TN = ceil(F / 32) ; HP = heads padded to 4 or 8
-__global__ void __launch_bounds__(WPB * 32)
+template <int TN, int HP, int DHC>              // TN = ceil(F / 32) ; HP = heads padded to 4 or 8 ; DHC = compile-time
+__global__ void __launch_bounds__(WPB * 32)     // head width F/H (0: run-time)
 k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
             const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
             const float* __restrict__ alpha, const float* __restrict__ xbar1, const float* __restrict__ chibar1,
@@ -322,8 +343,12 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 #pragma unroll
         for (int t = 0; t < TN; ++t) {
           const float p = xb[t] * vv[k][t];
+          if (DHC >= 32) {
+            head_accum<(DHC >= 32 ? DHC : 32), HP>(val + k * HP, t, lane, p);
+          } else {
 #pragma unroll
-          for (int h = 0; h < HP; ++h) val[k * HP + h] += (hsel[t] == h) ? p : 0.f;
+            for (int h = 0; h < HP; ++h) val[k * HP + h] += (hsel[t] == h) ? p : 0.f;
+          }
           accv[t] = fmaf(am[k] * aq[hsel[t]], xx[k][t], accv[t]);
         }
       }
@@ -670,12 +695,14 @@ void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float*
 #define SO3K_AA_CASE(TN_)                                                                                              \
   case TN_:                                                                                                            \
     if (D.H <= 4 && D.nl <= 4)                                                                                         \
-      SO3K_LAUNCH((k_alpha_aggregate<TN_, 4>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, \
-                  g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                                  \
+      SO3K_LAUNCH((k_alpha_aggregate<TN_, 4, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
+                  g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
     else                                                                                                               \
-      SO3K_LAUNCH((k_alpha_aggregate<TN_, 8>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, \
-                  g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                                  \
+      SO3K_LAUNCH((k_alpha_aggregate<TN_, 8, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
+                  g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
     break;
+  // (compile-time head widths, as in so3k_launch_alpha_bwd, were measured to be SLOWER here: with the cheaper
+  //  arithmetic ptxas no longer keeps the 50 row loads of an iteration in flight -- 10.6 instead of 7.2 ms per step)
   switch (so3k_cdiv(D.F, 32)) {
     SO3K_AA_CASE(1) SO3K_AA_CASE(2) SO3K_AA_CASE(3) SO3K_AA_CASE(4) SO3K_AA_CASE(5) SO3K_AA_CASE(6) SO3K_AA_CASE(7)
     SO3K_AA_CASE(8)
@@ -690,12 +717,17 @@ void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj,
 #define SO3K_AB_CASE(TN_)                                                                                              \
   case TN_:                                                                                                            \
     if (D.H <= 4)                                                                                                      \
-      SO3K_LAUNCH((k_alpha_bwd<TN_, 4>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
+      SO3K_LAUNCH((k_alpha_bwd<TN_, 4, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,   \
                   g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
     else                                                                                                               \
-      SO3K_LAUNCH((k_alpha_bwd<TN_, 8>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
+      SO3K_LAUNCH((k_alpha_bwd<TN_, 8, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,   \
                   g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
     break;
+  if (D.F == 132 && D.H == 4) {                    // the reference's default shape: head boundaries known at compile time
+    SO3K_LAUNCH((k_alpha_bwd<5, 4, 33>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,
+                g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);
+    return;
+  }
   switch (so3k_cdiv(D.F, 32)) {
     SO3K_AB_CASE(1) SO3K_AB_CASE(2) SO3K_AB_CASE(3) SO3K_AB_CASE(4) SO3K_AB_CASE(5) SO3K_AB_CASE(6) SO3K_AB_CASE(7)
     SO3K_AB_CASE(8)
