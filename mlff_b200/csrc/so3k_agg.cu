@@ -34,6 +34,18 @@ __device__ __forceinline__ void head_accum(float* val, int t, int lane, float p)
   }
 }
 
+// A load the compiler may not move or merge (asm volatile): used where a whole batch of independent row loads has to be
+// in flight before its first use.  Read-only path, L1-allocating like a plain load.
+__device__ __forceinline__ float ld_pinned(const float* p) {
+#ifdef SO3K_EMU
+  return *p;
+#else
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -448,31 +460,36 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       }
     }
     __syncwarp();
-    // two edges per iteration: 6 * TN independent loads in flight per lane (the kernel is latency-bound otherwise)
-    for (int q = 0; q < cnt; q += 2) {
-      float wv[2][TN], kj[2][TN], qj[2][TN];
-      int qk[2], pp[2];
+    // Two edges per batch, two batches in flight: the 6 * TN row loads of the NEXT batch are issued before the current
+    // one is consumed (explicit double buffering -- left to itself ptxas sinks the loads towards their first use and
+    // the kernel becomes latency-bound).  Indices beyond the chunk are clamped (valid addresses), their terms masked.
+    auto load_batch = [&](int q, float (&wv)[2][TN], float (&kj)[2][TN], float (&qj)[2][TN], int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
-        pp[k] = s_p[w][qk[k]];
-        const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
+        const int qc = (q + k < cnt) ? q + k : cnt - 1;
+        pp[k] = s_p[w][qc];
+        const float* pj = proj + (size_t)s_j[w][qc] * F5;
         const float* pw = wst + (size_t)(pp[k] & 0x7fffffff) * F;
 #pragma unroll
         for (int t = 0; t < TN; ++t) {
           const int f = lane + 32 * t;
           const bool ok = (t + 1 < TN) || f < F;
-          wv[k][t] = ok ? pw[f] : 0.f;
-          kj[k][t] = ok ? pj[koff + f] : 0.f;
-          qj[k][t] = ok ? pj[qoff + f] : 0.f;
+          wv[k][t] = ok ? ld_pinned(pw + f) : 0.f;
+          kj[k][t] = ok ? ld_pinned(pj + koff + f) : 0.f;
+          qj[k][t] = ok ? ld_pinned(pj + qoff + f) : 0.f;
         }
       }
+    };
+    auto use_batch = [&](int q, const float (&wv)[2][TN], const float (&kj)[2][TN], const float (&qj)[2][TN],
+                         const int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const float m = (q + k < cnt) ? 1.f : 0.f;
-        const float* ab = &s_ab[w][qk[k] * 8];
-        const float* abr = &s_abr[w][qk[k] * 8];
-        const bool canon = (pp[k] < 0) && (q + k < cnt);          // warp-uniform
+        const bool live = q + k < cnt;                              // warp-uniform
+        const int qc = live ? q + k : cnt - 1;
+        const float m = live ? 1.f : 0.f;
+        const float* ab = &s_ab[w][qc * 8];
+        const float* abr = &s_abr[w][qc * 8];
+        const bool canon = (pp[k] < 0) && live;
         float* wb = wbar + (size_t)(pp[k] & 0x7fffffff) * F;
 #pragma unroll
         for (int t = 0; t < TN; ++t) {
@@ -483,6 +500,15 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
           if (canon && ((t + 1 < TN) || f < F)) __stcs(wb + f, fmaf(a0 * qi[t], kj[k][t], a1 * qj[k][t] * ki[t]));
         }
       }
+    };
+    float wA[2][TN], kA[2][TN], qA[2][TN], wB[2][TN], kB[2][TN], qB[2][TN];
+    int pA[2], pB[2];
+    load_batch(0, wA, kA, qA, pA);
+    for (int q = 0; q < cnt; q += 4) {
+      load_batch(q + 2, wB, kB, qB, pB);
+      use_batch(q, wA, kA, qA, pA);
+      load_batch(q + 4, wA, kA, qA, pA);
+      use_batch(q + 2, wB, kB, qB, pB);
     }
     __syncwarp();
   }
@@ -701,8 +727,8 @@ void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float*
       SO3K_LAUNCH((k_alpha_aggregate<TN_, 8, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
                   g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
     break;
-  // (compile-time head widths, as in so3k_launch_alpha_bwd, were measured to be SLOWER here: with the cheaper
-  //  arithmetic ptxas no longer keeps the 50 row loads of an iteration in flight -- 10.6 instead of 7.2 ms per step)
+  // (compile-time head widths, as in so3k_launch_alpha_bwd, bring nothing here: 7.3 ms per step either way -- the kernel
+  //  is bound by its 50 row loads per iteration, and with cheaper arithmetic ptxas keeps fewer of them in flight)
   switch (so3k_cdiv(D.F, 32)) {
     SO3K_AA_CASE(1) SO3K_AA_CASE(2) SO3K_AA_CASE(3) SO3K_AA_CASE(4) SO3K_AA_CASE(5) SO3K_AA_CASE(6) SO3K_AA_CASE(7)
     SO3K_AA_CASE(8)
