@@ -11,6 +11,7 @@ update rules, on torch tensors instead of jax arrays:
 * `CalculatorX`       mlff/mdx/calculator.py:46-49 (energy + forces of an AtomsX)
 * `VelocityVerletX`   mlff/mdx/integrator.py:313-342 (the reference evaluates the forces twice per step; the second
                       evaluation of a step is the first of the next one, so it is cached here -- same trajectory)
+* `NoseHooverX`, `LangevinX`   mlff/mdx/integrator.py:17-83, 86-159
 * `simulate`          mlff/mdx/simulate.py:60-82 (kinetic / potential energy per step, one host read-back at the end)
 
 Everything per step is O(N) tensor arithmetic on the device plus the engine calls; the only host synchronisation is the
@@ -112,6 +113,9 @@ class AtomsX:
     def update_momenta(self, momenta: torch.Tensor) -> 'AtomsX':
         return replace(self, momenta=momenta)
 
+    def update_velocities(self, velocities: torch.Tensor) -> 'AtomsX':
+        return replace(self, momenta=velocities * self.masses[:, None])      # mlff/mdx/atoms.py:174-186
+
     def init_spatial_partitioning(self, engine, cutoff: float, skin: float, capacity_multiplier: float = 1.25,
                                   mode: Optional[int] = None) -> 'AtomsX':
         nl = SkinNeighborList(engine, cutoff, skin, self.cell, self.pbc, capacity_multiplier, mode).allocate(self.positions)
@@ -175,7 +179,96 @@ class VelocityVerletX:
         return self, atoms_displaced, properties
 
 
-def simulate(integrator: VelocityVerletX, atoms: AtomsX, steps: int):
+class NoseHooverX:
+    """Nose-Hoover thermostat, mlff/mdx/integrator.py:17-83 (temperature in eV, ttime in units of the time step)."""
+
+    def __init__(self, timestep: float, temperature: float, ttime: float, calculator: CalculatorX, zeta=0.0):
+        self.timestep, self.temperature, self.ttime, self.calculator = float(timestep), float(temperature), float(ttime), calculator
+        self.zeta = zeta
+
+    @classmethod
+    def create(cls, timestep, temperature, ttime, calculator):
+        return cls(timestep, temperature, ttime, calculator)
+
+    def target_Ekin(self, atoms):
+        return 0.5 * (3.0 * atoms.get_number_of_atoms()) * self.temperature
+
+    def Q(self, atoms):
+        return 3.0 * atoms.get_number_of_atoms() * self.temperature * (self.ttime * self.timestep) ** 2
+
+    def step(self, atoms: AtomsX):
+        dt = self.timestep
+        masses = atoms.get_masses()[:, None]
+        accel = self.calculator(atoms)['forces'] / masses
+        vel = atoms.get_velocities()
+        x = atoms.get_positions() + vel * dt + (accel - self.zeta * vel) * (0.5 * dt ** 2)
+        atoms_displaced = atoms.update_positions(x, update_neighbors=True)
+        KE_0 = atoms_displaced.get_kinetic_energy()
+        vel_half = vel + 0.5 * dt * (accel - self.zeta * vel)
+        atoms_displaced = atoms_displaced.update_velocities(vel_half)
+        properties = self.calculator(atoms_displaced)
+        accel = properties['forces'] / masses
+        zeta = self.zeta + 0.5 * dt * (1 / self.Q(atoms)) * (KE_0 - self.target_Ekin(atoms))
+        zeta = zeta + 0.5 * dt * (1 / self.Q(atoms)) * (atoms_displaced.get_kinetic_energy() - self.target_Ekin(atoms))
+        vel = (atoms_displaced.get_velocities() + 0.5 * dt * accel) / (1 + 0.5 * dt * zeta)
+        atoms_displaced = atoms_displaced.update_velocities(vel)
+        return NoseHooverX(self.timestep, self.temperature, self.ttime, self.calculator, zeta), atoms_displaced, properties
+
+
+class LangevinX:
+    """Langevin dynamics, mlff/mdx/integrator.py:86-159 (ASE's scheme: temperature in eV, friction in 1 / ASE time).
+    The reference draws its noise from jax.random; here a torch generator on the atoms' device (the streams differ, the
+    distributions do not)."""
+
+    def __init__(self, timestep: float, temperature: float, friction: float, calculator: CalculatorX, fixcm: bool = True,
+                 seed: int = 0):
+        self.timestep, self.temperature, self.friction = float(timestep), float(temperature), float(friction)
+        self.calculator, self.fixcm = calculator, fixcm
+        self._gen: Optional[torch.Generator] = None
+        self._seed = seed
+
+    @classmethod
+    def create(cls, timestep, temperature, friction, calculator, fixcm=True, seed=0):
+        return cls(timestep, temperature, friction, calculator, fixcm, seed)
+
+    def coefficients(self, atoms: AtomsX):
+        dt, fr = self.timestep, self.friction
+        sigma = torch.sqrt(2 * self.temperature * fr / atoms.get_masses())
+        c1 = dt / 2. - dt * dt * fr / 8.
+        c2 = dt * fr / 2 - dt * dt * fr * fr / 8.
+        c3 = dt ** 0.5 * sigma / 2. - dt ** 1.5 * fr * sigma / 8.
+        c5 = dt ** 1.5 * sigma / (2 * 3 ** 0.5)
+        c4 = fr / 2. * c5
+        return c1, c2, c3[:, None], c4[:, None], c5[:, None]
+
+    def step(self, atoms: AtomsX):
+        dev = atoms.positions.device
+        if self._gen is None:
+            self._gen = torch.Generator(device=dev).manual_seed(self._seed)
+        masses = atoms.get_masses()[:, None]
+        n = atoms.get_number_of_atoms()
+        forces = self.calculator(atoms)['forces']
+        vel = atoms.get_velocities()
+        c1, c2, c3, c4, c5 = self.coefficients(atoms)
+        xi = torch.randn(n, 3, generator=self._gen, dtype=forces.dtype, device=dev)
+        eta = torch.randn(n, 3, generator=self._gen, dtype=forces.dtype, device=dev)
+        rnd_pos = c5 * eta
+        rnd_vel = c3 * xi - c4 * eta
+        if self.fixcm:
+            rnd_pos = rnd_pos - rnd_pos.sum(0, keepdim=True) / n
+            rnd_vel = rnd_vel - (rnd_vel * masses).sum(0, keepdim=True) / (masses * n)
+        vel = vel + (c1 * forces / masses - c2 * vel + rnd_vel)
+        x = atoms.get_positions()
+        atoms_displaced = atoms.update_positions(x + self.timestep * vel + rnd_pos)
+        vel = (atoms_displaced.get_positions() - x - rnd_pos) / self.timestep
+        properties = self.calculator(atoms_displaced)
+        forces = properties['forces']
+        vel = vel + (c1 * forces / masses - c2 * vel + rnd_vel)
+        atoms_displaced = atoms_displaced.update_momenta(vel * masses)
+        return self, atoms_displaced, properties
+
+
+def simulate(integrator, atoms: AtomsX, steps: int):
     """Take `steps` steps; returns (atoms, {'kinetic_energy', 'potential_energy', 'temperature'} as (steps,) numpy arrays)."""
     ek, ep = [], []
     for _ in range(steps):

@@ -174,3 +174,61 @@ def test_md_cuda_graph_replay_equals_eager():
         out.append((atoms.positions.cpu().numpy(), stats['potential_energy']))
     np.testing.assert_allclose(out[0][0], out[1][0], atol=1e-9)
     np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-6)
+
+
+
+def test_nose_hoover_matches_plain_integrator():
+    # NoseHooverX.step (mlff/mdx/integrator.py:49-83) against the same update rule written out in numpy with oracle forces
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    params = o.init_params(cfg, 0, embed_scale=4.0)
+    R0, z, masses, p0, atoms = ethanol_state()
+    eng = OracleEngine(cfg, params)
+    atoms = atoms.init_spatial_partitioning(eng, cutoff=5.0, skin=1.0)
+    dt, T, ttime, steps = 0.5 * md.FS, 300.0 * md.KB_EV, 20.0, 5
+    integ = md.NoseHooverX.create(dt, T, ttime, md.CalculatorX(eng))
+    for _ in range(steps):
+        integ, atoms, _ = integ.step(atoms)
+
+    def forces(R):
+        nl = o.get_indices(R[None], z[None], 5.0)
+        return o.energy_forces(cfg, params, R.astype(np.float32).astype(np.float64), z, nl['idx_i'][0], nl['idx_j'][0])[1].numpy()
+    m = masses[:, None]
+    n = len(z)
+    R, v, zeta = R0.copy(), p0 / m, 0.0
+    target, Q = 0.5 * 3.0 * n * T, 3.0 * n * T * (ttime * dt) ** 2
+    ekin = lambda vv: 0.5 * float((m * vv * vv).sum())
+    for _ in range(steps):
+        a = forces(R) / m
+        R = R + v * dt + (a - zeta * v) * (0.5 * dt ** 2)
+        ke0 = ekin(v)
+        vh = v + 0.5 * dt * (a - zeta * v)
+        a = forces(R) / m
+        zeta = zeta + 0.5 * dt / Q * (ke0 - target)
+        zeta = zeta + 0.5 * dt / Q * (ekin(vh) - target)
+        v = (vh + 0.5 * dt * a) / (1 + 0.5 * dt * zeta)
+    np.testing.assert_allclose(atoms.positions.numpy(), R, atol=1e-8)
+    np.testing.assert_allclose(atoms.get_velocities().numpy(), v, atol=1e-8)
+    assert abs(float(integ.zeta) - zeta) < 1e-10
+
+
+def test_langevin_thermalises_free_particles():
+    # no forces: the Langevin step must drive the kinetic temperature to the target and keep the centre of mass fixed
+    class FreeEngine:
+        def neighbor_list(self, positions, cutoff, capacity, cell=None, pbc=(False,) * 3, **kw):
+            z1 = torch.full((capacity,), -1, dtype=torch.int32)
+            return z1, z1.clone(), torch.zeros((capacity, 3), dtype=torch.int32), torch.tensor([0])
+
+        def energy_forces(self, R, z, ii, jj, cell=None, off=None):
+            return torch.zeros(1, 1), torch.zeros_like(R), None
+    n = 2000
+    masses = torch.full((n,), 12.0, dtype=torch.float64)
+    atoms = md.AtomsX(positions=torch.zeros(n, 3, dtype=torch.float64), momenta=torch.zeros(n, 3, dtype=torch.float64),
+                      masses=masses, numbers=torch.full((n,), 6, dtype=torch.int32))
+    atoms = atoms.init_spatial_partitioning(FreeEngine(), cutoff=1.0, skin=1e9)
+    T = 300.0 * md.KB_EV
+    integ = md.LangevinX.create(1.0 * md.FS, T, 0.05 / md.FS, md.CalculatorX(FreeEngine()), seed=3)
+    for _ in range(400):
+        integ, atoms, _ = integ.step(atoms)
+    temp = float(2.0 * atoms.get_kinetic_energy() / (3 * n)) / md.KB_EV
+    assert abs(temp - 300.0) < 15.0                                      # 6000 degrees of freedom: ~1.8 % standard deviation
+    assert float(atoms.momenta.sum(0).abs().max()) < 1e-9 * n
