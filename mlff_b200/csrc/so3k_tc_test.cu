@@ -44,12 +44,31 @@ k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A
       for (int q = 0; q < 8; ++q) v[q] = B[(size_t)r * imgCols + c * 8 + q];
       tc::store_chunk8(Bhi, Blo, tc::canon_off(r, c, sboB), v);
     }
+  if (variant >= 3) {                              // zero A image for the TMEM clear of the layout probe
+    for (uint32_t o = (uint32_t)tid * 16u; o < szA; o += 128u * 16u) *reinterpret_cast<uint4*>(Alo + o) = make_uint4(0, 0, 0, 0);
+  }
   tc::fence_async_smem();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
+  if (tid == 0 && variant >= 3) {
+    // Layout probe for M = 64 (round-2 groundwork: two 64-row half tiles per CTA).  TMEM is first zeroed by an
+    // M = 128 MMA on an all-zero A image (the lo image, overwritten with zeros below by every thread before the
+    // barrier when variant >= 3), then ONE M = 64 GEMM on rows 0..63 of A is written at lane offset 0 (variant 3) or
+    // 16 (variant 4); the host sees on which of the 128 lanes the 64 result rows land.
+    const uint32_t id128 = tc::make_idesc_bf16(128, N, 0, 0), id64 = tc::make_idesc_bf16(64, N, 0, 0);
+    tc::mma_bf16(tmem, tc::make_desc(tc::smem_u32(Alo), 128u, sboA), tc::make_desc(tc::smem_u32(Bhi), 128u, sboB), id128, 0);
+    const uint32_t dst = tmem + (variant == 4 ? (16u << 16) : 0u);
+    uint32_t acc = 0;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t aoff = (uint32_t)ks * 256u;
+      tc::mma_bf16(dst, tc::make_desc(tc::smem_u32(Ahi) + aoff, 128u, sboA),
+                   tc::make_desc(tc::smem_u32(Bhi) + aoff, 128u, sboB), id64, acc);
+      acc = 1;
+    }
+    tc::commit(&bar);
+  } else if (tid == 0) {
     const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, variant == 2 ? 1 : 0);
     uint32_t acc = 0;
     for (int ks = 0; ks < K / 16; ++ks) {
