@@ -96,6 +96,17 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_ready(self, timeout: float = 3.0):
+        """Block until the first sample has been written (NVML is initialised by then) or the timeout expires."""
+        t0 = time.perf_counter()
+        while self.proc is not None and time.perf_counter() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.proc is None:
@@ -287,6 +298,13 @@ def run_ours(args, w):
             mark('energy all-reduce')
             return e_tot, ddrank.forces[:plan.n_own], None
 
+    # the clock / throttle sampler (nvidia-smi polling) is started BEFORE the warm-up so that its start-up (NVML
+    # initialisation touches every GPU of the box) does not land in the first timed steps; it keeps sampling through the
+    # timed region, which is where its samples are needed
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_ready()
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -296,9 +314,6 @@ def run_ours(args, w):
     prof_in_loop = world == 1
     eng.lib.profile_collect(eng.h, reset=True)
     eng.lib.profile_enable(eng.h, prof_in_loop)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     nl_ev = []
     l0 = eng.lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
