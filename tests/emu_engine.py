@@ -49,7 +49,7 @@ class EmuEngine:
         self.blob = blob
         self.lib.load_params(self.h, ptr(blob), n)
 
-    def energy_forces(self, R, z, idx_i, idx_j, cell=None, cell_offset=None):
+    def energy_forces(self, R, z, idx_i, idx_j, cell=None, cell_offset=None, want_stress=False):
         R = np.ascontiguousarray(R, dtype=np.float32)
         z = np.ascontiguousarray(z, dtype=np.int32)
         ii = np.ascontiguousarray(idx_i, dtype=np.int32)
@@ -66,6 +66,10 @@ class EmuEngine:
         st = np.zeros(1, np.int32)
         self.lib.energy_forces(self.h, B, n, P, ptr(R), ptr(z), ptr(ii), ptr(jj), ptr(cell), ptr(off), ptr(E), ptr(F),
                                ptr(ea), ptr(ws), ws.nbytes, ptr(st))
+        if want_stress:
+            stress = np.zeros((B, 3, 3), np.float32)
+            self.lib.stress(self.h, B, n, P, ptr(ws), ws.nbytes, ptr(stress))
+            return E, F, ea, int(st[0]), stress
         return E, F, ea, int(st[0])
 
     def potential(self, edges, z, centers, others, mask=None, energy_scale=1.0):

@@ -101,12 +101,19 @@ def test_periodic_solid_with_cell_offsets(solid):
     cfg = o.OracleConfig()
     p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
     eng = make(cfg, p)
-    E, F, ea, st = eng.energy_forces(solid['R'][None], solid['z'][None], g['idx_i'][None], g['idx_j'][None],
-                                     cell=solid['unit_cell'][None], cell_offset=g['shifts'][None])
+    E, F, ea, st, stress = eng.energy_forces(solid['R'][None], solid['z'][None], g['idx_i'][None], g['idx_j'][None],
+                                              cell=solid['unit_cell'][None], cell_offset=g['shifts'][None],
+                                              want_stress=True)
     assert st == 0
     assert abs(E[0] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
     assert np.abs(F[0] - g['F']).max() < F_ATOL
     np.testing.assert_allclose(ea[0], g['e_atom'], atol=2e-5)
+    # so3k_stress (k_stress): the strain derivative of the same evaluation (several periodic images per pair)
+    _, _, So = o.energy_forces_stress(cfg, p, solid['R'], solid['z'], g['idx_i'], g['idx_j'], cell=solid['unit_cell'],
+                                      cell_offset=g['shifts'])
+    scale = max(np.abs(So.numpy()).max(), 1.0)
+    assert np.abs(stress[0] - So.numpy()).max() < 1e-4 * scale
+    assert np.abs(stress[0] - stress[0].T).max() < 1e-6 * scale
 
 
 def test_md_seam_displacements(ethanol):
@@ -229,3 +236,20 @@ def test_zbl_repulsion(ethanol):
     ea_o, dE_o = o.potential_displacements(cfg, p, edges, z[0], ii, jj, mask, energy_scale=1.3)
     np.testing.assert_allclose(out[0], ea_o.numpy(), rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(out[1], dE_o.numpy(), rtol=2e-5, atol=2e-5)
+
+
+def test_stress_of_a_molecular_batch(ethanol):
+    # so3k_stress: one tensor per structure of a padded batch (the periodic case is part of
+    # test_periodic_solid_with_cell_offsets)
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 3, embed_scale=4.0)
+    eng = make(cfg, p)
+    B = 2
+    Rb = ethanol['R'][:B]
+    zb = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(Rb, zb, 5.0)
+    _, _, _, st, stb = eng.energy_forces(Rb, zb, nl['idx_i'], nl['idx_j'], want_stress=True)
+    assert st == 0
+    for b in range(B):
+        _, _, So = o.energy_forces_stress(cfg, p, Rb[b], zb[b], nl['idx_i'][b], nl['idx_j'][b])
+        assert np.abs(stb[b] - So.numpy()).max() < 1e-4 * max(np.abs(So.numpy()).max(), 1.0)
