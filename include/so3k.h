@@ -81,7 +81,20 @@ enum {
    * ends with the ten RAW ZBLRepulsion scalars zbl/{a1,a2,a3,a4,c1,c2,c3,c4,p,d} (softplus is applied at use, as in the
    * reference).  so3k_config.zbl_shift is subtracted once per structure (so3k_energy_forces, 'per_structure'
    * convention) or from every atom (so3k_potential_displacements, 'per_atom' convention), as the reference does. */
-  SO3K_FLAG_ZBL = 4
+  SO3K_FLAG_ZBL = 4,
+  /* Optional So3kratesLayer branches (mlff/nn/layer/so3krates_layer.py:30-42, selected in the reference through
+   * So3krates(so3krates_layer_kwargs=...), so they hold for EVERY layer):
+   *   SO3K_FLAG_LAYER_NORM      layer_normalization=True: flax LayerNorm (eps 1e-6, scale + bias over the F features)
+   *                             before the feature/geometric blocks and before the interaction block (:103-106, :153-156);
+   *                             the skip connections keep the un-normalised features (:146, :163)
+   *   SO3K_FLAG_FINAL_LAYER     final_layer=True: with LAYER_NORM, a third LayerNorm on the layer's output (:170-174)
+   *   SO3K_FLAG_RESIDUAL_MLP_1  residual_mlp_1=True: ResidualMLP (mlff/nn/mlp/mlp.py:30-72; three bias-free F x F
+   *   SO3K_FLAG_RESIDUAL_MLP_2  Dense with silu) after the first / second skip connection (:149-150, :166-167)
+   * The parameter blob grows per layer as documented at so3k_load_params. */
+  SO3K_FLAG_LAYER_NORM = 8,
+  SO3K_FLAG_RESIDUAL_MLP_1 = 16,
+  SO3K_FLAG_RESIDUAL_MLP_2 = 32,
+  SO3K_FLAG_FINAL_LAYER = 64
 };
 
 enum {
@@ -117,6 +130,10 @@ const char* so3k_version(void);
  *       layers_t/blk/q/kernel (heads, d, d) ; layers_t/blk/k/kernel (heads, d, d)
  *       [fb only] layers_t/fb/v/kernel (H, F/H, F/H)        (fb: heads=H ; gb: heads=nl)
  *     layers_t/int/layers_0/{kernel (F+nl,F+nl), bias (F+nl)}
+ *     [SO3K_FLAG_LAYER_NORM]      layers_t/ln_1/{scale (F), bias (F)} ; layers_t/ln_2/{scale, bias}
+ *     [.. + SO3K_FLAG_FINAL_LAYER] layers_t/ln_3/{scale, bias}
+ *     [SO3K_FLAG_RESIDUAL_MLP_1]  layers_t/res_1/{layers_0/kernel, layers_1/kernel, out/kernel}   (F,F) each
+ *     [SO3K_FLAG_RESIDUAL_MLP_2]  layers_t/res_2/{layers_0/kernel, layers_1/kernel, out/kernel}
  *   energy/layers_0/{kernel (F,F), bias (F)} ; energy/layers_1/{kernel (F,1), bias (1)}
  *   energy/per_atom_scale (num_embeddings) ; energy/per_atom_shift (num_embeddings)
  * so3k_param_lookup maps such a name to (offset, count) in the blob. */

@@ -20,6 +20,10 @@ STATUS_BAD_Z = 4
 FLAG_TENSOR = 1
 FLAG_KEEP_FILTERS = 2    # with FLAG_TENSOR: keep the forward's filters for the backward (memory for time)
 FLAG_ZBL = 4             # Energy(zbl_repulsion=True): ZBL pair repulsion, ten extra scalars at the end of the blob
+FLAG_LAYER_NORM = 8      # So3kratesLayer(layer_normalization=True)
+FLAG_RESIDUAL_MLP_1 = 16 # So3kratesLayer(residual_mlp_1=True)
+FLAG_RESIDUAL_MLP_2 = 32 # So3kratesLayer(residual_mlp_2=True)
+FLAG_FINAL_LAYER = 64    # So3kratesLayer(final_layer=True): post LayerNorm (with FLAG_LAYER_NORM)
 NL_ASE = 0
 NL_DENSE = 1
 

@@ -5,6 +5,7 @@
 """
 from __future__ import annotations
 
+import copy
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence
 
@@ -27,6 +28,12 @@ class So3kratesConfig:
     mic: bool = False
     zbl_repulsion: bool = False           # Energy(zbl_repulsion=...), mlff/nn/observable/observable.py:39 (CLI --zbl_repulsion)
     zbl_repulsion_shift: float = 0.0      # observable.py:40
+    # optional So3kratesLayer branches (so3krates_layer.py:30-42), set for every layer through
+    # So3krates(so3krates_layer_kwargs=...) (so3krates.py:23-25, 38)
+    layer_normalization: bool = False     # pre-LayerNorm before the blocks and before the interaction block
+    final_layer: bool = False             # with layer_normalization: post-LayerNorm on the layer output
+    residual_mlp_1: bool = False          # ResidualMLP after the first skip connection
+    residual_mlp_2: bool = False          # ResidualMLP after the second skip connection
     prop_keys: Dict[str, str] = field(default_factory=lambda: dict(md17_property_keys))
 
     def validate(self):
@@ -58,10 +65,14 @@ class So3kratesConfig:
             'solid_harmonic': (geo.get('solid_harmonic', False), (False,)),
             'fb_filter': (l0.get('fb_filter', 'radial_spherical'), ('radial_spherical',)),
             'gb_filter': (l0.get('gb_filter', 'radial_spherical'), ('radial_spherical',)),
-            'layer_normalization': (l0.get('layer_normalization', False), (False,)),
-            'residual_mlp_1': (l0.get('residual_mlp_1', False), (False,)),
-            'residual_mlp_2': (l0.get('residual_mlp_2', False), (False,)),
+            'non_local_feature': (l0.get('non_local_feature', False), (False,)),
+            'non_local_sphc': (l0.get('non_local_sphc', False), (False,)),
         }
+        opt_keys = ('layer_normalization', 'final_layer', 'residual_mlp_1', 'residual_mlp_2')
+        for k in opt_keys:      # So3krates() gives every layer the same keyword arguments; mixed stacks are not implemented
+            if any(bool(l.get(k, False)) != bool(l0.get(k, False)) for l in layers):
+                raise NotImplementedError(f'hyper-parameter {k} differs between layers: outside the hot path implemented '
+                                          'by mlff_b200')
         for k, (v, ok) in checks.items():
             if v not in ok:
                 raise NotImplementedError(f'hyper-parameter {k}={v!r} is outside the hot path implemented by mlff_b200')
@@ -74,6 +85,7 @@ class So3kratesConfig:
                    num_embeddings=int(feat.get('num_embeddings', 100)), mic=bool(geo.get('mic', False)),
                    zbl_repulsion=bool(obs.get('zbl_repulsion', False)),
                    zbl_repulsion_shift=float(obs.get('zbl_repulsion_shift', 0.0) or 0.0),
+                   **{k: bool(l0.get(k, False)) for k in opt_keys},
                    prop_keys=dict(sn.get('prop_keys', md17_property_keys)))
 
     def to_hyperparameters(self) -> Dict:
@@ -83,10 +95,11 @@ class So3kratesConfig:
             'fb_filter': 'radial_spherical', 'fb_rad_filter_features': [F, F], 'fb_sph_filter_features': [int(F / 4), F],
             'fb_attention': 'conv_att', 'gb_filter': 'radial_spherical', 'gb_rad_filter_features': [F, F],
             'gb_sph_filter_features': [int(F / 4), F], 'gb_attention': 'conv_att', 'n_heads': self.n_heads,
-            'residual_mlp_1': False, 'residual_mlp_2': False, 'non_local_sphc': False, 'non_local_feature': False,
+            'residual_mlp_1': self.residual_mlp_1, 'residual_mlp_2': self.residual_mlp_2, 'non_local_sphc': False,
+            'non_local_feature': False,
             'fast_attention_kwargs': None, 'chi_cut': None, 'chi_cut_dynamic': False, 'degrees': list(self.degrees),
-            'parity': True, 'layer_normalization': False, 'sphc_normalization': False,
-            'neighborhood_normalization': False, 'final_layer': False}}
+            'parity': True, 'layer_normalization': self.layer_normalization, 'sphc_normalization': False,
+            'neighborhood_normalization': False, 'final_layer': self.final_layer}}
         geo = {'geometry_embed': {'degrees': list(self.degrees), 'radial_basis_function': 'phys', 'n_rbf': self.n_rbf,
                                   'radial_cutoff_fn': 'cosine_cutoff_fn', 'r_cut': self.r_cut, 'sphc': True,
                                   'sphc_normalization': None, 'solid_harmonic': False, 'mic': self.mic,
@@ -97,5 +110,5 @@ class So3kratesConfig:
                           'zbl_repulsion_shift': self.zbl_repulsion_shift,
                           'prop_keys': self.prop_keys}}
         return {'stack_net': {'geometry_embeddings': [geo], 'feature_embeddings': [feat],
-                              'layers': [layer for _ in range(self.n_layer)], 'observables': [obs],
+                              'layers': [copy.deepcopy(layer) for _ in range(self.n_layer)], 'observables': [obs],
                               'prop_keys': self.prop_keys, 'n_layers': self.n_layer}}

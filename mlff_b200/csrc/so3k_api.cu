@@ -130,7 +130,7 @@ bool make_dims(const so3k_config& c, So3kDims* D) {
   return true;
 }
 
-void make_layout(const So3kDims& D, ModelLayout* ml, bool zbl) {
+void make_layout(const So3kDims& D, ModelLayout* ml, bool zbl, int node_opts) {
   size_t off = 0;
   auto add = [&](const std::string& name, size_t count) {
     size_t o = off;
@@ -161,7 +161,21 @@ void make_layout(const So3kDims& D, ModelLayout* ml, bool zbl) {
     }
     ml->layers[t].int_W = add(lt + "int/layers_0/kernel", (F + nl) * (F + nl));
     ml->layers[t].int_b = add(lt + "int/layers_0/bias", F + nl);
+    LayerParams& lp = ml->layers[t];
+    const int n_ln = (node_opts & SO3K_OPT_LN) ? ((node_opts & SO3K_OPT_LN_POST) ? 3 : 2) : 0;
+    for (int k = 0; k < n_ln; ++k) {
+      lp.ln_s[k] = add(lt + "ln_" + std::to_string(k + 1) + "/scale", F);
+      lp.ln_b[k] = add(lt + "ln_" + std::to_string(k + 1) + "/bias", F);
+    }
+    for (int r = 0; r < 2; ++r) {
+      if (!(node_opts & (r ? SO3K_OPT_RES2 : SO3K_OPT_RES1))) continue;
+      std::string pre = lt + "res_" + std::to_string(r + 1) + "/";
+      lp.res[r][0] = add(pre + "layers_0/kernel", F * F);
+      lp.res[r][1] = add(pre + "layers_1/kernel", F * F);
+      lp.res[r][2] = add(pre + "out/kernel", F * F);
+    }
   }
+  ml->node_opts = node_opts;
   ml->out_W1 = add("energy/layers_0/kernel", F * F);
   ml->out_b1 = add("energy/layers_0/bias", F);
   ml->out_W2 = add("energy/layers_1/kernel", F);
@@ -196,13 +210,24 @@ struct Workspace {
   float *wbar;             // tensor mode: pair-indexed filter cotangents of the layer being differentiated [block][pair][F]
   float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
   float *e_atom;
+  // optional node-level branches (SO3K_OPT_*; all null in the default model)
+  float *xn;               // LayerNorm output feeding the projections / the interaction block ; backward scratch
+  float *x1a;              // per layer: x + x_local, the input of ResidualMLP 1
+  float *x1b;              // per layer: first skip state (input of the second LayerNorm)
+  float *x2a;              // per layer: second skip state before ResidualMLP 2
+  float *x2b;              // per layer: layer output before the post LayerNorm
   size_t bytes;
 };
 
-static inline int wst_layers_of(const HandleImpl* h) { return h->use_tc ? (h->keep_w ? h->dims.L : 1) : 0; }
+// low bits: 0 (fp32 CUDA-core mode), 1 (tensor mode, filters recomputed in the backward) or L (kept) ; the SO3K_OPT_*
+// bits of the optional node-level branches ride above them
+constexpr int WS_OPT_SHIFT = 16;
+static inline int wst_layers_of(const HandleImpl* h) {
+  return (h->use_tc ? (h->keep_w ? h->dims.L : 1) : 0) | (h->layout.node_opts << WS_OPT_SHIFT);
+}
 
-// wst_layers: 0 (fp32 CUDA-core mode), 1 (tensor mode, filters recomputed in the backward) or L (kept)
-Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int wst_layers) {
+Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int ws_mode) {
+  const int wst_layers = ws_mode & ((1 << WS_OPT_SHIFT) - 1), opts = ws_mode >> WS_OPT_SHIFT;
   Workspace w;
   char* p = (char*)base;
   auto take = [&](size_t bytes) {
@@ -246,6 +271,12 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int wst_layers)
   w.chibar_a = (float*)take(sizeof(float) * N * M);
   w.chibar_b = (float*)take(sizeof(float) * N * M);
   w.e_atom = (float*)take(sizeof(float) * N);
+  const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST);
+  w.xn = ln ? (float*)take(sizeof(float) * N * F) : nullptr;
+  w.x1a = (opts & SO3K_OPT_RES1) ? (float*)take(sizeof(float) * L * N * F) : nullptr;
+  w.x1b = ln ? (float*)take(sizeof(float) * L * N * F) : nullptr;
+  w.x2a = (opts & SO3K_OPT_RES2) ? (float*)take(sizeof(float) * L * N * F) : nullptr;
+  w.x2b = post ? (float*)take(sizeof(float) * L * N * F) : nullptr;
   w.bytes = (size_t)(p - (char*)base);
   return w;
 }
@@ -270,7 +301,21 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
   float* ct = w.chi + (size_t)t * N * M;
   float* alpha_t = w.alpha + (size_t)t * Pe * Ast;
   float* proj_t = w.proj + (size_t)t * N * 5 * F;
-  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xt, prm, lp, proj_t, st); }
+  // optional branches: the states between the blocks (each aliases its successor when the branch is absent)
+  const int opts = h->layout.node_opts;
+  const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST);
+  const bool res1 = opts & SO3K_OPT_RES1, res2 = opts & SO3K_OPT_RES2;
+  float* x1b = ln ? w.x1b + (size_t)t * N * F : w.x1;              // first skip state
+  float* x1a = res1 ? w.x1a + (size_t)t * N * F : x1b;            // x + x_local
+  float* x2b = post ? w.x2b + (size_t)t * N * F : xt + N * F;     // layer output before the post LayerNorm
+  float* x2a = res2 ? w.x2a + (size_t)t * N * F : x2b;            // second skip state before ResidualMLP 2
+  const float* xin = xt;
+  if (ln) {
+    PROF(CAT_NODE_PROJ);
+    so3k_launch_layernorm((int)N, (int)F, xt, prm + lp.ln_s[0], prm + lp.ln_b[0], w.xn, st);
+    xin = w.xn;
+  }
+  { PROF(CAT_NODE_PROJ); so3k_launch_node_proj(D, (int)N, xin, prm, lp, proj_t, st); }
   if (h->use_tc) {
     // filters of both blocks per undirected pair on the tensor cores, then one streaming pass: attention coefficients
     // + both aggregations
@@ -283,15 +328,19 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
       so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
     }
     PROF(CAT_AGGREGATE);
-    so3k_launch_alpha_aggregate(D, w.g, xt, ct, proj_t, wst_t, wst_t + Pc * F, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+    so3k_launch_alpha_aggregate(D, w.g, xt, ct, proj_t, wst_t, wst_t + Pc * F, alpha_t, x1a, w.chi1 + (size_t)t * N * M, st);
   } else {
     { PROF(CAT_EDGE_FWD); so3k_launch_edge_fwd(D, w.g, h->wf[t], h->wg[t], ct, proj_t, alpha_t, st); }
     PROF(CAT_AGGREGATE);
-    so3k_launch_aggregate(D, w.g, xt, ct, proj_t, alpha_t, w.x1, w.chi1 + (size_t)t * N * M, st);
+    so3k_launch_aggregate(D, w.g, xt, ct, proj_t, alpha_t, x1a, w.chi1 + (size_t)t * N * M, st);
   }
   PROF(CAT_INTERACTION);
-  so3k_launch_interaction(D, (int)N, w.x1, w.chi1 + (size_t)t * N * M, prm, lp, xt + N * F, ct + N * M,
-                          w.bcoef + (size_t)t * N * nl, st);
+  if (res1) so3k_launch_resmlp(D, (int)N, x1a, prm, lp.res[0], x1b, st);
+  if (ln) so3k_launch_layernorm((int)N, (int)F, x1b, prm + lp.ln_s[1], prm + lp.ln_b[1], w.xn, st);
+  so3k_launch_interaction(D, (int)N, ln ? w.xn : x1b, w.chi1 + (size_t)t * N * M, prm, lp, x2a, ct + N * M,
+                          w.bcoef + (size_t)t * N * nl, st, ln ? x1b : nullptr);
+  if (res2) so3k_launch_resmlp(D, (int)N, x2a, prm, lp.res[1], x2b, st);
+  if (post) so3k_launch_layernorm((int)N, (int)F, x2b, prm + lp.ln_s[2], prm + lp.ln_b[2], xt + N * F, st);
 }
 
 // e_atom and d(sum e)/dx_L -> xbar_a ; chibar_a = 0 ; rbar = 0
@@ -316,10 +365,27 @@ void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, f
 // interaction block of layer t: (xbar_a, chibar_a) = cotangent of (x_{t+1}, chi_{t+1})  ->  (xbar_b, chibar_b) = (xbar1, chibar1)
 void stage_layer_bwd_a(HandleImpl* h, Workspace& w, int t, cudaStream_t st) {
   const So3kDims& D = h->dims;
-  const size_t N = w.g.N;
+  const size_t N = w.g.N, F = D.F;
+  const LayerParams& lp = h->layout.layers[t];
+  const int opts = h->layout.node_opts;
+  const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST);
+  const bool res1 = opts & SO3K_OPT_RES1, res2 = opts & SO3K_OPT_RES2;
   PROF(CAT_INTERACTION_BWD);
+  // the optional branches above the interaction block, last to first (all in place on xbar_a)
+  if (post) {
+    const float* x2b = w.x2b + (size_t)t * N * F;
+    so3k_launch_layernorm_bwd((int)N, (int)F, x2b, h->params + lp.ln_s[2], w.xbar_a, nullptr, w.xbar_a, st);
+  }
+  if (res2)
+    so3k_launch_resmlp_bwd(D, (int)N, w.x2a + (size_t)t * N * F, h->params, h->params_T, lp.res[1], w.xbar_a, w.xbar_a, st);
   so3k_launch_interaction_bwd(D, (int)N, w.chi1 + (size_t)t * N * D.M, w.bcoef + (size_t)t * N * D.nl, h->params_T,
-                              h->layout.layers[t], w.xbar_a, w.chibar_a, w.xbar_b, w.chibar_b, st);
+                              lp, w.xbar_a, w.chibar_a, w.xbar_b, w.chibar_b, st, !ln);
+  // ... and those between the first skip connection and the interaction block: xbar_b becomes the cotangent of x + x_local
+  if (ln)       // xbar_b holds the cotangent of the normalised input: back through LayerNorm 2, plus the skip connection
+    so3k_launch_layernorm_bwd((int)N, (int)F, w.x1b + (size_t)t * N * F, h->params + lp.ln_s[1], w.xbar_b, w.xbar_a,
+                              w.xbar_b, st);
+  if (res1)
+    so3k_launch_resmlp_bwd(D, (int)N, w.x1a + (size_t)t * N * F, h->params, h->params_T, lp.res[0], w.xbar_b, w.xbar_b, st);
 }
 
 // everything below the interaction block of layer t: edge cotangents, rbar += ..., and (t > 0) the cotangent of
@@ -364,8 +430,16 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
   if (t > 0) {
     // chi0 = 0 and x0 = embedding are constants of the positions: their cotangents are not needed
     { PROF(CAT_CHI_BWD); so3k_launch_chi_bwd(D, w.g, ct, w.gbar, w.chibar_b, w.chibar_a, st); }     // chibar_a <- d/d chi_t
-    { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, (int)N, w.gproj, h->params_T, lp, w.xbar_b, st); }   // xbar_b += proj^T
-    cudaMemcpyAsync(w.xbar_a, w.xbar_b, sizeof(float) * N * F, cudaMemcpyDeviceToDevice, st);      // xbar_a <- d/d x_t
+    if (h->layout.node_opts & SO3K_OPT_LN) {
+      // the projections read LayerNorm 1 (x_t): their cotangent goes back through it, the skip connection adds xbar_b
+      PROF(CAT_NODE_PROJ_BWD);
+      cudaMemsetAsync(w.xn, 0, sizeof(float) * N * F, st);
+      so3k_launch_node_proj_bwd(D, (int)N, w.gproj, h->params_T, lp, w.xn, st);
+      so3k_launch_layernorm_bwd((int)N, (int)F, w.x + (size_t)t * N * F, h->params + lp.ln_s[0], w.xn, w.xbar_b, w.xbar_a, st);
+    } else {
+      { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, (int)N, w.gproj, h->params_T, lp, w.xbar_b, st); }   // xbar_b += proj^T
+      cudaMemcpyAsync(w.xbar_a, w.xbar_b, sizeof(float) * N * F, cudaMemcpyDeviceToDevice, st);      // xbar_a <- d/d x_t
+    }
   }
 }
 
@@ -414,7 +488,11 @@ int so3k_create(const so3k_config* cfg, so3k_handle** out) {
   h->use_tc = (cfg->flags & SO3K_FLAG_TENSOR) != 0;
   h->keep_w = h->use_tc && (cfg->flags & SO3K_FLAG_KEEP_FILTERS) != 0;
   if (const char* e = getenv("SO3K_TC_B2")) h->tc_b2 = atoi(e) != 0;
-  make_layout(D, &h->layout, (cfg->flags & SO3K_FLAG_ZBL) != 0);
+  int node_opts = 0;
+  if (cfg->flags & SO3K_FLAG_LAYER_NORM) node_opts |= SO3K_OPT_LN | ((cfg->flags & SO3K_FLAG_FINAL_LAYER) ? SO3K_OPT_LN_POST : 0);
+  if (cfg->flags & SO3K_FLAG_RESIDUAL_MLP_1) node_opts |= SO3K_OPT_RES1;
+  if (cfg->flags & SO3K_FLAG_RESIDUAL_MLP_2) node_opts |= SO3K_OPT_RES2;
+  make_layout(D, &h->layout, (cfg->flags & SO3K_FLAG_ZBL) != 0, node_opts);
   *out = h;
   return SO3K_OK;
 }

@@ -14,7 +14,12 @@ struct BlockParams {            // one filter block (fb or gb) of one layer
 struct LayerParams {
   BlockParams fb, gb;
   size_t int_W, int_b;                      // (F+nl,F+nl) (F+nl)
+  // optional branches (SO3K_FLAG_LAYER_NORM / _FINAL_LAYER / _RESIDUAL_MLP_1 / _2); 0 when absent
+  size_t ln_s[3] = {0, 0, 0}, ln_b[3] = {0, 0, 0};     // LayerNorm scale / bias (F): pre-1, pre-2, post
+  size_t res[2][3] = {{0, 0, 0}, {0, 0, 0}};           // ResidualMLP r: Residual layers_0, layers_1, final Dense (F,F)
 };
+// optional node-level branches of every layer
+enum { SO3K_OPT_LN = 1, SO3K_OPT_LN_POST = 2, SO3K_OPT_RES1 = 4, SO3K_OPT_RES2 = 8 };
 struct ModelLayout {
   size_t embed;
   std::vector<LayerParams> layers;
@@ -22,6 +27,7 @@ struct ModelLayout {
   size_t scale, shift;                      // (nemb) each
   size_t zbl = 0;                           // 10 raw ZBLRepulsion scalars (a1..a4, c1..c4, p, d) with SO3K_FLAG_ZBL
   bool has_zbl = false;
+  int node_opts = 0;                        // SO3K_OPT_*
   size_t total;
   std::vector<std::pair<std::string, std::pair<size_t, size_t>>> names;   // name -> (offset, count)
 };
@@ -73,11 +79,26 @@ void so3k_launch_transpose_params(const So3kDims& D, const ModelLayout& ml, cons
                                   cudaStream_t st);
 void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, const float* params_T,
                                const LayerParams& lp, float* xbar /* += */, cudaStream_t st);
+// x2 = xbase + a(x1, chi1) ; xbase = nullptr means x1 (the default layer: input and skip base coincide)
 void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const float* chi1, const float* params,
-                             const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st);
+                             const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st,
+                             const float* xbase = nullptr);
+// skip = false leaves the identity (skip-connection) term out of xbar1: only the cotangent of the block's x input
 void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, const float* bcoef,
                                  const float* params_T, const LayerParams& lp, const float* xbar_out,
-                                 const float* chibar_out, float* xbar1, float* chibar1, cudaStream_t st);
+                                 const float* chibar_out, float* xbar1, float* chibar1, cudaStream_t st,
+                                 bool skip = true);
+// flax LayerNorm over the F features of every row: y = (x - mean) * rsqrt(var + 1e-6) * scale + bias
+void so3k_launch_layernorm(int N, int F, const float* x, const float* scale, const float* bias, float* y, cudaStream_t st);
+// out = (add ? add : 0) + dLayerNorm(x)^T gy ; out may alias gy or add
+void so3k_launch_layernorm_bwd(int N, int F, const float* x, const float* scale, const float* gy, const float* add,
+                               float* out, cudaStream_t st);
+// ResidualMLP: y = silu(x + silu(silu(x) W0) W1) W2 ; W = the three (F,F) matrices of LayerParams::res[r]
+void so3k_launch_resmlp(const So3kDims& D, int N, const float* x, const float* params, const size_t* W, float* y,
+                        cudaStream_t st);
+// xbar = dResidualMLP(x)^T ybar ; xbar may alias ybar ; params_T holds the transposed matrices
+void so3k_launch_resmlp_bwd(const So3kDims& D, int N, const float* x, const float* params, const float* params_T,
+                            const size_t* W, const float* ybar, float* xbar, cudaStream_t st);
 void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* params,
                          const float* params_T, const ModelLayout& ml, float out_scale, float* e_atom, float* xbar,
                          cudaStream_t st);

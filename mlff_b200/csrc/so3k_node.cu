@@ -8,6 +8,8 @@
 //   q / k / v Dense          mlff/nn/layer/so3krates_layer.py:583-584, 607  (per head, no bias)
 //   InteractionBlock         mlff/nn/layer/so3krates_layer.py:355-379 (+ skip :163-164)
 //   Energy                   mlff/nn/observable/observable.py:77-91
+//   LayerNorm (optional)     mlff/nn/layer/so3krates_layer.py:103-106, 153-156, 170-174 (flax nn.LayerNorm defaults)
+//   ResidualMLP (optional)   mlff/nn/mlp/mlp.py:30-72, so3krates_layer.py:149-150, 166-167
 #include "so3k_internal.h"
 
 namespace {
@@ -119,11 +121,12 @@ k_node_proj_bwd(So3kDims D, int N, const float* __restrict__ gproj, const float*
   }
 }
 
-// x2 = x1 + a ; chi2 = chi1 * (1 + repeat(b)) ; [a|b] = [x1 | l0(chi1)] W + bias
+// x2 = xbase + a ; chi2 = chi1 * (1 + repeat(b)) ; [a|b] = [x1 | l0(chi1)] W + bias ; xbase = nullptr: x1
+// (with layer normalisation x1 is the normalised input and xbase the un-normalised skip connection)
 __global__ void __launch_bounds__(NT)
 k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __restrict__ chi1,
-              const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ x2,
-              float* __restrict__ chi2, float* __restrict__ bcoef) {
+              const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ xbase,
+              float* __restrict__ x2, float* __restrict__ chi2, float* __restrict__ bcoef) {
   SO3K_DYN_SMEM(float, sm);
   const int F = D.F, nl = D.nl, M = D.M, FI = D.F + D.nl;
   float* ys = sm;                 // [FI][LDA]
@@ -155,7 +158,8 @@ k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __re
     if (o < F) {
 #pragma unroll
       for (int a = 0; a < TA; ++a)
-        if (a0 + a < N) x2[(size_t)(a0 + a) * F + o] = ys[o * LDA + a] + acc[a];
+        if (a0 + a < N)
+          x2[(size_t)(a0 + a) * F + o] = (xbase ? xbase[(size_t)(a0 + a) * F + o] : ys[o * LDA + a]) + acc[a];
     } else {
 #pragma unroll
       for (int a = 0; a < TA; ++a) {
@@ -174,7 +178,8 @@ k_interaction(So3kDims D, int N, const float* __restrict__ x1, const float* __re
 __global__ void __launch_bounds__(NT)
 k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float* __restrict__ bcoef,
                   const float* __restrict__ W, const float* __restrict__ xbar_out,
-                  const float* __restrict__ chibar_out, float* __restrict__ xbar1, float* __restrict__ chibar1) {
+                  const float* __restrict__ chibar_out, int skip, float* __restrict__ xbar1,
+                  float* __restrict__ chibar1) {
   SO3K_DYN_SMEM(float, sm);
   const int F = D.F, nl = D.nl, M = D.M, FI = D.F + D.nl;
   float* gs = sm;                 // [FI][LDA] = [xbar_out | bbar] transposed
@@ -208,7 +213,7 @@ k_interaction_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float
     if (c < F) {
 #pragma unroll
       for (int a = 0; a < TA; ++a)
-        if (a0 + a < N) xbar1[(size_t)(a0 + a) * F + c] = gs[c * LDA + a] + acc[a];
+        if (a0 + a < N) xbar1[(size_t)(a0 + a) * F + c] = skip ? gs[c * LDA + a] + acc[a] : acc[a];
     } else {
 #pragma unroll
       for (int a = 0; a < TA; ++a) Gb[a * nl + (c - F)] = acc[a];
@@ -307,6 +312,210 @@ __global__ void k_energy_sum(int B, int n, const float* __restrict__ e_atom, flo
   }
 }
 
+// ---- optional branches ------------------------------------------------------------------------------------
+// flax nn.LayerNorm defaults: statistics over the last axis, var = max(0, E[x^2] - E[x]^2) (use_fast_variance),
+// eps = 1e-6, learnable scale and bias.  One warp per atom row.  (Rows of padding atoms are normalised like any
+// other: they have no edges and are masked in the read-out, so the reference's safe_mask there is unobservable.)
+constexpr float LN_EPS = 1e-6f;
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(128)
+k_layernorm(int N, int F, const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ bias,
+            float* __restrict__ y) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;                 // warp-uniform
+  const float* xr = x + (size_t)row * F;
+  float s1 = 0.f, s2 = 0.f;
+  for (int f = lane; f < F; f += 32) {
+    const float v = xr[f];
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float mean = s1 / (float)F;
+  const float var = fmaxf(0.f, s2 / (float)F - mean * mean);
+  const float r = rsqrtf(var + LN_EPS);
+  for (int f = lane; f < F; f += 32) y[(size_t)row * F + f] = (xr[f] - mean) * r * scale[f] + bias[f];
+}
+
+// out = add + r * (g - mean(g) - xhat * mean(g * xhat)),  g = gy * scale,  xhat = (x - mean) * r
+// gy / add / out are not __restrict__: out may alias either (every element is read before it is written, by the
+// lane that writes it)
+__global__ void __launch_bounds__(128)
+k_layernorm_bwd(int N, int F, const float* __restrict__ x, const float* __restrict__ scale, const float* gy,
+                const float* add, float* out) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* xr = x + (size_t)row * F;
+  const float* gr = gy + (size_t)row * F;
+  float s1 = 0.f, s2 = 0.f;
+  for (int f = lane; f < F; f += 32) {
+    const float v = xr[f];
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float mean = s1 / (float)F;
+  const float var = fmaxf(0.f, s2 / (float)F - mean * mean);
+  const float r = rsqrtf(var + LN_EPS);
+  float g1 = 0.f, g2 = 0.f;
+  for (int f = lane; f < F; f += 32) {
+    const float g = gr[f] * scale[f];
+    g1 += g;
+    g2 = fmaf(g, (xr[f] - mean) * r, g2);
+  }
+  g1 = warp_sum(g1) / (float)F;
+  g2 = warp_sum(g2) / (float)F;
+  for (int f = lane; f < F; f += 32) {
+    const float g = gr[f] * scale[f];
+    const float v = r * (g - g1 - (xr[f] - mean) * r * g2);
+    out[(size_t)row * F + f] = add ? add[(size_t)row * F + f] + v : v;
+  }
+}
+
+// tile[c][a] (transposed, column stride LDA) <- rows a0.. of a row-major (N,F) array
+__device__ __forceinline__ void load_tile_T(float* tile, const float* src, int a0, int N, int F) {
+  for (int t = threadIdx.x; t < TA * F; t += NT) {
+    int a = t / F, f = t % F;
+    tile[f * LDA + a] = (a0 + a < N) ? src[(size_t)(a0 + a) * F + f] : 0.f;
+  }
+}
+
+// ResidualMLP(num_residuals=1, num_blocks_per_residual=2, use_bias=False), mlp.py:30-72:
+//   h1 = silu(x) W0 ; r = x + silu(h1) W1 ; y = silu(r) W2
+__global__ void __launch_bounds__(NT)
+k_resmlp(So3kDims D, int N, const float* __restrict__ x, const float* __restrict__ W0, const float* __restrict__ W1,
+         const float* __restrict__ W2, float* __restrict__ y) {
+  SO3K_DYN_SMEM(float, sm);
+  const int F = D.F;
+  float* X = sm;                  // [F][LDA] x
+  float* T0 = X + F * LDA;        // silu(x), then silu(r)
+  float* T1 = T0 + F * LDA;       // silu(h1)
+  const int a0 = blockIdx.x * TA;
+  load_tile_T(X, x, a0, N, F);
+  __syncthreads();
+  for (int t = threadIdx.x; t < F * TA; t += NT) {
+    const int k = (t / TA) * LDA + (t % TA);
+    T0[k] = so3k_silu(X[k]);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F; o += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(T0, 0, F, W0, F, o, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) T1[o * LDA + a] = so3k_silu(acc[a]);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F; o += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = X[o * LDA + a];
+    col_dot(T1, 0, F, W1, F, o, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) T0[o * LDA + a] = so3k_silu(acc[a]);     // T0 was last read before the barrier above
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F; o += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(T0, 0, F, W2, F, o, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a)
+      if (a0 + a < N) y[(size_t)(a0 + a) * F + o] = acc[a];
+  }
+}
+
+// xbar = rbar + (hbar1 W0^T) silu'(x) ; rbar = (ybar W2^T) silu'(r) ; hbar1 = (rbar W1^T) silu'(h1)
+// h1 and r are recomputed from x.  W0 / W1 are the forward matrices, W0T / W1T / W2T their transposes.
+// ybar / xbar are not __restrict__: xbar may alias ybar (a block reads its rows of ybar before it writes them).
+__global__ void __launch_bounds__(NT)
+k_resmlp_bwd(So3kDims D, int N, const float* __restrict__ x, const float* __restrict__ W0,
+             const float* __restrict__ W1, const float* __restrict__ W0T, const float* __restrict__ W1T,
+             const float* __restrict__ W2T, const float* ybar, float* xbar) {
+  SO3K_DYN_SMEM(float, sm);
+  const int F = D.F;
+  float* X = sm;                  // [F][LDA] x
+  float* H1 = X + F * LDA;        // h1, then hbar1
+  float* T0 = H1 + F * LDA;       // silu(x), then r, then rbar
+  float* T1 = T0 + F * LDA;       // silu(h1), then ybar
+  const int a0 = blockIdx.x * TA;
+  load_tile_T(X, x, a0, N, F);
+  __syncthreads();
+  for (int t = threadIdx.x; t < F * TA; t += NT) {
+    const int k = (t / TA) * LDA + (t % TA);
+    T0[k] = so3k_silu(X[k]);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F; o += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(T0, 0, F, W0, F, o, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) {
+      H1[o * LDA + a] = acc[a];
+      T1[o * LDA + a] = so3k_silu(acc[a]);
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < F; o += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = X[o * LDA + a];
+    col_dot(T1, 0, F, W1, F, o, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) T0[o * LDA + a] = acc[a];                // r
+  }
+  __syncthreads();
+  load_tile_T(T1, ybar, a0, N, F);
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(T1, 0, F, W2T, F, c, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) {
+      float s, ds;
+      so3k_silu_d(T0[c * LDA + a], &s, &ds);
+      T0[c * LDA + a] = acc[a] * ds;                                      // rbar (column c is read by this thread only)
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(T0, 0, F, W1T, F, c, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) {
+      float s, ds;
+      so3k_silu_d(H1[c * LDA + a], &s, &ds);
+      H1[c * LDA + a] = acc[a] * ds;                                      // hbar1
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < F; c += NT) {
+    float acc[TA];
+#pragma unroll
+    for (int a = 0; a < TA; ++a) acc[a] = 0.f;
+    col_dot(H1, 0, F, W0T, F, c, acc);
+#pragma unroll
+    for (int a = 0; a < TA; ++a) {
+      float s, ds;
+      so3k_silu_d(X[c * LDA + a], &s, &ds);
+      if (a0 + a < N) xbar[(size_t)(a0 + a) * F + c] = T0[c * LDA + a] + acc[a] * ds;
+    }
+  }
+}
+
 }  // namespace
 
 void so3k_launch_embed(const So3kDims& D, int N, const int* z, const float* emb, float* x, float* chi,
@@ -344,6 +553,9 @@ void so3k_launch_transpose_params(const So3kDims& D, const ModelLayout& ml, cons
     transpose_sq(D.nl, D.dg, p + lp.gb.Wq, pT + lp.gb.Wq, st);
     transpose_sq(D.nl, D.dg, p + lp.gb.Wk, pT + lp.gb.Wk, st);
     transpose_sq(1, D.F + D.nl, p + lp.int_W, pT + lp.int_W, st);
+    for (int r = 0; r < 2; ++r)
+      if (ml.node_opts & (r ? SO3K_OPT_RES2 : SO3K_OPT_RES1))
+        for (int k = 0; k < 3; ++k) transpose_sq(1, D.F, p + lp.res[r][k], pT + lp.res[r][k], st);
   }
   transpose_sq(1, D.F, p + ml.out_W1, pT + ml.out_W1, st);
 }
@@ -357,20 +569,21 @@ void so3k_launch_node_proj_bwd(const So3kDims& D, int N, const float* gproj, con
 }
 
 void so3k_launch_interaction(const So3kDims& D, int N, const float* x1, const float* chi1, const float* p,
-                             const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st) {
+                             const LayerParams& lp, float* x2, float* chi2, float* bcoef, cudaStream_t st,
+                             const float* xbase) {
   size_t smem = sizeof(float) * (LDA * (D.F + D.nl) + TA * (D.M + D.nl));
   SO3K_SET_MAX_SMEM(k_interaction, smem);
   SO3K_LAUNCH(k_interaction, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x1, chi1, p + lp.int_W, p + lp.int_b,
-              x2, chi2, bcoef);
+              xbase, x2, chi2, bcoef);
 }
 
 void so3k_launch_interaction_bwd(const So3kDims& D, int N, const float* chi1, const float* bcoef, const float* p,
                                  const LayerParams& lp, const float* xbar_out, const float* chibar_out, float* xbar1,
-                                 float* chibar1, cudaStream_t st) {
+                                 float* chibar1, cudaStream_t st, bool skip) {
   size_t smem = sizeof(float) * (LDA * (D.F + D.nl) + TA * (2 * D.M + D.nl));
   SO3K_SET_MAX_SMEM(k_interaction_bwd, smem);
   SO3K_LAUNCH(k_interaction_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, chi1, bcoef, p + lp.int_W,
-              xbar_out, chibar_out, xbar1, chibar1);
+              xbar_out, chibar_out, skip ? 1 : 0, xbar1, chibar1);
 }
 
 void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z, const float* p, const float* pT,
@@ -383,4 +596,28 @@ void so3k_launch_readout(const So3kDims& D, int N, const float* x, const int* z,
 
 void so3k_launch_energy_sum(int B, int n, const float* e_atom, float offset, float* E, cudaStream_t st) {
   SO3K_LAUNCH(k_energy_sum, dim3(B), dim3(NT), 0, st, B, n, e_atom, offset, E);
+}
+
+void so3k_launch_layernorm(int N, int F, const float* x, const float* scale, const float* bias, float* y, cudaStream_t st) {
+  SO3K_LAUNCH(k_layernorm, dim3(so3k_cdiv(N, 4)), dim3(128), 0, st, N, F, x, scale, bias, y);
+}
+
+void so3k_launch_layernorm_bwd(int N, int F, const float* x, const float* scale, const float* gy, const float* add,
+                               float* out, cudaStream_t st) {
+  SO3K_LAUNCH(k_layernorm_bwd, dim3(so3k_cdiv(N, 4)), dim3(128), 0, st, N, F, x, scale, gy, add, out);
+}
+
+void so3k_launch_resmlp(const So3kDims& D, int N, const float* x, const float* p, const size_t* W, float* y,
+                        cudaStream_t st) {
+  size_t smem = sizeof(float) * 3 * LDA * D.F;
+  SO3K_SET_MAX_SMEM(k_resmlp, smem);
+  SO3K_LAUNCH(k_resmlp, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, p + W[0], p + W[1], p + W[2], y);
+}
+
+void so3k_launch_resmlp_bwd(const So3kDims& D, int N, const float* x, const float* p, const float* pT, const size_t* W,
+                            const float* ybar, float* xbar, cudaStream_t st) {
+  size_t smem = sizeof(float) * 4 * LDA * D.F;
+  SO3K_SET_MAX_SMEM(k_resmlp_bwd, smem);
+  SO3K_LAUNCH(k_resmlp_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, p + W[0], p + W[1], pT + W[0],
+              pT + W[1], pT + W[2], ybar, xbar);
 }

@@ -27,9 +27,15 @@ class So3kEngine:
         self.cfg = cfg
         self.device = torch.device(device)
         self.lib = _lib.load()
-        from .capi import FLAG_ZBL
+        from .capi import FLAG_ZBL, FLAG_LAYER_NORM, FLAG_RESIDUAL_MLP_1, FLAG_RESIDUAL_MLP_2, FLAG_FINAL_LAYER
         if cfg.zbl_repulsion:
             flags |= FLAG_ZBL
+        if cfg.layer_normalization:
+            flags |= FLAG_LAYER_NORM | (FLAG_FINAL_LAYER if cfg.final_layer else 0)
+        if cfg.residual_mlp_1:
+            flags |= FLAG_RESIDUAL_MLP_1
+        if cfg.residual_mlp_2:
+            flags |= FLAG_RESIDUAL_MLP_2
         self.h = self.lib.create(cfg.F, cfg.n_rbf, cfg.n_layer, cfg.n_heads, list(cfg.degrees), cfg.r_cut,
                                  cfg.num_embeddings, flags, cfg.zbl_repulsion_shift)
         self._ws: Optional[torch.Tensor] = None

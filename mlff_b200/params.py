@@ -10,6 +10,8 @@ the reference's modules (inferred from the module code, 
   params/layers_t/FeatureBlock_0/attention_fn/VmapAttentionAggregation_0/Dense_0/kernel      (H,d,d)
   params/layers_t/GeometricBlock_0/...            (same, nl heads, no aggregation Dense)
   params/layers_t/InteractionBlock_0/MLP_0/layers_0/{kernel, bias}
+  params/layers_t/LayerNorm_{0,1[,2]}/{scale, bias}                                        (layer_normalization)
+  params/layers_t/ResidualMLP_k/{Residual_0/layers_{0,1}/kernel, Dense_0/kernel}           (residual_mlp_1 / _2)
   params/observables_0/MLP_0/layers_{0,1}/{kernel, bias}
 """
 from __future__ import annotations
@@ -38,6 +40,12 @@ def param_shapes(cfg: So3kratesConfig) -> List[Tuple[str, Tuple[int, ...]]]:
             if blk == 'fb':
                 out += [(pre + 'v/kernel', (heads, d, d))]
         out += [(f'layers_{t}/int/layers_0/kernel', (F + nl, F + nl)), (f'layers_{t}/int/layers_0/bias', (F + nl,))]
+        if cfg.layer_normalization:      # flax nn.LayerNorm: scale, bias (so3krates_layer.py:103-106, 153-156, 170-174)
+            for k in range(3 if cfg.final_layer else 2):
+                out += [(f'layers_{t}/ln_{k + 1}/scale', (F,)), (f'layers_{t}/ln_{k + 1}/bias', (F,))]
+        for r, on in ((1, cfg.residual_mlp_1), (2, cfg.residual_mlp_2)):      # ResidualMLP, mlp.py:30-72 (bias-free)
+            if on:
+                out += [(f'layers_{t}/res_{r}/{k}/kernel', (F, F)) for k in ('layers_0', 'layers_1', 'out')]
     out += [('energy/layers_0/kernel', (F, F)), ('energy/layers_0/bias', (F,)),
             ('energy/layers_1/kernel', (F, 1)), ('energy/layers_1/bias', (1,)),
             ('energy/per_atom_scale', (cfg.num_embeddings,)), ('energy/per_atom_shift', (cfg.num_embeddings,))]
@@ -60,6 +68,8 @@ def init_params(cfg: So3kratesConfig, seed: int = 0) -> Dict[str, np.ndarray]:
     for name, shape in param_shapes(cfg):
         if name.endswith('/bias'):
             p[name] = np.zeros(shape, np.float32)
+        elif name.endswith('/scale'):
+            p[name] = np.ones(shape, np.float32)
         elif name == 'energy/per_atom_scale':
             p[name] = np.ones(shape, np.float32)
         elif name == 'energy/per_atom_shift':
@@ -89,8 +99,9 @@ def pack_blob(cfg: So3kratesConfig, params: Dict[str, np.ndarray]) -> np.ndarray
 
 
 # ---- flax tree <-> flat names ---------------------------------------------------------------------
-def _flax_path(name: str) -> Tuple[List[str], bool]:
-    """flat name -> (path inside variables['params'], has_leading_vmap_axis)."""
+def _flax_path(name: str, res_first: bool = True) -> Tuple[List[str], bool]:
+    """flat name -> (path inside variables['params'], has_leading_vmap_axis).  ``res_first``: the layer has a
+    ResidualMLP after the first skip connection (it is then ResidualMLP_0 and the second one ResidualMLP_1)."""
     parts = name.split('/')
     if parts[0] == 'embed':
         return ['feature_embeddings_0', 'Embed_0', 'embedding'], False
@@ -101,6 +112,13 @@ def _flax_path(name: str) -> Tuple[List[str], bool]:
             return [], False
         return ['observables_0', 'MLP_0', parts[1], parts[2]], False
     lt = parts[0]
+    if parts[1].startswith('ln_'):       # auto-named in call order inside So3kratesLayer.__call__
+        return [lt, f'LayerNorm_{int(parts[1][3:]) - 1}', parts[2]], False
+    if parts[1].startswith('res_'):      # ResidualMLP_k counts only the ResidualMLPs that exist in the layer
+        k = int(parts[1][4:]) - 1 if res_first else 0
+        if parts[2] == 'out':
+            return [lt, f'ResidualMLP_{k}', 'Dense_0', 'kernel'], False
+        return [lt, f'ResidualMLP_{k}', 'Residual_0', parts[2], 'kernel'], False
     if parts[1] == 'int':
         return [lt, 'InteractionBlock_0', 'MLP_0', parts[2], parts[3]], False
     blk = 'FeatureBlock_0' if parts[1] == 'fb' else 'GeometricBlock_0'
@@ -120,7 +138,7 @@ def from_flax_tree(cfg: So3kratesConfig, variables: Dict, per_atom_scale=None, p
     tree = variables['params'] if 'params' in variables else variables
     out: Dict[str, np.ndarray] = {}
     for name, shape in param_shapes(cfg):
-        path, vm = _flax_path(name)
+        path, vm = _flax_path(name, cfg.residual_mlp_1)
         if not path:
             continue
         node = tree
@@ -139,7 +157,7 @@ def from_flax_tree(cfg: So3kratesConfig, variables: Dict, per_atom_scale=None, p
 def to_flax_tree(cfg: So3kratesConfig, params: Dict[str, np.ndarray]) -> Dict:
     tree: Dict = {}
     for name, shape in param_shapes(cfg):
-        path, vm = _flax_path(name)
+        path, vm = _flax_path(name, cfg.residual_mlp_1)
         if not path:
             continue
         node = tree

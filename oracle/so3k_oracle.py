@@ -64,6 +64,10 @@ class OracleConfig:
     num_embeddings: int = 100
     zbl_repulsion: bool = False           # Energy(zbl_repulsion=...)   observable.py:39, CLI --zbl_repulsion
     zbl_repulsion_shift: float = 0.0      # observable.py:40
+    layer_normalization: bool = False     # so3krates_layer.py:42, 103-106, 153-156
+    final_layer: bool = False             # so3krates_layer.py:35, 170-174
+    residual_mlp_1: bool = False          # so3krates_layer.py:30, 149-150
+    residual_mlp_2: bool = False          # so3krates_layer.py:31, 166-167
 
     @property
     def nl(self) -> int:
@@ -113,6 +117,15 @@ def init_params(cfg: OracleConfig, seed: int = 0, bias_scale: float = 0.01,
                 dense(pre + '/q', dg, dg, bias=False, lead=(nl,))
                 dense(pre + '/k', dg, dg, bias=False, lead=(nl,))
         dense(f'layers_{t}/int/layers_0', F + nl, F + nl)
+        if cfg.layer_normalization:
+            # flax initialises scale = 1, bias = 0; noise makes the parity tests discriminate
+            for k in range(3 if cfg.final_layer else 2):
+                p[f'layers_{t}/ln_{k + 1}/scale'] = 1.0 + rng.normal(0.0, 0.1, size=(F,))
+                p[f'layers_{t}/ln_{k + 1}/bias'] = rng.normal(0.0, 0.1, size=(F,))
+        for r, on in ((1, cfg.residual_mlp_1), (2, cfg.residual_mlp_2)):
+            if on:
+                for k in ('layers_0', 'layers_1', 'out'):
+                    dense(f'layers_{t}/res_{r}/{k}', F, F, bias=False)
     dense('energy/layers_0', F, F)
     dense('energy/layers_1', F, 1)
     if scale_shift:
@@ -276,6 +289,22 @@ def mlp2(x, W0, b0, W1, b1):
     return silu(x @ W0 + b0) @ W1 + b1
 
 
+def layer_norm(x, scale, bias, eps: float = 1e-6):
+    """flax.linen.LayerNorm defaults (the reference calls nn.LayerNorm() bare, so3krates_layer.py:104, 154, 172):
+    statistics over the last axis with the 'fast variance' E[x^2] - E[x]^2 clipped at 0, epsilon 1e-6, learnable
+    scale and bias."""
+    mean = x.mean(-1, keepdim=True)
+    var = torch.clamp((x * x).mean(-1, keepdim=True) - mean * mean, min=0.0)
+    return (x - mean) * torch.rsqrt(var + eps) * scale + bias
+
+
+def residual_mlp(x, W0, W1, W2):
+    """ResidualMLP() with its defaults num_residuals=1, num_blocks_per_residual=2, silu, use_bias=False
+    (mlff/nn/mlp/mlp.py:30-72): one Residual block (x + Dense(silu(Dense(silu(x))))) followed by Dense(silu(.))."""
+    r = x + silu(silu(x) @ W0) @ W1                                          # mlp.py:36-43
+    return silu(r) @ W2                                                       # mlp.py:70-72
+
+
 def segment_sum(data, ids, n):
     """jax.ops.segment_sum; callers guarantee rows with invalid ids carry exact zeros."""
     ids = torch.where(ids < 0, torch.zeros_like(ids), ids)
@@ -332,9 +361,21 @@ def _coefficients(xh, wh, Wq, Wk, gi, gj):
 
 
 def so3krates_layer(cfg: OracleConfig, params, t: int, x, chi, geo, idx_i, idx_j, pair_mask,
-                    record: Optional[dict] = None):
-    """So3kratesLayer.__call__, so3krates_layer.py:57-178 (default branches only)."""
+                    record: Optional[dict] = None, point_mask=None):
+    """So3kratesLayer.__call__, so3krates_layer.py:57-178 (default branches + layer_normalization / final_layer /
+    residual_mlp_1 / residual_mlp_2; the non-local branches raise NotImplementedError in the reference itself)."""
     dtype = x.dtype
+    x_skip = x                                                                # the skip connections keep the raw x (:146)
+
+    def ln(k, v):                                                             # safe_mask(point_mask != 0, LayerNorm(), v)
+        y = layer_norm(v, _t(params, f'layers_{t}/ln_{k}/scale', dtype), _t(params, f'layers_{t}/ln_{k}/bias', dtype))
+        return y if point_mask is None else torch.where(point_mask[:, None] != 0, y, torch.zeros_like(y))
+
+    def res(r, v):
+        return residual_mlp(v, *(_t(params, f'layers_{t}/res_{r}/{k}/kernel', dtype) for k in ('layers_0', 'layers_1', 'out')))
+
+    if cfg.layer_normalization:
+        x = ln(1, x)                                                          # x_pre_1, :103-106
     n = x.shape[0]
     pm = pair_mask
     gi = torch.where(idx_i < 0, torch.zeros_like(idx_i), idx_i)
@@ -368,16 +409,25 @@ def so3krates_layer(cfg: OracleConfig, params, t: int, x, chi, geo, idx_i, idx_j
     a_gb = a_r + a_s                                                          # :553
     chi_local = segment_sum(repeat_degrees(a_gb, cfg.degrees) * geo['sph_ij'], idx_i, n)  # :563-564
 
-    x1 = x + x_local                                                          # :146
+    x1 = x_skip + x_local                                                     # :146
     chi1 = chi + chi_local                                                    # :147
+    if cfg.residual_mlp_1:
+        x1 = res(1, x1)                                                       # :149-150
+    x_skip = x1
+    if cfg.layer_normalization:
+        x1 = ln(2, x1)                                                        # x_pre_2, :153-156
 
     # InteractionBlock (:355-379): single Dense, no activation (mlp.py:24-26)
     d_chi = l0_contraction(chi1, cfg.degrees)
     y = torch.cat([x1, d_chi], -1)
     ab = y @ P('int/layers_0/kernel') + P('int/layers_0/bias')
     a1, b1 = ab[:, :cfg.F], ab[:, cfg.F:]
-    x2 = x1 + a1                                                              # :163
+    x2 = x_skip + a1                                                          # :163
     chi2 = chi1 + repeat_degrees(b1, cfg.degrees) * chi1                      # :164, :379
+    if cfg.residual_mlp_2:
+        x2 = res(2, x2)                                                       # :166-167
+    if cfg.final_layer and cfg.layer_normalization:
+        x2 = ln(3, x2)                                                        # :170-174
     if record is not None:
         record[f'layer{t}'] = {'g': g, 'w_fb': w_fb, 'w_gb': w_gb, 'alpha_fb': alpha, 'alpha_gb': a_gb,
                                'x_local': x_local, 'chi_local': chi_local, 'x': x2, 'chi': chi2}
@@ -401,7 +451,7 @@ def forward(cfg: OracleConfig, params, z, idx_i, idx_j, dtype=torch.float64, R=N
     x = safe_scale(_t(params, 'embed/embedding', dtype)[z], point_mask[:, None])   # embed.py:227-229
     x = x / math.sqrt(1.0)                                                    # stacknet.py:73 (one embed)
     for t in range(cfg.n_layers):
-        x, chi = so3krates_layer(cfg, params, t, x, chi, geo, idx_i, idx_j, pair_mask, record)
+        x, chi = so3krates_layer(cfg, params, t, x, chi, geo, idx_i, idx_j, pair_mask, record, point_mask)
     e = mlp2(x, _t(params, 'energy/layers_0/kernel', dtype), _t(params, 'energy/layers_0/bias', dtype),
              _t(params, 'energy/layers_1/kernel', dtype), _t(params, 'energy/layers_1/bias', dtype)).squeeze(-1)
     e = _t(params, 'energy/per_atom_scale', dtype)[z] * e + _t(params, 'energy/per_atom_shift', dtype)[z]  # :78

@@ -28,3 +28,16 @@ def as_sets(ii, jj, S=None):
         return sorted(zip(ii[keep].tolist(), jj[keep].tolist()))
     S = np.asarray(S)
     return sorted(zip(ii[keep].tolist(), jj[keep].tolist(), S[keep, 0].tolist(), S[keep, 1].tolist(), S[keep, 2].tolist()))
+
+
+def engine_flags(cfg) -> int:
+    """SO3K_FLAG_* bits of the optional model branches selected by an oracle / engine config."""
+    from mlff_b200.capi import (FLAG_ZBL, FLAG_LAYER_NORM, FLAG_RESIDUAL_MLP_1, FLAG_RESIDUAL_MLP_2, FLAG_FINAL_LAYER)
+    f = FLAG_ZBL if getattr(cfg, 'zbl_repulsion', False) else 0
+    if getattr(cfg, 'layer_normalization', False):
+        f |= FLAG_LAYER_NORM | (FLAG_FINAL_LAYER if getattr(cfg, 'final_layer', False) else 0)
+    if getattr(cfg, 'residual_mlp_1', False):
+        f |= FLAG_RESIDUAL_MLP_1
+    if getattr(cfg, 'residual_mlp_2', False):
+        f |= FLAG_RESIDUAL_MLP_2
+    return f

@@ -72,8 +72,26 @@ def test_config_json_roundtrip_and_flax_tree():
     assert tree['params']['layers_0']['FeatureBlock_0']['filter_fn']['VmapMLP_0']['layers_0']['kernel'].shape == (1, 32, 36)
     back = P.from_flax_tree(cfg, tree)
     assert all(np.array_equal(back[k], p[k]) for k in p)
+    # optional branches: round trip, flax names (modules are auto-numbered in call order inside So3kratesLayer)
+    cfo = So3kratesConfig(F=36, n_layer=2, degrees=(1, 2), n_heads=4, layer_normalization=True, final_layer=True,
+                          residual_mlp_2=True)
+    cf2 = So3kratesConfig.from_hyperparameters(cfo.to_hyperparameters())
+    assert (cf2.layer_normalization, cf2.final_layer, cf2.residual_mlp_1, cf2.residual_mlp_2) == (True, True, False, True)
+    po = P.init_params(cfo, 0)
+    to = P.to_flax_tree(cfo, po)['params']['layers_1']
+    assert set(to) >= {'LayerNorm_0', 'LayerNorm_1', 'LayerNorm_2', 'ResidualMLP_0'} and 'ResidualMLP_1' not in to
+    assert to['ResidualMLP_0']['Residual_0']['layers_1']['kernel'].shape == (36, 36)
+    assert to['ResidualMLP_0']['Dense_0']['kernel'].shape == (36, 36) and to['LayerNorm_2']['scale'].shape == (36,)
+    back = P.from_flax_tree(cfo, {'params': P.to_flax_tree(cfo, po)['params']})
+    assert all(np.array_equal(back[k], po[k]) for k in po)
+    # what the engine does not implement is refused: stacks whose layers differ, the non-local branches
     h = cfg.to_hyperparameters()
     h['stack_net']['layers'][0]['so3krates_layer']['layer_normalization'] = True
+    with pytest.raises(NotImplementedError):
+        So3kratesConfig.from_hyperparameters(h)
+    h = cfg.to_hyperparameters()
+    for l in h['stack_net']['layers']:
+        l['so3krates_layer']['non_local_feature'] = True
     with pytest.raises(NotImplementedError):
         So3kratesConfig.from_hyperparameters(h)
 

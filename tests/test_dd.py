@@ -10,6 +10,7 @@ import torch
 import so3k_oracle as o
 from conftest import golden
 from emu_engine import build_emu
+from common import engine_flags
 from mlff_b200.capi import So3kLib
 from mlff_b200 import dist as dd
 from mlff_b200 import params as P
@@ -24,8 +25,9 @@ def _problem(solid):
 
 
 def _make_rank(lib, cfg, p, device):
-    pc = So3kratesConfig(F=cfg.F, n_layer=cfg.n_layers, degrees=tuple(cfg.degrees), n_heads=cfg.n_heads)
-    h = lib.create(pc.F, pc.n_rbf, pc.n_layer, pc.n_heads, list(pc.degrees), pc.r_cut)
+    opts = {k: getattr(cfg, k) for k in ('layer_normalization', 'final_layer', 'residual_mlp_1', 'residual_mlp_2')}
+    pc = So3kratesConfig(F=cfg.F, n_layer=cfg.n_layers, degrees=tuple(cfg.degrees), n_heads=cfg.n_heads, **opts)
+    h = lib.create(pc.F, pc.n_rbf, pc.n_layer, pc.n_heads, list(pc.degrees), pc.r_cut, flags=engine_flags(cfg))
     blob = torch.from_numpy(P.pack_blob(pc, {k: np.asarray(v, np.float32) for k, v in p.items()})).to(device)
     lib.load_params(h, blob.data_ptr(), blob.numel())
     r = dd.DDRank(lib, h, pc.n_layer, device)
@@ -80,6 +82,35 @@ def test_domain_decomposed_energy_forces_match_oracle(solid, world):
         F[rk.plan.local_atoms[:rk.plan.n_own].numpy()] = rk.forces[:rk.plan.n_own].numpy()
     assert abs(E - float(g['E'])) <= 1e-5 * abs(float(g['E']))
     assert np.abs(F - g['F']).max() < 1e-4
+
+
+def test_domain_decomposition_with_optional_layer_branches(solid):
+    """LayerNorm / ResidualMLP are node-local, so the ghost exchanges of the default model carry them unchanged."""
+    g = golden('oracle_solid_pbc.npz')
+    cfg = o.OracleConfig(F=36, n_layers=2, layer_normalization=True, final_layer=True, residual_mlp_1=True,
+                         residual_mlp_2=True)
+    p = o.init_params(cfg, 3, embed_scale=4.0)
+    lib = So3kLib(build_emu())
+    dev = torch.device('cpu')
+    pos = torch.as_tensor(solid['R'])
+    z = torch.as_tensor(solid['z'])
+    ii, jj, S = (torch.as_tensor(g[k]) for k in ('idx_i', 'idx_j', 'shifts'))
+    Eo, Fo, _ = o.energy_forces(cfg, p, solid['R'], solid['z'], g['idx_i'], g['idx_j'], cell=solid['unit_cell'],
+                             cell_offset=g['shifts'])
+    owner = dd.assign_owners_slab(pos, solid['unit_cell'], 2, axis=2)
+    ranks = []
+    for r in range(2):
+        rk = _make_rank(lib, cfg, p, dev)
+        rk.begin(dd.build_plan(ii, jj, S, owner, r, 2), pos, z, solid['unit_cell'])
+        ranks.append(rk)
+    dd.run_energy_forces(ranks, dd.exchange_inprocess)
+    E = sum(float(rk.e_atom[:rk.plan.n_own].double().sum()) for rk in ranks)
+    F = np.zeros((110, 3), np.float32)
+    for rk in ranks:
+        assert int(rk.status[0]) == 0
+        F[rk.plan.local_atoms[:rk.plan.n_own].numpy()] = rk.forces[:rk.plan.n_own].numpy()
+    assert abs(E - float(Eo)) <= 1e-5 * max(abs(float(Eo)), 1.0)
+    assert np.abs(F - Fo.numpy()).max() < 1e-4
 
 
 def _gloo_worker(rank, world, port, q):

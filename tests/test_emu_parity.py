@@ -9,16 +9,15 @@ import so3k_oracle as o
 from conftest import golden
 from emu_engine import EmuEngine, ptr, build_emu
 from mlff_b200.capi import So3kLib, NL_ASE, NL_DENSE, STATUS_ASYMMETRIC, STATUS_OVERFLOW
-from common import as_sets
+from common import as_sets, engine_flags
 
 E_RTOL = 1e-5      # north_star: energies within 1e-5 relative
 F_ATOL = 1e-4      # north_star: forces within 1e-4 eV/A max-abs (fp32)
 
 
 def make(cfg, p):
-    from mlff_b200.capi import FLAG_ZBL
     eng = EmuEngine(cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads, cfg.degrees, cfg.r_cut,
-                    flags=FLAG_ZBL if cfg.zbl_repulsion else 0, zbl_shift=cfg.zbl_repulsion_shift)
+                    flags=engine_flags(cfg), zbl_shift=cfg.zbl_repulsion_shift)
     eng.load(p)
     return eng
 
@@ -253,3 +252,34 @@ def test_stress_of_a_molecular_batch(ethanol):
     for b in range(B):
         _, _, So = o.energy_forces_stress(cfg, p, Rb[b], zb[b], nl['idx_i'][b], nl['idx_j'][b])
         assert np.abs(stb[b] - So.numpy()).max() < 1e-4 * max(np.abs(So.numpy()).max(), 1.0)
+
+
+@pytest.mark.parametrize('opts', [dict(layer_normalization=True), dict(layer_normalization=True, final_layer=True),
+                                  dict(residual_mlp_1=True), dict(residual_mlp_2=True),
+                                  dict(layer_normalization=True, final_layer=True, residual_mlp_1=True, residual_mlp_2=True)],
+                         ids=['ln', 'ln+post', 'res1', 'res2', 'all'])
+def test_optional_layer_branches(ethanol, opts):
+    # So3kratesLayer(layer_normalization / final_layer / residual_mlp_1 / residual_mlp_2), so3krates_layer.py:103-174
+    cfg = o.OracleConfig(F=36, n_layers=2, **opts)
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    eng = make(cfg, p)
+    B = 2
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1)).copy()
+    nl = o.get_indices(R, z, 5.0)
+    # one padding atom and padding edge slots: the masked LayerNorm rows must stay unobservable
+    R = np.concatenate([R, np.zeros((B, 1, 3))], 1)
+    z = np.concatenate([z, np.zeros((B, 1), z.dtype)], 1)
+    ii = np.concatenate([nl['idx_i'], -np.ones((B, 3), nl['idx_i'].dtype)], 1)
+    jj = np.concatenate([nl['idx_j'], -np.ones((B, 3), nl['idx_j'].dtype)], 1)
+    E, Fo, ea, st = eng.energy_forces(R, z, ii, jj)
+    assert st == 0
+    Eo, Fr = o.energy_forces_batch(cfg, p, R, z, ii, jj)
+    base = o.OracleConfig(F=36, n_layers=2)
+    E0, F0 = o.energy_forces_batch(base, p, R, z, ii, jj)
+    assert np.abs(Fr.numpy() - F0.numpy()).max() > 1e-2         # the branch changes the model
+    scale = np.maximum(np.abs(Eo.numpy().reshape(-1)), np.abs(ea).sum(-1))
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= E_RTOL * scale).all()
+    assert np.abs(Fo - Fr.numpy()).max() < F_ATOL
+    assert np.abs(Fo - Fr.numpy()).max() < 5e-5 * np.abs(Fr.numpy()).max()
+    assert (Fo[:, -1] == 0).all() and (ea[:, -1] == 0).all()

@@ -1,0 +1,82 @@
+"""Optional So3kratesLayer branches on the device: layer_normalization / final_layer / residual_mlp_1 / residual_mlp_2
+(mlff/nn/layer/so3krates_layer.py:103-174, mlff/nn/mlp/mlp.py:30-72) against the CPU oracle, in the fp32 and the
+tensor-core modes.  The same comparison runs on the CPU-emulated kernels in tests/test_emu_parity.py.
+(This file sorts last so that `pytest -x` reaches it after the default model's suite.)"""
+import numpy as np
+import pytest
+import torch
+
+import so3k_oracle as o
+from common import jittered_lattice, water_like_numbers
+
+pytestmark = pytest.mark.gpu
+
+E_RTOL = 1e-5
+F_ATOL = 1e-4
+OPTS = {'ln': dict(layer_normalization=True),
+        'ln+post': dict(layer_normalization=True, final_layer=True),
+        'res1': dict(residual_mlp_1=True),
+        'res2': dict(residual_mlp_2=True),
+        'all': dict(layer_normalization=True, final_layer=True, residual_mlp_1=True, residual_mlp_2=True)}
+
+
+def make(ocfg, p, flags):
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.engine import So3kEngine
+    cfg = So3kratesConfig(F=ocfg.F, n_layer=ocfg.n_layers, degrees=tuple(ocfg.degrees), n_heads=ocfg.n_heads,
+                          n_rbf=ocfg.n_rbf, r_cut=ocfg.r_cut, layer_normalization=ocfg.layer_normalization,
+                          final_layer=ocfg.final_layer, residual_mlp_1=ocfg.residual_mlp_1,
+                          residual_mlp_2=ocfg.residual_mlp_2)
+    eng = So3kEngine(cfg, 'cuda:0', flags)
+    eng.load_params({k: np.asarray(v, np.float32) for k, v in p.items()})
+    return eng
+
+
+def dev(a, dt):
+    return torch.as_tensor(np.asarray(a)).to('cuda:0', dt)
+
+
+@pytest.mark.parametrize('flags', [0, 1, 3], ids=['fp32', 'tensor', 'tensor+keep'])
+@pytest.mark.parametrize('name', list(OPTS))
+def test_optional_layer_branches_ethanol(ethanol, name, flags):
+    cfg = o.OracleConfig(F=132, n_layers=3, **OPTS[name])
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    eng = make(cfg, p, flags)
+    B = 2
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1)).copy()
+    nl = o.get_indices(R, z, 5.0)
+    R = np.concatenate([R, np.zeros((B, 1, 3))], 1)                      # one padding atom, three padding edge slots
+    z = np.concatenate([z, np.zeros((B, 1), z.dtype)], 1)
+    ii = np.concatenate([nl['idx_i'], -np.ones((B, 3), nl['idx_i'].dtype)], 1)
+    jj = np.concatenate([nl['idx_j'], -np.ones((B, 3), nl['idx_j'].dtype)], 1)
+    E, F, ea = eng.energy_forces(dev(R, torch.float32), dev(z, torch.int32), dev(ii, torch.int32), dev(jj, torch.int32),
+                                 want_e_atom=True)
+    assert eng.check_status() == 0
+    E, F, ea = E.cpu().numpy().reshape(-1), F.cpu().numpy(), ea.cpu().numpy()
+    Eo, Fo = o.energy_forces_batch(cfg, p, R, z, ii, jj)
+    scale = np.maximum(np.abs(Eo.numpy().reshape(-1)), np.abs(ea).sum(-1))
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= E_RTOL * scale).all()
+    assert np.abs(F - Fo.numpy()).max() < F_ATOL
+    assert (F[:, -1] == 0).all() and (ea[:, -1] == 0).all()
+
+
+def test_optional_layer_branches_periodic_box():
+    """A 600-atom periodic box (several blocks of every node kernel, ragged last block) with all branches on."""
+    from mlff_b200.engine import So3kEngine  # noqa: F401  (fails loudly without the CUDA library)
+    n, box = 600, 18.2
+    pos = jittered_lattice(n, box, 5)
+    z = water_like_numbers(n, 5)
+    cell = np.eye(3) * box
+    ii, jj, S = o.periodic_neighbor_list_kdtree(pos, box, 5.0)
+    cfg = o.OracleConfig(F=132, n_layers=2, **OPTS['all'])
+    p = o.init_params(cfg, 2, embed_scale=4.0)
+    Eo, Fo, _ = o.energy_forces(cfg, p, pos, z, ii, jj, cell=cell, cell_offset=S)
+    for flags in (0, 3):
+        eng = make(cfg, p, flags)
+        E, F, ea = eng.energy_forces(dev(pos[None], torch.float32), dev(z[None], torch.int32), dev(ii[None], torch.int32),
+                                     dev(jj[None], torch.int32), dev(cell[None], torch.float32), dev(S[None], torch.int32),
+                                     want_e_atom=True)
+        assert eng.check_status() == 0
+        assert abs(float(E.cpu()) - float(Eo)) <= E_RTOL * max(abs(float(Eo)), float(ea.abs().sum()))
+        assert np.abs(F.cpu().numpy()[0] - Fo.numpy()).max() < F_ATOL
