@@ -46,9 +46,24 @@ def test_handle_and_param_layout(cuda_lib_path):
         o_, c_ = lib.param_lookup(h, name)
         assert (o_, c_) == (off, int(np.prod(shape))), name
         off += c_
-    assert lib.workspace_bytes(h, 288, 2304) > 0
+    ws0 = lib.workspace_bytes(h, 288, 2304)
+    assert ws0 > 0
     with pytest.raises(KeyError):
         lib.param_lookup(h, 'nope')
+    lib.destroy(h)
+    # optional branches append their parameters per layer, in the same order on both sides, and grow the workspace
+    from common import engine_flags
+    cfo = So3kratesConfig(n_layer=3, layer_normalization=True, final_layer=True, residual_mlp_1=True, residual_mlp_2=True,
+                          zbl_repulsion=True)
+    h = lib.create(cfo.F, cfo.n_rbf, cfo.n_layer, cfo.n_heads, list(cfo.degrees), cfo.r_cut, flags=engine_flags(cfo))
+    assert lib.param_count(h) == 319413 + 3 * (6 * 132 + 6 * 132 * 132) + 10
+    off = 0
+    for name, shape in P.param_shapes(cfo):
+        o_, c_ = lib.param_lookup(h, name)
+        assert (o_, c_) == (off, int(np.prod(shape))), name
+        off += c_
+    assert off == lib.param_count(h)
+    assert lib.workspace_bytes(h, 288, 2304) >= ws0 + (1 + 4 * 3) * 288 * 132 * 4
     lib.destroy(h)
 
 
