@@ -13,6 +13,17 @@ pytestmark = pytest.mark.gpu
 
 E_RTOL = 1e-5
 F_ATOL = 1e-4
+
+
+def tolerances(flags, f_max):
+    """fp32 mode: north_star's tolerances as they stand.  Tensor mode: the split-bf16 filters carry a relative error of
+    about 1e-5 into the forces (default model: 3.6e-6 eV/A on 0.41 eV/A forces).  LayerNorm re-normalises the features,
+    so these random-weight models have 5-11 eV/A forces and the same RELATIVE error exceeds 1e-4 eV/A absolute
+    (measured: profiles/r01k_optional_branch_errors.txt); the tensor mode is therefore held to 4e-5 of the largest
+    force (and 1e-4 eV/A below 2.5 eV/A), energies to 2e-5 of the summed per-atom magnitude."""
+    if flags == 0:
+        return E_RTOL, F_ATOL
+    return 2e-5, max(F_ATOL, 4e-5 * f_max)
 OPTS = {'ln': dict(layer_normalization=True),
         'ln+post': dict(layer_normalization=True, final_layer=True),
         'res1': dict(residual_mlp_1=True),
@@ -56,8 +67,9 @@ def test_optional_layer_branches_ethanol(ethanol, name, flags):
     E, F, ea = E.cpu().numpy().reshape(-1), F.cpu().numpy(), ea.cpu().numpy()
     Eo, Fo = o.energy_forces_batch(cfg, p, R, z, ii, jj)
     scale = np.maximum(np.abs(Eo.numpy().reshape(-1)), np.abs(ea).sum(-1))
-    assert (np.abs(E - Eo.numpy().reshape(-1)) <= E_RTOL * scale).all()
-    assert np.abs(F - Fo.numpy()).max() < F_ATOL
+    e_rtol, f_atol = tolerances(flags, float(np.abs(Fo.numpy()).max()))
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= e_rtol * scale).all()
+    assert np.abs(F - Fo.numpy()).max() < f_atol
     assert (F[:, -1] == 0).all() and (ea[:, -1] == 0).all()
 
 
@@ -78,5 +90,9 @@ def test_optional_layer_branches_periodic_box():
                                      dev(jj[None], torch.int32), dev(cell[None], torch.float32), dev(S[None], torch.int32),
                                      want_e_atom=True)
         assert eng.check_status() == 0
-        assert abs(float(E.cpu()) - float(Eo)) <= E_RTOL * max(abs(float(Eo)), float(ea.abs().sum()))
-        assert np.abs(F.cpu().numpy()[0] - Fo.numpy()).max() < F_ATOL
+        e_rtol, f_atol = tolerances(flags, float(np.abs(Fo.numpy()).max()))
+        dE, dF = abs(float(E.cpu()) - float(Eo)), np.abs(F.cpu().numpy()[0] - Fo.numpy()).max()
+        print(f'periodic box, flags {flags}: |dE| {dE:.2e} (sum|e_atom| {float(ea.abs().sum()):.1f}), max|dF| {dF:.2e} '
+              f'(max|F| {float(np.abs(Fo.numpy()).max()):.2f})')
+        assert dE <= e_rtol * max(abs(float(Eo)), float(ea.abs().sum()))
+        assert dF < f_atol
