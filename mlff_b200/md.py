@@ -13,6 +13,8 @@ update rules, on torch tensors instead of jax arrays:
                       evaluation of a step is the first of the next one, so it is cached here -- same trajectory)
 * `NoseHooverX`, `LangevinX`   mlff/mdx/integrator.py:17-83, 86-159
 * `simulate`          mlff/mdx/simulate.py:60-82 (kinetic / potential energy per step, one host read-back at the end)
+* `GradientDescent`, `LBFGS`   mlff/mdx/optimizer.py:16-52, 55-149 (structure relaxation; same `create` / `step` /
+                      `minimize(atoms, max_steps, tol)` contract and error behaviour)
 
 Everything per step is O(N) tensor arithmetic on the device plus the engine calls; the only host synchronisation is the
 scalar "has any atom moved more than skin / 2" decision of the neighbour list (and the list size after a rebuild).
@@ -279,6 +281,117 @@ def simulate(integrator, atoms: AtomsX, steps: int):
     n = atoms.get_number_of_atoms()
     return atoms, {'kinetic_energy': ek_t, 'potential_energy': ep_t,
                    'temperature': 2.0 * ek_t / max(3 * n - 6, 1) / KB_EV}
+
+
+class GradientDescent:
+    """mlff/mdx/optimizer.py:16-52: x <- x - learning_rate * dE/dx until max_i |dE/dx_i| < tol."""
+
+    def __init__(self, calculator: CalculatorX, learning_rate: float = 1e-2):
+        self.calculator, self.learning_rate = calculator, float(learning_rate)
+
+    @classmethod
+    def create(cls, calculator, learning_rate: float = 1e-2):
+        return cls(calculator, learning_rate)
+
+    def step(self, atoms: AtomsX):
+        grads = -self.calculator(atoms)['forces']
+        return atoms.update_positions(atoms.get_positions() - self.learning_rate * grads), grads
+
+    def minimize(self, atoms: AtomsX, max_steps: int = 1000, tol: float = 1e-2):
+        for _ in range(max_steps):
+            atoms, grads = self.step(atoms)
+            if float(torch.linalg.norm(grads, dim=-1).max()) < tol:        # the reference's per-step read-back
+                return atoms, grads
+        raise RuntimeError('Optimization did not converge!')
+
+
+class LBFGS:
+    """Limited-memory BFGS relaxation with the settings the reference hands to jaxopt (mlff/mdx/optimizer.py:71-76,
+    152-157): backtracking line search on the strong Wolfe conditions, initial inverse-Hessian scale gamma =
+    s.y / y.y (`use_gamma`), step size capped at `max_stepsize` = 0.2, history 10, one iteration per `step`.
+    jaxopt is not available in this image, so the sequence of iterates is this class's own (standard two-loop
+    recursion); the contract is the reference's: `minimize` returns (relaxed atoms, forces) once the largest atomic
+    force norm is below `tol`, raises RuntimeError otherwise.  Positions stay on the device; each iteration reads back
+    a handful of scalars (as the reference's progress bar does)."""
+
+    def __init__(self, calculator: CalculatorX, history_size: int = 10, max_stepsize: float = 0.2,
+                 decrease_factor: float = 0.8, c1: float = 1e-4, c2: float = 0.9, max_linesearch: int = 15):
+        self.calculator = calculator
+        self.history_size, self.max_stepsize, self.decrease_factor = history_size, max_stepsize, decrease_factor
+        self.c1, self.c2, self.max_linesearch = c1, c2, max_linesearch
+        self.s_hist, self.y_hist = [], []
+        self.n_iter = 0
+
+    @classmethod
+    def create(cls, atoms, calculator, save_dir: Optional[str] = None):
+        opt = cls(calculator)
+        opt.save_dir = save_dir
+        return opt
+
+    def _evaluate(self, atoms: AtomsX, x: torch.Tensor):
+        a = atoms.update_positions(x)
+        prop = self.calculator(a)
+        return a, float(prop['energy']), -prop['forces']
+
+    def _direction(self, g: torch.Tensor) -> torch.Tensor:
+        q = g.clone()
+        alphas = []
+        for s_k, y_k in zip(reversed(self.s_hist), reversed(self.y_hist)):
+            a_k = (s_k * q).sum() / (y_k * s_k).sum()
+            q = q - a_k * y_k
+            alphas.append(a_k)
+        if self.s_hist:
+            q = q * ((self.s_hist[-1] * self.y_hist[-1]).sum() / (self.y_hist[-1] * self.y_hist[-1]).sum())
+        for (s_k, y_k), a_k in zip(zip(self.s_hist, self.y_hist), reversed(alphas)):
+            b_k = (y_k * q).sum() / (y_k * s_k).sum()
+            q = q + (a_k - b_k) * s_k
+        return -q
+
+    def step(self, atoms: AtomsX):
+        """One L-BFGS iteration from `atoms`; returns (atoms at the new iterate, gradient there)."""
+        x = atoms.get_positions()
+        prop = self.calculator(atoms)          # cached when `atoms` comes out of the previous step
+        e0, g0 = float(prop['energy']), -prop['forces']
+        d = self._direction(g0)
+        slope = float((d * g0).sum())
+        if slope >= 0.0:                       # not a descent direction (stale curvature pairs): restart from steepest descent
+            self.s_hist, self.y_hist = [], []
+            d, slope = -g0, -float((g0 * g0).sum())
+        # unit step of the quasi-Newton direction, capped so that no atom moves more than max_stepsize
+        t = min(1.0, self.max_stepsize / max(float(torch.linalg.norm(d, dim=-1).max()), 1e-30))
+        best = None
+        for _ in range(self.max_linesearch):
+            a1, e1, g1 = self._evaluate(atoms, x + t * d)
+            armijo = e1 <= e0 + self.c1 * t * slope
+            if armijo and best is None:
+                best = (a1, g1, t)             # fall back to the first sufficient-decrease point
+            if armijo and abs(float((d * g1).sum())) <= self.c2 * abs(slope):
+                best = (a1, g1, t)
+                break
+            t *= self.decrease_factor
+        if best is None:                       # no decrease found along d: tiny steepest-descent step, history dropped
+            self.s_hist, self.y_hist = [], []
+            a1, e1, g1 = self._evaluate(atoms, x - 1e-3 * self.max_stepsize * g0 / max(float(g0.abs().max()), 1e-30))
+            best = (a1, g1, 0.0)
+        a1, g1, _ = best
+        s_k, y_k = a1.get_positions() - x, g1 - g0
+        if float((s_k * y_k).sum()) > 1e-12:   # curvature condition keeps the inverse Hessian positive definite
+            self.s_hist.append(s_k)
+            self.y_hist.append(y_k)
+            if len(self.s_hist) > self.history_size:
+                self.s_hist.pop(0)
+                self.y_hist.pop(0)
+        self.n_iter += 1
+        return a1, g1
+
+    def minimize(self, atoms: AtomsX, max_steps: int, tol: float = 1e-3):
+        max_force_norm = None
+        for _ in range(max_steps):
+            atoms, grads = self.step(atoms)
+            max_force_norm = float(torch.linalg.norm(grads, dim=-1).max())
+            if max_force_norm < tol:
+                return atoms, -grads
+        raise RuntimeError(f'BFGS optimization did not converge! {max_force_norm} (max. force norm ) > {tol} (tolerance).')
 
 
 def maxwell_boltzmann_momenta(masses: torch.Tensor, temperature_K: float, seed: int = 0) -> torch.Tensor:

@@ -232,3 +232,78 @@ def test_langevin_thermalises_free_particles():
     temp = float(2.0 * atoms.get_kinetic_energy() / (3 * n)) / md.KB_EV
     assert abs(temp - 300.0) < 15.0                                      # 6000 degrees of freedom: ~1.8 % standard deviation
     assert float(atoms.momenta.sum(0).abs().max()) < 1e-9 * n
+
+
+class SpringEngine:
+    """Engine stand-in with a known minimum: E = sum over directed edges of k/4 (d - d0)^2 (each bond counted twice)."""
+
+    def __init__(self, d0=1.2, k=5.0):
+        self.d0, self.k = d0, k
+        self.neighbor_list = OracleEngine(None, None).neighbor_list
+
+    def energy_forces(self, R, z, idx_i, idx_j, cell=None, cell_offset=None):
+        R0 = R[0].double().clone().requires_grad_(True)
+        keep = idx_i[0] >= 0
+        i, j = idx_i[0][keep].long(), idx_j[0][keep].long()
+        d = (R0[j] - R0[i]).norm(dim=-1)
+        E = (0.25 * self.k * (d - self.d0) ** 2).sum()
+        (g,) = torch.autograd.grad(E, R0)
+        return E.detach().reshape(1, 1), (-g).detach()[None], None
+
+
+def _tetrahedron():
+    R0 = np.array([[0.0, 0.0, 0.0], [1.5, 0.1, 0.0], [0.6, 1.3, 0.2], [0.5, 0.4, 1.6]])
+    n = len(R0)
+    return md.AtomsX(positions=torch.as_tensor(R0), momenta=torch.zeros(n, 3, dtype=torch.float64),
+                     masses=torch.ones(n, dtype=torch.float64), numbers=torch.ones(n, dtype=torch.int32))
+
+
+def test_gradient_descent_relaxer_follows_the_reference_rule():
+    # mlff/mdx/optimizer.py:29-52: x <- x - lr * dE/dx ; stops when the largest atomic gradient norm < tol
+    eng = SpringEngine()
+    atoms = _tetrahedron().init_spatial_partitioning(eng, cutoff=5.0, skin=0.5)
+    calc = md.CalculatorX(eng)
+    gd = md.GradientDescent.create(calc, learning_rate=5e-2)
+    F0 = calc(atoms)['forces'].clone()
+    a1, grads = gd.step(atoms)
+    np.testing.assert_allclose(grads.numpy(), -F0.numpy(), atol=0)
+    np.testing.assert_allclose(a1.get_positions().numpy(), (atoms.get_positions() + 5e-2 * F0).numpy(), atol=1e-15)
+    relaxed, grads = gd.minimize(atoms, max_steps=2000, tol=1e-4)
+    assert float(torch.linalg.norm(grads, dim=-1).max()) < 1e-4
+    d = torch.cdist(relaxed.get_positions(), relaxed.get_positions())[np.triu_indices(4, 1)]
+    np.testing.assert_allclose(d.numpy(), 1.2, atol=2e-4)          # regular tetrahedron with the spring length
+    with pytest.raises(RuntimeError, match='did not converge'):
+        gd.minimize(atoms, max_steps=3, tol=1e-8)
+
+
+def test_lbfgs_relaxer_converges_and_beats_gradient_descent():
+    eng = SpringEngine()
+    atoms = _tetrahedron().init_spatial_partitioning(eng, cutoff=5.0, skin=0.5)
+    calc = md.CalculatorX(eng)
+    opt = md.LBFGS.create(atoms, calc)
+    relaxed, forces = opt.minimize(atoms, max_steps=60, tol=1e-6)
+    assert float(torch.linalg.norm(forces, dim=-1).max()) < 1e-6
+    d = torch.cdist(relaxed.get_positions(), relaxed.get_positions())[np.triu_indices(4, 1)]
+    np.testing.assert_allclose(d.numpy(), 1.2, atol=1e-5)
+    assert calc.n_calls < 150                                     # gradient descent needs > 300 evaluations for 1e-4
+    with pytest.raises(RuntimeError, match='did not converge'):
+        md.LBFGS.create(atoms, calc).minimize(atoms, max_steps=1, tol=1e-12)
+
+
+def test_lbfgs_relaxes_ethanol_on_the_model_surface():
+    """The SO3krates surface itself (oracle-backed engine): the energy goes down monotonically and the largest force
+    falls by more than an order of magnitude; the skin list is rebuilt on the way when atoms move far enough."""
+    cfg = o.OracleConfig(F=32, n_layers=2, degrees=(1, 2), n_heads=4)
+    params = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = OracleEngine(cfg, params)
+    _, _, _, _, atoms = ethanol_state()
+    atoms = atoms.init_spatial_partitioning(eng, cutoff=5.0, skin=0.5)
+    calc = md.CalculatorX(eng)
+    f0 = float(torch.linalg.norm(calc(atoms)['forces'], dim=-1).max())
+    opt = md.LBFGS.create(atoms, calc)
+    energies = [float(calc(atoms)['energy'])]
+    for _ in range(25):
+        atoms, grads = opt.step(atoms)
+        energies.append(float(calc(atoms)['energy']))
+    assert all(b <= a + 1e-12 for a, b in zip(energies, energies[1:]))
+    assert float(torch.linalg.norm(grads, dim=-1).max()) < 0.1 * f0
