@@ -30,16 +30,20 @@ def test_lbfgs_relaxes_ethanol_on_the_device(flags):
     f0 = float(torch.linalg.norm(calc(atoms)['forces'], dim=-1).max())
     opt = md.LBFGS.create(atoms, calc)
     energies = [float(calc(atoms)['energy'])]
-    for _ in range(25):
+    f_tol = 0.05                       # eV/A; f0 = 1.39.  The float64 oracle-driven run gets there in 30 iterations
+    for _ in range(80):                # (0.178 after 25; the device run measured 0.177 fp32 / 0.173 tensor at that point)
         atoms, grads = opt.step(atoms)
         energies.append(float(calc(atoms)['energy']))
+        if float(torch.linalg.norm(grads, dim=-1).max()) < f_tol:
+            break
     assert eng.check_status() == 0
     tol = 1e-5 * max(abs(e) for e in energies) + 1e-6                    # fp32 energies
     assert all(b <= a + tol for a, b in zip(energies, energies[1:]))
-    assert float(torch.linalg.norm(grads, dim=-1).max()) < 0.1 * f0
+    assert f0 > 1.0 and float(torch.linalg.norm(grads, dim=-1).max()) < f_tol
+    assert energies[-1] < energies[0] - 1.0
     # the oracle agrees that the relaxed structure is (nearly) stationary
     R = atoms.get_positions().cpu().numpy()
     nl = o.get_indices(R[None], z[None], 5.0)
     _, F, _ = o.energy_forces(cfg, params, R, z, nl['idx_i'][0], nl['idx_j'][0])
     assert np.abs(F.numpy() + grads.cpu().numpy()).max() < 1e-4
-    assert float(np.linalg.norm(F.numpy(), axis=-1).max()) < 0.1 * f0 + 1e-4
+    assert float(np.linalg.norm(F.numpy(), axis=-1).max()) < f_tol + 1e-4
