@@ -283,3 +283,71 @@ def test_optional_layer_branches(ethanol, opts):
     assert np.abs(Fo - Fr.numpy()).max() < F_ATOL
     assert np.abs(Fo - Fr.numpy()).max() < 5e-5 * np.abs(Fr.numpy()).max()
     assert (Fo[:, -1] == 0).all() and (ea[:, -1] == 0).all()
+
+
+class EmuNLEngine:
+    """`engine.neighbor_list` of mlff_b200.engine.So3kEngine, backed by the emulated cell-list kernels (host tensors)."""
+    device = torch.device('cpu')
+
+    def __init__(self):
+        self.lib = So3kLib(build_emu())
+        self._status = torch.zeros(1, dtype=torch.int32)
+
+    def neighbor_list(self, positions, cutoff, capacity, cell=None, pbc=(False, False, False), z=None, mode=NL_ASE):
+        zz = None if z is None else z.numpy()
+        ii, jj, S, cnt, st = run_nl(self.lib, mode, positions.numpy(), zz, cell, pbc, cutoff, capacity)
+        self._status |= st
+        return torch.as_tensor(ii), torch.as_tensor(jj), torch.as_tensor(S), torch.tensor([cnt])
+
+
+def test_get_pbc_neighbors_and_padding_helpers(solid):
+    # mlff/indexing/indices.py:111-191 -- a padded batch of periodic frames with different sizes, cells and pbc
+    from mlff_b200 import indexing as ix
+    rng = np.random.default_rng(0)
+    R0, cell0 = solid['R'], solid['unit_cell']
+    frames = [(R0, cell0, (1, 1, 1)), (R0[:70] + rng.normal(0, 0.05, (70, 3)), cell0 * 1.3, (1, 1, 0)),
+              (R0[:25], cell0, (0, 0, 0))]
+    n_max = max(len(f[0]) for f in frames)
+    pos = np.concatenate([ix.pad_coordinates(f[0][None], n_max) for f in frames])
+    mask = np.stack([np.arange(n_max) < len(f[0]) for f in frames])
+    out = ix.get_pbc_neighbors(EmuNLEngine(), pos, mask, np.array([f[2] for f in frames]),
+                               np.stack([f[1] for f in frames]), 5.0)
+    lens = []
+    for b, (R, cell, pbc) in enumerate(frames):
+        oi, oj, oS = o.primitive_neighbor_list(R, cell, pbc, 5.0)
+        lens.append(len(oi))
+        ii, jj, S = (out[k][b].numpy() for k in ('idx_i', 'idx_j', 'shifts'))
+        assert as_sets(ii, jj, S) == as_sets(oi, oj, oS)
+        assert (ii[len(oi):] == -1).all() and (jj[len(oi):] == -1).all() and (S[len(oi):] == 0).all()
+        assert ii[:len(oi)].max() < len(R)                      # padding atoms never appear
+    assert out['idx_i'].shape == (3, max(lens)) and out['shifts'].shape == (3, max(lens), 3)
+    # ... and straight into the batched energy+force call (per-frame cells, padding atoms and slots)
+    cfg = o.OracleConfig(F=36, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    zs = [solid['z'][:len(f[0])] for f in frames]
+    z = np.concatenate([ix.pad_atomic_types(zz[None], n_max) for zz in zs])
+    E, F, ea, st = make(cfg, p).energy_forces(pos, z, out['idx_i'].numpy(), out['idx_j'].numpy(),
+                                              np.stack([f[1] for f in frames]), out['shifts'].numpy())
+    assert st == 0
+    for b, (R, cell, pbc) in enumerate(frames):
+        oi, oj, oS = o.primitive_neighbor_list(R, cell, pbc, 5.0)
+        Eo, Fo, _ = o.energy_forces(cfg, p, R, zs[b], oi, oj, cell=cell, cell_offset=oS)
+        assert abs(E[b] - float(Eo)) <= E_RTOL * max(abs(float(Eo)), np.abs(ea[b]).sum())
+        assert np.abs(F[b, :len(R)] - Fo.numpy()).max() < F_ATOL and (F[b, len(R):] == 0).all()
+    holed = mask.copy()
+    holed[1, 3] = False                                         # a padding atom in front of real ones
+    with pytest.raises(ValueError):
+        ix.get_pbc_neighbors(EmuNLEngine(), pos, holed, np.ones((3, 3), bool), np.stack([f[1] for f in frames]), 5.0)
+    empty = ix.get_pbc_neighbors(EmuNLEngine(), pos[:1], np.zeros((1, n_max), bool), np.ones((1, 3), bool), cell0[None], 5.0)
+    assert empty['idx_i'].shape == (1, 0)
+    # padding helpers: numpy and torch, the reference's shapes and fill values (mlff/padding/padding.py:47-108)
+    z = np.arange(1, 7).reshape(2, 3)
+    assert ix.pad_atomic_types(z, 5).tolist() == [[1, 2, 3, 0, 0], [4, 5, 6, 0, 0]]
+    assert ix.pad_coordinates(torch.ones(2, 3, 3), 4).shape == (2, 4, 3) and ix.pad_forces(np.ones((2, 3, 3)), 4)[:, 3].sum() == 0
+    pi, pj = ix.pad_indices(np.zeros((2, 4), np.int32), torch.zeros(2, 4, dtype=torch.int32), 6)
+    assert pi.shape == (2, 6) and (pi[:, 4:] == -1).all() and bool((pj[:, 4:] == -1).all())
+    assert ix.pad_index_list(np.array([1, 2]), 4).tolist() == [1, 2, -1, -1]
+    assert ix.pad_shift(np.ones((2, 3), np.int32), 3).tolist() == [[1, 1, 1], [1, 1, 1], [0, 0, 0]]
+    assert ix.pad_per_atom_quantity(np.ones((1, 2, 1)), 3).shape == (1, 3, 1)
+    with pytest.raises(AssertionError):
+        ix.pad_atomic_types(z, 2)

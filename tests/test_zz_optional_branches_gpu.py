@@ -96,3 +96,34 @@ def test_optional_layer_branches_periodic_box():
               f'(max|F| {float(np.abs(Fo.numpy()).max()):.2f})')
         assert dE <= e_rtol * max(abs(float(Eo)), float(ea.abs().sum()))
         assert dF < f_atol
+
+
+def test_periodic_training_batch_through_get_pbc_neighbors(solid):
+    """a padded batch of periodic frames of different sizes, cells and pbc goes through
+    `get_pbc_neighbors` (mlff/indexing/indices.py:111-191) and the padding helpers straight into the batched
+    energy+force call; every frame is checked against the oracle on its own ASE-style list."""
+    from mlff_b200 import indexing as ix
+    from common import as_sets
+    rng = np.random.default_rng(0)
+    R0, z0, cell0 = solid['R'], solid['z'], solid['unit_cell']
+    frames = [(R0, z0, cell0, (1, 1, 1)), (R0[:70] + rng.normal(0, 0.05, (70, 3)), z0[:70], cell0 * 1.3, (1, 1, 0)),
+              (R0[:25], z0[:25], cell0, (0, 0, 0))]
+    n_max = max(len(f[0]) for f in frames)
+    pos = np.concatenate([ix.pad_coordinates(f[0][None], n_max) for f in frames])
+    z = np.concatenate([ix.pad_atomic_types(f[1][None], n_max) for f in frames])
+    cells = np.stack([f[2] for f in frames])
+    cfg = o.OracleConfig(F=132, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p, 3)
+    nb = ix.get_pbc_neighbors(eng, pos, z != 0, np.array([f[3] for f in frames]), cells, 5.0)
+    assert eng.check_status() == 0
+    E, F, ea = eng.energy_forces(dev(pos, torch.float32), dev(z, torch.int32), nb['idx_i'], nb['idx_j'],
+                                 dev(cells, torch.float32), nb['shifts'], want_e_atom=True)
+    assert eng.check_status() == 0
+    for b, (R, zz, cell, pbc) in enumerate(frames):
+        oi, oj, oS = o.primitive_neighbor_list(R, cell, pbc, 5.0)
+        assert as_sets(*(nb[k][b].cpu().numpy() for k in ('idx_i', 'idx_j', 'shifts'))) == as_sets(oi, oj, oS)
+        Eo, Fo, _ = o.energy_forces(cfg, p, R, zz, oi, oj, cell=cell, cell_offset=oS)
+        assert abs(float(E[b].cpu()) - float(Eo)) <= E_RTOL * max(abs(float(Eo)), float(ea[b].abs().sum()))
+        assert np.abs(F[b, :len(R)].cpu().numpy() - Fo.numpy()).max() < F_ATOL
+        assert float(F[b, len(R):].abs().sum()) == 0.0
