@@ -283,6 +283,14 @@ def test_optional_layer_branches(ethanol, opts):
     assert np.abs(Fo - Fr.numpy()).max() < F_ATOL
     assert np.abs(Fo - Fr.numpy()).max() < 5e-5 * np.abs(Fr.numpy()).max()
     assert (Fo[:, -1] == 0).all() and (ea[:, -1] == 0).all()
+    if len(opts) == 4:                                          # the MD seam shares the stages: displacements in, dE/d(edges) out
+        i0, j0 = nl['idx_i'][0], nl['idx_j'][0]
+        edges = ethanol['R'][0][j0] - ethanol['R'][0][i0]
+        mask = np.ones(len(i0), bool)
+        out = eng.potential(edges, ethanol['z'], i0, j0, mask, energy_scale=0.7)
+        ea_o, dE_o = o.potential_displacements(cfg, p, edges, ethanol['z'], i0, j0, mask, energy_scale=0.7)
+        np.testing.assert_allclose(out[0], ea_o.numpy(), rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(out[1], dE_o.numpy(), rtol=5e-5, atol=5e-5)
 
 
 class EmuNLEngine:
