@@ -165,3 +165,39 @@ def test_stress_is_the_strain_derivative_of_the_energy():
     e_atom, dE = o.potential_displacements(cfg, p, r, z, ii, jj, np.ones(len(ii), bool))
     vir = dE.numpy().T @ r
     np.testing.assert_allclose(0.5 * (vir + vir.T), st, atol=1e-9 * max(np.abs(st).max(), 1.0))
+
+
+def test_oracle_matches_reference_source_functions():
+    """The stateless pieces of the path against arrays produced by the REFERENCE'S OWN SOURCE FILES (executed by
+    tests/golden/make_reference_function_golden.py with numpy standing in for jax.numpy): GeometryEmbed.__call__ in
+    the positions, periodic (cell offsets) and displacements conventions with padded pairs, an out-of-cutoff pair and a
+    zero vector -- r_ij, d_ij, PhysNet basis, cosine cutoff, unit vectors, real spherical harmonics l = 0..4 -- and
+    make_l0_contraction_fn for three degree lists.  This pins the oracle's formulas and masks to the reference itself."""
+    g = golden('reference_functions.npz')
+    cfg = o.OracleConfig(degrees=(0, 1, 2, 3, 4), n_rbf=32, r_cut=5.0)
+    t = lambda a: torch.as_tensor(np.asarray(a))
+    for tag in ('molecule', 'periodic', 'displacements'):
+        ins = {k.split('/in/')[1]: g[k] for k in g.files if k.startswith(tag + '/in/')}
+        kw = {}
+        if tag == 'displacements':
+            kw['displacements'] = t(ins['displacements'])
+        else:
+            kw['R'] = t(ins['R'])
+        if tag == 'periodic':
+            kw['cell'], kw['cell_offset'] = t(ins['unit_cell']), t(ins['cell_offset'])
+        geo = o.geometry_embed(cfg, t(ins['idx_i']).long(), t(ins['idx_j']).long(), t(ins['pair_mask']), torch.float64, **kw)
+        n_checked = 0
+        for k in ('r_ij', 'd_ij', 'rbf_ij', 'phi_r_cut', 'unit_r_ij', 'sph_ij'):
+            ref = g[f'{tag}/{k}']
+            assert np.isfinite(ref).all()
+            np.testing.assert_allclose(geo[k].numpy(), ref, rtol=1e-12, atol=1e-13, err_msg=f'{tag}/{k}')
+            n_checked += ref.size
+        assert n_checked > 1000
+        assert (g[f'{tag}/chi'] == 0).all()                     # sphc_normalization=None: chi0 = 0 (embed.py:196-197)
+    # the fixtures do exercise the special cases
+    assert (g['molecule/phi_r_cut'] == 0).sum() >= 5            # the 6.5 A pair (both directions) and the padding slots
+    assert (g['displacements/unit_r_ij'][5] == 0).all() and g['displacements/d_ij'][5] == 0
+    for tag in ('123', '1223', '01234'):
+        degs = tuple(int(x) for x in g[f'l0/{tag}/degrees'])
+        out = o.l0_contraction(t(g[f'l0/{tag}/chi']), degs)
+        np.testing.assert_allclose(out.numpy(), g[f'l0/{tag}/out'], rtol=1e-12, atol=1e-14)
