@@ -201,3 +201,28 @@ def test_oracle_matches_reference_source_functions():
         degs = tuple(int(x) for x in g[f'l0/{tag}/degrees'])
         out = o.l0_contraction(t(g[f'l0/{tag}/chi']), degs)
         np.testing.assert_allclose(out.numpy(), g[f'l0/{tag}/out'], rtol=1e-12, atol=1e-14)
+
+
+def test_oracle_matches_reference_model_code():
+    """Energies and finite-difference forces produced by the REFERENCE'S OWN MODEL CODE (init_so3krates ->
+    StackNet.__call__ -> So3kratesLayer / Energy, executed unmodified in float64 on the jax / flax stand-ins of
+    tests/golden/ref_shim.py by tests/golden/make_reference_model_golden.py) against the oracle restatement on the same
+    parameters and inputs: default model on ethanol with padding, a repeated-degree list, every optional layer
+    branch, the ZBL repulsion, and the periodic solid with cell offsets."""
+    g = golden('reference_model.npz')
+    cases = {'ethanol_default': (o.OracleConfig(), dict(scale_shift=True)),
+             'ethanol_1223': (o.OracleConfig(F=32, n_layers=2, degrees=(1, 2, 2, 3), n_heads=2), {}),
+             'ethanol_all_branches': (o.OracleConfig(F=36, n_layers=2, layer_normalization=True, final_layer=True,
+                                                     residual_mlp_1=True, residual_mlp_2=True), {}),
+             'ethanol_zbl': (o.OracleConfig(F=36, n_layers=2, zbl_repulsion=True, zbl_repulsion_shift=0.37),
+                             dict(scale_shift=True)),
+             'solid_periodic': (o.OracleConfig(F=36, n_layers=2), {})}
+    for tag, (cfg, kw) in cases.items():
+        p = o.init_params(cfg, int(g[f'{tag}/seed']), embed_scale=4.0, **kw)
+        ins = {k.split('/in/')[1]: g[k] for k in g.files if k.startswith(tag + '/in/')}
+        E, F, _ = o.energy_forces(cfg, p, ins['R'], ins['z'], ins['idx_i'], ins['idx_j'], cell=ins.get('unit_cell'),
+                                  cell_offset=ins.get('cell_offset'))
+        assert abs(float(E) - float(g[f'{tag}/E'])) <= 1e-11 * max(1.0, abs(float(g[f'{tag}/E']))), tag
+        F_fd = g[f'{tag}/F_fd']                                # central differences of the reference energy, h = 1e-4
+        np.testing.assert_allclose(F.numpy()[g[f'{tag}/fd_atoms']], F_fd, rtol=1e-6, atol=2e-7, err_msg=tag)
+        assert np.abs(F_fd).max() > 0.05
