@@ -2,7 +2,9 @@
 
 The engine consumes ONE float32 blob whose order is documented in include/so3k.h.  The reference stores a flax
 variable dict (``valid_params``, mlff/io/checkpoint.py:12-16); the tree paths below are the ones flax generates for
-the reference's modules (inferred from the module code, a real checkpoint was not available):
+the reference's modules (derived from the module code -- a real checkpoint was not available --
+and confirmed by running the reference's own model code on a tree built by `to_flax_tree`, with every leaf looked up
+by flax's naming rules: tests/golden/make_reference_model_golden.py):
 
   params/feature_embeddings_0/Embed_0/embedding                                             (100, F)
   params/layers_t/FeatureBlock_0/filter_fn/VmapMLP_{0=rad,1=sph}/layers_{0,1}/{kernel (1,in,out), bias (1,out)}

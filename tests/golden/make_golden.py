@@ -9,8 +9,9 @@ Writes (all small):
   solid_0.npz         R (110,3), z (110,), unit_cell (3,3) = frame 0 of tests/test_data/test_solid.npz
   oracle_*.npz        float64 oracle outputs (E, F, ...) for fixed-seed weights on those inputs, so that the oracle
                       itself is regression-pinned and GPU tests can compare without re-deriving anything.
-The reference cannot be executed here (no jax/flax/ase), so no reference OUTPUTS exist to record: the oracle
-restatement is the arbiter (oracle/so3k_oracle.py header).
+These are ORACLE outputs (regression pins).  Outputs of the reference's own code are produced by the two sibling
+scripts make_reference_function_golden.py / make_reference_model_golden.py (reference source executed on numpy /
+apply-only flax stand-ins, since jax / flax / ase are not installed here).
 """
 import os
 import sys
