@@ -123,6 +123,52 @@ def main():
     si, sj, S = o.primitive_neighbor_list(pos, cell, [True, True, True], 5.0)
     per = {'R': pos, 'z': zs, 'idx_i': si, 'idx_j': sj, 'unit_cell': cell, 'cell_offset': S}
     run('solid_periodic', o.OracleConfig(F=36, n_layers=2), 3, per, True, [0, 57])
+
+    # ---- MD seam: what MLFFPotential.potential_fn computes (mdx/potential/mlff_potential.py:58-109): displacements in,
+    # per-atom energies out, masked edges -> idx -1, energy scale applied outside the net
+    def run_md_seam(tag, ocfg, seed, energy_kwargs, scale):
+        p = o.init_params(ocfg, seed, embed_scale=4.0, scale_shift=True)
+        pcfg = So3kratesConfig(F=ocfg.F, n_layer=ocfg.n_layers, degrees=tuple(ocfg.degrees), n_heads=ocfg.n_heads,
+                               **energy_kwargs)
+        tree = P.to_flax_tree(pcfg, {k: np.asarray(v, np.float64) for k, v in p.items()})
+        tree = {'params': _f64(tree['params'], p, pcfg)}
+        Energy = sys.modules['mlff.nn.observable'].Energy
+        i0, j0 = nl['idx_i'][0], nl['idx_j'][0]
+        edges0 = R[j0] - R[i0]
+        mask = np.ones(len(i0), bool)
+        mask[[3, 17]] = False                                  # two edges switched off by the graph mask (not symmetric
+        mask[[k for k in range(len(i0)) if (i0[k], j0[k]) in ((j0[3], i0[3]), (j0[17], i0[17]))]] = False  # ... made so)
+
+        def atomic_energies(edges):
+            obs = [Energy(prop_keys=PROP_KEYS, per_atom_scale=list(p['energy/per_atom_scale']),
+                          per_atom_shift=list(p['energy/per_atom_shift']), **energy_kwargs)]
+            net = so3krates.init_so3krates(PROP_KEYS, F=ocfg.F, n_layer=ocfg.n_layers, obs=obs,
+                                           so3krates_layer_kwargs={'degrees': list(ocfg.degrees), 'n_heads': ocfg.n_heads},
+                                           geometry_embed_kwargs={'degrees': list(ocfg.degrees)})
+            net.reset_input_convention('displacements')        # mlff_potential.py:65-66
+            net.reset_output_convention('per_atom')
+            x = {'displacements': edges, 'z': z, 'idx_i': np.where(mask, i0, -1), 'idx_j': np.where(mask, j0, -1)}
+            return scale * np.asarray(net.apply(tree, x)['atomic_energy']).reshape(-1)     # :86-87, :104-107
+
+        out[f'{tag}/e_atom'] = atomic_energies(edges0)
+        fd_edges = [0, 3, 10, 40, 71]
+        h = 1e-4
+        g = np.zeros((len(fd_edges), 3))
+        for a, e in enumerate(fd_edges):
+            for c in range(3):
+                ep, em = edges0.copy(), edges0.copy()
+                ep[e, c] += h
+                em[e, c] -= h
+                g[a, c] = (atomic_energies(ep).sum() - atomic_energies(em).sum()) / (2 * h)
+        out[f'{tag}/dE_dedges_fd'], out[f'{tag}/fd_edges'] = g, np.array(fd_edges)
+        out[f'{tag}/seed'], out[f'{tag}/scale'] = np.array(seed), np.array(scale)
+        for k, v in (('edges', edges0), ('z', z), ('centers', i0), ('others', j0), ('mask', mask)):
+            out[f'{tag}/in/{k}'] = v
+        print(tag, 'sum e_atom =', out[f'{tag}/e_atom'].sum())
+
+    run_md_seam('md_seam_default', o.OracleConfig(F=36, n_layers=2), 5, {}, 1.3)
+    zk = dict(zbl_repulsion=True, zbl_repulsion_shift=0.37)
+    run_md_seam('md_seam_zbl', o.OracleConfig(F=36, n_layers=2, **zk), 6, zk, 0.7)
     np.savez_compressed(os.path.join(HERE, 'reference_model.npz'), **out)
     print('wrote reference_model.npz')
 

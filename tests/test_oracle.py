@@ -226,3 +226,22 @@ def test_oracle_matches_reference_model_code():
         F_fd = g[f'{tag}/F_fd']                                # central differences of the reference energy, h = 1e-4
         np.testing.assert_allclose(F.numpy()[g[f'{tag}/fd_atoms']], F_fd, rtol=1e-6, atol=2e-7, err_msg=tag)
         assert np.abs(F_fd).max() > 0.05
+
+
+def test_oracle_md_seam_matches_reference_model_code():
+    """MLFFPotential.potential_fn (mdx/potential/mlff_potential.py:58-109) replayed on the reference's own model code
+    ('displacements' input and 'per_atom' output conventions, graph mask -> idx -1, energy scale, ZBL shift per atom):
+    per-atom energies and finite-difference dE/d(edges) against the oracle's potential_displacements."""
+    g = golden('reference_model.npz')
+    zk = dict(zbl_repulsion=True, zbl_repulsion_shift=0.37)
+    for tag, cfg in (('md_seam_default', o.OracleConfig(F=36, n_layers=2)),
+                     ('md_seam_zbl', o.OracleConfig(F=36, n_layers=2, **zk))):
+        p = o.init_params(cfg, int(g[f'{tag}/seed']), embed_scale=4.0, scale_shift=True)
+        ins = {k.split('/in/')[1]: g[k] for k in g.files if k.startswith(tag + '/in/')}
+        assert not ins['mask'].all()
+        ea, dE = o.potential_displacements(cfg, p, ins['edges'], ins['z'], ins['centers'], ins['others'], ins['mask'],
+                                           energy_scale=float(g[f'{tag}/scale']))
+        np.testing.assert_allclose(ea.numpy(), g[f'{tag}/e_atom'], rtol=1e-11, atol=1e-12, err_msg=tag)
+        fd = g[f'{tag}/dE_dedges_fd']
+        np.testing.assert_allclose(dE.numpy()[g[f'{tag}/fd_edges']], fd, rtol=1e-6, atol=2e-7, err_msg=tag)
+        assert (fd[1] == 0).all() and np.abs(fd).max() > 0.05          # edge 3 is masked: no dependence
