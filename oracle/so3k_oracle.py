@@ -33,13 +33,14 @@ for this path.  The oracle is pinned against the reference
     apply-only re-implementation of the flax.linen pieces used (Module naming, Dense, Embed, LayerNorm, vmap), see
     tests/golden/ref_shim.py -- and records E and central-difference forces of init_so3krates(...).apply(params, inputs)
     for: the default model on ethanol with padding, a repeated degree list, every optional layer branch
-    (LayerNorm pre/post, ResidualMLP 1/2), the ZBL repulsion, and the periodic solid with cell offsets.
+    (LayerNorm pre/post, ResidualMLP 1/2), the ZBL repulsion, the periodic solid with cell offsets, and the MD seam
+    (MLFFPotential.potential_fn: displacements in, per-atom energies out, mask, scale, per-atom ZBL shift).
     tests/test_oracle.py::test_oracle_matches_reference_model_code: E agrees to 1e-11 relative, forces to the
     finite-difference accuracy (1e-6).  The parameter tree is addressed by flax's path names, which also checks the
     flat-name <-> flax-path map of mlff_b200/params.py.
   * tests/golden/make_reference_function_golden.py does the same for GeometryEmbed.__call__ (positions / cell offsets /
-    displacements, l = 0..4, masks, zero vectors, out-of-cutoff pairs) and make_l0_contraction_fn
-    (::test_oracle_matches_reference_source_functions, 1e-12).
+    displacements, l = 0..4, masks, zero vectors, out-of-cutoff pairs), make_l0_contraction_fn
+    (::test_oracle_matches_reference_source_functions, 1e-12) and get_indices (identical index arrays).
   * the l=0 contraction coefficients are checked against the reference's own ``sph_ops/cgmatrix.npz``; the dense
     neighbour list reproduces the reference fixture property "every ethanol frame has 72 directed edges at 5 A" and the
     distance-multiset test of tests/test_neighbor_list.py:20-49; the model obeys the reference's behavioural spec

@@ -3,8 +3,8 @@
 jax / flax are not installed in this image, so the reference cannot be run as a whole.  Its geometry embedding,
 basis functions, cutoff, masks and l=0 contraction, however, are plain array code: this script executes those
 reference files UNMODIFIED, where they lie under /root/reference, with thin stand-ins for the three imports they need --
-`jax.numpy` (numpy, float64), `jax.jit / jax.vmap / jax.ops.segment_sum` (Python loops) and `flax.linen.Module` (a
-dataclass base; no parameters are involved in these modules).  Nothing is copied: the files are loaded by path.
+`jax.numpy` (numpy, float64), `jax.jit / jax.vmap / jax.ops.segment_sum` (Python loops) and `flax.linen.Module`
+(tests/golden/ref_shim.py; no parameters are involved in these modules).  Nothing is copied: the files are loaded by path.
 
     python tests/golden/make_reference_function_golden.py        (build container only; needs /root/reference)
 
@@ -17,80 +17,32 @@ Writes tests/golden/reference_functions.npz:
      -> add_cell_offsets   mlff/cutoff_function/pbc.py:8-18
      -> safe_mask / safe_scale   mlff/masking/mask.py:5-54
   make_l0_contraction_fn   mlff/sph_ops/contract.py:162-190     degrees [1,2,3], [1,2,2,3], [0,1,2,3,4]
+  get_indices              mlff/indexing/indices.py:15-84       padded batch of ethanol frames, two cutoffs, a pair at
+                           exactly r_cut, an isolated atom, padding atoms
 tests/test_oracle.py::test_oracle_matches_reference_source_functions compares the oracle with these arrays.
 """
-import dataclasses
-import importlib.util
-import io
 import os
-import pickle
 import sys
 import types
 
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF = '/root/reference'
+sys.path.insert(0, HERE)
+import ref_shim as rs  # noqa: E402
+
+REF = rs.REF
+load = rs.load
 
 
 def install_stand_ins():
-    jnp = types.ModuleType('jax.numpy')
-    jnp.__dict__.update({k: v for k, v in np.__dict__.items() if not k.startswith('__')})
-    jnp.float32 = lambda x=0.0: np.float64(np.nan if x is None else x)      # jnp.float32(None) is nan in jax
-    jnp.ndarray = np.ndarray
-
-    def segment_sum(data, segment_ids, num_segments=None):
-        data, ids = np.asarray(data), np.asarray(segment_ids)
-        out = np.zeros((int(num_segments if num_segments is not None else ids.max() + 1),) + data.shape[1:], data.dtype)
-        np.add.at(out, ids, data)
-        return out
-
-    def vmap(fn, *a, **k):
-        return lambda *xs: np.stack([fn(*row) for row in zip(*xs)])
-
-    jax = types.ModuleType('jax')
-    jax.numpy, jax.jit, jax.vmap = jnp, (lambda f=None, **k: f), vmap
-    jax.ops = types.ModuleType('jax.ops')
-    jax.ops.segment_sum = segment_sum
-
-    class Module:
-        def __init_subclass__(cls, **kw):
-            super().__init_subclass__(**kw)
-            dataclasses.dataclass(cls, eq=False)
-
-    linen = types.ModuleType('flax.linen')
-    linen.Module, linen.compact = Module, (lambda f: f)
-    flax = types.ModuleType('flax')
-    flax.linen = linen
-
-    pkg = types.ModuleType('pkg_resources')
-
-    def resource_stream(name, fn):
-        path = os.path.join(REF, *name.split('.')[:-1], fn)
-        if not os.path.exists(path):      # u_matrix.pickle (SymmetricContraction, another model family) is not in the checkout
-            return io.BytesIO(pickle.dumps({}))
-        return open(path, 'rb')
-
-    pkg.resource_stream = resource_stream
-    sys.modules.update({'jax': jax, 'jax.numpy': jnp, 'jax.ops': jax.ops, 'flax': flax, 'flax.linen': linen,
-                        'pkg_resources': pkg})
-    for name in ('mlff', 'mlff.masking', 'mlff.basis_function', 'mlff.cutoff_function', 'mlff.sph_ops', 'mlff.nn',
-                 'mlff.nn.base', 'mlff.nn.embed', 'mlff.properties'):
+    rs.install()
+    for name in ('mlff.geometric', 'mlff.indexing', 'mlff.utils', 'ase', 'ase.neighborlist'):
         m = types.ModuleType(name)
-        m.__path__ = []                                  # a package whose __init__ is NOT executed
+        m.__path__ = []
         sys.modules[name] = m
-
-
-def load(name):
-    """Execute one reference source file, by path, as module `name`."""
-    path = os.path.join(REF, *name.split('.')) + '.py'
-    spec = importlib.util.spec_from_file_location(name, path)
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    parent, _, leaf = name.rpartition('.')
-    setattr(sys.modules[parent], leaf, mod)
-    return mod
+    sys.modules['ase.neighborlist'].primitive_neighbor_list = None      # ASE is absent; only get_pbc_neighbors needs it
+    sys.modules['mlff.utils'].PrimitiveNeighbors = None
 
 
 def main():
@@ -102,7 +54,7 @@ def main():
     pbc = load('mlff.cutoff_function.pbc')
     rad = load('mlff.cutoff_function.radial')
     cf = sys.modules['mlff.cutoff_function']             # what mlff/cutoff_function/__init__.py re-exports
-    cf.add_cell_offsets, cf.get_cutoff_fn = pbc.add_cell_offsets, rad.get_cutoff_fn
+    cf.add_cell_offsets, cf.get_cutoff_fn, cf.pbc_diff = pbc.add_cell_offsets, rad.get_cutoff_fn, pbc.pbc_diff
     load('mlff.nn.base.sub_module')
     embed = load('mlff.nn.embed.embed')
     contract = load('mlff.sph_ops.contract')
@@ -117,8 +69,7 @@ def main():
         ge = embed.GeometryEmbed(prop_keys=prop_keys, degrees=degrees, radial_basis_function='phys', n_rbf=32,
                                  radial_cutoff_fn='cosine_cutoff_fn', r_cut=5.0, sphc=True, mic=mic,
                                  input_convention=convention)
-        ge.setup()
-        g = ge(inputs)
+        g = ge.apply({'params': {}}, inputs)
         for k in ('r_ij', 'd_ij', 'rbf_ij', 'phi_r_cut', 'unit_r_ij', 'sph_ij', 'chi'):
             out[f'{tag}/{k}'] = np.asarray(g[k], np.float64)
         for k, v in inputs.items():
@@ -172,6 +123,18 @@ def main():
         out[f'l0/{tag}/chi'] = chi
         out[f'l0/{tag}/degrees'] = np.array(degs)
         out[f'l0/{tag}/out'] = np.asarray(fn(chi), np.float64)
+
+    # training-set neighbour lists: get_indices (mlff/indexing/indices.py:15-84) on padded ethanol frames
+    load('mlff.geometric.metric')
+    indices = load('mlff.indexing.indices')
+    Rb = np.concatenate([eth['R'][:6].astype(np.float64), np.zeros((6, 2, 3))], axis=1)       # two padding atoms (z = 0)
+    zb = np.tile(np.concatenate([z, [0, 0]])[None], (6, 1))
+    Rb[3, 1] = Rb[3, 0] + np.array([4.0, 3.0, 0.0])                           # a pair at exactly r_cut (d <= r_cut counts)
+    Rb[4, 2] = Rb[4, 0] + 30.0                                                 # an atom with no neighbours at all
+    for rc in (5.0, 2.0):
+        nlr = indices.get_indices(Rb, zb, rc)
+        out[f'get_indices/{rc}/idx_i'], out[f'get_indices/{rc}/idx_j'] = nlr['idx_i'], nlr['idx_j']
+    out['get_indices/R'], out['get_indices/z'] = Rb, zb
 
     np.savez_compressed(os.path.join(HERE, 'reference_functions.npz'), **out)
     print('wrote', os.path.join(HERE, 'reference_functions.npz'), len(out), 'arrays')

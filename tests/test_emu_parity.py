@@ -359,3 +359,20 @@ def test_get_pbc_neighbors_and_padding_helpers(solid):
     assert ix.pad_per_atom_quantity(np.ones((1, 2, 1)), 3).shape == (1, 3, 1)
     with pytest.raises(AssertionError):
         ix.pad_atomic_types(z, 2)
+
+
+def test_device_dense_list_matches_reference_get_indices():
+    """The cell-list kernel in SO3K_NL_DENSE mode (emulated) against arrays produced by the reference's own get_indices
+    source (tests/golden/reference_functions.npz): identical (i, j) sequences per frame -- the kernel's order (sorted by
+    i, then j) is the reference's row-major order."""
+    g = golden('reference_functions.npz')
+    lib = So3kLib(build_emu())
+    R, z = g['get_indices/R'], g['get_indices/z']
+    for rc in (5.0, 2.0):
+        ref_i, ref_j = g[f'get_indices/{rc}/idx_i'], g[f'get_indices/{rc}/idx_j']
+        for b in range(len(R)):
+            ii, jj, S, cnt, st = run_nl(lib, NL_DENSE, R[b], z[b], None, (0, 0, 0), rc, 128)
+            k = int((ref_i[b] >= 0).sum())
+            assert st == 0 and cnt == k
+            assert np.array_equal(ii[:k], ref_i[b][:k]) and np.array_equal(jj[:k], ref_j[b][:k])
+            assert (ii[k:] == -1).all() and (S == 0).all()

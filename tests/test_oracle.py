@@ -245,3 +245,18 @@ def test_oracle_md_seam_matches_reference_model_code():
         fd = g[f'{tag}/dE_dedges_fd']
         np.testing.assert_allclose(dE.numpy()[g[f'{tag}/fd_edges']], fd, rtol=1e-6, atol=2e-7, err_msg=tag)
         assert (fd[1] == 0).all() and np.abs(fd).max() > 0.05          # edge 3 is masked: no dependence
+
+
+def test_get_indices_matches_reference_source():
+    """mlff/indexing/indices.py:15-84 executed from the reference's source (numpy stand-in for jax.numpy) on a padded
+    batch: the oracle's get_indices returns the identical arrays (same row-major order, same -1 padding), including a
+    pair at exactly r_cut, an isolated atom and padding atoms."""
+    g = golden('reference_functions.npz')
+    R, z = g['get_indices/R'], g['get_indices/z']
+    for rc in (5.0, 2.0):
+        nl = o.get_indices(R, z, rc)
+        assert np.array_equal(nl['idx_i'], g[f'get_indices/{rc}/idx_i'])
+        assert np.array_equal(nl['idx_j'], g[f'get_indices/{rc}/idx_j'])
+    assert (g['get_indices/5.0/idx_i'] >= 9).sum() == 0          # padding atoms (z = 0) never appear
+    i3, j3 = g['get_indices/5.0/idx_i'][3], g['get_indices/5.0/idx_j'][3]
+    assert ((i3 == 0) & (j3 == 1)).any()                         # d == r_cut exactly is a neighbour (<=)
