@@ -307,3 +307,46 @@ def test_lbfgs_relaxes_ethanol_on_the_model_surface():
         energies.append(float(calc(atoms)['energy']))
     assert all(b <= a + 1e-12 for a, b in zip(energies, energies[1:]))
     assert float(torch.linalg.norm(grads, dim=-1).max()) < 0.1 * f0
+
+
+def test_integrators_match_reference_source():
+    """VelocityVerletX and NoseHooverX of mlff_b200.md against trajectories recorded from the REFERENCE'S OWN integrator
+    code (mlff/mdx/integrator.py:16-83, 312-342, executed by tests/golden/make_reference_md_golden.py on numpy
+    stand-ins) for the same spring network, initial state and time step: positions, momenta, potential energy and the
+    thermostat variable agree step by step for 50 steps."""
+    g = golden('reference_md.npz')
+    D0, K = float(g['D0']), float(g['K'])
+
+    class Springs:                                  # the generator's analytic calculator, in torch
+        def __call__(self, atoms):
+            if atoms.cache is None:
+                R = atoms.get_positions()
+                d = R[None, :, :] - R[:, None, :]
+                eye = torch.eye(len(R), dtype=R.dtype)
+                r = d.norm(dim=-1) + eye
+                f = K * (r - D0) / r * (1 - eye)
+                atoms.cache = {'energy': 0.25 * K * ((r - D0) ** 2 * (1 - eye)).sum(), 'forces': (f[:, :, None] * d).sum(1)}
+            return atoms.cache
+
+    class NoList:
+        def update(self, positions):
+            return self
+
+    def start():
+        return md.AtomsX(positions=torch.as_tensor(g['R0']), momenta=torch.as_tensor(g['p0']),
+                         masses=torch.as_tensor(g['masses']), numbers=torch.ones(len(g['masses']), dtype=torch.int32),
+                         neighbors=NoList())
+
+    dt = float(g['dt'])
+    runs = {'velocity_verlet': md.VelocityVerletX.create(dt, Springs()),
+            'nose_hoover': md.NoseHooverX.create(dt, float(g['nh_temperature']), float(g['nh_ttime']), Springs())}
+    for tag, integrator in runs.items():
+        atoms = start()
+        for k in range(len(g[f'{tag}/E'])):
+            integrator, atoms, prop = integrator.step(atoms)
+            np.testing.assert_allclose(atoms.get_positions().numpy(), g[f'{tag}/R'][k], rtol=1e-12, atol=1e-13, err_msg=f'{tag} {k}')
+            np.testing.assert_allclose(atoms.get_momenta().numpy(), g[f'{tag}/p'][k], rtol=1e-12, atol=1e-13, err_msg=f'{tag} {k}')
+            assert abs(float(prop['energy']) - g[f'{tag}/E'][k]) < 1e-12
+            if tag == 'nose_hoover':
+                assert abs(float(integrator.zeta) - g[f'{tag}/zeta'][k]) < 1e-12
+    assert g['nose_hoover/zeta'][-1] > 1.0                        # the thermostat is active in this run
