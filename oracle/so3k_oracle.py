@@ -34,7 +34,8 @@ for this path.  The oracle is pinned against the reference
     tests/golden/ref_shim.py -- and records E and central-difference forces of init_so3krates(...).apply(params, inputs)
     for: the default model on ethanol with padding, a repeated degree list, every optional layer branch
     (LayerNorm pre/post, ResidualMLP 1/2), the ZBL repulsion, the periodic solid with cell offsets, and the MD seam
-    (MLFFPotential.potential_fn: displacements in, per-atom energies out, mask, scale, per-atom ZBL shift).
+    (MLFFPotential.potential_fn: displacements in, per-atom energies out, mask, scale, per-atom ZBL shift), and the
+    stress function get_energy_force_stress_fn (jax.value_and_grad replaced by float64 central differences).
     tests/test_oracle.py::test_oracle_matches_reference_model_code: E agrees to 1e-11 relative, forces to the
     finite-difference accuracy (1e-6).  The parameter tree is addressed by flax's path names, which also checks the
     flat-name <-> flax-path map of mlff_b200/params.py.

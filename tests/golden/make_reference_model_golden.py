@@ -166,6 +166,26 @@ def main():
             out[f'{tag}/in/{k}'] = v
         print(tag, 'sum e_atom =', out[f'{tag}/e_atom'].sum())
 
+    # ---- stress: get_energy_force_stress_fn (mlff/nn/stacknet/observable_function.py:152-186) run as written, with
+    # jax.value_and_grad replaced by central differences; a sparse periodic system (30 atoms of the solid in its cell)
+    obs_fn_mod = rs.load('mlff.nn.stacknet.observable_function')
+    scfg = o.OracleConfig(F=32, n_layers=2, degrees=(1, 2), n_heads=2)
+    sp = o.init_params(scfg, 7, embed_scale=4.0)
+    spc = So3kratesConfig(F=32, n_layer=2, degrees=(1, 2), n_heads=2)
+    stree = {'params': _f64(P.to_flax_tree(spc, {k: np.asarray(v, np.float64) for k, v in sp.items()})['params'], sp, spc)}
+    Rp, zp = pos[:30], zs[:30]
+    qi, qj, qS = o.primitive_neighbor_list(Rp, cell, [True, True, True], 5.0)
+    keys = dict(PROP_KEYS, stress='stress')
+    snet = so3krates.init_so3krates(keys, F=32, n_layer=2,
+                                    so3krates_layer_kwargs={'degrees': [1, 2], 'n_heads': 2},
+                                    geometry_embed_kwargs={'degrees': [1, 2], 'mic': True})
+    res = obs_fn_mod.get_energy_force_stress_fn(snet)(stree, {'R': Rp, 'z': zp, 'idx_i': qi, 'idx_j': qj,
+                                                              'unit_cell': cell, 'cell_offset': qS})
+    out['stress/E'], out['stress/F'], out['stress/stress'] = (np.asarray(res[k], np.float64) for k in ('E', 'F', 'stress'))
+    for k, v in (('R', Rp), ('z', zp), ('idx_i', qi), ('idx_j', qj), ('unit_cell', cell), ('cell_offset', qS)):
+        out[f'stress/in/{k}'] = v
+    print('stress: E =', out['stress/E'], ' |stress|max =', np.abs(out['stress/stress']).max())
+
     run_md_seam('md_seam_default', o.OracleConfig(F=36, n_layers=2), 5, {}, 1.3)
     zk = dict(zbl_repulsion=True, zbl_repulsion_shift=0.37)
     run_md_seam('md_seam_zbl', o.OracleConfig(F=36, n_layers=2, **zk), 6, zk, 0.7)

@@ -6,6 +6,7 @@ reference's files where they lie under /root/reference (loaded by path, nothing 
   jax.numpy            numpy, with every float computed in float64 (jnp.float32 -> float64)
   jax.jit / jax.vmap / jax.ops.segment_sum / jax.nn.{silu, softplus} / jax.nn.initializers.constant
                        identity / Python loop / np.add.at / closed forms
+  jax.value_and_grad   central finite differences in float64 (used for the reference's stress function only)
   flax.linen           an APPLY-ONLY re-implementation of the few pieces the SO3krates path uses:
                        Module (dataclass fields, setup, compact, flax's naming rules: attribute names for sub-modules
                        assigned in setup or passed as fields -- `layers_0`, `filter_fn` -- and `ClassName_<k>` in call
@@ -47,12 +48,59 @@ def _vmap(fn, *a, **k):
     return lambda *xs: np.stack([fn(*row) for row in zip(*xs)])
 
 
+def _value_and_grad(fn, argnums=0, has_aux=False, allow_int=False, h=1e-4):
+    """jax.value_and_grad by central finite differences in float64 (error ~h^2): the gradient w.r.t. every float array
+    among the selected arguments (dict arguments leaf by leaf; integer leaves get None)."""
+    single = isinstance(argnums, int)
+    nums = (argnums,) if single else tuple(argnums)
+
+    def wrapped(*args):
+        value = fn(*args)
+
+        def fd(k, get, put):
+            x0 = np.asarray(get(args[k]), np.float64)
+            g = np.zeros_like(x0)
+            for idx in np.ndindex(x0.shape):
+                vals = []
+                for sgn in (1.0, -1.0):
+                    xp = x0.copy()
+                    xp[idx] += sgn * h
+                    a = list(args)
+                    a[k] = put(args[k], xp)
+                    vals.append(float(np.asarray(fn(*a)).reshape(())))
+                g[idx] = (vals[0] - vals[1]) / (2 * h)
+            return g
+
+        grads = []
+        for k in nums:
+            if isinstance(args[k], dict):
+                gk = {}
+                for key, leaf in args[k].items():
+                    if isinstance(leaf, np.ndarray) and np.issubdtype(leaf.dtype, np.floating):
+                        gk[key] = fd(k, lambda d, key=key: d[key], lambda d, v, key=key: {**d, key: v})
+                    else:
+                        gk[key] = None
+                grads.append(gk)
+            else:
+                grads.append(fd(k, lambda a: a, lambda a, v: v))
+        return value, (grads[0] if single else tuple(grads))
+
+    return wrapped
+
+
 def _silu(x):
     return x / (1.0 + np.exp(-x))
 
 
 def _softplus(x):
     return np.logaddexp(x, 0.0)
+
+
+class _JArray(np.ndarray):
+    """numpy array that accepts jax's argument-less `.reshape()` (-> scalar shape) on the outputs of apply()."""
+
+    def reshape(self, *shape, **kw):
+        return np.asarray(self).reshape(*(shape if shape else ((),)), **kw)
 
 
 # ---- flax.linen, apply-only ---------------------------------------------------------------------------------------
@@ -126,7 +174,10 @@ class Module:
     def apply(self, variables, *args, **kwargs):
         d = self.__dict__
         d['_params'], d['_path'] = variables['params'] if 'params' in variables else variables, ''
-        return self(*args, **kwargs)
+        out = self(*args, **kwargs)
+        if isinstance(out, dict):
+            out = {k: np.asarray(v).view(_JArray) if isinstance(v, np.ndarray) else v for k, v in out.items()}
+        return out
 
 
 Module = dataclasses.dataclass(eq=False, repr=False)(Module)
@@ -196,6 +247,7 @@ def install():
     jnp.repeat = lambda a, repeats, axis=None, total_repeat_length=None: np.repeat(a, repeats, axis=axis)   # jax-only kwarg
     jax = types.ModuleType('jax')
     jax.numpy, jax.jit, jax.vmap = jnp, (lambda f=None, **k: f), _vmap
+    jax.value_and_grad = _value_and_grad
     jax.ops = types.ModuleType('jax.ops')
     jax.ops.segment_sum = _segment_sum
     jax.nn = types.ModuleType('jax.nn')
@@ -207,6 +259,10 @@ def install():
         Module, (lambda f: f), Dense, Embed, LayerNorm, vmap
     flax = types.ModuleType('flax')
     flax.linen = linen
+    flax.core = types.ModuleType('flax.core')
+    flax.core.frozen_dict = types.ModuleType('flax.core.frozen_dict')
+    flax.core.frozen_dict.FrozenDict = dict
+    sys.modules.update({'flax.core': flax.core, 'flax.core.frozen_dict': flax.core.frozen_dict})
     pkg = types.ModuleType('pkg_resources')
 
     def resource_stream(name, fn):

@@ -260,3 +260,19 @@ def test_get_indices_matches_reference_source():
     assert (g['get_indices/5.0/idx_i'] >= 9).sum() == 0          # padding atoms (z = 0) never appear
     i3, j3 = g['get_indices/5.0/idx_i'][3], g['get_indices/5.0/idx_j'][3]
     assert ((i3 == 0) & (j3 == 1)).any()                         # d == r_cut exactly is a neighbour (<=)
+
+
+def test_oracle_stress_matches_reference_stress_function():
+    """get_energy_force_stress_fn (mlff/nn/stacknet/observable_function.py:152-186) executed from the reference's source
+    (jax.value_and_grad replaced by float64 central differences) on a periodic system: E, forces and the strain
+    derivative (the reference's stress convention, no volume factor) against the oracle."""
+    g = golden('reference_model.npz')
+    cfg = o.OracleConfig(F=32, n_layers=2, degrees=(1, 2), n_heads=2)
+    p = o.init_params(cfg, 7, embed_scale=4.0)
+    ins = {k.split('/in/')[1]: g[k] for k in g.files if k.startswith('stress/in/')}
+    E, F, stress = o.energy_forces_stress(cfg, p, ins['R'], ins['z'], ins['idx_i'], ins['idx_j'], cell=ins['unit_cell'],
+                                          cell_offset=ins['cell_offset'])
+    assert abs(float(E) - float(g['stress/E'].reshape(()))) < 1e-11 * abs(float(E))
+    np.testing.assert_allclose(F.numpy(), g['stress/F'], rtol=1e-6, atol=5e-7)
+    np.testing.assert_allclose(stress.numpy(), g['stress/stress'], rtol=1e-6, atol=5e-7)
+    assert np.abs(g['stress/stress']).max() > 1.0
