@@ -186,6 +186,26 @@ def main():
         out[f'stress/in/{k}'] = v
     print('stress: E =', out['stress/E'], ' |stress|max =', np.abs(out['stress/stress']).max())
 
+    # ---- hyperparameters.json as the reference writes it: StackNet.__dict_repr__ (stacknet.py:89-111) of nets built by
+    # init_so3krates -- the schema So3kratesConfig.from_hyperparameters / to_hyperparameters must read and write
+    import json
+    md17 = {'energy': 'E', 'force': 'F', 'atomic_type': 'z', 'atomic_position': 'R', 'hirshfeld_volume': 'V_eff',
+            'total_charge': 'Q', 'total_spin': 'S', 'partial_charge': 'q', 'idx_i': 'idx_i', 'idx_j': 'idx_j',
+            'unit_cell': 'unit_cell', 'cell_offset': 'cell_offset', 'node_mask': 'node_mask', 'stress': 'stress',
+            'pbc': 'pbc', 'displacement_vector': 'displacements', 'atomic_energy': 'atomic_energy'}
+    Energy = sys.modules['mlff.nn.observable'].Energy
+    hp = {}
+    for tag, F_, L_, lk, ek in (('default', 132, 3, {}, {}),
+                                ('optional', 64, 2, dict(allk, n_heads=2, degrees=[1, 2, 3, 4]),
+                                 dict(zbl_repulsion=True, zbl_repulsion_shift=0.37))):
+        hnet = so3krates.init_so3krates(dict(md17), F=F_, n_layer=L_, so3krates_layer_kwargs=lk or None,
+                                        geometry_embed_kwargs={'degrees': lk['degrees'], 'mic': True} if lk else None,
+                                        obs=[Energy(prop_keys=dict(md17), **ek)])
+        hp[tag] = hnet.__dict_repr__()
+    with open(os.path.join(HERE, 'reference_hyperparameters.json'), 'w', encoding='utf-8') as f:
+        json.dump(hp, f, ensure_ascii=False, indent=1)
+    print('wrote reference_hyperparameters.json')
+
     run_md_seam('md_seam_default', o.OracleConfig(F=36, n_layers=2), 5, {}, 1.3)
     zk = dict(zbl_repulsion=True, zbl_repulsion_shift=0.37)
     run_md_seam('md_seam_zbl', o.OracleConfig(F=36, n_layers=2, **zk), 6, zk, 0.7)

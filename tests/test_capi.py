@@ -124,3 +124,21 @@ def test_product_has_no_cpu_path():
         from mlff_b200.engine import So3kEngine
         with pytest.raises(RuntimeError):
             So3kEngine(So3kratesConfig(n_layer=1))
+
+
+def test_hyperparameters_json_schema_matches_reference_written_files():
+    """tests/golden/reference_hyperparameters.json is StackNet.__dict_repr__ (stacknet.py:89-111) of nets built by the
+    reference's own init_so3krates (generated by tests/golden/make_reference_model_golden.py): the config class reads
+    it and writes the identical dict back, for the default model and for one with every optional switch."""
+    import json
+    with open(os.path.join(ROOT, 'tests', 'golden', 'reference_hyperparameters.json')) as f:
+        ref = json.load(f)
+    d = So3kratesConfig.from_hyperparameters(ref['default'])
+    assert (d.F, d.n_layer, tuple(d.degrees), d.n_heads, d.n_rbf, d.r_cut, d.mic) == (132, 3, (1, 2, 3), 4, 32, 5.0, False)
+    assert not (d.layer_normalization or d.final_layer or d.residual_mlp_1 or d.residual_mlp_2 or d.zbl_repulsion)
+    q = So3kratesConfig.from_hyperparameters(ref['optional'])
+    assert (q.F, q.n_layer, tuple(q.degrees), q.n_heads, q.mic) == (64, 2, (1, 2, 3, 4), 2, True)
+    assert q.layer_normalization and q.final_layer and q.residual_mlp_1 and q.residual_mlp_2
+    assert q.zbl_repulsion and q.zbl_repulsion_shift == 0.37
+    for cfg, tag in ((d, 'default'), (q, 'optional')):
+        assert json.loads(json.dumps(cfg.to_hyperparameters())) == ref[tag], tag
