@@ -37,7 +37,7 @@ load = rs.load
 
 def install_stand_ins():
     rs.install()
-    for name in ('mlff.geometric', 'mlff.indexing', 'mlff.utils', 'ase', 'ase.neighborlist'):
+    for name in ('mlff.geometric', 'mlff.indexing', 'mlff.padding', 'mlff.utils', 'ase', 'ase.neighborlist'):
         m = types.ModuleType(name)
         m.__path__ = []
         sys.modules[name] = m
@@ -135,6 +135,20 @@ def main():
         nlr = indices.get_indices(Rb, zb, rc)
         out[f'get_indices/{rc}/idx_i'], out[f'get_indices/{rc}/idx_j'] = nlr['idx_i'], nlr['idx_j']
     out['get_indices/R'], out['get_indices/z'] = Rb, zb
+
+    # batch padding helpers (mlff/padding/padding.py:47-108, mlff/indexing/indices.py:87-108)
+    padding = load('mlff.padding.padding')
+    zz_ = np.arange(1, 7).reshape(2, 3)
+    RR_ = rng.normal(size=(2, 3, 3))
+    ij_ = rng.integers(0, 3, (2, 4))
+    out['pad/in/z'], out['pad/in/R'], out['pad/in/idx'] = zz_, RR_, ij_
+    out['pad/atomic_types'] = padding.pad_atomic_types(zz_, 5)
+    out['pad/coordinates'] = padding.pad_coordinates(RR_, 5)
+    out['pad/forces'] = padding.pad_forces(RR_, 4)
+    out['pad/per_atom_quantity'] = padding.pad_per_atom_quantity(RR_[..., :1], 6)
+    out['pad/indices_i'], out['pad/indices_j'] = padding.pad_indices(ij_, ij_[:, ::-1], 7)
+    out['pad/index_list'] = indices.pad_index_list(ij_[0], 6)
+    out['pad/shift'] = indices.pad_shift(ij_[:, :3], 5)
 
     np.savez_compressed(os.path.join(HERE, 'reference_functions.npz'), **out)
     print('wrote', os.path.join(HERE, 'reference_functions.npz'), len(out), 'arrays')

@@ -359,6 +359,15 @@ def test_get_pbc_neighbors_and_padding_helpers(solid):
     assert ix.pad_per_atom_quantity(np.ones((1, 2, 1)), 3).shape == (1, 3, 1)
     with pytest.raises(AssertionError):
         ix.pad_atomic_types(z, 2)
+    # ... and against the outputs of the reference's own padding functions (tests/golden/reference_functions.npz)
+    g = golden('reference_functions.npz')
+    zz, RR, ij = g['pad/in/z'], g['pad/in/R'], g['pad/in/idx']
+    assert np.array_equal(ix.pad_atomic_types(zz, 5), g['pad/atomic_types'])
+    assert np.array_equal(ix.pad_coordinates(RR, 5), g['pad/coordinates']) and np.array_equal(ix.pad_forces(RR, 4), g['pad/forces'])
+    assert np.array_equal(ix.pad_per_atom_quantity(RR[..., :1], 6), g['pad/per_atom_quantity'])
+    pi, pj = ix.pad_indices(ij, ij[:, ::-1], 7)
+    assert np.array_equal(pi, g['pad/indices_i']) and np.array_equal(pj, g['pad/indices_j'])
+    assert np.array_equal(ix.pad_index_list(ij[0], 6), g['pad/index_list']) and np.array_equal(ix.pad_shift(ij[:, :3], 5), g['pad/shift'])
 
 
 def test_device_dense_list_matches_reference_get_indices():
