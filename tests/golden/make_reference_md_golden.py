@@ -1,5 +1,5 @@
 """Golden MD trajectories from the REFERENCE'S OWN INTEGRATOR CODE (mlff/mdx/integrator.py: VelocityVerletX :312-342,
-NoseHooverX :16-83), executed unmodified from /root/reference on the numpy stand-ins of ref_shim.py (`flax.struct`
+NoseHooverX :16-83, LangevinX :86-159 with its noise recorded), executed unmodified from /root/reference on the numpy stand-ins of ref_shim.py (`flax.struct`
 becomes a plain dataclass with `.replace`).  The integrators are duck-typed on the atoms object and the calculator, so
 both are small numpy objects here: the atoms object implements exactly the accessors the reference's AtomsX offers
 (mlff/mdx/atoms.py:174-246, 365-383) and the calculator is an analytic spring network whose forces the test
@@ -42,6 +42,7 @@ class NumpyAtoms:
     def get_momenta(self): return self.momenta.copy()          # jax arrays are immutable: `p += ...` must not alias
     def get_masses(self): return self.masses
     def get_number_of_atoms(self): return len(self.masses)
+    def get_atomic_numbers(self): return np.ones(len(self.masses), np.int32)
     def get_velocities(self): return self.momenta / self.masses[:, None]
     def get_kinetic_energy(self): return 0.5 * (self.momenta * self.get_velocities()).sum()
     def update_positions(self, x, update_neighbors=True): return dataclasses.replace(self, positions=x)
@@ -74,7 +75,16 @@ def main():
         for a in attrs:
             setattr(m, a, None)
         sys.modules[name] = m
-    sys.modules['jax'].random = types.SimpleNamespace(PRNGKey=lambda s: s)
+    # LangevinX draws xi, eta from jax.random: here from a numpy stream that is RECORDED, so the test can feed the same
+    # numbers to mlff_b200.md.LangevinX and compare the deterministic part of the update
+    noise_rng, noise = np.random.default_rng(42), []
+
+    def normal(key=None, shape=None, dtype=None):
+        noise.append(noise_rng.normal(size=shape))
+        return noise[-1].copy()
+
+    sys.modules['jax'].random = types.SimpleNamespace(PRNGKey=lambda s: s, normal=normal,
+                                                      split=lambda key, num=2: tuple(range(num)))
     integ = rs.load('mlff.mdx.integrator')
 
     rng = np.random.default_rng(0)
@@ -99,6 +109,9 @@ def main():
     record('velocity_verlet', integ.VelocityVerletX.create(timestep=dt, calculator=calculator), 50)
     out['nh_temperature'], out['nh_ttime'] = np.array(0.05), np.array(10.0)
     record('nose_hoover', integ.NoseHooverX.create(timestep=dt, temperature=0.05, ttime=10.0, calculator=calculator), 50)
+    out['lv_temperature'], out['lv_friction'] = np.array(0.05), np.array(0.8)
+    record('langevin', integ.LangevinX.create(timestep=dt, temperature=0.05, friction=0.8, calculator=calculator), 30)
+    out['langevin/noise'] = np.array(noise)                       # (2 * steps, n, 3): xi, eta, xi, eta, ...
     np.savez_compressed(os.path.join(HERE, 'reference_md.npz'), **out)
     print('wrote reference_md.npz; final VV E =', out['velocity_verlet/E'][-1], ' NH zeta =', out['nose_hoover/zeta'][-1])
 

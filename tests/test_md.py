@@ -350,3 +350,36 @@ def test_integrators_match_reference_source():
             if tag == 'nose_hoover':
                 assert abs(float(integrator.zeta) - g[f'{tag}/zeta'][k]) < 1e-12
     assert g['nose_hoover/zeta'][-1] > 1.0                        # the thermostat is active in this run
+
+
+def test_langevin_update_matches_reference_source(monkeypatch):
+    """LangevinX (mlff/mdx/integrator.py:86-159) executed from the reference's source with its jax.random draws recorded;
+    mlff_b200.md.LangevinX fed the same xi / eta reproduces the trajectory (coefficients c1..c5, centre-of-mass fix,
+    RATTLE-style velocity recomputation) to 1e-12."""
+    g = golden('reference_md.npz')
+    D0, K = float(g['D0']), float(g['K'])
+    stream = iter(g['langevin/noise'])
+    monkeypatch.setattr(md.torch, 'randn', lambda *shape, **kw: torch.as_tensor(next(stream)))
+
+    class Springs:
+        def __call__(self, atoms):
+            if atoms.cache is None:
+                R = atoms.get_positions()
+                d = R[None, :, :] - R[:, None, :]
+                eye = torch.eye(len(R), dtype=R.dtype)
+                r = d.norm(dim=-1) + eye
+                f = K * (r - D0) / r * (1 - eye)
+                atoms.cache = {'energy': 0.25 * K * ((r - D0) ** 2 * (1 - eye)).sum(), 'forces': (f[:, :, None] * d).sum(1)}
+            return atoms.cache
+
+    class NoList:
+        def update(self, positions):
+            return self
+
+    atoms = md.AtomsX(positions=torch.as_tensor(g['R0']), momenta=torch.as_tensor(g['p0']), masses=torch.as_tensor(g['masses']),
+                      numbers=torch.ones(len(g['masses']), dtype=torch.int32), neighbors=NoList())
+    integrator = md.LangevinX.create(float(g['dt']), float(g['lv_temperature']), float(g['lv_friction']), Springs())
+    for k in range(len(g['langevin/E'])):
+        integrator, atoms, prop = integrator.step(atoms)
+        np.testing.assert_allclose(atoms.get_positions().numpy(), g['langevin/R'][k], rtol=1e-12, atol=1e-13, err_msg=str(k))
+        np.testing.assert_allclose(atoms.get_momenta().numpy(), g['langevin/p'][k], rtol=1e-12, atol=1e-13, err_msg=str(k))
