@@ -385,3 +385,31 @@ def test_device_dense_list_matches_reference_get_indices():
             assert st == 0 and cnt == k
             assert np.array_equal(ii[:k], ref_i[b][:k]) and np.array_equal(jj[:k], ref_j[b][:k])
             assert (ii[k:] == -1).all() and (S == 0).all()
+
+
+REFERENCE_MODEL_CASES = {
+    'ethanol_default': (dict(), dict(scale_shift=True)),
+    'ethanol_1223': (dict(F=32, n_layers=2, degrees=(1, 2, 2, 3), n_heads=2), {}),
+    'ethanol_all_branches': (dict(F=36, n_layers=2, layer_normalization=True, final_layer=True, residual_mlp_1=True,
+                                  residual_mlp_2=True), {}),
+    'ethanol_zbl': (dict(F=36, n_layers=2, zbl_repulsion=True, zbl_repulsion_shift=0.37), dict(scale_shift=True)),
+    'solid_periodic': (dict(F=36, n_layers=2), {})}
+
+
+@pytest.mark.parametrize('tag', list(REFERENCE_MODEL_CASES))
+def test_kernels_match_reference_model_code(tag):
+    """The kernels (emulated) DIRECTLY against energies and finite-difference forces produced by the reference's own
+    model code (tests/golden/reference_model.npz, see tests/golden/make_reference_model_golden.py) -- no oracle in
+    between: default model with padding, repeated degrees, all optional layer branches, ZBL, periodic solid."""
+    g = golden('reference_model.npz')
+    ckw, pkw = REFERENCE_MODEL_CASES[tag]
+    cfg = o.OracleConfig(**ckw)
+    p = o.init_params(cfg, int(g[f'{tag}/seed']), embed_scale=4.0, **pkw)      # the generator's parameters
+    ins = {k.split('/in/')[1]: g[k] for k in g.files if k.startswith(tag + '/in/')}
+    cell = ins['unit_cell'][None] if 'unit_cell' in ins else None
+    off = ins['cell_offset'][None] if 'cell_offset' in ins else None
+    E, F, ea, st = make(cfg, p).energy_forces(ins['R'][None], ins['z'][None], ins['idx_i'][None], ins['idx_j'][None], cell, off)
+    assert st == 0
+    E_ref, F_fd, atoms = float(g[f'{tag}/E']), g[f'{tag}/F_fd'], g[f'{tag}/fd_atoms']
+    assert abs(float(E[0]) - E_ref) <= E_RTOL * max(abs(E_ref), np.abs(ea).sum())
+    assert np.abs(F[0][atoms] - F_fd).max() < F_ATOL
