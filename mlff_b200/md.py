@@ -11,7 +11,7 @@ update rules, on torch tensors instead of jax arrays:
 * `CalculatorX`       mlff/mdx/calculator.py:46-49 (energy + forces of an AtomsX)
 * `VelocityVerletX`   mlff/mdx/integrator.py:313-342 (the reference evaluates the forces twice per step; the second
                       evaluation of a step is the first of the next one, so it is cached here -- same trajectory)
-* `NoseHooverX`, `LangevinX`   mlff/mdx/integrator.py:17-83, 86-159
+* `NoseHooverX`, `LangevinX`, `BerendsenX`   mlff/mdx/integrator.py:17-83, 86-159, 237-310
 * `simulate`          mlff/mdx/simulate.py:60-82 (kinetic / potential energy per step, one host read-back at the end)
 * `GradientDescent`, `LBFGS`   mlff/mdx/optimizer.py:16-52, 55-149 (structure relaxation; same `create` / `step` /
                       `minimize(atoms, max_steps, tol)` contract and error behaviour)
@@ -268,6 +268,33 @@ class LangevinX:
         vel = vel + (c1 * forces / masses - c2 * vel + rnd_vel)
         atoms_displaced = atoms_displaced.update_momenta(vel * masses)
         return self, atoms_displaced, properties
+
+
+class BerendsenX:
+    """Berendsen velocity-rescaling thermostat, mlff/mdx/integrator.py:237-310 (temperature in eV, timestep and
+    time_constant in ASE time units; the rescaling uses AtomsX.get_temperature(), i.e. 3n - 6 degrees of freedom)."""
+
+    def __init__(self, timestep: float, temperature: float, calculator: CalculatorX, time_constant: float, fixcm: bool = True):
+        self.timestep, self.temperature, self.calculator = float(timestep), float(temperature), calculator
+        self.time_constant, self.fixcm = float(time_constant), fixcm
+
+    @classmethod
+    def create(cls, timestep, temperature, calculator, time_constant, fixcm: bool = True):
+        return cls(timestep, temperature, calculator, time_constant, fixcm)
+
+    def step(self, atoms: AtomsX):
+        tr = self.timestep / self.time_constant
+        scl = torch.sqrt(1.0 + tr * (self.temperature / atoms.get_temperature() - 1.0))
+        atoms = atoms.update_momenta(scl * atoms.get_momenta())
+        masses = atoms.get_masses()[:, None]
+        forces = self.calculator(atoms)['forces']
+        p = atoms.get_momenta() + 0.5 * self.timestep * forces
+        if self.fixcm:
+            p = p - p.sum(0) / float(len(p))
+        atoms = atoms.update_positions(atoms.get_positions() + self.timestep * p / masses, update_neighbors=True)
+        properties = self.calculator(atoms)
+        atoms = atoms.update_momenta(p + 0.5 * self.timestep * properties['forces'])
+        return self, atoms, properties
 
 
 def simulate(integrator, atoms: AtomsX, steps: int):

@@ -1,5 +1,5 @@
 """Golden MD trajectories from the REFERENCE'S OWN INTEGRATOR CODE (mlff/mdx/integrator.py: VelocityVerletX :312-342,
-NoseHooverX :16-83, LangevinX :86-159 with its noise recorded), executed unmodified from /root/reference on the numpy stand-ins of ref_shim.py (`flax.struct`
+NoseHooverX :16-83, BerendsenX :237-310, LangevinX :86-159 with its noise recorded), executed unmodified from /root/reference on the numpy stand-ins of ref_shim.py (`flax.struct`
 becomes a plain dataclass with `.replace`).  The integrators are duck-typed on the atoms object and the calculator, so
 both are small numpy objects here: the atoms object implements exactly the accessors the reference's AtomsX offers
 (mlff/mdx/atoms.py:174-246, 365-383) and the calculator is an analytic spring network whose forces the test
@@ -45,6 +45,7 @@ class NumpyAtoms:
     def get_atomic_numbers(self): return np.ones(len(self.masses), np.int32)
     def get_velocities(self): return self.momenta / self.masses[:, None]
     def get_kinetic_energy(self): return 0.5 * (self.momenta * self.get_velocities()).sum()
+    def get_temperature(self): return 2 * self.get_kinetic_energy() / (3 * len(self.masses) - 6)   # atoms.py:210-225
     def update_positions(self, x, update_neighbors=True): return dataclasses.replace(self, positions=x)
     def update_momenta(self, p): return dataclasses.replace(self, momenta=p)
     def update_velocities(self, v): return dataclasses.replace(self, momenta=v * self.masses[:, None])
@@ -109,6 +110,8 @@ def main():
     record('velocity_verlet', integ.VelocityVerletX.create(timestep=dt, calculator=calculator), 50)
     out['nh_temperature'], out['nh_ttime'] = np.array(0.05), np.array(10.0)
     record('nose_hoover', integ.NoseHooverX.create(timestep=dt, temperature=0.05, ttime=10.0, calculator=calculator), 50)
+    out['be_temperature'], out['be_time_constant'] = np.array(0.05), np.array(0.5)
+    record('berendsen', integ.BerendsenX.create(timestep=dt, temperature=0.05, calculator=calculator, time_constant=0.5), 50)
     out['lv_temperature'], out['lv_friction'] = np.array(0.05), np.array(0.8)
     record('langevin', integ.LangevinX.create(timestep=dt, temperature=0.05, friction=0.8, calculator=calculator), 30)
     out['langevin/noise'] = np.array(noise)                       # (2 * steps, n, 3): xi, eta, xi, eta, ...

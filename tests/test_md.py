@@ -310,8 +310,8 @@ def test_lbfgs_relaxes_ethanol_on_the_model_surface():
 
 
 def test_integrators_match_reference_source():
-    """VelocityVerletX and NoseHooverX of mlff_b200.md against trajectories recorded from the REFERENCE'S OWN integrator
-    code (mlff/mdx/integrator.py:16-83, 312-342, executed by tests/golden/make_reference_md_golden.py on numpy
+    """VelocityVerletX, NoseHooverX and BerendsenX of mlff_b200.md against trajectories recorded from the REFERENCE'S OWN integrator
+    code (mlff/mdx/integrator.py:16-83, 237-310, 312-342, executed by tests/golden/make_reference_md_golden.py on numpy
     stand-ins) for the same spring network, initial state and time step: positions, momenta, potential energy and the
     thermostat variable agree step by step for 50 steps."""
     g = golden('reference_md.npz')
@@ -339,7 +339,8 @@ def test_integrators_match_reference_source():
 
     dt = float(g['dt'])
     runs = {'velocity_verlet': md.VelocityVerletX.create(dt, Springs()),
-            'nose_hoover': md.NoseHooverX.create(dt, float(g['nh_temperature']), float(g['nh_ttime']), Springs())}
+            'nose_hoover': md.NoseHooverX.create(dt, float(g['nh_temperature']), float(g['nh_ttime']), Springs()),
+            'berendsen': md.BerendsenX.create(dt, float(g['be_temperature']), Springs(), float(g['be_time_constant']))}
     for tag, integrator in runs.items():
         atoms = start()
         for k in range(len(g[f'{tag}/E'])):
