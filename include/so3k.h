@@ -110,7 +110,9 @@ enum {
 enum {
   SO3K_STATUS_OVERFLOW = 1,    /* neighbour list did not fit `capacity`          */
   SO3K_STATUS_ASYMMETRIC = 2,  /* edge (i,j) without its reverse (j,i)           */
-  SO3K_STATUS_BAD_Z = 4        /* atomic number outside [0, num_embeddings)      */
+  SO3K_STATUS_BAD_Z = 4,       /* atomic number outside [0, num_embeddings)      */
+  SO3K_STATUS_TC_TIMEOUT = 8   /* a tensor-core kernel gave up waiting on an mbarrier (bounded wait instead of a
+                                  hang): the outputs of that call are undefined                              */
 };
 
 int so3k_create(const so3k_config* cfg, so3k_handle** out);

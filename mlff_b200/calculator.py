@@ -64,15 +64,19 @@ class mlffCalculator:
             cell32 = None if cell_h is None else torch.as_tensor(cell_h, dtype=torch.float32, device=dev)[None]
             E, F, _ = eng.energy_forces(R32[None], z[None], ii[None], jj[None],
                                         cell32, None if cell32 is None else S[None])
-            out = torch.cat([E.reshape(-1).double(), count.double(), F.reshape(-1).double()]).cpu()   # one D2H
+            # one D2H for everything the host needs: energy, edge count, device status word, forces
+            out = torch.cat([E.reshape(-1).double(), count.double(), eng._status.double(),
+                             F.reshape(-1).double()]).cpu()
+            eng._status.zero_()
             n_edges = int(out[1].item())
+            status = int(out[2].item())
             if n_edges <= self.capacity:
+                eng.raise_for_status(status & ~STATUS_OVERFLOW)
                 break
             self.capacity = int(np.ceil(self.capacity_multiplier * n_edges))      # overflow: re-allocate and redo
-            eng._status.zero_()
         self.n_edges = n_edges
         self.results = {'energy': float(out[0].item()) * self.energy_scale,
-                        'forces': out[2:].reshape(N, 3).numpy().astype(np.float32) * self.energy_scale}
+                        'forces': out[3:].reshape(N, 3).numpy().astype(np.float32) * self.energy_scale}
         return self.results
 
     def get_potential_energy(self):

@@ -17,6 +17,7 @@ ERR_NAMES = {0: 'SO3K_OK', 1: 'SO3K_ERR_CONFIG', 2: 'SO3K_ERR_ARG', 3: 'SO3K_ERR
 STATUS_OVERFLOW = 1
 STATUS_ASYMMETRIC = 2
 STATUS_BAD_Z = 4
+STATUS_TC_TIMEOUT = 8
 FLAG_TENSOR = 1
 FLAG_KEEP_FILTERS = 2    # with FLAG_TENSOR: keep the forward's filters for the backward (memory for time)
 FLAG_ZBL = 4             # Energy(zbl_repulsion=True): ZBL pair repulsion, ten extra scalars at the end of the blob

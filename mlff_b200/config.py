@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import copy
 from dataclasses import dataclass, field
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 md17_property_keys = {'energy': 'E', 'force': 'F', 'atomic_type': 'z', 'atomic_position': 'R', 'hirshfeld_volume': 'V_eff',
                       'total_charge': 'Q', 'total_spin': 'S', 'partial_charge': 'q', 'idx_i': 'idx_i', 'idx_j': 'idx_j',
@@ -34,6 +34,10 @@ class So3kratesConfig:
     final_layer: bool = False             # with layer_normalization: post-LayerNorm on the layer output
     residual_mlp_1: bool = False          # ResidualMLP after the first skip connection
     residual_mlp_2: bool = False          # ResidualMLP after the second skip connection
+    # Energy(per_atom_scale, per_atom_shift): constants indexed by atomic number, baked into the observable by
+    # init_stack_net from hyperparameters.json (observable.py:36-37, 49-58); None = 1 / 0
+    per_atom_scale: Optional[Sequence[float]] = None
+    per_atom_shift: Optional[Sequence[float]] = None
     prop_keys: Dict[str, str] = field(default_factory=lambda: dict(md17_property_keys))
 
     def validate(self):
@@ -43,6 +47,10 @@ class So3kratesConfig:
                              'so3krates_layer.py:611-615)')
         if any(l < 0 or l > 4 for l in self.degrees):
             raise NotImplementedError('Spherical harmonics are only defined up to order l = 4.')
+        for k in ('per_atom_scale', 'per_atom_shift'):
+            v = getattr(self, k)
+            if v is not None and len(v) > self.num_embeddings:
+                raise ValueError(f'{k} has {len(v)} entries for num_embeddings = {self.num_embeddings}')
         return unsupported
 
     @property
@@ -77,15 +85,42 @@ class So3kratesConfig:
             if v not in ok:
                 raise NotImplementedError(f'hyper-parameter {k}={v!r} is outside the hot path implemented by mlff_b200')
         F = int(feat['features'])
-        if list(l0['fb_rad_filter_features']) != [F, F] or list(l0['fb_sph_filter_features']) != [int(F / 4), F]:
-            raise NotImplementedError('only the default filter widths [F,F] / [F/4,F] are implemented')
+        for l in layers:
+            for blk in ('fb', 'gb'):
+                if (list(l.get(f'{blk}_rad_filter_features', [F, F])) != [F, F]
+                        or list(l.get(f'{blk}_sph_filter_features', [int(F / 4), F])) != [int(F / 4), F]):
+                    raise NotImplementedError(f'{blk} filter widths: only the defaults [F,F] / [F/4,F] are implemented')
+            for k, ok in (('fb_attention', 'conv_att'), ('gb_attention', 'conv_att'), ('chi_cut', None),
+                          ('chi_cut_dynamic', False), ('sphc_normalization', False),
+                          ('neighborhood_normalization', False), ('fast_attention_kwargs', None)):
+                if l.get(k, ok) not in (ok, None if ok is False else ok):
+                    raise NotImplementedError(f'layer hyper-parameter {k}={l.get(k)!r} is outside the hot path '
+                                              'implemented by mlff_b200')
+            if [int(x) for x in l.get('degrees', geo['degrees'])] != [int(x) for x in geo['degrees']]:
+                raise NotImplementedError('layer degrees differ from the geometry embedding degrees')
+            if int(l.get('n_heads', 4)) != int(l0.get('n_heads', 4)):
+                raise NotImplementedError('n_heads differs between layers')
+        if len(sn['geometry_embeddings']) != 1 or len(sn['feature_embeddings']) != 1:
+            raise NotImplementedError('exactly one geometry embedding and one feature embedding are implemented')
+        if geo.get('input_convention', 'positions') not in ('positions', 'displacements'):
+            raise NotImplementedError(f"input_convention={geo.get('input_convention')!r}")
+        if not geo.get('sphc', True):
+            raise NotImplementedError('sphc=False is outside the hot path implemented by mlff_b200')
+        if len(sn.get('observables', [])) > 1 or (sn.get('observables') and 'energy' not in sn['observables'][0]):
+            raise NotImplementedError('only the Energy observable is implemented')
         obs = next(iter(sn['observables'][0].values())) if sn.get('observables') else {}
+        if obs.get('output_convention', 'per_structure') not in ('per_structure', 'per_atom'):
+            raise NotImplementedError(f"output_convention={obs.get('output_convention')!r}")
+        scale_shift = {}
+        for k in ('per_atom_scale', 'per_atom_shift'):
+            v = obs.get(k, None)
+            scale_shift[k] = None if v is None else tuple(float(x) for x in v)
         return cls(F=F, n_layer=len(layers), degrees=tuple(int(x) for x in geo['degrees']),
                    n_heads=int(l0.get('n_heads', 4)), n_rbf=int(geo['n_rbf']), r_cut=float(geo['r_cut']),
                    num_embeddings=int(feat.get('num_embeddings', 100)), mic=bool(geo.get('mic', False)),
                    zbl_repulsion=bool(obs.get('zbl_repulsion', False)),
                    zbl_repulsion_shift=float(obs.get('zbl_repulsion_shift', 0.0) or 0.0),
-                   **{k: bool(l0.get(k, False)) for k in opt_keys},
+                   **{k: bool(l0.get(k, False)) for k in opt_keys}, **scale_shift,
                    prop_keys=dict(sn.get('prop_keys', md17_property_keys)))
 
     def to_hyperparameters(self) -> Dict:
@@ -105,7 +140,9 @@ class So3kratesConfig:
                                   'sphc_normalization': None, 'solid_harmonic': False, 'mic': self.mic,
                                   'input_convention': 'positions', 'prop_keys': self.prop_keys}}
         feat = {'atom_type_embed': {'num_embeddings': self.num_embeddings, 'features': F, 'prop_keys': self.prop_keys}}
-        obs = {'energy': {'per_atom_scale': None, 'per_atom_shift': None, 'num_embeddings': self.num_embeddings,
+        obs = {'energy': {'per_atom_scale': None if self.per_atom_scale is None else [float(x) for x in self.per_atom_scale],
+                          'per_atom_shift': None if self.per_atom_shift is None else [float(x) for x in self.per_atom_shift],
+                          'num_embeddings': self.num_embeddings,
                           'output_convention': 'per_structure', 'zbl_repulsion': self.zbl_repulsion,
                           'zbl_repulsion_shift': self.zbl_repulsion_shift,
                           'prop_keys': self.prop_keys}}

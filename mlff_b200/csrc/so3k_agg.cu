@@ -46,6 +46,16 @@ __device__ __forceinline__ float ld_pinned(const float* p) {
 #endif
 }
 
+__device__ __forceinline__ float4 ld_pinned4(const float* p) {
+#ifdef SO3K_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -130,43 +140,114 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
 }
 
+// ---- lane <-> feature map of the vectorised streaming kernels ---------------------------------------------------------
+// A lane owns NV 16-byte chunks of an F-wide row -- chunk index lane + 32 s, features 4 (lane + 32 s) .. + 3 -- and, with
+// TAIL, one scalar of the remainder (feature 128 NV + lane).  F = 132 is <NV = 1, TAIL>: ONE 128-bit load per lane covers
+// features 0..127 and lanes 0..3 add features 128..131 with a predicated 32-bit load -- two load instructions per row
+// where a lane-per-feature layout needs five.  Element e of a lane: e < 4 NV vector element, e == 4 NV the tail scalar.
+template <int NV, bool TAIL>
+struct LaneMap {
+  static constexpr int E = 4 * NV + (TAIL ? 1 : 0);
+  __device__ __forceinline__ static int feature(int lane, int e) {
+    return e < 4 * NV ? 4 * (lane + 32 * (e >> 2)) + (e & 3) : 128 * NV + lane;
+  }
+  // row p (16-byte aligned, F % 4 == 0) -> v[E]; elements beyond F read as 0
+  __device__ __forceinline__ static void load(const float* __restrict__ p, int lane, int F, float* v) {
+#pragma unroll
+    for (int s = 0; s < NV; ++s) {
+      const int c = lane + 32 * s;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (4 * c < F) t = ld_pinned4(p + 4 * c);
+      v[4 * s] = t.x; v[4 * s + 1] = t.y; v[4 * s + 2] = t.z; v[4 * s + 3] = t.w;
+    }
+    if (TAIL) {
+      const int f = 128 * NV + lane;
+      v[4 * NV] = (f < F) ? ld_pinned(p + f) : 0.f;
+    }
+  }
+  __device__ __forceinline__ static void store(float* __restrict__ p, int lane, int F, const float* v) {
+#pragma unroll
+    for (int s = 0; s < NV; ++s) {
+      const int c = lane + 32 * s;
+      if (4 * c < F) *reinterpret_cast<float4*>(p + 4 * c) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
+    }
+    if (TAIL) {
+      const int f = 128 * NV + lane;
+      if (f < F) p[f] = v[4 * NV];
+    }
+  }
+};
+// floats of product staging per (edge, block) and warp: F rounded up to 8, + 8 to move successive rows off the bank period
+SO3K_HD static inline int so3k_spw(int F) { return ((F + 7) & ~7) + 8; }
+
+// Who reduces what after a batch of EPB edges has staged its per-feature products in shared memory: NOUT = EPB * A head
+// sums (A heads per edge).  With NOUT <= 16 two lanes share a sum (halves of the head's feature range, combined by one
+// shuffle), otherwise one lane per sum.  All fields are loop-invariant per lane.
+struct HeadReducer {
+  int k, a, f0, len;        // edge of the batch, head slot, feature range [f0, f0 + len)
+  bool split, owner;        // two lanes per sum ; this lane writes the result
+};
+
 // Tensor-core path: attention coefficients from the pair-indexed filters, fused with both aggregations.
 //   alpha_fb[e][h] = phi_e / sqrt(F/H)  sum_{f in h} w_fb[pid e][f] q_fb[i][f] k_fb[j][f]       (so3krates_layer.py:590-606)
 //   alpha_gb[e][l] = phi_e / sqrt(F/nl) sum_{f in l} w_gb[pid e][f] q_gb[i][f] k_gb[j][f]       (so3krates_layer.py:545-562)
 //   x1 = x + sum_e alpha_fb[e][h(f)] v[j][f] ;  chi1 = chi + sum_e alpha_gb[e][l(m)] Y_m(u_e)
-// EP edges per iteration; their EP * 2 * HS per-lane head partials (HS slots per block) are reduced over the warp by one
-// halving butterfly (16 shuffles), as in k_alpha_bwd.
-template <int TN, int HS, int DHF, int DHG>     // TN = ceil(F / 32) ; HS = 4 (H, nl <= 4: two edges per pass) or 8 ;
-__global__ void __launch_bounds__(WPB * 32)     // DHF / DHG = compile-time head widths F/H, F/nl (0: run-time)
+// A warp owns a receiver row; two edges per pass.  Their five rows each (two filter rows, the sender's k_fb, k_gb, v)
+// arrive as 128-bit lane chunks (LaneMap); the per-feature products q w k go to a shared-memory staging row in feature
+// order, and the 2 (H + nl) head sums are formed by lanes that each add up (half of) one head's contiguous range -- a
+// dozen shared-memory reads instead of a select-and-add per (feature, head) and a 16-value butterfly.
+template <int NV, bool TAIL>
+__global__ void __launch_bounds__(WPB * 32)
 k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ x,
                   const float* __restrict__ chi, const float* __restrict__ proj, const float* __restrict__ wst_f,
                   const float* __restrict__ wst_g, float* __restrict__ alpha, float* __restrict__ x1,
                   float* __restrict__ chi1) {
-  constexpr int EP = 8 / HS;
+  using LM = LaneMap<NV, TAIL>;
+  constexpr int E = LM::E, EPB = 2;
   __shared__ float s_a[WPB][32 * AMAX];
   __shared__ float s_ph[WPB][32];
   __shared__ int s_j[WPB][32];
   __shared__ int s_p[WPB][32];
+  SO3K_DYN_SMEM(float, s_w_all);             // [WPB][EPB * 2][SPW]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * WPB + w;
-  const int F = D.F, M = D.M, H = D.H, nl = D.nl;
+  const int F = D.F, M = D.M, H = D.H, nl = D.nl, A = H + nl;
+  const int SPW = so3k_spw(F);
+  float* s_w = s_w_all + (size_t)w * EPB * 2 * SPW;
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
   const size_t F5 = 5 * (size_t)F;
   const float inv_f = 1.0f / sqrtf((float)(F / H)), inv_g = 1.0f / sqrtf((float)(F / nl));
-  float accx[TN], qf[TN], qg[TN];
-  int hf[TN], hg[TN];
-#pragma unroll
-  for (int t = 0; t < TN; ++t) {
-    accx[t] = 0.f;
-    const int f = lane + 32 * t;
-    const bool ok = rowok && f < F;
-    qf[t] = ok ? proj[(size_t)i * F5 + f] : 0.f;           // zero beyond F: those slots add nothing
-    qg[t] = ok ? proj[(size_t)i * F5 + F + f] : 0.f;
-    hf[t] = (f < F) ? f / (F / H) : 0;
-    hg[t] = (f < F) ? f / (F / nl) : 0;
+  float accx[E], qf[E], qg[E];
+  int hx[E];
+  if (rowok) {
+    LM::load(proj + (size_t)i * F5, lane, F, qf);
+    LM::load(proj + (size_t)i * F5 + F, lane, F, qg);
   }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    accx[e] = 0.f;
+    if (!rowok) qf[e] = qg[e] = 0.f;
+    const int f = LM::feature(lane, e);
+    hx[e] = (f < F) ? f / (F / H) : 0;
+  }
+  // this lane's share of the head sums of a batch
+  HeadReducer hr;
+  {
+    const int nout = EPB * A;
+    hr.split = nout <= 16;
+    const int o = hr.split ? (lane & 15) : lane, half = hr.split ? (lane >> 4) : 0;
+    hr.k = o / A;
+    hr.a = o - hr.k * A;
+    const bool ok = o < nout;
+    const int blk = hr.a >= H, h = blk ? hr.a - H : hr.a, dh = blk ? F / nl : F / H;
+    const int part = hr.split ? (dh + 1) / 2 : dh;
+    hr.f0 = (hr.k * 2 + blk) * SPW + h * dh + half * part;
+    hr.len = ok ? (half ? dh - part : part) : 0;
+    hr.owner = ok && half == 0;
+  }
+  const float hr_scale = hr.a >= H ? inv_g : inv_f;
   float cacc[SO3K_MAXM];
   for (int m = 0; m < M; ++m) cacc[m] = 0.f;
   for (int e0 = beg; e0 < end; e0 += 32) {
@@ -178,80 +259,51 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
       s_j[w][lane] = col[e];
       s_p[w][lane] = pid[e];
       s_ph[w][lane] = so3k_cutoff(g.w, D.r_cut);
-      for (int a = H + nl; a < Ast; ++a) s_a[w][lane * Ast + a] = 0.f;
+      for (int a = A; a < Ast; ++a) s_a[w][lane * Ast + a] = 0.f;
     }
     __syncwarp();
-    for (int q = 0; q < cnt; q += EP) {
-      float wf[EP][TN], wg[EP][TN], kf[EP][TN], kg[EP][TN], vv[EP][TN];
-      int qk[EP];
-#pragma unroll
-      for (int k = 0; k < EP; ++k) {
-        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
-        const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
-        const float* pwf = wst_f + (size_t)s_p[w][qk[k]] * F;
-        const float* pwg = wst_g + (size_t)s_p[w][qk[k]] * F;
-#pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const int f = lane + 32 * t;
-          const bool ok = (t + 1 < TN) || f < F;
-          wf[k][t] = ok ? pwf[f] : 0.f;
-          wg[k][t] = ok ? pwg[f] : 0.f;
-          kf[k][t] = ok ? pj[2 * F + f] : 0.f;
-          kg[k][t] = ok ? pj[3 * F + f] : 0.f;
-          vv[k][t] = ok ? pj[4 * F + f] : 0.f;
-        }
-      }
-      float val[16];                           // [edge k][block][head slot]
-#pragma unroll
-      for (int u = 0; u < 16; ++u) val[u] = 0.f;
-#pragma unroll
-      for (int k = 0; k < EP; ++k) {
-#pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const float pf = wf[k][t] * qf[t] * kf[k][t];
-          const float pg = wg[k][t] * qg[t] * kg[k][t];
-          if (DHF >= 32 && DHG >= 32) {
-            head_accum<(DHF >= 32 ? DHF : 32), HS>(val + k * 2 * HS, t, lane, pf);
-            head_accum<(DHG >= 32 ? DHG : 32), HS>(val + k * 2 * HS + HS, t, lane, pg);
-          } else {
-#pragma unroll
-            for (int h = 0; h < HS; ++h) {
-              val[k * 2 * HS + h] += (hf[t] == h) ? pf : 0.f;
-              val[k * 2 * HS + HS + h] += (hg[t] == h) ? pg : 0.f;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int st = 0; st < 4; ++st) {         // halving butterfly: afterwards a lane holds value index (lane >> 1)
-        const int off = 16 >> st, half = 8 >> st;
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int u = 0; u < half; ++u) {
-          const float send = up ? val[u] : val[u + half];
-          const float keep = up ? val[u + half] : val[u];
-          val[u] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-      }
-      val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+    for (int q = 0; q < cnt; q += EPB) {
+      float vv[EPB][E];
+      int qk[EPB];
       {
-        const int idx = lane >> 1, k = idx / (2 * HS), a = idx % (2 * HS);
-        if ((lane & 1) == 0 && q + k < cnt) {
-          const float ph = s_ph[w][q + k];
-          if (a < HS) {
-            if (a < H) s_a[w][(q + k) * Ast + a] = val[0] * inv_f * ph;
-          } else if (a - HS < nl) {
-            s_a[w][(q + k) * Ast + H + a - HS] = val[0] * inv_g * ph;
+        float wf[EPB][E], wg[EPB][E], kf[EPB][E], kg[EPB][E];
+#pragma unroll
+        for (int k = 0; k < EPB; ++k) {
+          qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+          const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
+          LM::load(wst_f + (size_t)s_p[w][qk[k]] * F, lane, F, wf[k]);
+          LM::load(wst_g + (size_t)s_p[w][qk[k]] * F, lane, F, wg[k]);
+          LM::load(pj + 2 * F, lane, F, kf[k]);
+          LM::load(pj + 3 * F, lane, F, kg[k]);
+          LM::load(pj + 4 * F, lane, F, vv[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < EPB; ++k) {
+          float pf[E], pg[E];
+#pragma unroll
+          for (int e2 = 0; e2 < E; ++e2) {
+            pf[e2] = wf[k][e2] * (qf[e2] * kf[k][e2]);
+            pg[e2] = wg[k][e2] * (qg[e2] * kg[k][e2]);
           }
+          LM::store(&s_w[(k * 2 + 0) * SPW], lane, F, pf);
+          LM::store(&s_w[(k * 2 + 1) * SPW], lane, F, pg);
         }
       }
       __syncwarp();
+      {
+        float sum = 0.f;
+        const float* sp = &s_w[hr.f0];
+        for (int t = 0; t < hr.len; ++t) sum += sp[t];
+        if (hr.split) sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        if (hr.owner && q + hr.k < cnt) s_a[w][(q + hr.k) * Ast + hr.a] = sum * hr_scale * s_ph[w][q + hr.k];
+      }
+      __syncwarp();
 #pragma unroll
-      for (int k = 0; k < EP; ++k) {
+      for (int k = 0; k < EPB; ++k) {
         const float m = (q + k < cnt) ? 1.f : 0.f;
         const float* aq = &s_a[w][qk[k] * Ast];
 #pragma unroll
-        for (int t = 0; t < TN; ++t) accx[t] = fmaf(m * aq[hf[t]], vv[k][t], accx[t]);
+        for (int e2 = 0; e2 < E; ++e2) accx[e2] = fmaf(m * aq[hx[e2]], vv[k][e2], accx[e2]);
       }
     }
     __syncwarp();
@@ -268,42 +320,61 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
     if (rowok && lane == 0) chi1[(size_t)i * M + m] = chi[(size_t)i * M + m] + s;
   }
   if (rowok) {
+    float xi[E];
+    LM::load(x + (size_t)i * F, lane, F, xi);
 #pragma unroll
-    for (int t = 0; t < TN; ++t) {
-      int f = lane + 32 * t;
-      if (f < F) x1[(size_t)i * F + f] = x[(size_t)i * F + f] + accx[t];
-    }
+    for (int e2 = 0; e2 < E; ++e2) xi[e2] += accx[e2];
+    LM::store(x1 + (size_t)i * F, lane, F, xi);
   }
 }
 
 // alphabar_fb[e][h] = sum_{f in h} xbar1[i][f] v[j][f] ; alphabar_gb[e][l] = sum_{m in l} chibar1[i][m] Y_m(u_e)
 // gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
-// EP = 16 / HP edges per iteration: their EP * HP per-lane head partials are reduced over the warp with ONE halving
-// butterfly (16 shuffles for all of them instead of 5 per value).
-template <int TN, int HP, int DHC>              // TN = ceil(F / 32) ; HP = heads padded to 4 or 8 ; DHC = compile-time
-__global__ void __launch_bounds__(WPB * 32)     // head width F/H (0: run-time)
+// Four edges per pass (two 128-bit row loads each); their 4 H head sums are formed from products staged in shared
+// memory, like in k_alpha_aggregate.
+template <int NV, bool TAIL>
+__global__ void __launch_bounds__(WPB * 32)
 k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
             const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
             const float* __restrict__ alpha, const float* __restrict__ xbar1, const float* __restrict__ chibar1,
             float* __restrict__ alphabar, float* __restrict__ gproj) {
-  constexpr int EP = 16 / HP;
+  using LM = LaneMap<NV, TAIL>;
+  constexpr int E = LM::E, EPB = 4;
   __shared__ float s_a[WPB][32 * AMAX];     // alpha_fb of the reverse edges
   __shared__ float s_o[WPB][32 * AMAX];     // alphabar staging (coalesced store)
   __shared__ int s_j[WPB][32];
+  SO3K_DYN_SMEM(float, s_w_all);             // [WPB][EPB][SPW]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * WPB + w;
   const int F = D.F, M = D.M, H = D.H, nl = D.nl;
+  const int SPW = so3k_spw(F);
+  float* s_w = s_w_all + (size_t)w * EPB * SPW;
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
   const size_t F5 = 5 * (size_t)F;
-  float xb[TN], accv[TN];
-  int hsel[TN];
+  float xb[E], accv[E];
+  int hx[E];
+  if (rowok) LM::load(xbar1 + (size_t)i * F, lane, F, xb);
 #pragma unroll
-  for (int t = 0; t < TN; ++t) {
-    int f = lane + 32 * t;
-    xb[t] = (rowok && f < F) ? xbar1[(size_t)i * F + f] : 0.f;
-    accv[t] = 0.f;
-    hsel[t] = (f < F) ? f / D.dh : 0;       // xb = 0 beyond F: those slots add nothing
+  for (int e = 0; e < E; ++e) {
+    if (!rowok) xb[e] = 0.f;
+    accv[e] = 0.f;
+    const int f = LM::feature(lane, e);
+    hx[e] = (f < F) ? f / (F / H) : 0;
+  }
+  HeadReducer hr;
+  {
+    const int nout = EPB * H;                 // <= 32 (H <= 8)
+    hr.split = nout <= 16;
+    const int o = hr.split ? (lane & 15) : lane, half = hr.split ? (lane >> 4) : 0;
+    hr.k = o / H;
+    hr.a = o - hr.k * H;
+    const bool ok = o < nout;
+    const int dh = F / H;
+    const int part = hr.split ? (dh + 1) / 2 : dh;
+    hr.f0 = hr.k * SPW + hr.a * dh + half * part;
+    hr.len = ok ? (half ? dh - part : part) : 0;
+    hr.owner = ok && half == 0;
   }
   float cb[SO3K_MAXM];
   for (int m = 0; m < M; ++m) cb[m] = rowok ? chibar1[(size_t)i * M + m] : 0.f;
@@ -319,81 +390,56 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
       float y[SO3K_MAXM];
       so3k_sph_all(D, g.x, g.y, g.z, y);
       for (int l = 0; l < nl; ++l) {
-        float s = 0.f;
-        for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s = fmaf(cb[m], y[m], s);
-        s_o[w][lane * Ast + H + l] = s;
+        float sm = 0.f;
+        for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) sm = fmaf(cb[m], y[m], sm);
+        s_o[w][lane * Ast + H + l] = sm;
       }
       for (int a = H + nl; a < Ast; ++a) s_o[w][lane * Ast + a] = 0.f;
     }
     s_j[w][lane] = j;
     __syncwarp();
-    for (int q = 0; q < cnt; q += EP) {
-      float vv[EP][TN], xx[EP][TN];
-      int qk[EP];
-      float am[EP];
+    for (int q = 0; q < cnt; q += EPB) {
+      float xx[EPB][E];
+      int qk[EPB];
+      {
+        float vv[EPB][E];
 #pragma unroll
-      for (int k = 0; k < EP; ++k) {
-        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
-        am[k] = (q + k < cnt) ? 1.f : 0.f;
-        const int jq = s_j[w][qk[k]];
-        const float* vj = proj + (size_t)jq * F5 + 4 * (size_t)F;
-        const float* xj = xbar1 + (size_t)jq * F;
+        for (int k = 0; k < EPB; ++k) {
+          qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+          const int jq = s_j[w][qk[k]];
+          LM::load(proj + (size_t)jq * F5 + 4 * (size_t)F, lane, F, vv[k]);
+          LM::load(xbar1 + (size_t)jq * F, lane, F, xx[k]);
+        }
 #pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const int f = lane + 32 * t;
-          const bool ok = (t + 1 < TN) || f < F;
-          vv[k][t] = ok ? vj[f] : 0.f;
-          xx[k][t] = ok ? xj[f] : 0.f;
+        for (int k = 0; k < EPB; ++k) {
+          float pr[E];
+#pragma unroll
+          for (int e2 = 0; e2 < E; ++e2) pr[e2] = xb[e2] * vv[k][e2];
+          LM::store(&s_w[k * SPW], lane, F, pr);
         }
       }
-      float val[16];                           // [edge k][head h]: this lane's partial of alphabar_fb
+      __syncwarp();
+      {
+        float sum = 0.f;
+        const float* sp = &s_w[hr.f0];
+        for (int t = 0; t < hr.len; ++t) sum += sp[t];
+        if (hr.split) sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        if (hr.owner && q + hr.k < cnt) s_o[w][(q + hr.k) * Ast + hr.a] = sum;
+      }
 #pragma unroll
-      for (int u = 0; u < 16; ++u) val[u] = 0.f;
-#pragma unroll
-      for (int k = 0; k < EP; ++k) {
+      for (int k = 0; k < EPB; ++k) {
+        const float m = (q + k < cnt) ? 1.f : 0.f;
         const float* aq = &s_a[w][qk[k] * Ast];
 #pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const float p = xb[t] * vv[k][t];
-          if (DHC >= 32) {
-            head_accum<(DHC >= 32 ? DHC : 32), HP>(val + k * HP, t, lane, p);
-          } else {
-#pragma unroll
-            for (int h = 0; h < HP; ++h) val[k * HP + h] += (hsel[t] == h) ? p : 0.f;
-          }
-          accv[t] = fmaf(am[k] * aq[hsel[t]], xx[k][t], accv[t]);
-        }
+        for (int e2 = 0; e2 < E; ++e2) accv[e2] = fmaf(m * aq[hx[e2]], xx[k][e2], accv[e2]);
       }
-      // halving butterfly: after the stages with offsets 16, 8, 4, 2 a lane holds value index (lane >> 1); the last
-      // stage completes the sum over the remaining lane bit
-#pragma unroll
-      for (int st = 0; st < 4; ++st) {
-        const int off = 16 >> st, half = 8 >> st;
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int u = 0; u < half; ++u) {
-          const float send = up ? val[u] : val[u + half];
-          const float keep = up ? val[u + half] : val[u];
-          val[u] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-      }
-      val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
-      {
-        const int idx = lane >> 1, k = idx / HP, h = idx % HP;
-        if ((lane & 1) == 0 && h < H && q + k < cnt) s_o[w][(q + k) * Ast + h] = val[0];
-      }
+      __syncwarp();
     }
     __syncwarp();
     for (int t = lane; t < cnt * Ast; t += 32) alphabar[(size_t)e0 * Ast + t] = s_o[w][t];
     __syncwarp();
   }
-  if (rowok) {
-#pragma unroll
-    for (int t = 0; t < TN; ++t) {
-      int f = lane + 32 * t;
-      if (f < F) gproj[(size_t)i * F5 + 4 * (size_t)F + f] = accv[t];
-    }
-  }
+  if (rowok) LM::store(gproj + (size_t)i * F5 + 4 * (size_t)F, lane, F, accv);
 }
 
 // q/k projection gradients of one filter block (blockIdx.y) from its pair-indexed filters w[pid e][f] (kept from the
@@ -404,14 +450,17 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 // and, for the canonical edge of every pair, the filter cotangent of the PAIR
 //   wbar[pid e][f] = ab_e[h(f)] q_i[f] k_j[f] + abr_e[h(f)] q_j[f] k_i[f]
 // which the tensor-core kernel of backward part 2 then reads as a contiguous tile.
-// Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics.
-template <int TN>                               // TN = ceil(F / 32): feature slots per lane
+// Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics; rows move as
+// 128-bit lane chunks (LaneMap).
+template <int NV, bool TAIL>
 __global__ void __launch_bounds__(WPB * 32)
 k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                 const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom,
                 const float* __restrict__ proj, const float* __restrict__ alpha, const float* __restrict__ alphabar,
                 const float* __restrict__ wst, size_t blk_stride, float* __restrict__ gproj, float* __restrict__ ebar,
                 float* __restrict__ wbar) {
+  using LM = LaneMap<NV, TAIL>;
+  constexpr int E = LM::E;
   __shared__ float s_ab[WPB][32 * 8];
   __shared__ float s_abr[WPB][32 * 8];
   __shared__ int s_j[WPB][32];
@@ -428,16 +477,18 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
   const float inv = 1.0f / sqrtf((float)(F / heads));
   wst += blk * blk_stride;
   wbar += blk * blk_stride;
-  float aq[TN], ak[TN], qi[TN], ki[TN];
-  int hf[TN];
+  float aq[E], ak[E], qi[E], ki[E];
+  int hf[E];
+  if (rowok) {
+    LM::load(proj + (size_t)i * F5 + qoff, lane, F, qi);
+    LM::load(proj + (size_t)i * F5 + koff, lane, F, ki);
+  }
 #pragma unroll
-  for (int t = 0; t < TN; ++t) {
-    aq[t] = ak[t] = 0.f;
-    const int f = lane + 32 * t;
-    const bool ok = rowok && f < F;
-    qi[t] = ok ? proj[(size_t)i * F5 + qoff + f] : 0.f;
-    ki[t] = ok ? proj[(size_t)i * F5 + koff + f] : 0.f;
-    hf[t] = (f < F) ? f / (F / heads) : 0;
+  for (int e2 = 0; e2 < E; ++e2) {
+    aq[e2] = ak[e2] = 0.f;
+    if (!rowok) qi[e2] = ki[e2] = 0.f;
+    const int f = LM::feature(lane, e2);
+    hf[e2] = (f < F) ? f / (F / heads) : 0;
   }
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
@@ -460,27 +511,21 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       }
     }
     __syncwarp();
-    // Two edges per batch, two batches in flight: the 6 * TN row loads of the NEXT batch are issued before the current
-    // one is consumed (explicit double buffering -- left to itself ptxas sinks the loads towards their first use and
-    // the kernel becomes latency-bound).  Indices beyond the chunk are clamped (valid addresses), their terms masked.
-    auto load_batch = [&](int q, float (&wv)[2][TN], float (&kj)[2][TN], float (&qj)[2][TN], int (&pp)[2]) {
+    // Two edges per batch, two batches in flight: the row loads of the NEXT batch are issued before the current one is
+    // consumed (explicit double buffering with pinned loads).  Indices beyond the chunk are clamped (valid addresses),
+    // their terms masked.
+    auto load_batch = [&](int q, float (&wv)[2][E], float (&kj)[2][E], float (&qj)[2][E], int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int qc = (q + k < cnt) ? q + k : cnt - 1;
         pp[k] = s_p[w][qc];
         const float* pj = proj + (size_t)s_j[w][qc] * F5;
-        const float* pw = wst + (size_t)(pp[k] & 0x7fffffff) * F;
-#pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const int f = lane + 32 * t;
-          const bool ok = (t + 1 < TN) || f < F;
-          wv[k][t] = ok ? ld_pinned(pw + f) : 0.f;
-          kj[k][t] = ok ? ld_pinned(pj + koff + f) : 0.f;
-          qj[k][t] = ok ? ld_pinned(pj + qoff + f) : 0.f;
-        }
+        LM::load(wst + (size_t)(pp[k] & 0x7fffffff) * F, lane, F, wv[k]);
+        LM::load(pj + koff, lane, F, kj[k]);
+        LM::load(pj + qoff, lane, F, qj[k]);
       }
     };
-    auto use_batch = [&](int q, const float (&wv)[2][TN], const float (&kj)[2][TN], const float (&qj)[2][TN],
+    auto use_batch = [&](int q, const float (&wv)[2][E], const float (&kj)[2][E], const float (&qj)[2][E],
                          const int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -490,18 +535,18 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
         const float* ab = &s_ab[w][qc * 8];
         const float* abr = &s_abr[w][qc * 8];
         const bool canon = (pp[k] < 0) && live;
-        float* wb = wbar + (size_t)(pp[k] & 0x7fffffff) * F;
+        float wb[E];
 #pragma unroll
-        for (int t = 0; t < TN; ++t) {
-          const float a0 = ab[hf[t]], a1 = abr[hf[t]];
-          aq[t] = fmaf(m * a0 * wv[k][t], kj[k][t], aq[t]);
-          ak[t] = fmaf(m * a1 * wv[k][t], qj[k][t], ak[t]);
-          const int f = lane + 32 * t;
-          if (canon && ((t + 1 < TN) || f < F)) __stcs(wb + f, fmaf(a0 * qi[t], kj[k][t], a1 * qj[k][t] * ki[t]));
+        for (int e2 = 0; e2 < E; ++e2) {
+          const float a0 = ab[hf[e2]], a1 = abr[hf[e2]];
+          aq[e2] = fmaf(m * a0 * wv[k][e2], kj[k][e2], aq[e2]);
+          ak[e2] = fmaf(m * a1 * wv[k][e2], qj[k][e2], ak[e2]);
+          wb[e2] = fmaf(a0 * qi[e2], kj[k][e2], a1 * qj[k][e2] * ki[e2]);
         }
+        if (canon) LM::store(wbar + (size_t)(pp[k] & 0x7fffffff) * F, lane, F, wb);
       }
     };
-    float wA[2][TN], kA[2][TN], qA[2][TN], wB[2][TN], kB[2][TN], qB[2][TN];
+    float wA[2][E], kA[2][E], qA[2][E], wB[2][E], kB[2][E], qB[2][E];
     int pA[2], pB[2];
     load_batch(0, wA, kA, qA, pA);
     for (int q = 0; q < cnt; q += 4) {
@@ -513,15 +558,8 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
     __syncwarp();
   }
   if (rowok) {
-    float* gi = gproj + (size_t)i * F5;
-#pragma unroll
-    for (int t = 0; t < TN; ++t) {
-      const int f = lane + 32 * t;
-      if (f < F) {
-        gi[qoff + f] = aq[t];
-        gi[koff + f] = ak[t];
-      }
-    }
+    LM::store(gproj + (size_t)i * F5 + qoff, lane, F, aq);
+    LM::store(gproj + (size_t)i * F5 + koff, lane, F, ak);
   }
 }
 
@@ -714,52 +752,38 @@ void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, co
 #undef SO3K_AGG_CASE
 }
 
+// NV / TAIL of the lane map for an F-wide row (LaneMap): F <= 128: one chunk per lane; 128 < F <= 160: + tail scalar;
+// else two chunks per lane (F <= 256)
+#define SO3K_LANEMAP_DISPATCH(F_, CALL)                  \
+  do {                                                   \
+    if ((F_) <= 128) { CALL(1, false); }                 \
+    else if ((F_) <= 160) { CALL(1, true); }             \
+    else { CALL(2, false); }                             \
+  } while (0)
+
 void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
                                  const float* wst_f, const float* wst_g, float* alpha, float* x1, float* chi1,
                                  cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
-#define SO3K_AA_CASE(TN_)                                                                                              \
-  case TN_:                                                                                                            \
-    if (D.H <= 4 && D.nl <= 4)                                                                                         \
-      SO3K_LAUNCH((k_alpha_aggregate<TN_, 4, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
-                  g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
-    else                                                                                                               \
-      SO3K_LAUNCH((k_alpha_aggregate<TN_, 8, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
-                  g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
-    break;
-  // (compile-time head widths, as in so3k_launch_alpha_bwd, bring nothing here: 7.3 ms per step either way -- the kernel
-  //  is bound by its 50 row loads per iteration, and with cheaper arithmetic ptxas keeps fewer of them in flight)
-  switch (so3k_cdiv(D.F, 32)) {
-    SO3K_AA_CASE(1) SO3K_AA_CASE(2) SO3K_AA_CASE(3) SO3K_AA_CASE(4) SO3K_AA_CASE(5) SO3K_AA_CASE(6) SO3K_AA_CASE(7)
-    SO3K_AA_CASE(8)
-    default: break;
-  }
-#undef SO3K_AA_CASE
+  const size_t smem = sizeof(float) * WPB * 4 * (size_t)so3k_spw(D.F);      // product staging: 2 edges x 2 blocks per warp
+#define SO3K_AA_CALL(NV_, TAIL_)                                                                                     \
+  SO3K_SET_MAX_SMEM((k_alpha_aggregate<NV_, TAIL_>), smem);                                                          \
+  SO3K_LAUNCH((k_alpha_aggregate<NV_, TAIL_>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), smem, st, D, g.N, Ast,     \
+              g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1)
+  SO3K_LANEMAP_DISPATCH(D.F, SO3K_AA_CALL);
+#undef SO3K_AA_CALL
 }
 
 void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                            const float* xbar1, const float* chibar1, float* alphabar, float* gproj, cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
-#define SO3K_AB_CASE(TN_)                                                                                              \
-  case TN_:                                                                                                            \
-    if (D.H <= 4)                                                                                                      \
-      SO3K_LAUNCH((k_alpha_bwd<TN_, 4, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,   \
-                  g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
-    else                                                                                                               \
-      SO3K_LAUNCH((k_alpha_bwd<TN_, 8, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,   \
-                  g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
-    break;
-  if (D.F == 132 && D.H == 4) {                    // the reference's default shape: head boundaries known at compile time
-    SO3K_LAUNCH((k_alpha_bwd<5, 4, 33>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,
-                g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);
-    return;
-  }
-  switch (so3k_cdiv(D.F, 32)) {
-    SO3K_AB_CASE(1) SO3K_AB_CASE(2) SO3K_AB_CASE(3) SO3K_AB_CASE(4) SO3K_AB_CASE(5) SO3K_AB_CASE(6) SO3K_AB_CASE(7)
-    SO3K_AB_CASE(8)
-    default: break;
-  }
-#undef SO3K_AB_CASE
+  const size_t smem = sizeof(float) * WPB * 4 * (size_t)so3k_spw(D.F);      // product staging: 4 edges per warp
+#define SO3K_AB_CALL(NV_, TAIL_)                                                                                      \
+  SO3K_SET_MAX_SMEM((k_alpha_bwd<NV_, TAIL_>), smem);                                                                 \
+  SO3K_LAUNCH((k_alpha_bwd<NV_, TAIL_>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), smem, st, D, g.N, Ast, g.rowptr,  \
+              g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj)
+  SO3K_LANEMAP_DISPATCH(D.F, SO3K_AB_CALL);
+#undef SO3K_AB_CALL
 }
 
 // wst / wbar: [block][pair capacity][F] (block stride = so3k_pair_capacity(Pt) * F floats)
@@ -768,17 +792,11 @@ void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* p
                                cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
   const size_t blk_stride = (size_t)so3k_pair_capacity(g.Pt) * D.F;
-#define SO3K_QK_CASE(TN_)                                                                                              \
-  case TN_:                                                                                                            \
-    SO3K_LAUNCH(k_qk_bwd_stream<TN_>, dim3(so3k_cdiv(g.N, WPB), 2), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
-                g.col, g.rev, g.pid, g.geom, proj, alpha, alphabar, wst, blk_stride, gproj, ebar, wbar);               \
-    break;
-  switch (so3k_cdiv(D.F, 32)) {
-    SO3K_QK_CASE(1) SO3K_QK_CASE(2) SO3K_QK_CASE(3) SO3K_QK_CASE(4) SO3K_QK_CASE(5) SO3K_QK_CASE(6) SO3K_QK_CASE(7)
-    SO3K_QK_CASE(8)
-    default: break;
-  }
-#undef SO3K_QK_CASE
+#define SO3K_QK_CALL(NV_, TAIL_)                                                                                       \
+  SO3K_LAUNCH((k_qk_bwd_stream<NV_, TAIL_>), dim3(so3k_cdiv(g.N, WPB), 2), dim3(WPB * 32), 0, st, D, g.N, Ast,         \
+              g.rowptr, g.col, g.rev, g.pid, g.geom, proj, alpha, alphabar, wst, blk_stride, gproj, ebar, wbar)
+  SO3K_LANEMAP_DISPATCH(D.F, SO3K_QK_CALL);
+#undef SO3K_QK_CALL
 }
 
 void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,

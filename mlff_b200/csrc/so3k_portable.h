@@ -17,6 +17,7 @@
   T* name = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(emu::g_dyn_smem) + 15) & ~uintptr_t(15))
 #define SO3K_SET_MAX_SMEM(kernel, bytes) ((void)0)
 #define SO3K_HD
+#define SO3K_SHARED16 alignas(16) static
 #else
 #include <cuda_runtime.h>
 #define SO3K_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
@@ -30,6 +31,7 @@
 #define SO3K_SET_MAX_SMEM(kernel, bytes) \
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #define SO3K_HD __host__ __device__
+#define SO3K_SHARED16 __shared__ __align__(16)          // a shared-memory array read / written with 128-bit accesses
 #endif
 
 void so3k_count_launch();

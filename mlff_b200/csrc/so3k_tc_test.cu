@@ -68,6 +68,37 @@ k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A
       acc = 1;
     }
     tc::commit(&bar);
+  } else if (variant == 5) {
+    // A operand from tensor memory (the layout the filter kernel's epilogue 1 writes IN PLACE over the GEMM1
+    // accumulator): k-step ks (16 reduction indices) occupies the 16 columns [16 ks, 16 ks + 16) of the row's lane --
+    // 8 columns of packed bf16 hi followed by 8 columns of packed bf16 lo.  D at column 128 (K, N <= 128).
+    for (int ks = 0; ks < K / 16; ++ks) {
+      uint32_t pk[16];
+      for (int q = 0; q < 8; ++q)
+        tc::split2(A[(size_t)tid * K + ks * 16 + 2 * q], A[(size_t)tid * K + ks * 16 + 2 * q + 1], &pk[q], &pk[8 + q]);
+      tc::tmem_st16(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)(16 * ks), pk);
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, 0);
+      uint32_t acc = 0;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint32_t aoff = (uint32_t)ks * 256u;
+        const uint64_t b_hi = tc::make_desc(tc::smem_u32(Bhi) + aoff, 128u, sboB);
+        const uint64_t b_lo = tc::make_desc(tc::smem_u32(Blo) + aoff, 128u, sboB);
+        const uint32_t a_hi = tmem + (uint32_t)(16 * ks), a_lo = a_hi + 8u;
+        tc::mma_bf16_ts(tmem + 128u, a_hi, b_hi, idesc, acc);
+        acc = 1;
+        if (passes == 3) {
+          tc::mma_bf16_ts(tmem + 128u, a_lo, b_hi, idesc, 1);
+          tc::mma_bf16_ts(tmem + 128u, a_hi, b_lo, idesc, 1);
+        }
+      }
+      tc::commit(&bar);
+    }
   } else if (tid == 0) {
     const uint32_t idesc = tc::make_idesc_bf16(128, N, 0, variant == 2 ? 1 : 0);
     uint32_t acc = 0;
@@ -96,9 +127,10 @@ k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A
   tc::mbar_wait(&bar, 0);
   tc::fence_after_sync();
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  const uint32_t dcol = variant == 5 ? 128u : 0u;
   for (int c = 0; c < N; c += 8) {
     float v[8];
-    tc::tmem_ld8(tmem + lane_base + (uint32_t)c, v);
+    tc::tmem_ld8(tmem + dcol + lane_base + (uint32_t)c, v);
     tc::tmem_ld_wait();
     for (int q = 0; q < 8; ++q) D[(size_t)tid * N + c + q] = v[q];
   }
@@ -161,6 +193,7 @@ extern "C" int so3k_tc_selftest(int32_t N, int32_t K, int32_t variant, int32_t p
   return SO3K_ERR_CONFIG;
 #else
   if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || !A || !B || !D) return SO3K_ERR_ARG;
+  if (variant == 5 && (N > 128 || K > 128)) return SO3K_ERR_ARG;
   size_t smem = 2 * (size_t)16 * (K / 8) * 128 + 2 * (size_t)N * K * 2 + 1024;
   if (smem > 227 * 1024) return SO3K_ERR_ARG;
   cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .capi import STATUS_ASYMMETRIC, STATUS_BAD_Z, STATUS_OVERFLOW, NL_ASE, NL_DENSE, So3kError
+from .capi import (STATUS_ASYMMETRIC, STATUS_BAD_Z, STATUS_OVERFLOW, STATUS_TC_TIMEOUT, NL_ASE, NL_DENSE, So3kError)
 from .config import So3kratesConfig
 from .params import pack_blob
 
@@ -71,15 +71,35 @@ class So3kEngine:
             self._ws = torch.empty(int(nbytes * 1.05) + 1024, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    @staticmethod
+    def raise_for_status(s: int) -> int:
+        """Raise So3kError for every ERROR bit of a status word already on the host (include/so3k.h, SO3K_STATUS_*).
+        SO3K_STATUS_OVERFLOW is not an error: the caller re-allocates and repeats the call, exactly like
+        PrimitiveNeighbors.overflow (mlff/indexing/indices.py:264-272); it is returned to the caller."""
+        if s & STATUS_ASYMMETRIC:
+            raise So3kError('edge list is not symmetric: an edge (i,j) has no reverse (j,i); outputs are undefined')
+        if s & STATUS_BAD_Z:
+            raise So3kError('atomic number outside [0, num_embeddings); outputs are undefined')
+        if s & STATUS_TC_TIMEOUT:
+            raise So3kError('a tensor-core kernel timed out waiting on an mbarrier; outputs are undefined')
+        if s & ~(STATUS_OVERFLOW | STATUS_ASYMMETRIC | STATUS_BAD_Z | STATUS_TC_TIMEOUT):
+            raise So3kError(f'unknown bits in the device status word: {s:#x}')
+        return s
+
+    def count_and_status(self, count: torch.Tensor) -> int:
+        """ONE synchronising read of a neighbour-list edge count together with the device status word.  Error bits
+        raised by any call since the last check (asymmetric list, bad Z, tensor-kernel time-out) raise here; the
+        overflow bit is cleared (the caller compares the returned count with its capacity and re-allocates)."""
+        v = torch.cat([count.reshape(1).to(torch.int64), self._status.to(torch.int64)]).cpu()
+        self._status.zero_()
+        self.raise_for_status(int(v[1]) & ~STATUS_OVERFLOW)
+        return int(v[0])
+
     def check_status(self) -> int:
-        """Synchronising read of the device status word (tests / debugging; not on the hot path)."""
+        """Synchronising read (and reset) of the device status word; raises on every error bit."""
         s = int(self._status.item())
         self._status.zero_()
-        if s & STATUS_ASYMMETRIC:
-            raise So3kError('edge list is not symmetric: an edge (i,j) has no reverse (j,i)')
-        if s & STATUS_BAD_Z:
-            raise So3kError('atomic number outside [0, num_embeddings)')
-        return s
+        return self.raise_for_status(s)
 
     # ---- energy + forces (training / evaluation seam) ----------------------------------------------
     def energy_forces(self, R: torch.Tensor, z: torch.Tensor, idx_i: torch.Tensor, idx_j: torch.Tensor,

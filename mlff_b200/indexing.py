@@ -24,6 +24,19 @@ import torch
 from .capi import NL_ASE, NL_DENSE
 
 
+
+def _count(engine, count) -> int:
+    """Edge count of a neighbour-list call, read together with the device status word (So3kEngine.count_and_status:
+    error bits raise, the overflow bit is cleared -- the callers below compare the count with their capacity)."""
+    f = getattr(engine, 'count_and_status', None)
+    if f is not None:
+        return f(count)
+    n = int(count.item())
+    if hasattr(engine, '_status'):
+        engine._status.zero_()
+    return n
+
+
 def get_indices(engine, R, z, r_cut: float) -> Dict[str, torch.Tensor]:
     """R (B,n,3), z (B,n) (0 = padding atom), numpy or torch.  Returns {'idx_i', 'idx_j'}: (B,P_max) int32 on the engine's
     device, per-frame atom indices, -1 padded."""
@@ -40,11 +53,10 @@ def get_indices(engine, R, z, r_cut: float) -> Dict[str, torch.Tensor]:
     cap = max(64, B * n * 32)
     while True:
         ii, jj, _, count = engine.neighbor_list(pos, r_cut, cap, z=z.reshape(-1), mode=NL_DENSE)
-        nv = int(count.item())
+        nv = _count(engine, count)
         if nv <= cap:
             break
         cap = int(1.25 * nv) + 16
-        engine._status.zero_()
     ii, jj = ii[:nv].long(), jj[:nv].long()                 # flat indices, sorted by (i, j): row-major inside a frame
     frame = ii // n
     per_frame = torch.bincount(frame, minlength=B)
@@ -82,11 +94,10 @@ def get_pbc_neighbors(engine, pos, node_mask, pbc, cell, cutoff: float) -> Dict[
         cap = max(cap, 64 * n_real + 16)
         while True:
             ii, jj, S, count = engine.neighbor_list(p, cutoff, cap, cell=cell_h[b], pbc=tuple(pbc_h[b]), mode=NL_ASE)
-            nv = int(count.item())
+            nv = _count(engine, count)
             if nv <= cap:
                 break
             cap = int(1.25 * nv) + 16                       # overflow: re-allocate, as the reference does (:151-155)
-            engine._status.zero_()
         frames.append((ii[:nv].clone(), jj[:nv].clone(), S[:nv].clone()))
     pmax = max((len(f[0]) for f in frames), default=0)
     idx_i = torch.full((B, pmax), -1, dtype=torch.int32, device=dev)

@@ -54,12 +54,12 @@ class SkinNeighborList:
         while True:
             ii, jj, S, count = self.engine.neighbor_list(positions, self.cutoff + self.skin, cap, cell=self.cell,
                                                          pbc=self.pbc, **kw)
-            n = int(count.item())
+            # edge count + device status word in one read: errors of the evaluations since the last build (asymmetric
+            # list, bad Z, tensor-kernel time-out) surface here, once per rebuild
+            n = self.engine.count_and_status(count) if hasattr(self.engine, 'count_and_status') else int(count.item())
             if n <= cap:
                 break
             cap = int(self.capacity_multiplier * n) + 16          # overflow: re-allocate (indices.py:264-272 semantics)
-            if hasattr(self.engine, '_status'):
-                self.engine._status.zero_()
         if self.capacity == 0 or cap > self.capacity:
             self.capacity = max(int(self.capacity_multiplier * n) + 16, n)
         # full-capacity arrays (padded with -1 / 0 behind `count`): their shape only changes when the capacity grows, which

@@ -150,9 +150,18 @@ def from_flax_tree(cfg: So3kratesConfig, variables: Dict, per_atom_scale=None, p
         if vm:
             a = a.reshape(a.shape[1:]) if a.shape[0] == 1 and a.ndim == len(shape) + 1 else a
         out[name] = a.reshape(shape)
+    # Energy's per-atom scale / shift are constants of the module, not flax parameters (observable.py:49-58): they come
+    # from hyperparameters.json through the config unless the caller overrides them
     n = cfg.num_embeddings
-    out['energy/per_atom_scale'] = np.ones(n, np.float32) if per_atom_scale is None else np.asarray(per_atom_scale, np.float32)
-    out['energy/per_atom_shift'] = np.zeros(n, np.float32) if per_atom_shift is None else np.asarray(per_atom_shift, np.float32)
+    for key, arg, fill in (('per_atom_scale', per_atom_scale, 1.0), ('per_atom_shift', per_atom_shift, 0.0)):
+        v = arg if arg is not None else getattr(cfg, key, None)
+        a = np.full(n, fill, np.float32)
+        if v is not None:
+            v = np.asarray(v, np.float32).reshape(-1)
+            if v.size > n:
+                raise ValueError(f'{key} has {v.size} entries for num_embeddings = {n}')
+            a[:v.size] = v                       # jnp.take(per_atom_scale, z): indexed by atomic number
+        out[f'energy/{key}'] = a
     return out
 
 

@@ -11,7 +11,7 @@ from mlff_b200.calculator import mlffCalculator
 from mlff_b200 import params as P
 from common import jittered_lattice, water_like_numbers
 cfg = So3kratesConfig(n_layer=3)
-calc = mlffCalculator(cfg, P.init_params(cfg, 0), flags=1)
+calc = mlffCalculator(cfg, P.init_params(cfg, 0), flags=3)
 N, box = 100_000, 100.0
 pos = jittered_lattice(N, box, 3); z = water_like_numbers(N, 3)
 for _ in range(2):

@@ -413,3 +413,41 @@ def test_kernels_match_reference_model_code(tag):
     E_ref, F_fd, atoms = float(g[f'{tag}/E']), g[f'{tag}/F_fd'], g[f'{tag}/fd_atoms']
     assert abs(float(E[0]) - E_ref) <= E_RTOL * max(abs(E_ref), np.abs(ea).sum())
     assert np.abs(F[0][atoms] - F_fd).max() < F_ATOL
+
+
+@pytest.mark.parametrize('keep', [0, 2])
+@pytest.mark.parametrize('F,degrees,H', [(132, (1, 2, 3), 4), (36, (1, 2, 3), 4), (32, (1, 2, 2, 3), 4), (144, (1, 2, 3), 8),
+                                         (140, (1, 2, 3, 4), 4), (256, (1, 2, 3, 4), 4)])
+def test_tensor_mode_orchestration_and_streaming_kernels(ethanol, solid, F, degrees, H, keep):
+    """Tensor mode on the emulator: the two tcgen05 pair kernels are stood in for by plain fp32 loops (so3k_edge_tc.cu,
+    SO3K_EMU branch); everything around them is the product source -- pair records, canonical pairs, the streaming
+    kernels that consume pair-indexed filters and emit pair-indexed filter cotangents (k_alpha_aggregate, k_alpha_bwd,
+    k_qk_bwd_stream with their 128-bit lane maps: one chunk per lane, chunk + tail scalar (F = 132, 140, 144), two chunks
+    (F = 256)), kept / recomputed filters."""
+    from mlff_b200.capi import FLAG_TENSOR
+    cfg = o.OracleConfig(F=F, n_layers=2, degrees=degrees, n_heads=H)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = EmuEngine(cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads, cfg.degrees, cfg.r_cut, flags=FLAG_TENSOR | keep)
+    eng.load(p)
+    B = 2
+    R = ethanol['R'][:B]
+    z = np.tile(ethanol['z'][None], (B, 1))
+    nl = o.get_indices(R, z, 5.0)
+    # padding atoms and padding pair slots, as the training batches have them
+    R = np.concatenate([R, np.zeros((B, 2, 3))], 1)
+    z = np.concatenate([z, np.zeros((B, 2), z.dtype)], 1)
+    ii = np.concatenate([nl['idx_i'], -np.ones((B, 5), nl['idx_i'].dtype)], 1)
+    jj = np.concatenate([nl['idx_j'], -np.ones((B, 5), nl['idx_j'].dtype)], 1)
+    E, Fc, ea, st = eng.energy_forces(R, z, ii, jj)
+    assert st == 0
+    Eo, Fo = o.energy_forces_batch(cfg, p, R, z, ii, jj)
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= E_RTOL * np.abs(Eo.numpy().reshape(-1))).all()
+    assert np.abs(Fc - Fo.numpy()).max() < F_ATOL and (Fc[:, -2:] == 0).all()
+    if F == 36:
+        # a periodic solid with several images per pair (cell < 2 r_cut): long receiver rows (> 32 edges per chunk)
+        Rs, zs, cell = solid['R'], solid['z'], solid['unit_cell']
+        oi, oj, oS = o.primitive_neighbor_list(Rs, cell, (True, True, True), 5.0)
+        E, Fc, ea, st = eng.energy_forces(Rs[None], zs[None], oi[None], oj[None], cell[None], oS[None])
+        Eo, Fo, _ = o.energy_forces(cfg, p, Rs, zs, oi, oj, cell=cell, cell_offset=oS)
+        assert st == 0 and abs(E[0] - float(Eo)) <= E_RTOL * abs(float(Eo))
+        assert np.abs(Fc[0] - Fo.numpy()).max() < F_ATOL

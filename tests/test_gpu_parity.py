@@ -336,26 +336,30 @@ def test_calculator_end_to_end(solid):
 
 
 # ---- tcgen05 operand-layout conventions ------------------------------------------------------------------------
-@pytest.mark.parametrize('N,K,variant', [(144, 32, 0), (144, 176, 0), (176, 144, 2), (256, 64, 0), (48, 144, 2)])
+@pytest.mark.parametrize('N,K,variant', [(144, 32, 0), (144, 176, 0), (176, 144, 2), (256, 64, 0), (48, 144, 2),
+                                         (128, 96, 5), (64, 128, 5)])
 def test_tcgen05_tile_gemm_layouts(N, K, variant):
     """One 128 x N x K tile on the tensor cores with the canonical no-swizzle operand images the edge kernels
-    build (K-major, and the same image consumed MN-major), single pass and 3-pass split-bf16."""
+    build (K-major, and the same image consumed MN-major), single pass and 3-pass split-bf16.  Variant 5: the A operand
+    comes from tensor memory in the layout the filter kernel's first epilogue writes in place (tcgen05.st, packed
+    bf16 hi | lo per 16-column k-step)."""
     from mlff_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(N * 1000 + K)
     A = rng.normal(size=(128, K)).astype(np.float32)
-    Bm = rng.normal(size=(N, K) if variant == 0 else (K, N)).astype(np.float32)
-    ref = A.astype(np.float64) @ (Bm.astype(np.float64).T if variant == 0 else Bm.astype(np.float64))
+    kmajor = variant in (0, 5)
+    Bm = rng.normal(size=(N, K) if kmajor else (K, N)).astype(np.float32)
+    ref = A.astype(np.float64) @ (Bm.astype(np.float64).T if kmajor else Bm.astype(np.float64))
     def bf(a):      # the kernels' hi part: round-half-up to bf16 (so3k_tc.cuh split2), done on the integer pipe
         b = np.ascontiguousarray(a, np.float32).view(np.uint32)
         return ((b + np.uint32(0x8000)) & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
-    ref1 = bf(A) @ (bf(Bm).T if variant == 0 else bf(Bm))
+    ref1 = bf(A) @ (bf(Bm).T if kmajor else bf(Bm))
     Ad, Bd = dev(A, torch.float32), dev(Bm, torch.float32)
     for passes, target, tol in ((1, ref1, 2e-5), (3, ref, 3e-5)):
         D = torch.zeros(128, N, dtype=torch.float32, device='cuda:0')
         lib.tc_selftest(N, K, variant, passes, Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
-        scale = np.abs(A).astype(np.float64) @ (np.abs(Bm).astype(np.float64).T if variant == 0 else np.abs(Bm))
+        scale = np.abs(A).astype(np.float64) @ (np.abs(Bm).astype(np.float64).T if kmajor else np.abs(Bm))
         err = np.abs(D.cpu().numpy() - target) / scale
         assert err.max() < tol, (passes, float(err.max()))
 
