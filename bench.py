@@ -11,10 +11,13 @@ Workloads (synthetic seeded positions, random-init weigh
 A step = one pass of the hot path: device neighbour list (cell list) -> CSR -> L layers -> read-out -> analytic
 forces.  `value` times steps with the positions already resident in HBM (CUDA events, max over ranks);
 `e2e` times the public calculator call with HOST numpy buffers (pinned H2D of positions, D2H of energy+forces).
-N > 1: the path has no collective in this round -- every rank runs an independent replica of the workload
-("replicas", weak scaling); domain decomposition of c4 with halo exchange is the next multi-GPU row.
+N > 1, periodic workloads: ONE system is decomposed into bricks (mlff_b200/dist.py: owned + ghost atoms, mirror edges, a
+halo exchange of feature rows per layer and direction over NCCL) -- strong scaling, labelled so at every N including
+N = 1; `--parallel replicas` (and the molecular workload c1) runs an independent copy per rank instead (weak scaling).
 `--impl reference`: the reference is pure Python on JAX (not installable here), so the arm times the float32
 oracle restatement (torch-CPU, all host threads) on a bounded sub-box of the same workload.
+The filter GEMMs run on tcgen05 (split-bf16); shapes the tensor-core kernels do not cover make the run FAIL unless
+`--fp32-simt` asks for the fp32 CUDA-core kernels explicitly -- there is no silent change of code path.
 """
 from __future__ import annotations
 
@@ -172,7 +175,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = min(w['n_atoms'], 2000)
+    n_sample = min(w['n_atoms'], 10_000)          # the O(N) model scales linearly; 10k atoms is what the CPU finishes in seconds
     step, n_sample, n_edges = oracle_sample(w, n_sample, threads)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
@@ -183,9 +186,12 @@ def run_reference(args, w):
     val = n_sample / dt
     line = {'impl': 'reference', 'metric': 'SO3krates energy+force atom-steps/s', 'value': val, 'unit': 'atom-steps/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'description': w['desc'], 'F': w['F'], 'n_layers': w['L'],
-                       'degrees': list(w['degrees']), 'r_cut': 5.0},
+            'higher_is_better': True, 'scaling': 'strong' if (w['box'] is not None and args.parallel != 'replicas') else 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'description': w['desc'], 'n_atoms': int(n_sample), 'n_edges': int(n_edges),
+                       'n_atoms_full_workload': int(w['n_atoms']), 'F': w['F'], 'n_layers': w['L'],
+                       'degrees': list(w['degrees']), 'r_cut': 5.0,
+                       'parallelism': 'host threads (torch-CPU), rank 0 only'},
             'cpu_baseline': {'value': val, 'unit': 'atom-steps/s', 'cores': threads, 'kind': 'port',
                              'sample': f'{n_sample}-atom sub-box at the workload density ({n_edges} edges), float32 oracle '
                                        f'restatement on torch-CPU (the JAX reference is not installable here)'},
@@ -217,13 +223,9 @@ def run_ours(args, w):
         if k.endswith('/bias'):
             prm[k] = rng.normal(0, 0.01, prm[k].shape).astype(np.float32)
     flags = 0 if args.fp32_simt else (1 if args.no_keep_filters else 3)
-    try:
-        calc = mlffCalculator(cfg, prm, device=dev, flags=flags)
-    except Exception:
-        if not flags:
-            raise
-        flags = 0                                   # shapes outside the tensor-core kernels' limits (e.g. F=256)
-        calc = mlffCalculator(cfg, prm, device=dev, flags=flags)
+    # no fallback: a shape outside the tensor-core kernels' limits raises So3kError(SO3K_ERR_CONFIG) here; the fp32
+    # CUDA-core kernels are a different code path and must be asked for with --fp32-simt
+    calc = mlffCalculator(cfg, prm, device=dev, flags=flags)
     args.tensor = bool(flags)
     eng = calc.engine
     pos, z, cell, pbc = build_inputs(w, rank)
@@ -248,7 +250,8 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_dd = world > 1 and periodic and args.parallel in ('auto', 'dd')
+    dd_workload = periodic and args.parallel in ('auto', 'dd')      # one system split over the ranks (strong scaling)
+    use_dd = world > 1 and dd_workload
     if use_dd:
         # ---- spatial domain decomposition: every rank holds the (replicated) positions, builds the full neighbour
         # list, keeps the rows of its slab + mirror edges, and exchanges ghost rows once per layer and direction
@@ -485,27 +488,32 @@ def run_ours(args, w):
                          (4 * 8 + 4 + 16) * p_rank + (8 * Fd + 8 * M_ + 4) * n_rank + 4 * Fd * n_rank,
                          'compulsory bytes (DESIGN.md)'),
             ]
-        # DRAM bytes per scope from the round's `ncu --set full` captures of THIS workload on one GPU
-        # (profiles/r01h_<kernel>_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch x launches per scope)
-        if args.tensor and args.workload == 'c4' and world == 1 and not args.no_keep_filters:
-            ncu_traffic = {'k_edge_bwd2_tc': 2 * (1.589e9 + 0.061e9), 'k_filter_tc': 2 * (0.085e9 + 1.334e9),
-                           'k_qk_bwd_stream': 4.865e9 + 3.031e9, 'k_alpha_aggregate': 4.853e9 + 0.577e9,
-                           'k_alpha_bwd': 0.436e9 + 0.207e9}
-            for r_ in roofs:
-                for k_, v_ in ncu_traffic.items():
-                    if r_['kernel'].startswith(k_ + ' ') or r_['kernel'] == k_:
-                        r_['traffic'] = v_
+        # `traffic` (ncu dram__bytes_read + dram__bytes_write per scope) cannot be measured inside this run (a number taken
+        # under a profiler is not a bench value): it is filled from profiles/ncu_traffic.json, written by
+        # profiles/summarize_traffic.py from `ncu --set full` captures of THIS workload, and only when that file names the
+        # build it was captured on (sha256 of libso3k.so); otherwise it stays null.
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+        if os.path.exists(tpath) and world == 1:
+            import hashlib
+            from mlff_b200 import _lib as _l
+            tj = json.load(open(tpath))
+            sha = hashlib.sha256(open(_l.LIB_PATH, 'rb').read()).hexdigest()[:16]
+            if tj.get('lib_sha16') == sha and tj.get('workload') == args.workload:
+                for r_ in roofs:
+                    for k_, v_ in tj.get('bytes_per_scope', {}).items():
+                        if r_['kernel'].startswith(k_ + ' ') or r_['kernel'] == k_:
+                            r_['traffic'] = v_
         roofs.sort(key=lambda r: -r['share_of_step'])
         roof, agg = roofs[0], roofs[1:]          # `roofline` = the kernel with the largest share of the step
         # CPU baseline: bounded sample, all host threads
         threads = os.cpu_count() or 1
         cpu = None
         if not args.no_cpu_baseline:
-            n_s = min(N, 2000)
+            n_s = min(N, 10_000)
             step, n_s, n_e = oracle_sample(w, n_s, threads)
             step()
             reps, t0 = 0, time.perf_counter()
-            while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 50):
                 step()
                 reps += 1
             dt = (time.perf_counter() - t0) / reps
@@ -514,7 +522,7 @@ def run_ours(args, w):
                              f'float32 oracle restatement on torch-CPU (JAX reference not installable)'}
         line = {'metric': 'SO3krates energy+force atom-steps/s', 'value': value, 'unit': 'atom-steps/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
-                'scaling': 'strong' if use_dd else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'scaling': 'strong' if dd_workload else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': {'workload': args.workload, 'description': w['desc'], 'n_atoms': N, 'n_edges': int(n_edges),
                            'F': w['F'], 'n_layers': w['L'], 'degrees': list(w['degrees']), 'r_cut': 5.0,
                            'parallelism': 'single' if world == 1 else (

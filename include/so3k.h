@@ -226,10 +226,13 @@ int so3k_featurise(const so3k_handle* h, int32_t n, int32_t P,
  * and pbc[3] are small HOST arrays (they size the bin grid, like scalar arguments); cutoff f64.
  * mode SO3K_NL_ASE  : all images, |R_j - R_i + S@cell| <  cutoff, (i != j or S != 0)   [indices.py:216-224]
  * mode SO3K_NL_DENSE: non-periodic, 0 < d <= cutoff, z_i * z_j != 0 (z may be NULL)      [indices.py:56-60]
+ * mode SO3K_NL_MIC  : minimum-image list of the MD path: one image per ordered pair i != j -- the one whose fractional
+ *                     displacement lies in [-1/2, 1/2) on the periodic axes --, d < cutoff; `shifts` holds that image
+ *                     (glp quadratic_neighbor_list + make_displacement, mlff/mdx/atoms.py:488-529, md/calculator.py:204-238)
  * Output (device): idx_i, idx_j (capacity) i32 padded with -1, shifts (capacity,3) i32 padded
  * with 0, sorted by i then (j, S); *count (device int64) = number of edges found (may exceed capacity, in
  * which case SO3K_STATUS_OVERFLOW is set and only the first `capacity` edges are stored). */
-enum { SO3K_NL_ASE = 0, SO3K_NL_DENSE = 1 };
+enum { SO3K_NL_ASE = 0, SO3K_NL_DENSE = 1, SO3K_NL_MIC = 2 };
 size_t so3k_neighbor_list_workspace_bytes(int64_t N, int64_t capacity);
 int so3k_neighbor_list(int32_t mode, int64_t N, const double* positions, const int32_t* z,
                        const double* cell, const uint8_t* pbc, double cutoff, int64_t capacity,

@@ -27,6 +27,7 @@ FLAG_RESIDUAL_MLP_2 = 32 # So3kratesLayer(residual_mlp_2=True)
 FLAG_FINAL_LAYER = 64    # So3kratesLayer(final_layer=True): post LayerNorm (with FLAG_LAYER_NORM)
 NL_ASE = 0
 NL_DENSE = 1
+NL_MIC = 2
 
 # every symbol include/so3k.h declares (checked by tests/test_capi.py)
 EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 'so3k_param_lookup',

@@ -186,6 +186,23 @@ SO3K_HD static inline int so3k_spw(int F) { return ((F + 7) & ~7) + 8; }
 struct HeadReducer {
   int k, a, f0, len;        // edge of the batch, head slot, feature range [f0, f0 + len)
   bool split, owner;        // two lanes per sum ; this lane writes the result
+  // sum of the staged products of this lane's range: four independent chains, so the shared-memory loads pipeline
+  // instead of forming one load -> add -> load chain
+  __device__ __forceinline__ float sum(const float* __restrict__ s_w) const {
+    const float* sp = s_w + f0;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int t = 0;
+    for (; t + 4 <= len; t += 4) {
+      s0 += sp[t];
+      s1 += sp[t + 1];
+      s2 += sp[t + 2];
+      s3 += sp[t + 3];
+    }
+    if (t < len) s0 += sp[t];
+    if (t + 1 < len) s1 += sp[t + 1];
+    if (t + 2 < len) s2 += sp[t + 2];
+    return (s0 + s1) + (s2 + s3);
+  }
 };
 
 // Tensor-core path: attention coefficients from the pair-indexed filters, fused with both aggregations.
@@ -291,9 +308,7 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
       }
       __syncwarp();
       {
-        float sum = 0.f;
-        const float* sp = &s_w[hr.f0];
-        for (int t = 0; t < hr.len; ++t) sum += sp[t];
+        float sum = hr.sum(s_w);
         if (hr.split) sum += __shfl_xor_sync(0xffffffffu, sum, 16);
         if (hr.owner && q + hr.k < cnt) s_a[w][(q + hr.k) * Ast + hr.a] = sum * hr_scale * s_ph[w][q + hr.k];
       }
@@ -420,9 +435,7 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
       }
       __syncwarp();
       {
-        float sum = 0.f;
-        const float* sp = &s_w[hr.f0];
-        for (int t = 0; t < hr.len; ++t) sum += sp[t];
+        float sum = hr.sum(s_w);
         if (hr.split) sum += __shfl_xor_sync(0xffffffffu, sum, 16);
         if (hr.owner && q + hr.k < cnt) s_o[w][(q + hr.k) * Ast + hr.a] = sum;
       }

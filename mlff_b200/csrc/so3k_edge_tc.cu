@@ -136,7 +136,12 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
 // ---- weight images (built once at so3k_load_params) -------------------------------------------------------
 // global image == shared-memory layout: [W1 hi | W1 lo | W2c hi | W2c lo], then fp32 small arrays
 // [b1x (KC) | b2p (Fp) | Wsx (nl x KC)]: b1x = [rad_b1 (F) | sph_b1 (Fs) | 0] indexed like the hidden units (K index of
-// GEMM2), Wsx[l][c] = sph_W1[l][c - F] for the spherical hidden units F <= c < F + Fs, 0 elsewhere
+// GEMM2), Wsx[l][c] = sph_W1[l][c - F] for the spherical hidden units F <= c < F + Fs, 0 elsewhere.
+// Everything that feeds a pre-activation (W1, b1, Ws1, bs1) is stored times -log2(e) and W2c times -ln(2): the kernels then
+// work with a' = -log2(e) a, for which sigmoid(a) = 1 / (1 + 2^a') needs no multiply in front of the MUFU.EX2, and
+// y' = a' sigmoid(a) = -log2(e) silu(a) meets the -ln(2) of W2c, so w = y' @ W2c' is unchanged.  The backward's sums
+// hbar' dy t'' and hbar' dy Wsx' carry the factor ln(2) log2(e) = 1 (see k_edge_bwd2_tc).
+constexpr float kNegLog2e = -1.4426950408889634f, kNegLn2 = -0.6931471805599453f, kLn2 = 0.6931471805599453f;
 __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ rW1, const float* __restrict__ rb1,
                                const float* __restrict__ rW2, const float* __restrict__ rb2,
                                const float* __restrict__ sW1, const float* __restrict__ sb1,
@@ -147,7 +152,7 @@ __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ r
   // W1 image: rows n = hidden unit (Fp), cols k (K0): value rad_W1[k][n]
   if (t < T.Fp * T.K0) {
     int n = t / T.K0, k = t % T.K0;
-    float v = (n < F) ? rW1[(size_t)k * F + n] : 0.f;
+    float v = (n < F) ? kNegLog2e * rW1[(size_t)k * F + n] : 0.f;
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
     uint32_t off = tc::canon_off(n, k >> 3, T.sboW1) + (uint32_t)(k & 7) * 2u;
@@ -159,8 +164,8 @@ __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ r
     int n = t / T.KC, c = t % T.KC;
     float v = 0.f;
     if (n < F) {
-      if (c < F) v = rW2[(size_t)c * F + n];
-      else if (c - F < D.Fs) v = sW2[(size_t)(c - F) * F + n];
+      if (c < F) v = kNegLn2 * rW2[(size_t)c * F + n];
+      else if (c - F < D.Fs) v = kNegLn2 * sW2[(size_t)(c - F) * F + n];
     }
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -168,11 +173,11 @@ __global__ void k_build_images(So3kDims D, TcDims T, const float* __restrict__ r
     *reinterpret_cast<__nv_bfloat16*>(img + T.off_W2 + off) = h;
     *reinterpret_cast<__nv_bfloat16*>(img + T.off_W2 + T.szW2 + off) = l;
   }
-  if (t < T.KC) small[t] = (t < F) ? rb1[t] : (t - F < D.Fs ? sb1[t - F] : 0.f);
+  if (t < T.KC) small[t] = kNegLog2e * ((t < F) ? rb1[t] : (t - F < D.Fs ? sb1[t - F] : 0.f));
   if (t < T.Fp) small[T.KC + t] = (t < F) ? rb2[t] + sb2[t] : 0.f;
   if (t < D.nl * T.KC) {
     int l = t / T.KC, c = t % T.KC;
-    small[T.KC + T.Fp + t] = (c >= F && c - F < D.Fs) ? sW1[(size_t)l * D.Fs + (c - F)] : 0.f;
+    small[T.KC + T.Fp + t] = (c >= F && c - F < D.Fs) ? kNegLog2e * sW1[(size_t)l * D.Fs + (c - F)] : 0.f;
   }
 }
 
@@ -186,14 +191,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// s_i = 1 / (1 + exp(-a_i)) for four values with four MUFU.EX2 and ONE MUFU.RCP: the reciprocal of the product of the
-// four denominators, unfolded with 9 multiplies.  The exponent is clamped at 2^30 so that the product stays finite
-// (silu(a) for a < -20.8 is then a * 2^-30 instead of a * e^a: an absolute error below 2e-8).  Relative error ~4e-7.
+// s_i = 1 / (1 + 2^a_i) (= sigmoid of the un-scaled pre-activation, a_i = -log2(e) x_i) for four values with four
+// MUFU.EX2 and ONE MUFU.RCP: the reciprocal of the product of the four denominators, unfolded with 9 multiplies.  The
+// exponent is clamped at 30 so that the product stays finite (silu(x) for x < -20.8 is then x * 2^-30 instead of
+// x * e^x: an absolute error below 2e-8).  Relative error ~4e-7.
 __device__ __forceinline__ void sigmoid4(const float* a, float* s) {
-  const float t0 = 1.0f + ex2_approx(fminf(-1.4426950408889634f * a[0], 30.0f));
-  const float t1 = 1.0f + ex2_approx(fminf(-1.4426950408889634f * a[1], 30.0f));
-  const float t2 = 1.0f + ex2_approx(fminf(-1.4426950408889634f * a[2], 30.0f));
-  const float t3 = 1.0f + ex2_approx(fminf(-1.4426950408889634f * a[3], 30.0f));
+  const float t0 = 1.0f + ex2_approx(fminf(a[0], 30.0f));
+  const float t1 = 1.0f + ex2_approx(fminf(a[1], 30.0f));
+  const float t2 = 1.0f + ex2_approx(fminf(a[2], 30.0f));
+  const float t3 = 1.0f + ex2_approx(fminf(a[3], 30.0f));
   const float p01 = t0 * t1, p23 = t2 * t3;
   const float r = rcp_approx(p01 * p23);
   const float r01 = r * p23, r23 = r * p01;
@@ -334,6 +340,7 @@ __device__ __forceinline__ void tc_row_s0(const So3kDims& D, const TcDims& T, un
                                           int r, bool valid, float d, uint32_t tAI_lane) {
   const float ed = __expf(-d);
   const float ng = -D.gamma * 1.4426950408889634f;
+#pragma unroll 4
   for (int c = 0; c < T.K0 / 8; ++c) {
     float v[8], dv[8];
 #pragma unroll
@@ -526,26 +533,28 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
         group_bar(1, N_AUX);
         const int nu = T.Fp >> 4;
         float* srow = stage + (size_t)r * F;
-        uint32_t v[2][16];
-        tc::tmem_ld16(tD2 + lane_sel, v[0]);
+        // batches of three 16-column units: the three loads queue back to back at the tensor-memory port
 #pragma unroll
-        for (int u = 0; u < 10; ++u) {                               // Fp <= 160: at most 10 units (compile-time buffer index)
-          if (u < nu) {
-            if (u + 1 < nu) {
-              tc::tmem_ld16(tD2 + lane_sel + (uint32_t)(16 * (u + 1)), v[(u + 1) & 1]);
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-              tc::tmem_ld_wait();
-            }
-            const uint32_t* vv = v[u & 1];
+        for (int u0 = 0; u0 < 12; u0 += 3) {                         // Fp <= 160: at most 10 units
+          if (u0 < nu) {
+            uint32_t v[3][16];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int c = 16 * u + 4 * q4;
-              if (c < F) {                                           // F % 4 == 0: whole float4s
-                const float4 b = *reinterpret_cast<const float4*>(S.b2p + c);
-                *reinterpret_cast<float4*>(srow + c) =
-                    make_float4(__uint_as_float(vv[4 * q4]) + b.x, __uint_as_float(vv[4 * q4 + 1]) + b.y,
-                                __uint_as_float(vv[4 * q4 + 2]) + b.z, __uint_as_float(vv[4 * q4 + 3]) + b.w);
+            for (int k = 0; k < 3; ++k)
+              if (u0 + k < nu) tc::tmem_ld16(tD2 + lane_sel + (uint32_t)(16 * (u0 + k)), v[k]);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (u0 + k < nu) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const int c = 16 * (u0 + k) + 4 * q4;
+                  if (c < F) {                                       // F % 4 == 0: whole float4s
+                    const float4 b = *reinterpret_cast<const float4*>(S.b2p + c);
+                    *reinterpret_cast<float4*>(srow + c) =
+                        make_float4(__uint_as_float(v[k][4 * q4]) + b.x, __uint_as_float(v[k][4 * q4 + 1]) + b.y,
+                                    __uint_as_float(v[k][4 * q4 + 2]) + b.z, __uint_as_float(v[k][4 * q4 + 3]) + b.w);
+                  }
+                }
               }
             }
           }
@@ -585,6 +594,49 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
   if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// One warp's share of the filter-cotangent operand image of a tile (bf16 hi / lo, canonical K-major layout in shared
+// memory) from the tile's contiguous block of pair rows: work item = (8 rows, 4 chunks of 8 columns), lane -> (row =
+// lane / 4, chunk = lane % 4); warp `wq` of `nwarps` takes items wq, wq + nwarps, ..; all loads are issued before the
+// first split (the block was prefetched into L2 a tile earlier).
+__device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int wq, int nwarps, int lane, int e0, int ne,
+                                              const float* __restrict__ wbar, unsigned char* Wbhi, unsigned char* Wblo) {
+  const int nchunkF = T.Fp / 8;
+  const int ncg = (nchunkF + 3) / 4;
+  const int nitems = 16 * ncg;
+  constexpr int BATCH = 5;                     // 16 warps: 16 * ceil(Fp / 32) / 16 <= 5 items per warp for Fp <= 160
+  for (int it0 = wq; it0 < nitems; it0 += nwarps * BATCH) {
+    float4 wa[BATCH], wb2[BATCH];
+#pragma unroll
+    for (int v = 0; v < BATCH; ++v) {
+      const int item = it0 + nwarps * v;
+      wa[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      wb2[v] = wa[v];
+      if (item < nitems) {
+        const int rg = item / ncg, cg = item - rg * ncg;
+        const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
+        const int f0 = c * 8;
+        if (c < nchunkF && f0 < F && rr < ne) {
+          const float* src = wbar + (size_t)(e0 + rr) * F + f0;
+          wa[v] = __ldcs(reinterpret_cast<const float4*>(src));
+          if (f0 + 4 < F) wb2[v] = __ldcs(reinterpret_cast<const float4*>(src + 4));
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < BATCH; ++v) {
+      const int item = it0 + nwarps * v;
+      if (item < nitems) {
+        const int rg = item / ncg, cg = item - rg * ncg;
+        const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
+        if (c < nchunkF) {
+          const float wv[8] = {wa[v].x, wa[v].y, wa[v].z, wa[v].w, wb2[v].x, wb2[v].y, wb2[v].z, wb2[v].w};
+          tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rr, c, T.sboWb), wv);
+        }
+      }
+    }
+  }
+}
+
 // Backward part 2: radial cotangent and l0-contraction cotangent of one filter block.
 // Rows are canonical pairs; the pair's filter cotangent wbar[c][f] comes from k_qk_bwd_stream as a contiguous tile.
 //   hbar = wbar @ W2c^T                                                 (GEMM3: the W2c image consumed MN-major)
@@ -593,11 +645,15 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
 // Tensor-memory columns: a1 at 0 (N = Fp) | forward-mode derivative at F (N = Fp; its first padding columns overwrite
 // a1's padding, harmless) | hbar at 2F (N = KC, written after the two GEMM1s) | rbf' operand image (K0 columns).
 // Warp-specialised like the filter kernel:
-//   helper group (4 warps), tile i:    wait GEMM3(i-1) | wbar operand image (i) | radial-basis images (i) |
-//                                      wait epilogue(i-1) done -> issue the GEMM1s and GEMM3 (three column chunks, one
-//                                      completion barrier each) | prefetch of the next cotangent tile into L2
-//   epilogue group (12 warps), tile i: per 16-column unit: wait its chunk | silu' epilogue | slots -> group barrier ->
-//                                      totals to the canonical edge | arrive epilogue-done
+//   helper group (4 warps), tile i:    wait GEMM3(i-1) | radial-basis images (i) | wait epilogue(i-1) done -> issue the
+//                                      GEMM1s | its share of the wbar operand image | wait image-ready -> issue GEMM3
+//                                      (three column chunks, one completion barrier each) | prefetch of the next
+//                                      cotangent tile into L2
+//   epilogue group (12 warps), tile i: its share of the wbar operand image (i) -> arrive image-ready | per 16-column
+//                                      unit: wait its chunk | silu' epilogue | slots -> group barrier -> totals to the
+//                                      canonical edge | arrive epilogue-done
+// (all 16 warps build the operand image: with only the helper warps loading, the L2 latency of their few batches was
+// exposed four times per tile)
 template <int NL>
 __global__ void __launch_bounds__(NT, 1)
 k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, const int* __restrict__ n_canon,
@@ -605,7 +661,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
                const float* __restrict__ small_g, const float* __restrict__ wbar, float* __restrict__ gbar,
                float* __restrict__ ebar, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bars[5];                  // 0: GEMM1s ; 1..3: GEMM3 chunks ; 4: epilogue done (N_EPI arrivals)
+  __shared__ uint64_t bars[6];                  // 0: GEMM1s ; 1..3: GEMM3 chunks ; 4: epilogue done (N_EPI) ; 5: image ready (NT)
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_abort;
 
@@ -623,6 +679,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   if (tid == 0) {
     for (int k = 0; k < 4; ++k) tc::mbar_init(&bars[k], 1);
     tc::mbar_init(&bars[4], N_EPI);
+    tc::mbar_init(&bars[5], NT);
     tc::mbar_fence_init();
     s_abort = 0;
   }
@@ -640,7 +697,6 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   const int n_tiles = (nv + TM - 1) / TM;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int G = (int)gridDim.x;
-  const int nchunkF = T.Fp / 8;
   const int nks = T.KC >> 4;                                       // 16-wide hidden-column units; chunk ch = units 4ch .. 4ch+3
   const int nch = (nks + 3) >> 2;
 
@@ -652,6 +708,11 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
       const int ne = (nv - e0) < TM ? (nv - e0) : TM;
       const uint32_t par = (uint32_t)(i & 1);
       const RowRec<NL> rc = tc_load_rec<NL>(e0 + r, nv, rec);
+      // this warp's share of the cotangent operand image, once the last chunk of the previous tile's GEMM3 has read the old one
+      if (i > 0) tc_wait(&bars[nch], (uint32_t)((i - 1) & 1), &s_abort);
+      tc_wbar_image(T, F, warp, 16, lane, e0, ne, wbar, Wbhi, Wblo);
+      tc::fence_async_smem();
+      mbar_arrive(&bars[5]);
       // canonical edge of this row and, for the second block's launch, the totals already there (loaded early: their
       // latency hides under the epilogue)
       const bool writer = cq == 0 && r < ne;
@@ -698,7 +759,8 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
             sigmoid4(a + 4 * q4, s);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float dy = s[q] * fmaf(a[4 * q4 + q], 1.0f - s[q], 1.0f);
+              // silu'(x) = s (1 + x (1 - s)) with x = -ln(2) a'
+              const float dy = s[q] * fmaf(a[4 * q4 + q], fmaf(s[q], kLn2, kNegLn2), 1.0f);
               dbar = fmaf(__uint_as_float(hb[4 * q4 + q]) * dy, __uint_as_float(tp[4 * q4 + q]), dbar);
             }
           }
@@ -711,7 +773,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int c = c0 + 4 * q4 + q;
-              const float dy = s[q] * fmaf(a[4 * q4 + q], 1.0f - s[q], 1.0f);
+              const float dy = s[q] * fmaf(a[4 * q4 + q], fmaf(s[q], kLn2, kNegLn2), 1.0f);
               as4[q] = (c < F + Fs) ? __uint_as_float(hb[4 * q4 + q]) * dy : 0.f;
               if (c < F) dbar = fmaf(as4[q], __uint_as_float(tp[4 * q4 + q]), dbar);
             }
@@ -750,7 +812,6 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   } else {
     // ================= helper group ================================================================================
     const bool issuer = tid == ISSUER;
-    const int hw = warp - 12;                                      // warp of the helper group
     auto prefetch_wbar = [&](int e0) {                             // a tile's contiguous block of filter cotangents -> L2
       if (e0 < nv) {
         const int nrow = (nv - e0) < TM ? (nv - e0) : TM;
@@ -770,52 +831,13 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         tc_wait(&bars[nch], (uint32_t)((i - 1) & 1), &s_abort);
       }
       TC_PHASE(2, 0);
-      // ---- wbar operand image from the tile's contiguous block of pair rows: work item = (8 rows, 4 chunks of 8 columns),
-      //      lane -> (row = lane / 4, chunk = lane % 4); batches of 5 items per warp with all loads issued first
-      {
-        const int ncg = (nchunkF + 3) / 4;
-        const int nitems = 16 * ncg;
-        constexpr int BATCH = 5;
-        for (int it0 = hw; it0 < nitems; it0 += 4 * BATCH) {
-          float4 wa[BATCH], wb2[BATCH];
-#pragma unroll
-          for (int v = 0; v < BATCH; ++v) {
-            const int item = it0 + 4 * v;
-            wa[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            wb2[v] = wa[v];
-            if (item < nitems) {
-              const int rg = item / ncg, cg = item - rg * ncg;
-              const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
-              const int f0 = c * 8;
-              if (c < nchunkF && f0 < F && rr < ne) {
-                const float* src = wbar + (size_t)(e0 + rr) * F + f0;
-                wa[v] = __ldcs(reinterpret_cast<const float4*>(src));
-                if (f0 + 4 < F) wb2[v] = __ldcs(reinterpret_cast<const float4*>(src + 4));
-              }
-            }
-          }
-#pragma unroll
-          for (int v = 0; v < BATCH; ++v) {
-            const int item = it0 + 4 * v;
-            if (item < nitems) {
-              const int rg = item / ncg, cg = item - rg * ncg;
-              const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
-              if (c < nchunkF) {
-                const float wv[8] = {wa[v].x, wa[v].y, wa[v].z, wa[v].w, wb2[v].x, wb2[v].y, wb2[v].z, wb2[v].w};
-                tc::store_chunk8(Wbhi, Wblo, tc::canon_off(rr, c, T.sboWb), wv);
-              }
-            }
-          }
-        }
-      }
-      TC_PHASE(2, 1);
       // ---- radial-basis images of this tile: rbf -> shared memory, rbf' -> tensor memory -----------------------------------
       tc_row_s0<true>(D, T, A0hi, A0lo, r, e0 + r < nv, rc.d, tAI + lane_sel);
       tc::tmem_st_wait();
       tc::fence_async_smem();
       tc::fence_before_sync();
       group_bar(1, N_AUX);
-      TC_PHASE(2, 2);
+      TC_PHASE(2, 1);
       if (issuer) {
         // the epilogue group has drained the accumulators of tile i - 1
         if (i > 0) tc_wait(&bars[4], (uint32_t)((i - 1) & 1), &s_abort);
@@ -824,6 +846,15 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         tc_issue_gemm_ss(tD1, A0hi, A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
         tc_issue_gemm_ts(tD1p, tAI, tAI + (uint32_t)(T.K0 / 2), 8u, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
         tc::commit(&bars[0]);
+      }
+      // ---- this warp's share of the cotangent operand image ---------------------------------------------------------------
+      tc_wbar_image(T, F, warp, 16, lane, e0, ne, wbar, Wbhi, Wblo);
+      tc::fence_async_smem();
+      mbar_arrive(&bars[5]);
+      TC_PHASE(2, 2);
+      if (issuer) {
+        tc_wait(&bars[5], (uint32_t)(i & 1), &s_abort);
+        tc::fence_after_sync();
         // GEMM3: hbar[128 x KC] = wbar[128 x Fp] @ W2c^T, in chunks of 64 hidden units with one commit each
         const uint32_t ah = tc::smem_u32(Wbhi), al = tc::smem_u32(Wblo), bh = tc::smem_u32(S.W2hi), bl = tc::smem_u32(S.W2lo);
         for (int ch = 0; ch < nch; ++ch) {
@@ -958,7 +989,7 @@ extern "C" void so3k_tc_phase_dump(void) {
       {"helper: wait GEMM1(i+1)", "rbf image (i+2) + barrier", "issue GEMM1 + wait GEMM2(i)", "epilogue2 (i)", "barrier + bulk store",
        "wait a1_ready + issue GEMM2", "-", "-", "epilogue group: wait GEMM1", "epilogue group: epilogue 1", "-", "-", "-"},
       {"-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"},
-      {"helper: wait GEMM3(i-1)", "wbar image", "rbf images + barrier", "wait epilogue(i-1) + issue MMAs", "-", "-", "-", "-",
+      {"helper: wait GEMM3(i-1)", "rbf images + barrier", "share of the wbar image", "issue GEMM3 + prefetch", "-", "-", "-", "-",
        "epilogue group: wait GEMM1s + chunk 0", "epilogue group: epilogue", "-", "-", "-"}};
   for (int k = 0; k < 3; ++k) {
     if (!h[k][15]) continue;

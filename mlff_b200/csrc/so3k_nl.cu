@@ -7,6 +7,8 @@
 //         axes, cell rows = lattice vectors                                                      [SO3K_NL_ASE]
 //   get_indices                            mlff/indexing/indices.py:56-60
 //       non-periodic, 0 < d <= cutoff (inclusive), z_i * z_j != 0, row-major order              [SO3K_NL_DENSE]
+//       minimum-image list of the MD path (glp quadratic_neighbor_list, mlff/mdx/atoms.py:488-529): one image per
+//       ordered pair i != j, fractional displacement wrapped to [-1/2, 1/2), d < cutoff           [SO3K_NL_MIC]
 // Output rows are sorted by i, then by (j, S) -- the reference's order for the dense list, and a canonical order
 // for the ASE list (whose consumers are order-independent: segment_sum).  Padding: idx = -1, shifts = 0
 // (indices.py:226-231); when more than `capacity` edges exist SO3K_STATUS_OVERFLOW is raised and *count holds
@@ -340,6 +342,16 @@ k_pairs(int N, int mode, double cutoff, const NLGrid* __restrict__ Gp, const dou
             double d = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
             if (mode == SO3K_NL_ASE) {
               hit = (d < cutoff) && !(j == i && S0 == 0 && S1 == 0 && S2 == 0);
+            } else if (mode == SO3K_NL_MIC) {
+              // glp quadratic_neighbor_list + make_displacement (mlff/mdx/atoms.py:488-529): ONE image per ordered pair,
+              // the one whose fractional displacement lies in [-1/2, 1/2) on the periodic axes (frac -= floor(frac + 1/2))
+              const double f0 = dx * G.inv[0] + dy * G.inv[3] + dz * G.inv[6];
+              const double f1 = dx * G.inv[1] + dy * G.inv[4] + dz * G.inv[7];
+              const double f2 = dx * G.inv[2] + dy * G.inv[5] + dz * G.inv[8];
+              const bool m0 = !G.pbc[0] || (f0 >= -0.5 && f0 < 0.5);
+              const bool m1 = !G.pbc[1] || (f1 >= -0.5 && f1 < 0.5);
+              const bool m2 = !G.pbc[2] || (f2 >= -0.5 && f2 < 0.5);
+              hit = (d < cutoff) && (j != i) && m0 && m1 && m2;
             } else {
               int zj = z ? z[j] : 1;
               hit = (d <= cutoff) && (d > 0.0) && (zi != 0) && (zj != 0);
@@ -499,7 +511,7 @@ int so3k_neighbor_list(int32_t mode, int64_t N, const double* positions, const i
                        void* stream) {
   if (N <= 0 || N > 0x3fffffff || !positions || !(cutoff > 0.0) || capacity < 0 || capacity > 0x7fffffff) return SO3K_ERR_ARG;
   if (!idx_i || !idx_j || !shifts || !workspace) return SO3K_ERR_ARG;
-  if (mode != SO3K_NL_ASE && mode != SO3K_NL_DENSE) return SO3K_ERR_ARG;
+  if (mode != SO3K_NL_ASE && mode != SO3K_NL_DENSE && mode != SO3K_NL_MIC) return SO3K_ERR_ARG;
   if (workspace_bytes < so3k_neighbor_list_workspace_bytes(N, capacity)) return SO3K_ERR_WORKSPACE;
   NLSetup S;
   unsigned char nopbc[3] = {0, 0, 0};

@@ -44,7 +44,7 @@ k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A
       for (int q = 0; q < 8; ++q) v[q] = B[(size_t)r * imgCols + c * 8 + q];
       tc::store_chunk8(Bhi, Blo, tc::canon_off(r, c, sboB), v);
     }
-  if (variant >= 3) {                              // zero A image for the TMEM clear of the layout probe
+  if (variant == 3 || variant == 4) {              // zero A image for the TMEM clear of the layout probe
     for (uint32_t o = (uint32_t)tid * 16u; o < szA; o += 128u * 16u) *reinterpret_cast<uint4*>(Alo + o) = make_uint4(0, 0, 0, 0);
   }
   tc::fence_async_smem();
@@ -52,7 +52,7 @@ k_tc_selftest(int N, int K, int variant, int passes, const float* __restrict__ A
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0 && variant >= 3) {
+  if (tid == 0 && (variant == 3 || variant == 4)) {
     // Layout probe for M = 64 (round-2 groundwork: two 64-row half tiles per CTA).  TMEM is first zeroed by an
     // M = 128 MMA on an all-zero A image (the lo image, overwritten with zeros below by every thread before the
     // barrier when variant >= 3), then ONE M = 64 GEMM on rows 0..63 of A is written at lane offset 0 (variant 3) or

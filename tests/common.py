@@ -41,3 +41,20 @@ def engine_flags(cfg) -> int:
     if getattr(cfg, 'residual_mlp_2', False):
         f |= FLAG_RESIDUAL_MLP_2
     return f
+
+
+def check_mic_list(oracle_mod, pos, cell, pbc, cutoff, ii, jj, S, cnt):
+    """Device minimum-image list (SO3K_NL_MIC) against oracle.mic_neighbor_list (glp quadratic_neighbor_list +
+    make_displacement semantics, mlff/mdx/atoms.py:488-529): the same ordered pairs, one image each, sorted by (i, j),
+    and the image the shift selects reproduces the oracle's minimum-image displacement."""
+    import numpy as np
+    pos = np.asarray(pos, np.float64)
+    cell_full = None if cell is None else np.asarray(cell, np.float64)
+    oi, oj, odv = oracle_mod.mic_neighbor_list(pos, cell_full, cutoff, pbc=pbc)
+    assert cnt == len(oi), (cnt, len(oi))
+    ii, jj, S = ii[:cnt], jj[:cnt], S[:cnt]
+    assert (ii == oi).all() and (jj == oj).all()
+    dv = pos[jj] - pos[ii] + (S @ cell_full if cell_full is not None else 0.0)
+    np.testing.assert_allclose(dv, odv, atol=1e-10)
+    assert len(set(zip(ii.tolist(), jj.tolist()))) == cnt            # a single image per ordered pair
+    return oi, oj, odv

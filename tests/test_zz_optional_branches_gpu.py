@@ -16,14 +16,17 @@ F_ATOL = 1e-4
 
 
 def tolerances(flags, f_max):
-    """fp32 mode: north_star's tolerances as they stand.  Tensor mode: the split-bf16 filters carry a relative error of
-    about 1e-5 into the forces (default model: 3.6e-6 eV/A on 0.41 eV/A forces).  LayerNorm re-normalises the features,
-    so these random-weight models have 5-11 eV/A forces and the same RELATIVE error exceeds 1e-4 eV/A absolute
-    (measured: profiles/r01k_optional_branch_errors.txt); the tensor mode is therefore held to 4e-5 of the largest
-    force (and 1e-4 eV/A below 2.5 eV/A), energies to 2e-5 of the summed per-atom magnitude."""
-    if flags == 0:
-        return E_RTOL, F_ATOL
-    return 2e-5, max(F_ATOL, 4e-5 * f_max)
+    """north_star's tolerances as they stand, in every arithmetic mode: energies 1e-5 relative to |E|, forces 1e-4 eV/A
+    max-abs.  (The split-bf16 tensor mode carries a RELATIVE force error of 1e-5 .. 2.5e-5 -- profiles/
+    r01k_optional_branch_errors.txt -- so the absolute bound presumes forces of trained-model size, a few eV/A; the
+    LayerNorm test models are scaled to that with `readout_gain`, see GAIN below.)"""
+    return E_RTOL, F_ATOL
+
+
+# LayerNorm re-normalises the features: with unit-scale random read-out weights those models have 5-11 eV/A forces.
+# The read-out gain brings them to the ~1 eV/A of the default model and of trained force fields (SURVEY 8(d): synthetic
+# parameters with O(1) forces, so that the absolute force tolerance is meaningful).
+GAIN = {'ln': 0.1, 'ln+post': 0.2, 'all': 0.2}
 OPTS = {'ln': dict(layer_normalization=True),
         'ln+post': dict(layer_normalization=True, final_layer=True),
         'res1': dict(residual_mlp_1=True),
@@ -51,7 +54,7 @@ def dev(a, dt):
 @pytest.mark.parametrize('name', list(OPTS))
 def test_optional_layer_branches_ethanol(ethanol, name, flags):
     cfg = o.OracleConfig(F=132, n_layers=3, **OPTS[name])
-    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True)
+    p = o.init_params(cfg, 0, embed_scale=4.0, scale_shift=True, readout_gain=GAIN.get(name, 1.0))
     eng = make(cfg, p, flags)
     B = 2
     R = ethanol['R'][:B]
@@ -66,9 +69,8 @@ def test_optional_layer_branches_ethanol(ethanol, name, flags):
     assert eng.check_status() == 0
     E, F, ea = E.cpu().numpy().reshape(-1), F.cpu().numpy(), ea.cpu().numpy()
     Eo, Fo = o.energy_forces_batch(cfg, p, R, z, ii, jj)
-    scale = np.maximum(np.abs(Eo.numpy().reshape(-1)), np.abs(ea).sum(-1))
     e_rtol, f_atol = tolerances(flags, float(np.abs(Fo.numpy()).max()))
-    assert (np.abs(E - Eo.numpy().reshape(-1)) <= e_rtol * scale).all()
+    assert (np.abs(E - Eo.numpy().reshape(-1)) <= e_rtol * np.abs(Eo.numpy().reshape(-1))).all()
     assert np.abs(F - Fo.numpy()).max() < f_atol
     assert (F[:, -1] == 0).all() and (ea[:, -1] == 0).all()
 
@@ -82,7 +84,7 @@ def test_optional_layer_branches_periodic_box():
     cell = np.eye(3) * box
     ii, jj, S = o.periodic_neighbor_list_kdtree(pos, box, 5.0)
     cfg = o.OracleConfig(F=132, n_layers=2, **OPTS['all'])
-    p = o.init_params(cfg, 2, embed_scale=4.0)
+    p = o.init_params(cfg, 2, embed_scale=4.0, scale_shift=True, readout_gain=GAIN['all'])
     Eo, Fo, _ = o.energy_forces(cfg, p, pos, z, ii, jj, cell=cell, cell_offset=S)
     for flags in (0, 3):
         eng = make(cfg, p, flags)
@@ -94,7 +96,7 @@ def test_optional_layer_branches_periodic_box():
         dE, dF = abs(float(E.cpu()) - float(Eo)), np.abs(F.cpu().numpy()[0] - Fo.numpy()).max()
         print(f'periodic box, flags {flags}: |dE| {dE:.2e} (sum|e_atom| {float(ea.abs().sum()):.1f}), max|dF| {dF:.2e} '
               f'(max|F| {float(np.abs(Fo.numpy()).max()):.2f})')
-        assert dE <= e_rtol * max(abs(float(Eo)), float(ea.abs().sum()))
+        assert dE <= e_rtol * abs(float(Eo))
         assert dF < f_atol
 
 
@@ -124,6 +126,6 @@ def test_periodic_training_batch_through_get_pbc_neighbors(solid):
         oi, oj, oS = o.primitive_neighbor_list(R, cell, pbc, 5.0)
         assert as_sets(*(nb[k][b].cpu().numpy() for k in ('idx_i', 'idx_j', 'shifts'))) == as_sets(oi, oj, oS)
         Eo, Fo, _ = o.energy_forces(cfg, p, R, zz, oi, oj, cell=cell, cell_offset=oS)
-        assert abs(float(E[b].cpu()) - float(Eo)) <= E_RTOL * max(abs(float(Eo)), float(ea[b].abs().sum()))
+        assert abs(float(E[b].cpu()) - float(Eo)) <= E_RTOL * abs(float(Eo))
         assert np.abs(F[b, :len(R)].cpu().numpy() - Fo.numpy()).max() < F_ATOL
         assert float(F[b, len(R):].abs().sum()) == 0.0
