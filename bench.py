@@ -260,46 +260,25 @@ def run_ours(args, w):
         pos_d = torch.as_tensor(pos, device=dev)
         z_d = torch.as_tensor(z, device=dev, dtype=torch.int32)
         N = len(pos)
-        ddrank = dd.DDRank(eng.lib, eng.h, cfg.n_layer, torch.device(dev))
         grid = dd.brick_grid(cell, world)
         e_tot = torch.zeros(1, dtype=torch.float64, device=dev)
-
-        cap_dd = [int(cap * 1.6 / world) + 4096]
-
-        dd_marks = []                                              # (label, event) of one step, --dd-timing
-
-        def mark(label):
-            if args.dd_timing:
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record()
-                dd_marks.append((label, ev))
+        # the plan (brick subset, neighbour list with r_cut + skin, owned / ghost order, mirror edges, send lists) is
+        # kept while no atom has moved more than skin / 2 -- checked on the device every step; --dd-skin 0 rebuilds it
+        # every step
+        sess = dd.DDSession(eng, cfg.n_layer, cell, world, rank, calc.cutoff, skin=args.dd_skin,
+                            capacity=int(cap * 1.6 / world) + 4096)
+        dd_phase = {}
 
         def step_resident():
-            # this rank only needs the atoms of its brick + r_cut: neighbour list, plan and kernels are O(local)
-            dd_marks.clear()
-            mark('start')
-            sub, owner = dd.brick_select(pos_d, cell, world, rank, calc.cutoff)   # ascending: subset order == global order
-            pos_s, z_s = pos_d[sub], z_d[sub]
-            while True:
-                ii, jj, S, count = eng.neighbor_list(pos_s, calc.cutoff, cap_dd[0], cell=cell, pbc=pbc, mode=NL_ASE)
-                nv = int(count.item())                            # plan sizes are host values (one sync per step)
-                if nv <= cap_dd[0]:
-                    break
-                cap_dd[0] = int(1.25 * nv)
-                eng._status.zero_()
-            mark('subset + neighbour list')
-            plan = dd.build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, rank, world, check=False)
-            mark('plan')
-            ddrank.begin(plan, pos_s, z_s, cell)
-            mark('begin (local arrays, CSR, embedding)')
-            step_resident.p_local = ddrank.P
-            step_resident.n_local = ddrank.N
-            dd.run_energy_forces([ddrank], dd.exchange_distributed)
-            mark('layers + exchanges')
-            e_tot[0] = ddrank.e_atom[:plan.n_own].double().sum()
+            e, f_own, ids = sess.energy_forces(pos_d, z_d, timing=args.dd_timing)
+            if args.dd_timing:
+                dd_phase.update(sess.phase_times())
+            step_resident.p_local = sess.dd.P
+            step_resident.n_local = sess.dd.N
+            step_resident.ids = ids
+            e_tot[0] = e
             dist.all_reduce(e_tot)
-            mark('energy all-reduce')
-            return e_tot, ddrank.forces[:plan.n_own], None
+            return e_tot, f_own, None
 
     # the clock / throttle sampler (nvidia-smi polling) is started BEFORE the warm-up so that its start-up (NVML
     # initialisation touches every GPU of the box) does not land in the first timed steps; it keeps sampling through the
@@ -328,9 +307,8 @@ def run_ours(args, w):
     barrier()
     launches = eng.lib.launch_count() - l0
     if use_dd and args.dd_timing and rank == 0:
-        torch.cuda.synchronize()
-        print('dd step phases (ms): ' + ', '.join(f'{lab} {a.elapsed_time(b):.3f}' for (_, a), (lab, b) in
-                                                     zip(dd_marks[:-1], dd_marks[1:])), file=sys.stderr)
+        print('dd step phases of the last step (ms): ' + ', '.join(f'{k} {v:.3f}' for k, v in dd_phase.items())
+              + f' | plan builds so far: {sess.n_builds}', file=sys.stderr)
     ms_total = e0.elapsed_time(e1)
     if not prof_in_loop:
         eng.lib.profile_enable(eng.h, True)
@@ -355,11 +333,20 @@ def run_ours(args, w):
         # e2e: host positions in (pinned H2D of the replicated positions on every rank), owned forces + energy out
         pin = torch.empty(pos.shape, dtype=torch.float64).pin_memory()
 
+        f_full = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+
         def e2e_call():
+            # host positions in on every rank; the WHOLE force array is assembled on rank 0 (owned rows scattered into a
+            # full-size array, summed onto rank 0 over NVLink) and read back to its host together with the energy
             pin.copy_(torch.from_numpy(pos))
             pos_d.copy_(pin, non_blocking=True)
             e, f, _ = step_resident()
-            return {'energy': float(e.item()), 'forces': f.cpu().numpy()}
+            f_full.zero_()
+            f_full[step_resident.ids] = f
+            dist.reduce(f_full, dst=0)
+            if rank == 0:
+                return {'energy': float(e.item()), 'forces': f_full.cpu().numpy()}
+            return {'energy': float(e.item()), 'forces': None}
     else:
         def e2e_call():
             return calc.calculate(pos, z, cell=cell, pbc=pbc)
@@ -376,7 +363,7 @@ def run_ours(args, w):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_val = (N if use_dd else world * N) / float(t_e2e.item())
     h2d = N * 3 * 8 + (0 if use_dd else N * 4)
-    d2h = ((N // world if use_dd else N) * 3 + 2) * 8
+    d2h = N * 3 * 4 + 8 if use_dd else (N * 3 + 3) * 8      # dd: rank 0 reads the assembled float32 forces + the energy
 
     # standalone featurisation kernel (rbf, phi, d, unit vector, Y_lm written out; not on the fused path, where these are
     # recomputed on chip): achieved bytes against the HBM peak, north_star's "featurisation kernel GB/s"
@@ -526,7 +513,8 @@ def run_ours(args, w):
                 'config': {'workload': args.workload, 'description': w['desc'], 'n_atoms': N, 'n_edges': int(n_edges),
                            'F': w['F'], 'n_layers': w['L'], 'degrees': list(w['degrees']), 'r_cut': 5.0,
                            'parallelism': 'single' if world == 1 else (
-                               f'domain decomposition: {grid[0]}x{grid[1]}x{grid[2]} bricks, mirror edges, per-layer halo exchange (NCCL all_to_all)'
+                               f'domain decomposition: {grid[0]}x{grid[1]}x{grid[2]} bricks, mirror edges, per-layer halo exchange (NCCL all_to_all), '
+                               f'plan re-used within a {args.dd_skin} A skin ({sess.n_builds} builds)'
                                if use_dd else f'replicas x{world} (no collective)'),
                            'filter_gemm': 'tcgen05 split-operand' if args.tensor else 'fp32 CUDA-core',
                            'filters': 'kept for the backward' if (args.tensor and not args.no_keep_filters) else 'recomputed',
@@ -555,6 +543,8 @@ def main():
     ap.add_argument('--md-skin', type=float, default=0.5, help='skin (Angstrom) of the MD neighbour list')
     ap.add_argument('--md-steps', type=int, default=0, help='additionally run this many velocity-Verlet MD steps with a '
                     '0.5 A skin list (mlff_b200.md, one GPU) and report them under "md"')
+    ap.add_argument('--dd-skin', type=float, default=0.2, help='domain decomposition: skin (Angstrom) of the per-rank plan; the plan '
+                    'is re-used while no atom has moved more than skin / 2 (0: rebuild every step)')
     ap.add_argument('--dd-timing', action='store_true', help='print the per-phase device time of one domain-decomposed step '
                     '(rank 0, stderr)')
     ap.add_argument('--no-keep-filters', action='store_true', help='recompute the filters in the backward instead of keeping '

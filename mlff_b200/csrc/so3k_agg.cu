@@ -140,131 +140,43 @@ k_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
   }
 }
 
-// ---- lane <-> feature map of the vectorised streaming kernels ---------------------------------------------------------
-// A lane owns NV 16-byte chunks of an F-wide row -- chunk index lane + 32 s, features 4 (lane + 32 s) .. + 3 -- and, with
-// TAIL, one scalar of the remainder (feature 128 NV + lane).  F = 132 is <NV = 1, TAIL>: ONE 128-bit load per lane covers
-// features 0..127 and lanes 0..3 add features 128..131 with a predicated 32-bit load -- two load instructions per row
-// where a lane-per-feature layout needs five.  Element e of a lane: e < 4 NV vector element, e == 4 NV the tail scalar.
-template <int NV, bool TAIL>
-struct LaneMap {
-  static constexpr int E = 4 * NV + (TAIL ? 1 : 0);
-  __device__ __forceinline__ static int feature(int lane, int e) {
-    return e < 4 * NV ? 4 * (lane + 32 * (e >> 2)) + (e & 3) : 128 * NV + lane;
-  }
-  // row p (16-byte aligned, F % 4 == 0) -> v[E]; elements beyond F read as 0
-  __device__ __forceinline__ static void load(const float* __restrict__ p, int lane, int F, float* v) {
-#pragma unroll
-    for (int s = 0; s < NV; ++s) {
-      const int c = lane + 32 * s;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (4 * c < F) t = ld_pinned4(p + 4 * c);
-      v[4 * s] = t.x; v[4 * s + 1] = t.y; v[4 * s + 2] = t.z; v[4 * s + 3] = t.w;
-    }
-    if (TAIL) {
-      const int f = 128 * NV + lane;
-      v[4 * NV] = (f < F) ? ld_pinned(p + f) : 0.f;
-    }
-  }
-  __device__ __forceinline__ static void store(float* __restrict__ p, int lane, int F, const float* v) {
-#pragma unroll
-    for (int s = 0; s < NV; ++s) {
-      const int c = lane + 32 * s;
-      if (4 * c < F) *reinterpret_cast<float4*>(p + 4 * c) = make_float4(v[4 * s], v[4 * s + 1], v[4 * s + 2], v[4 * s + 3]);
-    }
-    if (TAIL) {
-      const int f = 128 * NV + lane;
-      if (f < F) p[f] = v[4 * NV];
-    }
-  }
-};
-// floats of product staging per (edge, block) and warp: F rounded up to 8, + 8 to move successive rows off the bank period
-SO3K_HD static inline int so3k_spw(int F) { return ((F + 7) & ~7) + 8; }
-
-// Who reduces what after a batch of EPB edges has staged its per-feature products in shared memory: NOUT = EPB * A head
-// sums (A heads per edge).  With NOUT <= 16 two lanes share a sum (halves of the head's feature range, combined by one
-// shuffle), otherwise one lane per sum.  All fields are loop-invariant per lane.
-struct HeadReducer {
-  int k, a, f0, len;        // edge of the batch, head slot, feature range [f0, f0 + len)
-  bool split, owner;        // two lanes per sum ; this lane writes the result
-  // sum of the staged products of this lane's range: four independent chains, so the shared-memory loads pipeline
-  // instead of forming one load -> add -> load chain
-  __device__ __forceinline__ float sum(const float* __restrict__ s_w) const {
-    const float* sp = s_w + f0;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int t = 0;
-    for (; t + 4 <= len; t += 4) {
-      s0 += sp[t];
-      s1 += sp[t + 1];
-      s2 += sp[t + 2];
-      s3 += sp[t + 3];
-    }
-    if (t < len) s0 += sp[t];
-    if (t + 1 < len) s1 += sp[t + 1];
-    if (t + 2 < len) s2 += sp[t + 2];
-    return (s0 + s1) + (s2 + s3);
-  }
-};
-
 // Tensor-core path: attention coefficients from the pair-indexed filters, fused with both aggregations.
 //   alpha_fb[e][h] = phi_e / sqrt(F/H)  sum_{f in h} w_fb[pid e][f] q_fb[i][f] k_fb[j][f]       (so3krates_layer.py:590-606)
 //   alpha_gb[e][l] = phi_e / sqrt(F/nl) sum_{f in l} w_gb[pid e][f] q_gb[i][f] k_gb[j][f]       (so3krates_layer.py:545-562)
 //   x1 = x + sum_e alpha_fb[e][h(f)] v[j][f] ;  chi1 = chi + sum_e alpha_gb[e][l(m)] Y_m(u_e)
-// A warp owns a receiver row; two edges per pass.  Their five rows each (two filter rows, the sender's k_fb, k_gb, v)
-// arrive as 128-bit lane chunks (LaneMap); the per-feature products q w k go to a shared-memory staging row in feature
-// order, and the 2 (H + nl) head sums are formed by lanes that each add up (half of) one head's contiguous range -- a
-// dozen shared-memory reads instead of a select-and-add per (feature, head) and a 16-value butterfly.
-template <int NV, bool TAIL>
-__global__ void __launch_bounds__(WPB * 32)
+// EP edges per iteration; their EP * 2 * HS per-lane head partials (HS slots per block) are reduced over the warp by one
+// halving butterfly (16 shuffles), as in k_alpha_bwd.
+template <int TN, int HS, int DHF, int DHG>     // TN = ceil(F / 32) ; HS = 4 (H, nl <= 4: two edges per pass) or 8 ;
+__global__ void __launch_bounds__(WPB * 32)     // DHF / DHG = compile-time head widths F/H, F/nl (0: run-time)
 k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ x,
                   const float* __restrict__ chi, const float* __restrict__ proj, const float* __restrict__ wst_f,
                   const float* __restrict__ wst_g, float* __restrict__ alpha, float* __restrict__ x1,
                   float* __restrict__ chi1) {
-  using LM = LaneMap<NV, TAIL>;
-  constexpr int E = LM::E, EPB = 2;
+  constexpr int EP = 8 / HS;
   __shared__ float s_a[WPB][32 * AMAX];
   __shared__ float s_ph[WPB][32];
   __shared__ int s_j[WPB][32];
   __shared__ int s_p[WPB][32];
-  SO3K_DYN_SMEM(float, s_w_all);             // [WPB][EPB * 2][SPW]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * WPB + w;
-  const int F = D.F, M = D.M, H = D.H, nl = D.nl, A = H + nl;
-  const int SPW = so3k_spw(F);
-  float* s_w = s_w_all + (size_t)w * EPB * 2 * SPW;
+  const int F = D.F, M = D.M, H = D.H, nl = D.nl;
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
   const size_t F5 = 5 * (size_t)F;
   const float inv_f = 1.0f / sqrtf((float)(F / H)), inv_g = 1.0f / sqrtf((float)(F / nl));
-  float accx[E], qf[E], qg[E];
-  int hx[E];
-  if (rowok) {
-    LM::load(proj + (size_t)i * F5, lane, F, qf);
-    LM::load(proj + (size_t)i * F5 + F, lane, F, qg);
-  }
+  float accx[TN], qf[TN], qg[TN];
+  int hf[TN], hg[TN];
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    accx[e] = 0.f;
-    if (!rowok) qf[e] = qg[e] = 0.f;
-    const int f = LM::feature(lane, e);
-    hx[e] = (f < F) ? f / (F / H) : 0;
+  for (int t = 0; t < TN; ++t) {
+    accx[t] = 0.f;
+    const int f = lane + 32 * t;
+    const bool ok = rowok && f < F;
+    qf[t] = ok ? proj[(size_t)i * F5 + f] : 0.f;           // zero beyond F: those slots add nothing
+    qg[t] = ok ? proj[(size_t)i * F5 + F + f] : 0.f;
+    hf[t] = (f < F) ? f / (F / H) : 0;
+    hg[t] = (f < F) ? f / (F / nl) : 0;
   }
-  // this lane's share of the head sums of a batch
-  HeadReducer hr;
-  {
-    const int nout = EPB * A;
-    hr.split = nout <= 16;
-    const int o = hr.split ? (lane & 15) : lane, half = hr.split ? (lane >> 4) : 0;
-    hr.k = o / A;
-    hr.a = o - hr.k * A;
-    const bool ok = o < nout;
-    const int blk = hr.a >= H, h = blk ? hr.a - H : hr.a, dh = blk ? F / nl : F / H;
-    const int part = hr.split ? (dh + 1) / 2 : dh;
-    hr.f0 = (hr.k * 2 + blk) * SPW + h * dh + half * part;
-    hr.len = ok ? (half ? dh - part : part) : 0;
-    hr.owner = ok && half == 0;
-  }
-  const float hr_scale = hr.a >= H ? inv_g : inv_f;
   float cacc[SO3K_MAXM];
   for (int m = 0; m < M; ++m) cacc[m] = 0.f;
   for (int e0 = beg; e0 < end; e0 += 32) {
@@ -276,49 +188,80 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
       s_j[w][lane] = col[e];
       s_p[w][lane] = pid[e];
       s_ph[w][lane] = so3k_cutoff(g.w, D.r_cut);
-      for (int a = A; a < Ast; ++a) s_a[w][lane * Ast + a] = 0.f;
+      for (int a = H + nl; a < Ast; ++a) s_a[w][lane * Ast + a] = 0.f;
     }
     __syncwarp();
-    for (int q = 0; q < cnt; q += EPB) {
-      float vv[EPB][E];
-      int qk[EPB];
-      {
-        float wf[EPB][E], wg[EPB][E], kf[EPB][E], kg[EPB][E];
+    for (int q = 0; q < cnt; q += EP) {
+      float wf[EP][TN], wg[EP][TN], kf[EP][TN], kg[EP][TN], vv[EP][TN];
+      int qk[EP];
 #pragma unroll
-        for (int k = 0; k < EPB; ++k) {
-          qk[k] = (q + k < cnt) ? q + k : cnt - 1;
-          const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
-          LM::load(wst_f + (size_t)s_p[w][qk[k]] * F, lane, F, wf[k]);
-          LM::load(wst_g + (size_t)s_p[w][qk[k]] * F, lane, F, wg[k]);
-          LM::load(pj + 2 * F, lane, F, kf[k]);
-          LM::load(pj + 3 * F, lane, F, kg[k]);
-          LM::load(pj + 4 * F, lane, F, vv[k]);
+      for (int k = 0; k < EP; ++k) {
+        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+        const float* pj = proj + (size_t)s_j[w][qk[k]] * F5;
+        const float* pwf = wst_f + (size_t)s_p[w][qk[k]] * F;
+        const float* pwg = wst_g + (size_t)s_p[w][qk[k]] * F;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          const bool ok = (t + 1 < TN) || f < F;
+          wf[k][t] = ok ? pwf[f] : 0.f;
+          wg[k][t] = ok ? pwg[f] : 0.f;
+          kf[k][t] = ok ? pj[2 * F + f] : 0.f;
+          kg[k][t] = ok ? pj[3 * F + f] : 0.f;
+          vv[k][t] = ok ? pj[4 * F + f] : 0.f;
         }
+      }
+      float val[16];                           // [edge k][block][head slot]
 #pragma unroll
-        for (int k = 0; k < EPB; ++k) {
-          float pf[E], pg[E];
+      for (int u = 0; u < 16; ++u) val[u] = 0.f;
 #pragma unroll
-          for (int e2 = 0; e2 < E; ++e2) {
-            pf[e2] = wf[k][e2] * (qf[e2] * kf[k][e2]);
-            pg[e2] = wg[k][e2] * (qg[e2] * kg[k][e2]);
+      for (int k = 0; k < EP; ++k) {
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const float pf = wf[k][t] * qf[t] * kf[k][t];
+          const float pg = wg[k][t] * qg[t] * kg[k][t];
+          if (DHF >= 32 && DHG >= 32) {
+            head_accum<(DHF >= 32 ? DHF : 32), HS>(val + k * 2 * HS, t, lane, pf);
+            head_accum<(DHG >= 32 ? DHG : 32), HS>(val + k * 2 * HS + HS, t, lane, pg);
+          } else {
+#pragma unroll
+            for (int h = 0; h < HS; ++h) {
+              val[k * 2 * HS + h] += (hf[t] == h) ? pf : 0.f;
+              val[k * 2 * HS + HS + h] += (hg[t] == h) ? pg : 0.f;
+            }
           }
-          LM::store(&s_w[(k * 2 + 0) * SPW], lane, F, pf);
-          LM::store(&s_w[(k * 2 + 1) * SPW], lane, F, pg);
+        }
+      }
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {         // halving butterfly: afterwards a lane holds value index (lane >> 1)
+        const int off = 16 >> st, half = 8 >> st;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int u = 0; u < half; ++u) {
+          const float send = up ? val[u] : val[u + half];
+          const float keep = up ? val[u + half] : val[u];
+          val[u] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+      {
+        const int idx = lane >> 1, k = idx / (2 * HS), a = idx % (2 * HS);
+        if ((lane & 1) == 0 && q + k < cnt) {
+          const float ph = s_ph[w][q + k];
+          if (a < HS) {
+            if (a < H) s_a[w][(q + k) * Ast + a] = val[0] * inv_f * ph;
+          } else if (a - HS < nl) {
+            s_a[w][(q + k) * Ast + H + a - HS] = val[0] * inv_g * ph;
+          }
         }
       }
       __syncwarp();
-      {
-        float sum = hr.sum(s_w);
-        if (hr.split) sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-        if (hr.owner && q + hr.k < cnt) s_a[w][(q + hr.k) * Ast + hr.a] = sum * hr_scale * s_ph[w][q + hr.k];
-      }
-      __syncwarp();
 #pragma unroll
-      for (int k = 0; k < EPB; ++k) {
+      for (int k = 0; k < EP; ++k) {
         const float m = (q + k < cnt) ? 1.f : 0.f;
         const float* aq = &s_a[w][qk[k] * Ast];
 #pragma unroll
-        for (int e2 = 0; e2 < E; ++e2) accx[e2] = fmaf(m * aq[hx[e2]], vv[k][e2], accx[e2]);
+        for (int t = 0; t < TN; ++t) accx[t] = fmaf(m * aq[hf[t]], vv[k][t], accx[t]);
       }
     }
     __syncwarp();
@@ -335,61 +278,235 @@ k_alpha_aggregate(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, co
     if (rowok && lane == 0) chi1[(size_t)i * M + m] = chi[(size_t)i * M + m] + s;
   }
   if (rowok) {
-    float xi[E];
-    LM::load(x + (size_t)i * F, lane, F, xi);
 #pragma unroll
-    for (int e2 = 0; e2 < E; ++e2) xi[e2] += accx[e2];
-    LM::store(x1 + (size_t)i * F, lane, F, xi);
+    for (int t = 0; t < TN; ++t) {
+      int f = lane + 32 * t;
+      if (f < F) x1[(size_t)i * F + f] = x[(size_t)i * F + f] + accx[t];
+    }
+  }
+}
+
+// =====================================================================================================================
+// Fast variant of k_alpha_aggregate for rows of at most 160 features (one 128-bit chunk per lane + optional tail scalar)
+// whose head layout lets a warp scan form the head sums (so3k_scan_ok): a lane's chunk touches at most two adjacent heads
+// (head width >= 4), and the tail scalars together with the chunks of the last ntail lanes lie in the LAST head.  The
+// default model (F = 132, 4 heads of 33 / 3 heads of 44) qualifies.  Measured on c4: 6.74 ms per step against 7.31 ms for
+// the general kernel above.  (The same treatment of k_alpha_bwd and k_qk_bwd_stream was SLOWER than the lane-per-feature
+// kernels -- 3.71 vs 3.12 ms and 8.95 vs 8.04 ms -- and is not kept; a shared-memory staging of the per-feature products
+// for the head sums was slower still: 70 % of the LSU wavefront peak, profiles/README.md r02c.)
+// Two things make it cheaper:
+//   * row addresses: every array has a per-lane base pointer (array + this lane's float offset), so a row address is one
+//     64-bit multiply-add (base + row * stride) instead of a chain of integer instructions per load;
+//   * head sums: a lane folds its chunk's products into (lo, hi) = (part in the chunk's first head, part in the next), an
+//     inclusive warp scan of lo + hi gives running totals, and head h = X[last lane of h] - X[last lane of h - 1] with
+//     X = scan - hi: 8 shuffles and ~25 arithmetic instructions per edge and block, no shared memory.
+struct HeadScan {
+  float m[4];          // 1 where element c of the lane's chunk belongs to the chunk's first head h0, 0 where to h0 + 1
+  int h0, h1;          // heads of the chunk (h1 = min(h0 + 1, heads - 1))
+  int src_hi, src_lo;  // lanes whose X holds the running total through head `lane` / through head `lane - 1`
+  float use_lo;        // 1 for lanes 1 .. heads - 1 (subtract the previous running total), else 0
+};
+__device__ __forceinline__ HeadScan make_head_scan(int lane, int F, int heads) {
+  HeadScan s;
+  const int dw = F / heads, f0 = 4 * lane;
+  int h0 = f0 / dw;
+  if (h0 > heads - 1) h0 = heads - 1;
+  const int nlo = (h0 + 1) * dw - f0;                  // elements of the chunk inside head h0 (>= 4: all of them)
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s.m[c] = (c < nlo || h0 == heads - 1) ? 1.f : 0.f;
+  s.h0 = h0;
+  s.h1 = h0 + 1 < heads ? h0 + 1 : heads - 1;
+  const int o = lane < heads ? lane : heads - 1;
+  int bh = ((o + 1) * dw - 1) / 4, bl = o > 0 ? (o * dw - 1) / 4 : 0;
+  s.src_hi = (o == heads - 1 || bh > 31) ? 31 : bh;    // the last head runs to the end of the row (tail included)
+  s.src_lo = bl > 31 ? 31 : bl;
+  s.use_lo = (lane > 0 && lane < heads) ? 1.f : 0.f;
+  return s;
+}
+// head sums of one edge: lane h < heads returns the sum over head h of the per-feature products (p = this lane's chunk,
+// tailp = its tail scalar's product or 0)
+template <bool TAIL>
+__device__ __forceinline__ float head_scan_sums(const float* p, float tailp, const HeadScan& s, int lane) {
+  float lo = s.m[0] * p[0];
+  lo = fmaf(s.m[1], p[1], lo);
+  lo = fmaf(s.m[2], p[2], lo);
+  lo = fmaf(s.m[3], p[3], lo);
+  float tot = (p[0] + p[1]) + (p[2] + p[3]);
+  const float hi = tot - lo;
+  if (TAIL) tot += __shfl_sync(0xffffffffu, tailp, 31 - lane);     // tail scalars sit in lanes 0.. : hand them to the last lanes
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, tot, d);
+    tot += (lane >= d) ? v : 0.f;
+  }
+  const float X = tot - hi;
+  const float a = __shfl_sync(0xffffffffu, X, s.src_hi);
+  const float b = __shfl_sync(0xffffffffu, X, s.src_lo);
+  return fmaf(-s.use_lo, b, a);
+}
+// per-element coefficients of a lane's chunk from per-head values held by lanes 0 .. heads - 1
+__device__ __forceinline__ void head_scan_coef(float per_head, const HeadScan& s, float* coef) {
+  const float a0 = __shfl_sync(0xffffffffu, per_head, s.h0), a1 = __shfl_sync(0xffffffffu, per_head, s.h1);
+  const float d = a0 - a1;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) coef[c] = fmaf(s.m[c], d, a1);
+}
+static bool so3k_scan_ok(int F, int heads) {
+  if (F > 160 || F % 4 || heads < 1 || F % heads) return false;
+  const int dw = F / heads, ntail = F > 128 ? F - 128 : 0;
+  if (dw < 4) return false;
+  return ntail == 0 || (heads - 1) * dw <= 128 - 4 * ntail;
+}
+
+// k_alpha_aggregate, fast variant (see there for the math)
+template <bool TAIL>
+__global__ void __launch_bounds__(WPB * 32, 2)
+k_alpha_aggregate_scan(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
+                       const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ x,
+                       const float* __restrict__ chi, const float* __restrict__ proj, const float* __restrict__ wst_f,
+                       const float* __restrict__ wst_g, float* __restrict__ alpha, float* __restrict__ x1,
+                       float* __restrict__ chi1) {
+  constexpr int EPB = 2;
+  __shared__ float s_a[WPB][32 * AMAX];
+  __shared__ float s_ph[WPB][32];
+  __shared__ int s_j[WPB][32];
+  __shared__ int s_p[WPB][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * WPB + w;
+  const int F = D.F, M = D.M, H = D.H, nl = D.nl, A = H + nl;
+  const bool rowok = i < N;
+  const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
+  const unsigned F5 = 5u * (unsigned)F, Fu = (unsigned)F;
+  const float inv_f = 1.0f / sqrtf((float)(F / H)), inv_g = 1.0f / sqrtf((float)(F / nl));
+  const bool okv = 4 * lane < F, okt = TAIL && 128 + lane < F;
+  const int offv = okv ? 4 * lane : 0, offt = okt ? 128 + lane : 0;          // clamped: masked lanes read a valid address
+  // per-lane base pointers: row address = base + row * stride
+  const float* const wf_v = wst_f + offv; const float* const wf_t = wst_f + offt;
+  const float* const wg_v = wst_g + offv; const float* const wg_t = wst_g + offt;
+  const float* const kf_v = proj + 2 * F + offv; const float* const kf_t = proj + 2 * F + offt;
+  const float* const kg_v = proj + 3 * F + offv; const float* const kg_t = proj + 3 * F + offt;
+  const float* const vv_v = proj + 4 * F + offv; const float* const vv_t = proj + 4 * F + offt;
+  const float mv = okv ? 1.f : 0.f, mt = okt ? 1.f : 0.f;
+  const HeadScan hsf = make_head_scan(lane, F, H), hsg = make_head_scan(lane, F, nl);
+  float4 qf = make_float4(0.f, 0.f, 0.f, 0.f), qg = qf;
+  float qft = 0.f, qgt = 0.f;
+  if (rowok) {
+    const float* pi = proj + (size_t)i * F5;
+    if (okv) { qf = ld_pinned4(pi + offv); qg = ld_pinned4(pi + F + offv); }
+    if (okt) { qft = pi[offt]; qgt = pi[F + offt]; }
+  }
+  float accx[4] = {0.f, 0.f, 0.f, 0.f}, acct = 0.f;
+  float cacc[SO3K_MAXM];
+  for (int m = 0; m < M; ++m) cacc[m] = 0.f;
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const int cnt = (end - e0) < 32 ? (end - e0) : 32;
+    float4 g = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (e < end) {
+      g = geom[e];
+      s_j[w][lane] = col[e];
+      s_p[w][lane] = pid[e];
+      s_ph[w][lane] = so3k_cutoff(g.w, D.r_cut);
+      for (int a = A; a < Ast; ++a) s_a[w][lane * Ast + a] = 0.f;
+    }
+    __syncwarp();
+    for (int q = 0; q < cnt; q += EPB) {
+      float4 wf[EPB], wg[EPB], kf[EPB], kg[EPB], vv[EPB];
+      float wft[EPB], wgt[EPB], kft[EPB], kgt[EPB], vvt[EPB];
+#pragma unroll
+      for (int k = 0; k < EPB; ++k) {
+        const int qc = (q + k < cnt) ? q + k : cnt - 1;
+        const unsigned jr = (unsigned)s_j[w][qc], pr = (unsigned)s_p[w][qc];
+        wf[k] = ld_pinned4(wf_v + (size_t)pr * Fu);
+        wg[k] = ld_pinned4(wg_v + (size_t)pr * Fu);
+        kf[k] = ld_pinned4(kf_v + (size_t)jr * F5);
+        kg[k] = ld_pinned4(kg_v + (size_t)jr * F5);
+        vv[k] = ld_pinned4(vv_v + (size_t)jr * F5);
+        if (TAIL) {
+          wft[k] = ld_pinned(wf_t + (size_t)pr * Fu);
+          wgt[k] = ld_pinned(wg_t + (size_t)pr * Fu);
+          kft[k] = ld_pinned(kf_t + (size_t)jr * F5);
+          kgt[k] = ld_pinned(kg_t + (size_t)jr * F5);
+          vvt[k] = ld_pinned(vv_t + (size_t)jr * F5);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < EPB; ++k) {
+        const bool live = q + k < cnt;                               // warp-uniform
+        // masked lanes (beyond F) loaded a valid but foreign address: their products are zeroed by mv / mt
+        const float pf[4] = {mv * wf[k].x * (qf.x * kf[k].x), mv * wf[k].y * (qf.y * kf[k].y),
+                             mv * wf[k].z * (qf.z * kf[k].z), mv * wf[k].w * (qf.w * kf[k].w)};
+        const float pg[4] = {mv * wg[k].x * (qg.x * kg[k].x), mv * wg[k].y * (qg.y * kg[k].y),
+                             mv * wg[k].z * (qg.z * kg[k].z), mv * wg[k].w * (qg.w * kg[k].w)};
+        const float pft = TAIL ? mt * wft[k] * (qft * kft[k]) : 0.f, pgt = TAIL ? mt * wgt[k] * (qgt * kgt[k]) : 0.f;
+        const float ph = s_ph[w][live ? q + k : cnt - 1];
+        const float af = head_scan_sums<TAIL>(pf, pft, hsf, lane) * (inv_f * ph);    // lane h < H: alpha_fb[h]
+        const float ag = head_scan_sums<TAIL>(pg, pgt, hsg, lane) * (inv_g * ph);    // lane l < nl: alpha_gb[l]
+        if (live) {
+          if (lane < H) s_a[w][(q + k) * Ast + lane] = af;
+          if (lane < nl) s_a[w][(q + k) * Ast + H + lane] = ag;
+          float cf[4];
+          head_scan_coef(af, hsf, cf);
+          accx[0] = fmaf(cf[0], vv[k].x, accx[0]);
+          accx[1] = fmaf(cf[1], vv[k].y, accx[1]);
+          accx[2] = fmaf(cf[2], vv[k].z, accx[2]);
+          accx[3] = fmaf(cf[3], vv[k].w, accx[3]);
+          if (TAIL) acct = fmaf(__shfl_sync(0xffffffffu, af, H - 1), vvt[k], acct);
+        }
+      }
+    }
+    __syncwarp();
+    if (e < end) {                             // SPHC part, lane-per-edge
+      float y[SO3K_MAXM];
+      so3k_sph_all(D, g.x, g.y, g.z, y);
+      for (int m = 0; m < M; ++m) cacc[m] = fmaf(s_a[w][lane * Ast + H + D.m_seg[m]], y[m], cacc[m]);
+    }
+    for (int t = lane; t < cnt * Ast; t += 32) alpha[(size_t)e0 * Ast + t] = s_a[w][t];
+    __syncwarp();
+  }
+  for (int m = 0; m < M; ++m) {
+    float s = warp_sum(cacc[m]);
+    if (rowok && lane == 0) chi1[(size_t)i * M + m] = chi[(size_t)i * M + m] + s;
+  }
+  if (rowok) {
+    const float* xi = x + (size_t)i * Fu;
+    float* xo = x1 + (size_t)i * Fu;
+    if (okv) {
+      const float4 t = *reinterpret_cast<const float4*>(xi + offv);
+      *reinterpret_cast<float4*>(xo + offv) = make_float4(t.x + accx[0], t.y + accx[1], t.z + accx[2], t.w + accx[3]);
+    }
+    if (okt) xo[offt] = xi[offt] + acct;
   }
 }
 
 // alphabar_fb[e][h] = sum_{f in h} xbar1[i][f] v[j][f] ; alphabar_gb[e][l] = sum_{m in l} chibar1[i][m] Y_m(u_e)
 // gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
-// Four edges per pass (two 128-bit row loads each); their 4 H head sums are formed from products staged in shared
-// memory, like in k_alpha_aggregate.
-template <int NV, bool TAIL>
-__global__ void __launch_bounds__(WPB * 32)
+// EP = 16 / HP edges per iteration: their EP * HP per-lane head partials are reduced over the warp with ONE halving
+// butterfly (16 shuffles for all of them instead of 5 per value).
+template <int TN, int HP, int DHC>              // TN = ceil(F / 32) ; HP = heads padded to 4 or 8 ; DHC = compile-time
+__global__ void __launch_bounds__(WPB * 32)     // head width F/H (0: run-time)
 k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
             const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
             const float* __restrict__ alpha, const float* __restrict__ xbar1, const float* __restrict__ chibar1,
             float* __restrict__ alphabar, float* __restrict__ gproj) {
-  using LM = LaneMap<NV, TAIL>;
-  constexpr int E = LM::E, EPB = 4;
+  constexpr int EP = 16 / HP;
   __shared__ float s_a[WPB][32 * AMAX];     // alpha_fb of the reverse edges
   __shared__ float s_o[WPB][32 * AMAX];     // alphabar staging (coalesced store)
   __shared__ int s_j[WPB][32];
-  SO3K_DYN_SMEM(float, s_w_all);             // [WPB][EPB][SPW]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * WPB + w;
   const int F = D.F, M = D.M, H = D.H, nl = D.nl;
-  const int SPW = so3k_spw(F);
-  float* s_w = s_w_all + (size_t)w * EPB * SPW;
   const bool rowok = i < N;
   const int beg = rowok ? rowptr[i] : 0, end = rowok ? rowptr[i + 1] : 0;
   const size_t F5 = 5 * (size_t)F;
-  float xb[E], accv[E];
-  int hx[E];
-  if (rowok) LM::load(xbar1 + (size_t)i * F, lane, F, xb);
+  float xb[TN], accv[TN];
+  int hsel[TN];
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    if (!rowok) xb[e] = 0.f;
-    accv[e] = 0.f;
-    const int f = LM::feature(lane, e);
-    hx[e] = (f < F) ? f / (F / H) : 0;
-  }
-  HeadReducer hr;
-  {
-    const int nout = EPB * H;                 // <= 32 (H <= 8)
-    hr.split = nout <= 16;
-    const int o = hr.split ? (lane & 15) : lane, half = hr.split ? (lane >> 4) : 0;
-    hr.k = o / H;
-    hr.a = o - hr.k * H;
-    const bool ok = o < nout;
-    const int dh = F / H;
-    const int part = hr.split ? (dh + 1) / 2 : dh;
-    hr.f0 = hr.k * SPW + hr.a * dh + half * part;
-    hr.len = ok ? (half ? dh - part : part) : 0;
-    hr.owner = ok && half == 0;
+  for (int t = 0; t < TN; ++t) {
+    int f = lane + 32 * t;
+    xb[t] = (rowok && f < F) ? xbar1[(size_t)i * F + f] : 0.f;
+    accv[t] = 0.f;
+    hsel[t] = (f < F) ? f / D.dh : 0;       // xb = 0 beyond F: those slots add nothing
   }
   float cb[SO3K_MAXM];
   for (int m = 0; m < M; ++m) cb[m] = rowok ? chibar1[(size_t)i * M + m] : 0.f;
@@ -405,54 +522,81 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
       float y[SO3K_MAXM];
       so3k_sph_all(D, g.x, g.y, g.z, y);
       for (int l = 0; l < nl; ++l) {
-        float sm = 0.f;
-        for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) sm = fmaf(cb[m], y[m], sm);
-        s_o[w][lane * Ast + H + l] = sm;
+        float s = 0.f;
+        for (int m = D.seg_off[l]; m < D.seg_off[l + 1]; ++m) s = fmaf(cb[m], y[m], s);
+        s_o[w][lane * Ast + H + l] = s;
       }
       for (int a = H + nl; a < Ast; ++a) s_o[w][lane * Ast + a] = 0.f;
     }
     s_j[w][lane] = j;
     __syncwarp();
-    for (int q = 0; q < cnt; q += EPB) {
-      float xx[EPB][E];
-      int qk[EPB];
-      {
-        float vv[EPB][E];
+    for (int q = 0; q < cnt; q += EP) {
+      float vv[EP][TN], xx[EP][TN];
+      int qk[EP];
+      float am[EP];
 #pragma unroll
-        for (int k = 0; k < EPB; ++k) {
-          qk[k] = (q + k < cnt) ? q + k : cnt - 1;
-          const int jq = s_j[w][qk[k]];
-          LM::load(proj + (size_t)jq * F5 + 4 * (size_t)F, lane, F, vv[k]);
-          LM::load(xbar1 + (size_t)jq * F, lane, F, xx[k]);
-        }
+      for (int k = 0; k < EP; ++k) {
+        qk[k] = (q + k < cnt) ? q + k : cnt - 1;
+        am[k] = (q + k < cnt) ? 1.f : 0.f;
+        const int jq = s_j[w][qk[k]];
+        const float* vj = proj + (size_t)jq * F5 + 4 * (size_t)F;
+        const float* xj = xbar1 + (size_t)jq * F;
 #pragma unroll
-        for (int k = 0; k < EPB; ++k) {
-          float pr[E];
-#pragma unroll
-          for (int e2 = 0; e2 < E; ++e2) pr[e2] = xb[e2] * vv[k][e2];
-          LM::store(&s_w[k * SPW], lane, F, pr);
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          const bool ok = (t + 1 < TN) || f < F;
+          vv[k][t] = ok ? vj[f] : 0.f;
+          xx[k][t] = ok ? xj[f] : 0.f;
         }
       }
-      __syncwarp();
-      {
-        float sum = hr.sum(s_w);
-        if (hr.split) sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-        if (hr.owner && q + hr.k < cnt) s_o[w][(q + hr.k) * Ast + hr.a] = sum;
-      }
+      float val[16];                           // [edge k][head h]: this lane's partial of alphabar_fb
 #pragma unroll
-      for (int k = 0; k < EPB; ++k) {
-        const float m = (q + k < cnt) ? 1.f : 0.f;
+      for (int u = 0; u < 16; ++u) val[u] = 0.f;
+#pragma unroll
+      for (int k = 0; k < EP; ++k) {
         const float* aq = &s_a[w][qk[k] * Ast];
 #pragma unroll
-        for (int e2 = 0; e2 < E; ++e2) accv[e2] = fmaf(m * aq[hx[e2]], xx[k][e2], accv[e2]);
+        for (int t = 0; t < TN; ++t) {
+          const float p = xb[t] * vv[k][t];
+          if (DHC >= 32) {
+            head_accum<(DHC >= 32 ? DHC : 32), HP>(val + k * HP, t, lane, p);
+          } else {
+#pragma unroll
+            for (int h = 0; h < HP; ++h) val[k * HP + h] += (hsel[t] == h) ? p : 0.f;
+          }
+          accv[t] = fmaf(am[k] * aq[hsel[t]], xx[k][t], accv[t]);
+        }
       }
-      __syncwarp();
+      // halving butterfly: after the stages with offsets 16, 8, 4, 2 a lane holds value index (lane >> 1); the last
+      // stage completes the sum over the remaining lane bit
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        const int off = 16 >> st, half = 8 >> st;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int u = 0; u < half; ++u) {
+          const float send = up ? val[u] : val[u + half];
+          const float keep = up ? val[u + half] : val[u];
+          val[u] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      val[0] += __shfl_xor_sync(0xffffffffu, val[0], 1);
+      {
+        const int idx = lane >> 1, k = idx / HP, h = idx % HP;
+        if ((lane & 1) == 0 && h < H && q + k < cnt) s_o[w][(q + k) * Ast + h] = val[0];
+      }
     }
     __syncwarp();
     for (int t = lane; t < cnt * Ast; t += 32) alphabar[(size_t)e0 * Ast + t] = s_o[w][t];
     __syncwarp();
   }
-  if (rowok) LM::store(gproj + (size_t)i * F5 + 4 * (size_t)F, lane, F, accv);
+  if (rowok) {
+#pragma unroll
+    for (int t = 0; t < TN; ++t) {
+      int f = lane + 32 * t;
+      if (f < F) gproj[(size_t)i * F5 + 4 * (size_t)F + f] = accv[t];
+    }
+  }
 }
 
 // q/k projection gradients of one filter block (blockIdx.y) from its pair-indexed filters w[pid e][f] (kept from the
@@ -463,17 +607,14 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 // and, for the canonical edge of every pair, the filter cotangent of the PAIR
 //   wbar[pid e][f] = ab_e[h(f)] q_i[f] k_j[f] + abr_e[h(f)] q_j[f] k_i[f]
 // which the tensor-core kernel of backward part 2 then reads as a contiguous tile.
-// Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics; rows move as
-// 128-bit lane chunks (LaneMap).
-template <int NV, bool TAIL>
+// Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics.
+template <int TN>                               // TN = ceil(F / 32): feature slots per lane
 __global__ void __launch_bounds__(WPB * 32)
 k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                 const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom,
                 const float* __restrict__ proj, const float* __restrict__ alpha, const float* __restrict__ alphabar,
                 const float* __restrict__ wst, size_t blk_stride, float* __restrict__ gproj, float* __restrict__ ebar,
                 float* __restrict__ wbar) {
-  using LM = LaneMap<NV, TAIL>;
-  constexpr int E = LM::E;
   __shared__ float s_ab[WPB][32 * 8];
   __shared__ float s_abr[WPB][32 * 8];
   __shared__ int s_j[WPB][32];
@@ -490,18 +631,16 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
   const float inv = 1.0f / sqrtf((float)(F / heads));
   wst += blk * blk_stride;
   wbar += blk * blk_stride;
-  float aq[E], ak[E], qi[E], ki[E];
-  int hf[E];
-  if (rowok) {
-    LM::load(proj + (size_t)i * F5 + qoff, lane, F, qi);
-    LM::load(proj + (size_t)i * F5 + koff, lane, F, ki);
-  }
+  float aq[TN], ak[TN], qi[TN], ki[TN];
+  int hf[TN];
 #pragma unroll
-  for (int e2 = 0; e2 < E; ++e2) {
-    aq[e2] = ak[e2] = 0.f;
-    if (!rowok) qi[e2] = ki[e2] = 0.f;
-    const int f = LM::feature(lane, e2);
-    hf[e2] = (f < F) ? f / (F / heads) : 0;
+  for (int t = 0; t < TN; ++t) {
+    aq[t] = ak[t] = 0.f;
+    const int f = lane + 32 * t;
+    const bool ok = rowok && f < F;
+    qi[t] = ok ? proj[(size_t)i * F5 + qoff + f] : 0.f;
+    ki[t] = ok ? proj[(size_t)i * F5 + koff + f] : 0.f;
+    hf[t] = (f < F) ? f / (F / heads) : 0;
   }
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
@@ -524,21 +663,27 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       }
     }
     __syncwarp();
-    // Two edges per batch, two batches in flight: the row loads of the NEXT batch are issued before the current one is
-    // consumed (explicit double buffering with pinned loads).  Indices beyond the chunk are clamped (valid addresses),
-    // their terms masked.
-    auto load_batch = [&](int q, float (&wv)[2][E], float (&kj)[2][E], float (&qj)[2][E], int (&pp)[2]) {
+    // Two edges per batch, two batches in flight: the 6 * TN row loads of the NEXT batch are issued before the current
+    // one is consumed (explicit double buffering -- left to itself ptxas sinks the loads towards their first use and
+    // the kernel becomes latency-bound).  Indices beyond the chunk are clamped (valid addresses), their terms masked.
+    auto load_batch = [&](int q, float (&wv)[2][TN], float (&kj)[2][TN], float (&qj)[2][TN], int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int qc = (q + k < cnt) ? q + k : cnt - 1;
         pp[k] = s_p[w][qc];
         const float* pj = proj + (size_t)s_j[w][qc] * F5;
-        LM::load(wst + (size_t)(pp[k] & 0x7fffffff) * F, lane, F, wv[k]);
-        LM::load(pj + koff, lane, F, kj[k]);
-        LM::load(pj + qoff, lane, F, qj[k]);
+        const float* pw = wst + (size_t)(pp[k] & 0x7fffffff) * F;
+#pragma unroll
+        for (int t = 0; t < TN; ++t) {
+          const int f = lane + 32 * t;
+          const bool ok = (t + 1 < TN) || f < F;
+          wv[k][t] = ok ? ld_pinned(pw + f) : 0.f;
+          kj[k][t] = ok ? ld_pinned(pj + koff + f) : 0.f;
+          qj[k][t] = ok ? ld_pinned(pj + qoff + f) : 0.f;
+        }
       }
     };
-    auto use_batch = [&](int q, const float (&wv)[2][E], const float (&kj)[2][E], const float (&qj)[2][E],
+    auto use_batch = [&](int q, const float (&wv)[2][TN], const float (&kj)[2][TN], const float (&qj)[2][TN],
                          const int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -548,18 +693,18 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
         const float* ab = &s_ab[w][qc * 8];
         const float* abr = &s_abr[w][qc * 8];
         const bool canon = (pp[k] < 0) && live;
-        float wb[E];
+        float* wb = wbar + (size_t)(pp[k] & 0x7fffffff) * F;
 #pragma unroll
-        for (int e2 = 0; e2 < E; ++e2) {
-          const float a0 = ab[hf[e2]], a1 = abr[hf[e2]];
-          aq[e2] = fmaf(m * a0 * wv[k][e2], kj[k][e2], aq[e2]);
-          ak[e2] = fmaf(m * a1 * wv[k][e2], qj[k][e2], ak[e2]);
-          wb[e2] = fmaf(a0 * qi[e2], kj[k][e2], a1 * qj[k][e2] * ki[e2]);
+        for (int t = 0; t < TN; ++t) {
+          const float a0 = ab[hf[t]], a1 = abr[hf[t]];
+          aq[t] = fmaf(m * a0 * wv[k][t], kj[k][t], aq[t]);
+          ak[t] = fmaf(m * a1 * wv[k][t], qj[k][t], ak[t]);
+          const int f = lane + 32 * t;
+          if (canon && ((t + 1 < TN) || f < F)) __stcs(wb + f, fmaf(a0 * qi[t], kj[k][t], a1 * qj[k][t] * ki[t]));
         }
-        if (canon) LM::store(wbar + (size_t)(pp[k] & 0x7fffffff) * F, lane, F, wb);
       }
     };
-    float wA[2][E], kA[2][E], qA[2][E], wB[2][E], kB[2][E], qB[2][E];
+    float wA[2][TN], kA[2][TN], qA[2][TN], wB[2][TN], kB[2][TN], qB[2][TN];
     int pA[2], pB[2];
     load_batch(0, wA, kA, qA, pA);
     for (int q = 0; q < cnt; q += 4) {
@@ -571,8 +716,15 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
     __syncwarp();
   }
   if (rowok) {
-    LM::store(gproj + (size_t)i * F5 + qoff, lane, F, aq);
-    LM::store(gproj + (size_t)i * F5 + koff, lane, F, ak);
+    float* gi = gproj + (size_t)i * F5;
+#pragma unroll
+    for (int t = 0; t < TN; ++t) {
+      const int f = lane + 32 * t;
+      if (f < F) {
+        gi[qoff + f] = aq[t];
+        gi[koff + f] = ak[t];
+      }
+    }
   }
 }
 
@@ -765,38 +917,61 @@ void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, co
 #undef SO3K_AGG_CASE
 }
 
-// NV / TAIL of the lane map for an F-wide row (LaneMap): F <= 128: one chunk per lane; 128 < F <= 160: + tail scalar;
-// else two chunks per lane (F <= 256)
-#define SO3K_LANEMAP_DISPATCH(F_, CALL)                  \
-  do {                                                   \
-    if ((F_) <= 128) { CALL(1, false); }                 \
-    else if ((F_) <= 160) { CALL(1, true); }             \
-    else { CALL(2, false); }                             \
-  } while (0)
-
 void so3k_launch_alpha_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
                                  const float* wst_f, const float* wst_g, float* alpha, float* x1, float* chi1,
                                  cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
-  const size_t smem = sizeof(float) * WPB * 4 * (size_t)so3k_spw(D.F);      // product staging: 2 edges x 2 blocks per warp
-#define SO3K_AA_CALL(NV_, TAIL_)                                                                                     \
-  SO3K_SET_MAX_SMEM((k_alpha_aggregate<NV_, TAIL_>), smem);                                                          \
-  SO3K_LAUNCH((k_alpha_aggregate<NV_, TAIL_>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), smem, st, D, g.N, Ast,     \
-              g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1)
-  SO3K_LANEMAP_DISPATCH(D.F, SO3K_AA_CALL);
-#undef SO3K_AA_CALL
+  if (so3k_scan_ok(D.F, D.H) && so3k_scan_ok(D.F, D.nl)) {
+    if (D.F > 128)
+      SO3K_LAUNCH(k_alpha_aggregate_scan<true>, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,
+                  g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);
+    else
+      SO3K_LAUNCH(k_alpha_aggregate_scan<false>, dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,
+                  g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);
+    return;
+  }
+#define SO3K_AA_CASE(TN_)                                                                                              \
+  case TN_:                                                                                                            \
+    if (D.H <= 4 && D.nl <= 4)                                                                                         \
+      SO3K_LAUNCH((k_alpha_aggregate<TN_, 4, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
+                  g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
+    else                                                                                                               \
+      SO3K_LAUNCH((k_alpha_aggregate<TN_, 8, 0, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast,    \
+                  g.rowptr, g.col, g.pid, g.geom, x, chi, proj, wst_f, wst_g, alpha, x1, chi1);                        \
+    break;
+  // (compile-time head widths, as in so3k_launch_alpha_bwd, bring nothing here: 7.3 ms per step either way -- the kernel
+  //  is bound by its 50 row loads per iteration, and with cheaper arithmetic ptxas keeps fewer of them in flight)
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_AA_CASE(1) SO3K_AA_CASE(2) SO3K_AA_CASE(3) SO3K_AA_CASE(4) SO3K_AA_CASE(5) SO3K_AA_CASE(6) SO3K_AA_CASE(7)
+    SO3K_AA_CASE(8)
+    default: break;
+  }
+#undef SO3K_AA_CASE
 }
 
 void so3k_launch_alpha_bwd(const So3kDims& D, const Graph& g, const float* proj, const float* alpha,
                            const float* xbar1, const float* chibar1, float* alphabar, float* gproj, cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
-  const size_t smem = sizeof(float) * WPB * 4 * (size_t)so3k_spw(D.F);      // product staging: 4 edges per warp
-#define SO3K_AB_CALL(NV_, TAIL_)                                                                                      \
-  SO3K_SET_MAX_SMEM((k_alpha_bwd<NV_, TAIL_>), smem);                                                                 \
-  SO3K_LAUNCH((k_alpha_bwd<NV_, TAIL_>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), smem, st, D, g.N, Ast, g.rowptr,  \
-              g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj)
-  SO3K_LANEMAP_DISPATCH(D.F, SO3K_AB_CALL);
-#undef SO3K_AB_CALL
+#define SO3K_AB_CASE(TN_)                                                                                              \
+  case TN_:                                                                                                            \
+    if (D.H <= 4)                                                                                                      \
+      SO3K_LAUNCH((k_alpha_bwd<TN_, 4, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,   \
+                  g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
+    else                                                                                                               \
+      SO3K_LAUNCH((k_alpha_bwd<TN_, 8, 0>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,   \
+                  g.col, g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);                                 \
+    break;
+  if (D.F == 132 && D.H == 4) {                    // the reference's default shape: head boundaries known at compile time
+    SO3K_LAUNCH((k_alpha_bwd<5, 4, 33>), dim3(so3k_cdiv(g.N, WPB)), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr, g.col,
+                g.rev, g.geom, proj, alpha, xbar1, chibar1, alphabar, gproj);
+    return;
+  }
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_AB_CASE(1) SO3K_AB_CASE(2) SO3K_AB_CASE(3) SO3K_AB_CASE(4) SO3K_AB_CASE(5) SO3K_AB_CASE(6) SO3K_AB_CASE(7)
+    SO3K_AB_CASE(8)
+    default: break;
+  }
+#undef SO3K_AB_CASE
 }
 
 // wst / wbar: [block][pair capacity][F] (block stride = so3k_pair_capacity(Pt) * F floats)
@@ -805,11 +980,17 @@ void so3k_launch_qk_bwd_stream(const So3kDims& D, const Graph& g, const float* p
                                cudaStream_t st) {
   int Ast = (D.H + D.nl + 3) & ~3;
   const size_t blk_stride = (size_t)so3k_pair_capacity(g.Pt) * D.F;
-#define SO3K_QK_CALL(NV_, TAIL_)                                                                                       \
-  SO3K_LAUNCH((k_qk_bwd_stream<NV_, TAIL_>), dim3(so3k_cdiv(g.N, WPB), 2), dim3(WPB * 32), 0, st, D, g.N, Ast,         \
-              g.rowptr, g.col, g.rev, g.pid, g.geom, proj, alpha, alphabar, wst, blk_stride, gproj, ebar, wbar)
-  SO3K_LANEMAP_DISPATCH(D.F, SO3K_QK_CALL);
-#undef SO3K_QK_CALL
+#define SO3K_QK_CASE(TN_)                                                                                              \
+  case TN_:                                                                                                            \
+    SO3K_LAUNCH(k_qk_bwd_stream<TN_>, dim3(so3k_cdiv(g.N, WPB), 2), dim3(WPB * 32), 0, st, D, g.N, Ast, g.rowptr,      \
+                g.col, g.rev, g.pid, g.geom, proj, alpha, alphabar, wst, blk_stride, gproj, ebar, wbar);               \
+    break;
+  switch (so3k_cdiv(D.F, 32)) {
+    SO3K_QK_CASE(1) SO3K_QK_CASE(2) SO3K_QK_CASE(3) SO3K_QK_CASE(4) SO3K_QK_CASE(5) SO3K_QK_CASE(6) SO3K_QK_CASE(7)
+    SO3K_QK_CASE(8)
+    default: break;
+  }
+#undef SO3K_QK_CASE
 }
 
 void so3k_launch_chi_bwd(const So3kDims& D, const Graph& g, const float* chi, const float* gbar,

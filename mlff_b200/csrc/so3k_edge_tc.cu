@@ -30,9 +30,9 @@
 //   k_filter_tc       records -> radial-basis operand image -> GEMM1 -> epilogue 1 (TMEM in place) -> GEMM2 (A from
 //                     TMEM) -> + bias -> staging tile -> one bulk copy (cp.async.bulk) of the tile's 128 x F block of w
 //   k_edge_bwd2_tc    wbar tile -> operand image -> GEMM3 (hbar = wbar W2c^T) in three column chunks with their own
-//                     completion barriers, so the epilogue of chunk c runs under the MMAs of chunk c+1; pre-activations
-//                     and the forward-mode radial derivative from two GEMM1s (rbf from shared memory, rbf' from tensor
-//                     memory); epilogue: radial cotangent dbar and l0-contraction cotangents gbar on the canonical edge
+//                     completion barriers; pre-activations from GEMM1; epilogue phase 1 writes u = hbar silu'(a) in place
+//                     as the A operand of GEMM4 (rbfbar = u W1^T); phase 2 contracts rbfbar with d rbf / d d: radial
+//                     cotangent dbar and l0-contraction cotangents gbar on the canonical edge
 // Algorithmic FLOPs per k_filter_tc launch: 2 C (K F + F^2 + nl F/4 + F^2/4), C pairs; the tensor pipe
 // issues 3x that on padded shapes (Fp x KC).
 #include "so3k_internal.h"
@@ -119,9 +119,9 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   t.w_bytes = t.off_W2 + 2 * t.szW2;
   t.n_small = t.KC + t.Fp + D.nl * t.KC;
   const uint32_t small_b = ((uint32_t)t.n_small * 4u + 127u) & ~127u;
-  // filter kernel: weights | A0 hi,lo | staging tile [TM][F] fp32 | small
+  // filter kernel: weights | A0 hi,lo x 2 buffers | staging tile [TM][F] fp32 | small
   t.f_A0 = t.w_bytes;
-  t.f_stage = t.f_A0 + 2 * t.szA0;
+  t.f_stage = t.f_A0 + 4 * t.szA0;
   t.f_small = t.f_stage + (((uint32_t)TM * D.F * 4u + 127u) & ~127u);
   t.f_total = t.f_small + small_b;
   // backward part 2: weights | A0 hi,lo (rbf) | wbar image hi,lo | reduction slots [3][nl + 1][TM] fp32 | small
@@ -333,15 +333,15 @@ __device__ __forceinline__ RowRec<NL> tc_load_rec(int c, int nv, const float* __
   return m;
 }
 
-// S0: the radial-basis operand image (K-major, shared memory) of ONE row r, all K0 / 8 chunks.
+// S0: the radial-basis operand image (K-major, shared memory) of ONE row r, chunks c_first, c_first + c_step, .. of K0 / 8.
 // WITH_D additionally writes d rbf / d d as a TMEM operand image (packed bf16: hi at tAI + 4 c, lo at tAI + K0/2 + 4 c).
 template <bool WITH_D>
 __device__ __forceinline__ void tc_row_s0(const So3kDims& D, const TcDims& T, unsigned char* A0hi, unsigned char* A0lo,
-                                          int r, bool valid, float d, uint32_t tAI_lane) {
+                                          int r, bool valid, float d, uint32_t tAI_lane, int c_first = 0, int c_step = 1) {
   const float ed = __expf(-d);
   const float ng = -D.gamma * 1.4426950408889634f;
-#pragma unroll 4
-  for (int c = 0; c < T.K0 / 8; ++c) {
+#pragma unroll 2
+  for (int c = c_first; c < T.K0 / 8; c += c_step) {
     float v[8], dv[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -395,16 +395,48 @@ __device__ __forceinline__ void tc_preact16(const TcW& S, int KC, int F, int c0,
   }
 }
 
+// Epilogue 2 of one thread: w = D2 + b2 for its row -> staging tile (row stride F: F mod 32 == 4 keeps the 16-byte
+// row-per-lane stores conflict-free), three 16-column units per tensor-memory wait, starting at unit u0.
+// (Spreading this drain over all 16 warps was measured: 3.97 ms per step against 3.75 ms with the helper warps alone --
+// the epilogue-1 warps are the critical resource, every tensor-memory load they add lengthens the tile.)
+__device__ __forceinline__ void f_drain_d2(const TcDims& T, const TcW& S, int F, uint32_t tD2_lane, int u0, float* srow) {
+  const int nu = T.Fp >> 4;
+  uint32_t v[3][16];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (u0 + k < nu) tc::tmem_ld16(tD2_lane + (uint32_t)(16 * (u0 + k)), v[k]);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int u = u0 + k;
+    if (u < nu) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int c = 16 * u + 4 * q4;
+        if (c < F) {                                           // F % 4 == 0: whole float4s
+          const float4 b = *reinterpret_cast<const float4*>(S.b2p + c);
+          *reinterpret_cast<float4*>(srow + c) =
+              make_float4(__uint_as_float(v[k][4 * q4]) + b.x, __uint_as_float(v[k][4 * q4 + 1]) + b.y,
+                          __uint_as_float(v[k][4 * q4 + 2]) + b.z, __uint_as_float(v[k][4 * q4 + 3]) + b.w);
+        }
+      }
+    }
+  }
+}
+
 #define TILE_E0(i) (((int)blockIdx.x + (i) * G) * TM)
 constexpr int N_EPI = 12 * 32;     // epilogue group: warps 0..11 = 4 TMEM lane quadrants x 3 column groups
 constexpr int N_AUX = 4 * 32;      // helper group: warps 12..15, one per lane quadrant; lane 0 of warp 12 issues the MMAs
 
 // Filter kernel: w[c][f] of one filter block for every canonical pair c.  Warp-specialised, tiles of this CTA
 // i = 0, 1, .. (global tile blockIdx.x + i * gridDim.x), two hidden-layer buffers D1[2] and one output accumulator D2:
-//   epilogue group (12 warps), tile j:   wait GEMM1(j) | epilogue 1 in place on D1[j & 1] | arrive a1_ready[j & 1]
-//   helper group (4 warps), step i:      radial-basis image of tile i+2 -> issue GEMM1(i+2)
-//                                        wait GEMM2(i) | epilogue 2 (i) -> staging tile -> bulk store
+//   epilogue group (12 warps), tile j:   wait GEMM1(j) | radial-basis image of tile j+2 into A0[j & 1] -> arrive a0_ready |
+//                                        epilogue 1 in place on D1[j & 1] -> arrive a1_ready[j & 1]
+//   helper group (4 warps), step i:      wait a0_ready(i+2) -> issue GEMM1(i+2)
+//                                        wait GEMM2(i) | epilogue 2 (i) -> staging tile -> bulk store (i)
 //                                        wait a1_ready(i+1) -> issue GEMM2(i+1)
+// (the helper warps are latency-bound -- one warp per scheduler --, so they only keep what must be serial: MMA issue and
+// the drain of D2)
 // The tensor pipe executes MMAs in issue order: GEMM1(i+2) (which overwrites D1[i & 1]) is issued after GEMM2(i)
 // (which reads it), GEMM2(i+1) after epilogue 2 (i) has drained D2.
 template <int NL>
@@ -413,7 +445,7 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
             const unsigned char* __restrict__ img, const float* __restrict__ small_g, float* __restrict__ wst,
             int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bars[5];                  // 0,1: GEMM1 of buffer 0 / 1 ; 2: GEMM2 ; 3,4: a1_ready of buffer 0 / 1
+  __shared__ uint64_t bars[7];                  // 0,1: GEMM1 of buffer 0 / 1 ; 2: GEMM2 ; 3,4: a1_ready ; 5,6: a0_ready of buffer 0 / 1
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_abort;
 
@@ -421,8 +453,7 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
   const int r = 32 * (warp & 3) + lane;      // row of the tile == TMEM lane
   const int F = D.F;
   const TcW S = tc_weights(smem, T, T.f_small);
-  unsigned char* A0hi = smem + T.f_A0;
-  unsigned char* A0lo = A0hi + T.szA0;
+  unsigned char* const A0base = smem + T.f_A0;       // buffer b: hi at A0base + 2 b szA0, lo at + szA0
   float* stage = reinterpret_cast<float*>(smem + T.f_stage);
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
@@ -432,6 +463,8 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
     tc::mbar_init(&bars[2], 1);
     tc::mbar_init(&bars[3], N_EPI);
     tc::mbar_init(&bars[4], N_EPI);
+    tc::mbar_init(&bars[5], N_EPI);
+    tc::mbar_init(&bars[6], N_EPI);
     tc::mbar_fence_init();
     s_abort = 0;
   }
@@ -454,9 +487,19 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
     // ================= epilogue group: hidden activations, in place in tensor memory ===========================
     const int cq = warp >> 2;                         // k-steps cq, cq + 3, cq + 6, cq + 9
     const int nks = T.KC >> 4;
-    RowRec<NL> rc = tc_load_rec<NL>(n_my > 0 ? TILE_E0(0) + r : nv, nv, rec);
+    // radial-basis image of tile t (this thread: chunks cq, cq + 3, .. of its row) into buffer t & 1
+    auto image = [&](int t, float d) {
+      unsigned char* hi = A0base + (size_t)(t & 1) * 2 * T.szA0;
+      tc_row_s0<false>(D, T, hi, hi + T.szA0, r, TILE_E0(t) + r < nv, d, 0u, cq, 3);
+      tc::fence_async_smem();
+      mbar_arrive(&bars[5 + (t & 1)]);
+    };
+    RowRec<NL> rc = tc_load_rec<NL>(n_my > 0 ? TILE_E0(0) + r : nv, nv, rec);              // tile j
+    RowRec<NL> rc1 = tc_load_rec<NL>(n_my > 1 ? TILE_E0(1) + r : nv, nv, rec);             // tile j + 1
+    if (n_my > 0) image(0, rc.d);
+    if (n_my > 1) image(1, rc1.d);
     for (int j = 0; j < n_my; ++j) {
-      const RowRec<NL> rcn = tc_load_rec<NL>(j + 1 < n_my ? TILE_E0(j + 1) + r : nv, nv, rec);
+      const RowRec<NL> rc2 = tc_load_rec<NL>(j + 2 < n_my ? TILE_E0(j + 2) + r : nv, nv, rec);
       const uint32_t tD = TD1(j) + lane_sel;
       long long tq_ = TC_TIMING ? clock64() : 0;
       tc_wait(&bars[j & 1], (uint32_t)((j >> 1) & 1), &s_abort);
@@ -466,6 +509,8 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
         atomicAdd(&g_tc_phase[0][8], (unsigned long long)(now_ - tq_));
         tq_ = now_;
       }
+      // GEMM1(j) has consumed image buffer j & 1: the image of tile j + 2 goes there
+      if (j + 2 < n_my) image(j + 2, rc2.d);
       // two accumulator loads in flight: the unit being processed and the next one
       uint32_t v[2][16];
       if (cq < nks && 16 * cq < F) tc::tmem_ld16(tD + (uint32_t)(16 * cq), v[0]);
@@ -496,32 +541,25 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
       tc::fence_before_sync();
       mbar_arrive(&bars[3 + (j & 1)]);
       if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[0][9], (unsigned long long)(clock64() - tq_));
-      rc = rcn;
+      rc = rc1;
+      rc1 = rc2;
     }
   } else {
     // ================= helper group: radial-basis images, MMA issue, epilogue 2 + bulk store ====================
     const bool issuer = tid == ISSUER;
-    RowRec<NL> rc1 = tc_load_rec<NL>(n_my > 0 ? TILE_E0(0) + r : nv, nv, rec);          // tile i + 2
     for (int i = -2; i < n_my; ++i) {
       const bool has0 = i >= 0, has1 = i + 1 >= 0 && i + 1 < n_my, has2 = i + 2 < n_my;
       long long t_prev_ = TC_TIMING ? clock64() : 0;
-      const RowRec<NL> rc2 = tc_load_rec<NL>(i + 3 < n_my ? TILE_E0(i + 3) + r : nv, nv, rec);
-      // ---- radial-basis image of tile i + 2, then GEMM1(i + 2) ------------------------------------------------------
-      if (has2) {
-        if (has1) {                                   // GEMM1(i+1) has consumed the image buffer
-          tc_wait(&bars[(i + 1) & 1], (uint32_t)(((i + 1) >> 1) & 1), &s_abort);
-        }
-        TC_PHASE(0, 0);
-        tc_row_s0<false>(D, T, A0hi, A0lo, r, TILE_E0(i + 2) + r < nv, rc1.d, 0u);
-        tc::fence_async_smem();
-        group_bar(1, N_AUX);
-        TC_PHASE(0, 1);
-        if (issuer) {
-          tc::fence_after_sync();
-          tc_issue_gemm_ss(TD1(i + 2), A0hi, A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idescF);
-          tc::commit(&bars[(i + 2) & 1]);
-        }
+      // ---- GEMM1(i + 2) as soon as its radial-basis image is there (it follows GEMM2(i), issued last step, in the pipe:
+      //      it overwrites D1[i & 1], GEMM2(i)'s A operand) -----------------------------------------------------------------
+      if (has2 && issuer) {
+        tc_wait(&bars[5 + ((i + 2) & 1)], (uint32_t)(((i + 2) >> 1) & 1), &s_abort);
+        tc::fence_after_sync();
+        unsigned char* hi = A0base + (size_t)((i + 2) & 1) * 2 * T.szA0;
+        tc_issue_gemm_ss(TD1(i + 2), hi, hi + T.szA0, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idescF);
+        tc::commit(&bars[(i + 2) & 1]);
       }
+      TC_PHASE(0, 1);
       // ---- epilogue 2 of tile i: w = D2 + b2 -> staging tile (row stride F: F mod 32 == 4 keeps the 16-byte
       //      row-per-lane stores conflict-free) -> one bulk copy ------------------------------------------------------------
       if (has0) {
@@ -531,34 +569,9 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
         // the previous tile's bulk store must have finished READING the staging tile
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         group_bar(1, N_AUX);
-        const int nu = T.Fp >> 4;
-        float* srow = stage + (size_t)r * F;
-        // batches of three 16-column units: the three loads queue back to back at the tensor-memory port
 #pragma unroll
-        for (int u0 = 0; u0 < 12; u0 += 3) {                         // Fp <= 160: at most 10 units
-          if (u0 < nu) {
-            uint32_t v[3][16];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-              if (u0 + k < nu) tc::tmem_ld16(tD2 + lane_sel + (uint32_t)(16 * (u0 + k)), v[k]);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              if (u0 + k < nu) {
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const int c = 16 * (u0 + k) + 4 * q4;
-                  if (c < F) {                                       // F % 4 == 0: whole float4s
-                    const float4 b = *reinterpret_cast<const float4*>(S.b2p + c);
-                    *reinterpret_cast<float4*>(srow + c) =
-                        make_float4(__uint_as_float(v[k][4 * q4]) + b.x, __uint_as_float(v[k][4 * q4 + 1]) + b.y,
-                                    __uint_as_float(v[k][4 * q4 + 2]) + b.z, __uint_as_float(v[k][4 * q4 + 3]) + b.w);
-                  }
-                }
-              }
-            }
-          }
-        }
+        for (int u0 = 0; u0 < 12; u0 += 3)                           // Fp <= 160: at most 10 units
+          if (u0 < (T.Fp >> 4)) f_drain_d2(T, S, F, tD2 + lane_sel, u0, stage + (size_t)r * F);
         TC_PHASE(0, 3);
         tc::fence_async_smem();                  // staging tile (generic proxy) -> visible to the bulk-copy engine
         tc::fence_before_sync();
@@ -583,7 +596,6 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
       }
       TC_PHASE(0, 5);
       if (TC_TIMING && has0 && blockIdx.x == 0 && tid == TC_TIMER) atomicAdd(&g_tc_phase[0][15], 1ull);
-      rc1 = rc2;
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -595,15 +607,18 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
 }
 
 // One warp's share of the filter-cotangent operand image of a tile (bf16 hi / lo, canonical K-major layout in shared
-// memory) from the tile's contiguous block of pair rows: work item = (8 rows, 4 chunks of 8 columns), lane -> (row =
-// lane / 4, chunk = lane % 4); warp `wq` of `nwarps` takes items wq, wq + nwarps, ..; all loads are issued before the
-// first split (the block was prefetched into L2 a tile earlier).
+// memory) from the tile's contiguous block of fp32 pair rows: work item = (8 rows, 4 chunks of 8 columns), lane -> (row =
+// lane / 4, chunk = lane % 4); warp `wq` of `nwarps` takes items wq, wq + nwarps, ..  ALL of a warp's loads are issued
+// before the first split: the rows come from HBM (k_qk_bwd_stream streamed them out just before), and one exposed latency
+// per tile is what this costs.  (Writing the images where the cotangents are produced and landing them with a bulk copy
+// was measured: backward part 2 8.3 -> 6.75 ms per step, but the producer's 2-byte scattered stores took it from 8.0 to
+// 21 ms.)
+template <int BATCH>
 __device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int wq, int nwarps, int lane, int e0, int ne,
                                               const float* __restrict__ wbar, unsigned char* Wbhi, unsigned char* Wblo) {
   const int nchunkF = T.Fp / 8;
   const int ncg = (nchunkF + 3) / 4;
   const int nitems = 16 * ncg;
-  constexpr int BATCH = 5;                     // 16 warps: 16 * ceil(Fp / 32) / 16 <= 5 items per warp for Fp <= 160
   for (int it0 = wq; it0 < nitems; it0 += nwarps * BATCH) {
     float4 wa[BATCH], wb2[BATCH];
 #pragma unroll
@@ -639,21 +654,23 @@ __device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int wq, in
 
 // Backward part 2: radial cotangent and l0-contraction cotangent of one filter block.
 // Rows are canonical pairs; the pair's filter cotangent wbar[c][f] comes from k_qk_bwd_stream as a contiguous tile.
-//   hbar = wbar @ W2c^T                                                 (GEMM3: the W2c image consumed MN-major)
-//   dbar_rad[e] += sum_c hbar[c] silu'(a1[c]) (rbf'(d) @ W1)[c]         (a1 and the forward-mode term from 2 GEMM1s)
-//   gbar[e][l]  += sum_c hbar_s[c] silu'(a_s[c]) Ws1[l][c]
-// Tensor-memory columns: a1 at 0 (N = Fp) | forward-mode derivative at F (N = Fp; its first padding columns overwrite
-// a1's padding, harmless) | hbar at 2F (N = KC, written after the two GEMM1s) | rbf' operand image (K0 columns).
-// Warp-specialised like the filter kernel:
-//   helper group (4 warps), tile i:    wait GEMM3(i-1) | radial-basis images (i) | wait epilogue(i-1) done -> issue the
-//                                      GEMM1s | its share of the wbar operand image | wait image-ready -> issue GEMM3
-//                                      (three column chunks, one completion barrier each) | prefetch of the next
-//                                      cotangent tile into L2
-//   epilogue group (12 warps), tile i: its share of the wbar operand image (i) -> arrive image-ready | per 16-column
-//                                      unit: wait its chunk | silu' epilogue | slots -> group barrier -> totals to the
-//                                      canonical edge | arrive epilogue-done
-// (all 16 warps build the operand image: with only the helper warps loading, the L2 latency of their few batches was
-// exposed four times per tile)
+//   hbar = wbar @ W2c^T                                  (GEMM3: the W2c image consumed MN-major, three column chunks)
+//   u[c] = hbar[c] silu'(a[c])                           (a1 from GEMM1, a_s from the pair's l0 contractions)
+//   rbfbar = u_rad @ W1^T                                (GEMM4: u written IN PLACE over hbar as a tensor-memory A operand,
+//                                                         the W1 image consumed MN-major)
+//   dbar[e] += sum_k rbfbar[k] d rbf_k / d d ,   gbar[e][l] += sum_c u_s[c] Ws1[l][c]
+// Reverse mode through the first layer: the forward-mode variant of round 1 (a second GEMM1 on d rbf / d d and a dot
+// product per hidden unit) read THREE accumulators per hidden unit with tcgen05.ld; tensor-memory reads run at ~43 B per
+// clock and SM and were the kernel's floor (33 sixteen-column loads per scheduler and tile).  Here the epilogue reads
+// hbar and a1 (20 loads), writes u back (tcgen05.st is 4x faster) and reads 32 columns of rbfbar.
+// Tensor-memory columns: a1 at 0 (N = Fp) | hbar / u at Fp (N = KC) | rbfbar at Fp + KC (N = K0).
+// Warp-specialised:
+//   epilogue group (12 warps), tile i:  phase 1: per 16-column unit wait its GEMM3 chunk | u | tcgen05.st -> arrive u_ready
+//                                       operand image of the cotangents of tile i+1 (under GEMM4) -> arrive image_ready
+//                                       phase 2: wait GEMM4 | rbfbar . rbf' | slots -> group barrier -> totals to the
+//                                       canonical edge
+//   helper group (4 warps), tile i:     wait u_ready(i-1) -> issue GEMM4(i-1), GEMM1(i) | wait image_ready(i) -> issue
+//                                       GEMM3(i) | wait GEMM1(i) | radial-basis image of tile i+1
 template <int NL>
 __global__ void __launch_bounds__(NT, 1)
 k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, const int* __restrict__ n_canon,
@@ -661,7 +678,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
                const float* __restrict__ small_g, const float* __restrict__ wbar, float* __restrict__ gbar,
                float* __restrict__ ebar, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bars[6];                  // 0: GEMM1s ; 1..3: GEMM3 chunks ; 4: epilogue done (N_EPI) ; 5: image ready (NT)
+  __shared__ uint64_t bars[7];                  // 0: GEMM1 ; 1..3: GEMM3 chunks ; 4: u_ready (N_EPI) ; 5: image_ready (N_EPI) ; 6: GEMM4
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_abort;
 
@@ -679,7 +696,8 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   if (tid == 0) {
     for (int k = 0; k < 4; ++k) tc::mbar_init(&bars[k], 1);
     tc::mbar_init(&bars[4], N_EPI);
-    tc::mbar_init(&bars[5], NT);
+    tc::mbar_init(&bars[5], N_EPI);
+    tc::mbar_init(&bars[6], 1);
     tc::mbar_fence_init();
     s_abort = 0;
   }
@@ -689,10 +707,8 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tD1 = tmem, tD1p = tmem + (uint32_t)F, tD3 = tmem + 2u * (uint32_t)F;
-  const uint32_t tAI = tD3 + (uint32_t)T.KC;                       // rbf' image: hi (K0/2 columns) | lo (K0/2 columns)
+  const uint32_t tD1 = tmem, tD3 = tmem + (uint32_t)T.Fp, tD4 = tD3 + (uint32_t)T.KC;
   const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
-  const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
   const int nv = (*n_canon < pair_cap) ? *n_canon : pair_cap;
   const int n_tiles = (nv + TM - 1) / TM;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -703,16 +719,18 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   if (warp < 12) {
     // ================= epilogue group ==============================================================================
     const int cq = warp >> 2;                                      // units cq, cq + 3, cq + 6, cq + 9
+    auto wbar_image = [&](int t) {                                 // 16 * ceil(Fp / 32) = 80 items over 12 warps: one batch of 7
+      const int e1 = TILE_E0(t);
+      tc_wbar_image<7>(T, F, warp, 12, lane, e1, (nv - e1) < TM ? (nv - e1) : TM, wbar, Wbhi, Wblo);
+      tc::fence_async_smem();
+      mbar_arrive(&bars[5]);
+    };
+    if (n_my > 0) wbar_image(0);
     for (int i = 0; i < n_my; ++i) {
       const int e0 = TILE_E0(i);
       const int ne = (nv - e0) < TM ? (nv - e0) : TM;
       const uint32_t par = (uint32_t)(i & 1);
       const RowRec<NL> rc = tc_load_rec<NL>(e0 + r, nv, rec);
-      // this warp's share of the cotangent operand image, once the last chunk of the previous tile's GEMM3 has read the old one
-      if (i > 0) tc_wait(&bars[nch], (uint32_t)((i - 1) & 1), &s_abort);
-      tc_wbar_image(T, F, warp, 16, lane, e0, ne, wbar, Wbhi, Wblo);
-      tc::fence_async_smem();
-      mbar_arrive(&bars[5]);
       // canonical edge of this row and, for the second block's launch, the totals already there (loaded early: their
       // latency hides under the epilogue)
       const bool writer = cq == 0 && r < ne;
@@ -725,7 +743,6 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
 #pragma unroll
         for (int l = 0; l < NL; ++l) old[1 + l] = gbar[e * Gst + l];
       }
-      float dbar = 0.f;
       float gb[NL];
 #pragma unroll
       for (int l = 0; l < NL; ++l) gb[l] = 0.f;
@@ -737,51 +754,89 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         atomicAdd(&g_tc_phase[2][8], (unsigned long long)(now_ - tq_));
         tq_ = now_;
       }
+      // ---- phase 1: u = hbar silu'(a), radial part written back in place as the A operand of GEMM4 --------------------------
       for (int it = 0; it < 4; ++it) {
         const int u = cq + 3 * it;
         if (u >= nks) break;                                       // warp-uniform
         tc_wait(&bars[1 + (u >> 2)], par, &s_abort);
         tc::fence_after_sync();
         const int c0 = 16 * u;
-        uint32_t hb[16], a1[16], tp[16];
+        uint32_t hb[16], a1[16];
         tc::tmem_ld16(tD3 + lane_sel + (uint32_t)c0, hb);
-        if (c0 < F) {
-          tc::tmem_ld16(tD1 + lane_sel + (uint32_t)c0, a1);
-          tc::tmem_ld16(tD1p + lane_sel + (uint32_t)c0, tp);
-        }
+        if (c0 < F) tc::tmem_ld16(tD1 + lane_sel + (uint32_t)c0, a1);
         tc::tmem_ld_wait();
         float a[16];
         tc_preact16<NL>(S, T.KC, F, c0, a1, rc.g, a);
-        if (c0 + 16 <= F) {                                        // radial unit: no per-element control flow
+        float uu[16];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            float s[4];
-            sigmoid4(a + 4 * q4, s);
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float s[4];
+          sigmoid4(a + 4 * q4, s);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              // silu'(x) = s (1 + x (1 - s)) with x = -ln(2) a'
-              const float dy = s[q] * fmaf(a[4 * q4 + q], fmaf(s[q], kLn2, kNegLn2), 1.0f);
-              dbar = fmaf(__uint_as_float(hb[4 * q4 + q]) * dy, __uint_as_float(tp[4 * q4 + q]), dbar);
-            }
+          for (int q = 0; q < 4; ++q) {
+            // silu'(x) = s (1 + x (1 - s)) with x = -ln(2) a'
+            const float dy = s[q] * fmaf(a[4 * q4 + q], fmaf(s[q], kLn2, kNegLn2), 1.0f);
+            uu[4 * q4 + q] = __uint_as_float(hb[4 * q4 + q]) * dy;
           }
-        } else {                                                   // unit with spherical / padding columns
+        }
+        if (c0 + 16 > F) {                                         // unit with spherical / padding columns
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            float s[4];
-            sigmoid4(a + 4 * q4, s);
             float as4[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int c = c0 + 4 * q4 + q;
-              const float dy = s[q] * fmaf(a[4 * q4 + q], fmaf(s[q], kLn2, kNegLn2), 1.0f);
-              as4[q] = (c < F + Fs) ? __uint_as_float(hb[4 * q4 + q]) * dy : 0.f;
-              if (c < F) dbar = fmaf(as4[q], __uint_as_float(tp[4 * q4 + q]), dbar);
+              as4[q] = (c >= F && c < F + Fs) ? uu[4 * q4 + q] : 0.f;
+              if (c >= F) uu[4 * q4 + q] = 0.f;                    // not a radial unit: zero in the GEMM4 operand
             }
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
               const float4 w4 = *reinterpret_cast<const float4*>(S.Wsx + l * T.KC + c0 + 4 * q4);
               gb[l] = fmaf(as4[0], w4.x, fmaf(as4[1], w4.y, fmaf(as4[2], w4.z, fmaf(as4[3], w4.w, gb[l]))));
             }
+          }
+        }
+        if (c0 < T.Fp) {                                           // K range of GEMM4
+          uint32_t pk[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tc::split2(uu[2 * q], uu[2 * q + 1], &pk[q], &pk[8 + q]);
+          tc::tmem_st16(tD3 + lane_sel + (uint32_t)c0, pk);
+        }
+      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      mbar_arrive(&bars[4]);                                       // u_ready: a1 is free, GEMM4 may run
+      if (TC_TIMING && blockIdx.x == 0 && tid == 0) {
+        const long long now_ = clock64();
+        atomicAdd(&g_tc_phase[2][9], (unsigned long long)(now_ - tq_));
+        tq_ = now_;
+      }
+      // ---- under GEMM4: the operand image of the next tile's cotangents (GEMM3 of this tile is complete) --------------------
+      if (i + 1 < n_my) {
+        tc_wait(&bars[nch], par, &s_abort);
+        wbar_image(i + 1);
+      }
+      if (TC_TIMING && blockIdx.x == 0 && tid == 0) {
+        const long long now_ = clock64();
+        atomicAdd(&g_tc_phase[2][10], (unsigned long long)(now_ - tq_));
+        tq_ = now_;
+      }
+      // ---- phase 2: dbar = sum_k rbfbar[k] d rbf_k / d d  (this thread: the 16-wide k units cq, cq + 3, ..) ------------------
+      tc_wait(&bars[6], par, &s_abort);
+      tc::fence_after_sync();
+      float dbar = 0.f;
+      {
+        const float ed = __expf(-rc.d);
+        const float ng = -D.gamma * 1.4426950408889634f;
+        for (int ku = cq; 16 * ku < T.K0; ku += 3) {
+          uint32_t rb[16];
+          tc::tmem_ld16(tD4 + lane_sel + (uint32_t)(16 * ku), rb);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float t = ed - (D.mu0 + (float)(16 * ku + q) * D.dmu);
+            const float drb = ex2_approx(ng * t * t) * (2.0f * D.gamma * ed) * t;
+            dbar = fmaf(__uint_as_float(rb[q]), drb, dbar);
           }
         }
       }
@@ -806,12 +861,13 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
           if (l < D.nl) gbar[e * Gst + l] = old[1 + l] + s_red[o] + s_red[st + o] + s_red[2 * st + o];
         }
       }
-      mbar_arrive(&bars[4]);                                       // tensor memory and the slots are free for tile i + 1
-      if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[2][9], (unsigned long long)(clock64() - tq_));
+      if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[2][11], (unsigned long long)(clock64() - tq_));
     }
   } else {
     // ================= helper group ================================================================================
     const bool issuer = tid == ISSUER;
+    const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
+    const uint32_t idesc4 = tc::make_idesc_bf16(TM, T.K0, 0, 1);   // B = W1 image read MN-major
     auto prefetch_wbar = [&](int e0) {                             // a tile's contiguous block of filter cotangents -> L2
       if (e0 < nv) {
         const int nrow = (nv - e0) < TM ? (nv - e0) : TM;
@@ -820,64 +876,75 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         for (int k = tid - 12 * 32; k < nline; k += N_AUX) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)k * 128));
       }
     };
-    if (n_my > 0) prefetch_wbar(TILE_E0(0));
-    for (int i = 0; i < n_my; ++i) {
-      const int e0 = TILE_E0(i);
-      const int ne = (nv - e0) < TM ? (nv - e0) : TM;
-      long long t_prev_ = TC_TIMING ? clock64() : 0;
-      const RowRec<NL> rc = tc_load_rec<NL>(e0 + r, nv, rec);
-      if (i > 0) {
-        // GEMM3(i-1) has consumed the cotangent image, the GEMM1s(i-1) the radial-basis images
-        tc_wait(&bars[nch], (uint32_t)((i - 1) & 1), &s_abort);
-      }
-      TC_PHASE(2, 0);
-      // ---- radial-basis images of this tile: rbf -> shared memory, rbf' -> tensor memory -----------------------------------
-      tc_row_s0<true>(D, T, A0hi, A0lo, r, e0 + r < nv, rc.d, tAI + lane_sel);
-      tc::tmem_st_wait();
+    // radial-basis image of a tile (shared memory, single-buffered: the previous GEMM1 must have completed)
+    auto image = [&](int t) {
+      const RowRec<NL> rc = tc_load_rec<NL>(TILE_E0(t) + r, nv, rec);
+      tc_row_s0<false>(D, T, A0hi, A0lo, r, TILE_E0(t) + r < nv, rc.d, 0u);
       tc::fence_async_smem();
-      tc::fence_before_sync();
       group_bar(1, N_AUX);
-      TC_PHASE(2, 1);
-      if (issuer) {
-        // the epilogue group has drained the accumulators of tile i - 1
-        if (i > 0) tc_wait(&bars[4], (uint32_t)((i - 1) & 1), &s_abort);
-        tc::fence_after_sync();
-        // a1 (rbf from shared memory) and the forward-mode term (rbf' from tensor memory)
-        tc_issue_gemm_ss(tD1, A0hi, A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
-        tc_issue_gemm_ts(tD1p, tAI, tAI + (uint32_t)(T.K0 / 2), 8u, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
-        tc::commit(&bars[0]);
+    };
+    auto issue_gemm4 = [&]() {                                     // rbfbar[128 x K0] = u[128 x Fp] @ W1^T
+      const uint32_t bh = tc::smem_u32(S.W1hi), bl = tc::smem_u32(S.W1lo);
+      uint32_t acc = 0;
+      for (int ks = 0; ks < T.Fp / 16; ++ks) {
+        const uint32_t bo = (uint32_t)ks * 2u * T.sboW1;
+        const uint64_t b_hi = tc::make_desc(bh + bo, T.sboW1, 128u), b_lo = tc::make_desc(bl + bo, T.sboW1, 128u);
+        const uint32_t a_hi = tD3 + (uint32_t)(16 * ks), a_lo = a_hi + 8u;
+        tc::mma_bf16_ts(tD4, a_hi, b_hi, idesc4, acc);
+        tc::mma_bf16_ts(tD4, a_lo, b_hi, idesc4, 1);
+        tc::mma_bf16_ts(tD4, a_hi, b_lo, idesc4, 1);
+        acc = 1;
       }
-      // ---- this warp's share of the cotangent operand image ---------------------------------------------------------------
-      tc_wbar_image(T, F, warp, 16, lane, e0, ne, wbar, Wbhi, Wblo);
-      tc::fence_async_smem();
-      mbar_arrive(&bars[5]);
-      TC_PHASE(2, 2);
+      tc::commit(&bars[6]);
+    };
+    if (n_my > 0) {
+      if (n_my > 1) prefetch_wbar(TILE_E0(1));
+      image(0);
+    }
+    for (int i = 0; i <= n_my; ++i) {                              // one extra step issues the last GEMM4
+      long long t_prev_ = TC_TIMING ? clock64() : 0;
       if (issuer) {
-        tc_wait(&bars[5], (uint32_t)(i & 1), &s_abort);
-        tc::fence_after_sync();
-        // GEMM3: hbar[128 x KC] = wbar[128 x Fp] @ W2c^T, in chunks of 64 hidden units with one commit each
-        const uint32_t ah = tc::smem_u32(Wbhi), al = tc::smem_u32(Wblo), bh = tc::smem_u32(S.W2hi), bl = tc::smem_u32(S.W2lo);
-        for (int ch = 0; ch < nch; ++ch) {
-          const int u0 = 4 * ch, u1 = (u0 + 4 < nks) ? u0 + 4 : nks;
-          const int c0 = 16 * u0, wdt = 16 * (u1 - u0);
-          const uint32_t idesc3 = tc::make_idesc_bf16(TM, wdt, 0, 1);     // B = W2c image read MN-major
-          uint32_t acc = 0;
-          for (int ks = 0; ks < T.Fp / 16; ++ks) {
-            const uint32_t ao = (uint32_t)ks * 256u;
-            const uint32_t bo = (uint32_t)ks * 2u * T.sboW2 + (uint32_t)(c0 / 8) * 128u;
-            const uint64_t a_hi = tc::make_desc(ah + ao, 128u, T.sboWb), a_lo = tc::make_desc(al + ao, 128u, T.sboWb);
-            const uint64_t b_hi = tc::make_desc(bh + bo, T.sboW2, 128u), b_lo = tc::make_desc(bl + bo, T.sboW2, 128u);
-            tc::mma_bf16(tD3 + (uint32_t)c0, a_hi, b_hi, idesc3, acc);
-            tc::mma_bf16(tD3 + (uint32_t)c0, a_lo, b_hi, idesc3, 1);
-            tc::mma_bf16(tD3 + (uint32_t)c0, a_hi, b_lo, idesc3, 1);
-            acc = 1;
+        if (i > 0) {
+          tc_wait(&bars[4], (uint32_t)((i - 1) & 1), &s_abort);    // u(i-1) is in tensor memory, a1 has been read
+          tc::fence_after_sync();
+          issue_gemm4();
+        }
+        if (i < n_my) {
+          tc::fence_after_sync();
+          tc_issue_gemm_ss(tD1, A0hi, A0lo, T.sboA0, S.W1hi, S.W1lo, T.sboW1, T.K0 / 16, idesc1);
+          tc::commit(&bars[0]);
+          tc_wait(&bars[5], (uint32_t)(i & 1), &s_abort);          // operand image of tile i
+          tc::fence_after_sync();
+          // GEMM3: hbar[128 x KC] = wbar[128 x Fp] @ W2c^T, in chunks of 64 hidden units with one commit each.  It follows
+          // GEMM4(i-1) in the pipe, which reads u(i-1) from the columns it overwrites.
+          const uint32_t ah = tc::smem_u32(Wbhi), al = tc::smem_u32(Wblo), bh = tc::smem_u32(S.W2hi), bl = tc::smem_u32(S.W2lo);
+          for (int ch = 0; ch < nch; ++ch) {
+            const int u0 = 4 * ch, u1 = (u0 + 4 < nks) ? u0 + 4 : nks;
+            const int c0 = 16 * u0, wdt = 16 * (u1 - u0);
+            const uint32_t idesc3 = tc::make_idesc_bf16(TM, wdt, 0, 1);     // B = W2c image read MN-major
+            uint32_t acc = 0;
+            for (int ks = 0; ks < T.Fp / 16; ++ks) {
+              const uint32_t ao = (uint32_t)ks * 256u;
+              const uint32_t bo = (uint32_t)ks * 2u * T.sboW2 + (uint32_t)(c0 / 8) * 128u;
+              const uint64_t a_hi = tc::make_desc(ah + ao, 128u, T.sboWb), a_lo = tc::make_desc(al + ao, 128u, T.sboWb);
+              const uint64_t b_hi = tc::make_desc(bh + bo, T.sboW2, 128u), b_lo = tc::make_desc(bl + bo, T.sboW2, 128u);
+              tc::mma_bf16(tD3 + (uint32_t)c0, a_hi, b_hi, idesc3, acc);
+              tc::mma_bf16(tD3 + (uint32_t)c0, a_lo, b_hi, idesc3, 1);
+              tc::mma_bf16(tD3 + (uint32_t)c0, a_hi, b_lo, idesc3, 1);
+              acc = 1;
+            }
+            tc::commit(&bars[1 + ch]);
           }
-          tc::commit(&bars[1 + ch]);
         }
       }
-      if (i + 1 < n_my) prefetch_wbar(TILE_E0(i + 1));
-      TC_PHASE(2, 3);
-      if (TC_TIMING && blockIdx.x == 0 && tid == TC_TIMER) atomicAdd(&g_tc_phase[2][15], 1ull);
+      TC_PHASE(2, 0);
+      if (i + 1 < n_my) {
+        if (i + 2 < n_my) prefetch_wbar(TILE_E0(i + 2));
+        tc_wait(&bars[0], (uint32_t)(i & 1), &s_abort);            // GEMM1(i) has consumed the radial-basis image
+        image(i + 1);
+      }
+      TC_PHASE(2, 1);
+      if (TC_TIMING && i < n_my && blockIdx.x == 0 && tid == TC_TIMER) atomicAdd(&g_tc_phase[2][15], 1ull);
     }
   }
   tc::fence_before_sync();
@@ -895,7 +962,7 @@ bool so3k_edge_tc_supported(const So3kDims& D) {
   if (T.Fp > 160 || T.KC > 192) return false;                   // <= 3 sixteen-column units per thread and phase
   if (D.H > 8 || D.nl > 7) return false;                        // pair records hold 7 contractions
   if (2 * T.KC + T.Fp > 512) return false;                      // filter kernel: two hidden-layer buffers + the output tile
-  if (2 * D.F + T.KC + T.K0 > 512) return false;                // backward part 2: a | t' | hbar | rbf' image
+  if (T.Fp + T.KC + T.K0 > 512) return false;                   // backward part 2: a1 | hbar / u | rbfbar
   return T.f_total + 1024 <= 227u * 1024u && T.b_total + 1024 <= 227u * 1024u;
 }
 
@@ -986,11 +1053,12 @@ extern "C" void so3k_tc_phase_dump(void) {
   cudaMemcpyFromSymbol(h, g_tc_phase, sizeof(h));
   // phase names per kernel index (TC_PHASE(kernel, phase)): 0 = k_filter_tc, 2 = k_edge_bwd2_tc
   static const char* const names[3][13] = {
-      {"helper: wait GEMM1(i+1)", "rbf image (i+2) + barrier", "issue GEMM1 + wait GEMM2(i)", "epilogue2 (i)", "barrier + bulk store",
-       "wait a1_ready + issue GEMM2", "-", "-", "epilogue group: wait GEMM1", "epilogue group: epilogue 1", "-", "-", "-"},
+      {"-", "helper: wait a0_ready + issue GEMM1", "wait GEMM2(i)", "epilogue2 (i)", "barrier + bulk store",
+       "wait a1_ready + issue GEMM2", "-", "-", "epilogue group: wait GEMM1", "epilogue group: rbf image + epilogue 1", "-", "-", "-"},
       {"-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-", "-"},
-      {"helper: wait GEMM3(i-1)", "rbf images + barrier", "share of the wbar image", "issue GEMM3 + prefetch", "-", "-", "-", "-",
-       "epilogue group: wait GEMM1s + chunk 0", "epilogue group: epilogue", "-", "-", "-"}};
+      {"helper: issue GEMM4, GEMM1, GEMM3", "rbf image (i+1)", "-", "-", "-", "-", "-", "-",
+       "epilogue group: wait GEMM1 + chunk 0", "epilogue group: phase 1 (u)", "epilogue group: wbar image (i+1)",
+       "epilogue group: phase 2 + totals", "-"}};
   for (int k = 0; k < 3; ++k) {
     if (!h[k][15]) continue;
     double tot = 0;

@@ -59,6 +59,7 @@ struct Graph {
 // rows of the pair-indexed arrays (a symmetric list has exactly Pt / 2 pairs; malformed lists are clamped to this)
 SO3K_HD static inline int so3k_pair_capacity(int Pt) { return Pt / 2 + 1; }
 
+
 // ---- kernels' host launchers -------------------------------------------------------------------
 // graph.cu
 size_t so3k_graph_ws_ints(int N, int Pt);

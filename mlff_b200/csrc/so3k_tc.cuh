@@ -163,12 +163,12 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- split fp32 -> bf16 hi / lo ----------------------------------------------------------------------------
-// Integer-pipe split (no F2FP conversions, which share the XU pipe with the MUFU ops of the silu epilogues):
-//   hi = round-half-up(x) to bf16 ; lo = round-half-up(x - hi) to bf16.  x - hi is exact in fp32 and |lo| <= 2^-9 |x|
-//   with either sign (a truncating hi would make lo*lo a biased, coherently accumulating error).
+// hi = round(x) to bf16 ; lo = round(x - hi) to bf16.  x - hi is exact in fp32 and |lo| <= 2^-9 |x| with either sign
+// (a truncating hi would make lo*lo a biased, coherently accumulating error).
 __device__ __forceinline__ void split2(float x, float y, uint32_t* hi, uint32_t* lo) {
-#ifdef SO3K_SPLIT_F2FP
-  // variant with the packed conversion instruction (round-to-nearest-even): 6 instructions per pair instead of 10
+#ifndef SO3K_SPLIT_INT
+  // packed conversion instruction (round-to-nearest-even): 6 instructions per pair; measured 2-4 % faster kernels than the
+  // integer-pipe variant below (10 instructions per pair), which was written when F2FP was feared to share the MUFU pipe
   uint32_t h, l;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(y), "f"(x));
   const float rx = x - __uint_as_float(h << 16);

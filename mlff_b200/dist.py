@@ -9,9 +9,12 @@ the only communication is one owner->ghost row exchange per layer in each direct
 (forward: x_{t+1}, chi_{t+1}; backward: xbar1, chibar1), plus a scalar all-reduce of the energy.  Nothing is ever
 accumulated from ghosts back into owners.
 
-The plan is built from the full neighbour list, which every rank constructs redundantly from the replicated
-positions (1.3 ms for 10^5 atoms on a B200); no communication is needed to build it because both sides of every
-exchange derive the same sorted id lists from the same list.  All tensor plumbing here is torch (device memory,
+A rank prepares its problem from the atoms of its brick + r_cut only (brick_select): subset neighbour list on the
+device cell list, plan (owned rows, mirror edges, ghost order, send lists) from it -- O(local), and without
+communication, because both sides of every exchange derive the same (needing rank, atom id)-sorted lists from
+bit-identical distance tests.  DDSession keeps a plan across steps while no atom has moved more than skin / 2 (the
+list is then built with r_cut + skin; the extra pairs contribute exactly zero through the cosine cutoff), which takes
+the preparation -- a quarter of an 8-GPU step -- out of most steps.  All tensor plumbing here is torch (device memory,
 NCCL); the computation is libso3k's so3k_dd_* entry points.
 """
 from __future__ import annotations
@@ -208,6 +211,30 @@ class DDRank:
                           self.jj.data_ptr(), self.cell.data_ptr(), self.S.data_ptr(), self.ws.data_ptr(),
                           self.ws.numel(), self.status.data_ptr(), self._stream())
 
+    def begin_local(self, plan: DDPlan, R_local: torch.Tensor, z_local: torch.Tensor, cell: np.ndarray):
+        """`begin` for callers that keep the plan across steps: R_local / z_local are already in the plan's local order;
+        the int32 index arrays are converted once per plan."""
+        if getattr(self, '_plan_arrays_of', None) is not plan:
+            self.ii = plan.idx_i.to(torch.int32).contiguous()
+            self.jj = plan.idx_j.to(torch.int32).contiguous()
+            self.S = plan.shifts.to(torch.int32).contiguous()
+            self.cell = torch.as_tensor(np.asarray(cell, dtype=np.float32).reshape(1, 3, 3), device=self.device).contiguous()
+            self._plan_arrays_of = plan
+        self.plan = plan
+        dev = self.device
+        self.R = R_local.to(torch.float32).contiguous()
+        self.z = z_local.to(torch.int32).contiguous()
+        self.N, self.P = plan.n_local, int(self.ii.shape[0])
+        nbytes = self.lib.workspace_bytes(self.h, self.N, self.P)
+        if self.ws is None or self.ws.numel() < nbytes:
+            self.ws = torch.zeros(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=dev)
+        if getattr(self, 'e_atom', None) is None or self.e_atom.shape[0] != self.N:
+            self.e_atom = torch.zeros(self.N, dtype=torch.float32, device=dev)
+            self.forces = torch.zeros(self.N, 3, dtype=torch.float32, device=dev)
+        self.lib.dd_begin(self.h, self.N, self.P, self.R.data_ptr(), self.z.data_ptr(), self.ii.data_ptr(),
+                          self.jj.data_ptr(), self.cell.data_ptr(), self.S.data_ptr(), self.ws.data_ptr(),
+                          self.ws.numel(), self.status.data_ptr(), self._stream())
+
     def stage(self, stage: int, t: int = 0):
         out = {1: self.e_atom, 4: self.forces}.get(stage)
         self.lib.dd_stage(self.h, stage, t, self.N, self.P, self.z.data_ptr(), None if out is None else out.data_ptr(),
@@ -289,3 +316,76 @@ def run_energy_forces(ranks: Sequence[DDRank], exchange: Exchange) -> None:
             r.stage(3, t)
     for r in ranks:
         r.stage(4)
+
+
+class DDSession:
+    """One rank's domain-decomposed energy + force evaluation of a periodic system, with the plan (brick subset,
+    neighbour list, owned / ghost order, mirror edges, send lists) RE-USED across calls while no atom has moved more than
+    skin / 2 since it was built -- the skin rule of the reference's MD lists (glp quadratic_neighbor_list,
+    mlff/mdx/atoms.py:365-383, 488-510).  skin = 0 rebuilds on every call."""
+
+    def __init__(self, engine, n_layers: int, cell: np.ndarray, world: int, rank: int, cutoff: float, skin: float = 0.0,
+                 capacity: int = 0):
+        from .capi import NL_ASE
+        self.engine, self.cell, self.world, self.rank = engine, np.asarray(cell, dtype=np.float64), world, rank
+        self.cutoff, self.skin, self.mode = float(cutoff), float(skin), NL_ASE
+        self.dd = DDRank(engine.lib, engine.h, n_layers, engine.device)
+        self.capacity = int(capacity)
+        self.plan: Optional[DDPlan] = None
+        self.ref: Optional[torch.Tensor] = None
+        self.n_builds = 0
+        self.marks: Optional[list] = None            # (label, event) of the last call when timing is requested
+
+    def _mark(self, label: str):
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((label, ev))
+
+    def _rebuild(self, pos: torch.Tensor):
+        eng = self.engine
+        rc = self.cutoff + self.skin
+        sub, owner = brick_select(pos, self.cell, self.world, self.rank, rc)      # ascending: subset order == global order
+        pos_s = pos[sub]
+        if self.capacity <= 0:
+            self.capacity = 64 * int(sub.shape[0]) + 4096
+        while True:
+            ii, jj, S, count = eng.neighbor_list(pos_s, rc, self.capacity, cell=self.cell, pbc=(True, True, True),
+                                                 mode=self.mode)
+            nv = eng.count_and_status(count)                    # plan sizes are host values (one read per rebuild)
+            if nv <= self.capacity:
+                break
+            self.capacity = int(1.25 * nv) + 4096
+        self._mark('subset + neighbour list')
+        self.plan = build_plan(ii[:nv].long(), jj[:nv].long(), S[:nv], owner, self.rank, self.world, check=False)
+        self.atoms = sub[self.plan.local_atoms]                 # global ids of the local rows (owned, then ghosts)
+        self.ref = pos.clone()
+        self.n_builds += 1
+        self._mark('plan')
+
+    def energy_forces(self, pos: torch.Tensor, z: torch.Tensor, timing: bool = False):
+        """pos (N,3) float64 and z (N) int32: the WHOLE system, replicated on every rank (device tensors).  Returns the
+        sum of this rank's owned per-atom energies (float64 device scalar, to be all-reduced by the caller), the forces
+        of the owned atoms (n_own, 3) and their global ids."""
+        self.marks = [] if timing else None
+        self._mark('start')
+        rebuild = self.plan is None or self.skin <= 0.0
+        if not rebuild:
+            d2 = ((pos - self.ref) ** 2).sum(-1).max()
+            rebuild = float(d2.item()) > (0.5 * self.skin) ** 2
+        if rebuild:
+            self._rebuild(pos)
+        plan = self.plan
+        # local arrays straight from the global ones (the plan's local order), graph + embedding, then the layer sweep
+        self.dd.begin_local(plan, pos[self.atoms], z[self.atoms], self.cell)
+        self._mark('begin (local arrays, CSR, embedding)')
+        run_energy_forces([self.dd], exchange_distributed if self.world > 1 else exchange_inprocess)
+        self._mark('layers + exchanges')
+        e = self.dd.e_atom[:plan.n_own].double().sum()
+        return e, self.dd.forces[:plan.n_own], self.atoms[:plan.n_own]
+
+    def phase_times(self):
+        if not self.marks:
+            return {}
+        torch.cuda.synchronize()
+        return {lab: a.elapsed_time(b) for (_, a), (lab, b) in zip(self.marks[:-1], self.marks[1:])}

@@ -446,9 +446,9 @@ def test_kernels_match_reference_model_code(tag):
 def test_tensor_mode_orchestration_and_streaming_kernels(ethanol, solid, F, degrees, H, keep):
     """Tensor mode on the emulator: the two tcgen05 pair kernels are stood in for by plain fp32 loops (so3k_edge_tc.cu,
     SO3K_EMU branch); everything around them is the product source -- pair records, canonical pairs, the streaming
-    kernels that consume pair-indexed filters and emit pair-indexed filter cotangents (k_alpha_aggregate, k_alpha_bwd,
-    k_qk_bwd_stream with their 128-bit lane maps: one chunk per lane, chunk + tail scalar (F = 132, 140, 144), two chunks
-    (F = 256)), kept / recomputed filters."""
+    kernels that consume pair-indexed filters and emit pair-indexed filter cotangents (k_alpha_aggregate -- the warp-scan
+    variant for F = 132 / 36 / 32, the general one for F = 140 / 144 / 256 --, k_alpha_bwd, k_qk_bwd_stream), kept /
+    recomputed filters."""
     from mlff_b200.capi import FLAG_TENSOR
     cfg = o.OracleConfig(F=F, n_layers=2, degrees=degrees, n_heads=H)
     p = o.init_params(cfg, 0, embed_scale=4.0)

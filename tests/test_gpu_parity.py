@@ -381,9 +381,10 @@ def test_tcgen05_tile_gemm_layouts(N, K, variant):
     kmajor = variant in (0, 5)
     Bm = rng.normal(size=(N, K) if kmajor else (K, N)).astype(np.float32)
     ref = A.astype(np.float64) @ (Bm.astype(np.float64).T if kmajor else Bm.astype(np.float64))
-    def bf(a):      # the kernels' hi part: round-half-up to bf16 (so3k_tc.cuh split2), done on the integer pipe
+    def bf(a):      # the kernels' hi part: round-to-nearest-even to bf16 (so3k_tc.cuh split2: cvt.rn.bf16x2.f32)
         b = np.ascontiguousarray(a, np.float32).view(np.uint32)
-        return ((b + np.uint32(0x8000)) & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
+        b = b + np.uint32(0x7FFF) + ((b >> np.uint32(16)) & np.uint32(1))
+        return (b & np.uint32(0xFFFF0000)).view(np.float32).astype(np.float64)
     ref1 = bf(A) @ (bf(Bm).T if kmajor else bf(Bm))
     Ad, Bd = dev(A, torch.float32), dev(Bm, torch.float32)
     for passes, target, tol in ((1, ref1, 2e-5), (3, ref, 3e-5)):
@@ -533,3 +534,33 @@ def test_zbl_repulsion_matches_oracle(ethanol, flags):
                                     dev(jj, torch.int32), dev(mask, torch.uint8), energy_scale=1.3)
     ea_o, dE_o = o.potential_displacements(cfg, p, edges, z[0], ii, jj, mask, energy_scale=1.3)
     check_md_seam_outputs(flags, ii, jj, ea_g, dE_g, F_g, ea_o.numpy(), dE_o.numpy(), len(z[0]))
+
+
+def test_dd_session_reuses_its_plan_within_the_skin():
+    """DDSession (mlff_b200/dist.py): the per-rank plan is kept while no atom has moved more than skin / 2 (the skin rule
+    of the reference's MD lists, mlff/mdx/atoms.py:365-383); the list is built with r_cut + skin and the extra pairs
+    contribute exactly zero, so energies and forces equal a fresh evaluation at the moved positions."""
+    from mlff_b200 import dist as dd
+    from mlff_b200.capi import FLAG_TENSOR, FLAG_KEEP_FILTERS
+    from common import jittered_lattice, water_like_numbers
+    n, box = 800, 20.0
+    pos = jittered_lattice(n, box, 7)
+    z = water_like_numbers(n, 7)
+    cell = np.eye(3) * box
+    cfg = o.OracleConfig(F=132, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p, flags=FLAG_TENSOR | FLAG_KEEP_FILTERS)
+    sess = dd.DDSession(eng, cfg.n_layers, cell, 1, 0, cfg.r_cut, skin=0.3)
+    rng = np.random.default_rng(0)
+    z_d = dev(z, torch.int32)
+    for step, amp in enumerate((0.0, 0.05, 0.05, 0.4)):           # the last move exceeds skin / 2: the plan is rebuilt
+        pos = pos + rng.uniform(-amp, amp, pos.shape) / np.sqrt(3.0)
+        e, f, ids = sess.energy_forces(dev(pos, torch.float64), z_d)
+        ii, jj, S = o.periodic_neighbor_list_kdtree(pos, box, cfg.r_cut)
+        Eo, Fo, _ = o.energy_forces(cfg, p, pos, z, ii, jj, cell=cell, cell_offset=S)
+        assert abs(float(e.cpu()) - float(Eo)) <= E_RTOL * abs(float(Eo)), step
+        F = np.zeros((n, 3), np.float32)
+        F[ids.cpu().numpy()] = f.cpu().numpy()
+        assert np.abs(F - Fo.numpy()).max() < F_ATOL, step
+        assert sess.n_builds == (1 if step < 3 else 2), (step, sess.n_builds)
+    assert eng.check_status() == 0
