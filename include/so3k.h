@@ -190,6 +190,45 @@ int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
                                  float* e_atom, float* dE_dedges, float* forces,
                                  void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
 
+/* ---- training seam: cotangents of (E, F) -> parameter gradients -----------------------------------------------
+ * What `jax.value_and_grad(loss_fn)(params, batch)` needs from the model (mlff/training/run.py:34-50, loss.py:42-73 with
+ * obs_fn = vmap(get_obs_and_force_fn(net)), observable_function.py:127-149): for cotangents E_bar (B) of the energies
+ * and F_bar (B,n,3) of the forces of so3k_energy_forces (same padded inputs),
+ *     grad[theta] = sum_b E_bar[b] dE_b/dtheta + sum_(b,i,c) F_bar[b,i,c] dF[b,i,c]/dtheta ,
+ * a float32 blob in the order of so3k_load_params (overwritten; energy/per_atom_scale, _shift get 0: they are constants
+ * of the Energy module, observable.py:49-58).  Because F = -dE/dR this is second order; it is evaluated as the
+ * forward-mode derivative along -F_bar of the reverse-mode parameter gradient, in one dual-number sweep (so3k_train.cu).
+ * F_bar == NULL selects the first-order sweep (grad = sum_b E_bar[b] dE_b/dtheta; E_bar == NULL means all ones).
+ * E_out (B) or NULL receives the energies of the sweep.  Supported for the default model (no LAYER_NORM /
+ * RESIDUAL_MLP / ZBL flags; SO3K_ERR_CONFIG otherwise); arithmetic is fp32 on the CUDA cores in either filter mode. */
+size_t so3k_train_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total);
+int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P,
+                           const float* R, const int32_t* z, const int32_t* idx_i, const int32_t* idx_j,
+                           const float* cell, const int32_t* cell_offset,
+                           const float* E_bar, const float* F_bar, float* grad, float* E_out,
+                           void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
+
+/* Loss of the reference's training CLI (scaled_safe_masked_mse_loss, loss.py:13-29, scale 1; get_loss_fn :42-73):
+ *   loss = w_energy mse(E, E_true) + w_force mse(F, F_true), each a mean over the entries whose target is not NaN
+ *   (forces: and whose atom is real, z != 0 = node_mask).
+ * so3k_loss_sums ADDS (sum sq E residual, n_E, sum sq F residual, n_F) of this rank's batch onto sums[4] (device f64;
+ * data-parallel training all-reduces these four numbers so that every rank divides by the global denominators);
+ * so3k_loss_cotangents turns them into E_bar (B), F_bar (B,n,3) and loss[3] = (loss, mse_E, mse_F) (device f32). */
+int so3k_loss_sums(int32_t B, int32_t n, const float* E, const float* F, const float* E_true, const float* F_true,
+                   const int32_t* z, double* sums, void* stream);
+int so3k_loss_cotangents(int32_t B, int32_t n, const float* E, const float* F, const float* E_true, const float* F_true,
+                         const int32_t* z, const double* sums, float w_energy, float w_force,
+                         float* E_bar, float* F_bar, float* loss, void* stream);
+
+/* One update of the reference's optimiser chain (mlff/training/optimizer.py:64-97): optax.clip_by_global_norm
+ * (clip_norm <= 0: off) -> scale_by_adam(b1, b2, eps, eps_root) -> add_decayed_weights(weight_decay, mask) ->
+ * scale(-lr), in place on the float32 blobs params / m / v (n entries).  step is the 1-based update count (bias
+ * correction); frozen / decay_mask are per-entry u8 masks or NULL; *grad_sumsq (device f64) receives |grad|^2
+ * (train_metrics['gradients_norm'] squared, run.py:49).  Call so3k_load_params afterwards. */
+int so3k_adam_step(size_t n, float* params, const float* grad, float* m, float* v, const uint8_t* frozen,
+                   const uint8_t* decay_mask, int64_t step, float lr, float b1, float b2, float eps, float eps_root,
+                   float weight_decay, float clip_norm, double* grad_sumsq, void* stream);
+
 /* ---- stepwise evaluation (spatial domain decomposition) ----------------------------------------------------
  * No counterpart in the reference (it has no multi-device path).  A rank's local problem is
  * its OWNED atoms followed by GHOST atoms, with all edges received by owned atoms plus their reverses ("mirror

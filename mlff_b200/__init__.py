@@ -18,6 +18,9 @@ def __getattr__(name):
     if name == 'mlffCalculator':
         from . import calculator
         return calculator.mlffCalculator
+    if name in ('Trainer', 'TrainState', 'Optimizer'):
+        from . import training
+        return getattr(training, name)
     if name == 'So3kEngine':
         from . import engine
         return engine.So3kEngine

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG_DIR, 'csrc')
 # SO3K_LIB_PATH: another build of the SAME library (profiling / A-B builds under profiles/_scratch); never a different backend
 LIB_PATH = os.environ.get('SO3K_LIB_PATH') or os.path.join(PKG_DIR, 'lib', 'libso3k.so')
 SOURCES = ['so3k_api.cu', 'so3k_graph.cu', 'so3k_feat.cu', 'so3k_node.cu', 'so3k_agg.cu', 'so3k_edge.cu',
-           'so3k_nl.cu', 'so3k_tc_test.cu', 'so3k_edge_tc.cu']
+           'so3k_nl.cu', 'so3k_tc_test.cu', 'so3k_edge_tc.cu', 'so3k_train.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

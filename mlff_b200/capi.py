@@ -34,7 +34,8 @@ EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 's
            'so3k_load_params', 'so3k_workspace_bytes', 'so3k_energy_forces', 'so3k_potential_displacements',
            'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count',
            'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect', 'so3k_tc_selftest',
-           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_buffer', 'so3k_stress']
+           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_buffer', 'so3k_stress', 'so3k_train_workspace_bytes',
+           'so3k_energy_forces_vjp', 'so3k_loss_sums', 'so3k_loss_cotangents', 'so3k_adam_step']
 
 
 class So3kConfigC(C.Structure):
@@ -102,6 +103,16 @@ class So3kLib:
         d.so3k_profile_enable.restype = C.c_int
         d.so3k_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32, i32]
         d.so3k_profile_collect.restype = C.c_int
+        d.so3k_train_workspace_bytes.argtypes = [vp, i64, i64]
+        d.so3k_train_workspace_bytes.restype = sz
+        d.so3k_energy_forces_vjp.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]
+        d.so3k_energy_forces_vjp.restype = C.c_int
+        d.so3k_loss_sums.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        d.so3k_loss_sums.restype = C.c_int
+        d.so3k_loss_cotangents.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp]
+        d.so3k_loss_cotangents.restype = C.c_int
+        d.so3k_adam_step.argtypes = [sz, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp]
+        d.so3k_adam_step.restype = C.c_int
 
     # ---- handle -----------------------------------------------------------------------------
     def create(self, F: int, n_rbf: int, n_layers: int, n_heads: int, degrees: Sequence[int], r_cut: float,
@@ -169,6 +180,28 @@ class So3kLib:
                       ws_bytes, status, stream=0):
         _check(self.dll.so3k_neighbor_list(mode, N, positions, z, cell, pbc, float(cutoff), capacity, idx_i, idx_j,
                                            shifts, count, ws, ws_bytes, status, stream), 'so3k_neighbor_list')
+
+    # ---- training seam ------------------------------------------------------------------------
+    def train_workspace_bytes(self, h: int, n_atoms: int, n_edge_slots: int) -> int:
+        return int(self.dll.so3k_train_workspace_bytes(h, n_atoms, n_edge_slots))
+
+    def energy_forces_vjp(self, h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, grad, E_out, ws,
+                          ws_bytes, status, stream=0):
+        _check(self.dll.so3k_energy_forces_vjp(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, grad,
+                                               E_out, ws, ws_bytes, status, stream), 'so3k_energy_forces_vjp')
+
+    def loss_sums(self, B, n, E, F, E_true, F_true, z, sums, stream=0):
+        _check(self.dll.so3k_loss_sums(B, n, E, F, E_true, F_true, z, sums, stream), 'so3k_loss_sums')
+
+    def loss_cotangents(self, B, n, E, F, E_true, F_true, z, sums, w_energy, w_force, E_bar, F_bar, loss, stream=0):
+        _check(self.dll.so3k_loss_cotangents(B, n, E, F, E_true, F_true, z, sums, float(w_energy), float(w_force),
+                                             E_bar, F_bar, loss, stream), 'so3k_loss_cotangents')
+
+    def adam_step(self, n, params, grad, m, v, frozen, decay_mask, step, lr, b1, b2, eps, eps_root, weight_decay,
+                  clip_norm, grad_sumsq, stream=0):
+        _check(self.dll.so3k_adam_step(n, params, grad, m, v, frozen, decay_mask, int(step), float(lr), float(b1),
+                                       float(b2), float(eps), float(eps_root), float(weight_decay), float(clip_norm),
+                                       grad_sumsq, stream), 'so3k_adam_step')
 
     # ---- stepwise / domain decomposition --------------------------------------------------------
     def dd_begin(self, h, N, P, R, z, idx_i, idx_j, cell, cell_offset, ws, ws_bytes, status, stream=0):

@@ -72,11 +72,12 @@ SO3K_HD static inline float so3k_rbf_d(float ed, int k, float rbf, const So3kDim
 #define SO3K_C4G 0.6258357354491761f   /* 3/16 sqrt(35/pi) */
 #define SO3K_C0 0.28209479177387814f   /* 1/2 sqrt(1/pi) */
 
-// Y_l(x,y,z) -> out[0..2l]
-SO3K_HD static inline void so3k_sph(int l, float x, float y, float z, float* out) {
+// Y_l(x,y,z) -> out[0..2l] ; T = float, or a forward-mode dual number (so3k_train.cu) with float * T, T * T, T +- T defined
+template <class T>
+SO3K_HD static inline void so3k_sph_g(int l, T x, T y, T z, T* out) {
   switch (l) {
     case 0:
-      out[0] = SO3K_C0;
+      out[0] = x * 0.0f + SO3K_C0;
       break;
     case 1:
       out[0] = SO3K_C1 * y; out[1] = SO3K_C1 * z; out[2] = SO3K_C1 * x;
@@ -98,7 +99,7 @@ SO3K_HD static inline void so3k_sph(int l, float x, float y, float z, float* out
       out[6] = SO3K_C3A * x * (x * x - 3.0f * y * y);
       break;
     case 4: {
-      float x2 = x * x, y2 = y * y, z2 = z * z;
+      T x2 = x * x, y2 = y * y, z2 = z * z;
       out[0] = SO3K_C4A * x * y * (x2 - y2);
       out[1] = SO3K_C4B * y * (3.0f * x2 - y2) * z;
       out[2] = SO3K_C4C * x * y * (7.0f * z2 - 1.0f);
@@ -113,6 +114,8 @@ SO3K_HD static inline void so3k_sph(int l, float x, float y, float z, float* out
       break;
   }
 }
+
+SO3K_HD static inline void so3k_sph(int l, float x, float y, float z, float* out) { so3k_sph_g<float>(l, x, y, z, out); }
 
 // Accumulate g += sum_m ybar[m] * dY_lm/d(x,y,z)  (x,y,z treated as independent variables of the
 // polynomials above, exactly what reverse-mode AD of spherical.py does).

@@ -1,0 +1,170 @@
+"""Training step on the device: the host-side mirror of the reference's training seam.
+
+Reference interfaces mirrored here (paths relative to the reference checkout):
+  * ``Optimizer`` / ``optimizer``            mlff/training/optimizer.py:12-97  (clip -> adam -> decayed weights -> -lr)
+  * ``get_loss_fn``                          mlff/training/loss.py:42-73       (weighted, masked, NaN-safe MSE of E and F)
+  * ``train_step_fn`` / ``TrainState``       mlff/training/run.py:34-50        (value_and_grad + apply_gradients,
+                                                                               train_metrics incl. 'gradients_norm')
+  * data parallelism: the reference vmaps the loss over the batch (cAPI/mlff_train_so3krates.py:381) and has no
+    multi-device path; here each rank owns B / world structures and the ranks all-reduce the four loss sums (so that
+    every rank divides by the GLOBAL denominators of scaled_safe_masked_mse_loss) and the parameter-gradient blob.
+
+Everything numeric happens in libso3k (so3k_energy_forces, so3k_loss_*, so3k_energy_forces_vjp, so3k_adam_step);
+PyTorch provides device memory, the stream and ``torch.distributed`` (NCCL on GPUs, gloo in the CPU test-suite, where
+the same code drives the CPU-emulated build of the kernels through an engine stand-in).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class Optimizer:
+    """mlff/training/optimizer.py:12-62 (same field names and defaults).  ``get(learning_rate)`` returns the settings
+    the device update needs; the scheduled decay (`transition_steps`, `decay_rate`) raises like the reference does."""
+    b1: float = 0.9
+    b2: float = 0.999
+    eps: float = 1e-8
+    eps_root: float = 0.0
+    transition_steps: Optional[int] = None
+    decay_rate: Optional[float] = None
+    weight_decay: Optional[float] = None
+    clip_by_global_norm: Optional[float] = None
+
+    def get(self, learning_rate: float) -> 'Optimizer':
+        if self.transition_steps is not None and self.decay_rate is not None:
+            # optimizer.py:79-81
+            raise DeprecationWarning('Scheduled LR decay has been moved to the train_state class. No LR decay is used.')
+        self.learning_rate = float(learning_rate)
+        return self
+
+    def __dict_repr__(self):
+        return {'optimizer': {'learning_rate': getattr(self, 'learning_rate', None),
+                              'transition_steps': self.transition_steps, 'decay_rate': self.decay_rate,
+                              'weight_decay': self.weight_decay, 'clip_by_global_norm': self.clip_by_global_norm}}
+
+
+class TrainState:
+    """step counter + device parameter blob + Adam moments (flax TrainState stand-in).  The blob IS the engine's
+    parameter blob: apply_gradients updates it in place and re-loads it into the handle."""
+
+    def __init__(self, engine, tx: Optimizer):
+        if engine._blob is None:
+            raise RuntimeError('load parameters into the engine before creating a TrainState')
+        self.engine, self.tx, self.step = engine, tx, 0
+        self.params = engine._blob
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        lib, h = engine.lib, engine.h
+        n = self.params.numel()
+        decay = np.ones(n, np.uint8)
+        frozen = np.zeros(n, np.uint8)
+        for name in engine_param_names(engine):
+            off, cnt = lib.param_lookup(h, name)
+            leaf = name.rsplit('/', 1)[-1]
+            if leaf == 'bias' or name.startswith('energy/per_atom_'):
+                decay[off:off + cnt] = 0          # flattened_traversal(path[-1] != 'bias'), optimizer.py:40
+            if name.startswith('energy/per_atom_'):
+                frozen[off:off + cnt] = 1         # constants of the Energy module, not flax parameters
+        self.decay_mask = torch.from_numpy(decay).to(engine.device)
+        self.frozen = torch.from_numpy(frozen).to(engine.device)
+        self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=engine.device)
+
+    def apply_gradients(self, grads: torch.Tensor) -> 'TrainState':
+        e, tx = self.engine, self.tx
+        self.step += 1
+        wd = 0.0 if tx.weight_decay is None else tx.weight_decay
+        clip = 0.0 if tx.clip_by_global_norm is None else tx.clip_by_global_norm
+        e.lib.adam_step(self.params.numel(), _p(self.params), _p(grads), _p(self.m), _p(self.v), _p(self.frozen),
+                        _p(self.decay_mask) if tx.weight_decay is not None else None, self.step, tx.learning_rate,
+                        tx.b1, tx.b2, tx.eps, tx.eps_root, wd, clip, _p(self.grad_sumsq), e._stream())
+        e.lib.load_params(e.h, _p(self.params), self.params.numel(), e._stream())
+        return self
+
+
+def engine_param_names(engine):
+    from .params import param_shapes
+    return [name for name, _ in param_shapes(engine.cfg)]
+
+
+class Trainer:
+    """value_and_grad of the reference's loss + one optimiser update, for the rank's shard of the batch.
+
+    ``weights`` = {'energy': w_E, 'force': w_F} (the CLI's effective_loss_weights).  ``group``: a torch.distributed
+    process group (or True for the default group) for data-parallel training; None = single process."""
+
+    def __init__(self, engine, weights: Dict[str, float], tx: Optional[Optimizer] = None, group=None):
+        self.engine = engine
+        self.w_E = float(weights.get('energy', 0.0))
+        self.w_F = float(weights.get('force', 0.0))
+        self.state = TrainState(engine, tx) if tx is not None else None
+        self.group = group
+        dev = engine.device
+        self._sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._loss = torch.zeros(3, dtype=torch.float32, device=dev)
+        self._grad = torch.zeros(engine.lib.param_count(engine.h), dtype=torch.float32, device=dev)
+        self._ws: Optional[torch.Tensor] = None
+
+    def _dist(self):
+        if self.group is None:
+            return None
+        import torch.distributed as dist
+        return dist
+
+    def _workspace(self, n_atoms: int, n_slots: int) -> torch.Tensor:
+        nb = self.engine.lib.train_workspace_bytes(self.engine.h, n_atoms, n_slots)
+        if self._ws is None or self._ws.numel() < nb:
+            self._ws = torch.empty(int(nb) + 1024, dtype=torch.uint8, device=self.engine.device)
+        return self._ws
+
+    def loss_and_grad(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None):
+        """-> (loss[3] device tensor = (loss, mse_E, mse_F), grad blob, E (B,1), F (B,n,3)); jax.value_and_grad(loss_fn)
+        of run.py:46 for this rank's structures, all-reduced over the group."""
+        e = self.engine
+        dev = e.device
+        R = R.to(dev, torch.float32).contiguous()
+        z = z.to(dev, torch.int32).contiguous()
+        idx_i = idx_i.to(dev, torch.int32).contiguous()
+        idx_j = idx_j.to(dev, torch.int32).contiguous()
+        E_true = E_true.to(dev, torch.float32).reshape(-1).contiguous()
+        F_true = F_true.to(dev, torch.float32).contiguous()
+        if cell is not None:
+            cell = cell.to(dev, torch.float32).contiguous()
+            cell_offset = cell_offset.to(dev, torch.int32).contiguous()
+        B, n = z.shape
+        P = idx_i.shape[1]
+        lib, h, st = e.lib, e.h, e._stream()
+        E, F, _ = e.energy_forces(R, z, idx_i, idx_j, cell, cell_offset)
+        E1 = E.reshape(-1)
+        self._sums.zero_()
+        lib.loss_sums(B, n, _p(E1), _p(F), _p(E_true), _p(F_true), _p(z), _p(self._sums), st)
+        dist = self._dist()
+        grp = None if self.group is True else self.group
+        if dist is not None:
+            dist.all_reduce(self._sums, group=grp)
+        E_bar = torch.empty(B, dtype=torch.float32, device=dev)
+        F_bar = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+        lib.loss_cotangents(B, n, _p(E1), _p(F), _p(E_true), _p(F_true), _p(z), _p(self._sums), self.w_E, self.w_F,
+                            _p(E_bar), _p(F_bar), _p(self._loss), st)
+        ws = self._workspace(B * n, B * P)
+        lib.energy_forces_vjp(h, B, n, P, _p(R), _p(z), _p(idx_i), _p(idx_j), _p(cell), _p(cell_offset), _p(E_bar),
+                              _p(F_bar), _p(self._grad), None, _p(ws), ws.numel(), _p(e._status), st)
+        if dist is not None:
+            dist.all_reduce(self._grad, group=grp)
+        return self._loss, self._grad, E, F
+
+    def train_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None):
+        """train_step_fn (run.py:34-50): returns the device tensor (loss, mse_E, mse_F, gradients_norm^2 ... ) lazily:
+        a dict of device scalars; nothing is read back to the host here."""
+        loss, grad, _, _ = self.loss_and_grad(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset)
+        self.state.apply_gradients(grad)
+        loss = loss.clone()              # the metrics outlive the next step's buffers
+        return {'loss': loss[0], 'energy': loss[1], 'force': loss[2], 'gradients_norm': self.state.grad_sumsq.sqrt()[0]}

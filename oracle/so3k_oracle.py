@@ -524,6 +524,46 @@ def energy_forces_batch(cfg, params, R, z, idx_i, idx_j, dtype=torch.float64, ce
     return torch.stack(Es)[:, None], torch.stack(Fs)
 
 
+def scaled_safe_masked_mse_loss(y, y_true, scale, msk):
+    """mlff/training/loss.py:13-29: sum of scale * (y_true - y)^2 over the entries that are unmasked and not NaN in the
+    target, divided by their number (0 when there are none)."""
+    full = (~torch.isnan(y_true)) & msk
+    v = torch.where(full, scale * (torch.where(full, y_true, torch.zeros_like(y_true)) - y) ** 2, torch.zeros_like(y))
+    den = full.sum().to(v.dtype)
+    return v.sum() / den if float(den) > 0 else v.sum() * 0.0
+
+
+def loss_and_param_grads(cfg, params, R, z, idx_i, idx_j, E_true, F_true, w_energy: float, w_force: float,
+                         dtype=torch.float64, trainable=None):
+    """One training step's value_and_grad (mlff/training/run.py:34-50, loss.py:42-73): loss = w_E mse(E) + w_F mse(F)
+    over a padded batch (node_mask = z != 0; energy mask all true), with F = -dE/dR inside the loss -- the parameter
+    gradient therefore differentiates THROUGH the force (second order).  Returns loss, {name: dloss/dparam}, E, F.
+    Energy scale/shift tables and ZBL scalars are constants of the Energy module, not parameters (observable.py:49-58)."""
+    names = [k for k in params if not k.startswith('energy/per_atom_')] if trainable is None else list(trainable)
+    pt = {k: torch.as_tensor(np.asarray(v), dtype=dtype).clone() for k, v in params.items()}
+    for k in names:
+        pt[k].requires_grad_(True)
+    Es, Fs = [], []
+    for b in range(len(R)):
+        R_t = torch.as_tensor(np.asarray(R[b]), dtype=dtype).clone().requires_grad_(True)
+        e = forward(cfg, pt, z[b], idx_i[b], idx_j[b], dtype, R=R_t)
+        E = e.sum()
+        (g,) = torch.autograd.grad(E, R_t, create_graph=True)
+        Es.append(E)
+        Fs.append(-g)
+    E = torch.stack(Es)[:, None]
+    F = torch.stack(Fs)
+    node_mask = torch.as_tensor(np.asarray(z) != 0)
+    one = torch.ones((), dtype=dtype)
+    loss = (w_energy * scaled_safe_masked_mse_loss(E, torch.as_tensor(np.asarray(E_true), dtype=dtype).reshape(E.shape), one,
+                                                   torch.ones_like(E, dtype=torch.bool))
+            + w_force * scaled_safe_masked_mse_loss(F, torch.as_tensor(np.asarray(F_true), dtype=dtype), one,
+                                                    node_mask[..., None].expand(F.shape)))
+    grads = torch.autograd.grad(loss, [pt[k] for k in names], allow_unused=True)
+    out = {k: (torch.zeros_like(pt[k]) if g is None else g).detach().numpy() for k, g in zip(names, grads)}
+    return float(loss.detach()), out, E.detach(), F.detach()
+
+
 def potential_displacements(cfg, params, edges, z, centers, others, mask, dtype=torch.float64,
                             energy_scale: float = 1.0):
     """MLFFPotential.potential_fn (mlff_potential.py:95-109): per-atom energies from a Graph in the
