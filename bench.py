@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- SO3krates energy+force throughput (atom-steps/s) on B200, BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c5|c1] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c5|c1|c2] [--impl ours|reference]
 
 Workloads (synthetic seeded positions, random-init weights):
   c4  100 000-atom periodic box (100 A, water-like composition), default model F=132 L=3 r_cut=5   [default]
   c3  3 000-atom periodic water box (31.072 A)
   c5  1 000 atoms, F=256, degrees [1,2,3,4]
   c1  32 x 9-atom ethanol-sized molecules (latency-bound; fits in L2)
+  c2  TRAINING step (BASELINE.json configs[1]): 128 x 21-atom aspirin-sized molecules, loss = 0.01 mse(E) + 0.99 mse(F),
+      value_and_grad (second order: the loss contains F = -dE/dR) + one Adam update; N > 1: the batch is split over the
+      ranks (128 / N structures each), the four loss sums and the 1.3 MB gradient blob are all-reduced over NCCL
 A step = one pass of the hot path: device neighbour list (cell list) -> CSR -> L layers -> read-out -> analytic
 forces.  `value` times steps with the positions already resident in HBM (CUDA events, max over ranks);
 `e2e` times the public calculator call with HOST numpy buffers (pinned H2D of positions, D2H of energy+forces).
@@ -43,7 +46,30 @@ WORKLOADS = {
     'c3': dict(n_atoms=3_000, box=31.072, F=132, degrees=(1, 2, 3), L=3, seed=2, desc='3k-atom periodic water box, E+F'),
     'c5': dict(n_atoms=1_000, box=21.544, F=256, degrees=(1, 2, 3, 4), L=3, seed=4, desc='1k atoms, F=256, L_max=4, E+F'),
     'c1': dict(n_atoms=288, box=None, F=132, degrees=(1, 2, 3), L=3, seed=0, desc='32 x 9-atom molecules, E+F'),
+    'c2': dict(n_atoms=128 * 21, box=None, F=132, degrees=(1, 2, 3), L=3, seed=1, train=True, batch=128, n_per=21,
+               desc='training step: 128 x 21-atom aspirin-sized molecules, value_and_grad of 0.01 mse(E) + 0.99 mse(F) + Adam'),
 }
+
+
+def build_training_batch(w):
+    """aspirin composition (C9 H8 O4), one rejection-sampled template in a 7 A ball (min distance 0.9 A)
+    + N(0, 0.05 A) jitter per structure, dense neighbour list at r_cut = 5 A padded to the batch maximum with -1,
+    targets E ~ N(0,1), F ~ N(0,1).  Seeded numpy only."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import so3k_oracle as o
+    rng = np.random.default_rng(w['seed'])
+    B, n = w['batch'], w['n_per']
+    tmpl = []
+    while len(tmpl) < n:
+        x = rng.uniform(-3.5, 3.5, 3)
+        if np.linalg.norm(x) <= 3.5 and all(np.linalg.norm(x - y) >= 0.9 for y in tmpl):
+            tmpl.append(x)
+    R = np.asarray(tmpl)[None] + rng.normal(0, 0.05, (B, n, 3))
+    z = np.tile(np.array([6] * 9 + [8] * 4 + [1] * 8, np.int64)[None], (B, 1))
+    nl = o.get_indices(R, z, 5.0)
+    E_true = rng.normal(size=(B, 1))
+    F_true = rng.normal(size=(B, n, 3))
+    return R, z, nl['idx_i'], nl['idx_j'], E_true, F_true
 
 
 def peaks():
@@ -200,6 +226,207 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------------------------------------------
+def oracle_training_sample(w, n_structs, threads):
+    """float32 oracle (torch-CPU, double backward) of the training step's value_and_grad on the first structures."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import so3k_oracle as o
+    torch.set_num_threads(threads)
+    cfg = o.OracleConfig(F=w['F'], degrees=w['degrees'], n_layers=w['L'])
+    p = o.init_params(cfg, 0)
+    R, z, ii, jj, Et, Ft = (a[:n_structs] for a in build_training_batch(w))
+
+    def step():
+        return o.loss_and_param_grads(cfg, p, R, z, ii, jj, Et, Ft, 0.01, 0.99, dtype=torch.float32)[0]
+    return step, n_structs * w['n_per'], int((ii >= 0).sum())
+
+
+def run_reference_training(args, w):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    threads = os.cpu_count() or 1
+    step, n_atoms, n_edges = oracle_training_sample(w, 16, threads)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_atoms / dt
+    line = {'impl': 'reference', 'metric': 'SO3krates training-step atom-steps/s', 'value': val, 'unit': 'atom-steps/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'c2', 'description': w['desc'], 'n_atoms': int(n_atoms), 'n_edges': int(n_edges),
+                       'n_atoms_full_workload': int(w['n_atoms']), 'F': w['F'], 'n_layers': w['L'],
+                       'degrees': list(w['degrees']), 'r_cut': 5.0, 'parallelism': 'host threads (torch-CPU), rank 0 only'},
+            'cpu_baseline': {'value': val, 'unit': 'atom-steps/s', 'cores': threads, 'kind': 'port',
+                             'sample': f'16 of the 128 structures ({n_atoms} atoms, {n_edges} edges): value_and_grad of the loss '
+                                       f'by torch double backward of the float32 oracle restatement (no optimiser update; '
+                                       f'the JAX reference is not installable here)'},
+            'e2e': {'value': val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def run_training(args, w):
+    """c2: one training step = E+F pass (tensor mode) + loss sums / cotangents + dual-number sweep (parameter gradient)
+    + [all-reduce] + Adam + parameter re-load.  `value` with the batch resident in HBM; `e2e` with HOST batch arrays
+    (pinned H2D of R, z, idx_i, idx_j, E_true, F_true every step) and a D2H read of the loss metrics."""
+    import torch
+    import torch.distributed as dist
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.engine import So3kEngine
+    from mlff_b200 import params as P
+    from mlff_b200.training import Trainer, Optimizer
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = f'cuda:{local}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    cfg = So3kratesConfig(F=w['F'], n_layer=w['L'], degrees=w['degrees'])
+    prm = P.init_params(cfg, 0)
+    rng = np.random.default_rng(7)
+    for k in prm:
+        if k.endswith('/bias'):
+            prm[k] = rng.normal(0, 0.01, prm[k].shape).astype(np.float32)
+    flags = 0 if args.fp32_simt else 3
+    eng = So3kEngine(cfg, dev, flags).load_params(prm)
+    tr = Trainer(eng, {'energy': 0.01, 'force': 0.99}, Optimizer().get(learning_rate=1e-4), group=True if world > 1 else None)
+    R, z, ii, jj, Et, Ft = build_training_batch(w)
+    B, n = z.shape
+    assert B % world == 0, 'the batch must divide over the ranks'
+    sl = slice(rank * (B // world), (rank + 1) * (B // world))
+    host = [np.ascontiguousarray(R[sl], np.float32), np.ascontiguousarray(z[sl], np.int32),
+            np.ascontiguousarray(ii[sl], np.int32), np.ascontiguousarray(jj[sl], np.int32),
+            np.ascontiguousarray(Et[sl], np.float32), np.ascontiguousarray(Ft[sl], np.float32)]
+    pinned = [torch.from_numpy(a).pin_memory() for a in host]
+    devb = [t.to(dev) for t in pinned]
+
+    def step_resident():
+        return tr.train_step(*devb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_ready()
+    for _ in range(args.warmup):
+        m = step_resident()
+    barrier()
+    l0 = eng.lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        m = step_resident()
+    e1.record()
+    barrier()
+    launches = eng.lib.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    N_all = B * n
+    value = N_all / (ms_step * 1e-3)
+    # phases of one step on this rank (CUDA events on the launching stream, outside the timed region)
+    phases = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = [ev() for _ in range(4)]
+    reps = 5
+    acc = [0.0, 0.0, 0.0]
+    for _ in range(reps):
+        marks[0].record()
+        Eo, Fo, _ = eng.energy_forces(devb[0], devb[1], devb[2], devb[3])
+        marks[1].record()
+        loss, grad, _, _ = tr.loss_and_grad(*devb)
+        marks[2].record()
+        tr.state.apply_gradients(grad)
+        marks[3].record()
+        torch.cuda.synchronize()
+        acc[0] += marks[0].elapsed_time(marks[1])
+        acc[1] += marks[1].elapsed_time(marks[2])
+        acc[2] += marks[2].elapsed_time(marks[3])
+    phases = {'energy_forces_ms': acc[0] / reps, 'loss_and_grad_ms (E+F pass + loss + dual sweep + all-reduce)': acc[1] / reps,
+              'adam_and_reload_ms': acc[2] / reps}
+    # ---- e2e: host batch in, metrics out ---------------------------------------------------------------------
+    def e2e_call():
+        for a, pt in zip(host, pinned):
+            pt.copy_(torch.from_numpy(a))
+        batch = [pt.to(dev, non_blocking=True) for pt in pinned]
+        met = tr.train_step(*batch)
+        return {k: float(v) for k, v in met.items()}          # D2H of the loss metrics
+    for _ in range(2):
+        res = e2e_call()
+    barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        res = e2e_call()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / k_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_val = N_all / float(t_e2e.item())
+    h2d = sum(a.nbytes for a in host)
+    if rank == 0:
+        pk, pk_kind = peaks()
+        Fd, K, nl_ = w['F'], 32, len(w['degrees'])
+        Fs_ = Fd // 4
+        n_edges = int((ii >= 0).sum())
+        slots = (B // world) * ii.shape[1]
+        # dense work of the dual sweep on this rank: both planes, per filter block and layer -- forward (K F + F F + Fs F),
+        # input gradients (F F + Fs F), weight gradients (F F + K F + Fs F); x 2 FLOP, x 2 planes, x 2 blocks, x L layers
+        flops = 2.0 * 2 * slots * 2 * w['L'] * ((K * Fd + Fd * Fd + Fs_ * Fd) + (Fd * Fd + Fs_ * Fd) + (Fd * Fd + K * Fd + Fs_ * Fd))
+        ms_sweep = max(phases['loss_and_grad_ms (E+F pass + loss + dual sweep + all-reduce)'] - phases['energy_forces_ms'], 1e-6)
+        tf = flops / (ms_sweep * 1e-3) / 1e12
+        peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
+        roof = {'kernel': 'k_tr_gemm / k_tr_gemm_tn (fp32 GEMMs of the dual-number sweep, so3k_energy_forces_vjp)', 'bound': 'tensor',
+                'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
+                'peak_kind': f'{pk_kind} sustained bf16 (kernels timed inside a long step)',
+                'ms_per_step': ms_sweep, 'algorithmic_flops_per_step': flops,
+                'note': 'fp32 FMA on the CUDA cores, reported against the bf16 tensor peak; the time is the whole sweep '
+                        '(GEMMs + elementwise + gather kernels), so this is a lower bound of the GEMM kernels\' own rate'}
+        threads = os.cpu_count() or 1
+        cpu = None
+        if not args.no_cpu_baseline:
+            step, n_s, n_e = oracle_training_sample(w, 8, threads)
+            step()
+            reps_c, t0 = 0, time.perf_counter()
+            while reps_c < 2 or (time.perf_counter() - t0 < 10.0 and reps_c < 50):
+                step()
+                reps_c += 1
+            dt = (time.perf_counter() - t0) / reps_c
+            cpu = {'value': n_s / dt, 'unit': 'atom-steps/s', 'cores': threads, 'kind': 'port',
+                   'sample': f'8 of the 128 structures ({n_s} atoms, {n_e} edges), {reps_c} value_and_grad evaluations (torch '
+                             f'double backward of the float32 oracle restatement; JAX reference not installable)'}
+        line = {'metric': 'SO3krates training-step atom-steps/s', 'value': value, 'unit': 'atom-steps/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
+                'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'c2', 'description': w['desc'], 'n_atoms': N_all, 'n_edges': n_edges,
+                           'global_batch': B, 'F': w['F'], 'n_layers': w['L'], 'degrees': list(w['degrees']), 'r_cut': 5.0,
+                           'loss_weights': {'energy': 0.01, 'force': 0.99}, 'optimizer': 'adam (optax chain of the reference CLI)',
+                           'parallelism': 'single' if world == 1 else
+                                          f'data parallel x{world}: {B // world} structures per rank, all-reduce of 4 loss sums + '
+                                          f'{tr._grad.numel() * 4} B gradient blob (NCCL)',
+                           'first_pass': 'tcgen05 split-operand E+F' if flags else 'fp32 CUDA-core E+F',
+                           'l2': 'working set of a rank fits in L2 at N > 1; 0.8 GB of kept activations at N = 1'},
+                'e2e': {'value': e2e_val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 16},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+                'phases_ms': phases, 'loss_check': res}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -265,7 +492,7 @@ def run_ours(args, w):
         # the plan (brick subset, neighbour list with r_cut + skin, owned / ghost order, mirror edges, send lists) is
         # kept while no atom has moved more than skin / 2 -- checked on the device every step; --dd-skin 0 rebuilds it
         # every step
-        sess = dd.DDSession(eng, cfg.n_layer, cell, world, rank, calc.cutoff, skin=args.dd_skin,
+        sess = dd.DDSession(eng, cfg.n_layer, cell, world, rank, calc.cutoff, skin=args.dd_skin, cuda_graph=args.dd_graph,
                             capacity=int(cap * 1.6 / world) + 4096)
         dd_phase = {}
 
@@ -514,7 +741,7 @@ def run_ours(args, w):
                            'F': w['F'], 'n_layers': w['L'], 'degrees': list(w['degrees']), 'r_cut': 5.0,
                            'parallelism': 'single' if world == 1 else (
                                f'domain decomposition: {grid[0]}x{grid[1]}x{grid[2]} bricks, mirror edges, per-layer halo exchange (NCCL all_to_all), '
-                               f'plan re-used within a {args.dd_skin} A skin ({sess.n_builds} builds)'
+                               f'plan re-used within a {args.dd_skin} A skin ({sess.n_builds} builds)' + (', sweep replayed as one CUDA graph' if args.dd_graph else '')
                                if use_dd else f'replicas x{world} (no collective)'),
                            'filter_gemm': 'tcgen05 split-operand' if args.tensor else 'fp32 CUDA-core',
                            'filters': 'kept for the backward' if (args.tensor and not args.no_keep_filters) else 'recomputed',
@@ -527,8 +754,12 @@ def run_ours(args, w):
                 'featurise': (dict(feat_info, peak=pk['hbm_gbs'], frac=feat_info['GB/s'] / pk['hbm_gbs']) if feat_info else None),
                 'md': md_info, 'energy_check': float(res['energy']),
                 'rank0_local': {'atoms': int(getattr(step_resident, 'n_local', N)), 'edges': int(p_rank)}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        if use_dd:
+            sess.close()                  # a captured sweep holds NCCL kernels: release it before the process group goes
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -545,6 +776,8 @@ def main():
                     '0.5 A skin list (mlff_b200.md, one GPU) and report them under "md"')
     ap.add_argument('--dd-skin', type=float, default=0.2, help='domain decomposition: skin (Angstrom) of the per-rank plan; the plan '
                     'is re-used while no atom has moved more than skin / 2 (0: rebuild every step)')
+    ap.add_argument('--dd-graph', action='store_true', help='domain decomposition: replay the sweep of a kept plan as one CUDA graph '
+                    '(kernels + halo pack / NCCL exchange / unpack)')
     ap.add_argument('--dd-timing', action='store_true', help='print the per-phase device time of one domain-decomposed step '
                     '(rank 0, stderr)')
     ap.add_argument('--no-keep-filters', action='store_true', help='recompute the filters in the backward instead of keeping '
@@ -558,7 +791,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     w = WORKLOADS[args.workload]
-    if args.impl == 'reference':
+    if w.get('train'):
+        (run_reference_training if args.impl == 'reference' else run_training)(args, w)
+    elif args.impl == 'reference':
         run_reference(args, w)
     else:
         run_ours(args, w)

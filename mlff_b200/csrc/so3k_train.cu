@@ -75,6 +75,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ Dual warp_sum(Dual v) { return mkd(warp_sum(v.p), warp_sum(v.t)); }
 
 constexpr int TB = 256;
+constexpr int TN_PARTS = 296;     // row chunks of a weight-gradient reduction (2 per SM)
 
 // ---- geometry: r, d, u, phi, Y_lm, rbf per sorted edge (embed.py:88-127, radial.py:163-166, cutoff radial.py:50-51) ----
 template <class T>
@@ -210,22 +211,6 @@ __global__ void k_tr_headproj_bwd_x(int N, int F, int d, const float* __restrict
   for (int c = 0; c < d; ++c) acc += Tr<T>::ld(ybar, (size_t)n * F + h * d + c, ps) * Wh[c];
   Tr<T>::st(xbar, idx, ps, Tr<T>::ld(xbar, idx, ps) + acc);
 }
-// Wbar[h, r, c] += sum_n x[n, h d + r] ybar[n, h d + c]; grid (cdiv(heads d d, TB), atom chunks)
-template <class T>
-__global__ void k_tr_headproj_bwd_w(int N, int F, int d, int chunk, const float* __restrict__ x,
-                                    const float* __restrict__ ybar, float* __restrict__ Wbar) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  const int heads = F / d;
-  if (o >= heads * d * d) return;
-  const int h = o / (d * d), r = (o / d) % d, c = o % d;
-  const size_t ps = (size_t)N * F;
-  const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
-  T acc = Tr<T>::zero();
-  for (int n = n0; n < n1; ++n)
-    acc += Tr<T>::ld(x, (size_t)n * F + h * d + r, ps) * Tr<T>::ld(ybar, (size_t)n * F + h * d + c, ps);
-  atomicAdd(&Wbar[o], gout(acc));
-}
-
 // attention coefficients alpha[e, a] = phi_e / sqrt(d_head) * sum_{f in head a} q_i w_e k_j   (so3krates_layer.py:583-586,
 // 500-501, 551-554): heads 0..H-1 of the feature block, H..H+nl-1 of the geometric block.  One warp per edge.
 template <class T>
@@ -558,29 +543,48 @@ __global__ void __launch_bounds__(256) k_tr_gemm(int Mr, int Nc, int Kd, const f
                                                  const float* __restrict__ Bp, int sbk, int sbn,
                                                  const float* __restrict__ bias, int bias_rows, int beta,
                                                  float* __restrict__ C, int ldc) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Bs[GK][GN + 4];
+  SO3K_SHARED16 float As[GK][GM + 4];
+  SO3K_SHARED16 float Bs[GK][GN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // tx: 4 columns, ty: 8 rows
   const int r0 = blockIdx.y * GM, c0 = blockIdx.x * GN;
   float acc[8][4];
   for (int a = 0; a < 8; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  for (int k0 = 0; k0 < Kd; k0 += GK) {
-    for (int t = tid; t < GM * GK; t += 256) {
-      const int r = t / GK, kk = t % GK;
-      As[kk][r] = (r0 + r < Mr && k0 + kk < Kd) ? A[(size_t)(r0 + r) * lda + k0 + kk] : 0.f;
+  // the next K slab is fetched into registers while the current one is multiplied out of shared memory
+  float ra[8], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + 256 * q, r = t / GK, kk = t % GK;
+      ra[q] = (r0 + r < Mr && k0 + kk < Kd) ? A[(size_t)(r0 + r) * lda + k0 + kk] : 0.f;
     }
-    for (int t = tid; t < GK * GN; t += 256) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = tid + 256 * q;
       const int kk = sbn == 1 ? t / GN : t % GK, c = sbn == 1 ? t % GN : t / GK;
-      Bs[kk][c] = (k0 + kk < Kd && c0 + c < Nc) ? Bp[(size_t)(k0 + kk) * sbk + (size_t)(c0 + c) * sbn] : 0.f;
+      rb[q] = (k0 + kk < Kd && c0 + c < Nc) ? Bp[(size_t)(k0 + kk) * sbk + (size_t)(c0 + c) * sbn] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < Kd; k0 += GK) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = tid + 256 * q;
+      As[t % GK][t / GK] = ra[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = tid + 256 * q;
+      Bs[sbn == 1 ? t / GN : t % GK][sbn == 1 ? t % GN : t / GK] = rb[q];
     }
     __syncthreads();
+    if (k0 + GK < Kd) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      float av[8], bv[4];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) av[a] = As[kk][ty * 8 + a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][tx * 4 + b];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -602,67 +606,116 @@ __global__ void __launch_bounds__(256) k_tr_gemm(int Mr, int Nc, int Kd, const f
   }
 }
 // Weight gradient: G[k, n] += sum_r A'[r, k] B'[r, n] over the stacked rows r < planes R, where plane p of B' is plane
-// (planes - 1 - p) of B (x0^T ybar1 + x1^T ybar0; one plane: x^T ybar).  64 x 64 output tile, rows split over
-// gridDim.z chunks, atomics into the gradient blob.
-constexpr int WT = 64, WR = 16;
+// (planes - 1 - p) of B (x0^T ybar1 + x1^T ybar0; one plane: x^T ybar).  A block owns a 144 x 144 output tile (the whole
+// matrix for F = 132) and a chunk of rows: 9 x 9 outputs per thread, 18 shared-memory loads per 81 FMAs; the per-chunk
+// partial sums go to a scratch array and k_tr_reduce_parts adds them onto the gradient in a fixed order (no atomics).
+constexpr int WT = 144, WR = 8, WPT = 9;
 __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, int Nc, int chunk,
                                                     const float* __restrict__ A, int lda, const float* __restrict__ B,
-                                                    int ldb, float* __restrict__ G, int ldg) {
-  __shared__ float As[WR][WT + 4];
-  __shared__ float Bs[WR][WT + 4];
+                                                    int ldb, float* __restrict__ part) {
+  __shared__ float As[WR][WT];
+  __shared__ float Bs[WR][WT];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int k0 = blockIdx.y * WT, c0 = blockIdx.x * WT;
-  const long long Rt = (long long)R * planes;
-  const long long rbeg = (long long)blockIdx.z * chunk, rend = rbeg + chunk < Rt ? rbeg + chunk : Rt;
-  float acc[4][4];
-  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  for (long long rr = rbeg; rr < rend; rr += WR) {
-    for (int t = tid; t < WR * WT; t += 256) {
-      const int r = t / WT, c = t % WT;
-      const long long gr = rr + r;
+  const int Rt = R * planes;                                   // stacked rows (fits an int: planes * edge slots)
+  const int rbeg = blockIdx.z * chunk, rend = rbeg + chunk < Rt ? rbeg + chunk : Rt;
+  float acc[WPT][WPT];
+#pragma unroll
+  for (int a = 0; a < WPT; ++a)
+#pragma unroll
+    for (int b = 0; b < WPT; ++b) acc[a][b] = 0.f;
+  // 8 rows x 144 columns of both operands per step: 4.5 elements per thread, fetched a step ahead into registers
+  constexpr int NLD = (WR * WT + 255) / 256;
+  float ra[NLD], rb[NLD];
+  auto fetch = [&](int rr) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int t = tid + 256 * q, r = t / WT, c = t - r * WT;
+      const int gr = rr + r;
       float av = 0.f, bv = 0.f;
-      if (gr < rend) {
+      if (t < WR * WT && gr < rend) {
         if (k0 + c < Kd) av = A[(size_t)gr * lda + k0 + c];
         if (c0 + c < Nc) {
-          const long long pb = gr / R, rb = gr % R;
-          bv = B[(size_t)((planes - 1 - pb) * R + rb) * ldb + c0 + c];
+          const int pb = gr >= R ? 1 : 0, rb_ = gr - pb * R;     // planes <= 2
+          bv = B[(size_t)((planes - 1 - pb) * R + rb_) * ldb + c0 + c];
         }
       }
-      As[r][c] = av;
-      Bs[r][c] = bv;
+      ra[q] = av;
+      rb[q] = bv;
+    }
+  };
+  fetch(rbeg);
+  for (int rr = rbeg; rr < rend; rr += WR) {
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+      const int t = tid + 256 * q, r = t / WT, c = t - r * WT;
+      if (t < WR * WT) {
+        As[r][c] = ra[q];
+        Bs[r][c] = rb[q];
+      }
     }
     __syncthreads();
+    if (rr + WR < rend) fetch(rr + WR);
 #pragma unroll
     for (int r = 0; r < WR; ++r) {
-      float av[4], bv[4];
+      float av[WPT], bv[WPT];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[r][ty * 4 + a];
+      for (int a = 0; a < WPT; ++a) av[a] = As[r][ty + 16 * a];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[r][tx * 4 + b];
+      for (int b = 0; b < WPT; ++b) bv[b] = Bs[r][tx + 16 * b];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < WPT; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        for (int b = 0; b < WPT; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
-  for (int a = 0; a < 4; ++a) {
-    const int k = k0 + ty * 4 + a;
+  float* dst = part + (size_t)blockIdx.z * Kd * Nc;
+#pragma unroll
+  for (int a = 0; a < WPT; ++a) {
+    const int k = k0 + ty + 16 * a;
     if (k >= Kd) continue;
-    for (int b = 0; b < 4; ++b) {
-      const int c = c0 + tx * 4 + b;
-      if (c < Nc) atomicAdd(&G[(size_t)k * ldg + c], acc[a][b]);
+#pragma unroll
+    for (int b = 0; b < WPT; ++b) {
+      const int c = c0 + tx + 16 * b;
+      if (c < Nc) dst[(size_t)k * Nc + c] = acc[a][b];
     }
   }
 }
-// out[c] += sum_r X[r, c] over rows [0, R) of ONE plane (the caller passes the plane that belongs in the gradient)
-__global__ void k_tr_colsum(int R, int C, int chunk, const float* __restrict__ X, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// G[i] += sum_z part[z][i]  (i < count = Kd Nc of the call that filled `part`)
+__global__ void k_tr_reduce_parts(int count, int nz, const float* __restrict__ part, float* __restrict__ G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float acc = 0.f;
+  for (int z = 0; z < nz; ++z) acc += part[(size_t)z * count + i];
+  G[i] += acc;
+}
+// per-head blocks of a dense (F, F) product: Wbar[h, r, c] += Gd[h d + r, h d + c]
+__global__ void k_tr_extract_heads(int F, int d, const float* __restrict__ Gd, float* __restrict__ Wbar) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int heads = F / d;
+  if (o >= heads * d * d) return;
+  const int h = o / (d * d), r = (o / d) % d, c = o % d;
+  Wbar[o] += Gd[(size_t)(h * d + r) * F + h * d + c];
+}
+// out[c] += sum_r X[r, c] over rows [0, R) of ONE plane (the caller passes the plane that belongs in the gradient):
+// 32 columns x 8 row lanes per block, `chunk` rows per block
+__global__ void __launch_bounds__(256) k_tr_colsum(int R, int C, int chunk, const float* __restrict__ X, float* __restrict__ out) {
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   const int r0 = blockIdx.y * chunk, r1 = min(R, r0 + chunk);
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r) acc += X[(size_t)r * C + c];
-  atomicAdd(&out[c], acc);
+  if (c < C)
+    for (int r = r0 + ry; r < r1; r += 8) acc += X[(size_t)r * C + c];
+  sh[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sh[k][cx];
+    atomicAdd(&out[c], v);
+  }
 }
 
 // ---- loss (training/loss.py:13-29, 42-73) --------------------------------------------------------------------------
@@ -771,6 +824,7 @@ struct TrainWs {
   // temporaries
   float *H, *Hs, *cat, *abbar, *catbar;
   float *xbar, *chibar, *x1bar, *chi1bar, *sbar, *wbar, *projbar, *gbar, *hsbar;
+  float *part, *dense;                         // weight-gradient partial sums (TN_PARTS x C x C), dense (F, F) product
   size_t bytes;
 };
 
@@ -826,6 +880,8 @@ TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base) {
   w.projbar = (float*)take(fl * pl * 5 * N * F);
   w.gbar = (float*)take(fl * pl * Pe * nl);
   w.hsbar = (float*)take(fl * pl * Pe * Fs);
+  w.part = (float*)take(fl * (size_t)TN_PARTS * C * C);
+  w.dense = (float*)take(fl * F * F);
   w.bytes = (size_t)(p - (char*)base);
   return w;
 }
@@ -846,20 +902,27 @@ void gemm_nt(int rows, int Kd, int Nc, const float* A, const float* W, float* C,
   SO3K_LAUNCH(k_tr_gemm, dim3(so3k_cdiv(Kd, GN), so3k_cdiv(rows, GM)), dim3(256), 0, st, rows, Kd, Nc, A, Nc, W, 1, Nc,
               (const float*)nullptr, 0, 0, C, Kd);
 }
-// G (Kd, Nc) += X^T Ybar with the dual-number product rule
-void gemm_tn(int R, int planes, int Kd, int Nc, const float* X, const float* Ybar, float* G, cudaStream_t st) {
+// G (Kd, Nc) += X^T Ybar with the dual-number product rule; `part` = scratch of TN_PARTS * Kd * Nc floats
+void gemm_tn(int R, int planes, int Kd, int Nc, const float* X, int ldx, const float* Ybar, int ldy, float* G, float* part,
+             cudaStream_t st) {
   if (R <= 0) return;
   const long long Rt = (long long)R * planes;
-  int chunk = 1024;
-  int nz = (int)((Rt + chunk - 1) / chunk);
+  const int tiles = so3k_cdiv(Nc, WT) * so3k_cdiv(Kd, WT);
+  int nz = TN_PARTS / tiles;
+  if (nz < 1) nz = 1;
+  int chunk = (int)((Rt + nz - 1) / nz);
+  chunk = (chunk + WR - 1) / WR * WR;
+  if (chunk < 64) chunk = 64;
+  nz = (int)((Rt + chunk - 1) / chunk);
   SO3K_LAUNCH(k_tr_gemm_tn, dim3(so3k_cdiv(Nc, WT), so3k_cdiv(Kd, WT), nz), dim3(256), 0, st, R, planes, Kd, Nc, chunk, X,
-              Kd, Ybar, Nc, G, Nc);
+              ldx, Ybar, ldy, part);
+  SO3K_LAUNCH(k_tr_reduce_parts, dim3(so3k_cdiv((long long)Kd * Nc, 256)), dim3(256), 0, st, Kd * Nc, nz, part, G);
 }
 // out (C) += column sums of the gradient plane of X (R, C)
 void colsum(int R, int C, int planes, const float* X, float* out, cudaStream_t st) {
   if (R <= 0) return;
-  const int chunk = 512;
-  SO3K_LAUNCH(k_tr_colsum, dim3(so3k_cdiv(C, 128), so3k_cdiv(R, chunk)), dim3(128), 0, st, R, C, chunk,
+  const int chunk = 256;
+  SO3K_LAUNCH(k_tr_colsum, dim3(so3k_cdiv(C, 32), so3k_cdiv(R, chunk)), dim3(256), 0, st, R, C, chunk,
               X + (size_t)(planes - 1) * R * C, out);
 }
 
@@ -935,7 +998,7 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
   colsum(N, (int)F, pl, w.cat, grad + ml.out_W2, st);
   colsum(N, 1, pl, w.ebar, grad + ml.out_b2, st);
   float* abar = w.x1bar;
-  gemm_tn(N, pl, (int)F, (int)F, xL, abar, grad + ml.out_W1, st);
+  gemm_tn(N, pl, (int)F, (int)F, xL, (int)F, abar, (int)F, grad + ml.out_W1, w.part, st);
   colsum(N, (int)F, pl, abar, grad + ml.out_b1, st);
   gemm_nt(rowsN, (int)F, (int)F, abar, prm + ml.out_W1, w.xbar, st);
   cudaMemsetAsync(w.chibar, 0, sizeof(float) * sc, st);
@@ -953,7 +1016,7 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
     // interaction block
     SO3K_LAUNCH(k_tr_intpost_bwd<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, c1, w.xbar, w.chibar, w.abbar);
     SO3K_LAUNCH(k_tr_intpre<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, x1, c1, w.cat);
-    gemm_tn(N, pl, (int)C, (int)C, w.cat, w.abbar, grad + lp.int_W, st);
+    gemm_tn(N, pl, (int)C, (int)C, w.cat, (int)C, w.abbar, (int)C, grad + lp.int_W, w.part, st);
     colsum(N, (int)C, pl, w.abbar, grad + lp.int_b, st);
     gemm_nt(rowsN, (int)C, (int)C, w.abbar, prm + lp.int_W, w.catbar, st);
     SO3K_LAUNCH(k_tr_intpre_bwd<T>, g1((size_t)N * (F + M)), dim3(TB), 0, st, D, N, c1, ab, w.xbar, w.chibar, w.catbar,
@@ -973,17 +1036,17 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
       colsum((int)Pe, (int)F, pl, w.wbar, grad + bp.rad_b2, st);
       colsum((int)Pe, (int)F, pl, w.wbar, grad + bp.sph_b2, st);
       SO3K_LAUNCH(k_tr_silu<T>, g1(Pe * F), dim3(TB), 0, st, Pe * F, A1, w.H);
-      gemm_tn((int)Pe, pl, (int)F, (int)F, w.H, w.wbar, grad + bp.rad_W2, st);
+      gemm_tn((int)Pe, pl, (int)F, (int)F, w.H, (int)F, w.wbar, (int)F, grad + bp.rad_W2, w.part, st);
       gemm_nt(rowsE, (int)F, (int)F, w.wbar, prm + bp.rad_W2, w.H, st);              // Hbar
       SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(Pe * F), dim3(TB), 0, st, Pe * F, A1, w.H);   // A1bar
-      gemm_tn((int)Pe, pl, (int)K, (int)F, w.rbf, w.H, grad + bp.rad_W1, st);
+      gemm_tn((int)Pe, pl, (int)K, (int)F, w.rbf, (int)K, w.H, (int)F, grad + bp.rad_W1, w.part, st);
       colsum((int)Pe, (int)F, pl, w.H, grad + bp.rad_b1, st);
       // spherical branch: w += silu(g Ws1 + bs1) Ws2 + bs2
       SO3K_LAUNCH(k_tr_silu<T>, g1(Pe * Fs), dim3(TB), 0, st, Pe * Fs, As, w.Hs);
-      gemm_tn((int)Pe, pl, (int)Fs, (int)F, w.Hs, w.wbar, grad + bp.sph_W2, st);
+      gemm_tn((int)Pe, pl, (int)Fs, (int)F, w.Hs, (int)Fs, w.wbar, (int)F, grad + bp.sph_W2, w.part, st);
       gemm_nt(rowsE, (int)Fs, (int)F, w.wbar, prm + bp.sph_W2, w.hsbar, st);
       SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(Pe * Fs), dim3(TB), 0, st, Pe * Fs, As, w.hsbar);   // Asbar
-      gemm_tn((int)Pe, pl, (int)nl, (int)Fs, gl, w.hsbar, grad + bp.sph_W1, st);
+      gemm_tn((int)Pe, pl, (int)nl, (int)Fs, gl, (int)nl, w.hsbar, (int)Fs, grad + bp.sph_W1, w.part, st);
       colsum((int)Pe, (int)Fs, pl, w.hsbar, grad + bp.sph_b1, st);
       SO3K_LAUNCH(k_tr_sph1_bwd<T>, g1(Pe * nl), dim3(TB), 0, st, Pt, (int)nl, (int)Fs, b, w.hsbar, prm + bp.sph_W1, w.gbar);
     }
@@ -993,9 +1056,10 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
     float* Gp[5] = {grad + lp.fb.Wq, grad + lp.fb.Wk, grad + lp.fb.Wv, grad + lp.gb.Wq, grad + lp.gb.Wk};
     for (int k5 = 0; k5 < 5; ++k5) {
       const int d = k5 < 3 ? D.dh : D.dg;
-      const int heads = (int)F / d, chunk = 128;
-      SO3K_LAUNCH(k_tr_headproj_bwd_w<T>, dim3(so3k_cdiv(heads * d * d, TB), so3k_cdiv(N, chunk)), dim3(TB), 0, st, N, (int)F,
-                  d, chunk, xt, pbar[k5], Gp[k5]);
+      const int heads = (int)F / d;
+      cudaMemsetAsync(w.dense, 0, sizeof(float) * F * F, st);
+      gemm_tn(N, pl, (int)F, (int)F, xt, (int)F, pbar[k5], (int)F, w.dense, w.part, st);
+      SO3K_LAUNCH(k_tr_extract_heads, g1((size_t)heads * d * d), dim3(TB), 0, st, (int)F, d, w.dense, Gp[k5]);
       if (t > 0)
         SO3K_LAUNCH(k_tr_headproj_bwd_x<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, d, pbar[k5], Wp[k5], w.xbar);
     }

@@ -325,6 +325,7 @@ class DDSession:
     mlff/mdx/atoms.py:365-383, 488-510).  skin = 0 rebuilds on every call."""
 
     def __init__(self, engine, n_layers: int, cell: np.ndarray, world: int, rank: int, cutoff: float, skin: float = 0.0,
+                 cuda_graph: bool = False,
                  capacity: int = 0):
         from .capi import NL_ASE
         self.engine, self.cell, self.world, self.rank = engine, np.asarray(cell, dtype=np.float64), world, rank
@@ -335,6 +336,13 @@ class DDSession:
         self.ref: Optional[torch.Tensor] = None
         self.n_builds = 0
         self.marks: Optional[list] = None            # (label, event) of the last call when timing is requested
+        # cuda_graph: while a plan is kept, the whole sweep (local graph + embedding, layer stages, halo pack / NCCL
+        # exchange / unpack, energy sum: ~400 short launches at 8 ranks) is captured once and replayed as ONE CUDA graph
+        # -- libso3k only enqueues and never allocates, NCCL collectives are capturable, and every rank takes the same
+        # rebuild decisions (they all see the whole position array), so the ranks capture and replay in lock step
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
+        self._graph_plan = None
 
     def _mark(self, label: str):
         if self.marks is not None:
@@ -376,13 +384,55 @@ class DDSession:
         if rebuild:
             self._rebuild(pos)
         plan = self.plan
+        exchange = exchange_distributed if self.world > 1 else exchange_inprocess
+        if self.cuda_graph and self.skin > 0.0 and not timing:
+            if self._graph_plan is not plan:
+                self._capture(plan, pos, z, exchange)
+            torch.index_select(pos, 0, self.atoms, out=self._pos_l)
+            self._R_l.copy_(self._pos_l)
+            torch.index_select(z, 0, self.atoms, out=self._z_l)
+            self._graph.replay()
+            return self._e_l, self.dd.forces[:plan.n_own], self.atoms[:plan.n_own]
         # local arrays straight from the global ones (the plan's local order), graph + embedding, then the layer sweep
         self.dd.begin_local(plan, pos[self.atoms], z[self.atoms], self.cell)
         self._mark('begin (local arrays, CSR, embedding)')
-        run_energy_forces([self.dd], exchange_distributed if self.world > 1 else exchange_inprocess)
+        run_energy_forces([self.dd], exchange)
         self._mark('layers + exchanges')
         e = self.dd.e_atom[:plan.n_own].double().sum()
         return e, self.dd.forces[:plan.n_own], self.atoms[:plan.n_own]
+
+    def _capture(self, plan, pos, z, exchange):
+        """One eager sweep on a side stream (allocates the workspace, warms NCCL up for these message sizes), then the
+        capture of the same calls on static local buffers."""
+        dev = self.engine.device
+        self._graph = None                                          # release the previous plan's graph and its pool
+        self._pos_l = pos[self.atoms].contiguous()
+        self._R_l = self._pos_l.to(torch.float32)
+        self._z_l = z[self.atoms].to(torch.int32).contiguous()
+        if z.dtype != torch.int32:
+            raise TypeError('cuda_graph=True needs int32 atomic numbers (they are gathered into a static buffer)')
+
+        def sweep():
+            self.dd.begin_local(plan, self._R_l, self._z_l, self.cell)
+            run_energy_forces([self.dd], exchange)
+            return self.dd.e_atom[:plan.n_own].double().sum()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            sweep()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._e_l = sweep()
+        self._graph, self._graph_plan = g, plan
+
+    def close(self):
+        """Release the captured graph (it holds NCCL kernels: the process group must outlive it) and its buffers."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.engine.device)
+            self._graph = None
+            self._graph_plan = None
 
     def phase_times(self):
         if not self.marks:

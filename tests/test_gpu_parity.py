@@ -536,10 +536,12 @@ def test_zbl_repulsion_matches_oracle(ethanol, flags):
     check_md_seam_outputs(flags, ii, jj, ea_g, dE_g, F_g, ea_o.numpy(), dE_o.numpy(), len(z[0]))
 
 
-def test_dd_session_reuses_its_plan_within_the_skin():
+@pytest.mark.parametrize('cuda_graph', [False, True], ids=['eager', 'graph'])
+def test_dd_session_reuses_its_plan_within_the_skin(cuda_graph):
     """DDSession (mlff_b200/dist.py): the per-rank plan is kept while no atom has moved more than skin / 2 (the skin rule
     of the reference's MD lists, mlff/mdx/atoms.py:365-383); the list is built with r_cut + skin and the extra pairs
-    contribute exactly zero, so energies and forces equal a fresh evaluation at the moved positions."""
+    contribute exactly zero, so energies and forces equal a fresh evaluation at the moved positions.  cuda_graph: the
+    sweep of a kept plan is captured once and replayed (re-captured after the rebuild)."""
     from mlff_b200 import dist as dd
     from mlff_b200.capi import FLAG_TENSOR, FLAG_KEEP_FILTERS
     from common import jittered_lattice, water_like_numbers
@@ -550,7 +552,7 @@ def test_dd_session_reuses_its_plan_within_the_skin():
     cfg = o.OracleConfig(F=132, n_layers=2)
     p = o.init_params(cfg, 0, embed_scale=4.0)
     eng = make(cfg, p, flags=FLAG_TENSOR | FLAG_KEEP_FILTERS)
-    sess = dd.DDSession(eng, cfg.n_layers, cell, 1, 0, cfg.r_cut, skin=0.3)
+    sess = dd.DDSession(eng, cfg.n_layers, cell, 1, 0, cfg.r_cut, skin=0.3, cuda_graph=cuda_graph)
     rng = np.random.default_rng(0)
     z_d = dev(z, torch.int32)
     for step, amp in enumerate((0.0, 0.05, 0.05, 0.4)):           # the last move exceeds skin / 2: the plan is rebuilt
