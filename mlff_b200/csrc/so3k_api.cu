@@ -216,6 +216,9 @@ struct Workspace {
   float *x1b;              // per layer: first skip state (input of the second LayerNorm)
   float *x2a;              // per layer: second skip state before ResidualMLP 2
   float *x2b;              // per layer: layer output before the post LayerNorm
+  // rows whose node-level outputs are needed: all N, or (domain decomposition) the owned rows, which come first -- a
+  // ghost's layer output, read-out and cotangents belong to its owner and are overwritten by the halo exchange
+  int n_node;
   size_t bytes;
 };
 
@@ -239,6 +242,7 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int ws_mode) {
   const size_t Ast = (D.H + D.nl + 3) & ~3, Gst = (D.nl + 3) & ~3;
   const size_t Pe = Pt > 0 ? Pt : 1;
   w.g.N = N; w.g.Pt = Pt;
+  w.n_node = N;
   w.g.rowptr = (int*)take(sizeof(int) * (N + 1));
   w.g.col = (int*)take(sizeof(int) * Pe);
   w.g.row = (int*)take(sizeof(int) * Pe);
@@ -335,12 +339,13 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
     so3k_launch_aggregate(D, w.g, xt, ct, proj_t, alpha_t, x1a, w.chi1 + (size_t)t * N * M, st);
   }
   PROF(CAT_INTERACTION);
-  if (res1) so3k_launch_resmlp(D, (int)N, x1a, prm, lp.res[0], x1b, st);
-  if (ln) so3k_launch_layernorm((int)N, (int)F, x1b, prm + lp.ln_s[1], prm + lp.ln_b[1], w.xn, st);
-  so3k_launch_interaction(D, (int)N, ln ? w.xn : x1b, w.chi1 + (size_t)t * N * M, prm, lp, x2a, ct + N * M,
+  const int Nn = w.n_node;
+  if (res1) so3k_launch_resmlp(D, Nn, x1a, prm, lp.res[0], x1b, st);
+  if (ln) so3k_launch_layernorm(Nn, (int)F, x1b, prm + lp.ln_s[1], prm + lp.ln_b[1], w.xn, st);
+  so3k_launch_interaction(D, Nn, ln ? w.xn : x1b, w.chi1 + (size_t)t * N * M, prm, lp, x2a, ct + N * M,
                           w.bcoef + (size_t)t * N * nl, st, ln ? x1b : nullptr);
-  if (res2) so3k_launch_resmlp(D, (int)N, x2a, prm, lp.res[1], x2b, st);
-  if (post) so3k_launch_layernorm((int)N, (int)F, x2b, prm + lp.ln_s[2], prm + lp.ln_b[2], xt + N * F, st);
+  if (res2) so3k_launch_resmlp(D, Nn, x2a, prm, lp.res[1], x2b, st);
+  if (post) so3k_launch_layernorm(Nn, (int)F, x2b, prm + lp.ln_s[2], prm + lp.ln_b[2], xt + N * F, st);
 }
 
 // e_atom and d(sum e)/dx_L -> xbar_a ; chibar_a = 0 ; rbar = 0
@@ -351,7 +356,7 @@ void stage_readout(HandleImpl* h, Workspace& w, const int* z, float out_scale, f
   const size_t N = w.g.N, Pe = w.g.Pt > 0 ? w.g.Pt : 1;
   {
     PROF(CAT_READOUT);
-    so3k_launch_readout(D, (int)N, w.x + (size_t)D.L * N * D.F, z, h->params, h->params_T, h->layout, out_scale, e_atom,
+    so3k_launch_readout(D, w.n_node, w.x + (size_t)D.L * N * D.F, z, h->params, h->params_T, h->layout, out_scale, e_atom,
                         w.xbar_a, st);
   }
   cudaMemsetAsync(w.chibar_a, 0, sizeof(float) * N * D.M, st);
@@ -371,21 +376,22 @@ void stage_layer_bwd_a(HandleImpl* h, Workspace& w, int t, cudaStream_t st) {
   const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST);
   const bool res1 = opts & SO3K_OPT_RES1, res2 = opts & SO3K_OPT_RES2;
   PROF(CAT_INTERACTION_BWD);
+  const int Nn = w.n_node;
   // the optional branches above the interaction block, last to first (all in place on xbar_a)
   if (post) {
     const float* x2b = w.x2b + (size_t)t * N * F;
-    so3k_launch_layernorm_bwd((int)N, (int)F, x2b, h->params + lp.ln_s[2], w.xbar_a, nullptr, w.xbar_a, st);
+    so3k_launch_layernorm_bwd(Nn, (int)F, x2b, h->params + lp.ln_s[2], w.xbar_a, nullptr, w.xbar_a, st);
   }
   if (res2)
-    so3k_launch_resmlp_bwd(D, (int)N, w.x2a + (size_t)t * N * F, h->params, h->params_T, lp.res[1], w.xbar_a, w.xbar_a, st);
-  so3k_launch_interaction_bwd(D, (int)N, w.chi1 + (size_t)t * N * D.M, w.bcoef + (size_t)t * N * D.nl, h->params_T,
+    so3k_launch_resmlp_bwd(D, Nn, w.x2a + (size_t)t * N * F, h->params, h->params_T, lp.res[1], w.xbar_a, w.xbar_a, st);
+  so3k_launch_interaction_bwd(D, Nn, w.chi1 + (size_t)t * N * D.M, w.bcoef + (size_t)t * N * D.nl, h->params_T,
                               lp, w.xbar_a, w.chibar_a, w.xbar_b, w.chibar_b, st, !ln);
   // ... and those between the first skip connection and the interaction block: xbar_b becomes the cotangent of x + x_local
   if (ln)       // xbar_b holds the cotangent of the normalised input: back through LayerNorm 2, plus the skip connection
-    so3k_launch_layernorm_bwd((int)N, (int)F, w.x1b + (size_t)t * N * F, h->params + lp.ln_s[1], w.xbar_b, w.xbar_a,
+    so3k_launch_layernorm_bwd(Nn, (int)F, w.x1b + (size_t)t * N * F, h->params + lp.ln_s[1], w.xbar_b, w.xbar_a,
                               w.xbar_b, st);
   if (res1)
-    so3k_launch_resmlp_bwd(D, (int)N, w.x1a + (size_t)t * N * F, h->params, h->params_T, lp.res[0], w.xbar_b, w.xbar_b, st);
+    so3k_launch_resmlp_bwd(D, Nn, w.x1a + (size_t)t * N * F, h->params, h->params_T, lp.res[0], w.xbar_b, w.xbar_b, st);
 }
 
 // everything below the interaction block of layer t: edge cotangents, rbar += ..., and (t > 0) the cotangent of
@@ -434,10 +440,10 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
       // the projections read LayerNorm 1 (x_t): their cotangent goes back through it, the skip connection adds xbar_b
       PROF(CAT_NODE_PROJ_BWD);
       cudaMemsetAsync(w.xn, 0, sizeof(float) * N * F, st);
-      so3k_launch_node_proj_bwd(D, (int)N, w.gproj, h->params_T, lp, w.xn, st);
-      so3k_launch_layernorm_bwd((int)N, (int)F, w.x + (size_t)t * N * F, h->params + lp.ln_s[0], w.xn, w.xbar_b, w.xbar_a, st);
+      so3k_launch_node_proj_bwd(D, w.n_node, w.gproj, h->params_T, lp, w.xn, st);
+      so3k_launch_layernorm_bwd(w.n_node, (int)F, w.x + (size_t)t * N * F, h->params + lp.ln_s[0], w.xn, w.xbar_b, w.xbar_a, st);
     } else {
-      { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, (int)N, w.gproj, h->params_T, lp, w.xbar_b, st); }   // xbar_b += proj^T
+      { PROF(CAT_NODE_PROJ_BWD); so3k_launch_node_proj_bwd(D, w.n_node, w.gproj, h->params_T, lp, w.xbar_b, st); }   // xbar_b += proj^T
       cudaMemcpyAsync(w.xbar_a, w.xbar_b, sizeof(float) * N * F, cudaMemcpyDeviceToDevice, st);      // xbar_a <- d/d x_t
     }
   }
@@ -639,12 +645,13 @@ int so3k_dd_begin(so3k_handle* hh, int32_t N, int32_t P, const float* R, const i
 
 // stage: 0 = layer forward t ; 1 = read-out (e_atom (N) out, needs z) ; 2 = layer backward A (interaction block) ;
 //        3 = layer backward B ; 4 = forces (N,3) out
-int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t P, const int32_t* z, float* out,
-                  void* workspace, int32_t* dev_status, void* stream) {
-  if (!hh || !workspace || N <= 0) return SO3K_ERR_ARG;
+int so3k_dd_stage_owned(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t n_owned, int32_t P, const int32_t* z,
+                        float* out, void* workspace, int32_t* dev_status, void* stream) {
+  if (!hh || !workspace || N <= 0 || n_owned < 0 || n_owned > N) return SO3K_ERR_ARG;
   HandleImpl* h = static_cast<HandleImpl*>(hh);
   if (t < 0 || t >= h->dims.L) return SO3K_ERR_ARG;
   Workspace w = carve_ws(h->dims, N, P, workspace, wst_layers_of(h));
+  w.n_node = n_owned;
   cudaStream_t st = (cudaStream_t)stream;
   switch (stage) {
     case 0: stage_layer_fwd(h, w, t, dev_status, st); break;
@@ -655,6 +662,10 @@ int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t 
     default: return SO3K_ERR_ARG;
   }
   return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+int so3k_dd_stage(so3k_handle* hh, int32_t stage, int32_t t, int32_t N, int32_t P, const int32_t* z, float* out,
+                  void* workspace, int32_t* dev_status, void* stream) {
+  return so3k_dd_stage_owned(hh, stage, t, N, N, P, z, out, workspace, dev_status, stream);
 }
 
 // byte offset inside the workspace of a node buffer: which = 0: x_t (N,F) ; 1: chi_t (N,M) ; 2: xbar1 (N,F) ; 3: chibar1 (N,M)

@@ -13,19 +13,55 @@
 
 namespace {
 
-__device__ __forceinline__ bool edge_valid(int il, int jl, int n, const unsigned char* mask, int e) {
+// r = R[j] - R[i] (+ cell_offset @ cell) or the supplied displacement, in the arithmetic every user of the edge shares
+// (k_count / k_fill decide with it, k_rowsort_geom stores it): the reverse edge evaluates the exact negative, so both
+// directions of a pair always get the same distance.
+__device__ __forceinline__ void edge_vec(int e, int i, int j, int b, const float* __restrict__ R,
+                                         const float* __restrict__ cell, const int* __restrict__ cell_offset,
+                                         const float* __restrict__ disp, float* rx, float* ry, float* rz) {
+  if (disp) {
+    *rx = disp[3 * (size_t)e + 0]; *ry = disp[3 * (size_t)e + 1]; *rz = disp[3 * (size_t)e + 2];
+  } else {
+    *rx = R[3 * (size_t)j + 0] - R[3 * (size_t)i + 0];
+    *ry = R[3 * (size_t)j + 1] - R[3 * (size_t)i + 1];
+    *rz = R[3 * (size_t)j + 2] - R[3 * (size_t)i + 2];
+    if (cell && cell_offset) {
+      const float* c = cell + 9 * (size_t)b;
+      float s0 = (float)cell_offset[3 * (size_t)e + 0];
+      float s1 = (float)cell_offset[3 * (size_t)e + 1];
+      float s2 = (float)cell_offset[3 * (size_t)e + 2];
+      *rx += s0 * c[0] + s1 * c[3] + s2 * c[6];
+      *ry += s0 * c[1] + s1 * c[4] + s2 * c[7];
+      *rz += s0 * c[2] + s1 * c[5] + s2 * c[8];
+    }
+  }
+}
+
+// A slot is an edge of the graph if its indices are real (not -1 / >= n padding), its mask is set, and -- r_cut > 0 -- its
+// length is below the cutoff.  Pairs at d >= r_cut contribute exactly zero to the energy and to every derivative (the
+// cosine cutoff and its slope vanish there), so lists built with a skin (MD, domain decomposition: r_cut + skin) cost the
+// model kernels nothing for their skin pairs; the results are those of the reference, which carries them as zeros.
+__device__ __forceinline__ bool edge_valid(int il, int jl, int n, const unsigned char* mask, int e, int b, float r_cut,
+                                           const float* __restrict__ R, const float* __restrict__ cell,
+                                           const int* __restrict__ cell_offset, const float* __restrict__ disp) {
   bool ok = (il >= 0) && (il < n) && (jl >= 0) && (jl < n);
   if (mask) ok = ok && (mask[e] != 0);
+  if (ok && r_cut > 0.f) {
+    float rx, ry, rz;
+    edge_vec(e, b * n + il, b * n + jl, b, R, cell, cell_offset, disp, &rx, &ry, &rz);
+    ok = sqrtf(rx * rx + ry * ry + rz * rz) < r_cut;
+  }
   return ok;
 }
 
-__global__ void k_count(int Pt, int n, int P, const int* __restrict__ idx_i, const int* __restrict__ idx_j,
-                        const unsigned char* __restrict__ mask, int* __restrict__ deg) {
+__global__ void k_count(int Pt, int n, int P, float r_cut, const int* __restrict__ idx_i, const int* __restrict__ idx_j,
+                        const unsigned char* __restrict__ mask, const float* __restrict__ R, const float* __restrict__ cell,
+                        const int* __restrict__ cell_offset, const float* __restrict__ disp, int* __restrict__ deg) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < Pt) {
     int b = e / P;
     int il = idx_i[e], jl = idx_j[e];
-    if (edge_valid(il, jl, n, mask, e)) atomicAdd(&deg[b * n + il], 1);
+    if (edge_valid(il, jl, n, mask, e, b, r_cut, R, cell, cell_offset, disp)) atomicAdd(&deg[b * n + il], 1);
   }
 }
 
@@ -103,14 +139,15 @@ __global__ void k_scan_add(int n, int* __restrict__ out, const int* __restrict__
   if (i == 0) out[n] = *total;   // rowptr[N]
 }
 
-__global__ void k_fill(int Pt, int n, int P, const int* __restrict__ idx_i, const int* __restrict__ idx_j,
-                       const unsigned char* __restrict__ mask, const int* __restrict__ rowptr,
+__global__ void k_fill(int Pt, int n, int P, float r_cut, const int* __restrict__ idx_i, const int* __restrict__ idx_j,
+                       const unsigned char* __restrict__ mask, const float* __restrict__ R, const float* __restrict__ cell,
+                       const int* __restrict__ cell_offset, const float* __restrict__ disp, const int* __restrict__ rowptr,
                        int* __restrict__ cursor, int* __restrict__ tmp_src) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < Pt) {
     int b = e / P;
     int il = idx_i[e], jl = idx_j[e];
-    if (edge_valid(il, jl, n, mask, e)) {
+    if (edge_valid(il, jl, n, mask, e, b, r_cut, R, cell, cell_offset, disp)) {
       int i = b * n + il;
       int slot = rowptr[i] + atomicAdd(&cursor[i], 1);
       tmp_src[slot] = e;
@@ -141,22 +178,7 @@ __global__ void k_rowsort_geom(int N, int n, int P, const int* __restrict__ rowp
     col[dst] = j;
     src[dst] = me;
     float rx, ry, rz;
-    if (disp) {
-      rx = disp[3 * (size_t)me + 0]; ry = disp[3 * (size_t)me + 1]; rz = disp[3 * (size_t)me + 2];
-    } else {
-      rx = R[3 * (size_t)j + 0] - R[3 * (size_t)i + 0];
-      ry = R[3 * (size_t)j + 1] - R[3 * (size_t)i + 1];
-      rz = R[3 * (size_t)j + 2] - R[3 * (size_t)i + 2];
-      if (cell && cell_offset) {
-        const float* c = cell + 9 * (size_t)b;
-        float s0 = (float)cell_offset[3 * (size_t)me + 0];
-        float s1 = (float)cell_offset[3 * (size_t)me + 1];
-        float s2 = (float)cell_offset[3 * (size_t)me + 2];
-        rx += s0 * c[0] + s1 * c[3] + s2 * c[6];
-        ry += s0 * c[1] + s1 * c[4] + s2 * c[7];
-        rz += s0 * c[2] + s1 * c[5] + s2 * c[8];
-      }
-    }
+    edge_vec(me, i, j, b, R, cell, cell_offset, disp, &rx, &ry, &rz);
     float d = sqrtf(rx * rx + ry * ry + rz * rz);
     geom[dst] = make_float4(d > 0.f ? rx / d : 0.f, d > 0.f ? ry / d : 0.f, d > 0.f ? rz / d : 0.f, d);
   }
@@ -233,8 +255,8 @@ size_t so3k_graph_ws_ints(int N, int Pt) {
 void so3k_build_graph(const So3kDims& D, int B, int n, int P, const float* R, const int* idx_i, const int* idx_j,
                       const float* cell, const int* cell_offset, const float* disp, const unsigned char* mask,
                       Graph& g, int* scratch, int* dev_status, cudaStream_t st) {
-  (void)D;
   const int N = B * n, Pt = B * P;
+  const float r_cut = D.r_cut;
   g.N = N;
   g.Pt = Pt;
   int* deg = scratch;                    // N+1
@@ -246,13 +268,14 @@ void so3k_build_graph(const So3kDims& D, int B, int n, int P, const float* R, co
   int* total = bsum + nb + 1;
   cudaMemsetAsync(deg, 0, sizeof(int) * (size_t)(2 * N + 1), st);   // deg + cursor
   const int T = 256;
-  if (Pt > 0) SO3K_LAUNCH(k_count, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, n, P, idx_i, idx_j, mask, deg);
+  if (Pt > 0) SO3K_LAUNCH(k_count, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, n, P, r_cut, idx_i, idx_j, mask, R, cell, cell_offset, disp, deg);
   SO3K_LAUNCH(k_scan_local, dim3(nb), dim3(SCAN_T), 0, st, N, deg, g.rowptr, bsum);
   SO3K_LAUNCH(k_scan_bsum, dim3(1), dim3(SCAN_T), 0, st, nb, bsum, total);
   SO3K_LAUNCH(k_scan_add, dim3(so3k_cdiv(N, T)), dim3(T), 0, st, N, g.rowptr, bsum, total);
   g.n_valid = g.rowptr + N;
   if (Pt > 0) {
-    SO3K_LAUNCH(k_fill, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, n, P, idx_i, idx_j, mask, g.rowptr, cursor, tmp_src);
+    SO3K_LAUNCH(k_fill, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, Pt, n, P, r_cut, idx_i, idx_j, mask, R, cell, cell_offset, disp, g.rowptr, cursor,
+                tmp_src);
     SO3K_LAUNCH(k_slot_row, dim3(so3k_cdiv(N, T)), dim3(T), 0, st, N, g.rowptr, slot_row);
     SO3K_LAUNCH(k_rowsort_geom, dim3(so3k_cdiv(Pt, T)), dim3(T), 0, st, N, n, P, g.rowptr, deg, tmp_src, idx_j, R, cell,
                 cell_offset, disp, g.row, g.col, g.src, g.geom, slot_row);

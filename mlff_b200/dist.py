@@ -237,8 +237,10 @@ class DDRank:
 
     def stage(self, stage: int, t: int = 0):
         out = {1: self.e_atom, 4: self.forces}.get(stage)
-        self.lib.dd_stage(self.h, stage, t, self.N, self.P, self.z.data_ptr(), None if out is None else out.data_ptr(),
-                          self.ws.data_ptr(), self.status.data_ptr(), self._stream())
+        # node-level work on the owned rows only (they come first): a ghost's outputs are its owner's
+        self.lib.dd_stage_owned(self.h, stage, t, self.N, self.plan.n_own, self.P, self.z.data_ptr(),
+                                None if out is None else out.data_ptr(), self.ws.data_ptr(), self.status.data_ptr(),
+                                self._stream())
 
     def buffer(self, which: int, t: int) -> torch.Tensor:
         """(N_local, width) float32 view of x_t / chi_t / xbar1 / chibar1 inside the workspace."""

@@ -40,17 +40,15 @@ class MLFFPotential:
 
     @classmethod
     def create_from_ckpt_dir(cls, ckpt_dir: str, add_shift: bool = False, dtype=None, device: str = 'cuda:0'):
-        """hyperparameters.json + scales.json as written by the reference (mlff_train_so3krates.py:472-477);
-        parameters from ``params.npz`` (flat names) -- reading orbax ``ckpt_<n>/state`` needs orbax, which is not
-        available in this image."""
+        """hyperparameters.json + scales.json as written by the reference (mlff_train_so3krates.py:472-477); parameters
+        through mlff_b200.io.load_params_from_ckpt_dir: ``params.npz`` (flat names) or, where orbax is installed, the
+        reference's own ``ckpt_<n>/state`` (mlff/io/checkpoint.py:12-56; mdx/potential/mlff_potential.py:58-63)."""
+        from .io import load_params_from_ckpt_dir
         with open(os.path.join(ckpt_dir, 'hyperparameters.json')) as f:
             cfg = So3kratesConfig.from_hyperparameters(json.load(f))
         with open(os.path.join(ckpt_dir, 'scales.json')) as f:
             scales = json.load(f)
-        npz = os.path.join(ckpt_dir, 'params.npz')
-        if not os.path.exists(npz):
-            raise FileNotFoundError(f'{npz} not found (orbax checkpoints cannot be read without orbax)')
-        params = dict(np.load(npz))
+        params = load_params_from_ckpt_dir(ckpt_dir, cfg)
         return cls(cfg, params, energy_scale=float(np.asarray(scales['energy']['scale']).reshape(-1)[0]),
                    per_atom_shift=scales['energy'].get('per_atom_shift'), add_shift=add_shift, device=device)
 
