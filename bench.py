@@ -305,7 +305,7 @@ def run_training(args, w):
     devb = [t.to(dev) for t in pinned]
 
     def step_resident():
-        return tr.train_step(*devb)
+        return tr.train_step(*devb, cuda_graph=args.train_graph)
 
     def barrier():
         if world > 1:
@@ -328,6 +328,8 @@ def run_training(args, w):
     e1.record()
     barrier()
     launches = eng.lib.launch_count() - l0
+    if args.train_graph:                  # replays do not pass through the host-side launch counter
+        launches = tr.captured_launches * args.steps
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -361,7 +363,7 @@ def run_training(args, w):
         for a, pt in zip(host, pinned):
             pt.copy_(torch.from_numpy(a))
         batch = [pt.to(dev, non_blocking=True) for pt in pinned]
-        met = tr.train_step(*batch)
+        met = tr.train_step(*batch, cuda_graph=args.train_graph)
         return {k: float(v) for k, v in met.items()}          # D2H of the loss metrics
     for _ in range(2):
         res = e2e_call()
@@ -417,12 +419,16 @@ def run_training(args, w):
                                           f'data parallel x{world}: {B // world} structures per rank, all-reduce of 4 loss sums + '
                                           f'{tr._grad.numel() * 4} B gradient blob (NCCL)',
                            'first_pass': 'tcgen05 split-operand E+F' if flags else 'fp32 CUDA-core E+F',
+                           'step_replayed_as_cuda_graph': bool(args.train_graph),
                            'l2': 'working set of a rank fits in L2 at N > 1; 0.8 GB of kept activations at N = 1'},
                 'e2e': {'value': e2e_val, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 16},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
                 'phases_ms': phases, 'loss_check': res}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    tr.close()                            # a captured step holds NCCL kernels: release it before the process group goes
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -533,6 +539,8 @@ def run_ours(args, w):
     e1.record()
     barrier()
     launches = eng.lib.launch_count() - l0
+    if use_dd and args.dd_graph and sess._graph is not None:      # replays do not pass through the host-side launch counter
+        launches = sess.captured_launches * args.steps
     if use_dd and args.dd_timing and rank == 0:
         print('dd step phases of the last step (ms): ' + ', '.join(f'{k} {v:.3f}' for k, v in dd_phase.items())
               + f' | plan builds so far: {sess.n_builds}', file=sys.stderr)
@@ -778,6 +786,7 @@ def main():
                     'is re-used while no atom has moved more than skin / 2 (0: rebuild every step)')
     ap.add_argument('--dd-graph', action='store_true', help='domain decomposition: replay the sweep of a kept plan as one CUDA graph '
                     '(kernels + halo pack / NCCL exchange / unpack)')
+    ap.add_argument('--train-graph', action='store_true', help='c2: capture the training step once and replay it as one CUDA graph')
     ap.add_argument('--dd-timing', action='store_true', help='print the per-phase device time of one domain-decomposed step '
                     '(rank 0, stderr)')
     ap.add_argument('--no-keep-filters', action='store_true', help='recompute the filters in the backward instead of keeping '

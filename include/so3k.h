@@ -224,10 +224,12 @@ int so3k_loss_cotangents(int32_t B, int32_t n, const float* E, const float* F, c
  * (clip_norm <= 0: off) -> scale_by_adam(b1, b2, eps, eps_root) -> add_decayed_weights(weight_decay, mask) ->
  * scale(-lr), in place on the float32 blobs params / m / v (n entries).  step is the 1-based update count (bias
  * correction); frozen / decay_mask are per-entry u8 masks or NULL; *grad_sumsq (device f64) receives |grad|^2
- * (train_metrics['gradients_norm'] squared, run.py:49).  Call so3k_load_params afterwards. */
+ * (train_metrics['gradients_norm'] squared, run.py:49).  step_dev (device int64, may be NULL): when given, the update count
+ * lives on the device -- the call increments it and takes the bias corrections from it, `step` is ignored -- so that a
+ * captured CUDA graph of the training step can be replayed.  Call so3k_load_params afterwards. */
 int so3k_adam_step(size_t n, float* params, const float* grad, float* m, float* v, const uint8_t* frozen,
                    const uint8_t* decay_mask, int64_t step, float lr, float b1, float b2, float eps, float eps_root,
-                   float weight_decay, float clip_norm, double* grad_sumsq, void* stream);
+                   float weight_decay, float clip_norm, double* grad_sumsq, int64_t* step_dev, void* stream);
 
 /* ---- stepwise evaluation (spatial domain decomposition) ----------------------------------------------------
  * No counterpart in the reference (it has no multi-device path).  A rank's local problem is

@@ -113,7 +113,7 @@ class So3kLib:
         d.so3k_loss_sums.restype = C.c_int
         d.so3k_loss_cotangents.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp]
         d.so3k_loss_cotangents.restype = C.c_int
-        d.so3k_adam_step.argtypes = [sz, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp]
+        d.so3k_adam_step.argtypes = [sz, vp, vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp]
         d.so3k_adam_step.restype = C.c_int
 
     # ---- handle -----------------------------------------------------------------------------
@@ -200,10 +200,10 @@ class So3kLib:
                                              E_bar, F_bar, loss, stream), 'so3k_loss_cotangents')
 
     def adam_step(self, n, params, grad, m, v, frozen, decay_mask, step, lr, b1, b2, eps, eps_root, weight_decay,
-                  clip_norm, grad_sumsq, stream=0):
+                  clip_norm, grad_sumsq, stream=0, step_dev=None):
         _check(self.dll.so3k_adam_step(n, params, grad, m, v, frozen, decay_mask, int(step), float(lr), float(b1),
                                        float(b2), float(eps), float(eps_root), float(weight_decay), float(clip_norm),
-                                       grad_sumsq, stream), 'so3k_adam_step')
+                                       grad_sumsq, step_dev, stream), 'so3k_adam_step')
 
     # ---- stepwise / domain decomposition --------------------------------------------------------
     def dd_begin(self, h, N, P, R, z, idx_i, idx_j, cell, cell_offset, ws, ws_bytes, status, stream=0):

@@ -772,8 +772,9 @@ __global__ void k_loss_cotangents(int B, int n, const float* __restrict__ E, con
 }
 
 // ---- optimiser (training/optimizer.py:64-97: clip_by_global_norm -> scale_by_adam -> add_decayed_weights -> scale(-lr)) ----
-__global__ void k_sumsq(size_t n, const float* __restrict__ g, double* __restrict__ out) {
+__global__ void k_sumsq(size_t n, const float* __restrict__ g, double* __restrict__ out, long long* __restrict__ step_dev) {
   __shared__ double sh[TB / 32];
+  if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;       // the update count of k_adam (launched next)
   double s = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     s += (double)g[i] * (double)g[i];
@@ -789,10 +790,16 @@ __global__ void k_sumsq(size_t n, const float* __restrict__ g, double* __restric
 __global__ void k_adam(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, const unsigned char* __restrict__ frozen,
                        const unsigned char* __restrict__ decay_mask, const double* __restrict__ sumsq, float clip,
-                       float lr, float b1, float b2, float eps, float eps_root, float wd, float bc1, float bc2) {
+                       float lr, float b1, float b2, float eps, float eps_root, float wd, float bc1, float bc2,
+                       const long long* __restrict__ step_dev) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (frozen && frozen[i]) return;
+  if (step_dev) {                         // bias corrections from the device-resident update count (CUDA-graph replays)
+    const float t = (float)*step_dev;
+    bc1 = 1.0f - powf(b1, t);
+    bc2 = 1.0f - powf(b2, t);
+  }
   float gi = g[i];
   if (clip > 0.f) {
     const float nrm = (float)sqrt(*sumsq);
@@ -1127,15 +1134,15 @@ int so3k_loss_cotangents(int32_t B, int32_t n, const float* E, const float* F, c
 
 int so3k_adam_step(size_t n, float* params, const float* grad, float* m, float* v, const uint8_t* frozen,
                    const uint8_t* decay_mask, int64_t step, float lr, float b1, float b2, float eps, float eps_root,
-                   float weight_decay, float clip_norm, double* grad_sumsq, void* stream) {
-  if (!params || !grad || !m || !v || !grad_sumsq || step < 1) return SO3K_ERR_ARG;
+                   float weight_decay, float clip_norm, double* grad_sumsq, int64_t* step_dev, void* stream) {
+  if (!params || !grad || !m || !v || !grad_sumsq || (step < 1 && !step_dev)) return SO3K_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(grad_sumsq, 0, sizeof(double), st);
   int blocks = (int)((n + TB - 1) / TB);
-  SO3K_LAUNCH(k_sumsq, dim3(blocks > 512 ? 512 : blocks), dim3(TB), 0, st, n, grad, grad_sumsq);
+  SO3K_LAUNCH(k_sumsq, dim3(blocks > 512 ? 512 : blocks), dim3(TB), 0, st, n, grad, grad_sumsq, (long long*)step_dev);
   const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
   SO3K_LAUNCH(k_adam, dim3(blocks), dim3(TB), 0, st, n, params, grad, m, v, frozen, decay_mask, grad_sumsq, clip_norm, lr,
-              b1, b2, eps, eps_root, weight_decay, bc1, bc2);
+              b1, b2, eps, eps_root, weight_decay, bc1, bc2, (const long long*)step_dev);
   return cudaPeekAtLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
 }
 

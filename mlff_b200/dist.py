@@ -425,8 +425,10 @@ class DDSession:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
+        n0 = self.engine.lib.launch_count()
         with torch.cuda.graph(g):
             self._e_l = sweep()
+        self.captured_launches = self.engine.lib.launch_count() - n0          # libso3k kernels one replay runs
         self._graph, self._graph_plan = g, plan
 
     def close(self):

@@ -77,15 +77,19 @@ class TrainState:
         self.decay_mask = torch.from_numpy(decay).to(engine.device)
         self.frozen = torch.from_numpy(frozen).to(engine.device)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=engine.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=engine.device)      # the update count, device resident
 
     def apply_gradients(self, grads: torch.Tensor) -> 'TrainState':
+        """One optimiser update in place + re-load into the handle.  The update count lives on the device (incremented by
+        the call), so the same enqueued work can be replayed from a CUDA graph; `self.step` mirrors it on the host."""
         e, tx = self.engine, self.tx
         self.step += 1
         wd = 0.0 if tx.weight_decay is None else tx.weight_decay
         clip = 0.0 if tx.clip_by_global_norm is None else tx.clip_by_global_norm
         e.lib.adam_step(self.params.numel(), _p(self.params), _p(grads), _p(self.m), _p(self.v), _p(self.frozen),
                         _p(self.decay_mask) if tx.weight_decay is not None else None, self.step, tx.learning_rate,
-                        tx.b1, tx.b2, tx.eps, tx.eps_root, wd, clip, _p(self.grad_sumsq), e._stream())
+                        tx.b1, tx.b2, tx.eps, tx.eps_root, wd, clip, _p(self.grad_sumsq), e._stream(),
+                        step_dev=_p(self.step_dev))
         e.lib.load_params(e.h, _p(self.params), self.params.numel(), e._stream())
         return self
 
@@ -112,6 +116,8 @@ class Trainer:
         self._loss = torch.zeros(3, dtype=torch.float32, device=dev)
         self._grad = torch.zeros(engine.lib.param_count(engine.h), dtype=torch.float32, device=dev)
         self._ws: Optional[torch.Tensor] = None
+        self._graph = None                  # captured training step (train_step(..., cuda_graph=True)) for one batch shape
+        self._graph_key = None
 
     def _dist(self):
         if self.group is None:
@@ -161,10 +167,65 @@ class Trainer:
             dist.all_reduce(self._grad, group=grp)
         return self._loss, self._grad, E, F
 
-    def train_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None):
-        """train_step_fn (run.py:34-50): returns the device tensor (loss, mse_E, mse_F, gradients_norm^2 ... ) lazily:
-        a dict of device scalars; nothing is read back to the host here."""
+    def train_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None, cuda_graph: bool = False):
+        """train_step_fn (run.py:34-50): returns a dict of DEVICE scalars (loss, per-target MSE, gradients_norm); nothing
+        is read back to the host here.  cuda_graph=True: the whole step for this batch shape -- E+F pass, loss, dual-number
+        sweep, the two all-reduces, Adam, parameter re-load: ~500 short launches -- is captured once and replayed (a
+        small-molecule batch is launch-bound, above all when it is split over several ranks)."""
+        if cuda_graph:
+            return self._train_step_graphed(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset)
         loss, grad, _, _ = self.loss_and_grad(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset)
         self.state.apply_gradients(grad)
         loss = loss.clone()              # the metrics outlive the next step's buffers
         return {'loss': loss[0], 'energy': loss[1], 'force': loss[2], 'gradients_norm': self.state.grad_sumsq.sqrt()[0]}
+
+    def _train_step_graphed(self, R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset):
+        dev = self.engine.device
+        dts = (torch.float32, torch.int32, torch.int32, torch.int32, torch.float32, torch.float32, torch.float32, torch.int32)
+        args = [R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset]
+        key = tuple(None if a is None else tuple(a.shape) for a in args)
+        if self._graph_key != key:
+            self.close()
+            self._static = [None if a is None else a.to(dev, dt).contiguous().clone() for a, dt in zip(args, dts)]
+
+            def step():
+                loss, grad, _, _ = self.loss_and_grad(*self._static)
+                self.state.apply_gradients(grad)
+                return torch.cat([loss, self.state.grad_sumsq.sqrt().to(torch.float32)])
+            # one eager step on a side stream (workspaces, NCCL warm-up) -- undone afterwards so that the captured sequence
+            # starts from the caller's state
+            st = self.state
+            saved = (st.params.clone(), st.m.clone(), st.v.clone(), st.step, st.step_dev.clone())
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            st.params.copy_(saved[0]); st.m.copy_(saved[1]); st.v.copy_(saved[2]); st.step_dev.copy_(saved[4])
+            st.step = saved[3]
+            g = torch.cuda.CUDAGraph()
+            n0 = self.engine.lib.launch_count()
+            with torch.cuda.graph(g):
+                self._metrics = step()
+            self.captured_launches = self.engine.lib.launch_count() - n0      # libso3k kernels one replay runs
+            st.params.copy_(saved[0]); st.m.copy_(saved[1]); st.v.copy_(saved[2]); st.step_dev.copy_(saved[4])
+            st.step = saved[3]                       # capturing enqueues nothing, but the host counter moved
+            e = self.engine
+            e.lib.load_params(e.h, _p(st.params), st.params.numel(), e._stream())
+            self._graph, self._graph_key = g, key
+        else:
+            for s_, a in zip(self._static, args):
+                if s_ is not None:
+                    s_.copy_(a, non_blocking=True)
+        self._graph.replay()
+        self.state.step += 1
+        m = self._metrics.clone()
+        return {'loss': m[0], 'energy': m[1], 'force': m[2], 'gradients_norm': m[3]}
+
+    def close(self):
+        """Release a captured step (it holds NCCL kernels: the process group must outlive it)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.engine.device)
+            self._graph = None
+            self._graph_key = None

@@ -24,3 +24,13 @@ except Exception as e:
     print(sys.argv[1], 'parse failed', e)
 PY
 timeout 1500 python -m pytest tests/ -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/${TAG}_pytest.log
+timeout 300 python bench.py --workload c4 --steps 3 --warmup 3 --no-cpu-baseline --md-steps 30 --md-skin 0.5 > gpurun_out/${TAG}_bench_c4_md.json 2> gpurun_out/${TAG}_bench_c4_md.err
+python - gpurun_out/${TAG}_bench_c4_md.json <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print('md', d['md'])
+except Exception as e:
+    print(sys.argv[1], 'parse failed', e)
+PY
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches_c2.csv python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_c2.log 2>&1; echo "ncu c2 exit $?"

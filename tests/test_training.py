@@ -204,6 +204,17 @@ def test_adam_step_matches_optax_chain():
         rm, rv = np.where(keep, rm, 0.0), np.where(keep, rv, 0.0)
         np.testing.assert_allclose(p, rp, rtol=2e-5, atol=2e-6)
     assert (p[:10] == p0[:10]).all()
+    # the device-resident update count (CUDA-graph replays): `step` is ignored, the call increments step_dev
+    rng = np.random.default_rng(0)
+    rng.normal(size=n); rng.random(n)
+    p2, m2, v2 = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
+    sd = np.zeros(1, np.int64)
+    for step in range(1, 4):
+        g = (rng.normal(size=n) * (2.0 if step == 2 else 0.05)).astype(np.float32)
+        lib.adam_step(n, ptr(p2), ptr(g), ptr(m2), ptr(v2), ptr(frozen), ptr(mask), 0, lr, b1, b2, eps, er, wd, clip, ptr(ss),
+                      step_dev=ptr(sd))
+    assert sd[0] == 3
+    np.testing.assert_allclose(p2, p, rtol=1e-6, atol=1e-7)
 
 
 # ---- the Trainer driver on an emulator-backed engine stand-in, single process and gloo world_size 2 -------------------

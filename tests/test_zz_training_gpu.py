@@ -106,6 +106,27 @@ def test_training_steps_reduce_the_loss_on_device():
     assert float(tr.loss_and_grad(*args)[0][0]) < losses[0]
 
 
+def test_graph_replayed_training_step_equals_the_eager_one():
+    """train_step(cuda_graph=True): the captured step (device-resident Adam count) reproduces the eager sequence of updates."""
+    from mlff_b200.training import Trainer, Optimizer
+    ocfg, cfg, p, R, z, ii, jj, E_true, F_true = _problem(B=4)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a))
+    args = (t(R), t(z), t(ii), t(jj), t(E_true), t(F_true))
+    out = {}
+    for mode in (False, True):
+        eng = _engine(cfg, p, 0)
+        tr = Trainer(eng, {'energy': 0.01, 'force': 0.99}, Optimizer().get(learning_rate=2e-4))
+        losses = [float(tr.train_step(*args, cuda_graph=mode)['loss']) for _ in range(4)]
+        torch.cuda.synchronize()
+        assert eng.check_status() == 0 and tr.state.step == 4 and int(tr.state.step_dev.item()) == 4
+        out[mode] = (losses, eng._blob.clone())
+        tr.close()
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-5)
+    # atomics in the column sums make the gradient differ in the last bits between runs; Adam normalises the step size
+    assert (out[True][1] - out[False][1]).abs().max() < 1e-5
+    assert out[False][0][-1] < out[False][0][0]
+
+
 def test_vjp_refuses_optional_branches():
     from mlff_b200.config import So3kratesConfig
     from mlff_b200.capi import So3kError
