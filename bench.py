@@ -784,8 +784,8 @@ def main():
                     '0.5 A skin list (mlff_b200.md, one GPU) and report them under "md"')
     ap.add_argument('--dd-skin', type=float, default=0.2, help='domain decomposition: skin (Angstrom) of the per-rank plan; the plan '
                     'is re-used while no atom has moved more than skin / 2 (0: rebuild every step)')
-    ap.add_argument('--dd-graph', action='store_true', help='domain decomposition: replay the sweep of a kept plan as one CUDA graph '
-                    '(kernels + halo pack / NCCL exchange / unpack)')
+    ap.add_argument('--dd-eager', action='store_true', help='domain decomposition: launch the sweep kernel by kernel instead of replaying '
+                    'the sweep of a kept plan as one CUDA graph (kernels + halo pack / NCCL exchange / unpack; the default)')
     ap.add_argument('--train-graph', action='store_true', help='c2: capture the training step once and replay it as one CUDA graph')
     ap.add_argument('--dd-timing', action='store_true', help='print the per-phase device time of one domain-decomposed step '
                     '(rank 0, stderr)')
@@ -798,6 +798,7 @@ def main():
                     help='N > 1: dd = spatial domain decomposition of the ONE system with per-layer halo exchange over '
                          'NCCL (strong scaling; default for the periodic workloads), replicas = one independent copy per rank')
     args = ap.parse_args()
+    args.dd_graph = not args.dd_eager and args.dd_skin > 0 and not args.dd_timing
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     w = WORKLOADS[args.workload]
     if w.get('train'):

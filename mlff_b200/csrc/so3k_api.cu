@@ -208,6 +208,7 @@ struct Workspace {
   int wst_layers;
   float *rec;              // tensor mode: per-pair records of the current layer [pair][8]
   float *wbar;             // tensor mode: pair-indexed filter cotangents of the layer being differentiated [block][pair][F]
+  float *wtmp;             // tensor mode, wide model (2 x 2 sub-blocks): one sub-block's filter output [pair][F / 2]
   float *xbar_a, *xbar_b, *chibar_a, *chibar_b;
   float *e_atom;
   // optional node-level branches (SO3K_OPT_*; all null in the default model)
@@ -270,6 +271,7 @@ Workspace carve_ws(const So3kDims& D, int N, int Pt, void* base, int ws_mode) {
   w.wst = wst_layers ? (float*)take(sizeof(float) * wst_layers * 2 * (size_t)so3k_pair_capacity(Pt) * F) : nullptr;
   w.rec = wst_layers ? (float*)take(sizeof(float) * 8 * (size_t)so3k_pair_capacity(Pt)) : nullptr;
   w.wbar = wst_layers ? (float*)take(sizeof(float) * 2 * (size_t)so3k_pair_capacity(Pt) * F) : nullptr;
+  w.wtmp = (wst_layers && so3k_edge_tc_split(D) == 2) ? (float*)take(sizeof(float) * (size_t)so3k_pair_capacity(Pt) * (F / 2)) : nullptr;
   w.xbar_a = (float*)take(sizeof(float) * N * F);
   w.xbar_b = (float*)take(sizeof(float) * N * F);
   w.chibar_a = (float*)take(sizeof(float) * N * M);
@@ -328,8 +330,8 @@ void stage_layer_fwd(HandleImpl* h, Workspace& w, int t, int* dev_status, cudaSt
     { PROF(CAT_PAIR_RECORDS); so3k_launch_pair_records(D, w.g, ct, w.rec, st); }
     {
       PROF(CAT_EDGE_FWD);
-      so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
-      so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, w.wtmp, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, w.wtmp, dev_status, st);
     }
     PROF(CAT_AGGREGATE);
     so3k_launch_alpha_aggregate(D, w.g, xt, ct, proj_t, wst_t, wst_t + Pc * F, alpha_t, x1a, w.chi1 + (size_t)t * N * M, st);
@@ -411,8 +413,8 @@ void stage_layer_bwd_b(HandleImpl* h, Workspace& w, int t, int* dev_status, cuda
     { PROF(CAT_PAIR_RECORDS); so3k_launch_pair_records(D, w.g, ct, w.rec, st); }
     if (w.wst_layers == 1) {         // filters not kept: recompute this layer's
       PROF(CAT_FILTER_RECOMPUTE);
-      so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, dev_status, st);
-      so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tf[t], w.rec, wst_t, w.wtmp, dev_status, st);
+      so3k_launch_filter_tc(D, w.g, h->tg[t], w.rec, wst_t + Pc * F, w.wtmp, dev_status, st);
     }
     const size_t Gst = (D.nl + 3) & ~3;
     cudaMemsetAsync(w.ebar, 0, sizeof(float) * Pe * 2, st);

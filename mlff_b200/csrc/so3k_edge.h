@@ -32,16 +32,25 @@ struct TcBlockW {
   const float* bias;          // [b1x = (rad b1 | sph b1 | 0) over the KC hidden units | b2c padded to Fp]
   const float* Ws1;           // (nl, Fs) fp32 (epilogue of backward part 2)
   const float* bs1;           // (Fs)
+  // wide models (F > 144, e.g. F = 256): the block runs as split x split sub-blocks of the narrow kernels -- sub-block
+  // (kh, nh) = hidden units half kh (radial [kh F/2, (kh+1) F/2), spherical [kh Fs/2, ..)) -> output columns half nh; its
+  // images sit at simg / sbias[kh * 2 + nh].  split == 1: simg[0] == img.
+  int split = 1;
+  const unsigned char* simg[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* sbias[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 bool so3k_edge_tc_supported(const So3kDims& D);
+int so3k_edge_tc_split(const So3kDims& D);            // 1: narrow kernels as they are ; 2: 2 x 2 sub-blocks ; 0: unsupported
 size_t so3k_edge_tc_image_bytes(const So3kDims& D);   // per block
 void so3k_edge_tc_build(const So3kDims& D, const float* params, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
                         const EdgeBlockW& simt, cudaStream_t st);
 // filter w[pair][F] of one block for every canonical (undirected) pair of the list
 // rec[pair capacity][8]: per canonical pair (d, l0 contractions of chi_j - chi_i) of the current layer
 void so3k_launch_pair_records(const So3kDims& D, const Graph& g, const float* chi, float* rec, cudaStream_t st);
-void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, int* status,
-                           cudaStream_t st);
+// tmp: scratch of pair capacity x F / 2 floats, needed when so3k_edge_tc_split(D) == 2 (sub-block outputs before they are
+// combined into the F-wide rows)
+void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, float* tmp,
+                           int* status, cudaStream_t st);
 // radial cotangent ebar[e][0] and l0-contraction cotangent gbar of both blocks, added onto the canonical edge of each
 // pair (the arrays must be zero on entry); wbar: pair-indexed filter cotangents from so3k_launch_qk_bwd_stream
 void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,

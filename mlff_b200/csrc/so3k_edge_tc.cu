@@ -67,6 +67,64 @@ __global__ void k_pair_records(So3kDims D, int pair_cap, const int* __restrict__
   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+
+// ---- wide models (so3k_edge_tc_split == 2): a filter block runs as 2 x 2 sub-blocks of the narrow kernels ------------
+// Sub-block (kh, nh) is a filter block of its own with F_v = F / 2, Fs_v = Fs / 2: hidden radial units [kh F_v, +F_v) and
+// spherical units [kh Fs_v, +Fs_v) feeding output columns [nh F_v, +F_v).  k_slice_block cuts its weights out of the
+// parameter blob into one contiguous scratch (floats):
+//   W1 (K, F_v) | b1 (F_v) | W2 (F_v, F_v) | sW2 (Fs_v, F_v) | b2c (F_v; rad + sph bias for kh == 0, else 0) | zeros (F_v) |
+//   sW1 (nl, Fs_v) | sb1 (Fs_v)                       (W2 and sW2 adjacent: together the stacked second layer W2c)
+struct SliceOff { size_t W1, b1, W2, sW2, b2c, zero, sW1, sb1, total; };
+SO3K_HD inline SliceOff slice_offsets(const So3kDims& V) {
+  SliceOff o;
+  size_t p = 0;
+  o.W1 = p; p += (size_t)V.K * V.F;
+  o.b1 = p; p += V.F;
+  o.W2 = p; p += (size_t)V.F * V.F;
+  o.sW2 = p; p += (size_t)V.Fs * V.F;
+  o.b2c = p; p += V.F;
+  o.zero = p; p += V.F;
+  o.sW1 = p; p += (size_t)V.nl * V.Fs;
+  o.sb1 = p; p += V.Fs;
+  o.total = (p + 3) & ~(size_t)3;
+  return o;
+}
+__global__ void k_slice_block(So3kDims D, So3kDims V, int kh, int nh, const float* __restrict__ rW1,
+                              const float* __restrict__ rb1, const float* __restrict__ rW2, const float* __restrict__ rb2,
+                              const float* __restrict__ sW1, const float* __restrict__ sb1, const float* __restrict__ sW2,
+                              const float* __restrict__ sb2, float* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const SliceOff o = slice_offsets(V);
+  const int F = D.F, Fv = V.F, Fsv = V.Fs;
+  if (t < V.K * Fv) dst[o.W1 + t] = rW1[(size_t)(t / Fv) * F + kh * Fv + t % Fv];
+  if (t < Fv) {
+    dst[o.b1 + t] = rb1[kh * Fv + t];
+    dst[o.b2c + t] = kh == 0 ? rb2[nh * Fv + t] + sb2[nh * Fv + t] : 0.f;
+    dst[o.zero + t] = 0.f;
+  }
+  if (t < Fv * Fv) dst[o.W2 + t] = rW2[(size_t)(kh * Fv + t / Fv) * F + nh * Fv + t % Fv];
+  if (t < Fsv * Fv) dst[o.sW2 + t] = sW2[(size_t)(kh * Fsv + t / Fv) * F + nh * Fv + t % Fv];
+  if (t < V.nl * Fsv) dst[o.sW1 + t] = sW1[(size_t)(t / Fsv) * D.Fs + kh * Fsv + t % Fsv];
+  if (t < Fsv) dst[o.sb1 + t] = sb1[kh * Fsv + t];
+}
+// wst[c][col0 + f] (+)= tmp[c][f] for the canonical pairs c: a sub-block's output into its columns of the F-wide rows
+__global__ void k_combine_block(int pair_cap, const int* __restrict__ n_canon, int Fv, int F, int col0, int add,
+                                const float* __restrict__ tmp, float* __restrict__ wst) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = (*n_canon < pair_cap) ? *n_canon : pair_cap;
+  if (idx >= (size_t)nv * Fv) return;
+  const size_t c = idx / Fv;
+  const int f = (int)(idx % Fv);
+  float* d = wst + c * F + col0 + f;
+  *d = add ? *d + tmp[idx] : tmp[idx];
+}
+SO3K_HD inline So3kDims tc_virtual_dims(const So3kDims& D) {
+  So3kDims V = D;
+  V.F = D.F / 2;
+  V.Fs = D.Fs / 2;
+  return V;
+}
+
 }  // namespace
 
 // per-pair records of the current layer (distance + l0 contractions of the chi differences) -> rec[pair capacity][8]
@@ -614,7 +672,7 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
 // was measured: backward part 2 8.3 -> 6.75 ms per step, but the producer's 2-byte scattered stores took it from 8.0 to
 // 21 ms.)
 template <int BATCH>
-__device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int wq, int nwarps, int lane, int e0, int ne,
+__device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int ld, int wq, int nwarps, int lane, int e0, int ne,
                                               const float* __restrict__ wbar, unsigned char* Wbhi, unsigned char* Wblo) {
   const int nchunkF = T.Fp / 8;
   const int ncg = (nchunkF + 3) / 4;
@@ -631,7 +689,7 @@ __device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int wq, in
         const int rr = rg * 8 + (lane >> 2), c = cg * 4 + (lane & 3);
         const int f0 = c * 8;
         if (c < nchunkF && f0 < F && rr < ne) {
-          const float* src = wbar + (size_t)(e0 + rr) * F + f0;
+          const float* src = wbar + (size_t)(e0 + rr) * ld + f0;
           wa[v] = __ldcs(reinterpret_cast<const float4*>(src));
           if (f0 + 4 < F) wb2[v] = __ldcs(reinterpret_cast<const float4*>(src + 4));
         }
@@ -675,7 +733,7 @@ template <int NL>
 __global__ void __launch_bounds__(NT, 1)
 k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, const int* __restrict__ n_canon,
                const int* __restrict__ canon, const float* __restrict__ rec, const unsigned char* __restrict__ img,
-               const float* __restrict__ small_g, const float* __restrict__ wbar, float* __restrict__ gbar,
+               const float* __restrict__ small_g, const float* __restrict__ wbar, int wbar_ld, float* __restrict__ gbar,
                float* __restrict__ ebar, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[7];                  // 0: GEMM1 ; 1..3: GEMM3 chunks ; 4: u_ready (N_EPI) ; 5: image_ready (N_EPI) ; 6: GEMM4
@@ -721,7 +779,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
     const int cq = warp >> 2;                                      // units cq, cq + 3, cq + 6, cq + 9
     auto wbar_image = [&](int t) {                                 // 16 * ceil(Fp / 32) = 80 items over 12 warps: one batch of 7
       const int e1 = TILE_E0(t);
-      tc_wbar_image<7>(T, F, warp, 12, lane, e1, (nv - e1) < TM ? (nv - e1) : TM, wbar, Wbhi, Wblo);
+      tc_wbar_image<7>(T, F, wbar_ld, warp, 12, lane, e1, (nv - e1) < TM ? (nv - e1) : TM, wbar, Wbhi, Wblo);
       tc::fence_async_smem();
       mbar_arrive(&bars[5]);
     };
@@ -871,9 +929,16 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
     auto prefetch_wbar = [&](int e0) {                             // a tile's contiguous block of filter cotangents -> L2
       if (e0 < nv) {
         const int nrow = (nv - e0) < TM ? (nv - e0) : TM;
-        const char* pb = reinterpret_cast<const char*>(wbar + (size_t)e0 * F);
-        const int nline = (nrow * F * 4 + 127) / 128;
-        for (int k = tid - 12 * 32; k < nline; k += N_AUX) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)k * 128));
+        if (wbar_ld == F) {                                          // the tile is one contiguous block
+          const char* pb = reinterpret_cast<const char*>(wbar + (size_t)e0 * F);
+          const int nline = (nrow * F * 4 + 127) / 128;
+          for (int k = tid - 12 * 32; k < nline; k += N_AUX) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)k * 128));
+        } else {                                                     // a column slice of wider rows (wide models)
+          const int lpr = (F * 4 + 127) / 128;
+          for (int k = tid - 12 * 32; k < nrow * lpr; k += N_AUX)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wbar + (size_t)(e0 + k / lpr) * wbar_ld) +
+                                                         (size_t)(k % lpr) * 128));
+        }
       }
     };
     // radial-basis image of a tile (shared memory, single-buffered: the previous GEMM1 must have completed)
@@ -956,7 +1021,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
 
 }  // namespace
 
-bool so3k_edge_tc_supported(const So3kDims& D) {
+static bool tc_narrow_supported(const So3kDims& D) {
   if (D.F % 4 != 0 || D.K % 16 != 0 || D.K > 64) return false;
   TcDims T = make_tc_dims(D);
   if (T.Fp > 160 || T.KC > 192) return false;                   // <= 3 sixteen-column units per thread and phase
@@ -966,25 +1031,23 @@ bool so3k_edge_tc_supported(const So3kDims& D) {
   return T.f_total + 1024 <= 227u * 1024u && T.b_total + 1024 <= 227u * 1024u;
 }
 
-size_t so3k_edge_tc_image_bytes(const So3kDims& D) {
+static size_t tc_block_image_bytes(const So3kDims& D) {
   TcDims T = make_tc_dims(D);
   return ((size_t)T.w_bytes + 255) / 256 * 256 + sizeof(float) * (size_t)T.n_small + 256;
 }
 
-void so3k_edge_tc_build(const So3kDims& D, const float* p, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
-                        const EdgeBlockW& simt, cudaStream_t st) {
+// operand images + small arrays of one (sub-)block from its eight fp32 arrays
+static void tc_block_build(const So3kDims& D, const float* rW1, const float* rb1, const float* rW2, const float* rb2,
+                           const float* sW1, const float* sb1, const float* sW2, const float* sb2, unsigned char* dst,
+                           const unsigned char** img, const float** bias, cudaStream_t st) {
   TcDims T = make_tc_dims(D);
   size_t img_bytes = ((size_t)T.w_bytes + 255) / 256 * 256;
   float* small = reinterpret_cast<float*>(dst + img_bytes);
   int tot = T.Fp * T.KC;
   so3k_count_launch();
-  k_build_images<<<so3k_cdiv(tot, 256), 256, 0, st>>>(D, T, p + bp.rad_W1, p + bp.rad_b1, p + bp.rad_W2, p + bp.rad_b2,
-                                                       p + bp.sph_W1, p + bp.sph_b1, p + bp.sph_W2, p + bp.sph_b2, dst,
-                                                       small);
-  out->img = dst;
-  out->bias = small;
-  out->Ws1 = simt.Ws1;
-  out->bs1 = simt.bs1;
+  k_build_images<<<so3k_cdiv(tot, 256), 256, 0, st>>>(D, T, rW1, rb1, rW2, rb2, sW1, sb1, sW2, sb2, dst, small);
+  *img = dst;
+  *bias = small;
 }
 
 static int tc_grid(int n_tiles) {
@@ -997,10 +1060,9 @@ static int tc_grid(int n_tiles) {
   return n_tiles < n_sm ? n_tiles : n_sm;
 }
 
-// filter of one block for every canonical pair -> wst[pair][F]
-void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, int* status,
-                           cudaStream_t st) {
-  if (g.Pt <= 0) return;
+// filter of one (sub-)block for every canonical pair -> out[pair][D.F]
+static void tc_filter_block(const So3kDims& D, const Graph& g, const unsigned char* img, const float* bias, const float* rec,
+                            float* out, int* status, cudaStream_t st) {
   TcDims T = make_tc_dims(D);
   const int pair_cap = so3k_pair_capacity(g.Pt);
   int grid = tc_grid(so3k_cdiv(pair_cap, TM));
@@ -1009,7 +1071,7 @@ void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W,
 #define SO3K_FILTER_CASE(NL_)                                                                                   \
   case NL_:                                                                                                     \
     cudaFuncSetAttribute(k_filter_tc<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    k_filter_tc<NL_><<<grid, NT, smem, st>>>(D, T, pair_cap, g.n_canon, rec, W.img, W.bias, wst, status);       \
+    k_filter_tc<NL_><<<grid, NT, smem, st>>>(D, T, pair_cap, g.n_canon, rec, img, bias, out, status);           \
     break;
   switch (D.nl) {                       // number of degrees = K of the spherical first layer, a compile-time constant
     SO3K_FILTER_CASE(1) SO3K_FILTER_CASE(2) SO3K_FILTER_CASE(3) SO3K_FILTER_CASE(4) SO3K_FILTER_CASE(5)
@@ -1019,34 +1081,30 @@ void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W,
 #undef SO3K_FILTER_CASE
 }
 
-// radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of both filter blocks on the canonical edge of each
-// pair (the arrays are zero on entry: the reverse edges keep the zeros); wbar = [block][pair capacity][F] filter
-// cotangents from k_qk_bwd_stream.  The fb launch stores its totals, the gb launch adds to them.
-void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,
-                              const float* wbar, float* gbar, float* ebar, int* status, cudaStream_t st) {
-  if (g.Pt <= 0) return;
+// radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of one (sub-)block on the canonical edge of each pair;
+// wbar = the block's filter cotangents, rows of D.F columns with row stride ld; accumulate: add to what is there
+static void tc_bwd2_block(const So3kDims& D, const Graph& g, const unsigned char* img, const float* bias, const float* rec,
+                          const float* wbar, int ld, int accumulate, float* gbar, float* ebar, int* status, cudaStream_t st) {
   TcDims T = make_tc_dims(D);
   int Gst = (D.nl + 3) & ~3;
   const int pair_cap = so3k_pair_capacity(g.Pt);
   int grid = tc_grid(so3k_cdiv(pair_cap, TM));
   const size_t smem = T.b_total + 1024;
-  for (int blk = 0; blk < 2; ++blk) {
-    const TcBlockW& W = blk ? Wg : Wf;
-    so3k_count_launch();
+  so3k_count_launch();
 #define SO3K_BWD2_CASE(NL_)                                                                                        \
   case NL_:                                                                                                        \
     cudaFuncSetAttribute(k_edge_bwd2_tc<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    k_edge_bwd2_tc<NL_><<<grid, NT, smem, st>>>(D, T, Gst, pair_cap, blk, g.n_canon, g.canon, rec, W.img, W.bias,  \
-                                                wbar + (size_t)blk * pair_cap * D.F, gbar, ebar, status);          \
+    k_edge_bwd2_tc<NL_><<<grid, NT, smem, st>>>(D, T, Gst, pair_cap, accumulate, g.n_canon, g.canon, rec, img, bias, \
+                                                wbar, ld, gbar, ebar, status);                                     \
     break;
-    switch (D.nl) {
-      SO3K_BWD2_CASE(1) SO3K_BWD2_CASE(2) SO3K_BWD2_CASE(3) SO3K_BWD2_CASE(4) SO3K_BWD2_CASE(5) SO3K_BWD2_CASE(6)
-      SO3K_BWD2_CASE(7)
-      default: break;
-    }
-#undef SO3K_BWD2_CASE
+  switch (D.nl) {
+    SO3K_BWD2_CASE(1) SO3K_BWD2_CASE(2) SO3K_BWD2_CASE(3) SO3K_BWD2_CASE(4) SO3K_BWD2_CASE(5) SO3K_BWD2_CASE(6)
+    SO3K_BWD2_CASE(7)
+    default: break;
   }
+#undef SO3K_BWD2_CASE
 }
+static size_t tc_sub_scratch_bytes(const So3kDims& V) { return (sizeof(float) * slice_offsets(V).total + 255) / 256 * 256; }
 extern "C" void so3k_tc_phase_dump(void) {
   unsigned long long h[3][16];
   cudaDeviceSynchronize();
@@ -1107,7 +1165,7 @@ __global__ void k_filter_ref(So3kDims D, int pair_cap, const int* __restrict__ n
 }
 __global__ void k_edge_bwd2_ref(So3kDims D, int Gst, int pair_cap, int accumulate, const int* __restrict__ n_canon,
                                 const int* __restrict__ canon, const float* __restrict__ rec, EdgeBlockW W,
-                                const float* __restrict__ wbar, float* __restrict__ gbar, float* __restrict__ ebar) {
+                                const float* __restrict__ wbar, int ld, float* __restrict__ gbar, float* __restrict__ ebar) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int nv = (*n_canon < pair_cap) ? *n_canon : pair_cap;
   if (c >= nv) return;
@@ -1118,7 +1176,7 @@ __global__ void k_edge_bwd2_ref(So3kDims D, int Gst, int pair_cap, int accumulat
   for (int l = 0; l < SO3K_MAXDEG; ++l) gb[l] = 0.f;
   for (int k = 0; k < F + Fs; ++k) {
     float hb = 0.f;
-    for (int f = 0; f < F; ++f) hb = fmaf(wbar[(size_t)c * F + f], W.W2c[(size_t)k * F + f], hb);
+    for (int f = 0; f < F; ++f) hb = fmaf(wbar[(size_t)c * ld + f], W.W2c[(size_t)k * F + f], hb);
     float y, dy;
     if (k < F) {
       float a = W.b1[k], tp = 0.f;
@@ -1144,31 +1202,123 @@ __global__ void k_edge_bwd2_ref(So3kDims D, int Gst, int pair_cap, int accumulat
 }  // namespace
 
 extern "C" void so3k_tc_phase_dump(void) {}
-bool so3k_edge_tc_supported(const So3kDims& D) { return D.F % 4 == 0 && D.F + D.Fs <= FMAXR && D.nl <= 7 && D.H <= 8; }
-size_t so3k_edge_tc_image_bytes(const So3kDims&) { return 256; }
-void so3k_edge_tc_build(const So3kDims&, const float*, const BlockParams&, unsigned char* dst, TcBlockW* out,
-                        const EdgeBlockW& simt, cudaStream_t) {
-  out->img = reinterpret_cast<const unsigned char*>(&simt);      // the fp32 repack of the block (owned by the handle)
-  out->bias = nullptr;
-  out->Ws1 = simt.Ws1;
-  out->bs1 = simt.bs1;
-  (void)dst;
+// the stand-ins keep the CUDA kernels' narrow-shape limit, so that wide models take the same 2 x 2 sub-block path here
+static bool tc_narrow_supported(const So3kDims& D) { return D.F % 4 == 0 && D.F <= 144 && D.F + D.Fs <= FMAXR && D.nl <= 7 && D.H <= 8; }
+static size_t tc_block_image_bytes(const So3kDims&) { return 256; }
+static size_t tc_sub_scratch_bytes(const So3kDims& V) { return (sizeof(float) * slice_offsets(V).total + 255) / 256 * 256; }
+// a sub-block's "image" = an EdgeBlockW over its sliced scratch (layout of k_slice_block), stored in the image memory
+static void tc_block_build(const So3kDims&, const float* rW1, const float* rb1, const float* rW2, const float* rb2,
+                           const float* sW1, const float* sb1, const float*, const float*, unsigned char* dst,
+                           const unsigned char** img, const float** bias, cudaStream_t) {
+  EdgeBlockW* w = reinterpret_cast<EdgeBlockW*>(dst);
+  w->W1 = rW1; w->b1 = rb1; w->W2c = rW2; w->W2cT = nullptr; w->b2c = rb2; w->Ws1 = sW1; w->bs1 = sb1;
+  *img = dst;
+  *bias = nullptr;
 }
-void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, int*,
-                           cudaStream_t st) {
-  if (g.Pt <= 0) return;
+static void tc_filter_block(const So3kDims& D, const Graph& g, const unsigned char* img, const float*, const float* rec,
+                            float* out, int*, cudaStream_t st) {
   const int pair_cap = so3k_pair_capacity(g.Pt);
   SO3K_LAUNCH(k_filter_ref, dim3(so3k_cdiv(pair_cap, 32)), dim3(32), 0, st, D, pair_cap, g.n_canon, rec,
-              *reinterpret_cast<const EdgeBlockW*>(W.img), wst);
+              *reinterpret_cast<const EdgeBlockW*>(img), out);
 }
-void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,
-                              const float* wbar, float* gbar, float* ebar, int*, cudaStream_t st) {
-  if (g.Pt <= 0) return;
+static void tc_bwd2_block(const So3kDims& D, const Graph& g, const unsigned char* img, const float*, const float* rec,
+                          const float* wbar, int ld, int accumulate, float* gbar, float* ebar, int*, cudaStream_t st) {
   const int Gst = (D.nl + 3) & ~3;
   const int pair_cap = so3k_pair_capacity(g.Pt);
-  for (int blk = 0; blk < 2; ++blk)
-    SO3K_LAUNCH(k_edge_bwd2_ref, dim3(so3k_cdiv(pair_cap, 32)), dim3(32), 0, st, D, Gst, pair_cap, blk, g.n_canon, g.canon,
-                rec, *reinterpret_cast<const EdgeBlockW*>((blk ? Wg : Wf).img), wbar + (size_t)blk * pair_cap * D.F, gbar,
-                ebar);
+  SO3K_LAUNCH(k_edge_bwd2_ref, dim3(so3k_cdiv(pair_cap, 32)), dim3(32), 0, st, D, Gst, pair_cap, accumulate, g.n_canon, g.canon,
+              rec, *reinterpret_cast<const EdgeBlockW*>(img), wbar, ld, gbar, ebar);
 }
 #endif
+
+// ---- public entry points (both builds): narrow blocks as they are, wide blocks as 2 x 2 sub-blocks ---------------------
+int so3k_edge_tc_split(const So3kDims& D) {
+  if (tc_narrow_supported(D)) return 1;
+  if (D.F % 8 == 0 && D.Fs % 2 == 0 && tc_narrow_supported(tc_virtual_dims(D))) return 2;
+  return 0;
+}
+bool so3k_edge_tc_supported(const So3kDims& D) { return so3k_edge_tc_split(D) != 0; }
+
+size_t so3k_edge_tc_image_bytes(const So3kDims& D) {
+  if (so3k_edge_tc_split(D) != 2) return tc_block_image_bytes(D);
+  const So3kDims V = tc_virtual_dims(D);
+  return 4 * ((tc_block_image_bytes(V) + 255) / 256 * 256 + tc_sub_scratch_bytes(V));
+}
+
+void so3k_edge_tc_build(const So3kDims& D, const float* p, const BlockParams& bp, unsigned char* dst, TcBlockW* out,
+                        const EdgeBlockW& simt, cudaStream_t st) {
+  out->Ws1 = simt.Ws1;
+  out->bs1 = simt.bs1;
+  out->split = so3k_edge_tc_split(D);
+  if (out->split != 2) {
+#ifdef SO3K_EMU
+    out->simg[0] = reinterpret_cast<const unsigned char*>(&simt);   // the fp32 repack of the block (owned by the handle)
+    out->sbias[0] = nullptr;
+    (void)dst; (void)p; (void)bp; (void)st;
+#else
+    tc_block_build(D, p + bp.rad_W1, p + bp.rad_b1, p + bp.rad_W2, p + bp.rad_b2, p + bp.sph_W1, p + bp.sph_b1, p + bp.sph_W2,
+                   p + bp.sph_b2, dst, &out->simg[0], &out->sbias[0], st);
+#endif
+    out->img = out->simg[0];
+    out->bias = out->sbias[0];
+    return;
+  }
+  const So3kDims V = tc_virtual_dims(D);
+  const SliceOff o = slice_offsets(V);
+  const size_t ib = (tc_block_image_bytes(V) + 255) / 256 * 256, per = ib + tc_sub_scratch_bytes(V);
+  int tot = V.F * V.F;
+  if (V.K * V.F > tot) tot = V.K * V.F;
+  for (int kh = 0; kh < 2; ++kh)
+    for (int nh = 0; nh < 2; ++nh) {
+      const int sub = kh * 2 + nh;
+      unsigned char* base = dst + (size_t)sub * per;
+      float* scr = reinterpret_cast<float*>(base + ib);
+      SO3K_LAUNCH(k_slice_block, dim3(so3k_cdiv(tot, 256)), dim3(256), 0, st, D, V, kh, nh, p + bp.rad_W1, p + bp.rad_b1,
+                  p + bp.rad_W2, p + bp.rad_b2, p + bp.sph_W1, p + bp.sph_b1, p + bp.sph_W2, p + bp.sph_b2, scr);
+      tc_block_build(V, scr + o.W1, scr + o.b1, scr + o.W2, scr + o.b2c, scr + o.sW1, scr + o.sb1, scr + o.sW2, scr + o.zero,
+                     base, &out->simg[sub], &out->sbias[sub], st);
+    }
+  out->img = out->simg[0];
+  out->bias = out->sbias[0];
+}
+
+// filter of one block for every canonical pair -> wst[pair][F]
+void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W, const float* rec, float* wst, float* tmp,
+                           int* status, cudaStream_t st) {
+  if (g.Pt <= 0) return;
+  if (W.split != 2) {
+    tc_filter_block(D, g, W.simg[0], W.sbias[0], rec, wst, status, st);
+    return;
+  }
+  const So3kDims V = tc_virtual_dims(D);
+  const int pair_cap = so3k_pair_capacity(g.Pt);
+  for (int nh = 0; nh < 2; ++nh)
+    for (int kh = 0; kh < 2; ++kh) {
+      tc_filter_block(V, g, W.simg[kh * 2 + nh], W.sbias[kh * 2 + nh], rec, tmp, status, st);
+      SO3K_LAUNCH(k_combine_block, dim3(so3k_cdiv((long long)pair_cap * V.F, 256)), dim3(256), 0, st, pair_cap, g.n_canon, V.F,
+                  D.F, nh * V.F, kh, tmp, wst);
+    }
+}
+
+// radial cotangent (ebar[e][0]) and l0-contraction cotangent (gbar) of both filter blocks on the canonical edge of each
+// pair (the reverse edges keep the zeros of the memset); wbar = [block][pair capacity][F] filter cotangents from
+// k_qk_bwd_stream.  The first launch stores its totals, every later one adds to them (both are linear in wbar and in the
+// hidden-unit halves, so the sub-blocks of a wide model simply accumulate).
+void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,
+                              const float* wbar, float* gbar, float* ebar, int* status, cudaStream_t st) {
+  if (g.Pt <= 0) return;
+  const int pair_cap = so3k_pair_capacity(g.Pt);
+  int launched = 0;
+  for (int blk = 0; blk < 2; ++blk) {
+    const TcBlockW& W = blk ? Wg : Wf;
+    const float* wb = wbar + (size_t)blk * pair_cap * D.F;
+    if (W.split != 2) {
+      tc_bwd2_block(D, g, W.simg[0], W.sbias[0], rec, wb, D.F, launched++ > 0, gbar, ebar, status, st);
+      continue;
+    }
+    const So3kDims V = tc_virtual_dims(D);
+    for (int kh = 0; kh < 2; ++kh)
+      for (int nh = 0; nh < 2; ++nh)
+        tc_bwd2_block(V, g, W.simg[kh * 2 + nh], W.sbias[kh * 2 + nh], rec, wb + nh * V.F, D.F, launched++ > 0, gbar, ebar,
+                      status, st);
+  }
+}

@@ -15,7 +15,5 @@ except Exception as e:
     print(sys.argv[1], 'parse failed', e)
 PY
 }
-run c4_graph "--workload c4 --steps 40 --warmup 3 --dd-skin 0.2 --dd-graph"
-run c4_eager "--workload c4 --steps 40 --warmup 3 --dd-skin 0.2"
-run c4_timing "--workload c4 --steps 5 --warmup 3 --dd-skin 0.2 --dd-timing"
-run c2 "--workload c2 --steps 20 --warmup 3"
+run c4 "--workload c4 --steps 40 --warmup 3"
+run c2_graph "--workload c2 --steps 40 --warmup 3 --train-graph"

@@ -442,13 +442,15 @@ def test_kernels_match_reference_model_code(tag):
 
 @pytest.mark.parametrize('keep', [0, 2])
 @pytest.mark.parametrize('F,degrees,H', [(132, (1, 2, 3), 4), (36, (1, 2, 3), 4), (32, (1, 2, 2, 3), 4), (144, (1, 2, 3), 8),
-                                         (140, (1, 2, 3, 4), 4), (256, (1, 2, 3, 4), 4)])
+                                         (140, (1, 2, 3, 4), 4), (256, (1, 2, 3, 4), 4), (160, (1, 2, 3, 4), 4)])
 def test_tensor_mode_orchestration_and_streaming_kernels(ethanol, solid, F, degrees, H, keep):
     """Tensor mode on the emulator: the two tcgen05 pair kernels are stood in for by plain fp32 loops (so3k_edge_tc.cu,
     SO3K_EMU branch); everything around them is the product source -- pair records, canonical pairs, the streaming
     kernels that consume pair-indexed filters and emit pair-indexed filter cotangents (k_alpha_aggregate -- the warp-scan
     variant for F = 132 / 36 / 32, the general one for F = 140 / 144 / 256 --, k_alpha_bwd, k_qk_bwd_stream), kept /
-    recomputed filters."""
+    recomputed filters.  F = 160 and 256 exceed the narrow kernels' limit (the stand-ins keep it): they run as 2 x 2
+    sub-blocks -- sliced weights, sub-block outputs combined into the F-wide rows, cotangents accumulated over the
+    sub-blocks -- which is the host logic the B200 uses for the wide model (BASELINE configs[4])."""
     from mlff_b200.capi import FLAG_TENSOR
     cfg = o.OracleConfig(F=F, n_layers=2, degrees=degrees, n_heads=H)
     p = o.init_params(cfg, 0, embed_scale=4.0)

@@ -132,10 +132,10 @@ def test_periodic_training_batch_through_get_pbc_neighbors(solid):
 
 
 def test_c5_wide_model_at_its_configured_size():
-    """BASELINE.json configs[4] at its own size: 1 000 atoms in a 21.544 A periodic cell (several images per pair are NOT
-    needed: the cell is > 2 r_cut), F = 256, degrees 1-4 (M = 24), 3 layers -- against the float64 oracle.  F = 256 is
-    outside the tensor-core kernels' limit (W2 resident in shared memory: F <= 144), so this configuration runs the fp32
-    CUDA-core kernels; asking for tensor mode must fail loudly (SO3K_ERR_CONFIG), never fall back."""
+    """BASELINE.json configs[4] at its own size: 1 000 atoms in a 21.544 A periodic cell, F = 256, degrees 1-4 (M = 24),
+    3 layers -- against the float64 oracle, in the fp32 CUDA-core mode and on the tensor cores.  F = 256 exceeds the narrow
+    tcgen05 kernels' limit (weights resident in shared memory: F <= 144), so each filter block runs as 2 x 2 sub-blocks of
+    them (so3k_edge_tc_split == 2).  A width that does not fit even halved must fail loudly (SO3K_ERR_CONFIG)."""
     from mlff_b200.capi import So3kError
     n, box = 1000, 21.544
     pos = jittered_lattice(n, box, 4)
@@ -145,14 +145,16 @@ def test_c5_wide_model_at_its_configured_size():
     cfg = o.OracleConfig(F=256, n_layers=3, degrees=(1, 2, 3, 4))
     p = o.init_params(cfg, 4, embed_scale=4.0, scale_shift=True)
     Eo, Fo, _ = o.energy_forces(cfg, p, pos, z, ii, jj, cell=cell, cell_offset=S)
-    eng = make(cfg, p, 0)
-    E, F, _ = eng.energy_forces(dev(pos[None], torch.float32), dev(z[None], torch.int32), dev(ii[None], torch.int32),
-                                dev(jj[None], torch.int32), dev(cell[None], torch.float32), dev(S[None], torch.int32))
-    assert eng.check_status() == 0
-    dE, dF = abs(float(E.cpu()) - float(Eo)), np.abs(F.cpu().numpy()[0] - Fo.numpy()).max()
-    print(f'c5 (1000 atoms, F=256, L_max=4, {len(ii)} edges): |dE|/|E| {dE / abs(float(Eo)):.2e}, max|dF| {dF:.2e} '
-          f'(max|F| {float(np.abs(Fo.numpy()).max()):.2f})')
-    assert dE <= E_RTOL * abs(float(Eo))
-    assert dF < F_ATOL
+    for flags in (0, 1, 3):
+        eng = make(cfg, p, flags)
+        E, F, _ = eng.energy_forces(dev(pos[None], torch.float32), dev(z[None], torch.int32), dev(ii[None], torch.int32),
+                                    dev(jj[None], torch.int32), dev(cell[None], torch.float32), dev(S[None], torch.int32))
+        assert eng.check_status() == 0
+        dE, dF = abs(float(E.cpu()) - float(Eo)), np.abs(F.cpu().numpy()[0] - Fo.numpy()).max()
+        print(f'c5 (1000 atoms, F=256, L_max=4, {len(ii)} edges), flags {flags}: |dE|/|E| {dE / abs(float(Eo)):.2e}, '
+              f'max|dF| {dF:.2e} (max|F| {float(np.abs(Fo.numpy()).max()):.2f})')
+        assert dE <= E_RTOL * abs(float(Eo))
+        assert dF < F_ATOL
+    wide = o.OracleConfig(F=320, n_layers=1, degrees=(1, 2, 3, 4))
     with pytest.raises(So3kError, match='SO3K_ERR_CONFIG'):
-        make(cfg, p, 3)
+        make(wide, o.init_params(wide, 0), 1)
