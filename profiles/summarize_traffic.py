@@ -10,13 +10,19 @@ import csv, hashlib, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 workload = sys.argv[2] if len(sys.argv) > 2 else 'c4'
+# launches per bench scope (a scope of bench.py = one layer): the tensor kernels run once per filter block
 per_scope = {'k_filter_tc': 2, 'k_edge_bwd2_tc': 2, 'k_alpha_aggregate': 1, 'k_qk_bwd_stream': 1, 'k_alpha_bwd': 1}
+files = {'k_alpha_aggregate': 'k_alpha_aggregate_scan'}
 out = {}
 for k, mult in per_scope.items():
     rep = os.path.join(ROOT, 'gpurun_out', f'{tag}_{k}.ncu-rep')
-    if not os.path.exists(rep):
+    raw = os.path.join(ROOT, 'profiles', f'{tag}_{files.get(k, k)}_raw.csv')
+    if os.path.exists(raw):                      # exported on the GPU box (profiles/r02_ncu.sh)
+        txt = open(raw).read()
+    elif os.path.exists(rep):
+        txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     def get(name):
