@@ -713,14 +713,12 @@ def run_ours(args, w):
         # `traffic` (ncu dram__bytes_read + dram__bytes_write per scope) cannot be measured inside this run (a number taken
         # under a profiler is not a bench value): it is filled from profiles/ncu_traffic.json, written by
         # profiles/summarize_traffic.py from `ncu --set full` captures of THIS workload, and only when that file names the
-        # build it was captured on (sha256 of libso3k.so); otherwise it stays null.
+        # kernel sources it was captured on (sha256 over mlff_b200/csrc + include/so3k.h); otherwise it stays null.
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
         if os.path.exists(tpath) and world == 1:
-            import hashlib
             from mlff_b200 import _lib as _l
             tj = json.load(open(tpath))
-            sha = hashlib.sha256(open(_l.LIB_PATH, 'rb').read()).hexdigest()[:16]
-            if tj.get('lib_sha16') == sha and tj.get('workload') == args.workload:
+            if tj.get('source_sha16') == _l.source_sha16() and tj.get('workload') == args.workload:
                 for r_ in roofs:
                     for k_, v_ in tj.get('bytes_per_scope', {}).items():
                         if r_['kernel'].startswith(k_ + ' ') or r_['kernel'] == k_:

@@ -47,6 +47,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def source_sha16() -> str:
+    """sha256 (first 16 hex digits) over the CUDA sources and the public header: identifies the kernel code a profile was
+    taken on (the binary itself is not bit-reproducible across nvcc runs)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(PKG_DIR, '..', 'include', 'so3k.h')]
+    for f in files:
+        if os.path.isfile(f):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, 'rb').read())
+    return h.hexdigest()[:16]
+
+
 def load() -> So3kLib:
     global _lib
     if _lib is None:

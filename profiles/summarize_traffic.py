@@ -33,9 +33,10 @@ for k, mult in per_scope.items():
     b = get('dram__bytes_read.sum') + get('dram__bytes_write.sum')
     out[k] = b * mult
     print(k, 'DRAM bytes per launch %.3e' % b, 'duration', vals[hdr.index('gpu__time_duration.sum')], units[hdr.index('gpu__time_duration.sum')])
-lib = os.path.join(ROOT, 'mlff_b200', 'lib', 'libso3k.so')
-sha = hashlib.sha256(open(lib, 'rb').read()).hexdigest()[:16]
-json.dump({'tag': tag, 'workload': workload, 'lib_sha16': sha, 'bytes_per_scope': out,
+sys.path.insert(0, ROOT)
+from mlff_b200 import _lib
+sha = _lib.source_sha16()          # the kernel sources of the captured build (the binary is not bit-reproducible)
+json.dump({'tag': tag, 'workload': workload, 'source_sha16': sha, 'bytes_per_scope': out,
            'how': 'ncu --set full --clock-control none, one launch per kernel, x launches per bench scope'},
           open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'), 'w'), indent=1)
-print('wrote profiles/ncu_traffic.json for build', sha)
+print('wrote profiles/ncu_traffic.json for sources', sha)
