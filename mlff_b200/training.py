@@ -102,13 +102,21 @@ def engine_param_names(engine):
 class Trainer:
     """value_and_grad of the reference's loss + one optimiser update, for the rank's shard of the batch.
 
-    ``weights`` = {'energy': w_E, 'force': w_F} (the CLI's effective_loss_weights).  ``group``: a torch.distributed
-    process group (or True for the default group) for data-parallel training; None = single process."""
+    ``weights`` = {'energy': w_E, 'force': w_F} (the CLI's effective_loss_weights); ``scales`` = the optional per-target
+    scalars of get_loss_fn (loss.py:42-48; the CLI's variance scaling 1 / nanvar(target), mlff_train_so3krates.py:330-342):
+    the loss term of a target is weight * scale * MSE while the reported metric stays the plain MSE (`_l / scale`).
+    ``group``: a torch.distributed process group (or True for the default group) for data-parallel training; None =
+    single process."""
 
-    def __init__(self, engine, weights: Dict[str, float], tx: Optional[Optimizer] = None, group=None):
+    def __init__(self, engine, weights: Dict[str, float], tx: Optional[Optimizer] = None, group=None,
+                 scales: Optional[Dict[str, float]] = None):
         self.engine = engine
-        self.w_E = float(weights.get('energy', 0.0))
-        self.w_F = float(weights.get('force', 0.0))
+        scales = scales or {}
+        unknown = (set(weights) | set(scales)) - {'energy', 'force'}
+        if unknown:
+            raise NotImplementedError(f'loss targets {sorted(unknown)}: only energy and force targets are built')
+        self.w_E = float(weights.get('energy', 0.0)) * float(scales.get('energy', 1.0))
+        self.w_F = float(weights.get('force', 0.0)) * float(scales.get('force', 1.0))
         self.state = TrainState(engine, tx) if tx is not None else None
         self.group = group
         dev = engine.device
@@ -166,6 +174,33 @@ class Trainer:
         if dist is not None:
             dist.all_reduce(self._grad, group=grp)
         return self._loss, self._grad, E, F
+
+    def eval_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None):
+        """valid_step_fn (run.py:88-104): the loss metrics of a batch without gradients -- one E+F pass and the loss sums
+        (all-reduced over the group); returns a dict of device scalars."""
+        e = self.engine
+        dev = e.device
+        R = R.to(dev, torch.float32).contiguous()
+        z = z.to(dev, torch.int32).contiguous()
+        idx_i = idx_i.to(dev, torch.int32).contiguous()
+        idx_j = idx_j.to(dev, torch.int32).contiguous()
+        E_true = E_true.to(dev, torch.float32).reshape(-1).contiguous()
+        F_true = F_true.to(dev, torch.float32).contiguous()
+        if cell is not None:
+            cell = cell.to(dev, torch.float32).contiguous()
+            cell_offset = cell_offset.to(dev, torch.int32).contiguous()
+        B, n = z.shape
+        E, F, _ = e.energy_forces(R, z, idx_i, idx_j, cell, cell_offset)
+        E1 = E.reshape(-1)
+        self._sums.zero_()
+        e.lib.loss_sums(B, n, _p(E1), _p(F), _p(E_true), _p(F_true), _p(z), _p(self._sums), e._stream())
+        dist = self._dist()
+        if dist is not None:
+            dist.all_reduce(self._sums, group=None if self.group is True else self.group)
+        s = self._sums.clone()
+        mse_E = torch.where(s[1] > 0, s[0] / s[1].clamp_min(1.0), torch.zeros_like(s[0]))
+        mse_F = torch.where(s[3] > 0, s[2] / s[3].clamp_min(1.0), torch.zeros_like(s[2]))
+        return {'loss': (self.w_E * mse_E + self.w_F * mse_F).float(), 'energy': mse_E.float(), 'force': mse_F.float()}
 
     def train_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None, cuda_graph: bool = False):
         """train_step_fn (run.py:34-50): returns a dict of DEVICE scalars (loss, per-target MSE, gradients_norm); nothing

@@ -273,6 +273,16 @@ def test_trainer_step_reduces_the_loss_and_matches_oracle_gradient():
         off, cnt = eng.lib.param_lookup(eng.h, k)
         r = og[k].reshape(-1)
         assert np.abs(grad[off:off + cnt].numpy() - r).max() <= 5e-5 * max(np.abs(r).max(), 1e-3), k
+    ev = tr.eval_step(tR, tz, ti, tj, tE, tF)                              # valid_step_fn: same loss, no gradient
+    assert abs(float(ev['loss']) - lo) <= 2e-5 * abs(lo)
+    # per-target scales (variance scaling of the CLI): term = weight * scale * MSE, metric = plain MSE
+    trs = Trainer(eng, {'energy': 0.01, 'force': 0.99}, scales={'energy': 3.0, 'force': 0.5})
+    ls, gs_, _, _ = trs.loss_and_grad(tR, tz, ti, tj, tE, tF)
+    assert abs(float(ls[0]) - (0.03 * float(loss0[1]) + 0.495 * float(loss0[2]))) <= 1e-5 * abs(float(ls[0]))
+    assert abs(float(ls[1]) - float(loss0[1])) <= 1e-6 * abs(float(loss0[1]))
+    with pytest.raises(NotImplementedError):
+        Trainer(eng, {'energy': 1.0, 'stress': 1.0})
+    loss0, grad, _, _ = tr.loss_and_grad(tR, tz, ti, tj, tE, tF)           # (the buffers are shared between the trainers of an engine)
     blob0 = eng._blob.clone()
     gn = np.sqrt(sum(float((g ** 2).sum()) for g in og.values()))
     metrics = tr.train_step(tR, tz, ti, tj, tE, tF)
