@@ -713,7 +713,7 @@ def run_ours(args, w):
         # `traffic` (ncu dram__bytes_read + dram__bytes_write per scope) cannot be measured inside this run (a number taken
         # under a profiler is not a bench value): it is filled from profiles/ncu_traffic.json, written by
         # profiles/summarize_traffic.py from `ncu --set full` captures of THIS workload, and only when that file names the
-        # kernel sources it was captured on (sha256 over mlff_b200/csrc + include/so3k.h); otherwise it stays null.
+        # kernel sources it was captured on (sha256 over the source files of the profiled kernels, mlff_b200._lib.PROFILED_SOURCES); otherwise it stays null.
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
         if os.path.exists(tpath) and world == 1:
             from mlff_b200 import _lib as _l

@@ -257,6 +257,16 @@ int so3k_dd_stage_owned(so3k_handle* h, int32_t stage, int32_t t, int32_t N, int
                         float* out, void* workspace, int32_t* dev_status, void* stream);
 int so3k_dd_buffer(const so3k_handle* h, int32_t which, int32_t t, int32_t N, int32_t P, size_t* offset,
                    size_t* row_floats);
+/* Halo messages of an exchange, one kernel each.  pair 0 = (x_t, chi_t), pair 1 = (xbar1, chibar1); a message row is the
+ * F + M floats [x row | chi row] of one atom.
+ *   so3k_dd_pack:   out (n_send, F + M) <- the owned rows send_idx[r] (device int32, the sender's local row ids, grouped
+ *                   by destination rank) of both buffers
+ *   so3k_dd_unpack: the ghost rows n_owned .. N-1 of both buffers <- in (N - n_owned, F + M), in the receiver's ghost order
+ * The transport between the two (NCCL all-to-all, peer copies) is the caller's. */
+int so3k_dd_pack(const so3k_handle* h, int32_t pair, int32_t t, int32_t N, int32_t P, const int32_t* send_idx, int32_t n_send,
+                 float* out, void* workspace, void* stream);
+int so3k_dd_unpack(const so3k_handle* h, int32_t pair, int32_t t, int32_t N, int32_t n_owned, int32_t P, const float* in,
+                   void* workspace, void* stream);
 
 /* ---- edge featurisation (standalone; the fused model path recomputes these on chip) ---------
  * Inputs as GeometryEmbed: either positions R (n,3) [+ cell (3,3) row-wise + cell_offset (P,3)]

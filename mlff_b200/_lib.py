@@ -47,16 +47,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+# the files that define the kernels bench.py reports a roofline for (k_filter_tc, k_edge_bwd2_tc, k_alpha_aggregate_scan,
+# k_qk_bwd_stream, k_alpha_bwd) and the device-code headers they include
+PROFILED_SOURCES = ['so3k_edge_tc.cu', 'so3k_tc.cuh', 'so3k_agg.cu', 'so3k_math.h', 'so3k_portable.h']
+
+
 def source_sha16() -> str:
-    """sha256 (first 16 hex digits) over the CUDA sources and the public header: identifies the kernel code a profile was
-    taken on (the binary itself is not bit-reproducible across nvcc runs)."""
+    """sha256 (first 16 hex digits) over the sources of the profiled kernels: identifies the kernel code an ncu capture
+    was taken on (the binary itself is not bit-reproducible across nvcc runs)."""
     import hashlib
     h = hashlib.sha256()
-    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(PKG_DIR, '..', 'include', 'so3k.h')]
-    for f in files:
-        if os.path.isfile(f):
-            h.update(os.path.basename(f).encode())
-            h.update(open(f, 'rb').read())
+    for name in PROFILED_SOURCES:
+        h.update(name.encode())
+        h.update(open(os.path.join(CSRC, name), 'rb').read())
     return h.hexdigest()[:16]
 
 

@@ -34,7 +34,7 @@ EXPORTS = ['so3k_create', 'so3k_destroy', 'so3k_version', 'so3k_param_count', 's
            'so3k_load_params', 'so3k_workspace_bytes', 'so3k_energy_forces', 'so3k_potential_displacements',
            'so3k_featurise', 'so3k_neighbor_list_workspace_bytes', 'so3k_neighbor_list', 'so3k_launch_count',
            'so3k_profile_categories', 'so3k_profile_enable', 'so3k_profile_collect', 'so3k_tc_selftest',
-           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_stage_owned', 'so3k_dd_buffer', 'so3k_stress', 'so3k_train_workspace_bytes',
+           'so3k_dd_begin', 'so3k_dd_stage', 'so3k_dd_stage_owned', 'so3k_dd_buffer', 'so3k_dd_pack', 'so3k_dd_unpack', 'so3k_stress', 'so3k_train_workspace_bytes',
            'so3k_energy_forces_vjp', 'so3k_loss_sums', 'so3k_loss_cotangents', 'so3k_adam_step']
 
 
@@ -95,6 +95,10 @@ class So3kLib:
         d.so3k_dd_stage.restype = C.c_int
         d.so3k_dd_stage_owned.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
         d.so3k_dd_stage_owned.restype = C.c_int
+        d.so3k_dd_pack.argtypes = [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp]
+        d.so3k_dd_pack.restype = C.c_int
+        d.so3k_dd_unpack.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
+        d.so3k_dd_unpack.restype = C.c_int
         d.so3k_dd_buffer.argtypes = [vp, i32, i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]
         d.so3k_dd_buffer.restype = C.c_int
         d.so3k_tc_selftest.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp]
@@ -215,6 +219,12 @@ class So3kLib:
 
     def dd_stage_owned(self, h, stage, t, N, n_owned, P, z, out, ws, status, stream=0):
         _check(self.dll.so3k_dd_stage_owned(h, stage, t, N, n_owned, P, z, out, ws, status, stream), 'so3k_dd_stage_owned')
+
+    def dd_pack(self, h, pair, t, N, P, send_idx, n_send, out, ws, stream=0):
+        _check(self.dll.so3k_dd_pack(h, pair, t, N, P, send_idx, n_send, out, ws, stream), 'so3k_dd_pack')
+
+    def dd_unpack(self, h, pair, t, N, n_owned, P, inp, ws, stream=0):
+        _check(self.dll.so3k_dd_unpack(h, pair, t, N, n_owned, P, inp, ws, stream), 'so3k_dd_unpack')
 
     def dd_buffer(self, h, which, t, N, P):
         off, rf = C.c_size_t(), C.c_size_t()

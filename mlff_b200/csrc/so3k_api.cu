@@ -690,6 +690,36 @@ int so3k_dd_buffer(const so3k_handle* hh, int32_t which, int32_t t, int32_t N, i
   return SO3K_OK;
 }
 
+// the two node buffers of an exchange: pair 0 = (x_t, chi_t), pair 1 = (xbar1, chibar1)
+static bool dd_pair(const HandleImpl* h, int pair, int t, int N, int P, void* workspace, float** a, float** b, int* wa, int* wb) {
+  const So3kDims& D = h->dims;
+  if (t < 0 || t > D.L || (pair != 0 && pair != 1)) return false;
+  Workspace w = carve_ws(D, N, P, workspace, wst_layers_of(h));
+  *wa = D.F;
+  *wb = D.M;
+  if (pair == 0) { *a = w.x + (size_t)t * N * D.F; *b = w.chi + (size_t)t * N * D.M; }
+  else { *a = w.xbar_b; *b = w.chibar_b; }
+  return true;
+}
+int so3k_dd_pack(const so3k_handle* hh, int32_t pair, int32_t t, int32_t N, int32_t P, const int32_t* send_idx, int32_t n_send,
+                 float* out, void* workspace, void* stream) {
+  if (!hh || !workspace || N <= 0 || n_send < 0 || (n_send > 0 && (!send_idx || !out))) return SO3K_ERR_ARG;
+  float *a, *b;
+  int wa, wb;
+  if (!dd_pair(static_cast<const HandleImpl*>(hh), pair, t, N, P, workspace, &a, &b, &wa, &wb)) return SO3K_ERR_ARG;
+  so3k_launch_dd_pack(n_send, wa, wb, send_idx, a, b, out, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+int so3k_dd_unpack(const so3k_handle* hh, int32_t pair, int32_t t, int32_t N, int32_t n_owned, int32_t P, const float* in,
+                   void* workspace, void* stream) {
+  if (!hh || !workspace || N <= 0 || n_owned < 0 || n_owned > N || (n_owned < N && !in)) return SO3K_ERR_ARG;
+  float *a, *b;
+  int wa, wb;
+  if (!dd_pair(static_cast<const HandleImpl*>(hh), pair, t, N, P, workspace, &a, &b, &wa, &wb)) return SO3K_ERR_ARG;
+  so3k_launch_dd_unpack(N - n_owned, n_owned, wa, wb, in, a, b, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
+}
+
 // ---- instrumentation ----------------------------------------------------------------------------------
 const char* so3k_profile_categories(void) { return kCatNames; }
 

@@ -107,6 +107,11 @@ void so3k_launch_energy_sum(int B, int n, const float* e_atom, float offset, flo
 // Ziegler-Biersack-Littmark repulsion: e_atom[i] += out_scale * (sum_{e in row i} e_edge - atom_shift), rbar[e] += dE/dr_e
 void so3k_launch_zbl(const So3kDims& D, const Graph& g, const int* z, const float* zbl_raw, float out_scale,
                      float atom_shift, float* e_atom, float* rbar, cudaStream_t st);
+// halo rows of the domain decomposition: gather the rows a peer needs of two node buffers into one message / scatter the
+// received rows into the ghost blocks (rows n_own ..)
+void so3k_launch_dd_pack(int n_rows, int wa, int wb, const int* send_idx, const float* a, const float* b, float* out,
+                         cudaStream_t st);
+void so3k_launch_dd_unpack(int n_rows, int n_own, int wa, int wb, const float* in, float* a, float* b, cudaStream_t st);
 // agg.cu
 void so3k_launch_aggregate(const So3kDims& D, const Graph& g, const float* x, const float* chi, const float* proj,
                            const float* alpha, float* x1, float* chi1, cudaStream_t st);

@@ -621,3 +621,37 @@ void so3k_launch_resmlp_bwd(const So3kDims& D, int N, const float* x, const floa
   SO3K_LAUNCH(k_resmlp_bwd, dim3(so3k_cdiv(N, TA)), dim3(NT), smem, st, D, N, x, p + W[0], p + W[1], pT + W[0],
               pT + W[1], pT + W[2], ybar, xbar);
 }
+
+// ---- halo rows of the domain decomposition (so3k_dd_pack / so3k_dd_unpack) -------------------------------------------------
+// pack: out[r][0 .. wa + wb) = [a[send_idx[r]][0 .. wa) | b[send_idx[r]][0 .. wb)] -- the owned rows a peer needs, both buffers
+// of an exchange in one message row; unpack: a[n_own + r] = in[r][0 .. wa), b[n_own + r] = in[r][wa ..) -- the ghost rows.
+namespace {
+__global__ void k_dd_pack(int n_rows, int wa, int wb, const int* __restrict__ send_idx, const float* __restrict__ a,
+                          const float* __restrict__ b, float* __restrict__ out) {
+  const int w = wa + wb;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_rows * w) return;
+  const int r = (int)(idx / w), c = (int)(idx % w);
+  const size_t src = (size_t)send_idx[r];
+  out[idx] = c < wa ? a[src * wa + c] : b[src * wb + (c - wa)];
+}
+__global__ void k_dd_unpack(int n_rows, int n_own, int wa, int wb, const float* __restrict__ in, float* __restrict__ a,
+                            float* __restrict__ b) {
+  const int w = wa + wb;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_rows * w) return;
+  const int r = (int)(idx / w), c = (int)(idx % w);
+  if (c < wa) a[(size_t)(n_own + r) * wa + c] = in[idx];
+  else b[(size_t)(n_own + r) * wb + (c - wa)] = in[idx];
+}
+}  // namespace
+
+void so3k_launch_dd_pack(int n_rows, int wa, int wb, const int* send_idx, const float* a, const float* b, float* out,
+                         cudaStream_t st) {
+  if (n_rows <= 0) return;
+  SO3K_LAUNCH(k_dd_pack, dim3(so3k_cdiv((long long)n_rows * (wa + wb), 256)), dim3(256), 0, st, n_rows, wa, wb, send_idx, a, b, out);
+}
+void so3k_launch_dd_unpack(int n_rows, int n_own, int wa, int wb, const float* in, float* a, float* b, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  SO3K_LAUNCH(k_dd_unpack, dim3(so3k_cdiv((long long)n_rows * (wa + wb), 256)), dim3(256), 0, st, n_rows, n_own, wa, wb, in, a, b);
+}

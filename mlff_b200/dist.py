@@ -270,15 +270,27 @@ def exchange_inprocess(ranks: Sequence[DDRank], which: Sequence[int], t: int) ->
 
 
 def exchange_distributed(ranks: Sequence[DDRank], which: Sequence[int], t: int) -> None:
-    """One rank per process: pack the requested owned rows of all buffers into one message per peer and exchange
-    (NCCL all_to_all_single; point-to-point sends on backends without all-to-all, e.g. gloo in the CPU tests)."""
+    """One rank per process: the owned rows the peers need of both buffers of the exchange go into one message per peer
+    (so3k_dd_pack), are exchanged (NCCL all_to_all_single; point-to-point sends on backends without all-to-all, e.g. gloo in
+    the CPU tests) and land in the ghost blocks (so3k_dd_unpack)."""
     import torch.distributed as dist
     (r,) = ranks
     p = r.plan
-    bufs = [r.buffer(w, t) for w in which]
-    width = sum(b.shape[1] for b in bufs)
-    send = torch.cat([b[p.send_idx] for b in bufs], dim=1).contiguous()
-    recv = torch.empty(p.n_ghost, width, dtype=torch.float32, device=send.device)
+    pair = {(0, 1): 0, (2, 3): 1}[tuple(which)]
+    if getattr(r, '_halo_of', None) is not p:
+        # per plan: int32 send list on the device and the two message buffers (one row = [x row | chi row] of an atom)
+        bufs = [r.buffer(w, t) for w in which]
+        width = sum(b.shape[1] for b in bufs)
+        dev = bufs[0].device
+        r._send_idx32 = p.send_idx.to(dev, torch.int32).contiguous()
+        r._send = torch.empty(int(r._send_idx32.shape[0]), width, dtype=torch.float32, device=dev)
+        r._recv = torch.empty(p.n_ghost, width, dtype=torch.float32, device=dev)
+        r._halo_of = p
+    send, recv = r._send, r._recv
+    # gather the owned rows the peers need of both buffers into one message (one kernel), exchange, scatter the received
+    # rows into the ghost blocks (one kernel)
+    r.lib.dd_pack(r.h, pair, t, r.N, r.P, r._send_idx32.data_ptr(), int(send.shape[0]), send.data_ptr(), r.ws.data_ptr(),
+                  r._stream())
     if dist.get_backend() == 'nccl':
         dist.all_to_all_single(recv, send, output_split_sizes=p.recv_counts, input_split_sizes=p.send_counts)
     else:
@@ -294,10 +306,7 @@ def exchange_distributed(ranks: Sequence[DDRank], which: Sequence[int], t: int) 
             ro += rc
         for q in reqs:
             q.wait()
-    c = 0
-    for b in bufs:
-        b[p.n_own:] = recv[:, c: c + b.shape[1]]
-        c += b.shape[1]
+    r.lib.dd_unpack(r.h, pair, t, r.N, p.n_own, r.P, recv.data_ptr(), r.ws.data_ptr(), r._stream())
 
 
 def run_energy_forces(ranks: Sequence[DDRank], exchange: Exchange) -> None:
