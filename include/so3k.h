@@ -199,8 +199,9 @@ int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
  * of the Energy module, observable.py:49-58).  Because F = -dE/dR this is second order; it is evaluated as the
  * forward-mode derivative along -F_bar of the reverse-mode parameter gradient, in one dual-number sweep (so3k_train.cu).
  * F_bar == NULL selects the first-order sweep (grad = sum_b E_bar[b] dE_b/dtheta; E_bar == NULL means all ones).
- * E_out (B) or NULL receives the energies of the sweep.  Supported for the default model (no LAYER_NORM /
- * RESIDUAL_MLP / ZBL flags; SO3K_ERR_CONFIG otherwise); arithmetic is fp32 on the CUDA cores in either filter mode. */
+ * E_out (B) or NULL receives the energies of the sweep.  Every model variant of so3k_config.flags is covered: the optional
+ * LayerNorms and ResidualMLPs and the ten ZBL scalars have their gradients in the blob too.  Arithmetic is fp32 on the CUDA
+ * cores in either filter mode. */
 size_t so3k_train_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total);
 int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P,
                            const float* R, const int32_t* z, const int32_t* idx_i, const int32_t* idx_j,

@@ -14,7 +14,8 @@
 // Arrays are plane-major: [plane][row][col], plane stride = rows * cols, rows = atoms N or edge slots Pt (sorted CSR
 // order of so3k_graph.cu; rows >= n_valid are zero in every cotangent array, so reductions over rows may run over all
 // slots).  Reference rows: a5-a19 of SURVEY.md section 8 (embed.py:66-169, so3krates_layer.py:57-178, 449-465, 526-608,
-// observable.py:62-93); only the default model (no LayerNorm / ResidualMLP / ZBL) is trainable here.
+// observable.py:62-93) plus the optional branches: LayerNorm pre / post (so3krates_layer.py:103-106, 153-156, 170-174),
+// ResidualMLP 1 / 2 (mlp.py:30-72) and the ZBL repulsion with its ten scalars (observable.py:110-183).
 #include "so3k_internal.h"
 
 namespace {
@@ -42,6 +43,8 @@ SO3K_HD inline float t_sqrt(float a) { return sqrtf(a); }
 SO3K_HD inline Dual t_sqrt(Dual a) { float s = sqrtf(a.p); return mkd(s, s > 0.f ? 0.5f * a.t / s : 0.f); }
 SO3K_HD inline float t_cos(float a) { return cosf(a); }
 SO3K_HD inline Dual t_cos(Dual a) { return mkd(cosf(a.p), -sinf(a.p) * a.t); }
+SO3K_HD inline float t_max0(float a) { return a > 0.f ? a : 0.f; }
+SO3K_HD inline Dual t_max0(Dual a) { return a.p > 0.f ? a : mkd(0.f, 0.f); }
 SO3K_HD inline float prim(float a) { return a; }
 SO3K_HD inline float prim(Dual a) { return a.p; }
 // the component that is written into the parameter-gradient blob
@@ -83,12 +86,13 @@ __global__ void k_tr_geom(So3kDims D, int N, int Pt, int P, const int* __restric
                           const int* __restrict__ col, const int* __restrict__ src, const float* __restrict__ R,
                           const float* __restrict__ Rdot, const float* __restrict__ cell,
                           const int* __restrict__ cell_offset, float* __restrict__ phi, float* __restrict__ Y,
-                          float* __restrict__ rbf) {
+                          float* __restrict__ rbf, float* __restrict__ dist) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Pt) return;
   const size_t ps1 = (size_t)Pt, psM = (size_t)Pt * D.M, psK = (size_t)Pt * D.K;
   if (e >= rowptr[N]) {
     Tr<T>::st(phi, e, ps1, Tr<T>::zero());
+    Tr<T>::st(dist, e, ps1, Tr<T>::zero());
     for (int m = 0; m < D.M; ++m) Tr<T>::st(Y, (size_t)e * D.M + m, psM, Tr<T>::zero());
     for (int k = 0; k < D.K; ++k) Tr<T>::st(rbf, (size_t)e * D.K + k, psK, Tr<T>::zero());
     return;
@@ -111,6 +115,7 @@ __global__ void k_tr_geom(So3kDims D, int N, int Pt, int P, const int* __restric
   T ph = Tr<T>::zero();
   if (prim(d) < D.r_cut) ph = 0.5f * (t_cos(d * (3.14159265358979323846f / D.r_cut)) + 1.0f);
   Tr<T>::st(phi, e, ps1, ph);
+  Tr<T>::st(dist, e, ps1, d);
   T yl[9];
   for (int sgm = 0; sgm < D.nl; ++sgm) {
     const int l = D.deg[sgm];
@@ -331,15 +336,21 @@ __global__ void k_tr_intpost_bwd(So3kDims D, int N, const float* __restrict__ ch
 template <class T>
 __global__ void k_tr_intpre_bwd(So3kDims D, int N, const float* __restrict__ chi1, const float* __restrict__ ab,
                                 const float* __restrict__ x2bar, const float* __restrict__ chi2bar,
-                                const float* __restrict__ catbar, float* __restrict__ x1bar, float* __restrict__ chi1bar) {
+                                const float* __restrict__ catbar, float* __restrict__ x1bar, float* __restrict__ chi1bar,
+                                float* __restrict__ xnbar /* null, or (LayerNorm before the block): catbar[:, :F] goes here */) {
   const int C = D.F + D.M, Cab = D.F + D.nl;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * C) return;
   const int n = (int)(idx / C), c = (int)(idx % C);
   const size_t psn = (size_t)N * D.F, psm = (size_t)N * D.M, psab = (size_t)N * Cab;
   if (c < D.F) {
-    Tr<T>::st(x1bar, (size_t)n * D.F + c, psn,
-              Tr<T>::ld(x2bar, (size_t)n * D.F + c, psn) + Tr<T>::ld(catbar, (size_t)n * Cab + c, psab));
+    if (xnbar) {
+      Tr<T>::st(xnbar, (size_t)n * D.F + c, psn, Tr<T>::ld(catbar, (size_t)n * Cab + c, psab));
+      Tr<T>::st(x1bar, (size_t)n * D.F + c, psn, Tr<T>::ld(x2bar, (size_t)n * D.F + c, psn));
+    } else {
+      Tr<T>::st(x1bar, (size_t)n * D.F + c, psn,
+                Tr<T>::ld(x2bar, (size_t)n * D.F + c, psn) + Tr<T>::ld(catbar, (size_t)n * Cab + c, psab));
+    }
   } else {
     const int m = c - D.F, s = D.m_seg[m];
     T b = Tr<T>::ld(ab, (size_t)n * Cab + D.F + s, psab);
@@ -348,6 +359,74 @@ __global__ void k_tr_intpre_bwd(So3kDims D, int N, const float* __restrict__ chi
     Tr<T>::st(chi1bar, (size_t)n * D.M + m, psm,
               Tr<T>::ld(chi2bar, (size_t)n * D.M + m, psm) * (1.0f + b) + gb * (2.0f * D.m_cg[m]) * c1);
   }
+}
+
+// flax LayerNorm over the F features of a row (so3krates_layer.py:103-106, 153-156, 170-174; eps 1e-6, fast variance
+// max(0, E[x^2] - E[x]^2), scale and bias).  One warp per atom row.
+template <class T>
+__global__ void k_tr_layernorm(int N, int F, const float* __restrict__ x, const float* __restrict__ scale,
+                               const float* __restrict__ bias, float* __restrict__ y) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const size_t ps = (size_t)N * F;
+  T s1 = Tr<T>::zero(), s2 = Tr<T>::zero();
+  for (int f = lane; f < F; f += 32) {
+    T v = Tr<T>::ld(x, (size_t)n * F + f, ps);
+    s1 += v;
+    s2 += v * v;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float invF = 1.0f / (float)F;
+  T mu = s1 * invF;
+  T r = 1.0f / t_sqrt(t_max0(s2 * invF - mu * mu) + 1e-6f);
+  for (int f = lane; f < F; f += 32)
+    Tr<T>::st(y, (size_t)n * F + f, ps, (Tr<T>::ld(x, (size_t)n * F + f, ps) - mu) * r * scale[f] + bias[f]);
+}
+// out = (add ? add : 0) + dLayerNorm(x)^T ybar ; gs = ybar * xhat (its column sum is the scale gradient; the bias gradient is
+// the column sum of ybar).  out may alias ybar or add.
+template <class T>
+__global__ void k_tr_layernorm_bwd(int N, int F, const float* __restrict__ x, const float* __restrict__ scale,
+                                   const float* __restrict__ ybar, const float* __restrict__ add, float* __restrict__ out,
+                                   float* __restrict__ gs) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const size_t ps = (size_t)N * F;
+  T s1 = Tr<T>::zero(), s2 = Tr<T>::zero();
+  for (int f = lane; f < F; f += 32) {
+    T v = Tr<T>::ld(x, (size_t)n * F + f, ps);
+    s1 += v;
+    s2 += v * v;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const float invF = 1.0f / (float)F;
+  T mu = s1 * invF;
+  T r = 1.0f / t_sqrt(t_max0(s2 * invF - mu * mu) + 1e-6f);
+  T m1 = Tr<T>::zero(), m2 = Tr<T>::zero();
+  for (int f = lane; f < F; f += 32) {
+    T xh = (Tr<T>::ld(x, (size_t)n * F + f, ps) - mu) * r;
+    T gh = Tr<T>::ld(ybar, (size_t)n * F + f, ps) * scale[f];
+    m1 += gh;
+    m2 += gh * xh;
+  }
+  m1 = warp_sum(m1) * invF;
+  m2 = warp_sum(m2) * invF;
+  for (int f = lane; f < F; f += 32) {
+    const size_t i = (size_t)n * F + f;
+    T xh = (Tr<T>::ld(x, i, ps) - mu) * r;
+    T yb = Tr<T>::ld(ybar, i, ps);
+    T v = r * (yb * scale[f] - m1 - xh * m2);
+    if (add) v += Tr<T>::ld(add, i, ps);
+    Tr<T>::st(gs, i, ps, yb * xh);
+    Tr<T>::st(out, i, ps, v);
+  }
+}
+// out = a + b (all planes)
+template <class T>
+__global__ void k_tr_add(size_t count, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < count * Tr<T>::planes) out[idx] = a[idx] + b[idx];
 }
 
 // read-out (observable.py:80-83): e_i = (silu(a_i) . w2 + b2) scale[z] + shift[z], masked; and its reverse with the
@@ -385,12 +464,12 @@ __global__ void k_tr_readout(int N, int F, int n_per, int nemb, const int* __res
     Tr<T>::st(ebar, n, (size_t)N, sb);
   }
 }
-__global__ void k_tr_energy_sum(int B, int n_per, const float* __restrict__ e_atom, float* __restrict__ E) {
+__global__ void k_tr_energy_sum(int B, int n_per, const float* __restrict__ e_atom, float offset, float* __restrict__ E) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double s = 0.0;
   for (int i = 0; i < n_per; ++i) s += (double)e_atom[(size_t)b * n_per + i];
-  E[b] = (float)s;
+  E[b] = (float)(s - (double)offset);            // per-structure ZBL shift (observable.py:83-86)
 }
 
 // ---- reverse sweep over the edges --------------------------------------------------------------------------------
@@ -533,6 +612,75 @@ __global__ void k_tr_embed_bwd(int N, int F, int nemb, const int* __restrict__ z
 __global__ void k_tr_axpy_neg(size_t count, const float* __restrict__ a, float* __restrict__ out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < count) out[idx] = -a[idx];
+}
+
+// ---- Ziegler-Biersack-Littmark repulsion (observable.py:110-183): energy and the gradients of its ten scalars ------------
+// The ten raw scalars (softplus at use) enter through a second level of forward mode: D2<T> = (value, d / d theta_k) over T
+// (T itself float, or Dual in the position direction), one evaluation of the pair energy per scalar k.  The tangent part,
+// times the read-out seed, is d(seed E_rep)/d theta_k -- with T = Dual its tangent component is the mixed second derivative
+// the loss gradient needs.
+template <class T> struct D2 { T p, t; };
+template <class T> SO3K_HD inline D2<T> mk2(T p, T t) { D2<T> r; r.p = p; r.t = t; return r; }
+template <class T> SO3K_HD inline D2<T> operator+(D2<T> a, D2<T> b) { return mk2<T>(a.p + b.p, a.t + b.t); }
+template <class T> SO3K_HD inline D2<T> operator*(D2<T> a, D2<T> b) { return mk2<T>(a.p * b.p, a.p * b.t + a.t * b.p); }
+template <class T> SO3K_HD inline D2<T> operator/(D2<T> a, D2<T> b) { T q = a.p / b.p; return mk2<T>(q, (a.t - q * b.t) / b.p); }
+template <class T> SO3K_HD inline D2<T> scale2(D2<T> a, T s) { return mk2<T>(a.p * s, a.t * s); }
+template <class T> SO3K_HD inline D2<T> d2_exp(D2<T> a) { T e = t_exp(a.p); return mk2<T>(e, e * a.t); }
+template <class T> SO3K_HD inline D2<T> neg2(D2<T> a) { return mk2<T>(Tr<T>::zero() - a.p, Tr<T>::zero() - a.t); }
+// softplus(raw) of scalar k, seeded when k == which
+template <class T> SO3K_HD inline D2<T> zbl_par(const float* raw, int k, int which) {
+  const float x = raw[k];
+  const float sp = x > 20.f ? x : log1pf(expf(x));
+  const float sg = 1.0f / (1.0f + expf(-x));
+  return mk2<T>(Tr<T>::make(sp, 0.f), Tr<T>::make(k == which ? sg : 0.f, 0.f));
+}
+// sigma(u) = exp(-1 / u) for u > 0, else 0 (observable.py:17-18)
+template <class T> SO3K_HD inline T zbl_sigma_t(T u) { return prim(u) > 0.f ? t_exp(Tr<T>::zero() - 1.0f / u) : Tr<T>::zero(); }
+
+// e_atom[i] += sum_{e in row i} e_pair ; grad[zbl + k] += seed_b(i) * d e_pair / d theta_k.  One warp per receiver row.
+template <class T>
+__global__ void k_tr_zbl(So3kDims D, int N, int Pt, int n_per, const int* __restrict__ rowptr, const int* __restrict__ col,
+                         const int* __restrict__ z, const float* __restrict__ raw, const float* __restrict__ dist,
+                         const float* __restrict__ phi, const float* __restrict__ seed_t, float seed_p,
+                         float* __restrict__ e_atom, float* __restrict__ gzbl) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const float zi = (float)z[i];
+  const int e0 = rowptr[i], e1 = rowptr[i + 1];
+  const int b = i / n_per;
+  const T seed = Tr<T>::planes == 2 ? Tr<T>::make(seed_p, seed_t ? seed_t[b] : 0.f) : Tr<T>::make(seed_t ? seed_t[b] : seed_p, 0.f);
+  T esum = Tr<T>::zero();
+  float gk[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) gk[k] = 0.f;
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const float zj = (float)z[col[e]];
+    const T d = Tr<T>::ld(dist, e, (size_t)Pt), ph = Tr<T>::ld(phi, e, (size_t)Pt);
+    if (!(prim(d) > 0.f && zi > 0.f && zj > 0.f)) continue;
+    const T cc = d * (1.0f / 1.5f);
+    const T sa = zbl_sigma_t<T>(1.0f - cc), sb = zbl_sigma_t<T>(cc);
+    const T pre = (0.5f * 14.399645351950548f * zi * zj) * (sa / (sa + sb)) * ph / d;
+    const float lzi = logf(zi), lzj = logf(zj);
+    for (int which = -1; which < 10; ++which) {         // which = -1: the energy itself ; 0..9: d / d theta_which
+      D2<T> a[4], c[4];
+      for (int k = 0; k < 4; ++k) { a[k] = zbl_par<T>(raw, k, which); c[k] = zbl_par<T>(raw, 4 + k, which); }
+      const D2<T> csum = c[0] + c[1] + c[2] + c[3];
+      const D2<T> pw = zbl_par<T>(raw, 8, which), dd = zbl_par<T>(raw, 9, which);
+      // s = (z_i^p + z_j^p) d_par ; y = sum_k (c_k / csum) exp(-a_k s d)
+      const D2<T> s = (d2_exp<T>(scale2<T>(pw, Tr<T>::make(lzi, 0.f))) + d2_exp<T>(scale2<T>(pw, Tr<T>::make(lzj, 0.f)))) * dd;
+      D2<T> y = mk2<T>(Tr<T>::zero(), Tr<T>::zero());
+      for (int k = 0; k < 4; ++k) y = y + (c[k] / csum) * d2_exp<T>(neg2<T>(scale2<T>(a[k] * s, d)));
+      if (which < 0) esum += pre * y.p;
+      else gk[which] += gout(seed * (pre * y.t));
+    }
+  }
+  esum = warp_sum(esum);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const float v = warp_sum(gk[k]);
+    if (lane == 0 && v != 0.f) atomicAdd(&gzbl[k], v);
+  }
+  if (lane == 0) Tr<T>::st(e_atom, i, (size_t)N, Tr<T>::ld(e_atom, i, (size_t)N) + esum);
 }
 
 // ---- dense contractions (plain fp32 over the stacked planes) -------------------------------------------------------
@@ -821,7 +969,7 @@ struct TrainWs {
   Graph g;
   int* scratch;
   float *Rdot;
-  float *phi, *Y, *rbf;                        // geometry (T planes)
+  float *phi, *Y, *rbf, *dist;                 // geometry (T planes)
   float *x, *chi;                              // (L+1) states
   float *gl;                                   // per layer (Pt, nl)
   float *A1[2], *As[2], *w[2];                 // per layer and block
@@ -832,10 +980,14 @@ struct TrainWs {
   float *H, *Hs, *cat, *abbar, *catbar;
   float *xbar, *chibar, *x1bar, *chi1bar, *sbar, *wbar, *projbar, *gbar, *hsbar;
   float *part, *dense;                         // weight-gradient partial sums (TN_PARTS x C x C), dense (F, F) product
+  // optional node-level branches (SO3K_OPT_*; null when absent), per layer: LayerNorm-1 output, states between the
+  // blocks, ResidualMLP intermediates (a1 = silu(x) W0, r = x + silu(a1) W1) ; temporaries
+  float *xn1, *x1b, *x2a, *x2b, *ra1[2], *rr[2];
+  float *tA, *tB, *tC, *xnbar;
   size_t bytes;
 };
 
-TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base) {
+TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base, int opts = 0) {
   TrainWs w;
   char* p = (char*)base;
   auto take = [&](size_t bytes) { char* r = p; p += a256(bytes); return (void*)r; };
@@ -857,6 +1009,7 @@ TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base) {
   w.phi = (float*)take(fl * pl * Pe);
   w.Y = (float*)take(fl * pl * Pe * M);
   w.rbf = (float*)take(fl * pl * Pe * K);
+  w.dist = (float*)take(fl * pl * Pe);
   w.x = (float*)take(fl * pl * (L + 1) * N * F);
   w.chi = (float*)take(fl * pl * (L + 1) * N * M);
   w.gl = (float*)take(fl * pl * L * Pe * nl);
@@ -889,6 +1042,19 @@ TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base) {
   w.hsbar = (float*)take(fl * pl * Pe * Fs);
   w.part = (float*)take(fl * (size_t)TN_PARTS * C * C);
   w.dense = (float*)take(fl * F * F);
+  const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST), res1 = opts & SO3K_OPT_RES1, res2 = opts & SO3K_OPT_RES2;
+  auto layer_nf = [&](bool on) { return on ? (float*)take(fl * pl * L * N * F) : (float*)nullptr; };
+  w.xn1 = layer_nf(ln);
+  w.x1b = layer_nf(res1);
+  w.x2a = layer_nf(res2);
+  w.x2b = layer_nf(post);
+  w.ra1[0] = layer_nf(res1); w.rr[0] = layer_nf(res1);
+  w.ra1[1] = layer_nf(res2); w.rr[1] = layer_nf(res2);
+  const bool any = opts != 0;
+  w.tA = any ? (float*)take(fl * pl * N * F) : nullptr;
+  w.tB = any ? (float*)take(fl * pl * N * F) : nullptr;
+  w.tC = any ? (float*)take(fl * pl * N * F) : nullptr;
+  w.xnbar = any ? (float*)take(fl * pl * N * F) : nullptr;
   w.bytes = (size_t)(p - (char*)base);
   return w;
 }
@@ -943,7 +1109,9 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
   const size_t F = D.F, M = D.M, nl = D.nl, K = D.K, Fs = D.Fs, A = D.H + D.nl, C = D.F + D.nl;
   const size_t Pe = Pt > 0 ? Pt : 1;
   const float* prm = h->params;
-  TrainWs w = carve_train(D, N, Pt, pl, workspace);
+  const int opts = ml.node_opts;
+  const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST), res1 = opts & SO3K_OPT_RES1, res2 = opts & SO3K_OPT_RES2;
+  TrainWs w = carve_train(D, N, Pt, pl, workspace, opts);
   cudaMemsetAsync(grad, 0, sizeof(float) * ml.total, st);
   so3k_build_graph(D, B, n, P, R, idx_i, idx_j, cell, cell_offset, nullptr, nullptr, w.g, w.scratch, dev_status, st);
   const Graph& g = w.g;
@@ -955,7 +1123,7 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
     Rdot = w.Rdot;
   }
   SO3K_LAUNCH(k_tr_geom<T>, g1(Pe), dim3(TB), 0, st, D, N, Pt, P, g.rowptr, g.row, g.col, g.src, R, Rdot, cell,
-              cell_offset, w.phi, w.Y, w.rbf);
+              cell_offset, w.phi, w.Y, w.rbf, w.dist);
   // x0, chi0
   const size_t sx = (size_t)pl * N * F, sc = (size_t)pl * N * M;       // per-state strides
   cudaMemsetAsync(w.x, 0, sizeof(float) * sx, st);
@@ -963,7 +1131,40 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
   SO3K_LAUNCH(k_tr_embed, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.nemb, z, prm + ml.embed, w.x, dev_status);
 
   const int rowsE = pl * (int)Pe, rowsN = pl * N;
+  const size_t NF = (size_t)N * F;
   auto Lp = [&](float* base, size_t per, int t) { return base + (size_t)t * pl * per; };
+  // ResidualMLP (mlp.py:30-72, bias-free): y = silu(x + silu(silu(x) W0) W1) W2 ; keeps a1 = silu(x) W0 and r = x + silu(a1) W1
+  auto resmlp_fwd = [&](const size_t* Wk, const float* x, float* a1, float* rr, float* y) {
+    SO3K_LAUNCH(k_tr_silu<T>, g1(NF), dim3(TB), 0, st, NF, x, w.tA);
+    gemm_nn(rowsN, (int)F, (int)F, w.tA, prm + Wk[0], nullptr, 0, 0, a1, st);
+    SO3K_LAUNCH(k_tr_silu<T>, g1(NF), dim3(TB), 0, st, NF, a1, w.tA);
+    gemm_nn(rowsN, (int)F, (int)F, w.tA, prm + Wk[1], nullptr, 0, 0, w.tB, st);
+    SO3K_LAUNCH(k_tr_add<T>, g1(NF * pl), dim3(TB), 0, st, NF, x, w.tB, rr);
+    SO3K_LAUNCH(k_tr_silu<T>, g1(NF), dim3(TB), 0, st, NF, rr, w.tA);
+    gemm_nn(rowsN, (int)F, (int)F, w.tA, prm + Wk[2], nullptr, 0, 0, y, st);
+  };
+  // reverse: xbar <- dResidualMLP(x)^T ybar (in place on `bar`), weight gradients into the blob
+  auto resmlp_bwd = [&](const size_t* Wk, const float* x, const float* a1, const float* rr, float* bar) {
+    SO3K_LAUNCH(k_tr_silu<T>, g1(NF), dim3(TB), 0, st, NF, rr, w.tA);                       // h2
+    gemm_tn(N, pl, (int)F, (int)F, w.tA, (int)F, bar, (int)F, grad + Wk[2], w.part, st);
+    gemm_nt(rowsN, (int)F, (int)F, bar, prm + Wk[2], w.tB, st);                              // h2bar
+    SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(NF), dim3(TB), 0, st, NF, rr, w.tB);                   // rbar
+    SO3K_LAUNCH(k_tr_silu<T>, g1(NF), dim3(TB), 0, st, NF, a1, w.tA);                       // h1
+    gemm_tn(N, pl, (int)F, (int)F, w.tA, (int)F, w.tB, (int)F, grad + Wk[1], w.part, st);
+    gemm_nt(rowsN, (int)F, (int)F, w.tB, prm + Wk[1], w.tC, st);                             // h1bar
+    SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(NF), dim3(TB), 0, st, NF, a1, w.tC);                   // a1bar
+    SO3K_LAUNCH(k_tr_silu<T>, g1(NF), dim3(TB), 0, st, NF, x, w.tA);                        // h0
+    gemm_tn(N, pl, (int)F, (int)F, w.tA, (int)F, w.tC, (int)F, grad + Wk[0], w.part, st);
+    gemm_nt(rowsN, (int)F, (int)F, w.tC, prm + Wk[0], w.tA, st);                             // h0bar
+    SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(NF), dim3(TB), 0, st, NF, x, w.tA);                    // h0bar silu'(x)
+    SO3K_LAUNCH(k_tr_add<T>, g1(NF * pl), dim3(TB), 0, st, NF, w.tB, w.tA, bar);            // xbar = rbar + ...
+  };
+  // reverse of LayerNorm k of layer t: out = (add ? add : 0) + dLN(x)^T ybar, scale / bias gradients into the blob
+  auto ln_bwd = [&](const LayerParams& lp, int k, const float* x, const float* ybar, const float* add, float* out) {
+    colsum(N, (int)F, pl, ybar, grad + lp.ln_b[k], st);
+    SO3K_LAUNCH(k_tr_layernorm_bwd<T>, gw(N), dim3(TB), 0, st, N, (int)F, x, prm + lp.ln_s[k], ybar, add, out, w.tC);
+    colsum(N, (int)F, pl, w.tC, grad + lp.ln_s[k], st);
+  };
   for (int t = 0; t < D.L; ++t) {
     const LayerParams& lp = ml.layers[t];
     float* xt = w.x + t * sx; float* ct = w.chi + t * sc;
@@ -979,21 +1180,41 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
                   As, w.Hs);
       gemm_nn(rowsE, (int)F, (int)Fs, w.Hs, prm + bp.sph_W2, prm + bp.sph_b2, (int)Pe, 1, wf, st);
     }
-    float* pj = Lp(w.proj, 5 * (size_t)N * F, t);
-    float* q = pj, *k = pj + pl * N * F, *v = pj + 2 * pl * N * F, *qg = pj + 3 * pl * N * F, *kg = pj + 4 * pl * N * F;
-    SO3K_LAUNCH(k_tr_headproj<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.dh, xt, prm + lp.fb.Wq, q);
-    SO3K_LAUNCH(k_tr_headproj<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.dh, xt, prm + lp.fb.Wk, k);
-    SO3K_LAUNCH(k_tr_headproj<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.dh, xt, prm + lp.fb.Wv, v);
-    SO3K_LAUNCH(k_tr_headproj<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.dg, xt, prm + lp.gb.Wq, qg);
-    SO3K_LAUNCH(k_tr_headproj<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.dg, xt, prm + lp.gb.Wk, kg);
+    // the projections read LayerNorm 1 of x_t (so3krates_layer.py:103-106); the skip connection keeps x_t (:146)
+    const float* xin = xt;
+    if (ln) {
+      float* xn1 = Lp(w.xn1, NF, t);
+      SO3K_LAUNCH(k_tr_layernorm<T>, gw(N), dim3(TB), 0, st, N, (int)F, xt, prm + lp.ln_s[0], prm + lp.ln_b[0], xn1);
+      xin = xn1;
+    }
+    float* pj = Lp(w.proj, 5 * NF, t);
+    float* q = pj, *k = pj + pl * NF, *v = pj + 2 * pl * NF, *qg = pj + 3 * pl * NF, *kg = pj + 4 * pl * NF;
+    SO3K_LAUNCH(k_tr_headproj<T>, g1(NF), dim3(TB), 0, st, N, (int)F, D.dh, xin, prm + lp.fb.Wq, q);
+    SO3K_LAUNCH(k_tr_headproj<T>, g1(NF), dim3(TB), 0, st, N, (int)F, D.dh, xin, prm + lp.fb.Wk, k);
+    SO3K_LAUNCH(k_tr_headproj<T>, g1(NF), dim3(TB), 0, st, N, (int)F, D.dh, xin, prm + lp.fb.Wv, v);
+    SO3K_LAUNCH(k_tr_headproj<T>, g1(NF), dim3(TB), 0, st, N, (int)F, D.dg, xin, prm + lp.gb.Wq, qg);
+    SO3K_LAUNCH(k_tr_headproj<T>, g1(NF), dim3(TB), 0, st, N, (int)F, D.dg, xin, prm + lp.gb.Wk, kg);
     float* al = Lp(w.alpha, Pe * A, t);
     SO3K_LAUNCH(k_tr_alpha<T>, gw(Pe), dim3(TB), 0, st, D, N, Pt, g.rowptr, g.row, g.col, q, k, qg, kg,
                 Lp(w.w[0], Pe * F, t), Lp(w.w[1], Pe * F, t), w.phi, al);
-    float* x1 = Lp(w.x1, (size_t)N * F, t); float* c1 = Lp(w.chi1, (size_t)N * M, t); float* ab = Lp(w.ab, (size_t)N * C, t);
-    SO3K_LAUNCH(k_tr_aggregate<T>, gw(N), dim3(TB), 0, st, D, N, Pt, g.rowptr, g.col, xt, ct, v, al, w.Y, x1, c1);
-    SO3K_LAUNCH(k_tr_intpre<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, x1, c1, w.cat);
+    // states between the blocks; each aliases its successor when the branch is absent
+    float* x1a = Lp(w.x1, NF, t);                                     // x + x_local
+    float* x1b = res1 ? Lp(w.x1b, NF, t) : x1a;                       // first skip state
+    float* x2b = post ? Lp(w.x2b, NF, t) : xt + sx;                   // layer output before the post LayerNorm
+    float* x2a = res2 ? Lp(w.x2a, NF, t) : x2b;                       // second skip state before ResidualMLP 2
+    float* c1 = Lp(w.chi1, (size_t)N * M, t); float* ab = Lp(w.ab, (size_t)N * C, t);
+    SO3K_LAUNCH(k_tr_aggregate<T>, gw(N), dim3(TB), 0, st, D, N, Pt, g.rowptr, g.col, xt, ct, v, al, w.Y, x1a, c1);
+    if (res1) resmlp_fwd(lp.res[0], x1a, Lp(w.ra1[0], NF, t), Lp(w.rr[0], NF, t), x1b);
+    const float* xi2 = x1b;
+    if (ln) {
+      SO3K_LAUNCH(k_tr_layernorm<T>, gw(N), dim3(TB), 0, st, N, (int)F, x1b, prm + lp.ln_s[1], prm + lp.ln_b[1], w.xnbar);
+      xi2 = w.xnbar;
+    }
+    SO3K_LAUNCH(k_tr_intpre<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, xi2, c1, w.cat);
     gemm_nn(rowsN, (int)C, (int)C, w.cat, prm + lp.int_W, prm + lp.int_b, N, 0, ab, st);
-    SO3K_LAUNCH(k_tr_intpost<T>, g1((size_t)N * (F + M)), dim3(TB), 0, st, D, N, x1, c1, ab, xt + sx, ct + sc);
+    SO3K_LAUNCH(k_tr_intpost<T>, g1((size_t)N * (F + M)), dim3(TB), 0, st, D, N, x1b, c1, ab, x2a, ct + sc);
+    if (res2) resmlp_fwd(lp.res[1], x2a, Lp(w.ra1[1], NF, t), Lp(w.rr[1], NF, t), x2b);
+    if (post) SO3K_LAUNCH(k_tr_layernorm<T>, gw(N), dim3(TB), 0, st, N, (int)F, x2b, prm + lp.ln_s[2], prm + lp.ln_b[2], xt + sx);
   }
   // read-out and its reverse
   float* xL = w.x + (size_t)D.L * sx;
@@ -1001,7 +1222,10 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
   SO3K_LAUNCH(k_tr_readout<T>, gw(N), dim3(TB), 0, st, N, (int)F, n, D.nemb, z, w.aout, prm + ml.out_W2, prm + ml.out_b2,
               prm + ml.scale, prm + ml.shift, E_bar, 1.0f, w.e_atom, w.x1bar /* abar */, w.cat /* hs (N,F) fits in (N,C) */,
               w.ebar);
-  if (E_out) SO3K_LAUNCH(k_tr_energy_sum, g1(B), dim3(TB), 0, st, B, n, w.e_atom, E_out);
+  if (ml.has_zbl)       // Energy(zbl_repulsion=True): pair repulsion added to the atoms' energies, gradients of its ten scalars
+    SO3K_LAUNCH(k_tr_zbl<T>, gw(N), dim3(TB), 0, st, D, N, Pt, n, g.rowptr, g.col, z, prm + ml.zbl, w.dist, w.phi, E_bar, 1.0f,
+                w.e_atom, grad + ml.zbl);
+  if (E_out) SO3K_LAUNCH(k_tr_energy_sum, g1(B), dim3(TB), 0, st, B, n, w.e_atom, ml.has_zbl ? h->cfg.zbl_shift : 0.f, E_out);
   colsum(N, (int)F, pl, w.cat, grad + ml.out_W2, st);
   colsum(N, 1, pl, w.ebar, grad + ml.out_b2, st);
   float* abar = w.x1bar;
@@ -1013,21 +1237,35 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
   for (int t = D.L - 1; t >= 0; --t) {
     const LayerParams& lp = ml.layers[t];
     float* xt = w.x + t * sx; float* ct = w.chi + t * sc;
-    float* x1 = Lp(w.x1, (size_t)N * F, t); float* c1 = Lp(w.chi1, (size_t)N * M, t); float* ab = Lp(w.ab, (size_t)N * C, t);
+    float* x1a = Lp(w.x1, NF, t);
+    float* x1b = res1 ? Lp(w.x1b, NF, t) : x1a;
+    float* x2b = post ? Lp(w.x2b, NF, t) : xt + sx;
+    float* x2a = res2 ? Lp(w.x2a, NF, t) : x2b;
+    float* c1 = Lp(w.chi1, (size_t)N * M, t); float* ab = Lp(w.ab, (size_t)N * C, t);
     float* al = Lp(w.alpha, Pe * A, t);
     float* gl = Lp(w.gl, Pe * nl, t);
-    float* pj = Lp(w.proj, 5 * (size_t)N * F, t);
-    const size_t pn = (size_t)pl * N * F;
+    float* pj = Lp(w.proj, 5 * NF, t);
+    const size_t pn = (size_t)pl * NF;
     float* proj[5] = {pj, pj + pn, pj + 2 * pn, pj + 3 * pn, pj + 4 * pn};          // q k v qg kg
     float* pbar[5] = {w.projbar, w.projbar + pn, w.projbar + 2 * pn, w.projbar + 3 * pn, w.projbar + 4 * pn};
-    // interaction block
+    // the optional branches above the interaction block, last to first (in place on xbar)
+    if (post) ln_bwd(lp, 2, x2b, w.xbar, nullptr, w.xbar);
+    if (res2) resmlp_bwd(lp.res[1], x2a, Lp(w.ra1[1], NF, t), Lp(w.rr[1], NF, t), w.xbar);
+    // interaction block (its x input: LayerNorm 2 of the first skip state when LayerNorm is on)
+    const float* xi2 = x1b;
+    if (ln) {
+      SO3K_LAUNCH(k_tr_layernorm<T>, gw(N), dim3(TB), 0, st, N, (int)F, x1b, prm + lp.ln_s[1], prm + lp.ln_b[1], w.tA);
+      xi2 = w.tA;
+    }
     SO3K_LAUNCH(k_tr_intpost_bwd<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, c1, w.xbar, w.chibar, w.abbar);
-    SO3K_LAUNCH(k_tr_intpre<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, x1, c1, w.cat);
+    SO3K_LAUNCH(k_tr_intpre<T>, g1((size_t)N * C), dim3(TB), 0, st, D, N, xi2, c1, w.cat);
     gemm_tn(N, pl, (int)C, (int)C, w.cat, (int)C, w.abbar, (int)C, grad + lp.int_W, w.part, st);
     colsum(N, (int)C, pl, w.abbar, grad + lp.int_b, st);
     gemm_nt(rowsN, (int)C, (int)C, w.abbar, prm + lp.int_W, w.catbar, st);
     SO3K_LAUNCH(k_tr_intpre_bwd<T>, g1((size_t)N * (F + M)), dim3(TB), 0, st, D, N, c1, ab, w.xbar, w.chibar, w.catbar,
-                w.x1bar, w.chi1bar);
+                w.x1bar, w.chi1bar, ln ? w.xnbar : (float*)nullptr);
+    if (ln) ln_bwd(lp, 1, x1b, w.xnbar, w.x1bar, w.x1bar);           // + the skip connection already in x1bar
+    if (res1) resmlp_bwd(lp.res[0], x1a, Lp(w.ra1[0], NF, t), Lp(w.rr[0], NF, t), w.x1bar);
     // attention + aggregation
     SO3K_LAUNCH(k_tr_alpha_bwd<T>, gw(Pe), dim3(TB), 0, st, D, N, Pt, g.rowptr, g.row, g.col, w.x1bar, w.chi1bar, proj[2],
                 w.Y, w.phi, w.sbar);
@@ -1057,33 +1295,31 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
       colsum((int)Pe, (int)Fs, pl, w.hsbar, grad + bp.sph_b1, st);
       SO3K_LAUNCH(k_tr_sph1_bwd<T>, g1(Pe * nl), dim3(TB), 0, st, Pt, (int)nl, (int)Fs, b, w.hsbar, prm + bp.sph_W1, w.gbar);
     }
-    // cotangent of (x_t, chi_t): skip connections + projections + chi differences
-    cudaMemcpyAsync(w.xbar, w.x1bar, sizeof(float) * sx, cudaMemcpyDeviceToDevice, st);
+    // cotangent of (x_t, chi_t): skip connection + projections (through LayerNorm 1 when it is on) + chi differences
+    const float* xin = ln ? Lp(w.xn1, NF, t) : xt;                   // what the projections read
     const float* Wp[5] = {prm + lp.fb.Wq, prm + lp.fb.Wk, prm + lp.fb.Wv, prm + lp.gb.Wq, prm + lp.gb.Wk};
     float* Gp[5] = {grad + lp.fb.Wq, grad + lp.fb.Wk, grad + lp.fb.Wv, grad + lp.gb.Wq, grad + lp.gb.Wk};
+    float* pxbar = w.xbar;                                           // receives the projections' x cotangent
+    if (ln) {
+      pxbar = w.xnbar;
+      cudaMemsetAsync(w.xnbar, 0, sizeof(float) * sx, st);
+    } else {
+      cudaMemcpyAsync(w.xbar, w.x1bar, sizeof(float) * sx, cudaMemcpyDeviceToDevice, st);
+    }
     for (int k5 = 0; k5 < 5; ++k5) {
       const int d = k5 < 3 ? D.dh : D.dg;
       const int heads = (int)F / d;
       cudaMemsetAsync(w.dense, 0, sizeof(float) * F * F, st);
-      gemm_tn(N, pl, (int)F, (int)F, xt, (int)F, pbar[k5], (int)F, w.dense, w.part, st);
+      gemm_tn(N, pl, (int)F, (int)F, xin, (int)F, pbar[k5], (int)F, w.dense, w.part, st);
       SO3K_LAUNCH(k_tr_extract_heads, g1((size_t)heads * d * d), dim3(TB), 0, st, (int)F, d, w.dense, Gp[k5]);
-      if (t > 0)
-        SO3K_LAUNCH(k_tr_headproj_bwd_x<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, d, pbar[k5], Wp[k5], w.xbar);
+      SO3K_LAUNCH(k_tr_headproj_bwd_x<T>, g1(NF), dim3(TB), 0, st, N, (int)F, d, pbar[k5], Wp[k5], pxbar);
     }
+    if (ln) ln_bwd(lp, 0, xt, w.xnbar, w.x1bar, w.xbar);             // xbar = x1bar (skip) + dLN1^T (projections' cotangent)
     if (t > 0)
       SO3K_LAUNCH(k_tr_gdiff_bwd<T>, gw(N), dim3(TB), 0, st, D, N, Pt, g.rowptr, g.col, g.rev, ct, w.gbar, w.chi1bar, w.chibar);
   }
-  // x0 = Embed[z]: the cotangent of x0 is x1bar of layer 0 plus the projections' share
-  {
-    const LayerParams& lp = ml.layers[0];
-    const size_t pn = (size_t)pl * N * F;
-    float* pbar[5] = {w.projbar, w.projbar + pn, w.projbar + 2 * pn, w.projbar + 3 * pn, w.projbar + 4 * pn};
-    const float* Wp[5] = {prm + lp.fb.Wq, prm + lp.fb.Wk, prm + lp.fb.Wv, prm + lp.gb.Wq, prm + lp.gb.Wk};
-    for (int k5 = 0; k5 < 5; ++k5)
-      SO3K_LAUNCH(k_tr_headproj_bwd_x<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, k5 < 3 ? D.dh : D.dg, pbar[k5],
-                  Wp[k5], w.xbar);
-    SO3K_LAUNCH(k_tr_embed_bwd<T>, g1((size_t)N * F), dim3(TB), 0, st, N, (int)F, D.nemb, z, w.xbar, grad + ml.embed);
-  }
+  // x0 = Embed[z]: xbar now holds the cotangent of x0
+  SO3K_LAUNCH(k_tr_embed_bwd<T>, g1(NF), dim3(TB), 0, st, N, (int)F, D.nemb, z, w.xbar, grad + ml.embed);
   return SO3K_OK;
 }
 
@@ -1093,7 +1329,7 @@ extern "C" {
 
 size_t so3k_train_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total) {
   if (!h || n_atoms_total < 0 || n_edge_slots_total < 0) return 0;
-  return carve_train(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, 2, nullptr).bytes + 256;
+  return carve_train(h->dims, (int)n_atoms_total, (int)n_edge_slots_total, 2, nullptr, h->layout.node_opts).bytes + 256;
 }
 
 int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P, const float* R, const int32_t* z,
@@ -1102,7 +1338,6 @@ int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P, cons
                            size_t workspace_bytes, int32_t* dev_status, void* stream) {
   if (!h || !R || !z || !idx_i || !idx_j || !grad || !workspace || B <= 0 || n <= 0 || P < 0) return SO3K_ERR_ARG;
   if (!h->have_params) return SO3K_ERR_NOPARAMS;
-  if (h->layout.node_opts != 0 || h->layout.has_zbl) return SO3K_ERR_CONFIG;     // default model only
   if ((cell == nullptr) != (cell_offset == nullptr)) return SO3K_ERR_ARG;
   if (workspace_bytes < so3k_train_workspace_bytes(h, (int64_t)B * n, (int64_t)B * P)) return SO3K_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;

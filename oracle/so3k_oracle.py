@@ -547,7 +547,7 @@ def loss_and_param_grads(cfg, params, R, z, idx_i, idx_j, E_true, F_true, w_ener
     for b in range(len(R)):
         R_t = torch.as_tensor(np.asarray(R[b]), dtype=dtype).clone().requires_grad_(True)
         e = forward(cfg, pt, z[b], idx_i[b], idx_j[b], dtype, R=R_t)
-        E = e.sum()
+        E = e.sum() - (cfg.zbl_repulsion_shift if cfg.zbl_repulsion else 0.0)    # per_structure: observable.py:84, :91
         (g,) = torch.autograd.grad(E, R_t, create_graph=True)
         Es.append(E)
         Fs.append(-g)

@@ -150,6 +150,43 @@ def test_loss_gradient_matches_oracle(case):
     _compare_blob(eng, grad, og, _trainable(p), 5e-5)
 
 
+OPT_SETS = {'ln+post': dict(layer_normalization=True, final_layer=True),
+            'res1+res2': dict(residual_mlp_1=True, residual_mlp_2=True),
+            'all+zbl': dict(layer_normalization=True, final_layer=True, residual_mlp_1=True, residual_mlp_2=True,
+                            zbl_repulsion=True, zbl_repulsion_shift=0.2)}
+
+
+@pytest.mark.parametrize('name', list(OPT_SETS))
+def test_loss_gradient_with_optional_branches(name):
+    """LayerNorm (pre / post), both ResidualMLPs and the ZBL repulsion (its ten scalars included) in the training sweep:
+    so3krates_layer.py:103-106, 149-174, mlp.py:30-72, observable.py:110-183 -- every parameter of every model variant the
+    inference path supports has a gradient."""
+    from common import engine_flags
+    cfg = o.OracleConfig(**SMALL, **OPT_SETS[name])
+    p = o.init_params(cfg, 3, embed_scale=4.0, scale_shift=True, readout_gain=0.2 if 'ln' in name or 'all' in name else 1.0)
+    R, z, ii, jj, E_true, F_true = _batch()
+    eng = EmuEngine(cfg.F, cfg.n_rbf, cfg.n_layers, cfg.n_heads, cfg.degrees, cfg.r_cut, flags=engine_flags(cfg),
+                    zbl_shift=cfg.zbl_repulsion_shift)
+    eng.load(p)
+    lib = eng.lib
+    loss, og, E, F = o.loss_and_param_grads(cfg, p, R, z, ii, jj, E_true, F_true, 0.01, 0.99)
+    if cfg.zbl_repulsion:
+        assert max(np.abs(og['zbl/' + k]).max() for k in ('a1', 'c2', 'p', 'd')) > 1e-4       # the fixture exercises them
+    B, n = z.shape
+    Ee, Fe, _, st = eng.energy_forces(R, z, ii, jj)
+    assert st == 0
+    zi = np.ascontiguousarray(z, np.int32)
+    Et, Ft = np.ascontiguousarray(E_true.reshape(-1), np.float32), np.ascontiguousarray(F_true, np.float32)
+    sums, ls = np.zeros(4, np.float64), np.zeros(3, np.float32)
+    Eb, Fb = np.zeros(B, np.float32), np.zeros((B, n, 3), np.float32)
+    lib.loss_sums(B, n, ptr(Ee), ptr(Fe), ptr(Et), ptr(Ft), ptr(zi), ptr(sums))
+    lib.loss_cotangents(B, n, ptr(Ee), ptr(Fe), ptr(Et), ptr(Ft), ptr(zi), ptr(sums), 0.01, 0.99, ptr(Eb), ptr(Fb), ptr(ls))
+    assert abs(ls[0] - loss) <= 2e-5 * abs(loss)
+    grad, Esw = _vjp(eng, R, z, ii, jj, Eb, Fb)
+    np.testing.assert_allclose(Esw, E.numpy().reshape(-1), rtol=2e-6)            # incl. the per-structure ZBL shift
+    _compare_blob(eng, grad, og, _trainable(p), 5e-5)
+
+
 def test_loss_gradient_periodic_cell_offsets():
     sol = golden('solid_0.npz')
     pos, cell = sol['R'][:24].astype(np.float64), sol['unit_cell'].astype(np.float64)

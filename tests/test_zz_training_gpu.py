@@ -127,17 +127,23 @@ def test_graph_replayed_training_step_equals_the_eager_one():
     assert out[False][0][-1] < out[False][0][0]
 
 
-def test_vjp_refuses_optional_branches():
+def test_loss_gradient_with_all_optional_branches_on_device():
+    """LayerNorm (pre / post) + both ResidualMLPs + ZBL at the default width: every parameter, the ten ZBL scalars included."""
     from mlff_b200.config import So3kratesConfig
-    from mlff_b200.capi import So3kError
-    from mlff_b200 import params as P
-    from mlff_b200.engine import So3kEngine
-    cfg = So3kratesConfig(F=32, n_layer=1, degrees=(1, 2), n_heads=2, layer_normalization=True)
-    eng = So3kEngine(cfg, 'cuda:0', 0).load_params(P.init_params(cfg, 0))
-    g = torch.zeros(eng.lib.param_count(eng.h), device='cuda:0')
-    R = torch.zeros(1, 2, 3, device='cuda:0'); z = torch.ones(1, 2, dtype=torch.int32, device='cuda:0')
-    ii = torch.tensor([[0, 1]], dtype=torch.int32, device='cuda:0'); jj = torch.tensor([[1, 0]], dtype=torch.int32, device='cuda:0')
-    ws = torch.empty(eng.lib.train_workspace_bytes(eng.h, 2, 2) + 1024, dtype=torch.uint8, device='cuda:0')
-    with pytest.raises(So3kError, match='SO3K_ERR_CONFIG'):
-        eng.lib.energy_forces_vjp(eng.h, 1, 2, 2, R.data_ptr(), z.data_ptr(), ii.data_ptr(), jj.data_ptr(), None, None, None,
-                                  None, g.data_ptr(), None, ws.data_ptr(), ws.numel(), None, 0)
+    from mlff_b200.training import Trainer
+    allk = dict(layer_normalization=True, final_layer=True, residual_mlp_1=True, residual_mlp_2=True)
+    _, _, _, R, z, ii, jj, E_true, F_true = _problem()
+    ocfg = o.OracleConfig(F=132, n_layers=2, zbl_repulsion=True, zbl_repulsion_shift=0.3, **allk)
+    p = o.init_params(ocfg, 2, embed_scale=4.0, scale_shift=True, readout_gain=0.2)
+    cfg = So3kratesConfig(F=132, n_layer=2, zbl_repulsion=True, zbl_repulsion_shift=0.3, **allk)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a))
+    lo, og, _, _ = o.loss_and_param_grads(ocfg, p, R, z, ii, jj, E_true, F_true, 0.01, 0.99)
+    for flags in (0, 3):
+        eng = _engine(cfg, p, flags)
+        tr = Trainer(eng, {'energy': 0.01, 'force': 0.99})
+        loss, grad, _, _ = tr.loss_and_grad(t(R), t(z), t(ii), t(jj), t(E_true), t(F_true))
+        torch.cuda.synchronize()
+        assert eng.check_status() == 0
+        assert abs(float(loss[0]) - lo) <= 5e-5 * abs(lo)
+        worst = _check(eng, grad.cpu().numpy(), og, p, 1e-4 if flags == 0 else 5e-4)
+        print(f'all branches + ZBL, flags {flags}: loss {float(loss[0]):.6f} vs {lo:.6f}, worst relative gradient error {worst:.2e}')
