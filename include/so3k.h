@@ -192,13 +192,15 @@ int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
 
 /* ---- training seam: cotangents of (E, F) -> parameter gradients -----------------------------------------------
  * What `jax.value_and_grad(loss_fn)(params, batch)` needs from the model (mlff/training/run.py:34-50, loss.py:42-73 with
- * obs_fn = vmap(get_obs_and_force_fn(net)), observable_function.py:127-149): for cotangents E_bar (B) of the energies
- * and F_bar (B,n,3) of the forces of so3k_energy_forces (same padded inputs),
- *     grad[theta] = sum_b E_bar[b] dE_b/dtheta + sum_(b,i,c) F_bar[b,i,c] dF[b,i,c]/dtheta ,
+ * obs_fn = vmap(get_obs_and_force_fn(net)) or get_energy_force_stress_fn, observable_function.py:127-186): for cotangents
+ * E_bar (B) of the energies, F_bar (B,n,3) of the forces of so3k_energy_forces (same padded inputs) and S_bar (B,3,3) of the
+ * stress of so3k_stress (each may be NULL = zero),
+ *     grad[theta] = sum_b E_bar[b] dE_b/dtheta + sum F_bar dF/dtheta + sum S_bar dstress/dtheta ,
  * a float32 blob in the order of so3k_load_params (overwritten; energy/per_atom_scale, _shift get 0: they are constants
  * of the Energy module, observable.py:49-58).  Because F = -dE/dR this is second order; it is evaluated as the
- * forward-mode derivative along -F_bar of the reverse-mode parameter gradient, in one dual-number sweep (so3k_train.cu).
- * F_bar == NULL selects the first-order sweep (grad = sum_b E_bar[b] dE_b/dtheta; E_bar == NULL means all ones).
+ * forward-mode derivative along -F_bar (positions) and sym(S_bar) (strain: edge vectors move as r -> (1 + eps) r) of the
+ * reverse-mode parameter gradient, in one dual-number sweep (so3k_train.cu).
+ * F_bar == NULL and S_bar == NULL select the first-order sweep (grad = sum_b E_bar[b] dE_b/dtheta; E_bar == NULL means all ones).
  * E_out (B) or NULL receives the energies of the sweep.  Every model variant of so3k_config.flags is covered: the optional
  * LayerNorms and ResidualMLPs and the ten ZBL scalars have their gradients in the blob too.  Arithmetic is fp32 on the CUDA
  * cores in either filter mode. */
@@ -206,7 +208,7 @@ size_t so3k_train_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, i
 int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P,
                            const float* R, const int32_t* z, const int32_t* idx_i, const int32_t* idx_j,
                            const float* cell, const int32_t* cell_offset,
-                           const float* E_bar, const float* F_bar, float* grad, float* E_out,
+                           const float* E_bar, const float* F_bar, const float* S_bar, float* grad, float* E_out,
                            void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream);
 
 /* Loss of the reference's training CLI (scaled_safe_masked_mse_loss, loss.py:13-29, scale 1; get_loss_fn :42-73):

@@ -111,7 +111,7 @@ class So3kLib:
         d.so3k_profile_collect.restype = C.c_int
         d.so3k_train_workspace_bytes.argtypes = [vp, i64, i64]
         d.so3k_train_workspace_bytes.restype = sz
-        d.so3k_energy_forces_vjp.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]
+        d.so3k_energy_forces_vjp.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp, vp]
         d.so3k_energy_forces_vjp.restype = C.c_int
         d.so3k_loss_sums.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp]
         d.so3k_loss_sums.restype = C.c_int
@@ -192,9 +192,9 @@ class So3kLib:
         return int(self.dll.so3k_train_workspace_bytes(h, n_atoms, n_edge_slots))
 
     def energy_forces_vjp(self, h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, grad, E_out, ws,
-                          ws_bytes, status, stream=0):
-        _check(self.dll.so3k_energy_forces_vjp(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, grad,
-                                               E_out, ws, ws_bytes, status, stream), 'so3k_energy_forces_vjp')
+                          ws_bytes, status, stream=0, S_bar=None):
+        _check(self.dll.so3k_energy_forces_vjp(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, S_bar,
+                                               grad, E_out, ws, ws_bytes, status, stream), 'so3k_energy_forces_vjp')
 
     def loss_sums(self, B, n, E, F, E_true, F_true, z, sums, stream=0):
         _check(self.dll.so3k_loss_sums(B, n, E, F, E_true, F_true, z, sums, stream), 'so3k_loss_sums')

@@ -84,9 +84,9 @@ constexpr int TN_PARTS = 296;     // row chunks of a weight-gradient reduction (
 template <class T>
 __global__ void k_tr_geom(So3kDims D, int N, int Pt, int P, const int* __restrict__ rowptr, const int* __restrict__ row,
                           const int* __restrict__ col, const int* __restrict__ src, const float* __restrict__ R,
-                          const float* __restrict__ Rdot, const float* __restrict__ cell,
-                          const int* __restrict__ cell_offset, float* __restrict__ phi, float* __restrict__ Y,
-                          float* __restrict__ rbf, float* __restrict__ dist) {
+                          const float* __restrict__ Rdot, const float* __restrict__ strain_dot /* (B,3,3) or null */,
+                          const float* __restrict__ cell, const int* __restrict__ cell_offset, float* __restrict__ phi,
+                          float* __restrict__ Y, float* __restrict__ rbf, float* __restrict__ dist) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= Pt) return;
   const size_t ps1 = (size_t)Pt, psM = (size_t)Pt * D.M, psK = (size_t)Pt * D.K;
@@ -107,6 +107,17 @@ __global__ void k_tr_geom(So3kDims D, int N, int Pt, int P, const int* __restric
       rp += (float)o[0] * cb[0 + c] + (float)o[1] * cb[3 + c] + (float)o[2] * cb[6 + c];
     }
     r[c] = Tr<T>::make(rp, Rdot ? Rdot[(size_t)j * 3 + c] - Rdot[(size_t)i * 3 + c] : 0.f);
+  }
+  if (Tr<T>::planes == 2 && strain_dot) {
+    // stress cotangent: positions and cell are strained by the symmetrised eps (observable_function.py:172-174), so the edge
+    // vector moves as r -> (1 + eps_s) r: tangent rdot += sym(Sbar_b) r
+    const float* sb = strain_dot + (size_t)(s / P) * 9;
+    const float rp[3] = {prim(r[0]), prim(r[1]), prim(r[2])};
+    for (int c = 0; c < 3; ++c) {
+      float tdot = 0.f;
+      for (int dd = 0; dd < 3; ++dd) tdot += 0.5f * (sb[3 * c + dd] + sb[3 * dd + c]) * rp[dd];
+      r[c] = r[c] + Tr<T>::make(0.f, tdot);
+    }
   }
   T d = t_sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
   T u[3];
@@ -1101,8 +1112,8 @@ void colsum(int R, int C, int planes, const float* X, float* out, cudaStream_t s
 
 template <class T>
 int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, const int* idx_i, const int* idx_j,
-            const float* cell, const int* cell_offset, const float* E_bar, const float* F_bar, float* grad, float* E_out,
-            void* workspace, int* dev_status, cudaStream_t st) {
+            const float* cell, const int* cell_offset, const float* E_bar, const float* F_bar, const float* S_bar, float* grad,
+            float* E_out, void* workspace, int* dev_status, cudaStream_t st) {
   const So3kDims& D = h->dims;
   const ModelLayout& ml = h->layout;
   const int N = B * n, Pt = B * P, pl = Tr<T>::planes;
@@ -1122,8 +1133,8 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
     if (F_bar) SO3K_LAUNCH(k_tr_axpy_neg, g1((size_t)N * 3), dim3(TB), 0, st, (size_t)N * 3, F_bar, w.Rdot);
     Rdot = w.Rdot;
   }
-  SO3K_LAUNCH(k_tr_geom<T>, g1(Pe), dim3(TB), 0, st, D, N, Pt, P, g.rowptr, g.row, g.col, g.src, R, Rdot, cell,
-              cell_offset, w.phi, w.Y, w.rbf, w.dist);
+  SO3K_LAUNCH(k_tr_geom<T>, g1(Pe), dim3(TB), 0, st, D, N, Pt, P, g.rowptr, g.row, g.col, g.src, R, Rdot, pl == 2 ? S_bar : nullptr,
+              cell, cell_offset, w.phi, w.Y, w.rbf, w.dist);
   // x0, chi0
   const size_t sx = (size_t)pl * N * F, sc = (size_t)pl * N * M;       // per-state strides
   cudaMemsetAsync(w.x, 0, sizeof(float) * sx, st);
@@ -1334,16 +1345,17 @@ size_t so3k_train_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, i
 
 int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P, const float* R, const int32_t* z,
                            const int32_t* idx_i, const int32_t* idx_j, const float* cell, const int32_t* cell_offset,
-                           const float* E_bar, const float* F_bar, float* grad, float* E_out, void* workspace,
-                           size_t workspace_bytes, int32_t* dev_status, void* stream) {
+                           const float* E_bar, const float* F_bar, const float* S_bar, float* grad, float* E_out,
+                           void* workspace, size_t workspace_bytes, int32_t* dev_status, void* stream) {
   if (!h || !R || !z || !idx_i || !idx_j || !grad || !workspace || B <= 0 || n <= 0 || P < 0) return SO3K_ERR_ARG;
   if (!h->have_params) return SO3K_ERR_NOPARAMS;
   if ((cell == nullptr) != (cell_offset == nullptr)) return SO3K_ERR_ARG;
   if (workspace_bytes < so3k_train_workspace_bytes(h, (int64_t)B * n, (int64_t)B * P)) return SO3K_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   void* ws = (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  int rc = F_bar ? run_vjp<Dual>(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, grad, E_out, ws, dev_status, st)
-                 : run_vjp<float>(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, nullptr, grad, E_out, ws, dev_status, st);
+  int rc = (F_bar || S_bar)
+               ? run_vjp<Dual>(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, F_bar, S_bar, grad, E_out, ws, dev_status, st)
+               : run_vjp<float>(h, B, n, P, R, z, idx_i, idx_j, cell, cell_offset, E_bar, nullptr, nullptr, grad, E_out, ws, dev_status, st);
   if (rc != SO3K_OK) return rc;
   return cudaPeekAtLastError() == cudaSuccess ? SO3K_OK : SO3K_ERR_CUDA;
 }

@@ -112,15 +112,16 @@ class Trainer:
                  scales: Optional[Dict[str, float]] = None):
         self.engine = engine
         scales = scales or {}
-        unknown = (set(weights) | set(scales)) - {'energy', 'force'}
+        unknown = (set(weights) | set(scales)) - {'energy', 'force', 'stress'}
         if unknown:
-            raise NotImplementedError(f'loss targets {sorted(unknown)}: only energy and force targets are built')
+            raise NotImplementedError(f'loss targets {sorted(unknown)}: energy, force and stress targets are built')
         self.w_E = float(weights.get('energy', 0.0)) * float(scales.get('energy', 1.0))
         self.w_F = float(weights.get('force', 0.0)) * float(scales.get('force', 1.0))
+        self.w_S = float(weights.get('stress', 0.0)) * float(scales.get('stress', 1.0)) if 'stress' in weights else None
         self.state = TrainState(engine, tx) if tx is not None else None
         self.group = group
         dev = engine.device
-        self._sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._sums = torch.zeros(6, dtype=torch.float64, device=dev)       # E: sum sq, n ; F: sum sq, n ; stress: sum sq, n
         self._loss = torch.zeros(3, dtype=torch.float32, device=dev)
         self._grad = torch.zeros(engine.lib.param_count(engine.h), dtype=torch.float32, device=dev)
         self._ws: Optional[torch.Tensor] = None
@@ -139,9 +140,11 @@ class Trainer:
             self._ws = torch.empty(int(nb) + 1024, dtype=torch.uint8, device=self.engine.device)
         return self._ws
 
-    def loss_and_grad(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None):
+    def loss_and_grad(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None, S_true=None):
         """-> (loss[3] device tensor = (loss, mse_E, mse_F), grad blob, E (B,1), F (B,n,3)); jax.value_and_grad(loss_fn)
-        of run.py:46 for this rank's structures, all-reduced over the group."""
+        of run.py:46 for this rank's structures, all-reduced over the group.  With a 'stress' weight and S_true (B,3,3) the
+        loss gains w_S mse(stress) (get_energy_force_stress_fn, observable_function.py:152-186; masks[pn.stress] all true,
+        NaN labels skipped) and loss becomes (loss, mse_E, mse_F, mse_S)."""
         e = self.engine
         dev = e.device
         R = R.to(dev, torch.float32).contiguous()
@@ -156,10 +159,20 @@ class Trainer:
         B, n = z.shape
         P = idx_i.shape[1]
         lib, h, st = e.lib, e.h, e._stream()
-        E, F, _ = e.energy_forces(R, z, idx_i, idx_j, cell, cell_offset)
+        with_stress = self.w_S is not None and S_true is not None
+        if with_stress:
+            E, F, _, S = e.energy_forces(R, z, idx_i, idx_j, cell, cell_offset, want_stress=True)
+            S_true = S_true.to(dev, torch.float32).contiguous()
+        else:
+            E, F, _ = e.energy_forces(R, z, idx_i, idx_j, cell, cell_offset)
         E1 = E.reshape(-1)
         self._sums.zero_()
         lib.loss_sums(B, n, _p(E1), _p(F), _p(E_true), _p(F_true), _p(z), _p(self._sums), st)
+        if with_stress:
+            ok = ~torch.isnan(S_true)
+            resid = torch.where(ok, S - torch.where(ok, S_true, torch.zeros_like(S_true)), torch.zeros_like(S))
+            self._sums[4] = (resid.double() ** 2).sum()
+            self._sums[5] = ok.sum().double()
         dist = self._dist()
         grp = None if self.group is True else self.group
         if dist is not None:
@@ -168,12 +181,19 @@ class Trainer:
         F_bar = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
         lib.loss_cotangents(B, n, _p(E1), _p(F), _p(E_true), _p(F_true), _p(z), _p(self._sums), self.w_E, self.w_F,
                             _p(E_bar), _p(F_bar), _p(self._loss), st)
+        S_bar = None
+        loss = self._loss
+        if with_stress:
+            nS = self._sums[5].clamp_min(1.0)
+            S_bar = (2.0 * self.w_S * resid.double() / nS).float().contiguous()          # 0 where the label is NaN
+            mse_S = torch.where(self._sums[5] > 0, self._sums[4] / nS, torch.zeros_like(nS)).float()
+            loss = torch.cat([(self._loss[0] + self.w_S * mse_S).reshape(1), self._loss[1:3], mse_S.reshape(1)])
         ws = self._workspace(B * n, B * P)
         lib.energy_forces_vjp(h, B, n, P, _p(R), _p(z), _p(idx_i), _p(idx_j), _p(cell), _p(cell_offset), _p(E_bar),
-                              _p(F_bar), _p(self._grad), None, _p(ws), ws.numel(), _p(e._status), st)
+                              _p(F_bar), _p(self._grad), None, _p(ws), ws.numel(), _p(e._status), st, S_bar=_p(S_bar))
         if dist is not None:
             dist.all_reduce(self._grad, group=grp)
-        return self._loss, self._grad, E, F
+        return loss, self._grad, E, F
 
     def eval_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None):
         """valid_step_fn (run.py:88-104): the loss metrics of a batch without gradients -- one E+F pass and the loss sums
@@ -197,22 +217,28 @@ class Trainer:
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(self._sums, group=None if self.group is True else self.group)
-        s = self._sums.clone()
+        s = self._sums.clone()                                   # (the stress target is evaluated by loss_and_grad only)
         mse_E = torch.where(s[1] > 0, s[0] / s[1].clamp_min(1.0), torch.zeros_like(s[0]))
         mse_F = torch.where(s[3] > 0, s[2] / s[3].clamp_min(1.0), torch.zeros_like(s[2]))
         return {'loss': (self.w_E * mse_E + self.w_F * mse_F).float(), 'energy': mse_E.float(), 'force': mse_F.float()}
 
-    def train_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None, cuda_graph: bool = False):
+    def train_step(self, R, z, idx_i, idx_j, E_true, F_true, cell=None, cell_offset=None, cuda_graph: bool = False,
+                   S_true=None):
         """train_step_fn (run.py:34-50): returns a dict of DEVICE scalars (loss, per-target MSE, gradients_norm); nothing
         is read back to the host here.  cuda_graph=True: the whole step for this batch shape -- E+F pass, loss, dual-number
         sweep, the two all-reduces, Adam, parameter re-load: ~500 short launches -- is captured once and replayed (a
         small-molecule batch is launch-bound, above all when it is split over several ranks)."""
         if cuda_graph:
+            if S_true is not None:
+                raise NotImplementedError('cuda_graph=True with a stress target')
             return self._train_step_graphed(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset)
-        loss, grad, _, _ = self.loss_and_grad(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset)
+        loss, grad, _, _ = self.loss_and_grad(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset, S_true)
         self.state.apply_gradients(grad)
         loss = loss.clone()              # the metrics outlive the next step's buffers
-        return {'loss': loss[0], 'energy': loss[1], 'force': loss[2], 'gradients_norm': self.state.grad_sumsq.sqrt()[0]}
+        out = {'loss': loss[0], 'energy': loss[1], 'force': loss[2], 'gradients_norm': self.state.grad_sumsq.sqrt()[0]}
+        if loss.numel() > 3:
+            out['stress'] = loss[3]
+        return out
 
     def _train_step_graphed(self, R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset):
         dev = self.engine.device

@@ -534,33 +534,49 @@ def scaled_safe_masked_mse_loss(y, y_true, scale, msk):
 
 
 def loss_and_param_grads(cfg, params, R, z, idx_i, idx_j, E_true, F_true, w_energy: float, w_force: float,
-                         dtype=torch.float64, trainable=None):
+                         dtype=torch.float64, trainable=None, cell=None, cell_offset=None, S_true=None, w_stress: float = 0.0):
     """One training step's value_and_grad (mlff/training/run.py:34-50, loss.py:42-73): loss = w_E mse(E) + w_F mse(F)
-    over a padded batch (node_mask = z != 0; energy mask all true), with F = -dE/dR inside the loss -- the parameter
-    gradient therefore differentiates THROUGH the force (second order).  Returns loss, {name: dloss/dparam}, E, F.
-    Energy scale/shift tables and ZBL scalars are constants of the Energy module, not parameters (observable.py:49-58)."""
+    [+ w_S mse(stress)] over a padded batch (node_mask = z != 0; energy / stress masks all true), with F = -dE/dR and
+    stress = dE/d(strain) (get_energy_force_stress_fn, observable_function.py:152-186) inside the loss -- the parameter
+    gradient therefore differentiates THROUGH them (second order).  Returns loss, {name: dloss/dparam}, E, F [, stress when
+    S_true is given].  Energy scale/shift tables are constants of the Energy module, not parameters (observable.py:49-58)."""
     names = [k for k in params if not k.startswith('energy/per_atom_')] if trainable is None else list(trainable)
     pt = {k: torch.as_tensor(np.asarray(v), dtype=dtype).clone() for k, v in params.items()}
     for k in names:
         pt[k].requires_grad_(True)
-    Es, Fs = [], []
+    Es, Fs, Ss = [], [], []
     for b in range(len(R)):
         R_t = torch.as_tensor(np.asarray(R[b]), dtype=dtype).clone().requires_grad_(True)
-        e = forward(cfg, pt, z[b], idx_i[b], idx_j[b], dtype, R=R_t)
+        eps = torch.zeros(3, 3, dtype=dtype, requires_grad=True)
+        eps_s = 0.5 * (eps + eps.T)
+        Rs = R_t + torch.einsum('ij,nj->ni', eps_s, R_t)                     # observable_function.py:172-174
+        cell_t = off_t = None
+        if cell is not None:
+            c0 = torch.as_tensor(np.asarray(cell[b]), dtype=dtype)
+            cell_t = c0 + torch.einsum('ab,Ab->Aa', eps_s, c0)
+            off_t = torch.as_tensor(np.asarray(cell_offset[b]))
+        e = forward(cfg, pt, z[b], idx_i[b], idx_j[b], dtype, R=Rs, cell=cell_t, cell_offset=off_t)
         E = e.sum() - (cfg.zbl_repulsion_shift if cfg.zbl_repulsion else 0.0)    # per_structure: observable.py:84, :91
-        (g,) = torch.autograd.grad(E, R_t, create_graph=True)
+        g, st = torch.autograd.grad(E, (R_t, eps), create_graph=True)
         Es.append(E)
         Fs.append(-g)
+        Ss.append(st)
     E = torch.stack(Es)[:, None]
     F = torch.stack(Fs)
+    S = torch.stack(Ss)
     node_mask = torch.as_tensor(np.asarray(z) != 0)
     one = torch.ones((), dtype=dtype)
     loss = (w_energy * scaled_safe_masked_mse_loss(E, torch.as_tensor(np.asarray(E_true), dtype=dtype).reshape(E.shape), one,
                                                    torch.ones_like(E, dtype=torch.bool))
             + w_force * scaled_safe_masked_mse_loss(F, torch.as_tensor(np.asarray(F_true), dtype=dtype), one,
                                                     node_mask[..., None].expand(F.shape)))
+    if S_true is not None:
+        loss = loss + w_stress * scaled_safe_masked_mse_loss(S, torch.as_tensor(np.asarray(S_true), dtype=dtype), one,
+                                                             torch.ones_like(S, dtype=torch.bool))
     grads = torch.autograd.grad(loss, [pt[k] for k in names], allow_unused=True)
     out = {k: (torch.zeros_like(pt[k]) if g is None else g).detach().numpy() for k, g in zip(names, grads)}
+    if S_true is not None:
+        return float(loss.detach()), out, E.detach(), F.detach(), S.detach()
     return float(loss.detach()), out, E.detach(), F.detach()
 
 

@@ -75,7 +75,7 @@ def _emu(cfg, p):
     return eng
 
 
-def _vjp(eng, R, z, ii, jj, E_bar, F_bar, cell=None, off=None):
+def _vjp(eng, R, z, ii, jj, E_bar, F_bar, cell=None, off=None, S_bar=None):
     lib, h = eng.lib, eng.h
     B, n = z.shape
     P = ii.shape[1]
@@ -88,8 +88,9 @@ def _vjp(eng, R, z, ii, jj, E_bar, F_bar, cell=None, off=None):
     grad, E = np.zeros(lib.param_count(h), np.float32), np.zeros(B, np.float32)
     Eb = None if E_bar is None else np.ascontiguousarray(E_bar, np.float32)
     Fb = None if F_bar is None else np.ascontiguousarray(F_bar, np.float32)
+    Sb = None if S_bar is None else np.ascontiguousarray(S_bar, np.float32)
     lib.energy_forces_vjp(h, B, n, P, ptr(Rf), ptr(zi), ptr(i32), ptr(j32), ptr(cell), ptr(off), ptr(Eb), ptr(Fb),
-                          ptr(grad), ptr(E), ptr(ws), ws.nbytes, ptr(st))
+                          ptr(grad), ptr(E), ptr(ws), ws.nbytes, ptr(st), S_bar=ptr(Sb))
     assert st[0] == 0
     return grad, E
 
@@ -212,6 +213,43 @@ def test_loss_gradient_periodic_cell_offsets():
     _compare_blob(eng, grad, ref, names, 5e-5)
 
 
+def test_loss_gradient_with_stress_target():
+    """Stress in the loss (the CLI's get_energy_force_stress_fn branch, mlff_train_so3krates.py:366-369): the stress cotangent
+    enters the dual-number sweep as a strain direction (edge vectors move as r -> (1 + eps) r).  Periodic cell with several
+    images per pair; one NaN stress label."""
+    sol = golden('solid_0.npz')
+    pos, cell = sol['R'][:24].astype(np.float64), sol['unit_cell'].astype(np.float64)
+    zs = sol['z'][:24].astype(np.int64)
+    si, sj, S = o.primitive_neighbor_list(pos, cell, [True, True, True], 4.0)
+    cfg = o.OracleConfig(F=24, n_rbf=8, degrees=(1, 2), n_heads=2, n_layers=2, r_cut=4.0)
+    p = o.init_params(cfg, 5, embed_scale=4.0)
+    rng = np.random.default_rng(2)
+    E_true, F_true, S_true = rng.normal(size=(1, 1)), rng.normal(size=(1, 24, 3)), rng.normal(size=(1, 3, 3))
+    S_true[0, 1, 2] = np.nan
+    wE, wF, wS = 0.01, 0.6, 0.39
+    loss, og, E, F, St = o.loss_and_param_grads(cfg, p, pos[None], zs[None], si[None], sj[None], E_true, F_true, wE, wF,
+                                                cell=cell[None], cell_offset=S[None], S_true=S_true, w_stress=wS)
+    eng = _emu(cfg, p)
+    # the engine's stress (so3k_stress) is the quantity in the loss
+    Ee, Fe, _, st, Se = eng.energy_forces(pos[None], zs[None], si[None], sj[None], cell[None], S[None], want_stress=True)
+    assert st == 0 and np.abs(Se - St.numpy()).max() <= 2e-5 * np.abs(St.numpy()).max()
+    E_bar = 2 * wE * (E.numpy().reshape(-1) - E_true.reshape(-1))
+    F_bar = 2 * wF * (F.numpy() - F_true) / F_true.size
+    ok = ~np.isnan(S_true)
+    S_bar = np.where(ok, 2 * wS * (St.numpy() - np.where(ok, S_true, 0.0)) / ok.sum(), 0.0)
+    grad, _ = _vjp(eng, pos[None], zs[None], si[None], sj[None], E_bar, F_bar, cell=cell[None], off=S[None], S_bar=S_bar)
+    _compare_blob(eng, grad, og, _trainable(p), 5e-5)
+    # and through the Trainer (stress weight, NaN label masked out of numerator and denominator)
+    from mlff_b200.training import Trainer
+    te = EmuTorchEngine(cfg, p)
+    tr = Trainer(te, {'energy': wE, 'force': wF, 'stress': wS})
+    lt, gt, _, _ = tr.loss_and_grad(*_as_t(pos[None], zs[None], si[None], sj[None], E_true, F_true),
+                                    cell=torch.as_tensor(cell[None]), cell_offset=torch.as_tensor(S[None]),
+                                    S_true=torch.as_tensor(S_true))
+    assert abs(float(lt[0]) - loss) <= 2e-5 * abs(loss) and lt.numel() == 4
+    _compare_blob(eng, gt.numpy(), og, _trainable(p), 5e-5)
+
+
 def test_adam_step_matches_optax_chain():
     """clip_by_global_norm -> scale_by_adam -> add_decayed_weights(mask) -> scale(-lr) (optimizer.py:64-97; optax's
     published update rules restated in numpy, float64)."""
@@ -274,7 +312,7 @@ class EmuTorchEngine:
     def _stream(self):
         return 0
 
-    def energy_forces(self, R, z, ii, jj, cell=None, off=None):
+    def energy_forces(self, R, z, ii, jj, cell=None, off=None, want_stress=False):
         B, n = z.shape
         P = ii.shape[1]
         E, F = torch.zeros(B), torch.zeros(B, n, 3)
@@ -282,6 +320,10 @@ class EmuTorchEngine:
         dp = lambda t: None if t is None else t.data_ptr()
         self.lib.energy_forces(self.h, B, n, P, dp(R), dp(z), dp(ii), dp(jj), dp(cell), dp(off), dp(E), dp(F), None,
                                dp(ws), ws.numel() * 4, dp(self._status))
+        if want_stress:
+            S = torch.zeros(B, 3, 3)
+            self.lib.stress(self.h, B, n, P, dp(ws), ws.numel() * 4, dp(S))
+            return E[:, None], F, None, S
         return E[:, None], F, None
 
 
@@ -318,7 +360,7 @@ def test_trainer_step_reduces_the_loss_and_matches_oracle_gradient():
     assert abs(float(ls[0]) - (0.03 * float(loss0[1]) + 0.495 * float(loss0[2]))) <= 1e-5 * abs(float(ls[0]))
     assert abs(float(ls[1]) - float(loss0[1])) <= 1e-6 * abs(float(loss0[1]))
     with pytest.raises(NotImplementedError):
-        Trainer(eng, {'energy': 1.0, 'stress': 1.0})
+        Trainer(eng, {'energy': 1.0, 'partial_charge': 1.0})
     loss0, grad, _, _ = tr.loss_and_grad(tR, tz, ti, tj, tE, tF)           # (the buffers are shared between the trainers of an engine)
     blob0 = eng._blob.clone()
     gn = np.sqrt(sum(float((g ** 2).sum()) for g in og.values()))

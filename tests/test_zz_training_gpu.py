@@ -147,3 +147,32 @@ def test_loss_gradient_with_all_optional_branches_on_device():
         assert abs(float(loss[0]) - lo) <= 5e-5 * abs(lo)
         worst = _check(eng, grad.cpu().numpy(), og, p, 1e-4 if flags == 0 else 5e-4)
         print(f'all branches + ZBL, flags {flags}: loss {float(loss[0]):.6f} vs {lo:.6f}, worst relative gradient error {worst:.2e}')
+
+
+def test_loss_gradient_with_stress_target_on_device(solid):
+    """Energy + force + stress loss on a periodic cell (several images per pair) through the Trainer, tensor-core first pass."""
+    from mlff_b200.config import So3kratesConfig
+    from mlff_b200.training import Trainer
+    pos, cell, zs = solid['R'][:40].astype(np.float64), solid['unit_cell'].astype(np.float64), solid['z'][:40].astype(np.int64)
+    si, sj, S = o.primitive_neighbor_list(pos, cell, [True, True, True], 5.0)
+    ocfg = o.OracleConfig(F=132, n_layers=2)
+    p = o.init_params(ocfg, 6, embed_scale=4.0)
+    cfg = So3kratesConfig(F=132, n_layer=2)
+    rng = np.random.default_rng(3)
+    E_true, F_true, S_true = rng.normal(size=(1, 1)), rng.normal(size=(1, 40, 3)), rng.normal(size=(1, 3, 3))
+    w = {'energy': 0.01, 'force': 0.6, 'stress': 0.39}
+    lo, og, _, _, _ = o.loss_and_param_grads(ocfg, p, pos[None], zs[None], si[None], sj[None], E_true, F_true, w['energy'],
+                                             w['force'], cell=cell[None], cell_offset=S[None], S_true=S_true,
+                                             w_stress=w['stress'])
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a))
+    for flags in (0, 3):
+        eng = _engine(cfg, p, flags)
+        tr = Trainer(eng, w)
+        loss, grad, _, _ = tr.loss_and_grad(t(pos[None]), t(zs[None]), t(si[None]), t(sj[None]), t(E_true), t(F_true),
+                                            cell=t(cell[None]), cell_offset=t(S[None]), S_true=t(S_true))
+        torch.cuda.synchronize()
+        assert eng.check_status() == 0
+        assert abs(float(loss[0]) - lo) <= 5e-5 * abs(lo)
+        worst = _check(eng, grad.cpu().numpy(), og, p, 1e-4 if flags == 0 else 5e-4)
+        print(f'stress target, flags {flags}: loss {float(loss[0]):.6f} vs {lo:.6f}, worst relative gradient error {worst:.2e}')
+
