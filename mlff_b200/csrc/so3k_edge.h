@@ -55,3 +55,10 @@ void so3k_launch_filter_tc(const So3kDims& D, const Graph& g, const TcBlockW& W,
 // pair (the arrays must be zero on entry); wbar: pair-indexed filter cotangents from so3k_launch_qk_bwd_stream
 void so3k_launch_edge_bwd2_tc(const So3kDims& D, const Graph& g, const TcBlockW& Wf, const TcBlockW& Wg, const float* rec,
                               const float* wbar, float* gbar, float* ebar, int* status, cudaStream_t st);
+
+// C (rows, N) = A (rows, K; row stride lda) @ B (+ bias on the first bias_rows rows) on the tensor cores with split-bf16
+// operands; B(k, n) = Bp[k * sbk + n * sbn]; scratch: so3k_tc_gemm_scratch_bytes() bytes for the weight image.  Returns
+// false (nothing launched) when the shape is outside the kernel's limits -- the caller then runs its fp32 SIMT GEMM.
+size_t so3k_tc_gemm_scratch_bytes();
+bool so3k_tc_gemm(int rows, int N, int K, const float* A, int lda, const float* Bp, int sbk, int sbn, const float* bias,
+                  int bias_rows, float* C, int ldc, unsigned char* scratch, int* status, cudaStream_t st);

@@ -1105,6 +1105,164 @@ static void tc_bwd2_block(const So3kDims& D, const Graph& g, const unsigned char
 #undef SO3K_BWD2_CASE
 }
 static size_t tc_sub_scratch_bytes(const So3kDims& V) { return (sizeof(float) * slice_offsets(V).total + 255) / 256 * 256; }
+
+// ---- a plain dense layer on the tensor cores (training sweep, so3k_train.cu) ------------------------------------------------
+// C[rows x N] = A[rows x K] @ B (+ bias on the first bias_rows rows), fp32 in / out, split-bf16 operands (3 MMAs per
+// product, fp32 accumulation in tensor memory) -- the stacked-plane GEMMs of the dual-number sweep have exactly the shape of
+// the inference kernels' GEMM2 / GEMM3: a resident weight matrix (N, K <= 192) against 128-row tiles of a long row array.
+// Persistent CTAs, 16 warps; per tile: all warps split the tile's fp32 rows into the bf16 hi / lo operand image (the routine
+// of backward part 2), one thread issues the K / 16 x 3 MMAs, all warps drain the accumulator (+ bias) into a staging tile
+// that re-uses the operand-image region, one bulk copy stores the tile's contiguous rows (cooperative stores when the rows
+// are strided or N is not a multiple of 4).
+struct GemmDims {
+  int N, K, Np, Kp;
+  uint32_t sboA, sboB, szA, szB;      // bytes of ONE (hi or lo) image
+  uint32_t off_A, total;              // shared memory: B hi | B lo | A hi | A lo (the staging tile aliases the A images)
+};
+static inline GemmDims make_gemm_dims(int N, int K) {
+  GemmDims G;
+  G.N = N; G.K = K;
+  G.Np = (N + 15) & ~15;
+  G.Kp = (K + 15) & ~15;
+  G.sboA = G.sboB = (uint32_t)(G.Kp / 8) * 128u;
+  G.szA = (uint32_t)(TM / 8) * G.sboA;
+  G.szB = (uint32_t)(G.Np / 8) * G.sboB;
+  G.off_A = 2 * G.szB;
+  const uint32_t stage = (uint32_t)TM * (uint32_t)N * 4u, imgs = 2 * G.szA;
+  G.total = G.off_A + (((stage > imgs ? stage : imgs) + 127u) & ~127u);
+  return G;
+}
+// B image (K-major, rows n < Np, columns k < Kp): value B(k, n) = Bp[k * sbk + n * sbn]
+__global__ void k_gemm_b_image(GemmDims G, const float* __restrict__ Bp, int sbk, int sbn, unsigned char* __restrict__ img) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G.Np * G.Kp) return;
+  const int n = t / G.Kp, k = t % G.Kp;
+  const float v = (n < G.N && k < G.K) ? Bp[(size_t)k * sbk + (size_t)n * sbn] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  const uint32_t off = tc::canon_off(n, k >> 3, G.sboB) + (uint32_t)(k & 7) * 2u;
+  *reinterpret_cast<__nv_bfloat16*>(img + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(img + G.szB + off) = l;
+}
+__global__ void __launch_bounds__(NT, 1)
+k_tc_gemm(GemmDims G, int rows, const float* __restrict__ A, int lda, const unsigned char* __restrict__ Bimg,
+          const float* __restrict__ bias, int bias_rows, float* __restrict__ C, int ldc, int* __restrict__ status) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int s_abort;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* Bhi = smem;
+  unsigned char* Blo = smem + G.szB;
+  unsigned char* Ahi = smem + G.off_A;
+  unsigned char* Alo = Ahi + G.szA;
+  float* stage = reinterpret_cast<float*>(smem + G.off_A);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_fence_init();
+    s_abort = 0;
+  }
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(Bimg);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int k = tid; k < (int)(2 * G.szB / 16); k += NT) dst[k] = src[k];
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tD = tmem_base_s;
+  const uint32_t lane_sel = (uint32_t)(32 * (warp & 3)) << 16;
+  const uint32_t idesc = tc::make_idesc_bf16(TM, G.Np, 0, 0);
+  TcDims T;                                   // the two fields tc_wbar_image reads
+  T.Fp = G.Kp;
+  T.sboWb = G.sboA;
+  const int n_tiles = (rows + TM - 1) / TM;
+  const bool bulk = (G.N % 4 == 0) && ldc == G.N;
+  const int r = 32 * (warp & 3) + lane, cg = warp >> 2, nu = G.Np >> 4;
+  uint32_t parity = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int e0 = t * TM;
+    const int ne = (rows - e0) < TM ? (rows - e0) : TM;
+    // the previous tile's bulk store must have finished reading the staging tile (= this tile's operand-image region)
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    tc_wbar_image<5>(T, G.K, lda, warp, 16, lane, e0, ne, A, Ahi, Alo);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc_issue_gemm_ss(tD, Ahi, Alo, G.sboA, Bhi, Blo, G.sboB, G.Kp / 16, idesc);
+      tc::commit(&bar);
+    }
+    tc_wait(&bar, parity, &s_abort);
+    parity ^= 1u;
+    tc::fence_after_sync();
+    // drain: this thread's row, 16-column units cg, cg + 4, cg + 8
+    const bool add_bias = bias != nullptr && e0 + r < bias_rows;
+    for (int u = cg; u < nu; u += 4) {
+      uint32_t v[16];
+      tc::tmem_ld16(tD + lane_sel + (uint32_t)(16 * u), v);
+      tc::tmem_ld_wait();
+      if (G.N % 4 == 0) {                       // 16-byte row-per-lane stores (conflict-free for N mod 32 == 4, e.g. 132)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int c = 16 * u + 4 * q4;
+          if (c < G.N) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias) b = make_float4(bias[c], bias[c + 1], bias[c + 2], bias[c + 3]);     // (blob offsets need not be 16-byte aligned)
+            *reinterpret_cast<float4*>(stage + (size_t)r * G.N + c) =
+                make_float4(__uint_as_float(v[4 * q4]) + b.x, __uint_as_float(v[4 * q4 + 1]) + b.y,
+                            __uint_as_float(v[4 * q4 + 2]) + b.z, __uint_as_float(v[4 * q4 + 3]) + b.w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int c = 16 * u + q;
+          if (c < G.N) stage[(size_t)r * G.N + c] = __uint_as_float(v[q]) + (add_bias ? bias[c] : 0.f);
+        }
+      }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (bulk) {
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)ne * (uint32_t)G.N * 4u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(C + (size_t)e0 * G.N),
+                     "r"(tc::smem_u32(stage)), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else {
+      for (int k = tid; k < ne * G.N; k += NT) C[(size_t)(e0 + k / G.N) * ldc + k % G.N] = stage[k];
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  tc::fence_before_sync();
+  __syncthreads();
+  if (s_abort && tid == 0 && status) atomicOr(status, SO3K_STATUS_TC_TIMEOUT);
+  if (warp == 0) tc::tmem_dealloc(tD, 256);
+}
+size_t so3k_tc_gemm_scratch_bytes() { return 2u * 192u * 192u * 2u + 256u; }          // one B image (hi + lo) at the size limits
+bool so3k_tc_gemm(int rows, int N, int K, const float* A, int lda, const float* Bp, int sbk, int sbn, const float* bias,
+                  int bias_rows, float* C, int ldc, unsigned char* scratch, int* status, cudaStream_t st) {
+  if (rows < TM || N < 16 || N > 192 || K < 16 || K > 192 || K % 4 != 0 || lda % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(C) & 15)) return false;
+  const GemmDims G = make_gemm_dims(N, K);
+  if (G.total + 1024 > 227u * 1024u) return false;
+  so3k_count_launch();
+  k_gemm_b_image<<<so3k_cdiv(G.Np * G.Kp, 256), 256, 0, st>>>(G, Bp, sbk, sbn, scratch);
+  const size_t smem = G.total + 1024;
+  cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  so3k_count_launch();
+  k_tc_gemm<<<tc_grid(so3k_cdiv(rows, TM)), NT, smem, st>>>(G, rows, A, lda, scratch, bias, bias_rows, C, ldc, status);
+  return true;
+}
+
 extern "C" void so3k_tc_phase_dump(void) {
   unsigned long long h[3][16];
   cudaDeviceSynchronize();
@@ -1202,6 +1360,9 @@ __global__ void k_edge_bwd2_ref(So3kDims D, int Gst, int pair_cap, int accumulat
 }  // namespace
 
 extern "C" void so3k_tc_phase_dump(void) {}
+size_t so3k_tc_gemm_scratch_bytes() { return 256; }
+bool so3k_tc_gemm(int, int, int, const float*, int, const float*, int, int, const float*, int, float*, int, unsigned char*, int*,
+                  cudaStream_t) { return false; }     // the emulated build has no tensor cores: the fp32 SIMT GEMM runs
 // the stand-ins keep the CUDA kernels' narrow-shape limit, so that wide models take the same 2 x 2 sub-block path here
 static bool tc_narrow_supported(const So3kDims& D) { return D.F % 4 == 0 && D.F <= 144 && D.F + D.Fs <= FMAXR && D.nl <= 7 && D.H <= 8; }
 static size_t tc_block_image_bytes(const So3kDims&) { return 256; }

@@ -17,6 +17,7 @@
 // observable.py:62-93) plus the optional branches: LayerNorm pre / post (so3krates_layer.py:103-106, 153-156, 170-174),
 // ResidualMLP 1 / 2 (mlp.py:30-72) and the ZBL repulsion with its ten scalars (observable.py:110-183).
 #include "so3k_internal.h"
+#include "so3k_edge.h"
 
 namespace {
 
@@ -991,6 +992,7 @@ struct TrainWs {
   float *H, *Hs, *cat, *abbar, *catbar;
   float *xbar, *chibar, *x1bar, *chi1bar, *sbar, *wbar, *projbar, *gbar, *hsbar;
   float *part, *dense;                         // weight-gradient partial sums (TN_PARTS x C x C), dense (F, F) product
+  unsigned char* bimg;                         // weight operand image of the tensor-core GEMM in flight
   // optional node-level branches (SO3K_OPT_*; null when absent), per layer: LayerNorm-1 output, states between the
   // blocks, ResidualMLP intermediates (a1 = silu(x) W0, r = x + silu(a1) W1) ; temporaries
   float *xn1, *x1b, *x2a, *x2b, *ra1[2], *rr[2];
@@ -1053,6 +1055,7 @@ TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base, in
   w.hsbar = (float*)take(fl * pl * Pe * Fs);
   w.part = (float*)take(fl * (size_t)TN_PARTS * C * C);
   w.dense = (float*)take(fl * F * F);
+  w.bimg = (unsigned char*)take(so3k_tc_gemm_scratch_bytes());
   const bool ln = opts & SO3K_OPT_LN, post = ln && (opts & SO3K_OPT_LN_POST), res1 = opts & SO3K_OPT_RES1, res2 = opts & SO3K_OPT_RES2;
   auto layer_nf = [&](bool on) { return on ? (float*)take(fl * pl * L * N * F) : (float*)nullptr; };
   w.xn1 = layer_nf(ln);
@@ -1073,16 +1076,23 @@ TrainWs carve_train(const So3kDims& D, int N, int Pt, int planes, void* base, in
 inline dim3 g1(size_t count) { return dim3((unsigned)((count + TB - 1) / TB)); }
 inline dim3 gw(size_t warps) { return dim3((unsigned)((warps * 32 + TB - 1) / TB)); }
 
+// With SO3K_FLAG_TENSOR the large dense layers of the sweep run on the tensor cores (so3k_tc_gemm: split-bf16 operands, fp32
+// accumulation); shapes outside that kernel's limits, and the fp32 mode, use the SIMT GEMM below.
+struct TcCtx { bool on; unsigned char* scratch; int* status; };
 // C (rows, Nc) = A (rows, Kd) @ W (Kd, Nc) + bias on the first bias_rows rows
 void gemm_nn(int rows, int Nc, int Kd, const float* A, const float* W, const float* bias, int bias_rows, int beta,
-             float* C, cudaStream_t st) {
+             float* C, cudaStream_t st, const TcCtx* tc = nullptr) {
   if (rows <= 0) return;
+  if (tc && tc->on && !beta &&
+      so3k_tc_gemm(rows, Nc, Kd, A, Kd, W, Nc, 1, bias, bias_rows, C, Nc, tc->scratch, tc->status, st))
+    return;
   SO3K_LAUNCH(k_tr_gemm, dim3(so3k_cdiv(Nc, GN), so3k_cdiv(rows, GM)), dim3(256), 0, st, rows, Nc, Kd, A, Kd, W, Nc, 1,
               bias, bias_rows, beta, C, Nc);
 }
 // C (rows, Kd) = A (rows, Nc) @ W (Kd, Nc)^T
-void gemm_nt(int rows, int Kd, int Nc, const float* A, const float* W, float* C, cudaStream_t st) {
+void gemm_nt(int rows, int Kd, int Nc, const float* A, const float* W, float* C, cudaStream_t st, const TcCtx* tc = nullptr) {
   if (rows <= 0) return;
+  if (tc && tc->on && so3k_tc_gemm(rows, Kd, Nc, A, Nc, W, 1, Nc, nullptr, 0, C, Kd, tc->scratch, tc->status, st)) return;
   SO3K_LAUNCH(k_tr_gemm, dim3(so3k_cdiv(Kd, GN), so3k_cdiv(rows, GM)), dim3(256), 0, st, rows, Kd, Nc, A, Nc, W, 1, Nc,
               (const float*)nullptr, 0, 0, C, Kd);
 }
@@ -1143,6 +1153,8 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
 
   const int rowsE = pl * (int)Pe, rowsN = pl * N;
   const size_t NF = (size_t)N * F;
+  const TcCtx tcx = {(h->cfg.flags & SO3K_FLAG_TENSOR) != 0, w.bimg, dev_status};
+  const TcCtx* tc = &tcx;
   auto Lp = [&](float* base, size_t per, int t) { return base + (size_t)t * pl * per; };
   // ResidualMLP (mlp.py:30-72, bias-free): y = silu(x + silu(silu(x) W0) W1) W2 ; keeps a1 = silu(x) W0 and r = x + silu(a1) W1
   auto resmlp_fwd = [&](const size_t* Wk, const float* x, float* a1, float* rr, float* y) {
@@ -1184,9 +1196,9 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
     for (int b = 0; b < 2; ++b) {
       const BlockParams& bp = b ? lp.gb : lp.fb;
       float* A1 = Lp(w.A1[b], Pe * F, t); float* As = Lp(w.As[b], Pe * Fs, t); float* wf = Lp(w.w[b], Pe * F, t);
-      gemm_nn(rowsE, (int)F, (int)K, w.rbf, prm + bp.rad_W1, prm + bp.rad_b1, (int)Pe, 0, A1, st);
+      gemm_nn(rowsE, (int)F, (int)K, w.rbf, prm + bp.rad_W1, prm + bp.rad_b1, (int)Pe, 0, A1, st, tc);
       SO3K_LAUNCH(k_tr_silu<T>, g1(Pe * F), dim3(TB), 0, st, Pe * F, A1, w.H);
-      gemm_nn(rowsE, (int)F, (int)F, w.H, prm + bp.rad_W2, prm + bp.rad_b2, (int)Pe, 0, wf, st);
+      gemm_nn(rowsE, (int)F, (int)F, w.H, prm + bp.rad_W2, prm + bp.rad_b2, (int)Pe, 0, wf, st, tc);
       SO3K_LAUNCH(k_tr_sph1<T>, g1(Pe * Fs), dim3(TB), 0, st, Pt, (int)nl, (int)Fs, gl, prm + bp.sph_W1, prm + bp.sph_b1,
                   As, w.Hs);
       gemm_nn(rowsE, (int)F, (int)Fs, w.Hs, prm + bp.sph_W2, prm + bp.sph_b2, (int)Pe, 1, wf, st);
@@ -1293,14 +1305,14 @@ int run_vjp(so3k_handle* h, int B, int n, int P, const float* R, const int* z, c
       colsum((int)Pe, (int)F, pl, w.wbar, grad + bp.sph_b2, st);
       SO3K_LAUNCH(k_tr_silu<T>, g1(Pe * F), dim3(TB), 0, st, Pe * F, A1, w.H);
       gemm_tn((int)Pe, pl, (int)F, (int)F, w.H, (int)F, w.wbar, (int)F, grad + bp.rad_W2, w.part, st);
-      gemm_nt(rowsE, (int)F, (int)F, w.wbar, prm + bp.rad_W2, w.H, st);              // Hbar
+      gemm_nt(rowsE, (int)F, (int)F, w.wbar, prm + bp.rad_W2, w.H, st, tc);          // Hbar
       SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(Pe * F), dim3(TB), 0, st, Pe * F, A1, w.H);   // A1bar
       gemm_tn((int)Pe, pl, (int)K, (int)F, w.rbf, (int)K, w.H, (int)F, grad + bp.rad_W1, w.part, st);
       colsum((int)Pe, (int)F, pl, w.H, grad + bp.rad_b1, st);
       // spherical branch: w += silu(g Ws1 + bs1) Ws2 + bs2
       SO3K_LAUNCH(k_tr_silu<T>, g1(Pe * Fs), dim3(TB), 0, st, Pe * Fs, As, w.Hs);
       gemm_tn((int)Pe, pl, (int)Fs, (int)F, w.Hs, (int)Fs, w.wbar, (int)F, grad + bp.sph_W2, w.part, st);
-      gemm_nt(rowsE, (int)Fs, (int)F, w.wbar, prm + bp.sph_W2, w.hsbar, st);
+      gemm_nt(rowsE, (int)Fs, (int)F, w.wbar, prm + bp.sph_W2, w.hsbar, st, tc);
       SO3K_LAUNCH(k_tr_silu_bwd<T>, g1(Pe * Fs), dim3(TB), 0, st, Pe * Fs, As, w.hsbar);   // Asbar
       gemm_tn((int)Pe, pl, (int)nl, (int)Fs, gl, (int)nl, w.hsbar, (int)Fs, grad + bp.sph_W1, w.part, st);
       colsum((int)Pe, (int)Fs, pl, w.hsbar, grad + bp.sph_b1, st);
