@@ -390,7 +390,9 @@ def run_training(args, w):
         ms_sweep = max(phases['loss_and_grad_ms (E+F pass + loss + dual sweep + all-reduce)'] - phases['energy_forces_ms'], 1e-6)
         tf = flops / (ms_sweep * 1e-3) / 1e12
         peak_tf = pk.get('bf16_tflops_sustained', pk.get('bf16_tflops'))
-        roof = {'kernel': 'k_tr_gemm / k_tr_gemm_tn (fp32 GEMMs of the dual-number sweep, so3k_energy_forces_vjp)', 'bound': 'tensor',
+        roof = {'kernel': ('k_tc_gemm (tcgen05 split-bf16: forward + input-gradient layers) / k_tr_gemm_tn (fp32 FMA: weight gradients)'
+                           if flags else 'k_tr_gemm / k_tr_gemm_tn (fp32 FMA)') + ' of the dual-number sweep, so3k_energy_forces_vjp',
+                'bound': 'tensor',
                 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
                 'peak_kind': f'{pk_kind} sustained bf16 (kernels timed inside a long step)',
                 'ms_per_step': ms_sweep, 'algorithmic_flops_per_step': flops,

@@ -770,18 +770,20 @@ __global__ void __launch_bounds__(256) k_tr_gemm(int Mr, int Nc, int Kd, const f
 // matrix for F = 132) and a chunk of rows: 9 x 9 outputs per thread, 18 shared-memory loads per 81 FMAs; the per-chunk
 // partial sums go to a scratch array and k_tr_reduce_parts adds them onto the gradient in a fixed order (no atomics).
 constexpr int WT = 144, WR = 8, WPT = 9;
+template <int WPK>                // output rows per thread: the tile is 16 WPK rows (Kd) x 144 columns (Nc)
 __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, int Nc, int chunk,
                                                     const float* __restrict__ A, int lda, const float* __restrict__ B,
                                                     int ldb, float* __restrict__ part) {
-  __shared__ float As[WR][WT];
+  __shared__ float As[WR][16 * WPK];
   __shared__ float Bs[WR][WT];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int k0 = blockIdx.y * WT, c0 = blockIdx.x * WT;
+  constexpr int WTK = 16 * WPK;
+  const int k0 = blockIdx.y * WTK, c0 = blockIdx.x * WT;
   const int Rt = R * planes;                                   // stacked rows (fits an int: planes * edge slots)
   const int rbeg = blockIdx.z * chunk, rend = rbeg + chunk < Rt ? rbeg + chunk : Rt;
-  float acc[WPT][WPT];
+  float acc[WPK][WPT];
 #pragma unroll
-  for (int a = 0; a < WPT; ++a)
+  for (int a = 0; a < WPK; ++a)
 #pragma unroll
     for (int b = 0; b < WPT; ++b) acc[a][b] = 0.f;
   // 8 rows x 144 columns of both operands per step: 4.5 elements per thread, fetched a step ahead into registers
@@ -794,7 +796,7 @@ __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, i
       const int gr = rr + r;
       float av = 0.f, bv = 0.f;
       if (t < WR * WT && gr < rend) {
-        if (k0 + c < Kd) av = A[(size_t)gr * lda + k0 + c];
+        if (c < WTK && k0 + c < Kd) av = A[(size_t)gr * lda + k0 + c];
         if (c0 + c < Nc) {
           const int pb = gr >= R ? 1 : 0, rb_ = gr - pb * R;     // planes <= 2
           bv = B[(size_t)((planes - 1 - pb) * R + rb_) * ldb + c0 + c];
@@ -810,7 +812,7 @@ __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, i
     for (int q = 0; q < NLD; ++q) {
       const int t = tid + 256 * q, r = t / WT, c = t - r * WT;
       if (t < WR * WT) {
-        As[r][c] = ra[q];
+        if (c < WTK) As[r][c] = ra[q];
         Bs[r][c] = rb[q];
       }
     }
@@ -818,13 +820,13 @@ __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, i
     if (rr + WR < rend) fetch(rr + WR);
 #pragma unroll
     for (int r = 0; r < WR; ++r) {
-      float av[WPT], bv[WPT];
+      float av[WPK], bv[WPT];
 #pragma unroll
-      for (int a = 0; a < WPT; ++a) av[a] = As[r][ty + 16 * a];
+      for (int a = 0; a < WPK; ++a) av[a] = As[r][ty + 16 * a];
 #pragma unroll
       for (int b = 0; b < WPT; ++b) bv[b] = Bs[r][tx + 16 * b];
 #pragma unroll
-      for (int a = 0; a < WPT; ++a)
+      for (int a = 0; a < WPK; ++a)
 #pragma unroll
         for (int b = 0; b < WPT; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
     }
@@ -832,7 +834,7 @@ __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, i
   }
   float* dst = part + (size_t)blockIdx.z * Kd * Nc;
 #pragma unroll
-  for (int a = 0; a < WPT; ++a) {
+  for (int a = 0; a < WPK; ++a) {
     const int k = k0 + ty + 16 * a;
     if (k >= Kd) continue;
 #pragma unroll
@@ -1101,15 +1103,22 @@ void gemm_tn(int R, int planes, int Kd, int Nc, const float* X, int ldx, const f
              cudaStream_t st) {
   if (R <= 0) return;
   const long long Rt = (long long)R * planes;
-  const int tiles = so3k_cdiv(Nc, WT) * so3k_cdiv(Kd, WT);
+  // output rows per thread: 1 (Kd <= 16), 2 (<= 32), 3 (<= 48) or 9 (tiles of 144 rows) -- a small Kd does not pay for a full tile
+  const int wpk = Kd <= 16 ? 1 : Kd <= 32 ? 2 : Kd <= 48 ? 3 : 9;
+  const int tiles = so3k_cdiv(Nc, WT) * so3k_cdiv(Kd, 16 * wpk);
   int nz = TN_PARTS / tiles;
   if (nz < 1) nz = 1;
   int chunk = (int)((Rt + nz - 1) / nz);
   chunk = (chunk + WR - 1) / WR * WR;
   if (chunk < 64) chunk = 64;
   nz = (int)((Rt + chunk - 1) / chunk);
-  SO3K_LAUNCH(k_tr_gemm_tn, dim3(so3k_cdiv(Nc, WT), so3k_cdiv(Kd, WT), nz), dim3(256), 0, st, R, planes, Kd, Nc, chunk, X,
-              ldx, Ybar, ldy, part);
+  const dim3 grid(so3k_cdiv(Nc, WT), so3k_cdiv(Kd, 16 * wpk), nz);
+  switch (wpk) {
+    case 1: SO3K_LAUNCH(k_tr_gemm_tn<1>, grid, dim3(256), 0, st, R, planes, Kd, Nc, chunk, X, ldx, Ybar, ldy, part); break;
+    case 2: SO3K_LAUNCH(k_tr_gemm_tn<2>, grid, dim3(256), 0, st, R, planes, Kd, Nc, chunk, X, ldx, Ybar, ldy, part); break;
+    case 3: SO3K_LAUNCH(k_tr_gemm_tn<3>, grid, dim3(256), 0, st, R, planes, Kd, Nc, chunk, X, ldx, Ybar, ldy, part); break;
+    default: SO3K_LAUNCH(k_tr_gemm_tn<9>, grid, dim3(256), 0, st, R, planes, Kd, Nc, chunk, X, ldx, Ybar, ldy, part); break;
+  }
   SO3K_LAUNCH(k_tr_reduce_parts, dim3(so3k_cdiv((long long)Kd * Nc, 256)), dim3(256), 0, st, Kd * Nc, nz, part, G);
 }
 // out (C) += column sums of the gradient plane of X (R, C)
