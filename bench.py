@@ -396,8 +396,9 @@ def run_training(args, w):
                 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
                 'peak_kind': f'{pk_kind} sustained bf16 (kernels timed inside a long step)',
                 'ms_per_step': ms_sweep, 'algorithmic_flops_per_step': flops,
-                'note': 'fp32 FMA on the CUDA cores, reported against the bf16 tensor peak; the time is the whole sweep '
-                        '(GEMMs + elementwise + gather kernels), so this is a lower bound of the GEMM kernels\' own rate'}
+                'note': 'algorithmic FLOPs of all dense layers of the sweep (both planes; forward, input gradients, weight '
+                        'gradients) over the time of the WHOLE sweep (GEMMs + elementwise + gather kernels), against the bf16 tensor '
+                        'peak: a lower bound of the GEMM kernels\' own rate'}
         threads = os.cpu_count() or 1
         cpu = None
         if not args.no_cpu_baseline:
