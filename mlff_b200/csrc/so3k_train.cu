@@ -844,13 +844,23 @@ __global__ void __launch_bounds__(256) k_tr_gemm_tn(int R, int planes, int Kd, i
     }
   }
 }
-// G[i] += sum_z part[z][i]  (i < count = Kd Nc of the call that filled `part`)
-__global__ void k_tr_reduce_parts(int count, int nz, const float* __restrict__ part, float* __restrict__ G) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+// G[i] += sum_z part[z][i]  (i < count = Kd Nc of the call that filled `part`): 32 outputs x 8 partial-sum lanes per block, so
+// that the nz (up to 296) loads of an output are eight independent streams; the lanes are combined in a fixed order
+__global__ void __launch_bounds__(256) k_tr_reduce_parts(int count, int nz, const float* __restrict__ part, float* __restrict__ G) {
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, zy = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cx;
   float acc = 0.f;
-  for (int z = 0; z < nz; ++z) acc += part[(size_t)z * count + i];
-  G[i] += acc;
+  if (i < count)
+    for (int z = zy; z < nz; z += 8) acc += part[(size_t)z * count + i];
+  sh[zy][cx] = acc;
+  __syncthreads();
+  if (zy == 0 && i < count) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sh[k][cx];
+    G[i] += v;
+  }
 }
 // per-head blocks of a dense (F, F) product: Wbar[h, r, c] += Gd[h d + r, h d + c]
 __global__ void k_tr_extract_heads(int F, int d, const float* __restrict__ Gd, float* __restrict__ Wbar) {
@@ -1119,7 +1129,7 @@ void gemm_tn(int R, int planes, int Kd, int Nc, const float* X, int ldx, const f
     case 3: SO3K_LAUNCH(k_tr_gemm_tn<3>, grid, dim3(256), 0, st, R, planes, Kd, Nc, chunk, X, ldx, Ybar, ldy, part); break;
     default: SO3K_LAUNCH(k_tr_gemm_tn<9>, grid, dim3(256), 0, st, R, planes, Kd, Nc, chunk, X, ldx, Ybar, ldy, part); break;
   }
-  SO3K_LAUNCH(k_tr_reduce_parts, dim3(so3k_cdiv((long long)Kd * Nc, 256)), dim3(256), 0, st, Kd * Nc, nz, part, G);
+  SO3K_LAUNCH(k_tr_reduce_parts, dim3(so3k_cdiv((long long)Kd * Nc, 32)), dim3(256), 0, st, Kd * Nc, nz, part, G);
 }
 // out (C) += column sums of the gradient plane of X (R, C)
 void colsum(int R, int C, int planes, const float* X, float* out, cudaStream_t st) {
