@@ -202,8 +202,9 @@ int so3k_potential_displacements(so3k_handle* h, int32_t N, int32_t P,
  * reverse-mode parameter gradient, in one dual-number sweep (so3k_train.cu).
  * F_bar == NULL and S_bar == NULL select the first-order sweep (grad = sum_b E_bar[b] dE_b/dtheta; E_bar == NULL means all ones).
  * E_out (B) or NULL receives the energies of the sweep.  Every model variant of so3k_config.flags is covered: the optional
- * LayerNorms and ResidualMLPs and the ten ZBL scalars have their gradients in the blob too.  Arithmetic is fp32 on the CUDA
- * cores in either filter mode. */
+ * LayerNorms and ResidualMLPs and the ten ZBL scalars have their gradients in the blob too.  Arithmetic: fp32 on the CUDA
+ * cores; with SO3K_FLAG_TENSOR the large forward / input-gradient dense layers run on tcgen05 with split-bf16 operands
+ * (fp32 accumulation), the weight gradients stay fp32 FMA. */
 size_t so3k_train_workspace_bytes(const so3k_handle* h, int64_t n_atoms_total, int64_t n_edge_slots_total);
 int so3k_energy_forces_vjp(so3k_handle* h, int32_t B, int32_t n, int32_t P,
                            const float* R, const int32_t* z, const int32_t* idx_i, const int32_t* idx_j,
