@@ -627,6 +627,26 @@ def run_ours(args, w):
         del fout, ii_f, jj_f, S_f
 
     md_info = None
+    if args.md_steps > 0 and use_dd:
+        # the same MD loop with the force call decomposed over the ranks (md.CalculatorDD: one all-reduce of forces + energy)
+        from mlff_b200 import md
+        masses = torch.as_tensor(np.where(z == 8, 15.999, np.where(z == 6, 12.011, 1.008)), device=dev)
+        md_sess = dd.DDSession(eng, cfg.n_layer, cell, world, rank, calc.cutoff, skin=args.md_skin, cuda_graph=args.dd_graph,
+                               capacity=int(cap * 1.6 / world) + 4096)
+        atoms = md.AtomsX(positions=pos_d.clone(), momenta=md.maxwell_boltzmann_momenta(masses, 300.0, seed=1), masses=masses,
+                          numbers=z_d, cell=cell, pbc=pbc).init_domain_decomposition(md_sess)
+        integ = md.VelocityVerletX.create(0.5 * md.FS, md.CalculatorDD(md_sess))
+        atoms, _ = md.simulate(integ, atoms, 3)
+        barrier()
+        b0, t0 = md_sess.n_builds, time.perf_counter()
+        atoms, st_md = md.simulate(integ, atoms, args.md_steps)
+        barrier()
+        dt_md = (time.perf_counter() - t0) / args.md_steps
+        etot = st_md['kinetic_energy'] + st_md['potential_energy']
+        md_info = {'steps': args.md_steps, 'ms_per_step': dt_md * 1e3, 'atom_steps_per_s': N / dt_md, 'timestep_fs': 0.5,
+                   'skin_A': args.md_skin, 'ranks': world, 'plan_rebuilds': md_sess.n_builds - b0,
+                   'total_energy_drift_over_kinetic': float(np.abs(etot - etot[0]).max() / st_md['kinetic_energy'].mean())}
+        md_sess.close()
     if args.md_steps > 0 and world == 1:
         # MD inner loop on the device: velocity Verlet, skin list re-used until an atom moved skin / 2
         from mlff_b200 import md

@@ -87,7 +87,7 @@ class AtomsX:
     numbers: torch.Tensor                       # (N)   int32
     cell: Optional[np.ndarray] = None           # (3,3) row-wise (host)
     pbc: Sequence[bool] = (False, False, False)
-    neighbors: Optional[SkinNeighborList] = None
+    neighbors: Optional[object] = None          # SkinNeighborList, or DDNeighbors (domain decomposition)
     cache: Optional[Dict[str, torch.Tensor]] = None     # properties evaluated at `positions` (force re-use)
 
     def get_positions(self): return self.positions
@@ -117,6 +117,10 @@ class AtomsX:
 
     def update_velocities(self, velocities: torch.Tensor) -> 'AtomsX':
         return replace(self, momenta=velocities * self.masses[:, None])      # mlff/mdx/atoms.py:174-186
+
+    def init_domain_decomposition(self, session) -> 'AtomsX':
+        """The lists of a domain-decomposed run live in `session` (mlff_b200.dist.DDSession); use with CalculatorDD."""
+        return replace(self, neighbors=DDNeighbors(session), cache=None)
 
     def init_spatial_partitioning(self, engine, cutoff: float, skin: float, capacity_multiplier: float = 1.25,
                                   mode: Optional[int] = None) -> 'AtomsX':
@@ -156,6 +160,59 @@ class CalculatorX:
         self.n_calls += 1
         out = {'energy': self.energy_scale * E.reshape(()).to(torch.float64),
                'forces': self.energy_scale * F[0].to(torch.float64)}
+        atoms.cache = out
+        return out
+
+
+class DDNeighbors:
+    """What the integrators ask of `atoms.neighbors` when the lists live in a domain-decomposition session
+    (mlff_b200.dist.DDSession keeps the per-rank plan within its own skin): `update` is a no-op."""
+
+    def __init__(self, session):
+        self.session = session
+
+    def update(self, positions: torch.Tensor) -> 'DDNeighbors':
+        return self
+
+    @property
+    def n_builds(self) -> int:
+        return self.session.n_builds
+
+    @property
+    def count(self) -> int:
+        return int(self.session.dd.P) if getattr(self.session.dd, 'P', None) is not None else 0
+
+
+class CalculatorDD:
+    """energy + forces of ONE large periodic system decomposed over the ranks of a process group (spatial bricks, halo
+    exchange per layer: mlff_b200.dist.DDSession).  Every rank holds the whole AtomsX -- positions replicated, the O(N)
+    integrator update replicated and deterministic -- evaluates its brick, and the owned forces and energies are summed
+    into the full arrays with ONE all-reduce of 3 N + 1 float64 numbers (NCCL; skipped for a single rank).  The reference's
+    mdx loop is single-device; this is how its inner loop scales past one GPU."""
+
+    def __init__(self, session, energy_scale: float = 1.0, group=None):
+        self.session = session
+        self.energy_scale = energy_scale
+        self.group = group
+        self.n_calls = 0
+        self._buf: Optional[torch.Tensor] = None
+
+    def __call__(self, atoms: AtomsX) -> Dict[str, torch.Tensor]:
+        if atoms.cache is not None:
+            return atoms.cache
+        n = atoms.get_number_of_atoms()
+        e, f_own, ids = self.session.energy_forces(atoms.positions, atoms.numbers)
+        if self._buf is None or self._buf.shape[0] != 3 * n + 1:
+            self._buf = torch.zeros(3 * n + 1, dtype=torch.float64, device=atoms.positions.device)
+        buf = self._buf
+        buf.zero_()
+        buf[:3 * n].view(n, 3)[ids] = f_own.to(torch.float64)
+        buf[3 * n] = e
+        if self.session.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(buf, group=self.group)
+        self.n_calls += 1
+        out = {'energy': self.energy_scale * buf[3 * n].clone(), 'forces': self.energy_scale * buf[:3 * n].view(n, 3).clone()}
         atoms.cache = out
         return out
 

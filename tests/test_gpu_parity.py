@@ -566,3 +566,40 @@ def test_dd_session_reuses_its_plan_within_the_skin(cuda_graph):
         assert np.abs(F - Fo.numpy()).max() < F_ATOL, step
         assert sess.n_builds == (1 if step < 3 else 2), (step, sess.n_builds)
     assert eng.check_status() == 0
+
+
+def test_md_through_the_domain_decomposed_calculator():
+    """md.CalculatorDD (one rank here: the whole sweep -- plan with a skin, owned / ghost order, stepwise stages -- without the
+    collective): a velocity-Verlet trajectory equals the one driven by the single-domain CalculatorX on the same engine."""
+    from mlff_b200 import dist as dd
+    from mlff_b200 import md
+    from mlff_b200.capi import FLAG_TENSOR, FLAG_KEEP_FILTERS
+    from common import jittered_lattice, water_like_numbers
+    n, box = 600, 18.2
+    pos = jittered_lattice(n, box, 9)
+    z = water_like_numbers(n, 9)
+    cell = np.eye(3) * box
+    cfg = o.OracleConfig(F=132, n_layers=2)
+    p = o.init_params(cfg, 0, embed_scale=4.0)
+    eng = make(cfg, p, flags=FLAG_TENSOR | FLAG_KEEP_FILTERS)
+    masses = torch.as_tensor(np.where(z == 8, 15.999, np.where(z == 6, 12.011, 1.008)), device='cuda:0')
+    mom = md.maxwell_boltzmann_momenta(masses, 300.0, seed=2)
+    z_d = dev(z, torch.int32)
+    traj = {}
+    for kind in ('single', 'dd'):
+        atoms = md.AtomsX(positions=dev(pos, torch.float64), momenta=mom.clone(), masses=masses, numbers=z_d, cell=cell,
+                          pbc=(True, True, True))
+        if kind == 'single':
+            atoms = atoms.init_spatial_partitioning(eng, cfg.r_cut, 0.4)
+            calc = md.CalculatorX(eng)
+        else:
+            sess = dd.DDSession(eng, cfg.n_layers, cell, 1, 0, cfg.r_cut, skin=0.4, cuda_graph=True)
+            atoms = atoms.init_domain_decomposition(sess)
+            calc = md.CalculatorDD(sess)
+        integ = md.VelocityVerletX.create(0.5 * md.FS, calc)
+        atoms, st = md.simulate(integ, atoms, 12)
+        traj[kind] = (atoms.positions.cpu().numpy(), st['potential_energy'])
+    assert eng.check_status() == 0
+    assert np.abs(traj['dd'][0] - traj['single'][0]).max() < 1e-5
+    assert np.abs(traj['dd'][1] - traj['single'][1]).max() <= 2e-5 * np.abs(traj['single'][1]).max()
+
