@@ -36,22 +36,95 @@ __device__ __forceinline__ void head_accum(float* val, int t, int lane, float p)
 
 // A load the compiler may not move or merge (asm volatile): used where a whole batch of independent row loads has to be
 // in flight before its first use.  Read-only path, L1-allocating like a plain load.
-__device__ __forceinline__ float ld_pinned(const float* p) {
-#ifdef SO3K_EMU
-  return *p;
-#else
-  float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-#endif
-}
-
 __device__ __forceinline__ float4 ld_pinned4(const float* p) {
 #ifdef SO3K_EMU
   return *reinterpret_cast<const float4*>(p);
 #else
   float4 v;
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#endif
+}
+
+// Filter rows (w[pid e]) are read exactly twice per sweep -- by the two directed edges of the pair, from two different
+// SMs -- so they never re-hit in L1 and their second reader is their last use.  Load policy (template parameter MODE):
+//   0  plain read-only loads
+//   1  filter rows bypass L1 (L1::no_allocate): L1 keeps the sender rows, which neighbouring receivers share
+//   2  1 + the second reader (the sender's row comes before the receiver's: j < i) marks the line L2::evict_first
+//   3  2 + sender rows carry an L2::evict_last hint
+// Measured on c4 (profiles/README.md, r03d): k_alpha_aggregate_scan 6.66 / 6.60 / 6.48 / 6.53 ms per step for modes 0-3,
+// k_qk_bwd_stream 7.49 / 7.87 / 9.33 / 10.5 (the policy operand costs it registers) -> 2 and 0.
+#ifndef SO3K_AGG_W_POLICY
+#define SO3K_AGG_W_POLICY 2
+#endif
+#ifndef SO3K_QK_W_POLICY
+#define SO3K_QK_W_POLICY 0
+#endif
+struct WPolicy { unsigned long long first, normal, last; };
+template <int MODE>
+__device__ __forceinline__ WPolicy make_w_policy() {
+  WPolicy P;
+  P.first = P.normal = P.last = 0ull;
+#ifndef SO3K_EMU
+  if (MODE >= 2) {
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(P.first));
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(P.normal));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(P.last));
+  }
+#endif
+  return P;
+}
+template <int MODE>
+__device__ __forceinline__ float ld_w(const float* p, unsigned long long pol) {
+#ifdef SO3K_EMU
+  return *p;
+#else
+  float v;
+  if (MODE == 0) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  else if (MODE == 1) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+#endif
+}
+template <int MODE>
+__device__ __forceinline__ float4 ld_w4(const float* p, unsigned long long pol) {
+#ifdef SO3K_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 v;
+  if (MODE == 0)
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  else if (MODE == 1)
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+#endif
+}
+template <int MODE>
+__device__ __forceinline__ float ld_row(const float* p, unsigned long long pol) {      // sender rows
+#ifdef SO3K_EMU
+  return *p;
+#else
+  float v;
+  if (MODE < 3) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  else asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+#endif
+}
+template <int MODE>
+__device__ __forceinline__ float4 ld_row4(const float* p, unsigned long long pol) {
+#ifdef SO3K_EMU
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 v;
+  if (MODE < 3)
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 #endif
 }
@@ -359,14 +432,20 @@ static bool so3k_scan_ok(int F, int heads) {
 }
 
 // k_alpha_aggregate, fast variant (see there for the math)
+#ifndef SO3K_AGG_MINB
+#define SO3K_AGG_MINB 2
+#endif
+#ifndef SO3K_AGG_EPB
+#define SO3K_AGG_EPB 2
+#endif
 template <bool TAIL>
-__global__ void __launch_bounds__(WPB * 32, 2)
+__global__ void __launch_bounds__(WPB * 32, SO3K_AGG_MINB)
 k_alpha_aggregate_scan(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                        const int* __restrict__ pid, const float4* __restrict__ geom, const float* __restrict__ x,
                        const float* __restrict__ chi, const float* __restrict__ proj, const float* __restrict__ wst_f,
                        const float* __restrict__ wst_g, float* __restrict__ alpha, float* __restrict__ x1,
                        float* __restrict__ chi1) {
-  constexpr int EPB = 2;
+  constexpr int EPB = SO3K_AGG_EPB, WP = SO3K_AGG_W_POLICY;
   __shared__ float s_a[WPB][32 * AMAX];
   __shared__ float s_ph[WPB][32];
   __shared__ int s_j[WPB][32];
@@ -387,6 +466,7 @@ k_alpha_aggregate_scan(So3kDims D, int N, int Ast, const int* __restrict__ rowpt
   const float* const kg_v = proj + 3 * F + offv; const float* const kg_t = proj + 3 * F + offt;
   const float* const vv_v = proj + 4 * F + offv; const float* const vv_t = proj + 4 * F + offt;
   const float mv = okv ? 1.f : 0.f, mt = okt ? 1.f : 0.f;
+  const WPolicy wpol = make_w_policy<WP>();
   const HeadScan hsf = make_head_scan(lane, F, H), hsg = make_head_scan(lane, F, nl);
   float4 qf = make_float4(0.f, 0.f, 0.f, 0.f), qg = qf;
   float qft = 0.f, qgt = 0.f;
@@ -417,17 +497,18 @@ k_alpha_aggregate_scan(So3kDims D, int N, int Ast, const int* __restrict__ rowpt
       for (int k = 0; k < EPB; ++k) {
         const int qc = (q + k < cnt) ? q + k : cnt - 1;
         const unsigned jr = (unsigned)s_j[w][qc], pr = (unsigned)s_p[w][qc];
-        wf[k] = ld_pinned4(wf_v + (size_t)pr * Fu);
-        wg[k] = ld_pinned4(wg_v + (size_t)pr * Fu);
-        kf[k] = ld_pinned4(kf_v + (size_t)jr * F5);
-        kg[k] = ld_pinned4(kg_v + (size_t)jr * F5);
-        vv[k] = ld_pinned4(vv_v + (size_t)jr * F5);
+        const unsigned long long pw = (int)jr < i ? wpol.first : wpol.normal;      // second reader of the pair's rows
+        wf[k] = ld_w4<WP>(wf_v + (size_t)pr * Fu, pw);
+        wg[k] = ld_w4<WP>(wg_v + (size_t)pr * Fu, pw);
+        kf[k] = ld_row4<WP>(kf_v + (size_t)jr * F5, wpol.last);
+        kg[k] = ld_row4<WP>(kg_v + (size_t)jr * F5, wpol.last);
+        vv[k] = ld_row4<WP>(vv_v + (size_t)jr * F5, wpol.last);
         if (TAIL) {
-          wft[k] = ld_pinned(wf_t + (size_t)pr * Fu);
-          wgt[k] = ld_pinned(wg_t + (size_t)pr * Fu);
-          kft[k] = ld_pinned(kf_t + (size_t)jr * F5);
-          kgt[k] = ld_pinned(kg_t + (size_t)jr * F5);
-          vvt[k] = ld_pinned(vv_t + (size_t)jr * F5);
+          wft[k] = ld_w<WP>(wf_t + (size_t)pr * Fu, pw);
+          wgt[k] = ld_w<WP>(wg_t + (size_t)pr * Fu, pw);
+          kft[k] = ld_row<WP>(kf_t + (size_t)jr * F5, wpol.last);
+          kgt[k] = ld_row<WP>(kg_t + (size_t)jr * F5, wpol.last);
+          vvt[k] = ld_row<WP>(vv_t + (size_t)jr * F5, wpol.last);
         }
       }
 #pragma unroll
@@ -609,7 +690,7 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 // which the tensor-core kernel of backward part 2 then reads as a contiguous tile.
 // Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics.
 template <int TN>                               // TN = ceil(F / 32): feature slots per lane
-__global__ void __launch_bounds__(WPB * 32)
+__global__ void __launch_bounds__(WPB * 32, 2)
 k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                 const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom,
                 const float* __restrict__ proj, const float* __restrict__ alpha, const float* __restrict__ alphabar,
@@ -631,6 +712,8 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
   const float inv = 1.0f / sqrtf((float)(F / heads));
   wst += blk * blk_stride;
   wbar += blk * blk_stride;
+  constexpr int WP = SO3K_QK_W_POLICY;
+  const WPolicy wpol = make_w_policy<WP>();
   float aq[TN], ak[TN], qi[TN], ki[TN];
   int hf[TN];
 #pragma unroll
@@ -673,13 +756,14 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
         pp[k] = s_p[w][qc];
         const float* pj = proj + (size_t)s_j[w][qc] * F5;
         const float* pw = wst + (size_t)(pp[k] & 0x7fffffff) * F;
+        const unsigned long long pol = pp[k] < 0 ? wpol.normal : wpol.first;      // canonical edge = first reader
 #pragma unroll
         for (int t = 0; t < TN; ++t) {
           const int f = lane + 32 * t;
           const bool ok = (t + 1 < TN) || f < F;
-          wv[k][t] = ok ? ld_pinned(pw + f) : 0.f;
-          kj[k][t] = ok ? ld_pinned(pj + koff + f) : 0.f;
-          qj[k][t] = ok ? ld_pinned(pj + qoff + f) : 0.f;
+          wv[k][t] = ok ? ld_w<WP>(pw + f, pol) : 0.f;
+          kj[k][t] = ok ? ld_row<WP>(pj + koff + f, wpol.last) : 0.f;
+          qj[k][t] = ok ? ld_row<WP>(pj + qoff + f, wpol.last) : 0.f;
         }
       }
     };
