@@ -15,7 +15,14 @@
 
 namespace {
 
-constexpr int WPB = 8;          // warps (rows) per block
+// Warps (receiver rows) per block.  Small blocks + explicit minimum-blocks bounds set the occupancy of the three streaming
+// kernels (c4, ms per step, profiles/r03d_ab_stream_policies.txt): 8 warps -> 4: k_alpha_bwd 3.18 -> 2.56 (80 registers,
+// 24 resident warps), -> 2.38 at 63 registers / 32 warps; k_alpha_aggregate_scan 6.49 -> 6.05 at 96 registers / 20 warps;
+// k_qk_bwd_stream 7.49 -> 7.05 single-buffered at 96 registers / 20 warps (it spills below that).
+#ifndef SO3K_AGG_WPB
+#define SO3K_AGG_WPB 4
+#endif
+constexpr int WPB = SO3K_AGG_WPB;   // warps (rows) per block
 constexpr int AMAX = 16;        // H + nl <= AMAX (stride in the alpha arrays is a multiple of 4)
 
 // Head partial of feature slot t (features 32 t + lane) when the head width DHC is a compile-time constant >= 32: a
@@ -433,7 +440,7 @@ static bool so3k_scan_ok(int F, int heads) {
 
 // k_alpha_aggregate, fast variant (see there for the math)
 #ifndef SO3K_AGG_MINB
-#define SO3K_AGG_MINB 2
+#define SO3K_AGG_MINB (20 / WPB)      /* 20 resident warps per SM at <= 96 registers */
 #endif
 #ifndef SO3K_AGG_EPB
 #define SO3K_AGG_EPB 2
@@ -564,8 +571,17 @@ k_alpha_aggregate_scan(So3kDims D, int N, int Ast, const int* __restrict__ rowpt
 // gproj[i].v[f]     = sum_{e in row i} alpha_fb[rev e][h(f)] xbar1[col e][f]        (= d/dv_i, sender-indexed sum)
 // EP = 16 / HP edges per iteration: their EP * HP per-lane head partials are reduced over the warp with ONE halving
 // butterfly (16 shuffles for all of them instead of 5 per value).
+#ifndef SO3K_ABWD_MINB
+#define SO3K_ABWD_MINB (TN <= 5 ? 32 / WPB : 16 / WPB)     /* 63 registers hold up to 5 feature slots per lane */
+#endif
+#ifndef SO3K_QK_SINGLE
+#define SO3K_QK_SINGLE 1
+#endif
+#ifndef SO3K_QK_MINB
+#define SO3K_QK_MINB (SO3K_QK_SINGLE ? 20 / WPB : 16 / WPB)
+#endif
 template <int TN, int HP, int DHC>              // TN = ceil(F / 32) ; HP = heads padded to 4 or 8 ; DHC = compile-time
-__global__ void __launch_bounds__(WPB * 32)     // head width F/H (0: run-time)
+__global__ void __launch_bounds__(WPB * 32, SO3K_ABWD_MINB)     // head width F/H (0: run-time)
 k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
             const int* __restrict__ rev, const float4* __restrict__ geom, const float* __restrict__ proj,
             const float* __restrict__ alpha, const float* __restrict__ xbar1, const float* __restrict__ chibar1,
@@ -690,7 +706,7 @@ k_alpha_bwd(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const in
 // which the tensor-core kernel of backward part 2 then reads as a contiguous tile.
 // Pure streaming: F floats of filter per edge and block, 2F floats of sender q/k rows (L2), no atomics.
 template <int TN>                               // TN = ceil(F / 32): feature slots per lane
-__global__ void __launch_bounds__(WPB * 32, 2)
+__global__ void __launch_bounds__(WPB * 32, SO3K_QK_MINB)
 k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, const int* __restrict__ col,
                 const int* __restrict__ rev, const int* __restrict__ pid, const float4* __restrict__ geom,
                 const float* __restrict__ proj, const float* __restrict__ alpha, const float* __restrict__ alphabar,
@@ -746,9 +762,11 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       }
     }
     __syncwarp();
-    // Two edges per batch, two batches in flight: the 6 * TN row loads of the NEXT batch are issued before the current
-    // one is consumed (explicit double buffering -- left to itself ptxas sinks the loads towards their first use and
-    // the kernel becomes latency-bound).  Indices beyond the chunk are clamped (valid addresses), their terms masked.
+    // Two edges per batch; the 6 * TN row loads of a batch are pinned (asm volatile) ahead of its first use -- left to
+    // itself ptxas sinks the loads towards their first use and the kernel becomes latency-bound.  SO3K_QK_SINGLE = 0 keeps
+    // two batches in flight per warp (explicit double buffering, 128 registers, 16 resident warps); the default issues one
+    // batch at a time at 96 registers and lets 20 resident warps cover the latency (7.24 -> 7.05 ms per c4 step).
+    // Indices beyond the chunk are clamped (valid addresses), their terms masked.
     auto load_batch = [&](int q, float (&wv)[2][TN], float (&kj)[2][TN], float (&qj)[2][TN], int (&pp)[2]) {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -788,6 +806,14 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
         }
       }
     };
+#if SO3K_QK_SINGLE
+    float wA[2][TN], kA[2][TN], qA[2][TN];
+    int pA[2];
+    for (int q = 0; q < cnt; q += 2) {
+      load_batch(q, wA, kA, qA, pA);
+      use_batch(q, wA, kA, qA, pA);
+    }
+#else
     float wA[2][TN], kA[2][TN], qA[2][TN], wB[2][TN], kB[2][TN], qB[2][TN];
     int pA[2], pB[2];
     load_batch(0, wA, kA, qA, pA);
@@ -797,6 +823,7 @@ k_qk_bwd_stream(So3kDims D, int N, int Ast, const int* __restrict__ rowptr, cons
       load_batch(q + 4, wA, kA, qA, pA);
       use_batch(q + 2, wB, kB, qB, pB);
     }
+#endif
     __syncwarp();
   }
   if (rowok) {

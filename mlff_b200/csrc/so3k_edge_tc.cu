@@ -142,11 +142,10 @@ void so3k_launch_pair_records(const So3kDims& D, const Graph& g, const float* ch
 
 namespace {
 
-constexpr int NT = 512;        // threads per CTA (16 warps: 4 TMEM lane quadrants x 4 column groups)
+constexpr int NT = 512;        // threads per CTA of k_tc_gemm (the pair kernels: F_NT, B2_NT = 640)
 constexpr int TM = 128;        // pairs per tile
 // The thread that issues the MMAs: lane 0 of warp 12 = lane quadrant 0, column group 3 -- the column group with the
 // fewest hidden-unit k-steps (KC / 16 = 11 -> 3, 3, 3, 2), so the issue work rides on the least loaded warp.
-constexpr int ISSUER = 12 * 32;
 
 struct TcDims {
   int Fp, KC, K0;              // padded N, padded K of GEMM2 (hidden units), K of GEMM1
@@ -186,7 +185,7 @@ __host__ __device__ inline TcDims make_tc_dims(const So3kDims& D) {
   t.b_A0 = t.w_bytes;
   t.b_Wb = t.b_A0 + 2 * t.szA0;
   t.b_red = t.b_Wb + 2 * t.szWb;
-  t.b_small = t.b_red + 3u * (uint32_t)(D.nl + 1) * TM * 4u;
+  t.b_small = t.b_red + 3u * (uint32_t)(D.nl + 1) * TM * 4u;      // column groups 1 .. 3 (group 0 is the writer)
   t.b_total = t.b_small + small_b;
   return t;
 }
@@ -289,8 +288,8 @@ __device__ __forceinline__ void tc_setup(unsigned char* smem, const TcDims& T, c
   const uint4* src = reinterpret_cast<const uint4*>(img);
   uint4* dst = reinterpret_cast<uint4*>(smem);
   const int n16 = (int)(T.w_bytes / 16);
-  for (int k = threadIdx.x; k < n16; k += NT) dst[k] = src[k];
-  for (int k = threadIdx.x; k < T.n_small; k += NT) S.b1x[k] = small_g[k];
+  for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = src[k];
+  for (int k = threadIdx.x; k < T.n_small; k += blockDim.x) S.b1x[k] = small_g[k];
 }
 
 // D[128 x N] (+)= A[128 x 16*ksteps] @ B^T, both operands K-major in shared memory; 3 MMAs per K step
@@ -331,7 +330,7 @@ __device__ unsigned long long g_tc_phase[3][16];
 #ifndef TC_TIMING
 #define TC_TIMING 0
 #endif
-constexpr int TC_TIMER = 13 * 32;   // the timed thread: lane 0 of a helper warp that does not issue MMAs
+constexpr int TC_TIMER = 17 * 32;   // the timed thread: lane 0 of a helper warp (both kernels) that does not issue MMAs
 #define TC_PHASE(kern, idx)                                                        \
   if (TC_TIMING && blockIdx.x == 0 && threadIdx.x == TC_TIMER) {                   \
     const long long now_ = clock64();                                              \
@@ -457,8 +456,8 @@ __device__ __forceinline__ void tc_preact16(const TcW& S, int KC, int F, int c0,
 // row-per-lane stores conflict-free), three 16-column units per tensor-memory wait, starting at unit u0.
 // (Spreading this drain over all 16 warps was measured: 3.97 ms per step against 3.75 ms with the helper warps alone --
 // the epilogue-1 warps are the critical resource, every tensor-memory load they add lengthens the tile.)
-__device__ __forceinline__ void f_drain_d2(const TcDims& T, const TcW& S, int F, uint32_t tD2_lane, int u0, float* srow) {
-  const int nu = T.Fp >> 4;
+__device__ __forceinline__ void f_drain_d2(const TcDims& T, const TcW& S, int F, uint32_t tD2_lane, int u0, int nu,
+                                           float* srow) {       // units u0 .. min(u0 + 3, nu) - 1
   uint32_t v[3][16];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -483,22 +482,33 @@ __device__ __forceinline__ void f_drain_d2(const TcDims& T, const TcW& S, int F,
 }
 
 #define TILE_E0(i) (((int)blockIdx.x + (i) * G) * TM)
-constexpr int N_EPI = 12 * 32;     // epilogue group: warps 0..11 = 4 TMEM lane quadrants x 3 column groups
-constexpr int N_AUX = 4 * 32;      // helper group: warps 12..15, one per lane quadrant; lane 0 of warp 12 issues the MMAs
+constexpr int N_AUX = 4 * 32;      // one helper group: a warp per TMEM lane quadrant; lane 0 of the first helper warp issues the MMAs
 
 // Filter kernel: w[c][f] of one filter block for every canonical pair c.  Warp-specialised, tiles of this CTA
 // i = 0, 1, .. (global tile blockIdx.x + i * gridDim.x), two hidden-layer buffers D1[2] and one output accumulator D2:
-//   epilogue group (12 warps), tile j:   wait GEMM1(j) | radial-basis image of tile j+2 into A0[j & 1] -> arrive a0_ready |
+//   epilogue group (F_EPI = 12 warps), tile j:   wait GEMM1(j) | radial-basis image of tile j+2 into A0[j & 1] -> arrive a0_ready |
 //                                        epilogue 1 in place on D1[j & 1] -> arrive a1_ready[j & 1]
-//   helper group (4 warps), step i:      wait a0_ready(i+2) -> issue GEMM1(i+2)
+//   helper groups (F_HG x 4 warps), step i:      wait a0_ready(i+2) -> issue GEMM1(i+2)
 //                                        wait GEMM2(i) | epilogue 2 (i) -> staging tile -> bulk store (i)
 //                                        wait a1_ready(i+1) -> issue GEMM2(i+1)
-// (the helper warps are latency-bound -- one warp per scheduler --, so they only keep what must be serial: MMA issue and
-// the drain of D2)
+// (the helper warps only keep what must be serial: MMA issue and the drain of D2.  Two helper groups split the drain by
+// column ranges: 3.94 -> 3.69 ms per c4 step; a 16-warp epilogue group or a third helper group did not pay at 96 / 80
+// registers per thread: profiles/r03d_ab_tensor_groups.txt)
 // The tensor pipe executes MMAs in issue order: GEMM1(i+2) (which overwrites D1[i & 1]) is issued after GEMM2(i)
 // (which reads it), GEMM2(i+1) after epilogue 2 (i) has drained D2.
+// Group sizes of the filter kernel: F_EPI epilogue warps (4 lane quadrants x F_CG column groups) + 4 F_HG helper warps
+// (F_HG groups of one warp per lane quadrant share the drain of D2 by column ranges).
+#ifndef SO3K_F_EPI
+#define SO3K_F_EPI 12
+#endif
+#ifndef SO3K_F_HG
+#define SO3K_F_HG 2
+#endif
+constexpr int F_EPI = SO3K_F_EPI, F_CG = F_EPI / 4, F_NEPI = F_EPI * 32, F_HG = SO3K_F_HG, F_NAUX = F_HG * 128,
+              F_NT = F_NEPI + F_NAUX, F_ITS = (12 + F_CG - 1) / F_CG;
+static_assert((F_EPI == 12 || F_EPI == 16) && F_HG >= 1 && F_HG <= 3, "group sizes");
 template <int NL>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(F_NT, 1)
 k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon, const float* __restrict__ rec,
             const unsigned char* __restrict__ img, const float* __restrict__ small_g, float* __restrict__ wst,
             int* __restrict__ status) {
@@ -519,10 +529,10 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
     tc::mbar_init(&bars[2], 1);
-    tc::mbar_init(&bars[3], N_EPI);
-    tc::mbar_init(&bars[4], N_EPI);
-    tc::mbar_init(&bars[5], N_EPI);
-    tc::mbar_init(&bars[6], N_EPI);
+    tc::mbar_init(&bars[3], F_NEPI);
+    tc::mbar_init(&bars[4], F_NEPI);
+    tc::mbar_init(&bars[5], F_NEPI);
+    tc::mbar_init(&bars[6], F_NEPI);
     tc::mbar_fence_init();
     s_abort = 0;
   }
@@ -541,14 +551,14 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
   const int G = (int)gridDim.x;
 #define TD1(buf) (tmem + (uint32_t)((buf) & 1) * (uint32_t)T.KC)
 
-  if (warp < 12) {
+  if (warp < F_EPI) {
     // ================= epilogue group: hidden activations, in place in tensor memory ===========================
-    const int cq = warp >> 2;                         // k-steps cq, cq + 3, cq + 6, cq + 9
+    const int cq = warp >> 2;                         // k-steps cq, cq + F_CG, cq + 2 F_CG, ..
     const int nks = T.KC >> 4;
     // radial-basis image of tile t (this thread: chunks cq, cq + 3, .. of its row) into buffer t & 1
     auto image = [&](int t, float d) {
       unsigned char* hi = A0base + (size_t)(t & 1) * 2 * T.szA0;
-      tc_row_s0<false>(D, T, hi, hi + T.szA0, r, TILE_E0(t) + r < nv, d, 0u, cq, 3);
+      tc_row_s0<false>(D, T, hi, hi + T.szA0, r, TILE_E0(t) + r < nv, d, 0u, cq, F_CG);
       tc::fence_async_smem();
       mbar_arrive(&bars[5 + (t & 1)]);
     };
@@ -573,14 +583,14 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
       uint32_t v[2][16];
       if (cq < nks && 16 * cq < F) tc::tmem_ld16(tD + (uint32_t)(16 * cq), v[0]);
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int ks = cq + 3 * it;
-        const int ksn = ks + 3;
-        if (it < 3 && ksn < nks && 16 * ksn < F) tc::tmem_ld16(tD + (uint32_t)(16 * ksn), v[(it + 1) & 1]);
+      for (int it = 0; it < F_ITS; ++it) {
+        const int ks = cq + F_CG * it;
+        const int ksn = ks + F_CG;
+        if (it < F_ITS - 1 && ksn < nks && 16 * ksn < F) tc::tmem_ld16(tD + (uint32_t)(16 * ksn), v[(it + 1) & 1]);
         if (ks < nks) {                               // warp-uniform
           const int c0 = 16 * ks;
           // the load of THIS unit was issued one step ago; the one just issued stays in flight while we compute
-          if (it < 3 && ksn < nks && 16 * ksn < F) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (it < F_ITS - 1 && ksn < nks && 16 * ksn < F) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           else tc::tmem_ld_wait();
           float a[16];
           tc_preact16<NL>(S, T.KC, F, c0, v[it & 1], rc.g, a);
@@ -604,7 +614,10 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
     }
   } else {
     // ================= helper group: radial-basis images, MMA issue, epilogue 2 + bulk store ====================
-    const bool issuer = tid == ISSUER;
+    const bool issuer = tid == F_NEPI;
+    const int hg = (warp - F_EPI) >> 2;               // helper group of this warp: its share of the D2 columns
+    const int nu2 = T.Fp >> 4, upg = (nu2 + F_HG - 1) / F_HG;
+    const int ua = hg * upg, ub = (ua + upg < nu2) ? ua + upg : nu2;
     for (int i = -2; i < n_my; ++i) {
       const bool has0 = i >= 0, has1 = i + 1 >= 0 && i + 1 < n_my, has2 = i + 2 < n_my;
       long long t_prev_ = TC_TIMING ? clock64() : 0;
@@ -626,14 +639,14 @@ k_filter_tc(So3kDims D, TcDims T, int pair_cap, const int* __restrict__ n_canon,
         TC_PHASE(0, 2);
         // the previous tile's bulk store must have finished READING the staging tile
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        group_bar(1, N_AUX);
+        group_bar(1, F_NAUX);
 #pragma unroll
-        for (int u0 = 0; u0 < 12; u0 += 3)                           // Fp <= 160: at most 10 units
-          if (u0 < (T.Fp >> 4)) f_drain_d2(T, S, F, tD2 + lane_sel, u0, stage + (size_t)r * F);
+        for (int k3 = 0; k3 < 12; k3 += 3)                           // Fp <= 160: at most 10 units
+          if (ua + k3 < ub) f_drain_d2(T, S, F, tD2 + lane_sel, ua + k3, ub, stage + (size_t)r * F);
         TC_PHASE(0, 3);
         tc::fence_async_smem();                  // staging tile (generic proxy) -> visible to the bulk-copy engine
         tc::fence_before_sync();
-        group_bar(1, N_AUX);
+        group_bar(1, F_NAUX);
         if (issuer) {
           const int e0 = TILE_E0(i);
           const int ne = (nv - e0) < TM ? (nv - e0) : TM;
@@ -723,20 +736,27 @@ __device__ __forceinline__ void tc_wbar_image(const TcDims& T, int F, int ld, in
 // hbar and a1 (20 loads), writes u back (tcgen05.st is 4x faster) and reads 32 columns of rbfbar.
 // Tensor-memory columns: a1 at 0 (N = Fp) | hbar / u at Fp (N = KC) | rbfbar at Fp + KC (N = K0).
 // Warp-specialised:
-//   epilogue group (12 warps), tile i:  phase 1: per 16-column unit wait its GEMM3 chunk | u | tcgen05.st -> arrive u_ready
+//   epilogue group (B2_EPI = 16 warps: 4 lane quadrants x 4 column groups; 12 warps: 8.39 -> 7.62 ms per c4 step), tile i:
+//                                       phase 1: per 16-column unit wait its GEMM3 chunk | u | tcgen05.st -> arrive u_ready
 //                                       operand image of the cotangents of tile i+1 (under GEMM4) -> arrive image_ready
 //                                       phase 2: wait GEMM4 | rbfbar . rbf' | slots -> group barrier -> totals to the
 //                                       canonical edge
 //   helper group (4 warps), tile i:     wait u_ready(i-1) -> issue GEMM4(i-1), GEMM1(i) | wait image_ready(i) -> issue
 //                                       GEMM3(i) | wait GEMM1(i) | radial-basis image of tile i+1
+// Group sizes of backward part 2: B2_EPI epilogue warps (4 lane quadrants x B2_CG column groups) + 4 helper warps.
+#ifndef SO3K_B2_EPI
+#define SO3K_B2_EPI 16
+#endif
+constexpr int B2_EPI = SO3K_B2_EPI, B2_CG = B2_EPI / 4, B2_NEPI = B2_EPI * 32, B2_NT = B2_NEPI + N_AUX;
+static_assert(B2_EPI == 12 || B2_EPI == 16, "3 or 4 column groups");
 template <int NL>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(B2_NT, 1)
 k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, const int* __restrict__ n_canon,
                const int* __restrict__ canon, const float* __restrict__ rec, const unsigned char* __restrict__ img,
                const float* __restrict__ small_g, const float* __restrict__ wbar, int wbar_ld, float* __restrict__ gbar,
                float* __restrict__ ebar, int* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t bars[7];                  // 0: GEMM1 ; 1..3: GEMM3 chunks ; 4: u_ready (N_EPI) ; 5: image_ready (N_EPI) ; 6: GEMM4
+  __shared__ uint64_t bars[7];                  // 0: GEMM1 ; 1..3: GEMM3 chunks ; 4: u_ready (B2_NEPI) ; 5: image_ready (B2_NEPI) ; 6: GEMM4
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int s_abort;
 
@@ -748,13 +768,13 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   unsigned char* A0lo = A0hi + T.szA0;
   unsigned char* Wbhi = smem + T.b_Wb;
   unsigned char* Wblo = Wbhi + T.szWb;
-  float* s_red = reinterpret_cast<float*>(smem + T.b_red);        // [3 column groups][NL + 1][TM]
+  float* s_red = reinterpret_cast<float*>(smem + T.b_red);        // [column groups 1 .. B2_CG - 1][NL + 1][TM]
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int k = 0; k < 4; ++k) tc::mbar_init(&bars[k], 1);
-    tc::mbar_init(&bars[4], N_EPI);
-    tc::mbar_init(&bars[5], N_EPI);
+    tc::mbar_init(&bars[4], B2_NEPI);
+    tc::mbar_init(&bars[5], B2_NEPI);
     tc::mbar_init(&bars[6], 1);
     tc::mbar_fence_init();
     s_abort = 0;
@@ -774,12 +794,12 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
   const int nks = T.KC >> 4;                                       // 16-wide hidden-column units; chunk ch = units 4ch .. 4ch+3
   const int nch = (nks + 3) >> 2;
 
-  if (warp < 12) {
+  if (warp < B2_EPI) {
     // ================= epilogue group ==============================================================================
-    const int cq = warp >> 2;                                      // units cq, cq + 3, cq + 6, cq + 9
-    auto wbar_image = [&](int t) {                                 // 16 * ceil(Fp / 32) = 80 items over 12 warps: one batch of 7
+    const int cq = warp >> 2;                                      // units cq, cq + B2_CG, cq + 2 B2_CG, ..
+    auto wbar_image = [&](int t) {                                 // 16 * ceil(Fp / 32) = 80 items over the group's warps: one batch
       const int e1 = TILE_E0(t);
-      tc_wbar_image<7>(T, F, wbar_ld, warp, 12, lane, e1, (nv - e1) < TM ? (nv - e1) : TM, wbar, Wbhi, Wblo);
+      tc_wbar_image<(80 + B2_EPI - 1) / B2_EPI>(T, F, wbar_ld, warp, B2_EPI, lane, e1, (nv - e1) < TM ? (nv - e1) : TM, wbar, Wbhi, Wblo);
       tc::fence_async_smem();
       mbar_arrive(&bars[5]);
     };
@@ -813,9 +833,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         tq_ = now_;
       }
       // ---- phase 1: u = hbar silu'(a), radial part written back in place as the A operand of GEMM4 --------------------------
-      for (int it = 0; it < 4; ++it) {
-        const int u = cq + 3 * it;
-        if (u >= nks) break;                                       // warp-uniform
+      for (int u = cq; u < nks; u += B2_CG) {                      // warp-uniform
         tc_wait(&bars[1 + (u >> 2)], par, &s_abort);
         tc::fence_after_sync();
         const int c0 = 16 * u;
@@ -886,7 +904,7 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
       {
         const float ed = __expf(-rc.d);
         const float ng = -D.gamma * 1.4426950408889634f;
-        for (int ku = cq; 16 * ku < T.K0; ku += 3) {
+        for (int ku = cq; 16 * ku < T.K0; ku += B2_CG) {
           uint32_t rb[16];
           tc::tmem_ld16(tD4 + lane_sel + (uint32_t)(16 * ku), rb);
           tc::tmem_ld_wait();
@@ -899,31 +917,37 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         }
       }
       // cross-group combination through shared memory (lanes = consecutive rows: conflict-free)
-      {
-        float* slot = s_red + (size_t)cq * (NL + 1) * TM + r;
+      if (cq > 0) {
+        float* slot = s_red + (size_t)(cq - 1) * (NL + 1) * TM + r;
         slot[0] = dbar;
 #pragma unroll
         for (int l = 0; l < NL; ++l) slot[(1 + l) * TM] = gb[l];
       }
       tc::fence_before_sync();
-      group_bar(2, N_EPI);
+      group_bar(2, B2_NEPI);
       if (writer) {
         // the pair's totals go to the canonical edge; its reverse keeps the zeros of the memset (only the sums
         // ebar[e] + ebar[rev e], gbar[e] + gbar[rev e] enter chi-bar and the forces).  One writer per slot and launch:
         // the first block's launch stores, the second one adds what it loaded above (no atomics).
         const int st = (NL + 1) * TM;
-        ebar[2 * e] = old[0] + s_red[r] + s_red[st + r] + s_red[2 * st + r];
+        float tot = old[0] + dbar;                                 // the writer is column group 0: its own partials
+#pragma unroll
+        for (int c = 0; c + 1 < B2_CG; ++c) tot += s_red[c * st + r];
+        ebar[2 * e] = tot;
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
           const int o = (1 + l) * TM + r;
-          if (l < D.nl) gbar[e * Gst + l] = old[1 + l] + s_red[o] + s_red[st + o] + s_red[2 * st + o];
+          float tg = old[1 + l] + gb[l];
+#pragma unroll
+          for (int c = 0; c + 1 < B2_CG; ++c) tg += s_red[c * st + o];
+          if (l < D.nl) gbar[e * Gst + l] = tg;
         }
       }
       if (TC_TIMING && blockIdx.x == 0 && tid == 0) atomicAdd(&g_tc_phase[2][11], (unsigned long long)(clock64() - tq_));
     }
   } else {
     // ================= helper group ================================================================================
-    const bool issuer = tid == ISSUER;
+    const bool issuer = tid == B2_NEPI;
     const uint32_t idesc1 = tc::make_idesc_bf16(TM, T.Fp, 0, 0);
     const uint32_t idesc4 = tc::make_idesc_bf16(TM, T.K0, 0, 1);   // B = W1 image read MN-major
     auto prefetch_wbar = [&](int e0) {                             // a tile's contiguous block of filter cotangents -> L2
@@ -932,10 +956,10 @@ k_edge_bwd2_tc(So3kDims D, TcDims T, int Gst, int pair_cap, int accumulate, cons
         if (wbar_ld == F) {                                          // the tile is one contiguous block
           const char* pb = reinterpret_cast<const char*>(wbar + (size_t)e0 * F);
           const int nline = (nrow * F * 4 + 127) / 128;
-          for (int k = tid - 12 * 32; k < nline; k += N_AUX) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)k * 128));
+          for (int k = tid - B2_NEPI; k < nline; k += N_AUX) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)k * 128));
         } else {                                                     // a column slice of wider rows (wide models)
           const int lpr = (F * 4 + 127) / 128;
-          for (int k = tid - 12 * 32; k < nrow * lpr; k += N_AUX)
+          for (int k = tid - B2_NEPI; k < nrow * lpr; k += N_AUX)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wbar + (size_t)(e0 + k / lpr) * wbar_ld) +
                                                          (size_t)(k % lpr) * 128));
         }
@@ -1071,7 +1095,7 @@ static void tc_filter_block(const So3kDims& D, const Graph& g, const unsigned ch
 #define SO3K_FILTER_CASE(NL_)                                                                                   \
   case NL_:                                                                                                     \
     cudaFuncSetAttribute(k_filter_tc<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    k_filter_tc<NL_><<<grid, NT, smem, st>>>(D, T, pair_cap, g.n_canon, rec, img, bias, out, status);           \
+    k_filter_tc<NL_><<<grid, F_NT, smem, st>>>(D, T, pair_cap, g.n_canon, rec, img, bias, out, status);           \
     break;
   switch (D.nl) {                       // number of degrees = K of the spherical first layer, a compile-time constant
     SO3K_FILTER_CASE(1) SO3K_FILTER_CASE(2) SO3K_FILTER_CASE(3) SO3K_FILTER_CASE(4) SO3K_FILTER_CASE(5)
@@ -1094,7 +1118,7 @@ static void tc_bwd2_block(const So3kDims& D, const Graph& g, const unsigned char
 #define SO3K_BWD2_CASE(NL_)                                                                                        \
   case NL_:                                                                                                        \
     cudaFuncSetAttribute(k_edge_bwd2_tc<NL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
-    k_edge_bwd2_tc<NL_><<<grid, NT, smem, st>>>(D, T, Gst, pair_cap, accumulate, g.n_canon, g.canon, rec, img, bias, \
+    k_edge_bwd2_tc<NL_><<<grid, B2_NT, smem, st>>>(D, T, Gst, pair_cap, accumulate, g.n_canon, g.canon, rec, img, bias, \
                                                 wbar, ld, gbar, ebar, status);                                     \
     break;
   switch (D.nl) {
