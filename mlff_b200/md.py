@@ -105,6 +105,28 @@ class AtomsX:
         dof = 3 * n - 6 if eckart_frame else 3 * n
         return 2.0 * self.get_kinetic_energy() / dof
 
+    def get_center_of_mass(self):
+        """mlff/mdx/atoms.py:385-400 (Cartesian; periodic boundary conditions ignored)."""
+        return (self.masses[:, None] * self.positions).sum(0) / self.masses.sum()
+
+    def get_center_of_mass_velocity(self):
+        """mlff/mdx/atoms.py:420-428."""
+        return self.momenta.sum(0) / self.masses.sum()
+
+    def get_angular_momentum(self):
+        """Total angular momentum about the centre of mass, mlff/mdx/atoms.py:430-441."""
+        return torch.linalg.cross(self.positions - self.get_center_of_mass(), self.momenta).sum(0)
+
+    def get_moments_of_inertia(self, vectors: bool = False):
+        """Principal moments of the inertia tensor about the centre of mass (ascending) and, with vectors=True, the
+        principal axes as ROWS -- mlff/mdx/atoms.py:248-288."""
+        r = self.positions - self.get_center_of_mass()
+        m = self.masses
+        eye = torch.eye(3, dtype=r.dtype, device=r.device)
+        inertia = (m * (r * r).sum(-1)).sum() * eye - torch.einsum('a,ai,aj->ij', m, r, r)
+        evals, evecs = torch.linalg.eigh(inertia)
+        return (evals, evecs.T) if vectors else evals
+
     def update_positions(self, positions: torch.Tensor, update_neighbors: bool = True) -> 'AtomsX':
         if update_neighbors:
             if self.neighbors is None:
@@ -352,6 +374,31 @@ class BerendsenX:
         properties = self.calculator(atoms)
         atoms = atoms.update_momenta(p + 0.5 * self.timestep * properties['forces'])
         return self, atoms, properties
+
+
+def scale_momenta(atoms: AtomsX, T0) -> AtomsX:
+    """Uniform rescaling of the momenta to the temperature T0 (eV) -- mlff/mdx/utils.py:70-83."""
+    return atoms.update_momenta(torch.sqrt(T0 / atoms.get_temperature()) * atoms.get_momenta())
+
+
+def zero_translation(atoms: AtomsX, preserve_temperature: bool = True) -> AtomsX:
+    """Remove the centre-of-mass motion: every atom loses the SAME velocity p_tot / m_tot -- mlff/mdx/utils.py:39-67."""
+    T0 = atoms.get_temperature()
+    atoms = atoms.update_velocities(atoms.get_velocities() - atoms.get_center_of_mass_velocity())
+    return scale_momenta(atoms, T0) if preserve_temperature else atoms
+
+
+def zero_rotation(atoms: AtomsX, preserve_temperature: bool = True) -> AtomsX:
+    """Remove the rigid rotation that carries the total angular momentum: omega from L in the principal-axes frame
+    (vanishing moments skipped), v <- v - omega x (r - r_com) -- mlff/mdx/utils.py:6-36."""
+    T0 = atoms.get_temperature()
+    Ip, basis = atoms.get_moments_of_inertia(vectors=True)
+    Lp = basis @ atoms.get_angular_momentum()
+    omega_p = torch.where(Ip > 0, Lp / torch.where(Ip > 0, Ip, torch.ones_like(Ip)), torch.zeros_like(Ip))
+    omega = torch.linalg.solve(basis, omega_p)
+    r = atoms.get_positions() - atoms.get_center_of_mass()
+    atoms = atoms.update_velocities(atoms.get_velocities() - torch.linalg.cross(omega.expand_as(r), r))
+    return scale_momenta(atoms, T0) if preserve_temperature else atoms
 
 
 def simulate(integrator, atoms: AtomsX, steps: int):

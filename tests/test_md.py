@@ -384,3 +384,64 @@ def test_langevin_update_matches_reference_source(monkeypatch):
         integrator, atoms, prop = integrator.step(atoms)
         np.testing.assert_allclose(atoms.get_positions().numpy(), g['langevin/R'][k], rtol=1e-12, atol=1e-13, err_msg=str(k))
         np.testing.assert_allclose(atoms.get_momenta().numpy(), g['langevin/p'][k], rtol=1e-12, atol=1e-13, err_msg=str(k))
+
+
+# ---- momentum utilities (mlff/mdx/utils.py), after the reference's tests/test_mdx_utils.py ---------------------------------
+def _utils_atoms(g, p=None):
+    return md.AtomsX(positions=torch.as_tensor(g['R']), momenta=torch.as_tensor(g['p0'] if p is None else p),
+                     masses=torch.as_tensor(g['masses']), numbers=torch.as_tensor(g['z']))
+
+
+def test_momentum_utilities_match_reference_source():
+    """zero_translation, zero_rotation, scale_momenta and the AtomsX accessors under them against values recorded from the
+    REFERENCE'S OWN code (mlff/mdx/utils.py:6-83, mlff/mdx/atoms.py:211-288, 385-441, executed by
+    tests/golden/make_reference_mdx_utils_golden.py) on the ethanol frame of the reference's test, 500 K momenta."""
+    g = golden('reference_mdx_utils.npz')
+    a0 = _utils_atoms(g)
+    tol = dict(rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(float(a0.get_temperature()), g['temperature'], **tol)
+    np.testing.assert_allclose(a0.get_center_of_mass().numpy(), g['center_of_mass'], **tol)
+    np.testing.assert_allclose(a0.get_center_of_mass_velocity().numpy(), g['center_of_mass_velocity'], **tol)
+    np.testing.assert_allclose(a0.get_angular_momentum().numpy(), g['angular_momentum'], **tol)
+    Ip, basis = a0.get_moments_of_inertia(vectors=True)
+    np.testing.assert_allclose(Ip.numpy(), g['moments_of_inertia'], rtol=1e-10)
+    np.testing.assert_allclose(a0.get_moments_of_inertia().numpy(), g['moments_of_inertia'], rtol=1e-10)
+    # principal axes: rows, defined up to a sign each
+    np.testing.assert_allclose(np.abs((basis.numpy() * g['principal_axes']).sum(1)), 1.0, rtol=1e-9)
+    cases = {'zero_translation': lambda a: md.zero_translation(a),
+             'zero_translation_keep_energy': lambda a: md.zero_translation(a, preserve_temperature=False),
+             'zero_rotation': lambda a: md.zero_rotation(a),
+             'zero_rotation_keep_energy': lambda a: md.zero_rotation(a, preserve_temperature=False),
+             'both': lambda a: md.zero_rotation(md.zero_translation(a)),
+             'scale_momenta': lambda a: md.scale_momenta(a, 300.0 * md.KB_EV)}
+    for tag, fn in cases.items():
+        a = fn(_utils_atoms(g))
+        np.testing.assert_allclose(a.get_momenta().numpy(), g[f'{tag}/p'], rtol=1e-10, atol=1e-13, err_msg=tag)
+        np.testing.assert_allclose(float(a.get_temperature()), g[f'{tag}/temperature'], rtol=1e-11, err_msg=tag)
+    np.testing.assert_allclose(a0.get_positions().numpy(), g['R'])          # the inputs are untouched
+
+
+def test_zero_rotation_and_zero_translation():
+    """The properties the reference's tests assert (tests/test_mdx_utils.py:6-88, there against ASE's Stationary /
+    ZeroRotation): no centre-of-mass velocity, no angular momentum, temperature preserved; and test_momenta_scaling."""
+    g = golden('reference_mdx_utils.npz')
+    a = _utils_atoms(g)
+    T0 = float(a.get_temperature())
+    assert np.abs(a.get_center_of_mass_velocity().numpy()).max() > 1e-4 and np.abs(a.get_angular_momentum().numpy()).max() > 1e-2
+    a = md.zero_translation(a)
+    assert np.abs(a.get_center_of_mass_velocity().numpy()).max() < 1e-12
+    assert abs(float(a.get_temperature()) - T0) < 1e-12
+    a = md.zero_rotation(a)
+    assert np.abs(a.get_angular_momentum().numpy()).max() < 1e-12
+    assert np.abs(a.get_center_of_mass_velocity().numpy()).max() < 1e-12     # a rotation about the centre of mass keeps it
+    assert abs(float(a.get_temperature()) - T0) < 1e-12
+    a = md.scale_momenta(a, 500.0 * md.KB_EV)
+    assert abs(float(a.get_temperature()) / md.KB_EV - 500.0) < 1e-9
+    # a linear molecule (one vanishing moment of inertia) is handled: that axis is skipped
+    lin = md.AtomsX(positions=torch.tensor([[0.0, 0, 0], [0, 0, 1.1], [0, 0, 2.3]], dtype=torch.float64),
+                    momenta=torch.tensor([[0.1, 0, 0], [0, 0.05, 0], [-0.1, 0.02, 0.3]], dtype=torch.float64),
+                    masses=torch.tensor([15.999, 12.011, 15.999], dtype=torch.float64), numbers=torch.tensor([8, 6, 8]))
+    out = md.zero_rotation(lin, preserve_temperature=False)
+    assert torch.isfinite(out.get_momenta()).all()
+    L = out.get_angular_momentum().numpy()
+    assert np.abs(L[:2]).max() < 1e-12
