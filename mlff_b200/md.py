@@ -349,6 +349,52 @@ class LangevinX:
         return self, atoms_displaced, properties
 
 
+class BAOABLangevinX:
+    """Langevin thermostat in the BAOAB splitting, mlff/mdx/integrator.py:162-233 (temperature in eV, gamma in 1 / ASE
+    time): half kick, half drift, Ornstein-Uhlenbeck momentum update p <- c1 p + c2 sqrt(m) xi with c1 = exp(-gamma dt),
+    c2 = sqrt(T (1 - c1^2)), optional removal of the centre-of-mass motion and of the rigid rotation (both WITHOUT
+    re-scaling the temperature), half drift, half kick with the new forces.  As in the reference (`Normal.sample` draws a
+    number per entry of the (n, 1) variance) ONE normal number per atom is shared by its three components."""
+
+    def __init__(self, timestep: float, temperature: float, calculator: CalculatorX, gamma: float = 1e-1, fixcm: bool = True,
+                 fixrot: bool = True, seed: int = 0):
+        self.timestep, self.temperature, self.gamma = float(timestep), float(temperature), float(gamma)
+        self.calculator, self.fixcm, self.fixrot = calculator, fixcm, fixrot
+        self._gen: Optional[torch.Generator] = None
+        self._seed = seed
+
+    @classmethod
+    def create(cls, timestep, temperature, calculator, gamma: float = 1e-1, fixcm: bool = True, fixrot: bool = True,
+               seed: int = 0):
+        return cls(timestep, temperature, calculator, gamma, fixcm, fixrot, seed)
+
+    def _thermostat(self, atoms: AtomsX) -> AtomsX:
+        dev = atoms.positions.device
+        if self._gen is None:
+            self._gen = torch.Generator(device=dev).manual_seed(self._seed)
+        c1 = float(np.exp(-self.gamma * self.timestep))
+        c2 = float(np.sqrt(self.temperature * (1.0 - c1 * c1)))
+        masses = atoms.get_masses()[:, None]
+        xi = torch.randn(atoms.get_number_of_atoms(), 1, generator=self._gen, dtype=masses.dtype, device=dev)
+        atoms = atoms.update_momenta(c1 * atoms.get_momenta() + c2 * torch.sqrt(masses) * xi)
+        if self.fixcm:
+            atoms = zero_translation(atoms, preserve_temperature=False)
+        if self.fixrot:
+            atoms = zero_rotation(atoms, preserve_temperature=False)
+        return atoms
+
+    def step(self, atoms: AtomsX):
+        half = 0.5 * self.timestep
+        forces = self.calculator(atoms)['forces']
+        atoms = atoms.update_momenta(atoms.get_momenta() + half * forces)
+        atoms = atoms.update_positions(atoms.get_positions() + half * atoms.get_velocities())
+        atoms = self._thermostat(atoms)
+        atoms = atoms.update_positions(atoms.get_positions() + half * atoms.get_velocities())
+        properties = self.calculator(atoms)
+        atoms = atoms.update_momenta(atoms.get_momenta() + half * properties['forces'])
+        return self, atoms, properties
+
+
 class BerendsenX:
     """Berendsen velocity-rescaling thermostat, mlff/mdx/integrator.py:237-310 (temperature in eV, timestep and
     time_constant in ASE time units; the rescaling uses AtomsX.get_temperature(), i.e. 3n - 6 degrees of freedom)."""
@@ -531,3 +577,12 @@ def maxwell_boltzmann_momenta(masses: torch.Tensor, temperature_K: float, seed: 
     xi = torch.randn(masses.shape[0], 3, generator=g, dtype=torch.float64).to(masses.device)
     p = xi * torch.sqrt(masses * KB_EV * temperature_K)[:, None]
     return p - p.mean(0, keepdim=True)
+
+
+def maxwell_boltzmann(masses: torch.Tensor, T0: float, seed: int = 0) -> torch.Tensor:
+    """Momenta following the Maxwell-Boltzmann distribution at temperature T0 in eV: p = xi sqrt(m T0), xi ~ N(0, 1) --
+    mlff/mdx/distributions.py:5-20 (there with a jax PRNG key; here a seeded torch generator -- the streams differ, the
+    distribution does not; no centre-of-mass correction, as in the reference)."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    xi = torch.randn(masses.shape[0], 3, generator=g, dtype=torch.float64).to(masses.device)
+    return xi * torch.sqrt(masses.to(torch.float64) * T0)[:, None]

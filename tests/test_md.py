@@ -445,3 +445,53 @@ def test_zero_rotation_and_zero_translation():
     assert torch.isfinite(out.get_momenta()).all()
     L = out.get_angular_momentum().numpy()
     assert np.abs(L[:2]).max() < 1e-12
+
+
+@pytest.mark.parametrize('tag', ['baoab', 'baoab_free'])
+def test_baoab_langevin_matches_reference_source(monkeypatch, tag):
+    """BAOABLangevinX (mlff/mdx/integrator.py:162-233) executed from the reference's source on the reference's AtomsX with
+    its jax.random draws recorded (tests/golden/make_reference_mdx_utils_golden.py); mlff_b200.md.BAOABLangevinX fed the same
+    numbers reproduces the 30-step trajectory -- with the centre-of-mass and rotation fixes of every step, and without."""
+    g = golden('reference_mdx_utils.npz')
+    D0, K = float(g['D0']), float(g['K'])
+    stream = iter(g[f'{tag}/noise'])
+    monkeypatch.setattr(md.torch, 'randn', lambda *shape, **kw: torch.as_tensor(next(stream)))
+
+    class Springs:
+        def __call__(self, atoms):
+            if atoms.cache is None:
+                R = atoms.get_positions()
+                d = R[None, :, :] - R[:, None, :]
+                eye = torch.eye(len(R), dtype=R.dtype)
+                r = d.norm(dim=-1) + eye
+                f = K * (r - D0) / r * (1 - eye)
+                atoms.cache = {'energy': 0.25 * K * ((r - D0) ** 2 * (1 - eye)).sum(), 'forces': (f[:, :, None] * d).sum(1)}
+            return atoms.cache
+
+    class NoList:
+        def update(self, positions):
+            return self
+
+    atoms = md.AtomsX(positions=torch.as_tensor(g['baoab_R0']), momenta=torch.as_tensor(g['baoab_p0']),
+                      masses=torch.as_tensor(g['baoab_masses']), numbers=torch.ones(5, dtype=torch.int32), neighbors=NoList())
+    fix = tag == 'baoab'
+    integrator = md.BAOABLangevinX.create(float(g['baoab_dt']), float(g['baoab_temperature']), Springs(),
+                                          gamma=float(g['baoab_gamma']), fixcm=fix, fixrot=fix)
+    for k in range(len(g[f'{tag}/E'])):
+        integrator, atoms, prop = integrator.step(atoms)
+        np.testing.assert_allclose(atoms.get_positions().numpy(), g[f'{tag}/R'][k], rtol=1e-10, atol=1e-12, err_msg=str(k))
+        np.testing.assert_allclose(atoms.get_momenta().numpy(), g[f'{tag}/p'][k], rtol=1e-10, atol=1e-12, err_msg=str(k))
+        assert abs(float(prop['energy']) - g[f'{tag}/E'][k]) < 1e-10
+    if fix:
+        assert np.abs(atoms.get_angular_momentum().numpy()).max() < 1e-6      # pair forces exert no net torque
+
+
+def test_maxwell_boltzmann_distribution():
+    """mlff/mdx/distributions.py:5-20: p = xi sqrt(m T0); the sample temperature (3n degrees of freedom) approaches T0."""
+    masses = torch.full((20000,), 12.011, dtype=torch.float64)
+    T0 = 300.0 * md.KB_EV
+    p = md.maxwell_boltzmann(masses, T0, seed=3)
+    a = md.AtomsX(positions=torch.zeros(20000, 3, dtype=torch.float64), momenta=p, masses=masses,
+                  numbers=torch.full((20000,), 6, dtype=torch.int32))
+    assert abs(float(a.get_temperature(eckart_frame=False)) / T0 - 1.0) < 0.02
+    assert torch.equal(p, md.maxwell_boltzmann(masses, T0, seed=3)) and not torch.equal(p, md.maxwell_boltzmann(masses, T0, seed=4))
