@@ -151,9 +151,13 @@ class AtomsX:
 
 
 class CalculatorX:
-    """energy + forces of an AtomsX through the engine (one structure; the skin list of the atoms object)."""
+    """energy + forces (+ stress) of an AtomsX through the engine (one structure; the skin list of the atoms object).
+    implemented_properties as in mlff/mdx/calculator.py:16-52: with 'stress' the result also holds dE/d(strain) (3,3) of the
+    periodic cell -- what the reference differentiates through glp's strain_graph (edge vectors move as r -> (1 + eps) r;
+    not divided by the volume)."""
 
-    def __init__(self, engine, energy_scale: float = 1.0, cuda_graph: bool = False):
+    def __init__(self, engine, energy_scale: float = 1.0, cuda_graph: bool = False,
+                 implemented_properties: Sequence[str] = ('energy', 'forces')):
         """cuda_graph=True replays one captured graph per evaluation while the list capacity is unchanged (small,
         launch-bound systems); the engine must provide `graphed_energy_forces`."""
         self.engine = engine
@@ -161,6 +165,16 @@ class CalculatorX:
         self.n_calls = 0
         self.cuda_graph = cuda_graph
         self._graphed = None
+        self.implemented_properties = tuple(implemented_properties)
+        unknown = set(self.implemented_properties) - {'energy', 'forces', 'stress'}
+        if unknown:
+            raise NotImplementedError(f'properties {sorted(unknown)} are not implemented')
+        if 'stress' in self.implemented_properties and cuda_graph:
+            raise NotImplementedError('the stress is evaluated by a second call on the workspace: use cuda_graph=False')
+
+    @classmethod
+    def create(cls, engine, implemented_properties: Sequence[str] = ('energy', 'forces'), energy_scale: float = 1.0):
+        return cls(engine, energy_scale, False, implemented_properties)
 
     def __call__(self, atoms: AtomsX) -> Dict[str, torch.Tensor]:
         if atoms.cache is not None:
@@ -177,11 +191,17 @@ class CalculatorX:
             if self._graphed is None or self._graphed.shape != shape:
                 self._graphed = self.engine.graphed_energy_forces(*shape, periodic)
             E, F = self._graphed(*args)
+        elif 'stress' in self.implemented_properties:
+            if not periodic:
+                raise ValueError('stress needs a periodic cell')
+            E, F, _, stress = self.engine.energy_forces(*args, want_stress=True)
         else:
             E, F, _ = self.engine.energy_forces(*args)
         self.n_calls += 1
         out = {'energy': self.energy_scale * E.reshape(()).to(torch.float64),
                'forces': self.energy_scale * F[0].to(torch.float64)}
+        if 'stress' in self.implemented_properties:
+            out['stress'] = self.energy_scale * stress[0].to(torch.float64)
         atoms.cache = out
         return out
 

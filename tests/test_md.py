@@ -33,10 +33,15 @@ class OracleEngine:
         ii[:m], jj[:m], SS[:m] = torch.as_tensor(i[:m]), torch.as_tensor(j[:m]), torch.as_tensor(S[:m])
         return ii, jj, SS, torch.tensor([n])
 
-    def energy_forces(self, R, z, idx_i, idx_j, cell=None, cell_offset=None):
+    def energy_forces(self, R, z, idx_i, idx_j, cell=None, cell_offset=None, want_stress=False):
+        kw = dict(cell=None if cell is None else cell[0].double().numpy(),
+                  cell_offset=None if cell_offset is None else cell_offset[0].numpy())
+        if want_stress:
+            E, F, st = o.energy_forces_stress(self.cfg, self.params, R[0].double().numpy(), z[0].numpy(), idx_i[0].numpy(),
+                                              idx_j[0].numpy(), **kw)
+            return E.reshape(1, 1), F[None], None, st[None]
         E, F, _ = o.energy_forces(self.cfg, self.params, R[0].double().numpy(), z[0].numpy(), idx_i[0].numpy(),
-                                  idx_j[0].numpy(), cell=None if cell is None else cell[0].double().numpy(),
-                                  cell_offset=None if cell_offset is None else cell_offset[0].numpy())
+                                  idx_j[0].numpy(), **kw)
         return E.reshape(1, 1), F[None], None
 
 
@@ -495,3 +500,42 @@ def test_maxwell_boltzmann_distribution():
                   numbers=torch.full((20000,), 6, dtype=torch.int32))
     assert abs(float(a.get_temperature(eckart_frame=False)) / T0 - 1.0) < 0.02
     assert torch.equal(p, md.maxwell_boltzmann(masses, T0, seed=3)) and not torch.equal(p, md.maxwell_boltzmann(masses, T0, seed=4))
+
+
+def test_calculator_with_stress_property():
+    """CalculatorX.create(engine, implemented_properties=('energy', 'forces', 'stress')) -- mlff/mdx/calculator.py:16-52:
+    the extra entry is dE/d(strain) of the periodic cell, here checked against central differences of the calculator's own
+    energy under r -> (1 + eps) r, cell -> cell (1 + eps)^T."""
+    sol = golden('solid_0.npz')
+    cfg = o.OracleConfig(F=16, n_layers=1, degrees=(1, 2), n_heads=2)
+    p = o.init_params(cfg, 2, embed_scale=4.0)
+    eng = OracleEngine(cfg, p)
+    R, z, cell = sol['R'].astype(np.float64), sol['z'].astype(np.int32), sol['unit_cell'].astype(np.float64)
+
+    def evaluate(Rx, cx, props):
+        n = len(z)
+        atoms = md.AtomsX(positions=torch.as_tensor(Rx), momenta=torch.zeros(n, 3, dtype=torch.float64),
+                          masses=torch.ones(n, dtype=torch.float64), numbers=torch.as_tensor(z), cell=cx,
+                          pbc=(True, True, True)).init_spatial_partitioning(eng, cfg.r_cut, 0.0)
+        return md.CalculatorX.create(eng, implemented_properties=props)(atoms)
+
+    out = evaluate(R, cell, ('energy', 'forces', 'stress'))
+    assert set(out) == {'energy', 'forces', 'stress'} and out['stress'].shape == (3, 3)
+    assert set(evaluate(R, cell, ('energy', 'forces'))) == {'energy', 'forces'}
+    # the calculator hands float32 positions / cell to the engine: finite differences see that rounding, so the step is large
+    h = 2e-3
+    for a, b in ((0, 0), (1, 2), (2, 2)):
+        vals = []
+        for sgn in (1.0, -1.0):
+            eps = np.zeros((3, 3))
+            eps[a, b] += 0.5 * sgn * h
+            eps[b, a] += 0.5 * sgn * h
+            vals.append(float(evaluate(R + R @ eps.T, cell + cell @ eps.T, ('energy', 'forces'))['energy']))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        sym = 0.5 * float(out['stress'][a, b] + out['stress'][b, a])
+        assert abs(fd - sym) <= 2e-3 * max(1.0, abs(fd)), (a, b, fd, sym)
+    ii, jj, S = o.primitive_neighbor_list(R, cell, (True, True, True), cfg.r_cut)
+    _, _, st = o.energy_forces_stress(cfg, p, R, z, ii, jj, cell=cell, cell_offset=S)
+    np.testing.assert_allclose(out['stress'].numpy(), st.numpy(), rtol=1e-4, atol=1e-4 * float(st.abs().max()))
+    with pytest.raises(NotImplementedError):
+        md.CalculatorX.create(eng, implemented_properties=('energy', 'forces', 'heat_flux'))
