@@ -20,10 +20,12 @@ from .engine import So3kEngine
 
 
 class mlffCalculator:
-    implemented_properties = ('energy', 'forces')
+    implemented_properties = ('energy', 'forces', 'stress')
 
     def __init__(self, cfg: So3kratesConfig, params: Dict, energy_scale: float = 1.0, capacity_multiplier: float = 1.25,
-                 device: str = 'cuda:0', flags: int = 0):
+                 device: str = 'cuda:0', flags: int = 0, calculate_stress: bool = False):
+        """calculate_stress (mlff/md/calculator.py:61, 87-99): periodic calls also return 'stress' = dE/d(strain) (3,3),
+        the quantity the reference differentiates through glp's strain_graph (no volume factor)."""
         from . import params as _params
         self.cfg = cfg
         self.engine = So3kEngine(cfg, device, flags)
@@ -32,6 +34,7 @@ class mlffCalculator:
         self.energy_scale = float(energy_scale)
         self.capacity_multiplier = float(capacity_multiplier)
         self.cutoff = float(cfg.r_cut)
+        self.calculate_stress = bool(calculate_stress)
         self.capacity: Optional[int] = None
         self.results: Dict[str, np.ndarray] = {}
         self._pin: Dict[str, torch.Tensor] = {}
@@ -62,11 +65,17 @@ class mlffCalculator:
                                                  pbc=pbc if periodic else (False, False, False), mode=NL_ASE)
             R32 = pos64.to(torch.float32)
             cell32 = None if cell_h is None else torch.as_tensor(cell_h, dtype=torch.float32, device=dev)[None]
-            E, F, _ = eng.energy_forces(R32[None], z[None], ii[None], jj[None],
-                                        cell32, None if cell32 is None else S[None])
-            # one D2H for everything the host needs: energy, edge count, device status word, forces
-            out = torch.cat([E.reshape(-1).double(), count.double(), eng._status.double(),
-                             F.reshape(-1).double()]).cpu()
+            want_stress = self.calculate_stress and periodic
+            if want_stress:
+                E, F, _, stress = eng.energy_forces(R32[None], z[None], ii[None], jj[None], cell32, S[None], want_stress=True)
+            else:
+                E, F, _ = eng.energy_forces(R32[None], z[None], ii[None], jj[None],
+                                            cell32, None if cell32 is None else S[None])
+            # one D2H for everything the host needs: energy, edge count, device status word, forces [, stress]
+            parts = [E.reshape(-1).double(), count.double(), eng._status.double(), F.reshape(-1).double()]
+            if want_stress:
+                parts.append(stress.reshape(-1).double())
+            out = torch.cat(parts).cpu()
             eng._status.zero_()
             n_edges = int(out[1].item())
             status = int(out[2].item())
@@ -76,7 +85,9 @@ class mlffCalculator:
             self.capacity = int(np.ceil(self.capacity_multiplier * n_edges))      # overflow: re-allocate and redo
         self.n_edges = n_edges
         self.results = {'energy': float(out[0].item()) * self.energy_scale,
-                        'forces': out[3:].reshape(N, 3).numpy().astype(np.float32) * self.energy_scale}
+                        'forces': out[3:3 + 3 * N].reshape(N, 3).numpy().astype(np.float32) * self.energy_scale}
+        if want_stress:
+            self.results['stress'] = out[3 + 3 * N:].reshape(3, 3).numpy().astype(np.float32) * self.energy_scale
         return self.results
 
     def get_potential_energy(self):
@@ -84,3 +95,6 @@ class mlffCalculator:
 
     def get_forces(self):
         return self.results['forces']
+
+    def get_stress(self):
+        return self.results['stress']

@@ -366,6 +366,24 @@ def test_calculator_end_to_end(solid):
     assert np.abs(res['forces'] - g['F']).max() < F_ATOL
 
 
+def test_calculator_with_stress(solid):
+    """mlffCalculator(calculate_stress=True), mlff/md/calculator.py:87-99: energy, forces and dE/d(strain) in one call."""
+    from mlff_b200.calculator import mlffCalculator
+    g = golden('oracle_solid_pbc.npz')
+    cfg = o.OracleConfig()
+    p = o.init_params(cfg, int(g['seed']), embed_scale=float(g['embed_scale']))
+    calc = mlffCalculator(_cfgs(cfg), {k: np.asarray(v, np.float32) for k, v in p.items()}, calculate_stress=True)
+    res = calc.calculate(solid['R'], solid['z'], cell=solid['unit_cell'], pbc=(True, True, True))
+    _, _, So = o.energy_forces_stress(cfg, p, solid['R'], solid['z'], g['idx_i'], g['idx_j'], cell=solid['unit_cell'],
+                                      cell_offset=g['shifts'])
+    assert abs(res['energy'] - float(g['E'])) <= E_RTOL * abs(float(g['E']))
+    assert np.abs(res['forces'] - g['F']).max() < F_ATOL
+    assert res['stress'].shape == (3, 3)
+    assert np.abs(calc.get_stress() - So.numpy()).max() < 2e-4 * max(np.abs(So.numpy()).max(), 1.0)
+    res = calc.calculate(solid['R'], solid['z'])                      # no cell: no stress entry
+    assert 'stress' not in res
+
+
 # ---- tcgen05 operand-layout conventions ------------------------------------------------------------------------
 @pytest.mark.parametrize('N,K,variant', [(144, 32, 0), (144, 176, 0), (176, 144, 2), (256, 64, 0), (48, 144, 2),
                                          (128, 96, 5), (64, 128, 5)])

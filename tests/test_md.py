@@ -539,3 +539,45 @@ def test_calculator_with_stress_property():
     np.testing.assert_allclose(out['stress'].numpy(), st.numpy(), rtol=1e-4, atol=1e-4 * float(st.abs().max()))
     with pytest.raises(NotImplementedError):
         md.CalculatorX.create(eng, implemented_properties=('energy', 'forces', 'heat_flux'))
+
+
+def test_ase_style_calculator_glue_with_a_stand_in_engine(monkeypatch):
+    """mlffCalculator.calculate (mlff/md/calculator.py:121-147) host logic on the CPU: the single read-back is sliced into
+    energy, forces and -- with calculate_stress -- the strain derivative; overflow re-allocates; no cell, no stress entry.
+    The engine is the float64 oracle stand-in (the CUDA engine is exercised by tests/test_gpu_parity.py)."""
+    from mlff_b200 import calculator as C
+    from mlff_b200.config import So3kratesConfig
+    sol = golden('solid_0.npz')
+    cfg = o.OracleConfig(F=16, n_layers=1, degrees=(1, 2), n_heads=2)
+    p = o.init_params(cfg, 2, embed_scale=4.0)
+
+    class StandIn(OracleEngine):
+        def __init__(self, pc, device, flags):
+            super().__init__(cfg, p)
+            self.device = torch.device('cpu')
+            self._status = torch.zeros(1, dtype=torch.int32)
+
+        def load_params(self, flat):
+            pass
+
+        def raise_for_status(self, s):
+            assert s == 0
+            return 0
+
+    monkeypatch.setattr(C, 'So3kEngine', StandIn)
+    monkeypatch.setattr(C.mlffCalculator, '_pinned', lambda self, name, arr: torch.from_numpy(arr))
+    pc = So3kratesConfig(F=cfg.F, n_layer=cfg.n_layers, degrees=tuple(cfg.degrees), n_heads=cfg.n_heads)
+    R, z, cell = sol['R'].astype(np.float64), sol['z'].astype(np.int32), sol['unit_cell'].astype(np.float64)
+    ii, jj, S = o.primitive_neighbor_list(R, cell, (True, True, True), cfg.r_cut)
+    Eo, Fo, So = o.energy_forces_stress(cfg, p, R, z, ii, jj, cell=cell, cell_offset=S)
+    calc = C.mlffCalculator(pc, {'embed/embedding': None}, calculate_stress=True, energy_scale=2.0)
+    calc.capacity = 500                                              # overflow branch first
+    res = calc.calculate(R, z, cell=cell, pbc=(True, True, True))
+    assert calc.n_edges == len(ii) and calc.capacity >= len(ii)
+    assert abs(res['energy'] - 2.0 * float(Eo)) <= 1e-6 * abs(float(Eo))
+    np.testing.assert_allclose(res['forces'], 2.0 * Fo.numpy(), atol=2e-5)
+    np.testing.assert_allclose(calc.get_stress(), 2.0 * So.numpy(), rtol=1e-4, atol=1e-4 * float(So.abs().max()))
+    assert res['forces'].shape == (len(z), 3) and res['stress'].shape == (3, 3)
+    plain = C.mlffCalculator(pc, {'embed/embedding': None}).calculate(R, z, cell=cell, pbc=(True, True, True))
+    assert set(plain) == {'energy', 'forces'} and abs(plain['energy'] - float(Eo)) <= 1e-6 * abs(float(Eo))
+    assert 'stress' not in calc.calculate(R, z)                     # non-periodic call
