@@ -16,7 +16,7 @@ the same code drives the CPU-emulated build of the kernels through an engine sta
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -52,15 +52,35 @@ class Optimizer:
                               'weight_decay': self.weight_decay, 'clip_by_global_norm': self.clip_by_global_norm}}
 
 
-class TrainState:
-    """step counter + device parameter blob + Adam moments (flax TrainState stand-in).  The blob IS the engine's
-    parameter blob: apply_gradients updates it in place and re-loads it into the handle."""
+def lr_decay_exponential(step: int, transition_steps: int, decay_factor: float) -> float:
+    """mlff/training/lr_decay/lr_decay.py:1-2."""
+    return decay_factor ** (step / transition_steps)
 
-    def __init__(self, engine, tx: Optimizer):
+
+def lr_decay_on_plateau(plateau_count: int, plateau_length: int, patience: int, decay_factor: float) -> Tuple[float, int, int]:
+    """mlff/training/lr_decay/lr_decay.py:5-22: (factor of the n-th plateau, plateau length carried over, plateaus completed
+    by this length)."""
+    return decay_factor ** plateau_count, plateau_length % patience, plateau_length // patience
+
+
+class TrainState:
+    """step counter + device parameter blob + Adam moments (CustomTrainState of mlff/training/train_state.py:17-127).  The
+    blob IS the engine's parameter blob: apply_gradients updates it in place and re-loads it into the handle.
+    As in the reference the update of a step is multiplied by lr_decay_fn(step) and by the plateau factor of
+    reduce_lr_on_plateau_fn(plateau_count, plateau_length) (train_state.py:75-83; defaults: no decay), `improved(x)` feeds
+    the plateau counter (:104-110), and with polyak_step_size `valid_params` = step_size * new + (1 - step_size) * previous
+    parameters (:85-90, optax.incremental_update) -- otherwise `valid_params` is `params`."""
+
+    def __init__(self, engine, tx: Optimizer, lr_decay_fn: Optional[Callable] = None,
+                 reduce_lr_on_plateau_fn: Optional[Callable] = None, polyak_step_size: Optional[float] = None):
         if engine._blob is None:
             raise RuntimeError('load parameters into the engine before creating a TrainState')
         self.engine, self.tx, self.step = engine, tx, 0
+        self.lr_decay_fn, self.reduce_lr_on_plateau_fn = lr_decay_fn, reduce_lr_on_plateau_fn
+        self.polyak_step_size = polyak_step_size
+        self.plateau_length, self.plateau_count = 0, 0
         self.params = engine._blob
+        self.valid_params = self.params if polyak_step_size is None else self.params.clone()
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         lib, h = engine.lib, engine.h
@@ -79,18 +99,39 @@ class TrainState:
         self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=engine.device)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=engine.device)      # the update count, device resident
 
+    @property
+    def scheduled(self) -> bool:
+        """True when a step depends on host-side schedule state (such a step cannot be replayed from a captured graph)."""
+        return self.lr_decay_fn is not None or self.reduce_lr_on_plateau_fn is not None or self.polyak_step_size is not None
+
+    def improved(self, x: bool) -> 'TrainState':
+        """train_state.py:104-110: an epoch without improvement lengthens the current plateau."""
+        self.plateau_length = 0 if x else self.plateau_length + 1
+        return self
+
     def apply_gradients(self, grads: torch.Tensor) -> 'TrainState':
         """One optimiser update in place + re-load into the handle.  The update count lives on the device (incremented by
         the call), so the same enqueued work can be replayed from a CUDA graph; `self.step` mirrors it on the host."""
         e, tx = self.engine, self.tx
+        factor = 1.0
+        if self.reduce_lr_on_plateau_fn is not None:
+            cd, self.plateau_length, inc = self.reduce_lr_on_plateau_fn(plateau_count=self.plateau_count,
+                                                                        plateau_length=self.plateau_length)
+            self.plateau_count += int(inc)
+            factor *= float(cd)
+        if self.lr_decay_fn is not None:
+            factor *= float(self.lr_decay_fn(self.step))         # the counter BEFORE this update, as in the reference
+        previous = self.params.clone() if self.polyak_step_size is not None else None
         self.step += 1
         wd = 0.0 if tx.weight_decay is None else tx.weight_decay
         clip = 0.0 if tx.clip_by_global_norm is None else tx.clip_by_global_norm
         e.lib.adam_step(self.params.numel(), _p(self.params), _p(grads), _p(self.m), _p(self.v), _p(self.frozen),
-                        _p(self.decay_mask) if tx.weight_decay is not None else None, self.step, tx.learning_rate,
+                        _p(self.decay_mask) if tx.weight_decay is not None else None, self.step, tx.learning_rate * factor,
                         tx.b1, tx.b2, tx.eps, tx.eps_root, wd, clip, _p(self.grad_sumsq), e._stream(),
                         step_dev=_p(self.step_dev))
         e.lib.load_params(e.h, _p(self.params), self.params.numel(), e._stream())
+        if previous is not None:
+            torch.lerp(previous, self.params, float(self.polyak_step_size), out=self.valid_params)
         return self
 
 
@@ -106,10 +147,12 @@ class Trainer:
     scalars of get_loss_fn (loss.py:42-48; the CLI's variance scaling 1 / nanvar(target), mlff_train_so3krates.py:330-342):
     the loss term of a target is weight * scale * MSE while the reported metric stays the plain MSE (`_l / scale`).
     ``group``: a torch.distributed process group (or True for the default group) for data-parallel training; None =
-    single process."""
+    single process.  ``lr_decay_fn`` / ``reduce_lr_on_plateau_fn`` / ``polyak_step_size``: the schedule hooks of the
+    reference's train state (see TrainState)."""
 
     def __init__(self, engine, weights: Dict[str, float], tx: Optional[Optimizer] = None, group=None,
-                 scales: Optional[Dict[str, float]] = None):
+                 scales: Optional[Dict[str, float]] = None, lr_decay_fn: Optional[Callable] = None,
+                 reduce_lr_on_plateau_fn: Optional[Callable] = None, polyak_step_size: Optional[float] = None):
         self.engine = engine
         scales = scales or {}
         unknown = (set(weights) | set(scales)) - {'energy', 'force', 'stress'}
@@ -118,7 +161,7 @@ class Trainer:
         self.w_E = float(weights.get('energy', 0.0)) * float(scales.get('energy', 1.0))
         self.w_F = float(weights.get('force', 0.0)) * float(scales.get('force', 1.0))
         self.w_S = float(weights.get('stress', 0.0)) * float(scales.get('stress', 1.0)) if 'stress' in weights else None
-        self.state = TrainState(engine, tx) if tx is not None else None
+        self.state = TrainState(engine, tx, lr_decay_fn, reduce_lr_on_plateau_fn, polyak_step_size) if tx is not None else None
         self.group = group
         dev = engine.device
         self._sums = torch.zeros(6, dtype=torch.float64, device=dev)       # E: sum sq, n ; F: sum sq, n ; stress: sum sq, n
@@ -231,6 +274,9 @@ class Trainer:
         if cuda_graph:
             if S_true is not None:
                 raise NotImplementedError('cuda_graph=True with a stress target')
+            if self.state.scheduled:
+                raise NotImplementedError('cuda_graph=True with a learning-rate schedule or Polyak averaging: the step '
+                                          'size is a host value of the captured launch')
             return self._train_step_graphed(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset)
         loss, grad, _, _ = self.loss_and_grad(R, z, idx_i, idx_j, E_true, F_true, cell, cell_offset, S_true)
         self.state.apply_gradients(grad)

@@ -422,3 +422,48 @@ def test_data_parallel_training_over_gloo_world_size_2():
     assert np.abs(g_dp - g1).max() <= 2e-5 * np.abs(g1).max()
     tr.train_step(*args)
     np.testing.assert_allclose(blob_dp, eng._blob.numpy(), rtol=0, atol=2e-5)
+
+
+def test_train_state_schedules_and_polyak_average():
+    """CustomTrainState.apply_gradients (mlff/training/train_state.py:59-101): the update of a step is scaled by
+    lr_decay_fn(step) (the counter before the update) and by the plateau factor, `improved` feeds the plateau counter, and
+    valid_params = step_size * new + (1 - step_size) * previous parameters -- against a numpy restatement of the chain."""
+    from functools import partial
+    from mlff_b200.training import TrainState, Optimizer, lr_decay_exponential, lr_decay_on_plateau
+    cfg, p, *_ = _trainer_problem()
+    eng = EmuTorchEngine(cfg, p)
+    n = eng._blob.numel()
+    lr, ss = 1e-2, 0.3
+    tx = Optimizer().get(learning_rate=lr)
+    st = TrainState(eng, tx, lr_decay_fn=partial(lr_decay_exponential, transition_steps=2, decay_factor=0.5),
+                    reduce_lr_on_plateau_fn=partial(lr_decay_on_plateau, patience=2, decay_factor=0.1), polyak_step_size=ss)
+    assert st.scheduled
+    frozen = st.frozen.numpy().astype(bool)
+    rng = np.random.default_rng(0)
+    rp = eng._blob.numpy().astype(np.float64).copy()
+    rm, rv = np.zeros(n), np.zeros(n)
+    b1, b2, eps = tx.b1, tx.b2, tx.eps
+    plateau_length, plateau_count = 0, 0
+    improved = [True, False, False, False, True]                 # the plateau of two bad epochs completes before step 4
+    for k, imp in enumerate(improved):
+        g = (rng.normal(size=n) * 0.1).astype(np.float32)
+        cd, plateau_length, inc = lr_decay_on_plateau(plateau_count, plateau_length, patience=2, decay_factor=0.1)
+        plateau_count += inc
+        factor = cd * 0.5 ** (k / 2)
+        old = rp.copy()
+        gd = g.astype(np.float64)
+        rm = b1 * rm + (1 - b1) * gd
+        rv = b2 * rv + (1 - b2) * gd ** 2
+        u = (rm / (1 - b1 ** (k + 1))) / (np.sqrt(rv / (1 - b2 ** (k + 1))) + eps)
+        rp = np.where(frozen, rp, rp - lr * factor * u)
+        st.apply_gradients(torch.from_numpy(g))
+        np.testing.assert_allclose(st.params.numpy(), rp, rtol=3e-5, atol=3e-6, err_msg=str(k))
+        np.testing.assert_allclose(st.valid_params.numpy(), ss * rp + (1 - ss) * old, rtol=3e-5, atol=3e-6, err_msg=str(k))
+        assert (st.plateau_length, st.plateau_count) == (plateau_length, plateau_count)
+        st.improved(imp)
+        plateau_length = 0 if imp else plateau_length + 1
+    assert plateau_count == 1 and st.step == len(improved)
+    # defaults: no schedule, valid_params IS params
+    st0 = TrainState(eng, tx)
+    assert not st0.scheduled and st0.valid_params is st0.params
+    assert lr_decay_exponential(4, 2, 0.5) == 0.25 and lr_decay_on_plateau(2, 5, 2, 0.1) == (0.1 ** 2, 1, 2)
