@@ -21,6 +21,9 @@ def __getattr__(name):
     if name in ('Trainer', 'TrainState', 'Optimizer'):
         from . import training
         return getattr(training, name)
+    if name in ('evaluate_model', 'mae_metric', 'mse_metric', 'rmse_metric', 'r2_metric'):
+        from . import inference
+        return getattr(inference, name)
     if name == 'So3kEngine':
         from . import engine
         return engine.So3kEngine
