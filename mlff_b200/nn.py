@@ -115,7 +115,7 @@ def _to_dev(a, dev, dtype):
     return torch.as_tensor(np.asarray(a)).to(dev, dtype)
 
 
-def _run(net: StackNet, params, inputs, want_forces: bool) -> Dict:
+def _run(net: StackNet, params, inputs, want_forces: bool, want_stress: bool = False) -> Dict:
     pk = net.prop_keys
     eng = net.engine(params)
     dev = eng.device
@@ -135,7 +135,14 @@ def _run(net: StackNet, params, inputs, want_forces: bool) -> Dict:
         R, z, ii, jj = R[None], z[None], ii[None], jj[None]
         if cell is not None:
             cell, off = cell[None], off[None]
-    E, F, ea = eng.energy_forces(R, z, ii, jj, cell, off, want_e_atom=(net.output_convention == 'per_atom'))
+    stress = None
+    if want_stress:
+        if cell is None:
+            raise ValueError('the stress needs `unit_cell` and `cell_offset` in the inputs')
+        E, F, ea, stress = eng.energy_forces(R, z, ii, jj, cell, off, want_e_atom=(net.output_convention == 'per_atom'),
+                                             want_stress=True)
+    else:
+        E, F, ea = eng.energy_forces(R, z, ii, jj, cell, off, want_e_atom=(net.output_convention == 'per_atom'))
     out = {}
     if net.output_convention == 'per_atom':
         out[pk.get('atomic_energy', pk['energy'])] = ea[..., None]
@@ -143,6 +150,8 @@ def _run(net: StackNet, params, inputs, want_forces: bool) -> Dict:
         out[pk['energy']] = E
     if want_forces:
         out[pk['force']] = F
+    if stress is not None:
+        out[pk['stress']] = stress
     if single:
         out = {k: v[0] for k, v in out.items()}
     if as_numpy:
@@ -163,3 +172,13 @@ def get_obs_and_force_fn(net: StackNet) -> Callable:
     def obs_and_force_fn(p, x):
         return _run(net, p, x, want_forces=True)
     return obs_and_force_fn
+
+
+def get_energy_force_stress_fn(net: StackNet) -> Callable:
+    """E, F and the stress = dE/d(strain) in one call -- mlff/nn/stacknet/observable_function.py:152-186, where positions
+    and cell are strained by the symmetrised eps and `jax.value_and_grad` differentiates with respect to both; here
+    `so3k_stress` contracts the edge cotangents of the same analytic backward (no volume factor, as in the reference).
+    The inputs need `unit_cell` and `cell_offset`; batched inputs give one (3,3) tensor per structure."""
+    def energy_force_stress_fn(p, x):
+        return _run(net, p, x, want_forces=True, want_stress=True)
+    return energy_force_stress_fn
