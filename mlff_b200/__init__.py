@@ -10,7 +10,7 @@ __version__ = '0.1.0'
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import mlff_b200` stays cheap
     if name in ('So3krates', 'StackNet', 'init_stack_net', 'get_obs_and_force_fn', 'get_observable_fn',
-                'get_energy_force_stress_fn'):
+                'get_energy_force_stress_fn', 'get_grad_observable_fn', 'get_obs_and_grad_obs_fn'):
         from . import nn
         return getattr(nn, name)
     if name in ('MLFFPotential', 'Graph'):

@@ -182,3 +182,36 @@ def get_energy_force_stress_fn(net: StackNet) -> Callable:
     def energy_force_stress_fn(p, x):
         return _run(net, p, x, want_forces=True, want_stress=True)
     return energy_force_stress_fn
+
+
+def get_grad_observable_fn(net: StackNet, derivatives) -> Callable:
+    """Gradients of observables with respect to inputs, requested as in the reference (observable_function.py:41-95):
+    each entry is `(name, (observable key, input key, op))` and the result holds `name: op(d observable / d input)`, the
+    raw gradient of the (1,)-shaped energy carrying the reference's extra leading axis -- (1, n, 3) per structure -- so
+    that the usual `('F', ('E', 'R', lambda y: -y.squeeze(-3)))` works unchanged.  The hot path provides exactly one
+    derivative, dE/dR (the analytic force backward); anything else raises NotImplementedError."""
+    pk = net.prop_keys
+    for _, (obs, inp, _) in derivatives:
+        if obs != pk['energy'] or inp != pk['atomic_position']:
+            raise NotImplementedError(f'd {obs} / d {inp}: only d {pk["energy"]} / d {pk["atomic_position"]} is on the hot path')
+
+    def all_grad_obs_fn(p, x):
+        F = _run(net, p, x, want_forces=True)[pk['force']]
+        dE_dR = -F
+        lead = dE_dR[None] if dE_dR.ndim == 2 else dE_dR[:, None]         # (1, n, 3), or (B, 1, n, 3) for a batch
+        return {name: op(lead) for name, (_, _, op) in derivatives}
+    return all_grad_obs_fn
+
+
+def get_obs_and_grad_obs_fn(net: StackNet, derivatives=None) -> Callable:
+    """Observables and the requested gradients in one dict (observable_function.py:98-124)."""
+    obs_fn = get_observable_fn(net)
+    if derivatives is None:
+        return obs_fn
+    grad_fn = get_grad_observable_fn(net, derivatives)
+
+    def obs_and_grad_fn(p, x):
+        out = obs_fn(p, x)
+        out.update(grad_fn(p, x))
+        return out
+    return obs_and_grad_fn

@@ -63,3 +63,30 @@ def test_energy_force_stress_fn_keys_shapes_and_values():
     # renamed property keys travel through (reset_prop_keys of the reference's StackNet)
     net.reset_prop_keys({'stress': 'virial_like', 'energy': 'U'})
     assert set(nn.get_energy_force_stress_fn(net)(None, x)) == {'U', 'F', 'virial_like'}
+
+
+def test_obs_and_grad_obs_fn_with_the_reference_derivative_spec():
+    """get_obs_and_grad_obs_fn(net, derivatives) as the reference's training CLI calls it: the force as the negative
+    gradient of the energy with respect to the positions, `lambda y: -y.squeeze(-3)` on the (1, n, 3) gradient."""
+    g = golden('ethanol_32.npz')
+    cfg = o.OracleConfig(F=16, n_layers=1, degrees=(1, 2), n_heads=2)
+    p = o.init_params(cfg, 2, embed_scale=4.0)
+    R, z = g['R'][:2].astype(np.float64), np.tile(g['z'][None], (2, 1)).astype(np.int32)
+    nl = o.get_indices(R, z, cfg.r_cut)
+    net = _net(cfg, p)
+    D_force = ('F', ('E', 'R', lambda y: -y.squeeze(-3)))
+    fn = nn.get_obs_and_grad_obs_fn(net, derivatives=(D_force,))
+    x1 = {'R': R[0], 'z': z[0], 'idx_i': nl['idx_i'][0], 'idx_j': nl['idx_j'][0]}
+    out = fn(None, x1)
+    Eo, Fo, _ = o.energy_forces(cfg, p, R[0], z[0], nl['idx_i'][0], nl['idx_j'][0])
+    assert set(out) == {'E', 'F'} and out['F'].shape == (9, 3)
+    np.testing.assert_allclose(out['F'], Fo.numpy(), atol=1e-4)
+    assert abs(out['E'][0] - float(Eo)) <= 1e-5 * abs(float(Eo))
+    raw = nn.get_grad_observable_fn(net, (('dE_dR', ('E', 'R', lambda y: y)),))(None, x1)['dE_dR']
+    assert raw.shape == (1, 9, 3) and np.allclose(raw[0], -out['F'])
+    xb = {'R': R, 'z': z, 'idx_i': nl['idx_i'], 'idx_j': nl['idx_j']}
+    outb = fn(None, xb)                                              # batched: (B, 1, n, 3) -> squeeze(-3) -> (B, n, 3)
+    assert outb['F'].shape == (2, 9, 3) and np.allclose(outb['F'][0], out['F'], atol=1e-6)
+    assert nn.get_obs_and_grad_obs_fn(net)(None, x1).keys() == {'E'}
+    with pytest.raises(NotImplementedError):
+        nn.get_grad_observable_fn(net, (('q', ('E', 'z', lambda y: y)),))
