@@ -1,6 +1,6 @@
 """Golden values from the reference's own mlff/data/preprocessing.py (get_per_atom_shift :11-51, with scikit-learn's
 DictVectorizer as shipped) and mlff/data/data.py (DataTuple), executed unmodified from /root/reference.
-tests/test_data_helpers.py replays the same inputs through mlff_b200.data.
+tests/test_data_helpers.py replays the same inputs through mlff_b200.dataprep.
 
     python tests/golden/make_reference_data_golden.py               (build container only; needs /root/reference)
 """

@@ -1,4 +1,4 @@
-"""mlff_b200.data (DataTuple, get_per_atom_shift) against values recorded from the reference's own source
+"""mlff_b200.dataprep (DataTuple, get_per_atom_shift) against values recorded from the reference's own source
 (tests/golden/make_reference_data_golden.py)."""
 import importlib.util
 import os
@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 from conftest import golden
-from mlff_b200 import data as D
+from mlff_b200 import dataprep as D
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
