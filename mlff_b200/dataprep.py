@@ -8,7 +8,6 @@ Host-side numpy; the data-set class with its splitting / scaling bookkeeping (ml
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
 from typing import Any, Dict, Optional, Sequence, Tuple
 
 import numpy as np
@@ -16,21 +15,26 @@ import numpy as np
 Array = Any
 
 
-@dataclass
 class DataTuple:
     """`DataTuple(inputs, targets, prop_keys)(ds)` -> ({input key: array}, {target key: array}); the names in `inputs` /
-    `targets` are property names (e.g. 'atomic_position', 'energy'), `prop_keys` maps them to the keys of the data set."""
-    inputs: Sequence[str]
-    targets: Sequence[str]
-    prop_keys: Dict[str, str]
+    `targets` are property names (e.g. 'atomic_position', 'energy'), `prop_keys` maps them to the keys of the data set.
+    Keys of `ds` that belong to neither side are dropped; a requested key that `ds` lacks is simply absent from the result
+    (the reference filters the same way)."""
 
-    def __post_init__(self):
-        self.input_keys = [self.prop_keys[i] for i in self.inputs]
-        self.target_keys = [self.prop_keys[t] for t in self.targets]
+    def __init__(self, inputs: Sequence[str], targets: Sequence[str], prop_keys: Dict[str, str]):
+        self.inputs, self.targets, self.prop_keys = list(inputs), list(targets), dict(prop_keys)
+        self.input_keys = [prop_keys[name] for name in self.inputs]
+        self.target_keys = [prop_keys[name] for name in self.targets]
+
+    def _subset(self, ds: Dict[str, Array], wanted) -> Dict[str, Array]:
+        wanted = set(wanted)
+        return {key: ds[key] for key in ds if key in wanted}
 
     def __call__(self, ds: Dict[str, Array]) -> Tuple[Dict[str, Array], Dict[str, Array]]:
-        pick = lambda keys: {k: v for k, v in ds.items() if k in keys}
-        return pick(self.input_keys), pick(self.target_keys)
+        return self._subset(ds, self.input_keys), self._subset(ds, self.target_keys)
+
+    def __repr__(self):
+        return f'DataTuple(inputs={self.inputs}, targets={self.targets})'
 
 
 def get_per_atom_shift(z: Array, q: Array, pad_value: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
