@@ -23,7 +23,8 @@ class mlffCalculator:
     implemented_properties = ('energy', 'forces', 'stress')
 
     def __init__(self, cfg: So3kratesConfig, params: Dict, energy_scale: float = 1.0, capacity_multiplier: float = 1.25,
-                 device: str = 'cuda:0', flags: int = 0, calculate_stress: bool = False):
+                 device: str = 'cuda:0', flags: int = 0, calculate_stress: bool = False,
+                 per_atom_shift: Optional[np.ndarray] = None):
         """calculate_stress (mlff/md/calculator.py:61, 87-99): periodic calls also return 'stress' = dE/d(strain) (3,3),
         the quantity the reference differentiates through glp's strain_graph (no volume factor)."""
         from . import params as _params
@@ -35,9 +36,31 @@ class mlffCalculator:
         self.capacity_multiplier = float(capacity_multiplier)
         self.cutoff = float(cfg.r_cut)
         self.calculate_stress = bool(calculate_stress)
+        # add_energy_shift of create_from_ckpt_dir: energy += sum over atoms of per_atom_shift[z] (NOT scaled, mlff_potential.py:95-103)
+        self.per_atom_shift = None if per_atom_shift is None else np.asarray(per_atom_shift, dtype=np.float64).reshape(-1)
         self.capacity: Optional[int] = None
         self.results: Dict[str, np.ndarray] = {}
         self._pin: Dict[str, torch.Tensor] = {}
+
+    @classmethod
+    def create_from_ckpt_dir(cls, ckpt_dir: str, calculate_stress: bool = False, E_to_eV: float = 1., F_to_eV_Ang: float = 1.,
+                             capacity_multiplier: float = 1.25, add_energy_shift: bool = False, dtype=np.float64,
+                             device: str = 'cuda:0', flags: int = 0) -> 'mlffCalculator':
+        """mlff/md/calculator.py:31-52: hyperparameters.json + scales.json + the parameters of the checkpoint directory
+        (mlff_b200.io).  `E_to_eV` / `F_to_eV_Ang` are accepted and, as in the reference (which only logs a reminder about
+        them, :80-85), not applied; `dtype` is the reference's host dtype of the results (the device arithmetic is fp32)."""
+        import json
+        import os
+        from .io import load_params_from_ckpt_dir
+        with open(os.path.join(ckpt_dir, 'hyperparameters.json')) as f:
+            cfg = So3kratesConfig.from_hyperparameters(json.load(f))
+        with open(os.path.join(ckpt_dir, 'scales.json')) as f:
+            scales = json.load(f)
+        shift = scales['energy'].get('per_atom_shift') if add_energy_shift else None
+        return cls(cfg, load_params_from_ckpt_dir(ckpt_dir, cfg),
+                   energy_scale=float(np.asarray(scales['energy']['scale']).reshape(-1)[0]),
+                   capacity_multiplier=capacity_multiplier, device=device, flags=flags, calculate_stress=calculate_stress,
+                   per_atom_shift=shift)
 
     def _pinned(self, name: str, arr: np.ndarray) -> torch.Tensor:
         t = self._pin.get(name)
@@ -84,7 +107,8 @@ class mlffCalculator:
                 break
             self.capacity = int(np.ceil(self.capacity_multiplier * n_edges))      # overflow: re-allocate and redo
         self.n_edges = n_edges
-        self.results = {'energy': float(out[0].item()) * self.energy_scale,
+        e_shift = 0.0 if self.per_atom_shift is None else float(self.per_atom_shift[np.asarray(numbers, dtype=np.int64)].sum())
+        self.results = {'energy': float(out[0].item()) * self.energy_scale + e_shift,
                         'forces': out[3:3 + 3 * N].reshape(N, 3).numpy().astype(np.float32) * self.energy_scale}
         if want_stress:
             self.results['stress'] = out[3 + 3 * N:].reshape(3, 3).numpy().astype(np.float32) * self.energy_scale
