@@ -10,7 +10,7 @@
 #            are torch's OpenMP workers -- libgomp is not instrumented -- are not about the kernels; the script counts the
 #            reports that have an emulated-kernel frame on BOTH sides.)
 #   sh tests/emu/sanitizer_check.sh address     (about 12 minutes; last run on the final sources: 69 passed, no reports)
-#   sh tests/emu/sanitizer_check.sh thread      (about 12 minutes; last run: 68 passed, no kernel-vs-kernel race)
+#   sh tests/emu/sanitizer_check.sh thread      (about 17 minutes; last run: 68 passed, no kernel-vs-kernel race)
 set -e
 SAN=${1:-address}
 cd "$(dirname "$0")/../.."
