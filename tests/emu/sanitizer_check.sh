@@ -9,8 +9,10 @@
 #            shared or global word without one of those in between is reported as a data race.  (Reports whose two stacks
 #            are torch's OpenMP workers -- libgomp is not instrumented -- are not about the kernels; the script counts the
 #            reports that have an emulated-kernel frame on BOTH sides.)
+#   undefined: misaligned vector loads / stores (the reinterpret_cast<float4*> accesses), signed overflow, bad shifts.
 #   sh tests/emu/sanitizer_check.sh address     (about 12 minutes; last run on the final sources: 69 passed, no reports)
 #   sh tests/emu/sanitizer_check.sh thread      (about 17 minutes; last run: 68 passed, no kernel-vs-kernel race)
+#   sh tests/emu/sanitizer_check.sh undefined   (about 5 minutes; last run: 68 passed, no reports)
 set -e
 SAN=${1:-address}
 cd "$(dirname "$0")/../.."
@@ -19,7 +21,7 @@ SRC="so3k_api.cu so3k_graph.cu so3k_feat.cu so3k_node.cu so3k_agg.cu so3k_edge.c
 FILES=""
 for f in $SRC; do [ -f mlff_b200/csrc/$f ] && FILES="$FILES mlff_b200/csrc/$f"; done
 SO=tests/emu/_build/libso3k_emu_$SAN.so
-g++ -std=c++20 -O1 -g -fsanitize=$SAN -fno-omit-frame-pointer -DSO3K_EMU -Itests/emu -Imlff_b200/csrc -shared -fPIC -pthread \
+g++ -std=c++20 -O1 -g -fsanitize=$SAN -fno-sanitize=vptr -fno-omit-frame-pointer -DSO3K_EMU -Itests/emu -Imlff_b200/csrc -shared -fPIC -pthread \
     -x c++ $FILES -o $SO
 cat > tests/emu/_build/san_run.py <<'PY'
 import os, sys
@@ -34,7 +36,12 @@ import pytest
 sys.exit(pytest.main(['-x', '-q', '-p', 'no:cacheprovider'] + sys.argv[1:]))
 PY
 SUITES="tests/test_emu_parity.py tests/test_loss_kernels.py tests/test_training.py tests/test_dd.py"
-if [ "$SAN" = address ]; then
+if [ "$SAN" = undefined ]; then
+  rm -f tests/emu/_build/ubsan_log*
+  SO3K_SAN_SO=$SO LD_PRELOAD=$(gcc -print-file-name=libubsan.so) UBSAN_OPTIONS=print_stacktrace=1:log_path=tests/emu/_build/ubsan_log \
+      python tests/emu/_build/san_run.py $SUITES -k "not gloo and not trainer_step"
+  echo "undefined-behaviour reports: $(cat tests/emu/_build/ubsan_log* 2>/dev/null | grep -c 'runtime error')"
+elif [ "$SAN" = address ]; then
   SO3K_SAN_SO=$SO LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
       python tests/emu/_build/san_run.py $SUITES -k "not gloo"
 else
